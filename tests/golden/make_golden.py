@@ -1,0 +1,320 @@
+#!/usr/bin/env python
+"""Generate the golden fixtures in this directory by running the UNMODIFIED reference.
+
+Run in the build container (needs /root/reference mounted):
+
+    python tests/golden/make_golden.py
+
+What is executed is the reference's own code, imported from /root/reference/src
+(only ``ftfy`` is stubbed, it is not used on this path):
+
+  * ``open_clip.loss.ClipLoss`` forward + autograd backward, world_size 1
+      -> clip_w1_*.npz
+  * ``open_clip.loss.ClipLoss`` with world_size 2 and 4 on real gloo process groups,
+    all four (local_loss, gather_with_grad) combinations
+      -> clip_dist_w{2,4}.npz
+  * ``training.train.compute_text_weights``
+      -> text_margins.npz
+  * one/two full iterations of ``training.train.train_one_epoch_v2`` (the inline
+    prototype / pseudo-label / mixture / EMA / bank-update code, train.py:384-530)
+    driven through mock model / data / optimizer objects that only supply feature
+    tables, so every arithmetic statement on the hot path is the reference's
+      -> proto_step_*.npz
+
+The fixtures hold both the inputs and the reference outputs, so tests never need the
+reference at run time (it does not exist on the GPU box).
+"""
+
+import math
+import os
+import sys
+import types
+from types import SimpleNamespace
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF_SRC = "/root/reference/src"
+
+
+def load_reference():
+    if not os.path.isdir(REF_SRC):
+        raise SystemExit("reference not mounted at /root/reference")
+    sys.modules.setdefault("ftfy", types.ModuleType("ftfy"))
+    if REF_SRC not in sys.path:
+        sys.path.insert(0, REF_SRC)
+    import open_clip  # noqa
+    import training.train as tt  # noqa
+    return open_clip, tt
+
+
+def synth_pairs(n, d, sigma, seed, dtype=torch.float32):
+    g = torch.Generator().manual_seed(seed)
+    i = F.normalize(torch.randn(n, d, generator=g), dim=1)
+    # sigma is in units of the feature norm: sigma=1 -> cos(I_i, T_i) ~ 0.7
+    t = F.normalize(i + sigma * torch.randn(n, d, generator=g) / math.sqrt(d), dim=1)
+    return i.to(dtype), t.to(dtype)
+
+
+# ----------------------------------------------------------------------------------
+# 1. ClipLoss, world_size == 1
+# ----------------------------------------------------------------------------------
+def gen_clip_w1(open_clip):
+    cases = [
+        # name, N, D, sigma, scale, text_norm_jitter
+        ("small_s100", 96, 64, 3.0, 100.0, 0.0),
+        ("small_s14", 96, 64, 2.0, 1.0 / 0.07, 0.0),
+        ("ragged_s100", 77, 48, 1.5, 100.0, 0.01),   # N, D not multiples of a tile
+        ("cfg1_s100", 256, 512, 4.0, 100.0, 0.005),  # BASELINE config 1 shape, non-unit text
+    ]
+    for k, (name, n, d, sigma, scale, jitter) in enumerate(cases):
+        i, t = synth_pairs(n, d, sigma, 1234 + k)
+        if jitter:
+            g = torch.Generator().manual_seed(99 + k)
+            t = t * (1.0 - jitter * torch.rand(n, 1, generator=g))   # |T| ~ 0.995
+        out = {}
+        for tag, dt in (("f32", torch.float32), ("f64", torch.float64)):
+            il = i.to(dt).clone().requires_grad_(True)
+            tl = t.to(dt).clone().requires_grad_(True)
+            log_s = torch.tensor(math.log(scale), dtype=dt, requires_grad=True)
+            s = log_s.exp()
+            s.retain_grad()
+            loss_mod = open_clip.ClipLoss(cache_labels=True)
+            res = loss_mod(il, tl, s, output_dict=True)
+            assert list(res.keys()) == ["contrastive_loss"]
+            res["contrastive_loss"].backward()
+            out[f"loss_{tag}"] = res["contrastive_loss"].detach().numpy()
+            # grads are stored in float32 to keep the fixtures small (loss/ds stay f64)
+            out[f"dI_{tag}"] = il.grad.numpy().astype(np.float32)
+            out[f"dT_{tag}"] = tl.grad.numpy().astype(np.float32)
+            out[f"ds_{tag}"] = s.grad.numpy()
+        np.savez_compressed(os.path.join(HERE, f"clip_w1_{name}.npz"),
+                            I=i.numpy(), T=t.numpy(), scale=np.float64(scale), **out)
+        print("clip_w1", name, float(out["loss_f64"]))
+
+
+# ----------------------------------------------------------------------------------
+# 2. ClipLoss on real gloo process groups
+# ----------------------------------------------------------------------------------
+def _dist_worker(rank, world, port, i_all, t_all, scale, ret):
+    import torch.distributed as dist
+    sys.modules.setdefault("ftfy", types.ModuleType("ftfy"))
+    sys.path.insert(0, REF_SRC)
+    import open_clip
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    n = i_all.shape[0] // world
+    res = {}
+    for local_loss in (False, True):
+        for gwg in (False, True):
+            il = i_all[rank * n:(rank + 1) * n].clone().requires_grad_(True)
+            tl = t_all[rank * n:(rank + 1) * n].clone().requires_grad_(True)
+            s = torch.tensor(scale, dtype=i_all.dtype, requires_grad=True)
+            mod = open_clip.ClipLoss(local_loss=local_loss, gather_with_grad=gwg,
+                                     cache_labels=True, rank=rank, world_size=world)
+            loss = mod(il, tl, s)
+            loss.backward()
+            key = f"ll{int(local_loss)}_gwg{int(gwg)}"
+            res[key] = dict(loss=loss.detach().numpy(), dI=il.grad.numpy(),
+                            dT=tl.grad.numpy(), ds=s.grad.numpy())
+    ret[rank] = res
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def gen_clip_dist():
+    import torch.multiprocessing as mp
+    for world, port in ((2, 29611), (4, 29613)):
+        n_glob, d, scale = 64, 32, 100.0
+        i, t = synth_pairs(n_glob, d, 1.5, 4321 + world, torch.float64)
+        mgr = mp.Manager()
+        ret = mgr.dict()
+        mp.spawn(_dist_worker, args=(world, port, i, t, scale, ret), nprocs=world, join=True)
+        out = {"I": i.numpy(), "T": t.numpy(), "scale": np.float64(scale), "world": np.int64(world)}
+        for r in range(world):
+            for key, v in ret[r].items():
+                for nm, arr in v.items():
+                    out[f"{key}_r{r}_{nm}"] = arr
+        np.savez_compressed(os.path.join(HERE, f"clip_dist_w{world}.npz"), **out)
+        print("clip_dist", world, float(ret[0]["ll1_gwg1"]["loss"]))
+
+
+# ----------------------------------------------------------------------------------
+# 3. compute_text_weights
+# ----------------------------------------------------------------------------------
+def gen_text_margins(tt):
+    g = torch.Generator().manual_seed(777)
+    protos = F.normalize(torch.randn(47, 512, generator=g), dim=1) * 0.997
+    x = F.normalize(protos[torch.randint(0, 47, (300,), generator=g)]
+                    + 0.6 * torch.randn(300, 512, generator=g) / math.sqrt(512) * 4, dim=1)
+    preds = torch.randint(0, 47, (300,), generator=g)
+    m32 = tt.compute_text_weights(x, protos, preds)
+    m64 = tt.compute_text_weights(x.double(), protos.double(), preds)
+    np.savez_compressed(os.path.join(HERE, "text_margins.npz"), X=x.numpy(), P=protos.numpy(),
+                        margin_f32=m32.numpy(), margin_f64=m64.numpy())
+    print("text_margins", float(m64.mean()))
+
+
+# ----------------------------------------------------------------------------------
+# 4. train_one_epoch_v2 through mocks
+# ----------------------------------------------------------------------------------
+class _TableModel(nn.Module):
+    """Supplies feature tables where the reference expects towers.  Everything the
+    reference does to those features is the reference's own code."""
+
+    def __init__(self, img, cls_text, pimg, pgrp, bank, class_names, log_scale):
+        super().__init__()
+        self.img = nn.Parameter(img.clone())            # [nb, B, D]
+        self.cls_text = nn.Parameter(cls_text.clone())  # [C, D]
+        self.pimg = nn.Parameter(pimg.clone())          # [nb, B, D]
+        self.pgrp = nn.Parameter(pgrp.clone())          # [nb, B, D]
+        self.logit_scale = nn.Parameter(torch.tensor(log_scale, dtype=img.dtype))
+        self.memory_bank = nn.ParameterDict(
+            {c: nn.Parameter(bank[k].clone()) for k, c in enumerate(class_names)})
+        self.class_names = class_names
+        self.batch = 0
+
+    def tokenizer(self, texts):
+        ids = [self.class_names.index(t.split("::")[1]) for t in texts]
+        tok = torch.zeros(len(ids), 2, dtype=torch.long)
+        tok[:, 0] = torch.tensor(ids)
+        tok[:, 1] = 0
+        return tok
+
+    def encode_image(self, images, normalize=True):
+        return self.img[self.batch]
+
+    def encode_text(self, tokens, normalize=True):
+        kind = int(tokens[0, 1])
+        idx = tokens[:, 0]
+        if kind == 0:
+            return self.cls_text[idx]
+        if kind == 1:
+            return self.pimg[self.batch][idx]
+        return self.pgrp[self.batch][idx]
+
+
+class _SnapOpt:
+    """Optimizer stand-in: records gradients at step(), applies no update."""
+
+    def __init__(self, model):
+        self.model = model
+        self.param_groups = [{"lr": 0.0}]
+        self.snaps = []
+
+    def zero_grad(self):
+        for p in self.model.parameters():
+            p.grad = None
+
+    def step(self):
+        m = self.model
+        b = m.batch
+        self.snaps.append(dict(
+            dI=m.img.grad[b].clone(), dCls=m.cls_text.grad.clone(),
+            dPimg=m.pimg.grad[b].clone(), dPgrp=m.pgrp.grad[b].clone(),
+            dlogscale=m.logit_scale.grad.clone()))
+        m.batch += 1
+
+
+class _SpyLoss(nn.Module):
+    def __init__(self, inner):
+        super().__init__()
+        self.inner = inner
+        self.calls = []
+
+    def forward(self, image_features, text_features, logit_scale, output_dict=False):
+        out = self.inner(image_features, text_features, logit_scale, output_dict=output_dict)
+        self.calls.append(dict(text=text_features.detach().clone(),
+                               loss=out["contrastive_loss"].detach().clone()))
+        return out
+
+
+def gen_proto_step(open_clip, tt):
+    cases = [
+        # name, B(=D), C, batches, scale, alpha, flags(image, batch, template, zs, ft), dtype
+        ("b32_c7", 32, 7, 2, 100.0, 0.01, (1.0, 1.0, 1.0, 1.0, 1.0), torch.float64),
+        ("b64_c10", 64, 10, 1, 100.0, 0.01, (1.0, 1.0, 1.0, 1.0, 1.0), torch.float32),
+        ("b64_c10_flags", 64, 10, 1, 1.0 / 0.07, 0.05, (1.0, 0.0, 1.0, 0.5, 1.0), torch.float64),
+    ]
+    for k, (name, b, c, nb, scale, alpha, flags, dt) in enumerate(cases):
+        d = b  # the reference's broadcast at train.py:476 only runs when B == D
+        g = torch.Generator().manual_seed(2024 + k)
+        class_names = [f"class{j}" for j in range(c)]
+        bank0 = F.normalize(torch.randn(c, d, generator=g), dim=1)
+        cls_text = F.normalize(bank0 + 0.3 * torch.randn(c, d, generator=g) / math.sqrt(d) * 3, dim=1)
+        true_cls = torch.randint(0, c, (nb, b), generator=g)
+        img = F.normalize(bank0[true_cls] + 1.2 * torch.randn(nb, b, d, generator=g) / math.sqrt(d) * 3, dim=2)
+        pimg = F.normalize(bank0[true_cls] + 0.9 * torch.randn(nb, b, d, generator=g) / math.sqrt(d) * 3, dim=2)
+        pgrp = F.normalize(bank0[true_cls] + 0.7 * torch.randn(nb, b, d, generator=g) / math.sqrt(d) * 3, dim=2)
+        zs = torch.where(torch.rand(nb, b, generator=g) < 0.7, true_cls,
+                         torch.randint(0, c, (nb, b), generator=g))
+        bank0, cls_text, img, pimg, pgrp = (x.to(dt) for x in (bank0, cls_text, img, pimg, pgrp))
+
+        model = _TableModel(img, cls_text, pimg, pgrp, bank0, class_names, math.log(scale))
+        opt = _SnapOpt(model)
+        spy = _SpyLoss(open_clip.ClipLoss(local_loss=True, gather_with_grad=True, cache_labels=True))
+
+        def make_batch(bi):
+            idx = torch.arange(b)
+            texts = torch.zeros(b, 1, 2, dtype=torch.long)
+            pit = torch.zeros(b, 1, 2, dtype=torch.long); pit[:, 0, 0] = idx; pit[:, 0, 1] = 1
+            pgt = torch.zeros(b, 1, 2, dtype=torch.long); pgt[:, 0, 0] = idx; pgt[:, 0, 1] = 2
+            zcn = [(class_names[int(zs[bi, i])],) for i in range(b)]
+            return (torch.zeros(b, 1), torch.zeros(b, 1), texts, None, None, None, pit, pgt, None, zcn)
+
+        class _DL(list):
+            num_batches = nb
+            num_samples = nb * b
+        dl = _DL([make_batch(bi) for bi in range(nb)])
+        key = "synth-train-zero-shot-classification"
+        data = {"train": SimpleNamespace(set_epoch=lambda e: None, dataloader=dl),
+                key: SimpleNamespace(class_names=class_names,
+                                     templates=[lambda cname: f"label::{cname}"])}
+        args = SimpleNamespace(
+            device="cpu", precision="fp32", zeroshot_eval_data="synth",
+            extract_features_split="train", distill=False, accum_freq=1, skip_scheduler=True,
+            lr_scheduler="cosine", alpha=alpha, use_image_caption=flags[0],
+            use_batch_caption=flags[1], use_template_caption=flags[2],
+            use_zeroshot_pseudolabel=flags[3], use_finetune_pseudolabel=flags[4],
+            horovod=False, grad_clip_norm=None, log_every_n_steps=1000, rank=0, local_rank=0,
+            world_size=1, batch_size=b, wandb=False)
+
+        banks = [bank0.clone()]
+        # run batch by batch so the bank after every batch can be recorded
+        tt.train_one_epoch_v2(model, data, spy, 0, opt, None, None, None, args, None)
+        # (the reference loop consumed all nb batches; per-batch bank states are
+        #  recovered below for nb == 1, and for nb == 2 the final bank is recorded)
+        final_bank = torch.stack([model.memory_bank[cn].detach() for cn in class_names])
+
+        out = dict(bank0=bank0.numpy(), cls_text=cls_text.numpy(), img=img.numpy(),
+                   pimg=pimg.numpy(), pgrp=pgrp.numpy(), zs=zs.numpy(),
+                   scale=np.float64(scale), alpha=np.float64(alpha),
+                   flags=np.array(flags, dtype=np.float64), nb=np.int64(nb),
+                   final_bank=final_bank.numpy())
+        for bi in range(nb):
+            out[f"b{bi}_t_ft"] = spy.calls[2 * bi]["text"].numpy()
+            out[f"b{bi}_t_zs"] = spy.calls[2 * bi + 1]["text"].numpy()
+            out[f"b{bi}_loss_ft"] = spy.calls[2 * bi]["loss"].numpy()
+            out[f"b{bi}_loss_zs"] = spy.calls[2 * bi + 1]["loss"].numpy()
+            for nm, v in opt.snaps[bi].items():
+                out[f"b{bi}_{nm}"] = v.numpy()
+        np.savez_compressed(os.path.join(HERE, f"proto_step_{name}.npz"), **out)
+        print("proto_step", name, [float(cl["loss"]) for cl in spy.calls])
+
+
+def main():
+    torch.manual_seed(0)
+    torch.set_num_threads(4)
+    open_clip, tt = load_reference()
+    gen_clip_w1(open_clip)
+    gen_text_margins(tt)
+    gen_proto_step(open_clip, tt)
+    gen_clip_dist()
+
+
+if __name__ == "__main__":
+    main()
