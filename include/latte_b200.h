@@ -1,0 +1,215 @@
+/*
+ * latte_b200.h -- C ABI of the B200-native LatteCLIP loss head (liblatte_b200.so).
+ *
+ * The reference (astra-vision/LatteCLIP) is pure Python/PyTorch and has no FFI for this
+ * path; every entry point below replaces a span of reference Python that today runs as
+ * a chain of torch library calls.  The citation after each prototype is the reference
+ * code it stands in for (paths relative to the reference repository root).
+ *
+ * Conventions
+ *   - All pointers are DEVICE pointers owned by the caller (PyTorch caching allocator);
+ *     the library never frees or retains them past the call.
+ *   - Sizes are int64_t element counts, ld* are row strides in ELEMENTS, rows are
+ *     row-major with unit stride along the feature axis.
+ *   - `stream` is a cudaStream_t passed as void*; every call only enqueues work on it
+ *     (no host synchronisation, no thread-local or global mutable state => re-entrant,
+ *     callable from autograd worker threads).
+ *   - Scalars that live on the device in the reference (logit_scale = model.logit_scale.exp(),
+ *     src/training/train.py:405; the upstream gradient of the loss) are passed as device
+ *     pointers so the host never has to .item() them.
+ *   - Return value: 0 on success, a negative latte_status_t otherwise.  There is no CPU or
+ *     PyTorch fallback behind any entry point.
+ */
+#ifndef LATTE_B200_H_
+#define LATTE_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  LATTE_OK = 0,
+  LATTE_ERR_BAD_ARG = -1,        /* null pointer, negative size, bad enum                */
+  LATTE_ERR_UNSUPPORTED = -2,    /* shape / dtype / alignment this build cannot run       */
+  LATTE_ERR_WORKSPACE = -3,      /* caller workspace too small                            */
+  LATTE_ERR_CUDA = -4,           /* a CUDA runtime / driver call or kernel launch failed  */
+  LATTE_ERR_NO_DEVICE = -5       /* no sm_100 device visible                              */
+} latte_status_t;
+
+typedef enum {
+  LATTE_F32 = 0,
+  LATTE_BF16 = 1,
+  LATTE_F16 = 2
+} latte_dtype_t;
+
+/* label_weight_axis of the text mixture, src/training/train.py:476,481 */
+typedef enum {
+  LATTE_LABEL_AXIS_ROW = 0,      /* w_lbl[i] scales row i    (the evident intent)                 */
+  LATTE_LABEL_AXIS_QUIRK = 1     /* w_lbl[d] scales column d (the reference's literal broadcast,  */
+                                 /* only defined when B == D)                                     */
+} latte_label_axis_t;
+
+/* ---- library ----------------------------------------------------------------------- */
+const char* latte_version(void);
+const char* latte_status_string(int status);
+/* Fills SM count and compute capability of the current device. */
+int latte_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---- ClipLoss: open_clip/loss.py ------------------------------------------------------ */
+
+/* Bytes of scratch latte_clip_fwd / latte_clip_bwd need for these sizes. */
+int latte_clip_workspace_bytes(int64_t n_loc, int64_t n_all, int64_t dim, int dtype,
+                               size_t* bytes);
+
+/*
+ * Forward of ClipLoss on one rank.  Replaces ClipLoss.get_logits + get_ground_truth + the
+ * two F.cross_entropy calls (src/open_clip/loss.py:102-118, 89-100, 126-129) without
+ * materialising the logits:
+ *   row_lse[i] = logsumexp_j( s * <img_loc[i], txt_all[j]> )        i in [0, n_loc)
+ *   col_lse[i] = logsumexp_j( s * <txt_loc[i], img_all[j]> )
+ *   diag[i]    = s * <img_loc[i], txt_all[label_offset + i]>
+ *   *loss      = ( mean_i(row_lse[i] - diag[i]) + mean_i(col_lse[i] - diag'[i]) ) / 2
+ * label_offset = rank * n_loc under local_loss (loss.py:93-94), 0 for world_size 1.
+ * For world_size 1 pass img_all = img_loc, txt_all = txt_loc, n_all = n_loc.
+ * bf16 / fp16 features run on tcgen05 tensor cores (fp32 accumulate in TMEM); fp32
+ * features run on an fp32 SIMT kernel.
+ */
+int latte_clip_fwd(const void* img_loc, int64_t ld_img_loc,
+                   const void* txt_loc, int64_t ld_txt_loc,
+                   const void* img_all, int64_t ld_img_all,
+                   const void* txt_all, int64_t ld_txt_all,
+                   int dtype, int64_t n_loc, int64_t n_all, int64_t dim,
+                   int64_t label_offset,
+                   const float* logit_scale,     /* device scalar s                       */
+                   float* row_lse, float* col_lse, /* [n_loc] each                        */
+                   float* loss,                  /* device scalar out                     */
+                   void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * Backward of ClipLoss on one rank (the autograd of loss.py:109-116 + 126-129, and the
+ * reduce-scatter in the backward of torch.distributed.nn.all_gather, loss.py:49-50,
+ * replaced by an exchange of the LSE vectors).  With S_ij = s*<img_i, txt_j>:
+ *   G_ij   = ca * exp(S_ij - row_lse[i]) + cb * exp(S_ij - col_lse[j]) - cd * [j == label(i)]
+ *   d_img  = coef * s * G[loc rows, :] @ txt_all          (and symmetrically d_txt)
+ *   d_scale= coef * sum_ij (exp(S_ij - row_lse[i]) - delta_ij) * S_ij / s   (+ text side)
+ * coef = grad_loss / (2 * n_loc) * grad_mult.   cross_terms = 1 gives ca = cb = 1, cd = 2
+ * (every mode except local_loss && !gather_with_grad); cross_terms = 0 gives ca = 1,
+ * cb = 0, cd = 1 (loss.py:52-55 with local_loss: gathered features carry no gradient).
+ * row_lse_all / col_lse_all are the all-gathered LSE vectors [n_all] (== the local ones
+ * when world_size is 1).  d_img / d_txt are [n_loc, dim] in `grad_dtype`.
+ */
+int latte_clip_bwd(const void* img_loc, int64_t ld_img_loc,
+                   const void* txt_loc, int64_t ld_txt_loc,
+                   const void* img_all, int64_t ld_img_all,
+                   const void* txt_all, int64_t ld_txt_all,
+                   int dtype, int64_t n_loc, int64_t n_all, int64_t dim,
+                   int64_t label_offset,
+                   const float* logit_scale,
+                   const float* row_lse_all, const float* col_lse_all,   /* [n_all]  */
+                   const float* grad_loss,       /* device scalar dL/dloss                */
+                   float grad_mult, int cross_terms,
+                   void* d_img, void* d_txt, int grad_dtype, int64_t ld_grad,
+                   float* d_scale,               /* device scalar out (d loss / d s)      */
+                   void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- prototype / pseudo-label path: src/training/train.py ---------------------------- */
+
+/* out[c,:] = in[c,:] / max(||in[c,:]||_2, 1e-12)   (F.normalize(dim=1), train.py:388;
+ * zero_shot.py:143).  fp32 [C, dim]. */
+int latte_normalize_rows(const float* in, int64_t ld_in, float* out, int64_t ld_out,
+                         int64_t rows, int64_t dim, void* stream);
+
+/*
+ * Fused N x C similarity + row reductions, logits never stored:
+ *   sim[i,c] = <x[i,:], protos[c,:]>   (fp32 accumulate)
+ *   argmax_out[i] = first c maximising sim[i,c]          (train.py:410-411; zero_shot.py:40)
+ *   margin_out[i] = top1(sim[i,:]) - top2(sim[i,:])      (compute_text_weights, train.py:292-303)
+ *   top1_out[i]   = scale * max_c sim[i,c]
+ * Any of the three outputs may be NULL.  x is [n, dim] in x_dtype; protos is fp32 [C, dim].
+ * If row_index is not NULL, row i of x is x[row_index[i], :] (class-text gather,
+ * train.py:420-438).
+ */
+int latte_nxc_argmax_margin(const void* x, int64_t ldx, int x_dtype,
+                            const int64_t* row_index,
+                            int64_t n, int64_t dim,
+                            const float* protos, int64_t ldp, int64_t num_classes,
+                            float scale,
+                            int64_t* argmax_out, float* margin_out, float* top1_out,
+                            void* stream);
+
+/*
+ * Fused N x C similarity + top-k class ids (k <= 16), for the zero-shot evaluator
+ * (zero_shot.py:14-20,40: logits.topk(max(topk)); train.py:1352-1358).
+ * topk_idx is [n, k] int64, topk_val [n, k] fp32 (scale * sim), sorted descending,
+ * lowest index first among equal values.
+ */
+int latte_nxc_topk(const void* x, int64_t ldx, int x_dtype, int64_t n, int64_t dim,
+                   const float* protos, int64_t ldp, int64_t num_classes, float scale,
+                   int k, int64_t* topk_idx, float* topk_val, void* stream);
+
+/*
+ * Text mixture + EMA toward the memory-bank rows (train.py:472-488), gathers fused:
+ *   L_ft = class_text[preds], L_zs = class_text[zs], M_ft = bank[preds], M_zs = bank[zs]
+ *   t_ft = M_ft + alpha * ((w_lbl (*) L_ft + w_img*P + w_grp*G) / (w_lbl   + w_img + w_grp) - M_ft)
+ *   t_zs = M_zs + alpha * ((w_lbl (*) L_zs + w_img*P + w_grp*G) / (w_lbl_zs+ w_img + w_grp) - M_zs)
+ * (*) per label_axis.  class_text/per_image/per_group/t_ft/t_zs share `dtype`; bank and
+ * the weight vectors are fp32.  Weights are the already flag-scaled, detached margins
+ * (train.py:444-469).
+ */
+int latte_mix_ema_fwd(const void* class_text, int64_t ld_ct,
+                      const void* per_image, int64_t ld_pi,
+                      const void* per_group, int64_t ld_pg,
+                      const float* bank, int64_t ld_bank,
+                      const int64_t* preds, const int64_t* zs,
+                      const float* w_lbl, const float* w_lbl_zs,
+                      const float* w_img, const float* w_grp,
+                      float alpha, int label_axis, int dtype,
+                      int64_t batch, int64_t dim, int64_t num_classes,
+                      void* t_ft, void* t_zs, int64_t ld_out, void* stream);
+
+/*
+ * Backward of latte_mix_ema_fwd w.r.t. the three text sources (weights are detached in
+ * the reference, train.py:444-449).  d_class_text [C, dim] fp32 is ACCUMULATED with a
+ * deterministic per-class segment sum (must be zeroed by the caller or hold a running
+ * gradient); d_per_image / d_per_group are [batch, dim] in `dtype`.  d_bank (nullable,
+ * fp32 [C, dim], accumulated) receives (1 - alpha) * d_t scattered by preds / zs -- the
+ * reference sends that gradient into memory-bank Parameters that the optimizer no
+ * longer owns, so callers normally pass NULL.
+ */
+int latte_mix_ema_bwd(const void* d_t_ft, const void* d_t_zs, int64_t ld_dt,
+                      const int64_t* preds, const int64_t* zs,
+                      const float* w_lbl, const float* w_lbl_zs,
+                      const float* w_img, const float* w_grp,
+                      float alpha, int label_axis, int dtype,
+                      int64_t batch, int64_t dim, int64_t num_classes,
+                      float* d_class_text, int64_t ld_dct,
+                      void* d_per_image, void* d_per_group, int64_t ld_dp,
+                      float* d_bank, int64_t ld_dbank, void* stream);
+
+/*
+ * Memory-bank update, step 1 (train.py:508-526): per-class sums and counts, accumulated
+ * in the reference's order (for each sample i ascending: t_zs[i] into class zs[i], then
+ * t_ft[i] into class preds[i]).  sums [C, dim] fp32 and counts [C] fp32 are OVERWRITTEN.
+ * Deterministic (no atomics).  On several ranks the caller all-reduces sums and counts
+ * between step 1 and step 2.
+ */
+int latte_bank_accumulate(const void* t_ft, const void* t_zs, int64_t ld_t, int dtype,
+                          const int64_t* preds, const int64_t* zs,
+                          int64_t batch, int64_t dim, int64_t num_classes,
+                          float* sums, int64_t ld_sums, float* counts, void* stream);
+
+/*
+ * Memory-bank update, step 2 (train.py:528-530): for every class with counts[c] > 0,
+ * bank[c,:] = normalize(sums[c,:] / counts[c]); other rows are left untouched.
+ */
+int latte_bank_finalize(const float* sums, int64_t ld_sums, const float* counts,
+                        float* bank, int64_t ld_bank,
+                        int64_t dim, int64_t num_classes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LATTE_B200_H_ */

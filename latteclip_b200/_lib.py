@@ -1,0 +1,356 @@
+"""ctypes binding of liblatte_b200.so (C ABI in include/latte_b200.h).
+
+PyTorch is used only for device memory and streams: every function here takes torch
+tensors, checks them, and passes raw device pointers + sizes to the C ABI on the current
+CUDA stream.  There is NO fallback: if the shared library is missing or a call fails, a
+RuntimeError is raised.
+"""
+
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+import sys
+from typing import Optional, Tuple
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO_DIR = os.path.join(_HERE, "_C")
+SO_PATH = os.path.join(_SO_DIR, "liblatte_b200.so")
+CSRC = os.path.join(_HERE, "csrc")
+SOURCES = ["api.cu", "clip_tc.cu", "clip_simt.cu", "nxc.cu", "proto.cu"]
+
+F32, BF16, F16 = 0, 1, 2
+LABEL_AXIS = {"row": 0, "quirk": 1}
+_DTYPES = {torch.float32: F32, torch.bfloat16: BF16, torch.float16: F16}
+
+_lib = None
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile the CUDA sources for sm_100a into latteclip_b200/_C/liblatte_b200.so
+    (in-tree, so the built library travels with the repository snapshot)."""
+    srcs = [os.path.join(CSRC, s) for s in SOURCES]
+    deps = srcs + [os.path.join(CSRC, h) for h in ("latte_common.cuh", "tc_ptx.cuh")] + \
+        [os.path.join(os.path.dirname(_HERE), "include", "latte_b200.h")]
+    if not force and os.path.exists(SO_PATH):
+        so_m = os.path.getmtime(SO_PATH)
+        if all(os.path.getmtime(d) <= so_m for d in deps):
+            return SO_PATH
+    os.makedirs(_SO_DIR, exist_ok=True)
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc, "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+           "-Xcompiler", "-fPIC", "-shared", "-cudart", "static", "-o", SO_PATH] + srcs
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    if verbose:
+        sys.stderr.write(res.stderr)
+    return SO_PATH
+
+
+def _declare(lib):
+    c = ctypes
+    vp, i64, i32, f32, sz = c.c_void_p, c.c_int64, c.c_int, c.c_float, c.c_size_t
+    lib.latte_version.restype = c.c_char_p
+    lib.latte_version.argtypes = []
+    lib.latte_status_string.restype = c.c_char_p
+    lib.latte_status_string.argtypes = [i32]
+    lib.latte_device_info.argtypes = [c.POINTER(i32)] * 3
+    lib.latte_clip_workspace_bytes.argtypes = [i64, i64, i64, i32, c.POINTER(sz)]
+    lib.latte_clip_fwd.argtypes = [vp, i64, vp, i64, vp, i64, vp, i64, i32, i64, i64, i64, i64,
+                                   vp, vp, vp, vp, vp, sz, vp]
+    lib.latte_clip_bwd.argtypes = [vp, i64, vp, i64, vp, i64, vp, i64, i32, i64, i64, i64, i64,
+                                   vp, vp, vp, vp, f32, i32, vp, vp, i32, i64, vp, vp, sz, vp]
+    lib.latte_normalize_rows.argtypes = [vp, i64, vp, i64, i64, i64, vp]
+    lib.latte_nxc_argmax_margin.argtypes = [vp, i64, i32, vp, i64, i64, vp, i64, i64, f32,
+                                            vp, vp, vp, vp]
+    lib.latte_nxc_topk.argtypes = [vp, i64, i32, i64, i64, vp, i64, i64, f32, i32, vp, vp, vp]
+    lib.latte_mix_ema_fwd.argtypes = [vp, i64, vp, i64, vp, i64, vp, i64, vp, vp, vp, vp, vp, vp,
+                                      f32, i32, i32, i64, i64, i64, vp, vp, i64, vp]
+    lib.latte_mix_ema_bwd.argtypes = [vp, vp, i64, vp, vp, vp, vp, vp, vp, f32, i32, i32, i64,
+                                      i64, i64, vp, i64, vp, vp, i64, vp, i64, vp]
+    lib.latte_bank_accumulate.argtypes = [vp, vp, i64, i32, vp, vp, i64, i64, i64, vp, i64, vp, vp]
+    lib.latte_bank_finalize.argtypes = [vp, i64, vp, vp, i64, i64, i64, vp]
+    for name in EXPORTS:
+        if name not in ("latte_version", "latte_status_string"):
+            getattr(lib, name).restype = i32
+
+
+EXPORTS = [
+    "latte_version", "latte_status_string", "latte_device_info", "latte_clip_workspace_bytes",
+    "latte_clip_fwd", "latte_clip_bwd", "latte_normalize_rows", "latte_nxc_argmax_margin",
+    "latte_nxc_topk", "latte_mix_ema_fwd", "latte_mix_ema_bwd", "latte_bank_accumulate",
+    "latte_bank_finalize",
+]
+
+
+def load():
+    """Load the shared library; raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(SO_PATH):
+            raise RuntimeError(
+                f"{SO_PATH} is missing: build the CUDA extension first "
+                "(python -c 'import __graft_entry__ as g; g.build()' or python -m latteclip_b200.build). "
+                "latteclip_b200 has no CPU / PyTorch fallback.")
+        lib = ctypes.CDLL(SO_PATH)
+        _declare(lib)
+        _lib = lib
+    return _lib
+
+
+def version() -> str:
+    return load().latte_version().decode()
+
+
+def _check(status: int, what: str):
+    if status != 0:
+        msg = load().latte_status_string(status).decode()
+        raise RuntimeError(f"{what} failed: {msg} (status {status})")
+
+
+def _stream(t: torch.Tensor) -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def _ptr(t: Optional[torch.Tensor]) -> ctypes.c_void_p:
+    return ctypes.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _dt(t: torch.Tensor) -> int:
+    try:
+        return _DTYPES[t.dtype]
+    except KeyError:
+        raise RuntimeError(f"unsupported dtype {t.dtype}") from None
+
+
+def _rows(t: torch.Tensor, name: str) -> torch.Tensor:
+    """2-D, unit stride along the feature axis (row stride is passed to the kernels)."""
+    if t.dim() != 2:
+        raise RuntimeError(f"{name} must be 2-D, got shape {tuple(t.shape)}")
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor: latteclip_b200 has no CPU path")
+    if t.stride(1) != 1 or t.stride(0) < t.shape[1]:
+        t = t.contiguous()
+    return t
+
+
+def _vec(t: torch.Tensor, dtype, name: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor")
+    return t.detach().to(dtype).contiguous()
+
+
+def _scalar_f32(t: torch.Tensor) -> torch.Tensor:
+    return t.detach().to(torch.float32).reshape(1).contiguous()
+
+
+def _workspace(n_loc: int, n_all: int, dim: int, dtype: int, device) -> torch.Tensor:
+    nbytes = ctypes.c_size_t(0)
+    _check(load().latte_clip_workspace_bytes(n_loc, n_all, dim, dtype, ctypes.byref(nbytes)),
+           "latte_clip_workspace_bytes")
+    return torch.empty(nbytes.value + 256, dtype=torch.uint8, device=device)
+
+
+def _aligned_ptr(ws: torch.Tensor) -> Tuple[ctypes.c_void_p, int]:
+    p = ws.data_ptr()
+    off = (-p) % 256
+    return ctypes.c_void_p(p + off), ws.numel() - off
+
+
+# ------------------------------------------------------------------------------ ClipLoss
+def clip_fwd(img_loc, txt_loc, img_all, txt_all, label_offset: int, logit_scale):
+    """-> (row_lse[n_loc], col_lse[n_loc], loss[1]) fp32 device tensors."""
+    lib = load()
+    img_loc, txt_loc = _rows(img_loc, "image_features"), _rows(txt_loc, "text_features")
+    img_all, txt_all = _rows(img_all, "all_image_features"), _rows(txt_all, "all_text_features")
+    dt = _dt(img_loc)
+    if not (_dt(txt_loc) == _dt(img_all) == _dt(txt_all) == dt):
+        raise RuntimeError("clip_fwd: all feature tensors must share one dtype")
+    n_loc, dim = img_loc.shape
+    n_all = img_all.shape[0]
+    dev = img_loc.device
+    s = _scalar_f32(logit_scale)
+    row_lse = torch.empty(n_loc, dtype=torch.float32, device=dev)
+    col_lse = torch.empty(n_loc, dtype=torch.float32, device=dev)
+    loss = torch.empty(1, dtype=torch.float32, device=dev)
+    ws = _workspace(n_loc, n_all, dim, dt, dev)
+    wp, wn = _aligned_ptr(ws)
+    with torch.cuda.device(dev):
+        _check(lib.latte_clip_fwd(_ptr(img_loc), img_loc.stride(0), _ptr(txt_loc), txt_loc.stride(0),
+                                  _ptr(img_all), img_all.stride(0), _ptr(txt_all), txt_all.stride(0),
+                                  dt, n_loc, n_all, dim, label_offset, _ptr(s), _ptr(row_lse),
+                                  _ptr(col_lse), _ptr(loss), wp, wn, _stream(img_loc)),
+               "latte_clip_fwd")
+    return row_lse, col_lse, loss
+
+
+def clip_bwd(img_loc, txt_loc, img_all, txt_all, label_offset: int, logit_scale,
+             row_lse_all, col_lse_all, grad_loss, grad_mult: float, cross_terms: bool):
+    """-> (d_img[n_loc, dim], d_txt[n_loc, dim] in the feature dtype, d_scale[1] fp32)."""
+    lib = load()
+    img_loc, txt_loc = _rows(img_loc, "image_features"), _rows(txt_loc, "text_features")
+    img_all, txt_all = _rows(img_all, "all_image_features"), _rows(txt_all, "all_text_features")
+    dt = _dt(img_loc)
+    n_loc, dim = img_loc.shape
+    n_all = img_all.shape[0]
+    dev = img_loc.device
+    s = _scalar_f32(logit_scale)
+    g = _scalar_f32(grad_loss)
+    row_lse_all = _vec(row_lse_all, torch.float32, "row_lse")
+    col_lse_all = _vec(col_lse_all, torch.float32, "col_lse")
+    if row_lse_all.numel() != n_all or col_lse_all.numel() != n_all:
+        raise RuntimeError("clip_bwd: LSE vectors must have n_all entries")
+    d_img = torch.empty(n_loc, dim, dtype=img_loc.dtype, device=dev)
+    d_txt = torch.empty(n_loc, dim, dtype=img_loc.dtype, device=dev)
+    d_scale = torch.empty(1, dtype=torch.float32, device=dev)
+    ws = _workspace(n_loc, n_all, dim, dt, dev)
+    wp, wn = _aligned_ptr(ws)
+    with torch.cuda.device(dev):
+        _check(lib.latte_clip_bwd(_ptr(img_loc), img_loc.stride(0), _ptr(txt_loc), txt_loc.stride(0),
+                                  _ptr(img_all), img_all.stride(0), _ptr(txt_all), txt_all.stride(0),
+                                  dt, n_loc, n_all, dim, label_offset, _ptr(s), _ptr(row_lse_all),
+                                  _ptr(col_lse_all), _ptr(g), float(grad_mult), int(bool(cross_terms)),
+                                  _ptr(d_img), _ptr(d_txt), dt, dim, _ptr(d_scale), wp, wn,
+                                  _stream(img_loc)),
+               "latte_clip_bwd")
+    return d_img, d_txt, d_scale
+
+
+# ------------------------------------------------------------------------------ prototypes
+def normalize_rows(x: torch.Tensor) -> torch.Tensor:
+    x = _rows(x.detach().to(torch.float32), "bank")
+    out = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        _check(load().latte_normalize_rows(_ptr(x), x.stride(0), _ptr(out), out.stride(0),
+                                           x.shape[0], x.shape[1], _stream(x)),
+               "latte_normalize_rows")
+    return out
+
+
+def nxc_argmax_margin(x, protos, scale: float = 1.0, row_index=None, want_argmax=True,
+                      want_margin=True, want_top1=False):
+    """-> (argmax int64[n] | None, margin fp32[n] | None, top1 fp32[n] | None)."""
+    x = _rows(x.detach(), "x")
+    protos = _rows(protos.detach().to(torch.float32), "prototypes")
+    if x.shape[1] != protos.shape[1]:
+        raise RuntimeError("nxc: feature dims differ")
+    dev = x.device
+    if row_index is not None:
+        row_index = _vec(row_index, torch.int64, "row_index")
+        n = row_index.numel()
+    else:
+        n = x.shape[0]
+    am = torch.empty(n, dtype=torch.int64, device=dev) if want_argmax else None
+    mg = torch.empty(n, dtype=torch.float32, device=dev) if want_margin else None
+    t1 = torch.empty(n, dtype=torch.float32, device=dev) if want_top1 else None
+    with torch.cuda.device(dev):
+        _check(load().latte_nxc_argmax_margin(_ptr(x), x.stride(0), _dt(x), _ptr(row_index), n,
+                                              x.shape[1], _ptr(protos), protos.stride(0),
+                                              protos.shape[0], float(scale), _ptr(am), _ptr(mg),
+                                              _ptr(t1), _stream(x)),
+               "latte_nxc_argmax_margin")
+    return am, mg, t1
+
+
+def nxc_topk(x, protos, k: int, scale: float = 1.0):
+    x = _rows(x.detach(), "x")
+    protos = _rows(protos.detach().to(torch.float32), "prototypes")
+    n = x.shape[0]
+    idx = torch.empty(n, k, dtype=torch.int64, device=x.device)
+    val = torch.empty(n, k, dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _check(load().latte_nxc_topk(_ptr(x), x.stride(0), _dt(x), n, x.shape[1], _ptr(protos),
+                                     protos.stride(0), protos.shape[0], float(scale), int(k),
+                                     _ptr(idx), _ptr(val), _stream(x)),
+               "latte_nxc_topk")
+    return idx, val
+
+
+def mix_ema_fwd(class_text, per_image, per_group, bank, preds, zs, w_lbl, w_lbl_zs, w_img, w_grp,
+                alpha: float, label_axis: str):
+    class_text = _rows(class_text.detach(), "class_text")
+    per_image = _rows(per_image.detach(), "per_image")
+    per_group = _rows(per_group.detach(), "per_group")
+    bank = _rows(bank.detach().to(torch.float32), "bank")
+    dt = _dt(class_text)
+    if not (_dt(per_image) == _dt(per_group) == dt):
+        raise RuntimeError("mix_ema: text sources must share one dtype")
+    b, d = per_image.shape
+    c = class_text.shape[0]
+    dev = per_image.device
+    preds, zs = _vec(preds, torch.int64, "preds"), _vec(zs, torch.int64, "zs")
+    ws = [_vec(w, torch.float32, "weight") for w in (w_lbl, w_lbl_zs, w_img, w_grp)]
+    t_ft = torch.empty(b, d, dtype=per_image.dtype, device=dev)
+    t_zs = torch.empty(b, d, dtype=per_image.dtype, device=dev)
+    with torch.cuda.device(dev):
+        _check(load().latte_mix_ema_fwd(_ptr(class_text), class_text.stride(0), _ptr(per_image),
+                                        per_image.stride(0), _ptr(per_group), per_group.stride(0),
+                                        _ptr(bank), bank.stride(0), _ptr(preds), _ptr(zs),
+                                        _ptr(ws[0]), _ptr(ws[1]), _ptr(ws[2]), _ptr(ws[3]),
+                                        float(alpha), LABEL_AXIS[label_axis], dt, b, d, c,
+                                        _ptr(t_ft), _ptr(t_zs), d, _stream(per_image)),
+               "latte_mix_ema_fwd")
+    return t_ft, t_zs
+
+
+def mix_ema_bwd(d_t_ft, d_t_zs, preds, zs, w_lbl, w_lbl_zs, w_img, w_grp, alpha: float,
+                label_axis: str, num_classes: int, want_bank: bool = False):
+    """-> (d_class_text fp32 [C, D], d_per_image, d_per_group [B, D], d_bank fp32 [C, D] | None)."""
+    d_t_ft = _rows(d_t_ft.detach(), "d_t_ft")
+    d_t_zs = _rows(d_t_zs.detach().to(d_t_ft.dtype), "d_t_zs")
+    if d_t_zs.stride(0) != d_t_ft.stride(0):
+        d_t_ft, d_t_zs = d_t_ft.contiguous(), d_t_zs.contiguous()
+    dt = _dt(d_t_ft)
+    b, d = d_t_ft.shape
+    dev = d_t_ft.device
+    preds, zs = _vec(preds, torch.int64, "preds"), _vec(zs, torch.int64, "zs")
+    ws = [_vec(w, torch.float32, "weight") for w in (w_lbl, w_lbl_zs, w_img, w_grp)]
+    d_ct = torch.zeros(num_classes, d, dtype=torch.float32, device=dev)
+    d_pi = torch.empty(b, d, dtype=d_t_ft.dtype, device=dev)
+    d_pg = torch.empty(b, d, dtype=d_t_ft.dtype, device=dev)
+    d_bank = torch.zeros(num_classes, d, dtype=torch.float32, device=dev) if want_bank else None
+    with torch.cuda.device(dev):
+        _check(load().latte_mix_ema_bwd(_ptr(d_t_ft), _ptr(d_t_zs), d_t_ft.stride(0), _ptr(preds),
+                                        _ptr(zs), _ptr(ws[0]), _ptr(ws[1]), _ptr(ws[2]), _ptr(ws[3]),
+                                        float(alpha), LABEL_AXIS[label_axis], dt, b, d, num_classes,
+                                        _ptr(d_ct), d, _ptr(d_pi), _ptr(d_pg), d, _ptr(d_bank), d,
+                                        _stream(d_t_ft)),
+               "latte_mix_ema_bwd")
+    return d_ct, d_pi, d_pg, d_bank
+
+
+def bank_accumulate(t_ft, t_zs, preds, zs, num_classes: int):
+    """-> (sums fp32 [C, D], counts fp32 [C])."""
+    t_ft = _rows(t_ft.detach(), "t_ft")
+    t_zs = _rows(t_zs.detach().to(t_ft.dtype), "t_zs")
+    if t_zs.stride(0) != t_ft.stride(0):
+        t_ft, t_zs = t_ft.contiguous(), t_zs.contiguous()
+    b, d = t_ft.shape
+    dev = t_ft.device
+    preds, zs = _vec(preds, torch.int64, "preds"), _vec(zs, torch.int64, "zs")
+    sums = torch.empty(num_classes, d, dtype=torch.float32, device=dev)
+    counts = torch.empty(num_classes, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _check(load().latte_bank_accumulate(_ptr(t_ft), _ptr(t_zs), t_ft.stride(0), _dt(t_ft),
+                                            _ptr(preds), _ptr(zs), b, d, num_classes, _ptr(sums), d,
+                                            _ptr(counts), _stream(t_ft)),
+               "latte_bank_accumulate")
+    return sums, counts
+
+
+def bank_finalize(sums, counts, bank):
+    """In-place update of ``bank`` (fp32 [C, D]) for every class with counts > 0."""
+    if bank.dtype != torch.float32 or not bank.is_contiguous() or not bank.is_cuda:
+        raise RuntimeError("bank_finalize: bank must be a contiguous fp32 CUDA tensor")
+    c, d = bank.shape
+    with torch.cuda.device(bank.device):
+        _check(load().latte_bank_finalize(_ptr(sums), sums.stride(0), _ptr(counts), _ptr(bank),
+                                          bank.stride(0), d, c, _stream(bank)),
+               "latte_bank_finalize")
+    return bank

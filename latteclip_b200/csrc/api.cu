@@ -1,0 +1,256 @@
+// C ABI of liblatte_b200: library info + the ClipLoss forward / backward orchestration
+// (row kernels in clip_tc.cu / clip_simt.cu, small finalize kernels here).
+#include "latte_common.cuh"
+
+namespace latte {
+
+int device_sm_count() {
+  int dev = 0, sms = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 148;
+  return sms > 0 ? sms : 148;
+}
+
+namespace {
+
+constexpr int kFinalThreads = 1024;
+constexpr int kMaxParts = 16;
+
+// Merge the per-(split, half) online-softmax partials of one row into a base-2 LSE.
+__device__ __forceinline__ float merge_parts(const float* pmax, const float* psum, int nparts,
+                                             int64_t n_loc, int64_t i) {
+  float M = -INFINITY;
+  for (int k = 0; k < nparts; ++k) M = fmaxf(M, pmax[(int64_t)k * n_loc + i]);
+  float L = 0.f;
+  for (int k = 0; k < nparts; ++k) {
+    const float m = pmax[(int64_t)k * n_loc + i];
+    if (m > -INFINITY) L += psum[(int64_t)k * n_loc + i] * exp2f(m - M);
+  }
+  return M + log2f(L);
+}
+
+// row_lse / col_lse in natural-log units and the scalar loss (loss.py:126-129).
+__global__ void __launch_bounds__(kFinalThreads)
+clip_finalize_kernel(const float* pmax_r, const float* psum_r, const float* diag_r,
+                     const float* pmax_c, const float* psum_c, const float* diag_c, int nparts,
+                     int64_t n_loc, const float* logit_scale, float* row_lse, float* col_lse,
+                     float* loss) {
+  __shared__ double red[kFinalThreads / 32];
+  const float s = __ldg(logit_scale);
+  double acc = 0.0;
+  for (int64_t i = threadIdx.x; i < n_loc; i += kFinalThreads) {
+    const float lr = merge_parts(pmax_r, psum_r, nparts, n_loc, i) * kLn2;
+    const float lc = merge_parts(pmax_c, psum_c, nparts, n_loc, i) * kLn2;
+    row_lse[i] = lr;
+    col_lse[i] = lc;
+    acc += (double)(lr - s * diag_r[i]) + (double)(lc - s * diag_c[i]);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tot = 0.0;
+    for (int w = 0; w < kFinalThreads / 32; ++w) tot += red[w];
+    *loss = (float)(tot / (2.0 * (double)n_loc));
+  }
+}
+
+// natural-log LSE -> base-2 units, zero padded to a multiple of the 128-column tile
+__global__ void lse_to_base2_kernel(const float* row_lse, const float* col_lse, int64_t n_all,
+                                    int64_t n_pad, float* row2, float* col2) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n_pad) return;
+  row2[j] = j < n_all ? row_lse[j] * kLog2e : 0.f;
+  col2[j] = j < n_all ? col_lse[j] * kLog2e : 0.f;
+}
+
+__global__ void __launch_bounds__(256)
+ds_reduce_kernel(const float* partial, int count, const float* grad_loss, float grad_mult,
+                 int64_t n_loc, float* d_scale) {
+  __shared__ double red[8];
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < count; i += 256) acc += (double)partial[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tot = 0.0;
+    for (int w = 0; w < 8; ++w) tot += red[w];
+    *d_scale = (float)(tot * (double)(__ldg(grad_loss) * grad_mult) / (2.0 * (double)n_loc));
+  }
+}
+
+struct WsLayout {
+  size_t part;      // floats per partial array (kMaxParts * n_loc)
+  size_t off_pmax_r, off_psum_r, off_diag_r, off_pmax_c, off_psum_c, off_diag_c;
+  size_t off_row2, off_col2, off_ds;
+  size_t n_pad, ds_cap;
+  size_t total;
+};
+
+WsLayout ws_layout(int64_t n_loc, int64_t n_all) {
+  WsLayout w;
+  auto up = [](size_t x) { return (x + 63) / 64 * 64; };   // keep every array 256-byte aligned
+  w.part = up((size_t)kMaxParts * (size_t)n_loc);
+  const size_t nl = up((size_t)n_loc);
+  size_t o = 0;
+  w.off_pmax_r = o; o += w.part;
+  w.off_psum_r = o; o += w.part;
+  w.off_diag_r = o; o += nl;
+  w.off_pmax_c = o; o += w.part;
+  w.off_psum_c = o; o += w.part;
+  w.off_diag_c = o; o += nl;
+  w.n_pad = ((size_t)n_all + 127) / 128 * 128 + 128;
+  w.off_row2 = o; o += up(w.n_pad);
+  w.off_col2 = o; o += up(w.n_pad);
+  w.ds_cap = up(2 * (((size_t)n_loc + 63) / 64));
+  w.off_ds = o; o += w.ds_cap;
+  w.total = o * sizeof(float);
+  return w;
+}
+
+bool use_tc(int dtype, int64_t dim, const void* xa, int64_t lda, const void* xb, int64_t ldb,
+            const void* xc, int64_t ldc, const void* xd, int64_t ldd) {
+  return clip_tc_supported(dtype, dim, lda, ldb, xa, xb) && clip_tc_supported(dtype, dim, ldc, ldd, xc, xd);
+}
+
+}  // namespace
+}  // namespace latte
+
+using namespace latte;
+
+extern "C" const char* latte_version(void) { return "latte_b200 0.1.0 (sm_100a)"; }
+
+extern "C" const char* latte_status_string(int status) {
+  switch (status) {
+    case LATTE_OK: return "ok";
+    case LATTE_ERR_BAD_ARG: return "bad argument (null pointer, negative size or unknown enum)";
+    case LATTE_ERR_UNSUPPORTED: return "unsupported shape, dtype or alignment";
+    case LATTE_ERR_WORKSPACE: return "workspace too small";
+    case LATTE_ERR_CUDA: return "CUDA runtime/driver call or kernel launch failed";
+    case LATTE_ERR_NO_DEVICE: return "no sm_100 CUDA device";
+    default: return "unknown status";
+  }
+}
+
+extern "C" int latte_device_info(int* sm_count, int* cc_major, int* cc_minor) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return LATTE_ERR_NO_DEVICE;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return LATTE_ERR_NO_DEVICE;
+  if (sm_count) *sm_count = prop.multiProcessorCount;
+  if (cc_major) *cc_major = prop.major;
+  if (cc_minor) *cc_minor = prop.minor;
+  return LATTE_OK;
+}
+
+extern "C" int latte_clip_workspace_bytes(int64_t n_loc, int64_t n_all, int64_t dim, int dtype,
+                                          size_t* bytes) {
+  LATTE_CHECK_ARG(bytes && n_loc > 0 && n_all >= n_loc && dim > 0);
+  LATTE_CHECK_ARG(dtype >= LATTE_F32 && dtype <= LATTE_F16);
+  *bytes = ws_layout(n_loc, n_all).total;
+  return LATTE_OK;
+}
+
+extern "C" int latte_clip_fwd(const void* img_loc, int64_t ld_img_loc, const void* txt_loc,
+                              int64_t ld_txt_loc, const void* img_all, int64_t ld_img_all,
+                              const void* txt_all, int64_t ld_txt_all, int dtype, int64_t n_loc,
+                              int64_t n_all, int64_t dim, int64_t label_offset,
+                              const float* logit_scale, float* row_lse, float* col_lse,
+                              float* loss, void* workspace, size_t workspace_bytes,
+                              void* stream) {
+  LATTE_CHECK_ARG(img_loc && txt_loc && img_all && txt_all && logit_scale && row_lse && col_lse &&
+                  loss && workspace);
+  LATTE_CHECK_ARG(n_loc > 0 && n_all >= n_loc && dim > 0);
+  LATTE_CHECK_ARG(label_offset >= 0 && label_offset + n_loc <= n_all);
+  LATTE_CHECK_ARG(dtype >= LATTE_F32 && dtype <= LATTE_F16);
+  LATTE_CHECK_ARG(ld_img_loc >= dim && ld_txt_loc >= dim && ld_img_all >= dim && ld_txt_all >= dim);
+  const WsLayout w = ws_layout(n_loc, n_all);
+  if (workspace_bytes < w.total) return LATTE_ERR_WORKSPACE;
+  if ((reinterpret_cast<uintptr_t>(workspace) & 255) != 0) return LATTE_ERR_BAD_ARG;
+  float* ws = static_cast<float*>(workspace);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+
+  const bool tc = use_tc(dtype, dim, img_loc, ld_img_loc, txt_all, ld_txt_all, txt_loc,
+                         ld_txt_loc, img_all, ld_img_all);
+  int nparts = 1;
+  if (tc) {
+    nparts = clip_tc_nparts(n_loc, n_all, device_sm_count());
+    if (nparts > kMaxParts) nparts = kMaxParts;
+  }
+  ClipFwdArgs a;
+  a.dtype = dtype; a.n_loc = n_loc; a.n_all = n_all; a.dim = dim;
+  a.label_offset = label_offset; a.logit_scale = logit_scale; a.nparts = nparts;
+  // image -> text: rows of logits_per_image (loss.py:109 / :115)
+  a.x = img_loc; a.ldx = ld_img_loc; a.y = txt_all; a.ldy = ld_txt_all;
+  a.part_max = ws + w.off_pmax_r; a.part_sum = ws + w.off_psum_r; a.diag = ws + w.off_diag_r;
+  int rc = tc ? clip_fwd_rows_tc(a, st) : clip_fwd_rows_simt(a, st);
+  if (rc) return rc;
+  // text -> image: rows of logits_per_text (loss.py:110 / :116)
+  a.x = txt_loc; a.ldx = ld_txt_loc; a.y = img_all; a.ldy = ld_img_all;
+  a.part_max = ws + w.off_pmax_c; a.part_sum = ws + w.off_psum_c; a.diag = ws + w.off_diag_c;
+  rc = tc ? clip_fwd_rows_tc(a, st) : clip_fwd_rows_simt(a, st);
+  if (rc) return rc;
+  clip_finalize_kernel<<<1, kFinalThreads, 0, st>>>(
+      ws + w.off_pmax_r, ws + w.off_psum_r, ws + w.off_diag_r, ws + w.off_pmax_c,
+      ws + w.off_psum_c, ws + w.off_diag_c, nparts, n_loc, logit_scale, row_lse, col_lse, loss);
+  LATTE_LAUNCH_OK();
+  return LATTE_OK;
+}
+
+extern "C" int latte_clip_bwd(const void* img_loc, int64_t ld_img_loc, const void* txt_loc,
+                              int64_t ld_txt_loc, const void* img_all, int64_t ld_img_all,
+                              const void* txt_all, int64_t ld_txt_all, int dtype, int64_t n_loc,
+                              int64_t n_all, int64_t dim, int64_t label_offset,
+                              const float* logit_scale, const float* row_lse_all,
+                              const float* col_lse_all, const float* grad_loss, float grad_mult,
+                              int cross_terms, void* d_img, void* d_txt, int grad_dtype,
+                              int64_t ld_grad, float* d_scale, void* workspace,
+                              size_t workspace_bytes, void* stream) {
+  LATTE_CHECK_ARG(img_loc && txt_loc && img_all && txt_all && logit_scale && row_lse_all &&
+                  col_lse_all && grad_loss && d_img && d_txt && d_scale && workspace);
+  LATTE_CHECK_ARG(n_loc > 0 && n_all >= n_loc && dim > 0);
+  LATTE_CHECK_ARG(label_offset >= 0 && label_offset + n_loc <= n_all);
+  LATTE_CHECK_ARG(dtype >= LATTE_F32 && dtype <= LATTE_F16);
+  LATTE_CHECK_ARG(grad_dtype >= LATTE_F32 && grad_dtype <= LATTE_F16);
+  LATTE_CHECK_ARG(ld_img_loc >= dim && ld_txt_loc >= dim && ld_img_all >= dim && ld_txt_all >= dim &&
+                  ld_grad >= dim);
+  const WsLayout w = ws_layout(n_loc, n_all);
+  if (workspace_bytes < w.total) return LATTE_ERR_WORKSPACE;
+  if ((reinterpret_cast<uintptr_t>(workspace) & 255) != 0) return LATTE_ERR_BAD_ARG;
+  float* ws = static_cast<float*>(workspace);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+
+  float* row2 = ws + w.off_row2;
+  float* col2 = ws + w.off_col2;
+  lse_to_base2_kernel<<<(unsigned)((w.n_pad + 255) / 256), 256, 0, st>>>(
+      row_lse_all, col_lse_all, n_all, (int64_t)w.n_pad, row2, col2);
+  LATTE_LAUNCH_OK();
+
+  const bool tc = use_tc(dtype, dim, img_loc, ld_img_loc, txt_all, ld_txt_all, txt_loc,
+                         ld_txt_loc, img_all, ld_img_all);
+  const int ds_count = tc ? clip_tc_ds_count(n_loc, dim) : clip_simt_ds_count(n_loc);
+  if ((size_t)(2 * ds_count) > w.ds_cap) return LATTE_ERR_WORKSPACE;
+
+  ClipBwdArgs a;
+  a.dtype = dtype; a.n_loc = n_loc; a.n_all = n_all; a.dim = dim;
+  a.label_offset = label_offset; a.logit_scale = logit_scale;
+  a.grad_loss = grad_loss; a.grad_mult = grad_mult; a.cross_terms = cross_terms;
+  a.grad_dtype = grad_dtype; a.ld_dx = ld_grad; a.ds_count = ds_count;
+  // d_img = coef*s * G[loc rows, :] @ txt_all
+  a.x = img_loc; a.ldx = ld_img_loc; a.y = txt_all; a.ldy = ld_txt_all;
+  a.lse_a2 = row2; a.lse_b2 = col2; a.dx = d_img; a.ds_partial = ws + w.off_ds;
+  int rc = tc ? clip_bwd_rows_tc(a, st) : clip_bwd_rows_simt(a, st);
+  if (rc) return rc;
+  // d_txt = coef*s * G[:, loc cols]^T @ img_all  (rows of the transposed problem)
+  a.x = txt_loc; a.ldx = ld_txt_loc; a.y = img_all; a.ldy = ld_img_all;
+  a.lse_a2 = col2; a.lse_b2 = row2; a.dx = d_txt; a.ds_partial = ws + w.off_ds + ds_count;
+  rc = tc ? clip_bwd_rows_tc(a, st) : clip_bwd_rows_simt(a, st);
+  if (rc) return rc;
+  ds_reduce_kernel<<<1, 256, 0, st>>>(ws + w.off_ds, 2 * ds_count, grad_loss, grad_mult, n_loc,
+                                      d_scale);
+  LATTE_LAUNCH_OK();
+  return LATTE_OK;
+}

@@ -1,0 +1,88 @@
+// Shared declarations for the liblatte_b200 translation units.
+#pragma once
+
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/latte_b200.h"
+
+namespace latte {
+
+#define LATTE_CHECK_ARG(cond) \
+  do {                        \
+    if (!(cond)) return LATTE_ERR_BAD_ARG; \
+  } while (0)
+
+#define LATTE_CUDA_OK(expr)                          \
+  do {                                               \
+    cudaError_t _e = (expr);                         \
+    if (_e != cudaSuccess) return LATTE_ERR_CUDA;    \
+  } while (0)
+
+// Checked after every launch: cudaGetLastError does not synchronise.
+#define LATTE_LAUNCH_OK()                            \
+  do {                                               \
+    cudaError_t _e = cudaGetLastError();             \
+    if (_e != cudaSuccess) return LATTE_ERR_CUDA;    \
+  } while (0)
+
+inline size_t dtype_size(int dtype) { return dtype == LATTE_F32 ? 4 : 2; }
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+
+// --------------------------------------------------------------------------------------
+// Row kernels of ClipLoss.  "x" is the rank-local row operand [n_loc, dim], "y" the
+// gathered column operand [n_all, dim]; S = x @ y^T is never stored.
+// --------------------------------------------------------------------------------------
+struct ClipFwdArgs {
+  const void* x; int64_t ldx;
+  const void* y; int64_t ldy;
+  int dtype;
+  int64_t n_loc, n_all, dim;
+  int64_t label_offset;
+  const float* logit_scale;   // device scalar
+  // per-(split,row) partial online-softmax state in base-2 units of (s*log2e)*dot
+  float* part_max;            // [nparts, n_loc]
+  float* part_sum;            // [nparts, n_loc]
+  float* diag;                // [n_loc]  raw dot of the label pair (unscaled)
+  int nparts;                 // partial slots per row (tc: 2 * column splits, simt: 1)
+};
+
+struct ClipBwdArgs {
+  const void* x; int64_t ldx;
+  const void* y; int64_t ldy;
+  int dtype;
+  int64_t n_loc, n_all, dim;
+  int64_t label_offset;
+  const float* logit_scale;   // device scalar
+  const float* lse_a2;        // [n_all] base-2 LSE of the x side (indexed label_offset + i)
+  const float* lse_b2;        // [n_all] base-2 LSE of the y side (indexed j)
+  const float* grad_loss;     // device scalar
+  float grad_mult;
+  int cross_terms;
+  void* dx; int grad_dtype; int64_t ld_dx;
+  float* ds_partial;          // [ds_count] per-CTA partial sums of d loss / d s
+  int ds_count;
+};
+
+// tcgen05 path (bf16 / fp16 features).  Return LATTE_ERR_UNSUPPORTED when the shape
+// cannot run on it (the caller then reports the error; there is no silent fallback).
+int clip_fwd_rows_tc(const ClipFwdArgs& a, cudaStream_t stream);
+int clip_bwd_rows_tc(const ClipBwdArgs& a, cudaStream_t stream);
+int clip_tc_nparts(int64_t n_loc, int64_t n_all, int sm_count);
+int clip_tc_ds_count(int64_t n_loc, int64_t dim);
+bool clip_tc_supported(int dtype, int64_t dim, int64_t ldx, int64_t ldy, const void* x, const void* y);
+
+// fp32 SIMT path (fp32 features; exact fp32 products).
+int clip_fwd_rows_simt(const ClipFwdArgs& a, cudaStream_t stream);
+int clip_bwd_rows_simt(const ClipBwdArgs& a, cudaStream_t stream);
+int clip_simt_ds_count(int64_t n_loc);
+
+int device_sm_count();
+
+}  // namespace latte

@@ -1,0 +1,259 @@
+"""Drop-in for the ClipLoss part of open_clip's ``loss.py``.
+
+Mirrors the reference interface (same names, arguments, defaults and error behaviour):
+  * ``gather_features``  -- /root/reference/src/open_clip/loss.py:19-63
+  * ``ClipLoss``         -- loss.py:66-130 (``__init__`` :68-87, ``get_ground_truth`` :89-100,
+                            ``get_logits`` :102-118, ``forward`` :120-130)
+  * ``create_loss``      -- /root/reference/src/open_clip/factory.py:323-351 (ClipLoss branch)
+
+``ClipLoss.forward`` is the hot path: it never materialises the logit matrices.  It calls
+the CUDA extension (C ABI in include/latte_b200.h) through ``latteclip_b200._lib`` inside a
+``torch.autograd.Function``; the cross-rank exchange is one all-gather of the feature
+shards in forward and one all-gather of the two LSE vectors in backward (instead of the
+reference's reduce-scatter of [N, D] gradients, loss.py:49-50).  ``get_logits`` /
+``get_ground_truth`` remain as materialising utilities for subclasses
+(DistillClipLoss, loss.py:341-345); they are plain torch and not on the fused path.
+"""
+
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+try:
+    import torch.distributed as dist
+    has_distributed = True
+except ImportError:  # pragma: no cover
+    dist = None
+    has_distributed = False
+
+from . import _lib
+
+
+# ------------------------------------------------------------------------------------------
+# differentiable all-gather used by the materialising utility path (loss.py:49-50)
+# ------------------------------------------------------------------------------------------
+class _AllGatherWithGrad(torch.autograd.Function):
+    """all_gather whose backward is reduce-scatter(SUM), like torch.distributed.nn.all_gather."""
+
+    @staticmethod
+    def forward(ctx, x, group):
+        ctx.group = group
+        world = dist.get_world_size(group)
+        out = torch.empty((world * x.shape[0],) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+        dist.all_gather_into_tensor(out, x.contiguous(), group=group)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad):
+        world = dist.get_world_size(ctx.group)
+        rank = dist.get_rank(ctx.group)
+        grad = grad.contiguous()
+        n = grad.shape[0] // world
+        if dist.get_backend(ctx.group) == "nccl":
+            out = torch.empty((n,) + tuple(grad.shape[1:]), dtype=grad.dtype, device=grad.device)
+            dist.reduce_scatter_tensor(out, grad, op=dist.ReduceOp.SUM, group=ctx.group)
+        else:  # gloo has no reduce_scatter
+            dist.all_reduce(grad, op=dist.ReduceOp.SUM, group=ctx.group)
+            out = grad[rank * n:(rank + 1) * n].clone()
+        return out, None
+
+
+def _all_gather_cat(x: torch.Tensor, group=None) -> torch.Tensor:
+    world = dist.get_world_size(group)
+    out = torch.empty((world * x.shape[0],) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+    dist.all_gather_into_tensor(out, x.contiguous(), group=group)
+    return out
+
+
+def gather_features(
+        image_features,
+        text_features,
+        local_loss=False,
+        gather_with_grad=False,
+        rank=0,
+        world_size=1,
+        use_horovod=False
+):
+    """Same contract as the reference (loss.py:19-63): returns (all_image_features,
+    all_text_features), rank-major row order.  gather_with_grad=True keeps the autograd link
+    (backward = reduce-scatter); False gathers without grad and, unless local_loss, re-inserts
+    the grad-carrying local shard (loss.py:56-59)."""
+    assert has_distributed, 'torch.distributed did not import correctly, please use a PyTorch version with support.'
+    if use_horovod:
+        # the reference's horovod branch (loss.py:29-45) needs horovod, which this build does not ship
+        raise NotImplementedError("latteclip_b200: horovod gather is not supported; use torch.distributed")
+    if gather_with_grad:
+        all_image_features = _AllGatherWithGrad.apply(image_features, None)
+        all_text_features = _AllGatherWithGrad.apply(text_features, None)
+    else:
+        with torch.no_grad():
+            all_image_features = _all_gather_cat(image_features)
+            all_text_features = _all_gather_cat(text_features)
+        if not local_loss:
+            n = image_features.shape[0]
+            chunks_i = list(all_image_features.split(n, dim=0))
+            chunks_t = list(all_text_features.split(n, dim=0))
+            chunks_i[rank] = image_features
+            chunks_t[rank] = text_features
+            all_image_features = torch.cat(chunks_i, dim=0)
+            all_text_features = torch.cat(chunks_t, dim=0)
+    return all_image_features, all_text_features
+
+
+# ------------------------------------------------------------------------------------------
+# fused ClipLoss
+# ------------------------------------------------------------------------------------------
+class _FusedClipLoss(torch.autograd.Function):
+    """loss.py:102-130 fused.  Gradient contract:
+         local_loss & gather_with_grad : grads = d(sum_r L_r)/dx_local   (W x global-mean grad)
+         !local_loss & gather_with_grad: loss = L_global on every rank, same feature grads
+         !local_loss & !gather_with_grad: grads = 1 x local slice of dL_global
+         local_loss & !gather_with_grad : own-block terms only (gathered copies carry no grad)
+    """
+
+    @staticmethod
+    def forward(ctx, image_features, text_features, logit_scale, local_loss, gather_with_grad,
+                rank, world_size, group):
+        img = image_features.detach()
+        txt = text_features.detach()
+        if world_size > 1:
+            all_img = _all_gather_cat(img, group)
+            all_txt = _all_gather_cat(txt, group)
+            label_offset = rank * img.shape[0]
+        else:
+            all_img, all_txt, label_offset = img, txt, 0
+        row_lse, col_lse, loss = _lib.clip_fwd(img, txt, all_img, all_txt, label_offset, logit_scale)
+        loss = loss.reshape(())
+        if world_size > 1 and not local_loss:
+            # L_global = mean over ranks of the per-rank block losses (equal shard sizes)
+            loss = loss.clone()
+            dist.all_reduce(loss, op=dist.ReduceOp.SUM, group=group)
+            loss = loss / world_size
+        ctx.save_for_backward(img, txt, all_img, all_txt, logit_scale.detach(), row_lse, col_lse)
+        ctx.cfg = (local_loss, gather_with_grad, rank, world_size, group, label_offset)
+        ctx.scale_meta = (logit_scale.dtype, logit_scale.shape)
+        ctx.feat_dtypes = (image_features.dtype, text_features.dtype)
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        img, txt, all_img, all_txt, scale, row_lse, col_lse = ctx.saved_tensors
+        local_loss, gather_with_grad, rank, world_size, group, label_offset = ctx.cfg
+        if world_size > 1:
+            both = _all_gather_cat(torch.stack([row_lse, col_lse], dim=1), group)   # [N, 2]
+            row_all, col_all = both[:, 0].contiguous(), both[:, 1].contiguous()
+        else:
+            row_all, col_all = row_lse, col_lse
+        cross_terms = not (world_size > 1 and local_loss and not gather_with_grad)
+        grad_mult = 1.0
+        if world_size > 1 and not local_loss and not gather_with_grad:
+            grad_mult = 1.0 / world_size
+        d_img, d_txt, d_scale = _lib.clip_bwd(img, txt, all_img, all_txt, label_offset, scale,
+                                              row_all, col_all, grad_out, grad_mult, cross_terms)
+        if world_size > 1 and not local_loss:
+            # every rank differentiates the same L_global: d/ds is the rank mean of the block sums
+            d_scale = d_scale / grad_mult
+            dist.all_reduce(d_scale, op=dist.ReduceOp.SUM, group=group)
+            d_scale = d_scale / world_size
+        s_dtype, s_shape = ctx.scale_meta
+        d_scale = d_scale.reshape(s_shape).to(s_dtype)
+        need = ctx.needs_input_grad
+        return (d_img if need[0] else None, d_txt if need[1] else None,
+                d_scale if need[2] else None, None, None, None, None, None)
+
+
+class ClipLoss(nn.Module):
+
+    def __init__(
+            self,
+            local_loss=False,
+            gather_with_grad=False,
+            cache_labels=False,
+            rank=0,
+            world_size=1,
+            use_horovod=False,
+    ):
+        super().__init__()
+        self.local_loss = local_loss
+        self.gather_with_grad = gather_with_grad
+        self.cache_labels = cache_labels
+        self.rank = rank
+        self.world_size = world_size
+        self.use_horovod = use_horovod
+        self.group = None          # process group for the collectives (None = default group)
+
+        # cache state (kept for interface parity, loss.py:85-87)
+        self.prev_num_logits = 0
+        self.labels = {}
+
+    def get_ground_truth(self, device, num_logits) -> torch.Tensor:
+        # loss.py:89-100 -- on the fused path the label is implicit (column rank*n + i)
+        if self.prev_num_logits != num_logits or device not in self.labels:
+            labels = torch.arange(num_logits, device=device, dtype=torch.long)
+            if self.world_size > 1 and self.local_loss:
+                labels = labels + num_logits * self.rank
+            if self.cache_labels:
+                self.labels[device] = labels
+                self.prev_num_logits = num_logits
+        else:
+            labels = self.labels[device]
+        return labels
+
+    def get_logits(self, image_features, text_features, logit_scale):
+        # loss.py:102-118 -- materialising utility, NOT used by forward()
+        if self.world_size > 1:
+            all_image_features, all_text_features = gather_features(
+                image_features, text_features,
+                self.local_loss, self.gather_with_grad, self.rank, self.world_size, self.use_horovod)
+            if self.local_loss:
+                logits_per_image = logit_scale * image_features @ all_text_features.T
+                logits_per_text = logit_scale * text_features @ all_image_features.T
+            else:
+                logits_per_image = logit_scale * all_image_features @ all_text_features.T
+                logits_per_text = logits_per_image.T
+        else:
+            logits_per_image = logit_scale * image_features @ text_features.T
+            logits_per_text = logit_scale * text_features @ image_features.T
+        return logits_per_image, logits_per_text
+
+    def forward(self, image_features, text_features, logit_scale, output_dict=False):
+        if self.use_horovod:
+            raise NotImplementedError("latteclip_b200: horovod is not supported")
+        if image_features.shape != text_features.shape:
+            raise RuntimeError(
+                f"image_features {tuple(image_features.shape)} and text_features "
+                f"{tuple(text_features.shape)} must have the same shape")
+        if not torch.is_tensor(logit_scale):
+            logit_scale = torch.tensor(float(logit_scale), device=image_features.device)
+        # One compute dtype for both operands: the autocast dtype when autocast is on (the
+        # reference's matmuls run in it), otherwise the promoted dtype of the two inputs.
+        if torch.is_autocast_enabled():
+            cdt = torch.get_autocast_gpu_dtype()
+        else:
+            cdt = torch.promote_types(image_features.dtype, text_features.dtype)
+        if cdt not in (torch.float32, torch.bfloat16, torch.float16):
+            cdt = torch.float32
+        with torch.autocast(device_type="cuda", enabled=False):
+            total_loss = _FusedClipLoss.apply(
+                image_features.to(cdt), text_features.to(cdt), logit_scale,
+                self.local_loss, self.gather_with_grad, self.rank, self.world_size, self.group)
+        return {"contrastive_loss": total_loss} if output_dict else total_loss
+
+
+def create_loss(args):
+    """ClipLoss branch of the reference factory (factory.py:344-351).  CoCa / SigLIP /
+    distillation losses are outside the accelerated path and are not provided here."""
+    if "coca" in getattr(args, "model", "").lower() or getattr(args, "siglip", False) \
+            or getattr(args, "distill", False):
+        raise NotImplementedError(
+            "latteclip_b200.create_loss only provides ClipLoss; use the reference factory for "
+            "CoCa / SigLIP / distillation losses")
+    return ClipLoss(
+        local_loss=args.local_loss,
+        gather_with_grad=args.gather_with_grad,
+        cache_labels=True,
+        rank=args.rank,
+        world_size=args.world_size,
+        use_horovod=args.horovod,
+    )

@@ -1,0 +1,192 @@
+"""LatteCLIP's prototype / pseudo-label / mixture / EMA / memory-bank path as functions.
+
+The reference has no function boundary here: the code is inline in
+``train_one_epoch_v2`` (/root/reference/src/training/train.py:306-636) plus the helper
+``compute_text_weights`` (train.py:292-303).  This module defines the boundary
+(boundary #2).  Each function states the reference lines it replaces;
+all arithmetic runs in the CUDA extension through ``latteclip_b200._lib`` -- there is no
+PyTorch fallback.
+
+The memory bank is handled as one stacked fp32 tensor ``bank[C, D]`` in class order;
+``stack_bank`` / ``unstack_bank`` convert from / to the reference's
+``model.memory_bank`` ParameterDict (model.py:489-499) so checkpoints keep their format.
+"""
+
+from __future__ import annotations
+
+from typing import Dict, Iterable, Optional
+
+import torch
+import torch.nn as nn
+
+try:
+    import torch.distributed as dist
+except ImportError:  # pragma: no cover
+    dist = None
+
+from . import _lib
+
+
+# ------------------------------------------------------------------------------ bank storage
+def stack_bank(memory_bank, class_names: Iterable[str]) -> torch.Tensor:
+    """train.py:347-350 / :384-387: stack the per-class Parameters in class order."""
+    return torch.stack([memory_bank[c].detach() for c in class_names]).to(torch.float32).contiguous()
+
+
+def unstack_bank(bank: torch.Tensor, memory_bank, class_names: Iterable[str], touched=None):
+    """Write rows of the stacked bank back into the ParameterDict (train.py:529-530 assigns a
+    new tensor per touched class).  ``touched``: optional bool/float [C] mask (counts > 0)."""
+    mask = None if touched is None else (touched > 0).tolist()
+    for k, c in enumerate(class_names):
+        if mask is None or mask[k]:
+            memory_bank[c] = nn.Parameter(bank[k].clone())
+    return memory_bank
+
+
+# ------------------------------------------------------------------------------ kernels
+def build_classifier(bank: torch.Tensor) -> torch.Tensor:
+    """train.py:384-389 (and zero_shot.py:138-145): ``F.normalize(stack(bank), dim=1)``.
+    Returns P_hat [C, D] fp32 (the reference then uses ``P_hat.T``)."""
+    return _lib.normalize_rows(bank)
+
+
+def pseudo_label(image_features: torch.Tensor, classifier: torch.Tensor,
+                 scale: float = 100.0) -> torch.Tensor:
+    """train.py:410-411: ``(100.0 * image_features @ classifier).argmax(dim=1)`` with
+    ``classifier = P_hat.T``; here ``classifier`` is P_hat [C, D].  int64 [B]; the first
+    maximal index wins.  The [B, C] logits are never stored."""
+    am, _, _ = _lib.nxc_argmax_margin(image_features, classifier, scale=scale,
+                                      want_argmax=True, want_margin=False)
+    return am
+
+
+def text_margins(text_features: torch.Tensor, prototypes: torch.Tensor,
+                 row_index: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``compute_text_weights`` (train.py:292-303): top-1 minus top-2 of
+    ``text_features @ prototypes.T`` per row (its ``preds`` argument is unused by the
+    reference, train.py:301-303).  With ``row_index`` the rows are gathered first:
+    ``text_features[row_index]`` (class-name text features by label, train.py:420-438)."""
+    _, mg, _ = _lib.nxc_argmax_margin(text_features, prototypes, scale=1.0, row_index=row_index,
+                                      want_argmax=False, want_margin=True)
+    return mg
+
+
+def zero_shot_topk(image_features: torch.Tensor, classifier: torch.Tensor, k: int,
+                   scale: float = 100.0):
+    """zero_shot.py:40 + :14-20 / train.py:1352-1358: ``(100 * I @ classifier).topk(k)``
+    without storing the logits.  Returns (idx int64 [B, k], val fp32 [B, k])."""
+    return _lib.nxc_topk(image_features, classifier, k, scale=scale)
+
+
+class _MixEma(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, class_text, per_image, per_group, bank, preds, zs, w_lbl, w_lbl_zs, w_img,
+                w_grp, alpha, label_weight_axis):
+        t_ft, t_zs = _lib.mix_ema_fwd(class_text, per_image, per_group, bank, preds, zs, w_lbl,
+                                      w_lbl_zs, w_img, w_grp, alpha, label_weight_axis)
+        ctx.save_for_backward(preds, zs, w_lbl, w_lbl_zs, w_img, w_grp)
+        ctx.meta = (alpha, label_weight_axis, class_text.shape[0], class_text.dtype,
+                    bank.dtype)
+        return t_ft, t_zs
+
+    @staticmethod
+    def backward(ctx, d_t_ft, d_t_zs):
+        preds, zs, w_lbl, w_lbl_zs, w_img, w_grp = ctx.saved_tensors
+        alpha, axis, num_classes, ct_dtype, bank_dtype = ctx.meta
+        want_bank = ctx.needs_input_grad[3]
+        d_ct, d_pi, d_pg, d_bank = _lib.mix_ema_bwd(d_t_ft, d_t_zs, preds, zs, w_lbl, w_lbl_zs,
+                                                    w_img, w_grp, alpha, axis, num_classes,
+                                                    want_bank=want_bank)
+        return (d_ct.to(ct_dtype) if ctx.needs_input_grad[0] else None,
+                d_pi if ctx.needs_input_grad[1] else None,
+                d_pg if ctx.needs_input_grad[2] else None,
+                d_bank.to(bank_dtype) if want_bank else None,
+                None, None, None, None, None, None, None, None)
+
+
+def mix_and_ema(class_text: torch.Tensor, per_image: torch.Tensor, per_group: torch.Tensor,
+                bank: torch.Tensor, preds: torch.Tensor, zs: torch.Tensor,
+                w_lbl: torch.Tensor, w_lbl_zs: torch.Tensor, w_img: torch.Tensor,
+                w_grp: torch.Tensor, alpha: float, label_weight_axis: str = "row"):
+    """train.py:472-488 with the gathers of :420-431 fused:
+
+        L_ft = class_text[preds]; L_zs = class_text[zs]; M_ft = bank[preds]; M_zs = bank[zs]
+        T_ft = M_ft + alpha * ((w_lbl (*) L_ft + w_img*P + w_grp*G) / (w_lbl    + w_img + w_grp) - M_ft)
+        T_zs = M_zs + alpha * ((w_lbl (*) L_zs + w_img*P + w_grp*G) / (w_lbl_zs + w_img + w_grp) - M_zs)
+
+    ``label_weight_axis="quirk"`` is the reference's literal broadcast (needs B == D,
+    train.py:476); ``"row"`` is ``w_lbl[:, None]``.  Differentiable w.r.t. class_text,
+    per_image, per_group (and bank, if it requires grad); the weights are detached in the
+    reference (train.py:444-449)."""
+    if label_weight_axis not in ("row", "quirk"):
+        raise ValueError(label_weight_axis)
+    if label_weight_axis == "quirk" and per_image.shape[0] != per_image.shape[1]:
+        # same failure the reference expression produces when B != D
+        raise RuntimeError(
+            f"The size of tensor a ({per_image.shape[0]}) must match the size of tensor b "
+            f"({per_image.shape[1]}) at non-singleton dimension 1")
+    return _MixEma.apply(class_text, per_image, per_group, bank, preds, zs,
+                         w_lbl.detach(), w_lbl_zs.detach(), w_img.detach(), w_grp.detach(),
+                         float(alpha), label_weight_axis)
+
+
+@torch.no_grad()
+def update_bank(bank: torch.Tensor, preds: torch.Tensor, zs: torch.Tensor,
+                t_ft: torch.Tensor, t_zs: torch.Tensor, group=None, world_size: int = 1):
+    """train.py:508-530: for every class c touched by the batch
+    ``bank[c] = normalize((sum_{zs_i=c} T_zs[i] + sum_{preds_i=c} T_ft[i]) / count_c)``; other
+    rows unchanged.  ``bank`` (fp32 [C, D], contiguous) is updated in place; returns
+    (bank, counts).  With world_size > 1 the per-class sums and counts are all-reduced first,
+    so every rank ends with the bank a single process would compute on the concatenated batch
+    (the reference loop is single-process only)."""
+    sums, counts = _lib.bank_accumulate(t_ft, t_zs, preds, zs, bank.shape[0])
+    if world_size > 1:
+        packed = torch.cat([sums, counts[:, None]], dim=1)
+        dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=group)
+        sums, counts = packed[:, :-1].contiguous(), packed[:, -1].contiguous()
+    _lib.bank_finalize(sums, counts, bank)
+    return bank, counts
+
+
+def prototype_step(image_features: torch.Tensor,
+                   logit_scale: torch.Tensor,
+                   bank: torch.Tensor,
+                   proto_snapshot: torch.Tensor,
+                   zs: torch.Tensor,
+                   class_text: torch.Tensor,
+                   per_image: torch.Tensor,
+                   per_group: torch.Tensor,
+                   loss_fn,
+                   alpha: float = 0.01,
+                   use_image_caption: float = 1.0,
+                   use_batch_caption: float = 1.0,
+                   use_template_caption: float = 1.0,
+                   use_zeroshot_pseudolabel: float = 1.0,
+                   use_finetune_pseudolabel: float = 1.0,
+                   label_weight_axis: str = "row") -> Dict[str, torch.Tensor]:
+    """The hot path of one ``train_one_epoch_v2`` iteration (train.py:384-504), steps 1-8 of
+    SURVEY.md appendix A.  ``class_text[c]`` is the text feature of class c's label template
+    (the reference re-encodes it per sample, train.py:433-438; the values are identical).
+    Returns the loss dict of the reference (keys ``contrastive_loss``, ``zeroshot``, ``loss``,
+    train.py:491-504) plus ``preds``, ``t_ft``, ``t_zs`` and the weights.  Call
+    ``out["loss"].backward()`` and then ``update_bank`` (train.py:506-530)."""
+    classifier = build_classifier(bank)                                         # :384-389
+    preds = pseudo_label(image_features, classifier, 100.0)                     # :410-411
+    # margins against the epoch-start snapshot (:347-350), weights detached (:444-449)
+    w_img = (text_margins(per_image, proto_snapshot) + 1e-6) * use_image_caption        # :444,:463
+    w_grp = (text_margins(per_group, proto_snapshot) + 1e-6) * use_batch_caption        # :445,:460
+    cls_margin = text_margins(class_text, proto_snapshot)        # one margin per class, gathered below
+    w_lbl = (cls_margin[preds] + 1e-6) * use_template_caption                   # :448,:468
+    w_lbl_zs = (cls_margin[zs] + 1e-6) * use_template_caption                   # :449,:469
+    t_ft, t_zs = mix_and_ema(class_text, per_image, per_group, bank, preds, zs,
+                             w_lbl, w_lbl_zs, w_img, w_grp, alpha, label_weight_axis)   # :472-488
+    losses = loss_fn(image_features=image_features, text_features=t_ft,
+                     logit_scale=logit_scale, output_dict=True)                 # :491-494
+    losses_zs = loss_fn(image_features=image_features, text_features=t_zs,
+                        logit_scale=logit_scale, output_dict=True)              # :496-499
+    losses["zeroshot"] = sum(losses_zs.values()) * use_zeroshot_pseudolabel     # :501
+    total = sum(losses.values()) * use_finetune_pseudolabel                     # :502
+    losses["loss"] = total                                                      # :504
+    losses.update(preds=preds, t_ft=t_ft, t_zs=t_zs, w_img=w_img, w_grp=w_grp,
+                  w_lbl=w_lbl, w_lbl_zs=w_lbl_zs)
+    return losses

@@ -1,0 +1,72 @@
+"""CPU-only checks of the C-ABI boundary: the shared library builds, loads without a GPU
+and exports exactly the symbols include/latte_b200.h declares."""
+
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from latteclip_b200 import _lib
+    _lib.build()
+    return _lib.load()
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "latte_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(latte_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_are_exported(lib):
+    syms = declared_symbols()
+    assert len(syms) >= 13
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in latte_b200.h but not exported"
+
+
+def test_python_binding_covers_header():
+    from latteclip_b200 import _lib
+    assert sorted(_lib.EXPORTS) == declared_symbols()
+
+
+def test_version_and_status_strings(lib):
+    assert b"sm_100a" in lib.latte_version()
+    assert lib.latte_status_string(0) == b"ok"
+    for code in (-1, -2, -3, -4, -5):
+        assert len(lib.latte_status_string(code)) > 3
+
+
+def test_bad_arguments_are_rejected_without_a_gpu(lib):
+    n = ctypes.c_size_t(0)
+    assert lib.latte_clip_workspace_bytes(0, 0, 512, 1, ctypes.byref(n)) == -1
+    assert lib.latte_clip_workspace_bytes(256, 256, 512, 7, ctypes.byref(n)) == -1
+    assert lib.latte_clip_workspace_bytes(256, 1024, 512, 1, ctypes.byref(n)) == 0
+    assert n.value > 0
+    # null pointers never reach a kernel launch
+    assert lib.latte_normalize_rows(None, 512, None, 512, 4, 512, None) == -1
+    assert lib.latte_clip_fwd(None, 0, None, 0, None, 0, None, 0, 1, 1, 1, 1, 0,
+                              None, None, None, None, None, 0, None) == -1
+
+
+def test_product_path_has_no_cpu_fallback():
+    import torch
+    import latteclip_b200 as lb
+    loss = lb.ClipLoss()
+    x = torch.randn(8, 16)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        loss(x, x, torch.tensor(10.0))
+
+
+def test_product_code_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "latteclip_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src, f

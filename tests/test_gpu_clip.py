@@ -1,0 +1,241 @@
+"""GPU parity tests for the fused ClipLoss (through the Python drop-in, which calls the C
+ABI).  Oracle = oracle/ (CPU) and the golden fixtures produced by the unmodified reference.
+
+Tolerances (BASELINE.json north_star / SURVEY.md 8d):
+  * fp32 features:            loss rel <= 1e-5, grads rel <= 1e-5
+  * bf16 / fp16 features:     loss rel <= 1e-5 (vs the fp64 oracle fed the same rounded
+                              inputs; 2e-5 abs floor), grads rel <= 2e-3
+"""
+
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+LOSS_RTOL = 1e-5
+GRAD_RTOL_16 = 2e-3
+GRAD_RTOL_32 = 1e-5
+
+
+def rel(a, b):
+    a = torch.as_tensor(np.asarray(a.detach().cpu() if torch.is_tensor(a) else a), dtype=torch.float64)
+    b = torch.as_tensor(np.asarray(b.detach().cpu() if torch.is_tensor(b) else b), dtype=torch.float64)
+    return float((a - b).norm() / b.norm().clamp_min(1e-300))
+
+
+def synth(n, d, sigma, seed, jitter=0.0):
+    g = torch.Generator().manual_seed(seed)
+    i = F.normalize(torch.randn(n, d, generator=g), dim=1)
+    t = F.normalize(i + sigma * torch.randn(n, d, generator=g) / math.sqrt(d), dim=1)
+    if jitter:
+        t = t * (1.0 - jitter * torch.rand(n, 1, generator=g))
+    return i, t
+
+
+def run_ours(i, t, scale, dtype, **kw):
+    import latteclip_b200 as lb
+    dev = torch.device("cuda:0")
+    il = i.to(dev).to(dtype).requires_grad_(True)
+    tl = t.to(dev).to(dtype).requires_grad_(True)
+    log_s = torch.tensor(math.log(scale), device=dev, dtype=torch.float32, requires_grad=True)
+    s = log_s.exp()
+    s.retain_grad()
+    out = lb.ClipLoss(cache_labels=True, **kw)(il, tl, s, output_dict=True)
+    assert list(out.keys()) == ["contrastive_loss"]
+    loss = out["contrastive_loss"]
+    assert loss.dim() == 0 and loss.dtype == torch.float32
+    loss.backward()
+    torch.cuda.synchronize()
+    return loss.detach(), il.grad, tl.grad, s.grad, il.detach(), tl.detach()
+
+
+def oracle_on(il, tl, scale, dtype=torch.float64):
+    from oracle.clip_loss import clip_loss_all_ranks
+    losses, di, dt, ds = clip_loss_all_ranks([il.float().cpu()], [tl.float().cpu()], scale,
+                                             False, False, dtype)
+    return losses[0], di[0], dt[0], ds[0]
+
+
+# ------------------------------------------------------------------ fp32 (SIMT path) vs goldens
+@pytest.mark.parametrize("name", ["small_s100", "small_s14", "ragged_s100", "cfg1_s100"])
+def test_fp32_matches_reference_golden(name):
+    g = load_golden(f"clip_w1_{name}.npz")
+    i, t, s = torch.from_numpy(g["I"]), torch.from_numpy(g["T"]), float(g["scale"])
+    loss, di, dt, ds, _, _ = run_ours(i, t, s, torch.float32)
+    ref = float(g["loss_f64"])
+    assert abs(float(loss) - ref) <= LOSS_RTOL * max(abs(ref), 1.0), (float(loss), ref)
+    assert rel(di, g["dI_f64"]) < GRAD_RTOL_32
+    assert rel(dt, g["dT_f64"]) < GRAD_RTOL_32
+    assert abs(float(ds) - float(g["ds_f64"])) <= 2e-4 * abs(float(g["ds_f64"])) + 1e-7
+
+
+# ------------------------------------------------------------------ bf16 / fp16 (tcgen05 path)
+TC_CASES = [
+    # n, d, sigma, scale, jitter
+    (128, 64, 3.0, 100.0, 0.0),
+    (256, 512, 4.0, 100.0, 0.005),      # BASELINE config 1 shape, non-unit text
+    (384, 512, 2.0, 1.0 / 0.07, 0.0),
+    (200, 200, 3.0, 100.0, 0.0),        # ragged rows and ragged feature tail
+    (1000, 768, 4.0, 100.0, 0.005),     # ViT-L width, rows not a tile multiple
+    (4096, 512, 4.0, 100.0, 0.005),
+]
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("case", TC_CASES)
+def test_tensor_core_path_matches_oracle(case, dtype):
+    n, d, sigma, scale, jitter = case
+    i, t = synth(n, d, sigma, 1000 + n + d, jitter)
+    loss, di, dt, ds, il, tl = run_ours(i, t, scale, dtype)
+    assert di.dtype == dtype and dt.dtype == dtype
+    rl, rdi, rdt, rds = oracle_on(il, tl, scale)
+    assert abs(float(loss) - float(rl)) <= LOSS_RTOL * abs(float(rl)) + 2e-5, (float(loss), float(rl))
+    assert rel(di, rdi) < GRAD_RTOL_16
+    assert rel(dt, rdt) < GRAD_RTOL_16
+    assert abs(float(ds) - float(rds)) <= 2e-3 * abs(float(rds)) + 1e-6
+
+
+def test_tensor_core_path_matches_reference_golden_inputs():
+    """Golden inputs rounded to bf16; compare with the reference's fp64 result on fp32 inputs
+    at bf16-input accuracy, and with the oracle on the rounded inputs at full accuracy."""
+    g = load_golden("clip_w1_cfg1_s100.npz")
+    i, t, s = torch.from_numpy(g["I"]), torch.from_numpy(g["T"]), float(g["scale"])
+    loss, di, dt, ds, il, tl = run_ours(i, t, s, torch.bfloat16)
+    rl, rdi, rdt, rds = oracle_on(il, tl, s)
+    assert abs(float(loss) - float(rl)) <= LOSS_RTOL * abs(float(rl)) + 2e-5
+    assert rel(di, rdi) < GRAD_RTOL_16 and rel(dt, rdt) < GRAD_RTOL_16
+    assert rel(di, g["dI_f64"]) < 0.1 and abs(float(loss) - float(g["loss_f64"])) < 0.05
+
+
+# ------------------------------------------------------------------ rank blocks (C-ABI semantics)
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("local_loss,gwg", [(True, True), (True, False), (False, True), (False, False)])
+def test_rank_block_semantics_match_gloo_reference(world, local_loss, gwg, dtype):
+    """Each rank's call of the C ABI, emulated on one GPU (rank r passes its shard as the local
+    operand and the full batch as the gathered operand), combined with the same host rules the
+    ClipLoss module applies, against the real gloo run of the reference (golden)."""
+    from latteclip_b200 import _lib
+    g = load_golden(f"clip_dist_w{world}.npz")
+    dev = torch.device("cuda:0")
+    i_all = torch.from_numpy(g["I"]).float().to(dev).to(dtype)
+    t_all = torch.from_numpy(g["T"]).float().to(dev).to(dtype)
+    scale = torch.tensor(float(g["scale"]), device=dev)
+    n = i_all.shape[0] // world
+    key = f"ll{int(local_loss)}_gwg{int(gwg)}"
+    if dtype == torch.float32:
+        ref = {r: {k: g[f"{key}_r{r}_{k}"] for k in ("loss", "dI", "dT", "ds")} for r in range(world)}
+        ltol, gtol = 1e-5, 1e-5
+    else:
+        from oracle.clip_loss import clip_loss_all_ranks
+        ish = [i_all[r * n:(r + 1) * n].float().cpu() for r in range(world)]
+        tsh = [t_all[r * n:(r + 1) * n].float().cpu() for r in range(world)]
+        lo, di, dt, ds = clip_loss_all_ranks(ish, tsh, float(g["scale"]), local_loss, gwg)
+        ref = {r: dict(loss=lo[r], dI=di[r], dT=dt[r], ds=ds[r]) for r in range(world)}
+        ltol, gtol = 1e-5, 2e-3
+    fw = [_lib.clip_fwd(i_all[r * n:(r + 1) * n], t_all[r * n:(r + 1) * n], i_all, t_all, r * n, scale)
+          for r in range(world)]
+    row_all = torch.cat([f[0] for f in fw])
+    col_all = torch.cat([f[1] for f in fw])
+    block_losses = torch.cat([f[2] for f in fw])
+    one = torch.ones(1, device=dev)
+    cross = not (local_loss and not gwg)
+    mult = 1.0 / world if (not local_loss and not gwg) else 1.0
+    bw = [_lib.clip_bwd(i_all[r * n:(r + 1) * n], t_all[r * n:(r + 1) * n], i_all, t_all, r * n, scale,
+                        row_all, col_all, one, mult, cross) for r in range(world)]
+    ds_blocks = torch.cat([b[2] for b in bw]) / mult
+    for r in range(world):
+        loss_r = block_losses[r] if local_loss else block_losses.mean()
+        ds_r = ds_blocks[r] if local_loss else ds_blocks.mean()
+        rl = float(np.asarray(ref[r]["loss"]))
+        assert abs(float(loss_r) - rl) <= ltol * abs(rl) + 2e-5
+        assert rel(bw[r][0], ref[r]["dI"]) < gtol
+        assert rel(bw[r][1], ref[r]["dT"]) < gtol
+        rds = float(np.asarray(ref[r]["ds"]))
+        assert abs(float(ds_r) - rds) <= 2e-3 * abs(rds) + 1e-6
+
+
+# ------------------------------------------------------------------ interface behaviour
+def test_positional_call_and_shape_errors():
+    import latteclip_b200 as lb
+    dev = torch.device("cuda:0")
+    i, t = synth(64, 64, 2.0, 5)
+    loss_fn = lb.ClipLoss()
+    a = loss_fn(i.to(dev), t.to(dev), torch.tensor(20.0, device=dev))
+    b = loss_fn(image_features=i.to(dev), text_features=t.to(dev), logit_scale=torch.tensor(20.0, device=dev),
+                output_dict=True)["contrastive_loss"]
+    assert torch.equal(a, b)
+    with pytest.raises(RuntimeError):
+        loss_fn(i.to(dev), t[:32].to(dev), torch.tensor(20.0, device=dev))
+    assert len(list(loss_fn.parameters())) == 0
+
+
+def test_get_logits_and_ground_truth_utilities():
+    import latteclip_b200 as lb
+    dev = torch.device("cuda:0")
+    i, t = synth(32, 16, 2.0, 6)
+    m = lb.ClipLoss(cache_labels=True)
+    li, lt = m.get_logits(i.to(dev), t.to(dev), torch.tensor(10.0, device=dev))
+    assert torch.allclose(li, 10.0 * i.to(dev) @ t.to(dev).T, atol=1e-4)
+    assert torch.allclose(lt, li.T, atol=1e-4)
+    assert torch.equal(m.get_ground_truth(dev, 32), torch.arange(32, device=dev))
+
+
+def test_autocast_uses_half_precision_kernels():
+    import latteclip_b200 as lb
+    dev = torch.device("cuda:0")
+    i, t = synth(256, 128, 3.0, 8)
+    il = i.to(dev).requires_grad_(True)
+    tl = t.to(dev).requires_grad_(True)
+    s = torch.tensor(50.0, device=dev, requires_grad=True)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        loss = lb.ClipLoss()(il, tl, s)
+    loss.backward()
+    assert il.grad.dtype == torch.float32 and s.grad is not None
+    rl, rdi, _, _ = oracle_on(il.detach().bfloat16(), tl.detach().bfloat16(), 50.0)
+    assert abs(float(loss) - float(rl)) <= 1e-5 * abs(float(rl)) + 2e-5
+    assert rel(il.grad, rdi) < 5e-3
+
+
+# ------------------------------------------------------------------ BASELINE size, properties
+def test_full_size_32k_properties():
+    """N = 32768, D = 512 (BASELINE.json metric size): size-independent checks.
+      (1) Euler identity: S is bilinear, so s*dL/ds == sum(dI*I) == sum(dT*T);
+      (2) a 256-row sample of the loss terms and gradients against plain torch fp32 on the GPU;
+      (3) lse >= positive logit for every row."""
+    import latteclip_b200 as lb
+    from latteclip_b200 import _lib
+    dev = torch.device("cuda:0")
+    n, d, scale = 32768, 512, 100.0
+    i, t = synth(n, d, 4.0, 99, 0.005)
+    loss, di, dt, ds, il, tl = run_ours(i, t, scale, torch.bfloat16)
+    e_i = float((di.float() * il.float()).sum())
+    e_t = float((dt.float() * tl.float()).sum())
+    assert abs(e_i - scale * float(ds)) <= 5e-3 * abs(e_i) + 1e-5
+    assert abs(e_t - scale * float(ds)) <= 5e-3 * abs(e_t) + 1e-5
+    # sampled rows vs torch
+    rows = torch.arange(0, n, n // 256, device=dev)[:256]
+    If, Tf = il.float(), tl.float()
+    S_r = scale * If[rows] @ Tf.T                  # rows of logits_per_image
+    S_c = scale * Tf[rows] @ If.T                  # rows of logits_per_text
+    row_lse, col_lse, loss2 = _lib.clip_fwd(il, tl, il, tl, 0, torch.tensor(scale, device=dev))
+    assert torch.allclose(row_lse[rows], torch.logsumexp(S_r, 1), rtol=0, atol=2e-4)
+    assert torch.allclose(col_lse[rows], torch.logsumexp(S_c, 1), rtol=0, atol=2e-4)
+    assert abs(float(loss2) - float(loss)) < 1e-6
+    diag = scale * (If * Tf).sum(1)
+    assert bool((row_lse >= diag - 1e-3).all()) and bool((col_lse >= diag - 1e-3).all())
+    full = (torch.logsumexp(S_r, 1) - diag[rows] + torch.logsumexp(S_c, 1) - diag[rows]).mean() / 2
+    # sampled gradient rows: dI_i = s/(2n) * sum_j (P_row_ij + P_col_ij - 2 delta_ij) T_j
+    P_row = torch.exp(S_r - row_lse[rows][:, None])
+    P_col = torch.exp(S_r - col_lse[None, :])
+    G = P_row + P_col
+    G[torch.arange(256, device=dev), rows] -= 2.0
+    dI_ref = scale / (2 * n) * G @ Tf
+    assert rel(di[rows], dI_ref) < GRAD_RTOL_16
+    assert math.isfinite(float(full))

@@ -1,0 +1,228 @@
+"""GPU parity tests for the prototype / pseudo-label / mixture / EMA / bank kernels, against
+the CPU oracle and the golden fixtures recorded from the unmodified train_one_epoch_v2."""
+
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def rel(a, b):
+    a = torch.as_tensor(np.asarray(a.detach().cpu() if torch.is_tensor(a) else a), dtype=torch.float64)
+    b = torch.as_tensor(np.asarray(b.detach().cpu() if torch.is_tensor(b) else b), dtype=torch.float64)
+    return float((a - b).norm() / b.norm().clamp_min(1e-300))
+
+
+def proto_inputs(b, d, c, seed):
+    g = torch.Generator().manual_seed(seed)
+    bank = F.normalize(torch.randn(c, d, generator=g), dim=1)
+    cls_text = F.normalize(bank + 0.9 * torch.randn(c, d, generator=g) / math.sqrt(d), dim=1)
+    true_cls = torch.randint(0, c, (b,), generator=g)
+    img = F.normalize(bank[true_cls] + 3.0 * torch.randn(b, d, generator=g) / math.sqrt(d), dim=1)
+    pimg = F.normalize(bank[true_cls] + 2.0 * torch.randn(b, d, generator=g) / math.sqrt(d), dim=1)
+    pgrp = F.normalize(bank[true_cls] + 1.5 * torch.randn(b, d, generator=g) / math.sqrt(d), dim=1)
+    zs = torch.where(torch.rand(b, generator=g) < 0.7, true_cls, torch.randint(0, c, (b,), generator=g))
+    return bank, cls_text, img, pimg, pgrp, zs
+
+
+# ------------------------------------------------------------------ K7: classifier
+@pytest.mark.parametrize("c,d", [(47, 512), (397, 768), (10, 33)])
+def test_build_classifier(c, d):
+    from latteclip_b200 import prototypes as P
+    import oracle
+    x = torch.randn(c, d) * 3
+    got = P.build_classifier(x.to(DEV))
+    assert rel(got, oracle.build_classifier(x)) < 1e-6
+
+
+# ------------------------------------------------------------------ K8: pseudo-labels (bit exact)
+@pytest.mark.parametrize("b,c,d", [(1000, 100, 512), (10000, 397, 512), (5000, 1000, 768), (100000, 100, 512)])
+def test_pseudo_labels_bit_exact_outside_ties(b, c, d):
+    """BASELINE config 5.  A row counts as a tie when its fp64 top-1/top-2 gap is <= tau
+    (tau = 1e-6 * scale); everywhere else the labels must be identical."""
+    from latteclip_b200 import prototypes as P
+    bank, _, img, _, _, _ = proto_inputs(b, d, c, 31 + c)
+    clf = F.normalize(bank, dim=1)
+    got = P.pseudo_label(img.to(DEV), clf.to(DEV), 100.0).cpu()
+    logits = 100.0 * img.double() @ clf.double().T
+    top2 = logits.topk(2, dim=1)
+    ref = top2.indices[:, 0]
+    gap = top2.values[:, 0] - top2.values[:, 1]
+    clear = gap > 1e-6 * 100.0
+    assert got.dtype == torch.int64
+    assert torch.equal(got[clear], ref[clear]), int((got[clear] != ref[clear]).sum())
+    assert int((~clear).sum()) <= max(3, b // 1000)
+
+
+def test_pseudo_labels_exact_ties_pick_lowest_index():
+    """Duplicate prototype rows and 4-bit quantised features force exact ties."""
+    from latteclip_b200 import prototypes as P
+    g = torch.Generator().manual_seed(3)
+    c, d, b = 64, 128, 2048
+    clf = (torch.randint(-8, 8, (c, d), generator=g).float() / 8.0)
+    clf[40] = clf[7]
+    clf[63] = clf[7]
+    clf[21] = clf[20]
+    img = torch.randint(-8, 8, (b, d), generator=g).float() / 8.0     # products exact in fp32
+    got = P.pseudo_label(img.to(DEV), clf.to(DEV), 100.0).cpu()
+    ref = (100.0 * img @ clf.T).argmax(dim=1)
+    assert torch.equal(got, ref)
+    assert not bool(((got == 40) | (got == 63) | (got == 21)).any())
+    # bf16 / fp16 inputs hold these values exactly as well
+    for dt in (torch.bfloat16, torch.float16):
+        assert torch.equal(P.pseudo_label(img.to(DEV).to(dt), clf.to(DEV), 100.0).cpu(), ref)
+
+
+def test_topk_matches_torch():
+    from latteclip_b200 import prototypes as P
+    bank, _, img, _, _, _ = proto_inputs(3000, 512, 397, 77)
+    clf = F.normalize(bank, dim=1)
+    idx, val = P.zero_shot_topk(img.to(DEV), clf.to(DEV), 10, 100.0)
+    ref = (100.0 * img.double() @ clf.double().T).topk(10, dim=1)
+    assert idx.shape == (3000, 10)
+    match = (idx.cpu() == ref.indices).float().mean()
+    assert float(match) > 0.999
+    assert torch.allclose(val.cpu().double(), ref.values, atol=2e-4)
+    # top-1 column equals the argmax kernel
+    assert torch.equal(idx[:, 0], P.pseudo_label(img.to(DEV), clf.to(DEV), 100.0))
+
+
+# ------------------------------------------------------------------ K9: margins
+def test_text_margins_match_compute_text_weights_golden():
+    from latteclip_b200 import prototypes as P
+    g = load_golden("text_margins.npz")
+    x, p = torch.from_numpy(g["X"]), torch.from_numpy(g["P"])
+    got = P.text_margins(x.to(DEV), p.to(DEV)).cpu()
+    # cancellation-sensitive: compare at fp32 dot-product accuracy
+    assert torch.allclose(got.double(), torch.from_numpy(g["margin_f64"]), atol=5e-7, rtol=0)
+    idx = torch.randint(0, x.shape[0], (500,))
+    got_g = P.text_margins(x.to(DEV), p.to(DEV), row_index=idx.to(DEV)).cpu()
+    assert torch.equal(got_g, got[idx])
+
+
+# ------------------------------------------------------------------ K10: mixture + EMA
+@pytest.mark.parametrize("axis,b,d,c", [("row", 256, 512, 47), ("quirk", 512, 512, 47),
+                                         ("row", 1000, 768, 397), ("row", 37, 50, 5)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_mix_and_ema_forward_backward(axis, b, d, c, dtype):
+    from latteclip_b200 import prototypes as P
+    import oracle
+    bank, cls_text, _, pimg, pgrp, zs = proto_inputs(b, d, c, 5 + b)
+    g = torch.Generator().manual_seed(b)
+    preds = torch.randint(0, c, (b,), generator=g)
+    w = [torch.rand(b, generator=g) * 0.3 + 1e-3 for _ in range(4)]
+    alpha = 0.01
+
+    def leaf(x):
+        return x.to(DEV).to(dtype).requires_grad_(True)
+    ct, pi, pg = leaf(cls_text), leaf(pimg), leaf(pgrp)
+    t_ft, t_zs = P.mix_and_ema(ct, pi, pg, bank.to(DEV), preds.to(DEV), zs.to(DEV),
+                               *[x.to(DEV) for x in w], alpha, axis)
+    gf = torch.randn(b, d, generator=g)
+    gz = torch.randn(b, d, generator=g)
+    (t_ft.float() * gf.to(DEV) + t_zs.float() * gz.to(DEV)).sum().backward()
+
+    def cl(x):
+        return x.detach().float().cpu().double().requires_grad_(True)
+    ct_c, pi_c, pg_c = cl(ct), cl(pi), cl(pg)
+    r_ft, r_zs = oracle.mix_and_ema(ct_c[preds], ct_c[zs], pi_c, pg_c, w[0].double(), w[1].double(),
+                                    w[2].double(), w[3].double(), bank.double()[preds],
+                                    bank.double()[zs], alpha, axis)
+    # the CUDA path receives the upstream gradient rounded to `dtype`
+    gf_r = gf.to(dtype).double() if dtype != torch.float32 else gf.double()
+    gz_r = gz.to(dtype).double() if dtype != torch.float32 else gz.double()
+    (r_ft * gf_r + r_zs * gz_r).sum().backward()
+    ftol = 2e-6 if dtype == torch.float32 else 4e-3
+    gtol = 1e-5 if dtype == torch.float32 else 8e-3
+    assert rel(t_ft, r_ft) < ftol and rel(t_zs, r_zs) < ftol
+    assert rel(pi.grad, pi_c.grad) < gtol and rel(pg.grad, pg_c.grad) < gtol
+    assert rel(ct.grad, ct_c.grad) < gtol
+
+
+def test_quirk_axis_requires_square_batch():
+    from latteclip_b200 import prototypes as P
+    bank, cls_text, _, pimg, pgrp, zs = proto_inputs(64, 32, 5, 1)
+    w = torch.rand(64).to(DEV)
+    with pytest.raises(RuntimeError, match="must match the size"):
+        P.mix_and_ema(cls_text.to(DEV), pimg.to(DEV), pgrp.to(DEV), bank.to(DEV), zs.to(DEV), zs.to(DEV),
+                      w, w, w, w, 0.01, "quirk")
+
+
+# ------------------------------------------------------------------ K11: bank update
+@pytest.mark.parametrize("b,d,c", [(512, 512, 47), (8192, 768, 397), (100, 64, 300)])
+def test_update_bank(b, d, c):
+    from latteclip_b200 import prototypes as P
+    import oracle
+    bank, _, _, pimg, pgrp, zs = proto_inputs(b, d, c, 11 + b)
+    g = torch.Generator().manual_seed(b)
+    preds = torch.randint(0, c, (b,), generator=g)
+    t_ft, t_zs = pimg * 0.995, pgrp * 0.996
+    bank_g = bank.to(DEV).clone()
+    _, counts = P.update_bank(bank_g, preds.to(DEV), zs.to(DEV), t_ft.to(DEV), t_zs.to(DEV))
+    ref = oracle.update_bank(bank, preds, zs, t_ft, t_zs)
+    assert rel(bank_g, ref) < 1e-6
+    touched = (torch.bincount(preds, minlength=c) + torch.bincount(zs, minlength=c)) > 0
+    assert torch.equal(counts.cpu() > 0, touched)
+    # untouched rows are bit-identical
+    assert torch.equal(bank_g.cpu()[~touched], bank[~touched])
+
+
+# ------------------------------------------------------------------ full step vs the real train loop
+@pytest.mark.parametrize("name", ["b32_c7", "b64_c10", "b64_c10_flags"])
+def test_prototype_step_matches_train_one_epoch_v2_golden(name):
+    """fp32 features, quirk axis (B == D): every output of our step against what the unmodified
+    reference loop produced (tests/golden/make_golden.py)."""
+    import latteclip_b200 as lb
+    from latteclip_b200 import prototypes as P
+    g = load_golden(f"proto_step_{name}.npz")
+    nb = int(g["nb"])
+    flags = [float(f) for f in g["flags"]]
+    scale, alpha = float(g["scale"]), float(g["alpha"])
+    bank = torch.from_numpy(g["bank0"]).float().to(DEV).contiguous()
+    snapshot = bank.clone()
+    loss_fn = lb.ClipLoss(local_loss=True, gather_with_grad=True, cache_labels=True)
+    for b in range(nb):
+        def leaf(x):
+            return torch.from_numpy(np.asarray(x)).float().to(DEV).requires_grad_(True)
+        img, cls_text = leaf(g["img"][b]), leaf(g["cls_text"])
+        pimg, pgrp = leaf(g["pimg"][b]), leaf(g["pgrp"][b])
+        log_s = torch.tensor(math.log(scale), device=DEV, requires_grad=True)
+        zs = torch.from_numpy(g["zs"][b]).to(DEV)
+        out = P.prototype_step(img, log_s.exp(), bank, snapshot, zs, cls_text, pimg, pgrp, loss_fn,
+                               alpha=alpha, use_image_caption=flags[0], use_batch_caption=flags[1],
+                               use_template_caption=flags[2], use_zeroshot_pseudolabel=flags[3],
+                               use_finetune_pseudolabel=flags[4], label_weight_axis="quirk")
+        out["loss"].backward()
+        tol = 2e-5
+        assert rel(out["t_ft"], g[f"b{b}_t_ft"]) < tol
+        assert rel(out["t_zs"], g[f"b{b}_t_zs"]) < tol
+        assert abs(float(out["contrastive_loss"]) - float(g[f"b{b}_loss_ft"])) < 1e-4 * max(1.0, float(g[f"b{b}_loss_ft"]))
+        assert abs(float(out["zeroshot"]) - flags[3] * float(g[f"b{b}_loss_zs"])) < 1e-4 * max(1.0, float(g[f"b{b}_loss_zs"]))
+        assert rel(img.grad, g[f"b{b}_dI"]) < 1e-4
+        assert rel(cls_text.grad, g[f"b{b}_dCls"]) < 1e-4
+        assert rel(pimg.grad, g[f"b{b}_dPimg"]) < 1e-4
+        if flags[1] != 0.0:
+            assert rel(pgrp.grad, g[f"b{b}_dPgrp"]) < 1e-4
+        ref_dl = float(g[f"b{b}_dlogscale"])
+        assert abs(float(log_s.grad) - ref_dl) < 1e-3 * max(1.0, abs(ref_dl))
+        P.update_bank(bank, out["preds"], zs, out["t_ft"], out["t_zs"])
+    assert rel(bank, g["final_bank"]) < 1e-5
+
+
+def test_bank_roundtrip_through_parameter_dict():
+    import torch.nn as nn
+    from latteclip_b200 import prototypes as P
+    names = [f"c{k}" for k in range(5)]
+    pd = nn.ParameterDict({n: nn.Parameter(torch.randn(8, device=DEV)) for n in names})
+    bank = P.stack_bank(pd, names)
+    assert bank.shape == (5, 8)
+    bank2 = bank * 2
+    P.unstack_bank(bank2, pd, names, touched=torch.tensor([1, 0, 1, 0, 0.0]))
+    assert torch.equal(pd["c0"].data, bank2[0]) and torch.equal(pd["c1"].data, bank[1])
