@@ -265,16 +265,13 @@ __device__ __forceinline__ void store_out<__nv_bfloat16>(__nv_bfloat16* p, float
 template <>
 __device__ __forceinline__ void store_out<__half>(__half* p, float v) { *p = __float2half_rn(v); }
 
-__device__ __forceinline__ float load_feat(const void* base, int64_t idx, int is_bf16) {
-  if (is_bf16) return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(base)[idx]);
-  return __half2float(reinterpret_cast<const __half*>(base)[idx]);
-}
+// G is handed to the second MMA as fp16 (11-bit significand; bf16's 8 bits cost ~5e-3 of
+// gradient accuracy) scaled by 2^13 so that weights down to ~1e-11 stay representable.
+// kind::f16 takes the A and B formats independently, so fp16 G pairs with bf16 features.
+constexpr float kGScaleLog2 = 13.0f;
+constexpr float kGScaleInv = 1.0f / 8192.0f;
 
-__device__ __forceinline__ uint32_t pack2(float lo, float hi, int is_bf16) {
-  if (is_bf16) {
-    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
-    return *reinterpret_cast<uint32_t*>(&v);
-  }
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
   __half2 v = __floats2half2_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
 }
@@ -425,8 +422,10 @@ clip_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constan
     const float s = __ldg(p.logit_scale);
     const float c2 = s * kLog2e;
     const int64_t label = p.label_offset + grow;
-    const float a2 = row_ok ? __ldg(p.lse_a2 + label) : 0.f;
+    // exponents are biased by +13: every weight below carries the factor 2^13
+    const float a2 = (row_ok ? __ldg(p.lse_a2 + label) : 0.f) - kGScaleLog2;
     const float cb = p.cb;
+    const float cd_scaled = p.cd * 8192.0f;
     float ds_acc = 0.f;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
 
@@ -442,16 +441,9 @@ clip_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constan
       tmem_ld_wait();
 
       const bool ragged = col0 + 64 > p.n_all;
-      if (label >= col0 && label < col0 + 64 && row_ok) {
-        const int want = (int)(label - col0);
-        float dv = 0.f;
-#pragma unroll
-        for (int h = 0; h < 2; ++h)
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (h * 32 + i == want) dv = __uint_as_float(r[h][i]);
-        ds_acc -= dv;
-      }
+      // column of this row's positive pair inside this half tile (-1: not here)
+      int want = -1;
+      if (label >= col0 && label < col0 + 64 && row_ok) want = (int)(label - col0);
       const float4* pb = reinterpret_cast<const float4*>(p.lse_b2 + col0);
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
@@ -466,13 +458,17 @@ clip_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constan
             const int i = i4 * 4 + e;
             const float v = __uint_as_float(r[h][i]);
             float ea = fast_exp2(fmaf(v, c2, -a2));
-            float eb = fast_exp2(fmaf(v, c2, -bb[e]));
+            float eb = fast_exp2(fmaf(v, c2, kGScaleLog2 - bb[e]));
             if (ragged && col0 + h * 32 + i >= p.n_all) { ea = 0.f; eb = 0.f; }
             ds_acc = fmaf(ea, v, ds_acc);
             g[e] = fmaf(cb, eb, ea);
+            if (h * 32 + i == want) {      // one-hot term, subtracted in fp32 before rounding
+              g[e] -= cd_scaled;
+              ds_acc = fmaf(-8192.0f, v, ds_acc);
+            }
           }
-          packed[i4 * 2 + 0] = pack2(g[0], g[1], p.is_bf16);
-          packed[i4 * 2 + 1] = pack2(g[2], g[3], p.is_bf16);
+          packed[i4 * 2 + 0] = pack2(g[0], g[1]);
+          packed[i4 * 2 + 1] = pack2(g[2], g[3]);
         }
         // G for columns [32h, 32h+32) of this half -> 16 packed TMEM columns
         tmem_st_32x16(tmem_s + lane_base + buf * kBN + half * 64 + h * 16, packed);
@@ -483,11 +479,11 @@ clip_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constan
       if (lane == 0) mbar_arrive(bar_gready + 8 * buf);
     }
 
-    // ---- final: dX slab = coef * s * (acc - cd * Y[label]) ----
+    // ---- final: dX slab = coef * s * 2^-13 * acc ----
     mbar_wait(bar_acc, 0);
     tc_fence_after();
     const float coef = __ldg(p.grad_loss) * p.grad_mult / (2.0f * (float)p.n_loc);
-    const float cs = coef * s;
+    const float cs = coef * s * kGScaleInv;
     const int cols_slab = nch * 64;
     const int cols_half = cols_slab / 2;      // 32, 64, 96 or 128
     for (int cc = 0; cc < cols_half; cc += 32) {
@@ -501,8 +497,7 @@ clip_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constan
         for (int i = 0; i < 32; ++i) {
           const int64_t d = d0 + i;
           if (d < p.dim) {
-            const float yl = load_feat(p.y, label * p.ldy + d, p.is_bf16);
-            const float o = cs * (__uint_as_float(v[i]) - p.cd * yl);
+            const float o = cs * __uint_as_float(v[i]);
             if (p.grad_dtype == LATTE_F32)
               store_out(reinterpret_cast<float*>(p.dx) + grow * p.ld_dx + d, o);
             else if (p.grad_dtype == LATTE_BF16)
@@ -515,7 +510,7 @@ clip_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constan
     }
     // ---- d loss / d s partial (slab 0 only; every slab computed the same S) ----
     if (dsplit == 0) {
-      float v = row_ok ? ds_acc : 0.f;
+      float v = row_ok ? ds_acc * kGScaleInv : 0.f;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
       if (lane == 0) red_ptr[warp - kEpiWarp0] = v;
@@ -654,7 +649,7 @@ int clip_bwd_rows_tc(const ClipBwdArgs& a, cudaStream_t stream) {
   p.is_bf16 = a.dtype == LATTE_BF16;
   const uint32_t fmt = p.is_bf16 ? 1u : 0u;
   p.idesc_g1 = make_idesc_f16(kBM, kBN, fmt, 0, 0);
-  p.idesc_g2 = make_idesc_f16(kBM, 64, fmt, 0, 1);
+  p.idesc_g2 = make_idesc_ab(kBM, 64, /*a_format=fp16*/ 0u, fmt, 0, 1);
   const int smem = smem_bytes_for(p.kch, p.stages);
   LATTE_CUDA_OK(cudaFuncSetAttribute(clip_bwd_tc_kernel,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, smem));

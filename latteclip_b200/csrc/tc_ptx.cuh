@@ -201,6 +201,13 @@ __host__ __device__ constexpr uint32_t make_idesc_f16(uint32_t m, uint32_t n, ui
          (b_mn_major << 16) | ((n >> 3) << 17) | ((m >> 4) << 24);
 }
 
+__host__ __device__ constexpr uint32_t make_idesc_ab(uint32_t m, uint32_t n, uint32_t a_format,
+                                                     uint32_t b_format, uint32_t a_mn_major,
+                                                     uint32_t b_mn_major) {
+  return (1u << 4) | (a_format << 7) | (b_format << 10) | (a_mn_major << 15) |
+         (b_mn_major << 16) | ((n >> 3) << 17) | ((m >> 4) << 24);
+}
+
 __device__ __forceinline__ float fast_exp2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));

@@ -14,9 +14,14 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 
+def _f64(x):
+    if torch.is_tensor(x):
+        return x.detach().to(torch.float64).cpu()
+    return torch.as_tensor(np.asarray(x), dtype=torch.float64)
+
+
 def rel(a, b):
-    a = torch.as_tensor(np.asarray(a.detach().cpu() if torch.is_tensor(a) else a), dtype=torch.float64)
-    b = torch.as_tensor(np.asarray(b.detach().cpu() if torch.is_tensor(b) else b), dtype=torch.float64)
+    a, b = _f64(a), _f64(b)
     return float((a - b).norm() / b.norm().clamp_min(1e-300))
 
 
