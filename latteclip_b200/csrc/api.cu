@@ -82,15 +82,38 @@ ds_reduce_kernel(const float* partial, int count, const float* grad_loss, float 
   }
 }
 
+// bf16 -> fp16 copy of a feature matrix (second GEMM of the tc backward, see clip_tc.cu)
+__global__ void bf16_to_fp16_kernel(const __nv_bfloat16* in, int64_t ld_in, __half* out,
+                                    int64_t ld_out, int64_t rows, int64_t dim) {
+  const int64_t per_row = (dim + 7) / 8;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * per_row) return;
+  const int64_t r = idx / per_row, c = (idx % per_row) * 8;
+  if (c + 8 <= dim && (ld_in % 8) == 0) {
+    const uint4 raw = *reinterpret_cast<const uint4*>(in + r * ld_in + c);
+    const __nv_bfloat162* v = reinterpret_cast<const __nv_bfloat162*>(&raw);
+    uint4 o;
+    __half2* h = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) h[k] = __float22half2_rn(__bfloat1622float2(v[k]));
+    *reinterpret_cast<uint4*>(out + r * ld_out + c) = o;
+  } else {
+    for (int64_t k = c; k < dim && k < c + 8; ++k)
+      out[r * ld_out + k] = __float2half_rn(__bfloat162float(in[r * ld_in + k]));
+  }
+}
+
 struct WsLayout {
   size_t part;      // floats per partial array (kMaxParts * n_loc)
   size_t off_pmax_r, off_psum_r, off_diag_r, off_pmax_c, off_psum_c, off_diag_c;
   size_t off_row2, off_col2, off_ds;
+  size_t off_y16a, off_y16b;    // fp16 copies of txt_all / img_all (bf16 features only)
+  size_t ld16;
   size_t n_pad, ds_cap;
   size_t total;
 };
 
-WsLayout ws_layout(int64_t n_loc, int64_t n_all) {
+WsLayout ws_layout(int64_t n_loc, int64_t n_all, int64_t dim, int dtype) {
   WsLayout w;
   auto up = [](size_t x) { return (x + 63) / 64 * 64; };   // keep every array 256-byte aligned
   w.part = up((size_t)kMaxParts * (size_t)n_loc);
@@ -107,6 +130,13 @@ WsLayout ws_layout(int64_t n_loc, int64_t n_all) {
   w.off_col2 = o; o += up(w.n_pad);
   w.ds_cap = up(2 * (((size_t)n_loc + 63) / 64));
   w.off_ds = o; o += w.ds_cap;
+  w.ld16 = ((size_t)dim + 7) / 8 * 8;
+  w.off_y16a = w.off_y16b = o;
+  if (dtype == LATTE_BF16) {
+    const size_t f = up(((size_t)n_all * w.ld16 + 1) / 2);   // fp16 elements counted in floats
+    w.off_y16a = o; o += f;
+    w.off_y16b = o; o += f;
+  }
   w.total = o * sizeof(float);
   return w;
 }
@@ -150,7 +180,7 @@ extern "C" int latte_clip_workspace_bytes(int64_t n_loc, int64_t n_all, int64_t 
                                           size_t* bytes) {
   LATTE_CHECK_ARG(bytes && n_loc > 0 && n_all >= n_loc && dim > 0);
   LATTE_CHECK_ARG(dtype >= LATTE_F32 && dtype <= LATTE_F16);
-  *bytes = ws_layout(n_loc, n_all).total;
+  *bytes = ws_layout(n_loc, n_all, dim, dtype).total;
   return LATTE_OK;
 }
 
@@ -167,7 +197,7 @@ extern "C" int latte_clip_fwd(const void* img_loc, int64_t ld_img_loc, const voi
   LATTE_CHECK_ARG(label_offset >= 0 && label_offset + n_loc <= n_all);
   LATTE_CHECK_ARG(dtype >= LATTE_F32 && dtype <= LATTE_F16);
   LATTE_CHECK_ARG(ld_img_loc >= dim && ld_txt_loc >= dim && ld_img_all >= dim && ld_txt_all >= dim);
-  const WsLayout w = ws_layout(n_loc, n_all);
+  const WsLayout w = ws_layout(n_loc, n_all, dim, dtype);
   if (workspace_bytes < w.total) return LATTE_ERR_WORKSPACE;
   if ((reinterpret_cast<uintptr_t>(workspace) & 255) != 0) return LATTE_ERR_BAD_ARG;
   float* ws = static_cast<float*>(workspace);
@@ -217,7 +247,7 @@ extern "C" int latte_clip_bwd(const void* img_loc, int64_t ld_img_loc, const voi
   LATTE_CHECK_ARG(grad_dtype >= LATTE_F32 && grad_dtype <= LATTE_F16);
   LATTE_CHECK_ARG(ld_img_loc >= dim && ld_txt_loc >= dim && ld_img_all >= dim && ld_txt_all >= dim &&
                   ld_grad >= dim);
-  const WsLayout w = ws_layout(n_loc, n_all);
+  const WsLayout w = ws_layout(n_loc, n_all, dim, dtype);
   if (workspace_bytes < w.total) return LATTE_ERR_WORKSPACE;
   if ((reinterpret_cast<uintptr_t>(workspace) & 255) != 0) return LATTE_ERR_BAD_ARG;
   float* ws = static_cast<float*>(workspace);
@@ -234,6 +264,28 @@ extern "C" int latte_clip_bwd(const void* img_loc, int64_t ld_img_loc, const voi
   const int ds_count = tc ? clip_tc_ds_count(n_loc, dim) : clip_simt_ds_count(n_loc);
   if ((size_t)(2 * ds_count) > w.ds_cap) return LATTE_ERR_WORKSPACE;
 
+  // fp16 operands for the second GEMM of the tc path
+  const void* txt16 = txt_all; int64_t ld_txt16 = ld_txt_all;
+  const void* img16 = img_all; int64_t ld_img16 = ld_img_all;
+  if (tc && dtype == LATTE_BF16) {
+    __half* ya = reinterpret_cast<__half*>(ws + w.off_y16a);
+    __half* yb = reinterpret_cast<__half*>(ws + w.off_y16b);
+    const int64_t work = n_all * ((dim + 7) / 8);
+    const unsigned blocks = (unsigned)((work + 255) / 256);
+    bf16_to_fp16_kernel<<<blocks, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(txt_all),
+                                                ld_txt_all, ya, (int64_t)w.ld16, n_all, dim);
+    LATTE_LAUNCH_OK();
+    if (img_all == txt_all) {
+      yb = ya;
+    } else {
+      bf16_to_fp16_kernel<<<blocks, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(img_all),
+                                                  ld_img_all, yb, (int64_t)w.ld16, n_all, dim);
+      LATTE_LAUNCH_OK();
+    }
+    txt16 = ya; ld_txt16 = (int64_t)w.ld16;
+    img16 = yb; ld_img16 = (int64_t)w.ld16;
+  }
+
   ClipBwdArgs a;
   a.dtype = dtype; a.n_loc = n_loc; a.n_all = n_all; a.dim = dim;
   a.label_offset = label_offset; a.logit_scale = logit_scale;
@@ -241,11 +293,13 @@ extern "C" int latte_clip_bwd(const void* img_loc, int64_t ld_img_loc, const voi
   a.grad_dtype = grad_dtype; a.ld_dx = ld_grad; a.ds_count = ds_count;
   // d_img = coef*s * G[loc rows, :] @ txt_all
   a.x = img_loc; a.ldx = ld_img_loc; a.y = txt_all; a.ldy = ld_txt_all;
+  a.y16 = txt16; a.ldy16 = ld_txt16;
   a.lse_a2 = row2; a.lse_b2 = col2; a.dx = d_img; a.ds_partial = ws + w.off_ds;
   int rc = tc ? clip_bwd_rows_tc(a, st) : clip_bwd_rows_simt(a, st);
   if (rc) return rc;
   // d_txt = coef*s * G[:, loc cols]^T @ img_all  (rows of the transposed problem)
   a.x = txt_loc; a.ldx = ld_txt_loc; a.y = img_all; a.ldy = ld_img_all;
+  a.y16 = img16; a.ldy16 = ld_img16;
   a.lse_a2 = col2; a.lse_b2 = row2; a.dx = d_txt; a.ds_partial = ws + w.off_ds + ds_count;
   rc = tc ? clip_bwd_rows_tc(a, st) : clip_bwd_rows_simt(a, st);
   if (rc) return rc;

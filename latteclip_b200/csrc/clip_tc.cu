@@ -65,7 +65,6 @@ struct BwdParams {
   float grad_mult;
   float cb;          // weight of the y-side softmax term (0 or 1)
   float cd;          // weight of the one-hot term (1 or 2)
-  const void* y; int64_t ldy;   // for the exact one-hot correction
   void* dx; int grad_dtype; int64_t ld_dx;
   float* ds_partial;
   int kch;
@@ -267,7 +266,9 @@ __device__ __forceinline__ void store_out<__half>(__half* p, float v) { *p = __f
 
 // G is handed to the second MMA as fp16 (11-bit significand; bf16's 8 bits cost ~5e-3 of
 // gradient accuracy) scaled by 2^13 so that weights down to ~1e-11 stay representable.
-// kind::f16 takes the A and B formats independently, so fp16 G pairs with bf16 features.
+// tcgen05.mma kind::f16 needs A and B in the same format (a mixed fp16 x bf16 descriptor
+// raises an illegal-instruction fault on sm_100a), so for bf16 features the second GEMM
+// reads Y from an fp16 copy (exact for |y| in [6e-5, 65504], which covers CLIP features).
 constexpr float kGScaleLog2 = 13.0f;
 constexpr float kGScaleInv = 1.0f / 8192.0f;
 
@@ -278,7 +279,7 @@ __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
 
 __global__ void __launch_bounds__(kThreads, 1)
 clip_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmy,
-                   const BwdParams p) {
+                   const __grid_constant__ CUtensorMap tmy16, const BwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t smem_base = smem_u32(smem);
   const int warp = threadIdx.x >> 5;
@@ -312,6 +313,7 @@ clip_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constan
   if (warp == 0 && elect_one()) {
     prefetch_tensormap(&tmx);
     prefetch_tensormap(&tmy);
+    prefetch_tensormap(&tmy16);
   }
   if (warp == 1 && elect_one()) {
     mbar_init(bar_x, 1);
@@ -345,18 +347,18 @@ clip_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constan
         tma_load_2d(x_smem + c * kChunkBytes, &tmx, bar_x, c * kBK, row0);
       int stage = 0;
       uint32_t phase = 0;
-      auto load_chunk = [&](int chunk, int tile) {
+      auto load_chunk = [&](const CUtensorMap* map, int chunk, int tile) {
         mbar_wait(bar_empty + 8 * stage, phase ^ 1);
         mbar_arrive_expect_tx(bar_full + 8 * stage, kChunkBytes);
-        tma_load_2d(ring + stage * kChunkBytes, &tmy, bar_full + 8 * stage, chunk * kBK,
+        tma_load_2d(ring + stage * kChunkBytes, map, bar_full + 8 * stage, chunk * kBK,
                     tile * kBN);
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
       };
-      for (int c = 0; c < p.kch; ++c) load_chunk(c, 0);                 // GEMM1(0)
+      for (int c = 0; c < p.kch; ++c) load_chunk(&tmy, c, 0);               // GEMM1(0)
       for (int it = 0; it < ntiles; ++it) {
         if (it + 1 < ntiles)
-          for (int c = 0; c < p.kch; ++c) load_chunk(c, it + 1);        // GEMM1(it+1)
-        for (int c = 0; c < nch; ++c) load_chunk(ch0 + c, it);          // GEMM2(it)
+          for (int c = 0; c < p.kch; ++c) load_chunk(&tmy, c, it + 1);      // GEMM1(it+1)
+        for (int c = 0; c < nch; ++c) load_chunk(&tmy16, ch0 + c, it);      // GEMM2(it), fp16 Y
       }
     }
   } else if (warp == 1) {
@@ -632,6 +634,9 @@ int clip_bwd_rows_tc(const ClipBwdArgs& a, cudaStream_t stream) {
   if (rc) return rc;
   rc = make_map(&tmy, a.y, a.dtype, a.n_all, a.dim, a.ldy);
   if (rc) return rc;
+  CUtensorMap tmy16;
+  rc = make_map(&tmy16, a.y16, LATTE_F16, a.n_all, a.dim, a.ldy16);
+  if (rc) return rc;
   BwdParams p;
   p.n_loc = a.n_loc; p.n_all = a.n_all; p.dim = a.dim;
   p.label_offset = a.label_offset;
@@ -640,7 +645,6 @@ int clip_bwd_rows_tc(const ClipBwdArgs& a, cudaStream_t stream) {
   p.grad_loss = a.grad_loss; p.grad_mult = a.grad_mult;
   p.cb = a.cross_terms ? 1.f : 0.f;
   p.cd = a.cross_terms ? 2.f : 1.f;
-  p.y = a.y; p.ldy = a.ldy;
   p.dx = a.dx; p.grad_dtype = a.grad_dtype; p.ld_dx = a.ld_dx;
   p.ds_partial = a.ds_partial;
   p.kch = (int)((a.dim + kBK - 1) / kBK);
@@ -649,12 +653,12 @@ int clip_bwd_rows_tc(const ClipBwdArgs& a, cudaStream_t stream) {
   p.is_bf16 = a.dtype == LATTE_BF16;
   const uint32_t fmt = p.is_bf16 ? 1u : 0u;
   p.idesc_g1 = make_idesc_f16(kBM, kBN, fmt, 0, 0);
-  p.idesc_g2 = make_idesc_ab(kBM, 64, /*a_format=fp16*/ 0u, fmt, 0, 1);
+  p.idesc_g2 = make_idesc_f16(kBM, 64, /*fp16*/ 0u, 0, 1);
   const int smem = smem_bytes_for(p.kch, p.stages);
   LATTE_CUDA_OK(cudaFuncSetAttribute(clip_bwd_tc_kernel,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   dim3 grid((unsigned)((a.n_loc + kBM - 1) / kBM), (unsigned)((p.kch + 3) / 4));
-  clip_bwd_tc_kernel<<<grid, kThreads, smem, stream>>>(tmx, tmy, p);
+  clip_bwd_tc_kernel<<<grid, kThreads, smem, stream>>>(tmx, tmy, tmy16, p);
   LATTE_LAUNCH_OK();
   return LATTE_OK;
 }

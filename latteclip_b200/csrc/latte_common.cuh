@@ -56,6 +56,7 @@ struct ClipFwdArgs {
 struct ClipBwdArgs {
   const void* x; int64_t ldx;
   const void* y; int64_t ldy;
+  const void* y16; int64_t ldy16;   // fp16 copy of y (tc path; == y for fp16 features)
   int dtype;
   int64_t n_loc, n_all, dim;
   int64_t label_offset;
