@@ -1,0 +1,364 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200-native LatteCLIP loss head.
+
+Metric (BASELINE.json): ClipLoss forward + backward samples/s at global batch 32768,
+dim 512 (bf16 features, logit_scale 100), on 1/2/4/8 B200.  A "step" is one fused ClipLoss
+forward + backward over the whole global batch (the reference's loss.py:120-130 + autograd),
+sharded by rows over the ranks exactly like open_clip's local_loss / gather_with_grad mode.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # our arm
+    python bench.py --impl reference [--gpus N] [--steps K] ...     # reference CPU arm
+
+For N > 1 launch with torchrun (one rank per GPU, NCCL).  Rank 0 prints ONE JSON line.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch
+import torch.nn.functional as F
+
+N_GLOBAL = 32768
+DIM = 512
+SCALE = 100.0
+METRIC = "clip_loss_fwd_bwd_samples_per_sec"
+UNIT = "samples/s"
+# DRAM traffic of the dominant kernel per launch, from the committed ncu capture
+# (profiles/r1_clip_32k_ncu_summary.md: dram__bytes_read.sum + dram__bytes_write.sum)
+NCU_TRAFFIC_BWD_BYTES = 264.0e6
+
+
+def synth_shard(n_global, dim, rank, world, set_id=0):
+    """Seeded synthetic unit-norm features with correlated pairs:
+    I = normalize(randn), T = normalize(I + sigma * randn / sqrt(D)), sigma = 4."""
+    n = n_global // world
+    g = torch.Generator().manual_seed(1234 + 1000 * 2 + rank + 97 * set_id)
+    i = F.normalize(torch.randn(n, dim, generator=g), dim=1)
+    t = F.normalize(i + 4.0 * torch.randn(n, dim, generator=g) / math.sqrt(dim), dim=1)
+    return i, t
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(burst=float(p["bf16_tflops"]), sustained=float(p.get("bf16_tflops_sustained", p["bf16_tflops"])),
+                    hbm=float(p["hbm_gbs"]), source="measured (MEASURED_PEAKS.json)")
+    return dict(burst=1590.0, sustained=1400.0, hbm=6650.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for k, nm in enumerate(names):
+                if f[4 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None, "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+def cpu_reference_sample(steps, warmup, target_s=6.0):
+    """The reference algorithm on the host cores (oracle port, fp32, all threads): forward +
+    backward of the loss terms owned by the first R rows of the N = 32768 problem (what one
+    rank of a local_loss run computes, loss.py:108-110).  Per-sample cost equals the full
+    batch's, so samples/s = R / time."""
+    from oracle.clip_loss import clip_loss_row_block_sample
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    i, t = synth_shard(N_GLOBAL, DIM, 0, 1)
+    rows = 256
+    t0 = time.perf_counter()
+    clip_loss_row_block_sample(i, t, SCALE, rows)
+    dt = time.perf_counter() - t0
+    # scale the row block so one step takes about target_s / steps seconds (bounded)
+    per_row = max(dt / rows, 1e-7)
+    rows = int(min(8192, max(256, (target_s / max(steps, 1)) / per_row)))
+    rows = max(256, rows // 256 * 256)
+    for _ in range(warmup):
+        clip_loss_row_block_sample(i, t, SCALE, rows)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        clip_loss_row_block_sample(i, t, SCALE, rows)
+    dt = (time.perf_counter() - t0) / steps
+    return dict(value=rows / dt, unit=UNIT, cores=torch.get_num_threads(), kind="port",
+                sample=f"fwd+bwd of the first {rows} rows (both CE directions) of the N={N_GLOBAL}, "
+                       f"D={DIM} fp32 problem, {steps} steps, {dt * 1e3:.1f} ms/step"), dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    base, dt = cpu_reference_sample(max(args.steps, 1), min(args.warmup, 1), target_s=20.0)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": f"ClipLoss fwd+bwd, global batch {N_GLOBAL}, dim {DIM}, logit_scale {SCALE:g}",
+                   "note": "reference algorithm (oracle port of open_clip/loss.py) on the host CPU cores"},
+        "cpu_baseline": base,
+        "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    import latteclip_b200 as lb
+    from latteclip_b200 import _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    if args.gpus != world:
+        if rank == 0:
+            sys.stderr.write(f"note: --gpus {args.gpus} but WORLD_SIZE {world}; using {world}\n")
+    n_loc = N_GLOBAL // world
+    peaks = load_peaks()
+
+    # rotating input sets: 4 x (I, T) x 32 MiB = 256 MiB of inputs at N=1, larger than the L2
+    n_sets = 4
+    host_sets = []
+    dev_sets = []
+    for sidx in range(n_sets):
+        i, t = synth_shard(N_GLOBAL, DIM, rank, world, sidx)
+        hi, ht = i.bfloat16().pin_memory(), t.bfloat16().pin_memory()
+        host_sets.append((hi, ht))
+        dev_sets.append((hi.to(dev).requires_grad_(True), ht.to(dev).requires_grad_(True)))
+    log_s = torch.tensor(math.log(SCALE), device=dev, requires_grad=True)
+    loss_fn = lb.ClipLoss(local_loss=True, gather_with_grad=True, cache_labels=True,
+                          rank=rank, world_size=world)
+
+    def step_resident(k):
+        i, t = dev_sets[k % n_sets]
+        i.grad = None; t.grad = None; log_s.grad = None
+        loss = loss_fn(i, t, log_s.exp())
+        loss.backward()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for k in range(max(args.warmup, 3)):
+        step_resident(k)
+    barrier()
+
+    # ---- timed region: exactly K steps, inputs resident in HBM ----------------------------
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for k in range(args.steps):
+        loss = step_resident(k)
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    t_ms = torch.tensor([ms_total], device=dev)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms_step = float(t_ms) / args.steps
+    value = N_GLOBAL / (ms_step * 1e-3)
+    last_loss = float(loss)
+
+    # ---- end to end: host (pinned) buffers -> public API -> loss back on the host ----------
+    stage_i = torch.empty(n_loc, DIM, dtype=torch.bfloat16, device=dev)
+    stage_t = torch.empty(n_loc, DIM, dtype=torch.bfloat16, device=dev)
+    host_loss = torch.empty((), dtype=torch.float32).pin_memory()
+
+    def step_e2e(k):
+        hi, ht = host_sets[k % n_sets]
+        stage_i.copy_(hi, non_blocking=True)
+        stage_t.copy_(ht, non_blocking=True)
+        i = stage_i.detach().requires_grad_(True)
+        t = stage_t.detach().requires_grad_(True)
+        log_s.grad = None
+        loss = loss_fn(i, t, log_s.exp())
+        loss.backward()
+        host_loss.copy_(loss.detach(), non_blocking=True)
+        return i.grad
+
+    for k in range(3):
+        step_e2e(k)
+    barrier()
+    e0.record()
+    for k in range(args.steps):
+        step_e2e(k)
+    e1.record()
+    barrier()
+    t_e = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
+    e2e_value = N_GLOBAL / (float(t_e) / args.steps * 1e-3)
+    h2d = 2 * n_loc * DIM * 2
+    d2h = 4
+
+    # ---- roofline of the dominant kernel (the tcgen05 backward row kernel), timed live ------
+    i, t = dev_sets[0]
+    idet, tdet = i.detach(), t.detach()
+    sc = torch.tensor(SCALE, device=dev)
+    one = torch.ones(1, device=dev)
+    if world > 1:
+        all_i = torch.empty(N_GLOBAL, DIM, dtype=torch.bfloat16, device=dev)
+        all_t = torch.empty(N_GLOBAL, DIM, dtype=torch.bfloat16, device=dev)
+        dist.all_gather_into_tensor(all_i, idet)
+        dist.all_gather_into_tensor(all_t, tdet)
+    else:
+        all_i, all_t = idet, tdet
+    off = rank * n_loc
+    row, col, _ = _lib.clip_fwd(idet, tdet, all_i, all_t, off, sc)
+    if world > 1:
+        both = torch.empty(N_GLOBAL, 2, device=dev)
+        dist.all_gather_into_tensor(both, torch.stack([row, col], dim=1))
+        row_all, col_all = both[:, 0].contiguous(), both[:, 1].contiguous()
+    else:
+        row_all, col_all = row, col
+    reps = 5
+    for _ in range(2):
+        _lib.clip_bwd(idet, tdet, all_i, all_t, off, sc, row_all, col_all, one, 1.0, True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(reps):
+        _lib.clip_bwd(idet, tdet, all_i, all_t, off, sc, row_all, col_all, one, 1.0, True)
+    e1.record()
+    torch.cuda.synchronize()
+    bwd_call_ms = e0.elapsed_time(e1) / reps
+    e0.record()
+    for _ in range(reps):
+        _lib.clip_fwd(idet, tdet, all_i, all_t, off, sc)
+    e1.record()
+    torch.cuda.synchronize()
+    fwd_call_ms = e0.elapsed_time(e1) / reps
+    # one backward call = 2 launches of clip_bwd_tc_kernel (+ ~3 tiny kernels); each launch is
+    # credited with ONE gradient GEMM: 2 * n_loc * N * D FLOP (recomputing S is not credited)
+    alg_flop_per_launch = 2.0 * n_loc * N_GLOBAL * DIM
+    launch_ms = bwd_call_ms / 2.0
+    achieved_tf = alg_flop_per_launch / (launch_ms * 1e-3) / 1e12
+    step_tf = 6.0 * n_loc * N_GLOBAL * DIM / (ms_step * 1e-3) / 1e12
+    roofline = {
+        "bound": "tensor", "kernel": "clip_bwd_tc_kernel", "achieved": achieved_tf,
+        "peak": peaks["burst"], "unit": "TFLOP/s", "frac": achieved_tf / peaks["burst"],
+        "traffic": NCU_TRAFFIC_BWD_BYTES if world == 1 else None,
+        "peak_source": peaks["source"] + ", burst bf16 figure (kernel timed alone)",
+        "launch_ms": launch_ms, "alg_flop_per_launch": alg_flop_per_launch,
+        "executed_flop_per_launch": 6.0 * n_loc * N_GLOBAL * DIM,
+        "step_alg_tflops_per_gpu": step_tf,
+        "step_frac_of_sustained": step_tf / peaks["sustained"],
+        "fwd_call_ms": fwd_call_ms, "bwd_call_ms": bwd_call_ms,
+    }
+
+    cpu_base = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu_base, _ = cpu_reference_sample(2, 1, target_s=12.0)
+
+    # kernels of ours per step: forward 2 row kernels + finalize; backward lse->base2,
+    # 2 bf16->fp16 copies, 2 row kernels, ds reduce
+    launches_per_step = 3 + 6
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {
+                "workload": f"ClipLoss fwd+bwd (open_clip loss.py:120-130 + autograd), global batch "
+                            f"{N_GLOBAL}, dim {DIM}, bf16 features, logit_scale {SCALE:g}, "
+                            f"local_loss + gather_with_grad, {n_loc} rows per rank",
+                "global_batch": N_GLOBAL, "dim": DIM, "rows_per_rank": n_loc,
+                "l2": "rotating 4 input sets (256 MiB at N=1) larger than the 126 MiB L2",
+                "loss": last_loss,
+            },
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": launches_per_step * args.steps,
+            "clocks": clocks, "roofline": roofline,
+        }
+        if cpu_base is not None:
+            line["cpu_baseline"] = cpu_base
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

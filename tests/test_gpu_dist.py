@@ -1,0 +1,88 @@
+"""Multi-GPU (NCCL) parity test of the fused ClipLoss + bank update: one process per GPU.
+Skipped when fewer than 2 GPUs are visible (the host logic is covered on CPU by
+test_dist_cpu.py with gloo)."""
+
+import math
+import os
+import sys
+
+import pytest
+import torch
+import torch.multiprocessing as mp
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+
+
+def _worker(rank, world, port, n, d, dtype_name, ret):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    import latteclip_b200 as lb
+    from latteclip_b200 import prototypes as P
+    dtype = getattr(torch, dtype_name)
+    g = torch.Generator().manual_seed(123)
+    i_all = F.normalize(torch.randn(n * world, d, generator=g), dim=1)
+    t_all = F.normalize(i_all + 3.0 * torch.randn(n * world, d, generator=g) / math.sqrt(d), dim=1)
+    out = {}
+    for local_loss, gwg in ((True, True), (True, False), (False, True), (False, False)):
+        il = i_all[rank * n:(rank + 1) * n].to(dev).to(dtype).requires_grad_(True)
+        tl = t_all[rank * n:(rank + 1) * n].to(dev).to(dtype).requires_grad_(True)
+        s = torch.tensor(100.0, device=dev, requires_grad=True)
+        loss = lb.ClipLoss(local_loss=local_loss, gather_with_grad=gwg, rank=rank, world_size=world)(il, tl, s)
+        loss.backward()
+        out[(local_loss, gwg)] = dict(loss=float(loss.detach()), dI=il.grad.float().cpu(),
+                                      dT=tl.grad.float().cpu(), ds=float(s.grad))
+    c = 11
+    bank = F.normalize(torch.randn(c, d, generator=g), dim=1)
+    preds = torch.randint(0, c, (n * world,), generator=g)
+    zs = torch.randint(0, c, (n * world,), generator=g)
+    sl = slice(rank * n, (rank + 1) * n)
+    bank_g = bank.to(dev).clone()
+    P.update_bank(bank_g, preds[sl].to(dev), zs[sl].to(dev), t_all[sl].to(dev), i_all[sl].to(dev), world_size=world)
+    out["bank"] = bank_g.cpu()
+    ret[rank] = out
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("dtype_name,n,d", [("bfloat16", 512, 512), ("float32", 96, 64)])
+def test_nccl_cliploss_matches_oracle(dtype_name, n, d):
+    world = min(torch.cuda.device_count(), 4)
+    if world < 2:
+        pytest.skip("needs >= 2 GPUs")
+    import oracle
+    from oracle.clip_loss import clip_loss_all_ranks
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, 29801 + n % 7, n, d, dtype_name, ret), nprocs=world, join=True)
+    dtype = getattr(torch, dtype_name)
+    g = torch.Generator().manual_seed(123)
+    i_all = F.normalize(torch.randn(n * world, d, generator=g), dim=1)
+    t_all = F.normalize(i_all + 3.0 * torch.randn(n * world, d, generator=g) / math.sqrt(d), dim=1)
+    ir, tr = i_all.to(dtype).float(), t_all.to(dtype).float()
+    ish = [ir[r * n:(r + 1) * n] for r in range(world)]
+    tsh = [tr[r * n:(r + 1) * n] for r in range(world)]
+    gtol = 2e-3 if dtype_name == "bfloat16" else 5e-5
+    for key in ((True, True), (True, False), (False, True), (False, False)):
+        lo, di, dt, ds = clip_loss_all_ranks(ish, tsh, 100.0, key[0], key[1])
+        for r in range(world):
+            got = ret[r][key]
+            assert abs(got["loss"] - float(lo[r])) <= 1e-5 * abs(float(lo[r])) + 2e-5
+            assert float((got["dI"].double() - di[r]).norm() / di[r].norm()) < gtol
+            assert float((got["dT"].double() - dt[r]).norm() / dt[r].norm()) < gtol
+            assert abs(got["ds"] - float(ds[r])) <= 2e-3 * abs(float(ds[r])) + 1e-6
+    c = 11
+    bank = F.normalize(torch.randn(c, d, generator=g), dim=1)
+    preds = torch.randint(0, c, (n * world,), generator=g)
+    zs = torch.randint(0, c, (n * world,), generator=g)
+    ref = oracle.update_bank(bank, preds, zs, t_all, i_all)
+    for r in range(world):
+        assert float((ret[r]["bank"] - ref).norm() / ref.norm()) < 1e-5
+        assert torch.equal(ret[r]["bank"], ret[0]["bank"])
