@@ -62,7 +62,7 @@ def load_peaks():
 
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
@@ -74,7 +74,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                  "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -83,7 +83,12 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
+
+    def mark(self):
+        """Start of the timed region: only samples taken after this point are reported
+        (falls back to every sample under load if the region was shorter than one period)."""
+        self.t_mark = time.time()
 
     def stop(self):
         if self.proc is None:
@@ -96,7 +101,13 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        t_mark = getattr(self, "t_mark", 0.0)
+        inside = [ln for (ts, ln) in self.lines if ts >= t_mark]
+        window = "timed region" if len(inside) >= 2 else "warm-up + timed region"
+        if len(inside) < 2:
+            inside = [ln for (_, ln) in self.lines[1:]] or [ln for (_, ln) in self.lines]
+        self.window = window
+        for ln in inside:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 8:
                 continue
@@ -108,7 +119,7 @@ class ClockSampler:
                 if f[4 + k].lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": statistics.median(sm) if sm else None,
-                "sm_max_mhz": max(mx) if mx else None, "samples": len(sm),
+                "sm_max_mhz": max(mx) if mx else None, "samples": len(sm), "window": self.window,
                 "reasons": sorted(reasons)}
 
 
@@ -205,16 +216,23 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for k in range(max(args.warmup, 3)):
-        step_resident(k)
-    barrier()
-
-    # ---- timed region: exactly K steps, inputs resident in HBM ----------------------------
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    t_w = time.time()
+    k = 0
+    # at least W warm-up steps, and long enough for nvidia-smi to be sampling under load
+    while k < max(args.warmup, 3) or time.time() - t_w < 0.6:
+        step_resident(k)
+        k += 1
+        if k % 8 == 0:
+            torch.cuda.synchronize()
+    barrier()
+
+    # ---- timed region: exactly K steps, inputs resident in HBM ----------------------------
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    sampler.mark()
     e0.record()
     for k in range(args.steps):
         loss = step_resident(k)
@@ -227,7 +245,7 @@ def run_ours(args):
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
     ms_step = float(t_ms) / args.steps
     value = N_GLOBAL / (ms_step * 1e-3)
-    last_loss = float(loss)
+    last_loss = float(loss.detach())
 
     # ---- end to end: host (pinned) buffers -> public API -> loss back on the host ----------
     stage_i = torch.empty(n_loc, DIM, dtype=torch.bfloat16, device=dev)

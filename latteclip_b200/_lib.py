@@ -191,8 +191,10 @@ def clip_fwd(img_loc, txt_loc, img_all, txt_all, label_offset: int, logit_scale)
 
 
 def clip_bwd(img_loc, txt_loc, img_all, txt_all, label_offset: int, logit_scale,
-             row_lse_all, col_lse_all, grad_loss, grad_mult: float, cross_terms: bool):
-    """-> (d_img[n_loc, dim], d_txt[n_loc, dim] in the feature dtype, d_scale[1] fp32)."""
+             row_lse_all, col_lse_all, grad_loss, grad_mult: float, cross_terms: bool,
+             grad_dtype=None):
+    """-> (d_img[n_loc, dim], d_txt[n_loc, dim], d_scale[1] fp32).  The feature gradients
+    come back in ``grad_dtype`` (default: the feature dtype, what autograd needs)."""
     lib = load()
     img_loc, txt_loc = _rows(img_loc, "image_features"), _rows(txt_loc, "text_features")
     img_all, txt_all = _rows(img_all, "all_image_features"), _rows(txt_all, "all_text_features")
@@ -206,8 +208,9 @@ def clip_bwd(img_loc, txt_loc, img_all, txt_all, label_offset: int, logit_scale,
     col_lse_all = _vec(col_lse_all, torch.float32, "col_lse")
     if row_lse_all.numel() != n_all or col_lse_all.numel() != n_all:
         raise RuntimeError("clip_bwd: LSE vectors must have n_all entries")
-    d_img = torch.empty(n_loc, dim, dtype=img_loc.dtype, device=dev)
-    d_txt = torch.empty(n_loc, dim, dtype=img_loc.dtype, device=dev)
+    gdt = img_loc.dtype if grad_dtype is None else grad_dtype
+    d_img = torch.empty(n_loc, dim, dtype=gdt, device=dev)
+    d_txt = torch.empty(n_loc, dim, dtype=gdt, device=dev)
     d_scale = torch.empty(1, dtype=torch.float32, device=dev)
     ws = _workspace(n_loc, n_all, dim, dt, dev)
     wp, wn = _aligned_ptr(ws)
@@ -216,7 +219,7 @@ def clip_bwd(img_loc, txt_loc, img_all, txt_all, label_offset: int, logit_scale,
                                   _ptr(img_all), img_all.stride(0), _ptr(txt_all), txt_all.stride(0),
                                   dt, n_loc, n_all, dim, label_offset, _ptr(s), _ptr(row_lse_all),
                                   _ptr(col_lse_all), _ptr(g), float(grad_mult), int(bool(cross_terms)),
-                                  _ptr(d_img), _ptr(d_txt), dt, dim, _ptr(d_scale), wp, wn,
+                                  _ptr(d_img), _ptr(d_txt), _DTYPES[gdt], dim, _ptr(d_scale), wp, wn,
                                   _stream(img_loc)),
                "latte_clip_bwd")
     return d_img, d_txt, d_scale

@@ -229,7 +229,7 @@ class ClipLoss(nn.Module):
         # One compute dtype for both operands: the autocast dtype when autocast is on (the
         # reference's matmuls run in it), otherwise the promoted dtype of the two inputs.
         if torch.is_autocast_enabled():
-            cdt = torch.get_autocast_gpu_dtype()
+            cdt = torch.get_autocast_dtype("cuda")
         else:
             cdt = torch.promote_types(image_features.dtype, text_features.dtype)
         if cdt not in (torch.float32, torch.bfloat16, torch.float16):

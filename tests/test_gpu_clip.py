@@ -6,7 +6,12 @@ Tolerances (BASELINE.json north_star / SURVEY.md 8d):
                               of magnitude ~100 carries 4e-6 of rounding, which exp() turns
                               into that much relative error of every softmax weight)
   * bf16 / fp16 features:     loss rel <= 1e-5 (vs the fp64 oracle fed the same rounded
-                              inputs; 2e-5 abs floor), grads rel <= 2e-3
+                              inputs; 2e-5 abs floor), grads rel <= 2e-3 for the gradient the
+                              kernels compute (read back in fp32 through the C ABI).  The
+                              nn.Module has to hand autograd a gradient in the FEATURE dtype;
+                              rounding anything to bf16 costs 2^-7/sqrt(12)*0.72 = 1.63e-3 rms
+                              by itself, so the module-level check on bf16 outputs allows
+                              sqrt(2e-3^2 + 1.63e-3^2) = 2.6e-3 (fp16 outputs: 2e-3).
 """
 
 import math
@@ -22,7 +27,23 @@ pytestmark = pytest.mark.gpu
 
 LOSS_RTOL = 1e-5
 GRAD_RTOL_16 = 2e-3
+GRAD_RTOL_BF16_OUT = 2.6e-3
 GRAD_RTOL_32 = 5e-5
+
+
+def out_tol(dtype):
+    return GRAD_RTOL_BF16_OUT if dtype == torch.bfloat16 else GRAD_RTOL_16
+
+
+def fp32_grads(il, tl, scale):
+    """The gradient the kernels compute, before it is rounded to the feature dtype."""
+    from latteclip_b200 import _lib
+    dev = il.device
+    sc = torch.tensor(scale, device=dev)
+    row, col, _ = _lib.clip_fwd(il, tl, il, tl, 0, sc)
+    di, dt, _ = _lib.clip_bwd(il, tl, il, tl, 0, sc, row, col, torch.ones(1, device=dev), 1.0, True,
+                              grad_dtype=torch.float32)
+    return di, dt
 
 
 def _f64(x):
@@ -103,9 +124,11 @@ def test_tensor_core_path_matches_oracle(case, dtype):
     assert di.dtype == dtype and dt.dtype == dtype
     rl, rdi, rdt, rds = oracle_on(il, tl, scale)
     assert abs(float(loss) - float(rl)) <= LOSS_RTOL * abs(float(rl)) + 2e-5, (float(loss), float(rl))
-    assert rel(di, rdi) < GRAD_RTOL_16
-    assert rel(dt, rdt) < GRAD_RTOL_16
+    assert rel(di, rdi) < out_tol(dtype)
+    assert rel(dt, rdt) < out_tol(dtype)
     assert abs(float(ds) - float(rds)) <= 2e-3 * abs(float(rds)) + 1e-6
+    di32, dt32 = fp32_grads(il, tl, scale)
+    assert rel(di32, rdi) < GRAD_RTOL_16 and rel(dt32, rdt) < GRAD_RTOL_16
 
 
 def test_tensor_core_path_matches_reference_golden_inputs():
@@ -116,7 +139,9 @@ def test_tensor_core_path_matches_reference_golden_inputs():
     loss, di, dt, ds, il, tl = run_ours(i, t, s, torch.bfloat16)
     rl, rdi, rdt, rds = oracle_on(il, tl, s)
     assert abs(float(loss) - float(rl)) <= LOSS_RTOL * abs(float(rl)) + 2e-5
-    assert rel(di, rdi) < GRAD_RTOL_16 and rel(dt, rdt) < GRAD_RTOL_16
+    assert rel(di, rdi) < GRAD_RTOL_BF16_OUT and rel(dt, rdt) < GRAD_RTOL_BF16_OUT
+    di32, dt32 = fp32_grads(il, tl, s)
+    assert rel(di32, rdi) < GRAD_RTOL_16 and rel(dt32, rdt) < GRAD_RTOL_16
     assert rel(di, g["dI_f64"]) < 0.1 and abs(float(loss) - float(g["loss_f64"])) < 0.05
 
 
@@ -145,7 +170,7 @@ def test_rank_block_semantics_match_gloo_reference(world, local_loss, gwg, dtype
         tsh = [t_all[r * n:(r + 1) * n].float().cpu() for r in range(world)]
         lo, di, dt, ds = clip_loss_all_ranks(ish, tsh, float(g["scale"]), local_loss, gwg)
         ref = {r: dict(loss=lo[r], dI=di[r], dT=dt[r], ds=ds[r]) for r in range(world)}
-        ltol, gtol = 1e-5, 2e-3
+        ltol, gtol = 1e-5, GRAD_RTOL_BF16_OUT
     fw = [_lib.clip_fwd(i_all[r * n:(r + 1) * n], t_all[r * n:(r + 1) * n], i_all, t_all, r * n, scale)
           for r in range(world)]
     row_all = torch.cat([f[0] for f in fw])
@@ -244,5 +269,5 @@ def test_full_size_32k_properties():
     G = P_row + P_col
     G[torch.arange(256, device=dev), rows] -= 2.0
     dI_ref = scale / (2 * n) * G @ Tf
-    assert rel(di[rows], dI_ref) < GRAD_RTOL_16
+    assert rel(di[rows], dI_ref) < GRAD_RTOL_BF16_OUT
     assert math.isfinite(float(full))

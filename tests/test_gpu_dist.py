@@ -69,7 +69,7 @@ def test_nccl_cliploss_matches_oracle(dtype_name, n, d):
     ir, tr = i_all.to(dtype).float(), t_all.to(dtype).float()
     ish = [ir[r * n:(r + 1) * n] for r in range(world)]
     tsh = [tr[r * n:(r + 1) * n] for r in range(world)]
-    gtol = 2e-3 if dtype_name == "bfloat16" else 5e-5
+    gtol = 2.6e-3 if dtype_name == "bfloat16" else 5e-5   # bf16 outputs: see test_gpu_clip.py
     for key in ((True, True), (True, False), (False, True), (False, False)):
         lo, di, dt, ds = clip_loss_all_ranks(ish, tsh, 100.0, key[0], key[1])
         for r in range(world):
