@@ -64,6 +64,12 @@ int latte_device_info(int* sm_count, int* cc_major, int* cc_minor);
 int latte_clip_workspace_bytes(int64_t n_loc, int64_t n_all, int64_t dim, int dtype,
                                size_t* bytes);
 
+/* Bytes of scratch latte_clip_bwd needs: the forward scratch plus, for 16-bit features with
+ * dim <= 512, the fp16 gradient-weight blocks G [n_loc, n_all] and two fp32 [n_loc, dim]
+ * accumulators of the CTA-pair backward (csrc/clip_pair.cu). */
+int latte_clip_bwd_workspace_bytes(int64_t n_loc, int64_t n_all, int64_t dim, int dtype,
+                                   size_t* bytes);
+
 /*
  * Forward of ClipLoss on one rank.  Replaces ClipLoss.get_logits + get_ground_truth + the
  * two F.cross_entropy calls (src/open_clip/loss.py:102-118, 89-100, 126-129) without
@@ -100,6 +106,7 @@ int latte_clip_fwd(const void* img_loc, int64_t ld_img_loc,
  * cb = 0, cd = 1 (loss.py:52-55 with local_loss: gathered features carry no gradient).
  * row_lse_all / col_lse_all are the all-gathered LSE vectors [n_all] (== the local ones
  * when world_size is 1).  d_img / d_txt are [n_loc, dim] in `grad_dtype`.
+ * `workspace` is sized by latte_clip_bwd_workspace_bytes.
  */
 int latte_clip_bwd(const void* img_loc, int64_t ld_img_loc,
                    const void* txt_loc, int64_t ld_txt_loc,

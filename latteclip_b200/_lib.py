@@ -20,7 +20,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO_DIR = os.path.join(_HERE, "_C")
 SO_PATH = os.path.join(_SO_DIR, "liblatte_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
-SOURCES = ["api.cu", "clip_tc.cu", "clip_simt.cu", "nxc.cu", "proto.cu"]
+SOURCES = ["api.cu", "clip_tc.cu", "clip_pair.cu", "clip_simt.cu", "nxc.cu", "proto.cu"]
 
 F32, BF16, F16 = 0, 1, 2
 LABEL_AXIS = {"row": 0, "quirk": 1}
@@ -62,6 +62,7 @@ def _declare(lib):
     lib.latte_status_string.argtypes = [i32]
     lib.latte_device_info.argtypes = [c.POINTER(i32)] * 3
     lib.latte_clip_workspace_bytes.argtypes = [i64, i64, i64, i32, c.POINTER(sz)]
+    lib.latte_clip_bwd_workspace_bytes.argtypes = [i64, i64, i64, i32, c.POINTER(sz)]
     lib.latte_clip_fwd.argtypes = [vp, i64, vp, i64, vp, i64, vp, i64, i32, i64, i64, i64, i64,
                                    vp, vp, vp, vp, vp, sz, vp]
     lib.latte_clip_bwd.argtypes = [vp, i64, vp, i64, vp, i64, vp, i64, i32, i64, i64, i64, i64,
@@ -83,6 +84,7 @@ def _declare(lib):
 
 EXPORTS = [
     "latte_version", "latte_status_string", "latte_device_info", "latte_clip_workspace_bytes",
+    "latte_clip_bwd_workspace_bytes",
     "latte_clip_fwd", "latte_clip_bwd", "latte_normalize_rows", "latte_nxc_argmax_margin",
     "latte_nxc_topk", "latte_mix_ema_fwd", "latte_mix_ema_bwd", "latte_bank_accumulate",
     "latte_bank_finalize",
@@ -150,10 +152,10 @@ def _scalar_f32(t: torch.Tensor) -> torch.Tensor:
     return t.detach().to(torch.float32).reshape(1).contiguous()
 
 
-def _workspace(n_loc: int, n_all: int, dim: int, dtype: int, device) -> torch.Tensor:
+def _workspace(n_loc: int, n_all: int, dim: int, dtype: int, device, bwd: bool = False) -> torch.Tensor:
     nbytes = ctypes.c_size_t(0)
-    _check(load().latte_clip_workspace_bytes(n_loc, n_all, dim, dtype, ctypes.byref(nbytes)),
-           "latte_clip_workspace_bytes")
+    fn = load().latte_clip_bwd_workspace_bytes if bwd else load().latte_clip_workspace_bytes
+    _check(fn(n_loc, n_all, dim, dtype, ctypes.byref(nbytes)), "latte_clip_workspace_bytes")
     return torch.empty(nbytes.value + 256, dtype=torch.uint8, device=device)
 
 
@@ -212,7 +214,7 @@ def clip_bwd(img_loc, txt_loc, img_all, txt_all, label_offset: int, logit_scale,
     d_img = torch.empty(n_loc, dim, dtype=gdt, device=dev)
     d_txt = torch.empty(n_loc, dim, dtype=gdt, device=dev)
     d_scale = torch.empty(1, dtype=torch.float32, device=dev)
-    ws = _workspace(n_loc, n_all, dim, dt, dev)
+    ws = _workspace(n_loc, n_all, dim, dt, dev, bwd=True)
     wp, wn = _aligned_ptr(ws)
     with torch.cuda.device(dev):
         _check(lib.latte_clip_bwd(_ptr(img_loc), img_loc.stride(0), _ptr(txt_loc), txt_loc.stride(0),

@@ -110,10 +110,17 @@ struct WsLayout {
   size_t off_y16a, off_y16b;    // fp16 copies of txt_all / img_all (bf16 features only)
   size_t ld16;
   size_t n_pad, ds_cap;
+  // CTA-pair backward scratch (bwd layout only): blocked fp16 G + two fp32 accumulators
+  bool pair;
+  size_t off_g, off_acc0, off_acc1, ld32;
   size_t total;
 };
 
-WsLayout ws_layout(int64_t n_loc, int64_t n_all, int64_t dim, int dtype) {
+bool pair_shape_ok(int dtype, int64_t dim) {
+  return (dtype == LATTE_BF16 || dtype == LATTE_F16) && dim >= 8 && dim <= 512 && (dim % 8) == 0;
+}
+
+WsLayout ws_layout(int64_t n_loc, int64_t n_all, int64_t dim, int dtype, bool bwd = false) {
   WsLayout w;
   auto up = [](size_t x) { return (x + 63) / 64 * 64; };   // keep every array 256-byte aligned
   w.part = up((size_t)kMaxParts * (size_t)n_loc);
@@ -125,10 +132,10 @@ WsLayout ws_layout(int64_t n_loc, int64_t n_all, int64_t dim, int dtype) {
   w.off_pmax_c = o; o += w.part;
   w.off_psum_c = o; o += w.part;
   w.off_diag_c = o; o += nl;
-  w.n_pad = ((size_t)n_all + 127) / 128 * 128 + 128;
+  w.n_pad = ((size_t)n_all + 255) / 256 * 256 + 128;
   w.off_row2 = o; o += up(w.n_pad);
   w.off_col2 = o; o += up(w.n_pad);
-  w.ds_cap = up(2 * (((size_t)n_loc + 63) / 64));
+  w.ds_cap = up(2 * (((size_t)n_loc + 63) / 64) + 2 * 160);
   w.off_ds = o; o += w.ds_cap;
   w.ld16 = ((size_t)dim + 7) / 8 * 8;
   w.off_y16a = w.off_y16b = o;
@@ -136,6 +143,16 @@ WsLayout ws_layout(int64_t n_loc, int64_t n_all, int64_t dim, int dtype) {
     const size_t f = up(((size_t)n_all * w.ld16 + 1) / 2);   // fp16 elements counted in floats
     w.off_y16a = o; o += f;
     w.off_y16b = o; o += f;
+  }
+  w.pair = bwd && pair_shape_ok(dtype, dim);
+  w.off_g = w.off_acc0 = w.off_acc1 = o;
+  w.ld32 = ((size_t)dim + 3) / 4 * 4;
+  if (w.pair) {
+    const PairGeom geo = clip_pair_geom(n_loc, n_all);
+    w.off_g = o; o += up((geo.g_elems + 1) / 2);
+    const size_t acc = up((size_t)n_loc * w.ld32);
+    w.off_acc0 = o; o += acc;
+    w.off_acc1 = o; o += acc;
   }
   w.total = o * sizeof(float);
   return w;
@@ -181,6 +198,14 @@ extern "C" int latte_clip_workspace_bytes(int64_t n_loc, int64_t n_all, int64_t 
   LATTE_CHECK_ARG(bytes && n_loc > 0 && n_all >= n_loc && dim > 0);
   LATTE_CHECK_ARG(dtype >= LATTE_F32 && dtype <= LATTE_F16);
   *bytes = ws_layout(n_loc, n_all, dim, dtype).total;
+  return LATTE_OK;
+}
+
+extern "C" int latte_clip_bwd_workspace_bytes(int64_t n_loc, int64_t n_all, int64_t dim, int dtype,
+                                              size_t* bytes) {
+  LATTE_CHECK_ARG(bytes && n_loc > 0 && n_all >= n_loc && dim > 0);
+  LATTE_CHECK_ARG(dtype >= LATTE_F32 && dtype <= LATTE_F16);
+  *bytes = ws_layout(n_loc, n_all, dim, dtype, true).total;
   return LATTE_OK;
 }
 
@@ -247,7 +272,7 @@ extern "C" int latte_clip_bwd(const void* img_loc, int64_t ld_img_loc, const voi
   LATTE_CHECK_ARG(grad_dtype >= LATTE_F32 && grad_dtype <= LATTE_F16);
   LATTE_CHECK_ARG(ld_img_loc >= dim && ld_txt_loc >= dim && ld_img_all >= dim && ld_txt_all >= dim &&
                   ld_grad >= dim);
-  const WsLayout w = ws_layout(n_loc, n_all, dim, dtype);
+  const WsLayout w = ws_layout(n_loc, n_all, dim, dtype, true);
   if (workspace_bytes < w.total) return LATTE_ERR_WORKSPACE;
   if ((reinterpret_cast<uintptr_t>(workspace) & 255) != 0) return LATTE_ERR_BAD_ARG;
   float* ws = static_cast<float*>(workspace);
@@ -284,6 +309,60 @@ extern "C" int latte_clip_bwd(const void* img_loc, int64_t ld_img_loc, const voi
     }
     txt16 = ya; ld_txt16 = (int64_t)w.ld16;
     img16 = yb; ld_img16 = (int64_t)w.ld16;
+  }
+
+  // ---- CTA-pair path: one logit recompute -> G, then the gradient GEMMs (clip_pair.cu)
+  if (tc && w.pair &&
+      clip_pair_supported(dtype, dim, ld_img_loc, ld_txt_all, img_loc, txt_all) &&
+      clip_pair_supported(dtype, dim, ld_txt_loc, ld_img_all, txt_loc, img_all) &&
+      clip_pair_supported(LATTE_F16, dim, ld_txt16, ld_img16, txt16, img16)) {
+    const int dsn = clip_pair_ds_count();
+    if ((size_t)(2 * dsn) > w.ds_cap) return LATTE_ERR_WORKSPACE;
+    float* dsp = ws + w.off_ds;
+    __half* gbuf = reinterpret_cast<__half*>(ws + w.off_g);
+    float* acc_i = ws + w.off_acc0;
+    float* acc_t = ws + w.off_acc1;
+    const size_t acc_bytes = (size_t)n_loc * w.ld32 * sizeof(float);
+    LATTE_CUDA_OK(cudaMemsetAsync(dsp, 0, (size_t)2 * dsn * sizeof(float), st));
+    LATTE_CUDA_OK(cudaMemsetAsync(acc_i, 0, acc_bytes, st));
+    LATTE_CUDA_OK(cudaMemsetAsync(acc_t, 0, acc_bytes, st));
+    const bool single = n_loc == n_all && img_loc == img_all && txt_loc == txt_all && cross_terms;
+    PairSweepArgs sa;
+    sa.dtype = dtype; sa.n_loc = n_loc; sa.n_all = n_all; sa.dim = dim;
+    sa.label_offset = label_offset; sa.logit_scale = logit_scale; sa.cross_terms = cross_terms;
+    sa.g = gbuf; sa.ds_both = single ? 1 : 0;
+    PairGemmArgs ga;
+    ga.g = gbuf; ga.n_loc = n_loc; ga.n_all = n_all; ga.dim = dim; ga.ld32 = (int64_t)w.ld32;
+    // image side: G[loc rows, :] and d_img = G . txt_all  (+ d_txt = G^T . img for one rank)
+    sa.x = img_loc; sa.ldx = ld_img_loc; sa.y = txt_all; sa.ldy = ld_txt_all;
+    sa.lse_a2 = row2; sa.lse_b2 = col2; sa.ds_partial = dsp;
+    int rc = clip_pair_sweep(sa, st);
+    if (rc) return rc;
+    ga.y16 = txt16; ga.ldy16 = ld_txt16;
+    ga.x16 = single ? img16 : nullptr; ga.ldx16 = ld_img16;
+    ga.dx32 = acc_i; ga.dy32 = acc_t;
+    rc = clip_pair_gemm(ga, st);
+    if (rc) return rc;
+    if (!single) {
+      // text side: the transposed block G'[loc cols, :] and d_txt = G' . img_all
+      sa.x = txt_loc; sa.ldx = ld_txt_loc; sa.y = img_all; sa.ldy = ld_img_all;
+      sa.lse_a2 = col2; sa.lse_b2 = row2; sa.ds_partial = dsp + dsn;
+      rc = clip_pair_sweep(sa, st);
+      if (rc) return rc;
+      ga.y16 = img16; ga.ldy16 = ld_img16; ga.x16 = nullptr;
+      ga.dx32 = acc_t; ga.dy32 = nullptr;
+      rc = clip_pair_gemm(ga, st);
+      if (rc) return rc;
+    }
+    rc = clip_pair_scale_cast(acc_i, (int64_t)w.ld32, d_img, grad_dtype, ld_grad, n_loc, dim,
+                              grad_loss, grad_mult, logit_scale, n_loc, st);
+    if (rc) return rc;
+    rc = clip_pair_scale_cast(acc_t, (int64_t)w.ld32, d_txt, grad_dtype, ld_grad, n_loc, dim,
+                              grad_loss, grad_mult, logit_scale, n_loc, st);
+    if (rc) return rc;
+    ds_reduce_kernel<<<1, 256, 0, st>>>(dsp, 2 * dsn, grad_loss, grad_mult, n_loc, d_scale);
+    LATTE_LAUNCH_OK();
+    return LATTE_OK;
   }
 
   ClipBwdArgs a;

@@ -1,0 +1,725 @@
+// ClipLoss backward on CTA pairs (tcgen05 cta_group::2), bf16 / fp16 features, dim <= 512.
+//
+// Replaces the autograd of open_clip/loss.py:109-116 + 126-129 with three kernels that
+// execute 6*n*N*D FLOP for the 4*n*N*D credited to the backward (one logit recompute, no
+// feature-slab recompute as in clip_tc.cu):
+//
+//   pair_sweep_grad_kernel : persistent CTA pairs sweep tiles of S = X . Y^T (256 x 128 per
+//       pair).  The X row block lives in TMEM as the A operand (tcgen05.mma "TS" form, so
+//       shared memory only streams Y), S accumulates in a double-buffered TMEM tile, the
+//       epilogue warps turn it into the gradient weights
+//           G_ij = 2^13 * ( exp(S_ij - lseA_i) + cb * exp(S_ij - lseB_j) - cd * [j == label_i] )
+//       (fp16) and TMA-store them as 16 KB blocks [128 rows x 64 cols].  The logits are never
+//       stored; G is a scratch of the backward only.
+//   pair_gemm_kernel       : dX += G . Y (A K-major) and, for world size 1, dY += G^T . X
+//       (A MN-major, same G) as ONE persistent stream-K launch: 256 x 512 tiles per pair
+//       fill TMEM, partial tiles are reduced with red.global.add.v4.f32.
+//   grad_scale_cast_kernel : coef * s * 2^-13 * acc -> gradient dtype.
+#include "latte_common.cuh"
+#include "tc_ptx.cuh"
+
+namespace latte {
+
+using namespace ptx;
+
+namespace {
+
+constexpr int kThreads = 384;
+constexpr int kEpiWarp0 = 4;
+constexpr int kNumEpiWarps = 8;
+constexpr int kPM = 128;              // rows per CTA (256 per pair)
+constexpr int kTN = 128;              // S tile columns (pair MMA N)
+constexpr int kBK = 64;               // feature columns per smem chunk (128 bytes)
+constexpr int kYChunkBytes = 64 * kBK * 2;      // this CTA's half of a Y chunk: 64 rows
+constexpr int kSweepStages = 16;
+constexpr int kStageBytes = 32 * 128;           // one epilogue warp's G staging: 32 rows x 128 B
+constexpr int kMiscBytes = 1024;
+constexpr int kSweepSmem = kSweepStages * kYChunkBytes + kNumEpiWarps * kStageBytes + kMiscBytes;
+
+constexpr int kGBlockElems = 128 * 64;          // one G block: 128 rows x 64 cols fp16
+
+constexpr float kGScaleLog2 = 13.0f;
+constexpr float kGScaleInv = 1.0f / 8192.0f;
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait on a barrier that CTAs of the cluster arrive on.
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait_cluster(bar, parity)) return;
+  uint64_t t0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  uint32_t spins = 0;
+  while (!mbar_try_wait_cluster(bar, parity)) {
+    if ((++spins & 0x3ff) == 0) {
+      uint64_t t1;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      if (t1 - t0 > 4000000000ull) __trap();
+    }
+  }
+}
+
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+  __half2 v = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// =========================================================================== sweep (G)
+struct SweepParams {
+  const void* x; int64_t ldx;        // [n_loc, dim] rows of this rank (16-bit features)
+  int64_t n_loc, n_all, dim;
+  int64_t label_offset;
+  const float* logit_scale;
+  const float* lse_a2;               // base-2 LSE of the x side, indexed label_offset + i
+  const float* lse_b2;               // base-2 LSE of the y side, indexed j (zero padded)
+  float cb, cd;
+  float ds_cb, ds_cd;                // weights of the same terms inside d loss / d s
+  float* ds_partial;                 // [gridDim.x]
+  int kch;                           // ceil(dim / 64)
+  int col_tiles;                     // tiles of 128 columns (even: columns padded to 256)
+  int row_blocks;                    // blocks of 256 rows
+  int ncb;                           // G block columns = 2 * col_tiles
+  uint32_t idesc;
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+pair_sweep_grad_kernel(const __grid_constant__ CUtensorMap tmy, const __grid_constant__ CUtensorMap tmg,
+                       const SweepParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t smem_base = smem_u32(smem);
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+
+  const uint32_t ring = smem_base;
+  const uint32_t stage_base = ring + kSweepStages * kYChunkBytes;
+  const uint32_t misc = stage_base + kNumEpiWarps * kStageBytes;
+  const uint32_t bar_full = misc;                         // [kSweepStages]
+  const uint32_t bar_empty = bar_full + 8 * kSweepStages; // [kSweepStages]
+  const uint32_t bar_tfull = bar_empty + 8 * kSweepStages;  // [2]
+  const uint32_t bar_tempty = bar_tfull + 16;               // [2]   (leader's are used)
+  const uint32_t bar_aready = bar_tempty + 16;              // [1]   (leader's is used)
+  const uint32_t tmem_slot = bar_aready + 8;
+  const uint32_t red_slot = tmem_slot + 8;
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem + (tmem_slot - smem_base));
+  float* red_ptr = reinterpret_cast<float*>(smem + (red_slot - smem_base));
+
+  if (threadIdx.x == 0 && (smem_base & 1023u) != 0) __trap();
+
+  // contiguous range of the flattened (row block, column tile) space for this pair
+  const int64_t total = (int64_t)p.row_blocks * p.col_tiles;
+  const int64_t ncl = gridDim.x >> 1;
+  const int64_t cl = blockIdx.x >> 1;
+  const int64_t u0 = cl * total / ncl;
+  const int64_t u1 = (cl + 1) * total / ncl;
+
+  if (warp == 0 && elect_one()) {
+    prefetch_tensormap(&tmy);
+    prefetch_tensormap(&tmg);
+  }
+  if (warp == 1 && elect_one()) {
+    for (int s = 0; s < kSweepStages; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(bar_tfull + 8 * b, 1);
+      mbar_init(bar_tempty + 8 * b, 2 * kNumEpiWarps);
+    }
+    mbar_init(bar_aready, 2 * kNumEpiWarps);
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc_pair(tmem_slot, 512);
+    tmem_relinquish_pair();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+  const uint32_t tmem_a = tmem_base;            // X block, packed 16-bit pairs: columns [0, 256)
+  const uint32_t tmem_s = tmem_base + 256;      // two S buffers of 128 columns
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer (both CTAs)
+    if (elect_one()) {
+      const uint32_t lead_full = mapa_rank(bar_full, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int64_t t = u0; t < u1; ++t) {
+        const int ct = (int)(t % p.col_tiles);
+        for (int c = 0; c < p.kch; ++c) {
+          mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+          if (rank == 0) mbar_arrive_expect_tx(bar_full + 8 * stage, 2 * kYChunkBytes);
+          tma_load_2d_pair(ring + stage * kYChunkBytes, &tmy, lead_full + 8 * stage, c * kBK,
+                           ct * kTN + (int)rank * 64);
+          if (++stage == kSweepStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer (leader CTA)
+    if (rank == 0 && elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0, a_phase = 0;
+      int64_t cur_rb = -1;
+      int it = 0;
+      for (int64_t t = u0; t < u1; ++t, ++it) {
+        const int64_t rb = t / p.col_tiles;
+        if (rb != cur_rb) {
+          mbar_wait_cluster(bar_aready, a_phase);
+          a_phase ^= 1;
+          cur_rb = rb;
+        }
+        const int buf = it & 1;
+        mbar_wait_cluster(bar_tempty + 8 * buf, ((it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_s + buf * kTN;
+        for (int c = 0; c < p.kch; ++c) {
+          mbar_wait_cluster(bar_full + 8 * stage, phase);
+          tc_fence_after();
+          const uint32_t b_addr = ring + stage * kYChunkBytes;
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k) {
+            const uint64_t db = make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
+            mma2_ts(tmem_d, tmem_a + c * 32 + k * 8, db, p.idesc, (c | k) != 0);
+          }
+          tc_commit_pair(bar_empty + 8 * stage, 3);
+          if (++stage == kSweepStages) { stage = 0; phase ^= 1; }
+        }
+        tc_commit_pair(bar_tfull + 8 * buf, 3);
+      }
+    }
+  } else if (warp >= kEpiWarp0) {
+    // ------------------------------------------------------------ epilogue (both CTAs)
+    const int q = warp & 3;
+    const int half = (warp - kEpiWarp0) >> 2;
+    const int row = q * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    const float s = __ldg(p.logit_scale);
+    const float c2 = s * kLog2e;
+    const float cd_scaled = p.cd * 8192.0f;
+    const float ds_cd_scaled = p.ds_cd * 8192.0f;
+    const uint32_t lead_tempty = mapa_rank(bar_tempty, 0);
+    const uint32_t lead_aready = mapa_rank(bar_aready, 0);
+    const uint32_t my_stage = stage_base + (warp - kEpiWarp0) * kStageBytes;
+    float ds_acc = 0.f;
+    int64_t cur_rb = -1;
+    int64_t grow = 0, label = 0;
+    bool row_ok = false;
+    float a2 = 0.f, cb = 0.f, ds_cb = 0.f;
+    int it = 0;
+    for (int64_t t = u0; t < u1; ++t, ++it) {
+      const int64_t rb = t / p.col_tiles;
+      const int ct = (int)(t % p.col_tiles);
+      if (rb != cur_rb) {
+        // ---- new row block: this CTA's 128 rows of X -> TMEM (A operand of the TS MMA)
+        cur_rb = rb;
+        grow = rb * 256 + (int64_t)rank * kPM + row;
+        row_ok = grow < p.n_loc;
+        label = p.label_offset + grow;
+        // rows past the end: huge LSE and no cross term -> G = 0
+        a2 = row_ok ? __ldg(p.lse_a2 + label) - kGScaleLog2 : 1.0e30f;
+        cb = row_ok ? p.cb : 0.f;
+        ds_cb = row_ok ? p.ds_cb : 0.f;
+        const uint16_t* xrow =
+            reinterpret_cast<const uint16_t*>(p.x) + (row_ok ? grow : 0) * p.ldx;
+        const int groups = p.kch * 2;              // groups of 32 features = 16 packed columns
+        for (int g = half; g < groups; g += 2) {
+          uint32_t w[16];
+#pragma unroll
+          for (int v4 = 0; v4 < 4; ++v4) {
+            const int e0 = g * 32 + v4 * 8;
+            uint4 val = make_uint4(0u, 0u, 0u, 0u);
+            if (row_ok && e0 < p.dim) val = __ldg(reinterpret_cast<const uint4*>(xrow + e0));
+            w[v4 * 4 + 0] = val.x; w[v4 * 4 + 1] = val.y;
+            w[v4 * 4 + 2] = val.z; w[v4 * 4 + 3] = val.w;
+          }
+          tmem_st_32x16(tmem_a + lane_base + g * 16, w);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(lead_aready);
+      }
+
+      const int buf = it & 1;
+      mbar_wait(bar_tfull + 8 * buf, (it >> 1) & 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem_s + lane_base + buf * kTN + half * 64;
+      uint32_t r[2][32];
+      tmem_ld_32x32(taddr, r[0]);
+      tmem_ld_32x32(taddr + 32, r[1]);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(lead_tempty + 8 * buf);
+
+      const int64_t col0 = (int64_t)ct * kTN + half * 64;
+      const bool ragged = col0 + 64 > p.n_all;
+      int want = -1;
+      if (row_ok && label >= col0 && label < col0 + 64) want = (int)(label - col0);
+      const float4* pb = reinterpret_cast<const float4*>(p.lse_b2 + col0);
+      uint32_t packed[32];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+#pragma unroll
+        for (int i4 = 0; i4 < 8; ++i4) {
+          const float4 b4 = __ldg(pb + h * 8 + i4);
+          const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+          float g[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int i = i4 * 4 + e;
+            const float v = __uint_as_float(r[h][i]);
+            float ea = fast_exp2(fmaf(v, c2, -a2));
+            float eb = fast_exp2(fmaf(v, c2, kGScaleLog2 - bb[e]));
+            if (ragged && col0 + h * 32 + i >= p.n_all) { ea = 0.f; eb = 0.f; }
+            float dw = fmaf(ds_cb, eb, ea);
+            g[e] = fmaf(cb, eb, ea);
+            if (h * 32 + i == want) {
+              g[e] -= cd_scaled;
+              dw -= ds_cd_scaled;
+            }
+            ds_acc = fmaf(dw, v, ds_acc);
+          }
+          packed[h * 16 + i4 * 2 + 0] = pack2(g[0], g[1]);
+          packed[h * 16 + i4 * 2 + 1] = pack2(g[2], g[3]);
+        }
+      }
+      // ---- stage the 32 x 64 fp16 piece (128B-swizzled) and TMA-store it into its G block
+      if (lane == 0) bulk_wait_group_read<0>();
+      __syncwarp();
+      const uint32_t row_addr = my_stage + lane * 128;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        st_shared_v4(row_addr + ((uint32_t)(j ^ (lane & 7)) << 4), packed[4 * j], packed[4 * j + 1],
+                     packed[4 * j + 2], packed[4 * j + 3]);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        const int64_t block = (rb * 2 + rank) * (int64_t)p.ncb + (ct * 2 + half);
+        tma_store_2d(&tmg, my_stage, 0, (int32_t)(block * 128 + q * 32));
+        bulk_commit_group();
+      }
+    }
+    if (lane == 0) bulk_wait_group<0>();
+
+    // ---- d loss / d s partial of this CTA
+    float v = ds_acc * kGScaleInv;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) red_ptr[warp - kEpiWarp0] = v;
+    named_bar_sync(1, kNumEpiWarps * 32);
+    if (warp == kEpiWarp0 && lane == 0) {
+      float tot = 0.f;
+      for (int w = 0; w < kNumEpiWarps; ++w) tot += red_ptr[w];
+      p.ds_partial[blockIdx.x] = tot;
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 2) tmem_dealloc_pair(tmem_base, 512);
+}
+
+// =========================================================================== stream-K GEMM
+constexpr int kGemmStages = 4;
+constexpr int kGemmABytes = 128 * kBK * 2;      // 16 KB: this CTA's 128 rows (or columns) of G
+constexpr int kGemmBChunk = 64 * 64 * 2;        // 8 KB: 64 k-rows x 64 feature columns
+constexpr int kGemmStageBytes = kGemmABytes + 4 * kGemmBChunk;   // 48 KB
+constexpr int kGemmSmem = kGemmStages * kGemmStageBytes + kMiscBytes;
+
+struct GemmProblem {
+  int mode;            // 0: A = G (K-major), 1: A = G^T (MN-major)
+  int m_tiles;         // tiles of 256 output rows
+  int k_chunks;        // chunks of 64 along the contraction
+  int64_t m_rows;      // valid output rows
+  float* out;          // [m_rows, ld_out] fp32, accumulated with red.add
+  int64_t ld_out;
+};
+
+struct GemmParams {
+  GemmProblem prob[2];
+  int nprob;
+  int ncb;             // G block columns
+  int dim;
+  int nhalf;           // 64-column feature chunks per CTA = round_up(dim, 128) / 128
+  uint32_t idesc[2][2];  // [mode][mma group]
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+pair_gemm_kernel(const __grid_constant__ CUtensorMap tma0, const __grid_constant__ CUtensorMap tma1,
+                 const __grid_constant__ CUtensorMap tmb0, const __grid_constant__ CUtensorMap tmb1,
+                 const GemmParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t smem_base = smem_u32(smem);
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+
+  const uint32_t misc = smem_base + kGemmStages * kGemmStageBytes;
+  const uint32_t bar_full = misc;
+  const uint32_t bar_empty = bar_full + 8 * kGemmStages;
+  const uint32_t bar_tfull = bar_empty + 8 * kGemmStages;
+  const uint32_t bar_tempty = bar_tfull + 8;
+  const uint32_t tmem_slot = bar_tempty + 8;
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem + (tmem_slot - smem_base));
+
+  if (threadIdx.x == 0 && (smem_base & 1023u) != 0) __trap();
+
+  const int64_t units0 = (int64_t)p.prob[0].m_tiles * p.prob[0].k_chunks;
+  const int64_t units1 = p.nprob > 1 ? (int64_t)p.prob[1].m_tiles * p.prob[1].k_chunks : 0;
+  const int64_t total = units0 + units1;
+  const int64_t ncl = gridDim.x >> 1;
+  const int64_t cl = blockIdx.x >> 1;
+  const int64_t u0 = cl * total / ncl;
+  const int64_t u1 = (cl + 1) * total / ncl;
+
+  if (warp == 0 && elect_one()) {
+    prefetch_tensormap(&tma0);
+    prefetch_tensormap(&tma1);
+    prefetch_tensormap(&tmb0);
+    prefetch_tensormap(&tmb1);
+  }
+  if (warp == 1 && elect_one()) {
+    for (int s = 0; s < kGemmStages; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    mbar_init(bar_tfull, 1);
+    mbar_init(bar_tempty, 2 * kNumEpiWarps);
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc_pair(tmem_slot, 512);
+    tmem_relinquish_pair();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+  const int nmma = (p.nhalf + 1) / 2;
+
+  // A segment = (problem, output tile, contiguous chunk range); all roles walk the same list.
+  auto next_segment = [&](int64_t u, int& pi, int& mt, int& k0, int& k1) {
+    pi = u < units0 ? 0 : 1;
+    const int64_t local = u - (pi ? units0 : 0);
+    const int kc = p.prob[pi].k_chunks;
+    mt = (int)(local / kc);
+    k0 = (int)(local % kc);
+    const int64_t left = u1 - u;
+    k1 = (int)((int64_t)(kc - k0) < left ? kc : k0 + left);
+  };
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer (both CTAs)
+    if (elect_one()) {
+      const uint32_t lead_full = mapa_rank(bar_full, 0);
+      const uint32_t stage_tx = 2u * (uint32_t)(kGemmABytes + p.nhalf * kGemmBChunk);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int64_t u = u0; u < u1;) {
+        int pi, mt, k0, k1;
+        next_segment(u, pi, mt, k0, k1);
+        const int mode = p.prob[pi].mode;
+        const CUtensorMap* tb = pi ? &tmb1 : &tmb0;
+        for (int kc = k0; kc < k1; ++kc) {
+          mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+          const uint32_t sa = smem_base + stage * kGemmStageBytes;
+          const uint32_t sb = sa + kGemmABytes;
+          const uint32_t lf = lead_full + 8 * stage;
+          if (rank == 0) mbar_arrive_expect_tx(bar_full + 8 * stage, stage_tx);
+          if (mode == 0) {
+            const int64_t block = (int64_t)(2 * mt + (int)rank) * p.ncb + kc;
+            tma_load_2d_pair(sa, &tma0, lf, 0, (int32_t)(block * 128));
+          } else {
+            const int64_t block = (int64_t)(kc >> 1) * p.ncb + 4 * mt + 2 * (int)rank;
+            const int32_t r0 = (int32_t)(block * 128 + (kc & 1) * 64);
+            tma_load_2d_pair(sa, &tma1, lf, 0, r0);
+            tma_load_2d_pair(sa + 8192, &tma1, lf, 0, r0 + 128);
+          }
+          for (int lc = 0; lc < p.nhalf; ++lc) {
+            const int g = lc >> 1;
+            const int cnt = min(2, p.nhalf - 2 * g);
+            const int dchunk = 4 * g + (int)rank * cnt + (lc - 2 * g);
+            tma_load_2d_pair(sb + lc * kGemmBChunk, tb, lf, dchunk * 64, kc * 64);
+          }
+          if (++stage == kGemmStages) { stage = 0; phase ^= 1; }
+        }
+        u += k1 - k0;
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer (leader CTA)
+    if (rank == 0 && elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int seg = 0;
+      for (int64_t u = u0; u < u1; ++seg) {
+        int pi, mt, k0, k1;
+        next_segment(u, pi, mt, k0, k1);
+        const int mode = p.prob[pi].mode;
+        mbar_wait_cluster(bar_tempty, (seg & 1) ^ 1);
+        tc_fence_after();
+        for (int kc = k0; kc < k1; ++kc) {
+          mbar_wait_cluster(bar_full + 8 * stage, phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * kGemmStageBytes;
+          const uint32_t sb = sa + kGemmABytes;
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k) {
+            const uint64_t da = mode == 0 ? make_smem_desc_sw128(sa + k * 32, 16, 1024)
+                                          : make_smem_desc_sw128(sa + k * 2048, 8192, 1024);
+            for (int g = 0; g < nmma; ++g) {
+              const uint64_t db = make_smem_desc_sw128(sb + g * 2 * kGemmBChunk + k * 2048, 8192, 1024);
+              mma2_ss(tmem_base + g * 256, da, db, p.idesc[mode][g], (kc > k0 || k > 0) ? 1u : 0u);
+            }
+          }
+          tc_commit_pair(bar_empty + 8 * stage, 3);
+          if (++stage == kGemmStages) { stage = 0; phase ^= 1; }
+        }
+        tc_commit_pair(bar_tfull, 3);
+        u += k1 - k0;
+      }
+    }
+  } else if (warp >= kEpiWarp0) {
+    // ------------------------------------------------------------ epilogue (both CTAs)
+    const int q = warp & 3;
+    const int half = (warp - kEpiWarp0) >> 2;
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    const uint32_t lead_tempty = mapa_rank(bar_tempty, 0);
+    const int cols_half = p.nhalf * 64;          // accumulator columns per epilogue half
+    int seg = 0;
+    for (int64_t u = u0; u < u1; ++seg) {
+      int pi, mt, k0, k1;
+      next_segment(u, pi, mt, k0, k1);
+      const GemmProblem& pr = p.prob[pi];
+      const int64_t m = (int64_t)mt * 256 + (int64_t)rank * kPM + q * 32 + lane;
+      const bool m_ok = m < pr.m_rows;
+      float* orow = pr.out + (m_ok ? m : 0) * pr.ld_out;
+      mbar_wait(bar_tfull, seg & 1);
+      tc_fence_after();
+      for (int cc = 0; cc < cols_half; cc += 32) {
+        const int col = half * cols_half + cc;
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + lane_base + col, v);
+        tmem_ld_wait();
+        if (m_ok) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            if (col + i < p.dim)
+              red_add_v4(orow + col + i, __uint_as_float(v[i]), __uint_as_float(v[i + 1]),
+                         __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(lead_tempty);
+      u += k1 - k0;
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 2) tmem_dealloc_pair(tmem_base, 512);
+}
+
+// out[i, d] = coef * s * 2^-13 * acc[i, d]   (coef = grad_loss * grad_mult / (2 n_loc))
+__global__ void grad_scale_cast_kernel(const float* acc, int64_t ld_acc, void* out, int out_dtype,
+                                       int64_t ld_out, int64_t rows, int64_t dim,
+                                       const float* grad_loss, float grad_mult,
+                                       const float* logit_scale, int64_t n_loc) {
+  const int64_t per_row = dim / 4;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * per_row) return;
+  const int64_t r = idx / per_row, c = (idx % per_row) * 4;
+  const float cs = __ldg(grad_loss) * grad_mult / (2.0f * (float)n_loc) * __ldg(logit_scale) * kGScaleInv;
+  const float4 a = *reinterpret_cast<const float4*>(acc + r * ld_acc + c);
+  const float o[4] = {a.x * cs, a.y * cs, a.z * cs, a.w * cs};
+  if (out_dtype == LATTE_F32) {
+    float* po = reinterpret_cast<float*>(out) + r * ld_out + c;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) po[k] = o[k];
+  } else if (out_dtype == LATTE_BF16) {
+    __nv_bfloat16* po = reinterpret_cast<__nv_bfloat16*>(out) + r * ld_out + c;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) po[k] = __float2bfloat16_rn(o[k]);
+  } else {
+    __half* po = reinterpret_cast<__half*>(out) + r * ld_out + c;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) po[k] = __float2half_rn(o[k]);
+  }
+}
+
+// =========================================================================== host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = []() -> EncodeTiledFn {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess)
+      return nullptr;
+    if (q != cudaDriverEntryPointSuccess) return nullptr;
+    return reinterpret_cast<EncodeTiledFn>(f);
+  }();
+  return fn;
+}
+
+// 16-bit row-major [rows, cols] (row pitch ld elements) -> boxes [box_rows x 64 cols], 128B swizzle
+int make_map16(CUtensorMap* map, const void* base, int dtype, int64_t rows, int64_t cols, int64_t ld,
+               int box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return LATTE_ERR_CUDA;
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, dtype == LATTE_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+                                           : CU_TENSOR_MAP_DATA_TYPE_FLOAT16,
+                  2, const_cast<void*>(base), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? LATTE_OK : LATTE_ERR_CUDA;
+}
+
+}  // namespace
+
+bool clip_pair_supported(int dtype, int64_t dim, int64_t ldx, int64_t ldy, const void* x,
+                         const void* y) {
+  if (dtype != LATTE_BF16 && dtype != LATTE_F16) return false;
+  if (dim < 8 || dim > 512 || (dim % 8) != 0) return false;
+  if ((ldx % 8) != 0 || (ldy % 8) != 0) return false;
+  if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(y) & 15)) return false;
+  return true;
+}
+
+PairGeom clip_pair_geom(int64_t n_loc, int64_t n_all) {
+  PairGeom g;
+  g.row_blocks = (int)((n_loc + 255) / 256);
+  g.col_tiles = (int)((n_all + 255) / 256) * 2;
+  g.ncb = g.col_tiles * 2;
+  g.g_elems = (size_t)g.row_blocks * 2 * (size_t)g.ncb * kGBlockElems;
+  return g;
+}
+
+int clip_pair_ds_count() { return device_sm_count() / 2 * 2; }
+
+int clip_pair_sweep(const PairSweepArgs& a, cudaStream_t stream) {
+  if (!clip_pair_supported(a.dtype, a.dim, a.ldx, a.ldy, a.x, a.y)) return LATTE_ERR_UNSUPPORTED;
+  const PairGeom geo = clip_pair_geom(a.n_loc, a.n_all);
+  CUtensorMap tmy, tmg;
+  int rc = make_map16(&tmy, a.y, a.dtype, a.n_all, a.dim, a.ldy, 64);
+  if (rc) return rc;
+  // blocked view of G: every 16 KB block is 128 consecutive rows of a [blocks*128, 64] matrix
+  const int64_t g_rows = (int64_t)geo.row_blocks * 2 * geo.ncb * 128;
+  rc = make_map16(&tmg, a.g, LATTE_F16, g_rows, 64, 64, 32);
+  if (rc) return rc;
+  SweepParams p;
+  p.x = a.x; p.ldx = a.ldx;
+  p.n_loc = a.n_loc; p.n_all = a.n_all; p.dim = a.dim;
+  p.label_offset = a.label_offset;
+  p.logit_scale = a.logit_scale;
+  p.lse_a2 = a.lse_a2; p.lse_b2 = a.lse_b2;
+  p.cb = a.cross_terms ? 1.f : 0.f;
+  p.cd = a.cross_terms ? 2.f : 1.f;
+  // one sweep standing for both directions (world size 1) carries both softmax terms in ds
+  p.ds_cb = a.ds_both ? p.cb : 0.f;
+  p.ds_cd = a.ds_both ? p.cd : 1.f;
+  p.ds_partial = a.ds_partial;
+  p.kch = (int)((a.dim + kBK - 1) / kBK);
+  p.col_tiles = geo.col_tiles;
+  p.row_blocks = geo.row_blocks;
+  p.ncb = geo.ncb;
+  p.idesc = make_idesc_f16(256, kTN, a.dtype == LATTE_BF16 ? 1u : 0u, 0, 0);
+  int ncl = device_sm_count() / 2;
+  const int64_t total = (int64_t)geo.row_blocks * geo.col_tiles;
+  if (total < ncl) ncl = (int)total;
+  LATTE_CUDA_OK(cudaFuncSetAttribute(pair_sweep_grad_kernel,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, kSweepSmem));
+  // every CTA of the launch writes its ds partial; unused slots are zeroed by the caller
+  pair_sweep_grad_kernel<<<2 * ncl, kThreads, kSweepSmem, stream>>>(tmy, tmg, p);
+  LATTE_LAUNCH_OK();
+  return LATTE_OK;
+}
+
+int clip_pair_gemm(const PairGemmArgs& a, cudaStream_t stream) {
+  const PairGeom geo = clip_pair_geom(a.n_loc, a.n_all);
+  const int64_t g_rows = (int64_t)geo.row_blocks * 2 * geo.ncb * 128;
+  CUtensorMap tma0, tma1, tmb0, tmb1;
+  int rc = make_map16(&tma0, a.g, LATTE_F16, g_rows, 64, 64, 128);
+  if (rc) return rc;
+  rc = make_map16(&tma1, a.g, LATTE_F16, g_rows, 64, 64, 64);
+  if (rc) return rc;
+  rc = make_map16(&tmb0, a.y16, LATTE_F16, a.n_all, a.dim, a.ldy16, 64);
+  if (rc) return rc;
+  rc = make_map16(&tmb1, a.x16 ? a.x16 : a.y16, LATTE_F16, a.x16 ? a.n_loc : a.n_all, a.dim,
+                  a.x16 ? a.ldx16 : a.ldy16, 64);
+  if (rc) return rc;
+  GemmParams p;
+  p.nprob = a.x16 ? 2 : 1;
+  p.ncb = geo.ncb;
+  p.dim = (int)a.dim;
+  p.nhalf = (int)((a.dim + 127) / 128);
+  // dX = G . Y : rows of this rank, contraction over all columns
+  p.prob[0].mode = 0;
+  p.prob[0].m_tiles = geo.row_blocks;
+  p.prob[0].k_chunks = (int)((a.n_all + 63) / 64);
+  p.prob[0].m_rows = a.n_loc;
+  p.prob[0].out = a.dx32;
+  p.prob[0].ld_out = a.ld32;
+  // dY = G^T . X : (world size 1) rows = columns of G, contraction over the rows of G
+  p.prob[1].mode = 1;
+  p.prob[1].m_tiles = geo.col_tiles / 2;
+  p.prob[1].k_chunks = (int)((a.n_loc + 63) / 64);
+  p.prob[1].m_rows = a.n_all;
+  p.prob[1].out = a.dy32;
+  p.prob[1].ld_out = a.ld32;
+  for (int mode = 0; mode < 2; ++mode)
+    for (int g = 0; g < 2; ++g) {
+      const int cnt = p.nhalf - 2 * g >= 2 ? 2 : (p.nhalf - 2 * g == 1 ? 1 : 0);
+      p.idesc[mode][g] = cnt ? make_idesc_f16(256, 2 * cnt * 64, 0u, mode, 1) : 0u;
+    }
+  int64_t total = (int64_t)p.prob[0].m_tiles * p.prob[0].k_chunks;
+  if (p.nprob > 1) total += (int64_t)p.prob[1].m_tiles * p.prob[1].k_chunks;
+  int ncl = device_sm_count() / 2;
+  if (total < ncl) ncl = (int)total;
+  LATTE_CUDA_OK(cudaFuncSetAttribute(pair_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     kGemmSmem));
+  pair_gemm_kernel<<<2 * ncl, kThreads, kGemmSmem, stream>>>(tma0, tma1, tmb0, tmb1, p);
+  LATTE_LAUNCH_OK();
+  return LATTE_OK;
+}
+
+int clip_pair_scale_cast(const float* acc, int64_t ld_acc, void* out, int out_dtype, int64_t ld_out,
+                         int64_t rows, int64_t dim, const float* grad_loss, float grad_mult,
+                         const float* logit_scale, int64_t n_loc, cudaStream_t stream) {
+  const int64_t work = rows * (dim / 4);
+  grad_scale_cast_kernel<<<(unsigned)((work + 255) / 256), 256, 0, stream>>>(
+      acc, ld_acc, out, out_dtype, ld_out, rows, dim, grad_loss, grad_mult, logit_scale, n_loc);
+  LATTE_LAUNCH_OK();
+  return LATTE_OK;
+}
+
+}  // namespace latte

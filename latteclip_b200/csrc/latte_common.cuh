@@ -79,6 +79,45 @@ int clip_tc_nparts(int64_t n_loc, int64_t n_all, int sm_count);
 int clip_tc_ds_count(int64_t n_loc, int64_t dim);
 bool clip_tc_supported(int dtype, int64_t dim, int64_t ldx, int64_t ldy, const void* x, const void* y);
 
+// CTA-pair backward (clip_pair.cu): gradient-weight sweep + stream-K gradient GEMMs, dim <= 512.
+struct PairGeom {
+  int row_blocks;     // blocks of 256 rows of the x side
+  int col_tiles;      // tiles of 128 columns (even)
+  int ncb;            // 64-column G blocks per block row
+  size_t g_elems;     // fp16 elements of the blocked G scratch
+};
+struct PairSweepArgs {
+  const void* x; int64_t ldx;
+  const void* y; int64_t ldy;
+  int dtype;
+  int64_t n_loc, n_all, dim;
+  int64_t label_offset;
+  const float* logit_scale;
+  const float* lse_a2;
+  const float* lse_b2;
+  int cross_terms;
+  int ds_both;                // 1: d loss / d s takes both softmax terms from this sweep
+  void* g;                    // blocked fp16 G scratch (PairGeom::g_elems)
+  float* ds_partial;          // [clip_pair_ds_count()] zeroed by the caller
+};
+struct PairGemmArgs {
+  const void* g;
+  const void* y16; int64_t ldy16;   // fp16 [n_all, dim]
+  const void* x16; int64_t ldx16;   // fp16 [n_loc, dim] or NULL (no transposed product)
+  int64_t n_loc, n_all, dim;
+  float* dx32;                      // [n_loc, ld32] zeroed
+  float* dy32;                      // [n_all, ld32] zeroed (with x16)
+  int64_t ld32;
+};
+bool clip_pair_supported(int dtype, int64_t dim, int64_t ldx, int64_t ldy, const void* x, const void* y);
+PairGeom clip_pair_geom(int64_t n_loc, int64_t n_all);
+int clip_pair_ds_count();
+int clip_pair_sweep(const PairSweepArgs& a, cudaStream_t stream);
+int clip_pair_gemm(const PairGemmArgs& a, cudaStream_t stream);
+int clip_pair_scale_cast(const float* acc, int64_t ld_acc, void* out, int out_dtype, int64_t ld_out,
+                         int64_t rows, int64_t dim, const float* grad_loss, float grad_mult,
+                         const float* logit_scale, int64_t n_loc, cudaStream_t stream);
+
 // fp32 SIMT path (fp32 features; exact fp32 products).
 int clip_fwd_rows_simt(const ClipFwdArgs& a, cudaStream_t stream);
 int clip_bwd_rows_simt(const ClipBwdArgs& a, cudaStream_t stream);
