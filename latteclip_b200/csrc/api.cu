@@ -13,7 +13,6 @@ int device_sm_count() {
 
 namespace {
 
-constexpr int kFinalThreads = 1024;
 constexpr int kMaxParts = 16;
 
 // Merge the per-(split, half) online-softmax partials of one row into a base-2 LSE.
@@ -29,21 +28,24 @@ __device__ __forceinline__ float merge_parts(const float* pmax, const float* psu
   return M + log2f(L);
 }
 
-// row_lse / col_lse in natural-log units and the scalar loss (loss.py:126-129).
-__global__ void __launch_bounds__(kFinalThreads)
+// row_lse / col_lse in natural-log units and per-block partial sums of the loss terms
+// (loss.py:126-129); loss_reduce_kernel adds the partials.
+constexpr int kFinalRows = 256;
+__global__ void __launch_bounds__(kFinalRows)
 clip_finalize_kernel(const float* pmax_r, const float* psum_r, const float* diag_r,
                      const float* pmax_c, const float* psum_c, const float* diag_c, int nparts,
                      int64_t n_loc, const float* logit_scale, float* row_lse, float* col_lse,
-                     float* loss) {
-  __shared__ double red[kFinalThreads / 32];
+                     double* loss_partial) {
+  __shared__ double red[kFinalRows / 32];
   const float s = __ldg(logit_scale);
   double acc = 0.0;
-  for (int64_t i = threadIdx.x; i < n_loc; i += kFinalThreads) {
+  const int64_t i = (int64_t)blockIdx.x * kFinalRows + threadIdx.x;
+  if (i < n_loc) {
     const float lr = merge_parts(pmax_r, psum_r, nparts, n_loc, i) * kLn2;
     const float lc = merge_parts(pmax_c, psum_c, nparts, n_loc, i) * kLn2;
     row_lse[i] = lr;
     col_lse[i] = lc;
-    acc += (double)(lr - s * diag_r[i]) + (double)(lc - s * diag_c[i]);
+    acc = (double)(lr - s * diag_r[i]) + (double)(lc - s * diag_c[i]);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
@@ -51,18 +53,73 @@ clip_finalize_kernel(const float* pmax_r, const float* psum_r, const float* diag
   __syncthreads();
   if (threadIdx.x == 0) {
     double tot = 0.0;
-    for (int w = 0; w < kFinalThreads / 32; ++w) tot += red[w];
+    for (int w = 0; w < kFinalRows / 32; ++w) tot += red[w];
+    loss_partial[blockIdx.x] = tot;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+loss_reduce_kernel(const double* partial, int count, int64_t n_loc, float* loss) {
+  __shared__ double red[8];
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < count; i += 256) acc += partial[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tot = 0.0;
+    for (int w = 0; w < 8; ++w) tot += red[w];
     *loss = (float)(tot / (2.0 * (double)n_loc));
   }
 }
 
-// natural-log LSE -> base-2 units, zero padded to a multiple of the 128-column tile
-__global__ void lse_to_base2_kernel(const float* row_lse, const float* col_lse, int64_t n_all,
-                                    int64_t n_pad, float* row2, float* col2) {
+// Range of all LSE values (base 2): rho = mid-point; flag = 1 when max - min <= 64, so that
+// 2^(lse - rho) and products of two such factors stay well inside fp32 range (clip_pair.cu's
+// one-ex2 epilogue); otherwise the sweep uses its two-ex2 epilogue.
+__global__ void __launch_bounds__(1024)
+lse_range_kernel(const float* row_lse, const float* col_lse, int64_t n_all, float* rho, int* flag) {
+  __shared__ float smin[32], smax[32];
+  float lo = INFINITY, hi = -INFINITY;
+  for (int64_t i = threadIdx.x; i < n_all; i += 1024) {
+    const float a = row_lse[i], b = col_lse[i];
+    lo = fminf(lo, fminf(a, b));
+    hi = fmaxf(hi, fmaxf(a, b));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+  }
+  if ((threadIdx.x & 31) == 0) { smin[threadIdx.x >> 5] = lo; smax[threadIdx.x >> 5] = hi; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 0; w < 32; ++w) { lo = fminf(lo, smin[w]); hi = fmaxf(hi, smax[w]); }
+    lo *= kLog2e; hi *= kLog2e;
+    const bool ok = (hi - lo) <= 64.0f && hi < 3.0e38f && lo > -3.0e38f;   // also rejects NaN / inf
+    *rho = ok ? 0.5f * (lo + hi) : 0.f;
+    *flag = ok ? 1 : 0;
+  }
+}
+
+// natural-log LSE -> base-2 units (zero padded to the tile grid) and the rank-one factors
+__global__ void lse_vectors_kernel(const float* row_lse, const float* col_lse, int64_t n_all,
+                                   int64_t n_pad, const float* rho_p, float* row2, float* col2,
+                                   float* e_row, float* einv_row, float* e_col, float* einv_col) {
   const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n_pad) return;
-  row2[j] = j < n_all ? row_lse[j] * kLog2e : 0.f;
-  col2[j] = j < n_all ? col_lse[j] * kLog2e : 0.f;
+  const bool in = j < n_all;
+  const float r2 = in ? row_lse[j] * kLog2e : 0.f;
+  const float c2 = in ? col_lse[j] * kLog2e : 0.f;
+  row2[j] = r2;
+  col2[j] = c2;
+  if (e_row) {
+    const float rho = *rho_p;
+    e_row[j] = in ? exp2f(r2 - rho) : 0.f;
+    einv_row[j] = in ? exp2f(rho - r2) : 0.f;
+    e_col[j] = in ? exp2f(c2 - rho) : 0.f;
+    einv_col[j] = in ? exp2f(rho - c2) : 0.f;
+  }
 }
 
 __global__ void __launch_bounds__(256)
@@ -106,13 +163,14 @@ __global__ void bf16_to_fp16_kernel(const __nv_bfloat16* in, int64_t ld_in, __ha
 struct WsLayout {
   size_t part;      // floats per partial array (kMaxParts * n_loc)
   size_t off_pmax_r, off_psum_r, off_diag_r, off_pmax_c, off_psum_c, off_diag_c;
-  size_t off_row2, off_col2, off_ds;
+  size_t off_row2, off_col2, off_ds, off_lossp;
   size_t off_y16a, off_y16b;    // fp16 copies of txt_all / img_all (bf16 features only)
   size_t ld16;
   size_t n_pad, ds_cap;
   // CTA-pair backward scratch (bwd layout only): blocked fp16 G + two fp32 accumulators
   bool pair;
   size_t off_g, off_acc0, off_acc1, ld32;
+  size_t off_rho, off_erow, off_einvrow, off_ecol, off_einvcol;
   size_t total;
 };
 
@@ -137,6 +195,7 @@ WsLayout ws_layout(int64_t n_loc, int64_t n_all, int64_t dim, int dtype, bool bw
   w.off_col2 = o; o += up(w.n_pad);
   w.ds_cap = up(2 * (((size_t)n_loc + 63) / 64) + 2 * 160);
   w.off_ds = o; o += w.ds_cap;
+  w.off_lossp = o; o += up(2 * (((size_t)n_loc + 255) / 256) + 2);   // doubles
   w.ld16 = ((size_t)dim + 7) / 8 * 8;
   w.off_y16a = w.off_y16b = o;
   if (dtype == LATTE_BF16) {
@@ -147,7 +206,13 @@ WsLayout ws_layout(int64_t n_loc, int64_t n_all, int64_t dim, int dtype, bool bw
   w.pair = bwd && pair_shape_ok(dtype, dim);
   w.off_g = w.off_acc0 = w.off_acc1 = o;
   w.ld32 = ((size_t)dim + 3) / 4 * 4;
+  w.off_rho = w.off_erow = w.off_einvrow = w.off_ecol = w.off_einvcol = o;
   if (w.pair) {
+    w.off_rho = o; o += 64;
+    w.off_erow = o; o += up(w.n_pad);
+    w.off_einvrow = o; o += up(w.n_pad);
+    w.off_ecol = o; o += up(w.n_pad);
+    w.off_einvcol = o; o += up(w.n_pad);
     const PairGeom geo = clip_pair_geom(n_loc, n_all);
     w.off_g = o; o += up((geo.g_elems + 1) / 2);
     const size_t acc = up((size_t)n_loc * w.ld32);
@@ -248,9 +313,13 @@ extern "C" int latte_clip_fwd(const void* img_loc, int64_t ld_img_loc, const voi
   a.part_max = ws + w.off_pmax_c; a.part_sum = ws + w.off_psum_c; a.diag = ws + w.off_diag_c;
   rc = tc ? clip_fwd_rows_tc(a, st) : clip_fwd_rows_simt(a, st);
   if (rc) return rc;
-  clip_finalize_kernel<<<1, kFinalThreads, 0, st>>>(
+  const int fblocks = (int)((n_loc + kFinalRows - 1) / kFinalRows);
+  double* lossp = reinterpret_cast<double*>(ws + w.off_lossp);
+  clip_finalize_kernel<<<fblocks, kFinalRows, 0, st>>>(
       ws + w.off_pmax_r, ws + w.off_psum_r, ws + w.off_diag_r, ws + w.off_pmax_c,
-      ws + w.off_psum_c, ws + w.off_diag_c, nparts, n_loc, logit_scale, row_lse, col_lse, loss);
+      ws + w.off_psum_c, ws + w.off_diag_c, nparts, n_loc, logit_scale, row_lse, col_lse, lossp);
+  LATTE_LAUNCH_OK();
+  loss_reduce_kernel<<<1, 256, 0, st>>>(lossp, fblocks, n_loc, loss);
   LATTE_LAUNCH_OK();
   return LATTE_OK;
 }
@@ -280,8 +349,15 @@ extern "C" int latte_clip_bwd(const void* img_loc, int64_t ld_img_loc, const voi
 
   float* row2 = ws + w.off_row2;
   float* col2 = ws + w.off_col2;
-  lse_to_base2_kernel<<<(unsigned)((w.n_pad + 255) / 256), 256, 0, st>>>(
-      row_lse_all, col_lse_all, n_all, (int64_t)w.n_pad, row2, col2);
+  float* rho = ws + w.off_rho;
+  int* fast_flag = reinterpret_cast<int*>(ws + w.off_rho + 1);
+  if (w.pair) {
+    lse_range_kernel<<<1, 1024, 0, st>>>(row_lse_all, col_lse_all, n_all, rho, fast_flag);
+    LATTE_LAUNCH_OK();
+  }
+  lse_vectors_kernel<<<(unsigned)((w.n_pad + 255) / 256), 256, 0, st>>>(
+      row_lse_all, col_lse_all, n_all, (int64_t)w.n_pad, rho, row2, col2,
+      w.pair ? ws + w.off_erow : nullptr, ws + w.off_einvrow, ws + w.off_ecol, ws + w.off_einvcol);
   LATTE_LAUNCH_OK();
 
   const bool tc = use_tc(dtype, dim, img_loc, ld_img_loc, txt_all, ld_txt_all, txt_loc,
@@ -336,6 +412,7 @@ extern "C" int latte_clip_bwd(const void* img_loc, int64_t ld_img_loc, const voi
     // image side: G[loc rows, :] and d_img = G . txt_all  (+ d_txt = G^T . img for one rank)
     sa.x = img_loc; sa.ldx = ld_img_loc; sa.y = txt_all; sa.ldy = ld_txt_all;
     sa.lse_a2 = row2; sa.lse_b2 = col2; sa.ds_partial = dsp;
+    sa.e_a = ws + w.off_erow; sa.einv_b = ws + w.off_einvcol; sa.fast_flag = fast_flag;
     int rc = clip_pair_sweep(sa, st);
     if (rc) return rc;
     ga.y16 = txt16; ga.ldy16 = ld_txt16;
@@ -347,6 +424,7 @@ extern "C" int latte_clip_bwd(const void* img_loc, int64_t ld_img_loc, const voi
       // text side: the transposed block G'[loc cols, :] and d_txt = G' . img_all
       sa.x = txt_loc; sa.ldx = ld_txt_loc; sa.y = img_all; sa.ldy = ld_img_all;
       sa.lse_a2 = col2; sa.lse_b2 = row2; sa.ds_partial = dsp + dsn;
+      sa.e_a = ws + w.off_ecol; sa.einv_b = ws + w.off_einvrow;
       rc = clip_pair_sweep(sa, st);
       if (rc) return rc;
       ga.y16 = img16; ga.ldy16 = ld_img16; ga.x16 = nullptr;

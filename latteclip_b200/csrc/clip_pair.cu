@@ -34,7 +34,9 @@ constexpr int kYChunkBytes = 64 * kBK * 2;      // this CTA's half of a Y chunk:
 constexpr int kSweepStages = 16;
 constexpr int kStageBytes = 32 * 128;           // one epilogue warp's G staging: 32 rows x 128 B
 constexpr int kMiscBytes = 1024;
-constexpr int kSweepSmem = kSweepStages * kYChunkBytes + kNumEpiWarps * kStageBytes + kMiscBytes;
+constexpr int kVecBytes = 64 * 4;               // one epilogue warp's column factors of a tile
+constexpr int kSweepSmem = kSweepStages * kYChunkBytes + kNumEpiWarps * (kStageBytes + kVecBytes) +
+                           kMiscBytes;
 
 constexpr int kGBlockElems = 128 * 64;          // one G block: 128 rows x 64 cols fp16
 
@@ -43,34 +45,6 @@ constexpr float kGScaleInv = 1.0f / 8192.0f;
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
-
-__device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t"
-      ".reg .pred P;\n\t"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, P;\n\t"
-      "}\n"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-// Bounded wait on a barrier that CTAs of the cluster arrive on.
-__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
-  if (mbar_try_wait_cluster(bar, parity)) return;
-  uint64_t t0;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-  uint32_t spins = 0;
-  while (!mbar_try_wait_cluster(bar, parity)) {
-    if ((++spins & 0x3ff) == 0) {
-      uint64_t t1;
-      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-      if (t1 - t0 > 4000000000ull) __trap();
-    }
-  }
 }
 
 __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
@@ -86,6 +60,9 @@ struct SweepParams {
   const float* logit_scale;
   const float* lse_a2;               // base-2 LSE of the x side, indexed label_offset + i
   const float* lse_b2;               // base-2 LSE of the y side, indexed j (zero padded)
+  const float* e_a;                  // 2^(lse_a2 - rho)   (x side, indexed like lse_a2)
+  const float* einv_b;               // 2^(rho - lse_b2)   (y side, indexed j)
+  const int* fast_flag;              // 1: the LSE range allows the one-ex2 epilogue
   float cb, cd;
   float ds_cb, ds_cd;                // weights of the same terms inside d loss / d s
   float* ds_partial;                 // [gridDim.x]
@@ -107,7 +84,8 @@ pair_sweep_grad_kernel(const __grid_constant__ CUtensorMap tmy, const __grid_con
 
   const uint32_t ring = smem_base;
   const uint32_t stage_base = ring + kSweepStages * kYChunkBytes;
-  const uint32_t misc = stage_base + kNumEpiWarps * kStageBytes;
+  const uint32_t vec_base = stage_base + kNumEpiWarps * kStageBytes;
+  const uint32_t misc = vec_base + kNumEpiWarps * kVecBytes;
   const uint32_t bar_full = misc;                         // [kSweepStages]
   const uint32_t bar_empty = bar_full + 8 * kSweepStages; // [kSweepStages]
   const uint32_t bar_tfull = bar_empty + 8 * kSweepStages;  // [2]
@@ -159,6 +137,7 @@ pair_sweep_grad_kernel(const __grid_constant__ CUtensorMap tmy, const __grid_con
     // ------------------------------------------------------------ TMA producer (both CTAs)
     if (elect_one()) {
       const uint32_t lead_full = mapa_rank(bar_full, 0);
+      const uint64_t keep = policy_evict_last();      // features are re-read by every pair
       int stage = 0;
       uint32_t phase = 0;
       for (int64_t t = u0; t < u1; ++t) {
@@ -166,8 +145,8 @@ pair_sweep_grad_kernel(const __grid_constant__ CUtensorMap tmy, const __grid_con
         for (int c = 0; c < p.kch; ++c) {
           mbar_wait(bar_empty + 8 * stage, phase ^ 1);
           if (rank == 0) mbar_arrive_expect_tx(bar_full + 8 * stage, 2 * kYChunkBytes);
-          tma_load_2d_pair(ring + stage * kYChunkBytes, &tmy, lead_full + 8 * stage, c * kBK,
-                           ct * kTN + (int)rank * 64);
+          tma_load_2d_pair_hint(ring + stage * kYChunkBytes, &tmy, lead_full + 8 * stage, c * kBK,
+                                ct * kTN + (int)rank * 64, keep);
           if (++stage == kSweepStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -182,16 +161,16 @@ pair_sweep_grad_kernel(const __grid_constant__ CUtensorMap tmy, const __grid_con
       for (int64_t t = u0; t < u1; ++t, ++it) {
         const int64_t rb = t / p.col_tiles;
         if (rb != cur_rb) {
-          mbar_wait_cluster(bar_aready, a_phase);
+          mbar_wait(bar_aready, a_phase);
           a_phase ^= 1;
           cur_rb = rb;
         }
         const int buf = it & 1;
-        mbar_wait_cluster(bar_tempty + 8 * buf, ((it >> 1) & 1) ^ 1);
+        mbar_wait(bar_tempty + 8 * buf, ((it >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_s + buf * kTN;
         for (int c = 0; c < p.kch; ++c) {
-          mbar_wait_cluster(bar_full + 8 * stage, phase);
+          mbar_wait(bar_full + 8 * stage, phase);
           tc_fence_after();
           const uint32_t b_addr = ring + stage * kYChunkBytes;
 #pragma unroll
@@ -218,11 +197,27 @@ pair_sweep_grad_kernel(const __grid_constant__ CUtensorMap tmy, const __grid_con
     const uint32_t lead_tempty = mapa_rank(bar_tempty, 0);
     const uint32_t lead_aready = mapa_rank(bar_aready, 0);
     const uint32_t my_stage = stage_base + (warp - kEpiWarp0) * kStageBytes;
+    const uint64_t stream_pol = policy_evict_first();   // G is written once, read once
     float ds_acc = 0.f;
     int64_t cur_rb = -1;
     int64_t grow = 0, label = 0;
     bool row_ok = false;
     float a2 = 0.f, cb = 0.f, ds_cb = 0.f;
+    float off_h = 0.f, cbA = 0.f;
+    int64_t warp_label0 = 0;
+    const float c2h = 0.5f * c2;
+    const bool fast = __ldg(p.fast_flag) != 0;
+    const bool ds_both = p.ds_cb != 0.f;
+    // column factors B_j of the current half tile, staged per warp in shared memory one tile
+    // ahead (a broadcast LDG inside the loop would expose the global-load latency)
+    float* my_vec = reinterpret_cast<float*>(smem + (vec_base - smem_base) +
+                                             (warp - kEpiWarp0) * kVecBytes);
+    if (u0 < u1) {
+      const int64_t c0 = (u0 % p.col_tiles) * kTN + half * 64;
+      my_vec[lane] = __ldg(p.einv_b + c0 + lane);
+      my_vec[32 + lane] = __ldg(p.einv_b + c0 + 32 + lane);
+      __syncwarp();
+    }
     int it = 0;
     for (int64_t t = u0; t < u1; ++t, ++it) {
       const int64_t rb = t / p.col_tiles;
@@ -237,6 +232,9 @@ pair_sweep_grad_kernel(const __grid_constant__ CUtensorMap tmy, const __grid_con
         a2 = row_ok ? __ldg(p.lse_a2 + label) - kGScaleLog2 : 1.0e30f;
         cb = row_ok ? p.cb : 0.f;
         ds_cb = row_ok ? p.ds_cb : 0.f;
+        warp_label0 = p.label_offset + rb * 256 + (int64_t)rank * kPM + q * 32;
+        off_h = row_ok ? 0.5f * (kGScaleLog2 - __ldg(p.lse_a2 + label)) : -1.0e30f;
+        cbA = (row_ok && fast) ? p.cb * __ldg(p.e_a + label) : 0.f;
         const uint16_t* xrow =
             reinterpret_cast<const uint16_t*>(p.x) + (row_ok ? grow : 0) * p.ldx;
         const int groups = p.kch * 2;              // groups of 32 features = 16 packed columns
@@ -258,6 +256,12 @@ pair_sweep_grad_kernel(const __grid_constant__ CUtensorMap tmy, const __grid_con
         if (lane == 0) mbar_arrive_cluster(lead_aready);
       }
 
+      float bn0 = 0.f, bn1 = 0.f;
+      if (t + 1 < u1) {
+        const int64_t cn = ((t + 1) % p.col_tiles) * kTN + half * 64;
+        bn0 = __ldg(p.einv_b + cn + lane);
+        bn1 = __ldg(p.einv_b + cn + 32 + lane);
+      }
       const int buf = it & 1;
       mbar_wait(bar_tfull + 8 * buf, (it >> 1) & 1);
       tc_fence_after();
@@ -272,39 +276,69 @@ pair_sweep_grad_kernel(const __grid_constant__ CUtensorMap tmy, const __grid_con
 
       const int64_t col0 = (int64_t)ct * kTN + half * 64;
       const bool ragged = col0 + 64 > p.n_all;
-      int want = -1;
-      if (row_ok && label >= col0 && label < col0 + 64) want = (int)(label - col0);
-      const float4* pb = reinterpret_cast<const float4*>(p.lse_b2 + col0);
+      // labels of this warp's 32 rows are consecutive: does this half tile hold any of them?
+      const bool diag_tile = warp_label0 < col0 + 64 && warp_label0 + 32 > col0;
       uint32_t packed[32];
+      if (fast && !ragged && !diag_tile) {
+        // One ex2 per logit: ea = h*h with h = 2^((x - a_i + 13)/2); the y-side softmax term
+        // is ea * 2^(a_i - b_j) = ea * A_i * B_j (rank one; the vectors come from the prep
+        // kernel, which also verified that the LSE range keeps every factor in fp32 range).
+        const float4* pB = reinterpret_cast<const float4*>(my_vec);
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
+        for (int h = 0; h < 2; ++h) {
 #pragma unroll
-        for (int i4 = 0; i4 < 8; ++i4) {
-          const float4 b4 = __ldg(pb + h * 8 + i4);
-          const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
-          float g[4];
+          for (int i4 = 0; i4 < 8; ++i4) {
+            const float4 b4 = pB[h * 8 + i4];
+            const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+            float g[4];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int i = i4 * 4 + e;
-            const float v = __uint_as_float(r[h][i]);
-            float ea = fast_exp2(fmaf(v, c2, -a2));
-            float eb = fast_exp2(fmaf(v, c2, kGScaleLog2 - bb[e]));
-            if (ragged && col0 + h * 32 + i >= p.n_all) { ea = 0.f; eb = 0.f; }
-            float dw = fmaf(ds_cb, eb, ea);
-            g[e] = fmaf(cb, eb, ea);
-            if (h * 32 + i == want) {
-              g[e] -= cd_scaled;
-              dw -= ds_cd_scaled;
+            for (int e = 0; e < 4; ++e) {
+              const float v = __uint_as_float(r[h][i4 * 4 + e]);
+              const float hh = fast_exp2(fmaf(v, c2h, off_h));
+              const float ea = hh * hh;
+              g[e] = ea * fmaf(cbA, bb[e], 1.0f);
+              ds_acc = fmaf(ds_both ? g[e] : ea, v, ds_acc);
             }
-            ds_acc = fmaf(dw, v, ds_acc);
+            packed[h * 16 + i4 * 2 + 0] = pack2(g[0], g[1]);
+            packed[h * 16 + i4 * 2 + 1] = pack2(g[2], g[3]);
           }
-          packed[h * 16 + i4 * 2 + 0] = pack2(g[0], g[1]);
-          packed[h * 16 + i4 * 2 + 1] = pack2(g[2], g[3]);
+        }
+      } else {
+        int want = -1;
+        if (row_ok && label >= col0 && label < col0 + 64) want = (int)(label - col0);
+        const float4* pb = reinterpret_cast<const float4*>(p.lse_b2 + col0);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+#pragma unroll
+          for (int i4 = 0; i4 < 8; ++i4) {
+            const float4 b4 = __ldg(pb + h * 8 + i4);
+            const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+            float g[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int i = i4 * 4 + e;
+              const float v = __uint_as_float(r[h][i]);
+              float ea = fast_exp2(fmaf(v, c2, -a2));
+              float eb = fast_exp2(fmaf(v, c2, kGScaleLog2 - bb[e]));
+              if (ragged && col0 + h * 32 + i >= p.n_all) { ea = 0.f; eb = 0.f; }
+              float dw = fmaf(ds_cb, eb, ea);
+              g[e] = fmaf(cb, eb, ea);
+              if (h * 32 + i == want) {
+                g[e] -= cd_scaled;
+                dw -= ds_cd_scaled;
+              }
+              ds_acc = fmaf(dw, v, ds_acc);
+            }
+            packed[h * 16 + i4 * 2 + 0] = pack2(g[0], g[1]);
+            packed[h * 16 + i4 * 2 + 1] = pack2(g[2], g[3]);
+          }
         }
       }
       // ---- stage the 32 x 64 fp16 piece (128B-swizzled) and TMA-store it into its G block
       if (lane == 0) bulk_wait_group_read<0>();
       __syncwarp();
+      my_vec[lane] = bn0;            // column factors of the next tile
+      my_vec[32 + lane] = bn1;
       const uint32_t row_addr = my_stage + lane * 128;
 #pragma unroll
       for (int j = 0; j < 8; ++j)
@@ -314,7 +348,7 @@ pair_sweep_grad_kernel(const __grid_constant__ CUtensorMap tmy, const __grid_con
       __syncwarp();
       if (lane == 0) {
         const int64_t block = (rb * 2 + rank) * (int64_t)p.ncb + (ct * 2 + half);
-        tma_store_2d(&tmg, my_stage, 0, (int32_t)(block * 128 + q * 32));
+        tma_store_2d_hint(&tmg, my_stage, 0, (int32_t)(block * 128 + q * 32), stream_pol);
         bulk_commit_group();
       }
     }
@@ -433,6 +467,8 @@ pair_gemm_kernel(const __grid_constant__ CUtensorMap tma0, const __grid_constant
     if (elect_one()) {
       const uint32_t lead_full = mapa_rank(bar_full, 0);
       const uint32_t stage_tx = 2u * (uint32_t)(kGemmABytes + p.nhalf * kGemmBChunk);
+      const uint64_t keep = policy_evict_last();        // features: re-read by every tile
+      const uint64_t stream_pol = policy_evict_first(); // G: read once per product
       int stage = 0;
       uint32_t phase = 0;
       for (int64_t u = u0; u < u1;) {
@@ -448,18 +484,18 @@ pair_gemm_kernel(const __grid_constant__ CUtensorMap tma0, const __grid_constant
           if (rank == 0) mbar_arrive_expect_tx(bar_full + 8 * stage, stage_tx);
           if (mode == 0) {
             const int64_t block = (int64_t)(2 * mt + (int)rank) * p.ncb + kc;
-            tma_load_2d_pair(sa, &tma0, lf, 0, (int32_t)(block * 128));
+            tma_load_2d_pair_hint(sa, &tma0, lf, 0, (int32_t)(block * 128), stream_pol);
           } else {
             const int64_t block = (int64_t)(kc >> 1) * p.ncb + 4 * mt + 2 * (int)rank;
             const int32_t r0 = (int32_t)(block * 128 + (kc & 1) * 64);
-            tma_load_2d_pair(sa, &tma1, lf, 0, r0);
-            tma_load_2d_pair(sa + 8192, &tma1, lf, 0, r0 + 128);
+            tma_load_2d_pair_hint(sa, &tma1, lf, 0, r0, stream_pol);
+            tma_load_2d_pair_hint(sa + 8192, &tma1, lf, 0, r0 + 128, stream_pol);
           }
           for (int lc = 0; lc < p.nhalf; ++lc) {
             const int g = lc >> 1;
             const int cnt = min(2, p.nhalf - 2 * g);
             const int dchunk = 4 * g + (int)rank * cnt + (lc - 2 * g);
-            tma_load_2d_pair(sb + lc * kGemmBChunk, tb, lf, dchunk * 64, kc * 64);
+            tma_load_2d_pair_hint(sb + lc * kGemmBChunk, tb, lf, dchunk * 64, kc * 64, keep);
           }
           if (++stage == kGemmStages) { stage = 0; phase ^= 1; }
         }
@@ -476,10 +512,10 @@ pair_gemm_kernel(const __grid_constant__ CUtensorMap tma0, const __grid_constant
         int pi, mt, k0, k1;
         next_segment(u, pi, mt, k0, k1);
         const int mode = p.prob[pi].mode;
-        mbar_wait_cluster(bar_tempty, (seg & 1) ^ 1);
+        mbar_wait(bar_tempty, (seg & 1) ^ 1);
         tc_fence_after();
         for (int kc = k0; kc < k1; ++kc) {
-          mbar_wait_cluster(bar_full + 8 * stage, phase);
+          mbar_wait(bar_full + 8 * stage, phase);
           tc_fence_after();
           const uint32_t sa = smem_base + stage * kGemmStageBytes;
           const uint32_t sb = sa + kGemmABytes;
@@ -642,6 +678,7 @@ int clip_pair_sweep(const PairSweepArgs& a, cudaStream_t stream) {
   p.label_offset = a.label_offset;
   p.logit_scale = a.logit_scale;
   p.lse_a2 = a.lse_a2; p.lse_b2 = a.lse_b2;
+  p.e_a = a.e_a; p.einv_b = a.einv_b; p.fast_flag = a.fast_flag;
   p.cb = a.cross_terms ? 1.f : 0.f;
   p.cd = a.cross_terms ? 2.f : 1.f;
   // one sweep standing for both directions (world size 1) carries both softmax terms in ds

@@ -95,6 +95,9 @@ struct PairSweepArgs {
   const float* logit_scale;
   const float* lse_a2;
   const float* lse_b2;
+  const float* e_a;           // 2^(lse_a2 - rho)
+  const float* einv_b;        // 2^(rho - lse_b2)
+  const int* fast_flag;       // device flag: LSE range small enough for the one-ex2 epilogue
   int cross_terms;
   int ds_both;                // 1: d loss / d s takes both softmax terms from this sweep
   void* g;                    // blocked fp16 G scratch (PairGeom::g_elems)
