@@ -58,6 +58,76 @@ clip_finalize_kernel(const float* pmax_r, const float* psum_r, const float* diag
   }
 }
 
+// ---- CTA-pair forward (clip_pair.cu): merge the slot partials of a row
+__global__ void __launch_bounds__(256)
+pair_row_finalize_kernel(const float* pmax, const float* psum, int64_t n_loc, int col_tiles,
+                         int64_t total, int ncl, float* lse_out) {
+  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (i >= n_loc) return;
+  const int64_t rb = i / 256;
+  const int64_t c0 = cluster_of_tile(rb * col_tiles, total, ncl);
+  const int64_t c1 = cluster_of_tile(rb * col_tiles + col_tiles - 1, total, ncl);
+  const int nparts = 2 * (int)(c1 - c0 + 1);
+  lse_out[i] = merge_parts(pmax, psum, nparts, n_loc, i) * kLn2;
+}
+
+// Column LSE from the per-128-row-block partial sums.  Terms below 2^-126 of a block's
+// reference were flushed; if that could matter for a column (its LSE sits more than ~95
+// binary orders below the largest block reference) the exact fallback is requested.
+__global__ void __launch_bounds__(256)
+pair_col_finalize_kernel(const float* col_part, const float* col_ref, int64_t ld, int nblk,
+                         int col_tiles, int64_t n_all, float* col_lse, int* flag) {
+  const int64_t j = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (j >= n_all) return;
+  const int64_t ht = j / 64;
+  float M = -INFINITY, L = 0.f;
+  for (int b = 0; b < nblk; ++b) {
+    const float mb = col_ref[(int64_t)b * 2 * col_tiles + ht];
+    if (!(mb > -INFINITY)) continue;
+    const float c = col_part[(int64_t)b * ld + j];
+    if (mb > M) {
+      L = L * exp2f(M - mb) + c;
+      M = mb;
+    } else {
+      L = fmaf(c, exp2f(mb - M), L);
+    }
+  }
+  const float lse2 = M + log2f(L);
+  col_lse[j] = lse2 * kLn2;
+  const bool ok = (M - lse2) + log2f((float)nblk) < 95.0f;    // false for NaN / -inf too
+  if (!ok) atomicOr(flag, 1);
+}
+
+// Fallback only: overwrite col_lse with the exact row-kernel result when requested.
+__global__ void __launch_bounds__(256)
+gated_merge_kernel(const int* gate, const float* pmax, const float* psum, int nparts,
+                   int64_t n_loc, float* lse_out) {
+  if (*gate == 0) return;
+  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (i >= n_loc) return;
+  lse_out[i] = merge_parts(pmax, psum, nparts, n_loc, i) * kLn2;
+}
+
+__global__ void __launch_bounds__(256)
+lse_loss_partial_kernel(const float* row_lse, const float* col_lse, const float* diag_r,
+                        const float* diag_c, const float* logit_scale, int64_t n_loc,
+                        double* loss_partial) {
+  __shared__ double red[8];
+  const float s = __ldg(logit_scale);
+  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  double acc = 0.0;
+  if (i < n_loc) acc = (double)(row_lse[i] - s * diag_r[i]) + (double)(col_lse[i] - s * diag_c[i]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tot = 0.0;
+    for (int w = 0; w < 8; ++w) tot += red[w];
+    loss_partial[blockIdx.x] = tot;
+  }
+}
+
 __global__ void __launch_bounds__(256)
 loss_reduce_kernel(const double* partial, int count, int64_t n_loc, float* loss) {
   __shared__ double red[8];
@@ -171,6 +241,9 @@ struct WsLayout {
   bool pair;
   size_t off_g, off_acc0, off_acc1, ld32;
   size_t off_rho, off_erow, off_einvrow, off_ecol, off_einvcol;
+  // CTA-pair forward scratch (fwd layout only)
+  bool pair_fwd;
+  size_t off_pp_max_r, off_pp_sum_r, off_pp_max_c, off_pp_sum_c, off_colpart, off_colref, off_flag;
   size_t total;
 };
 
@@ -218,6 +291,20 @@ WsLayout ws_layout(int64_t n_loc, int64_t n_all, int64_t dim, int dtype, bool bw
     const size_t acc = up((size_t)n_loc * w.ld32);
     w.off_acc0 = o; o += acc;
     w.off_acc1 = o; o += acc;
+  }
+  w.pair_fwd = !bwd && pair_shape_ok(dtype, dim);
+  w.off_pp_max_r = w.off_pp_sum_r = w.off_pp_max_c = w.off_pp_sum_c = o;
+  w.off_colpart = w.off_colref = w.off_flag = o;
+  if (w.pair_fwd) {
+    const PairFwdGeom f = clip_pair_fwd_geom(n_loc, n_all);
+    const size_t pp = up((size_t)2 * f.slots * (size_t)n_loc);
+    w.off_pp_max_r = o; o += pp;
+    w.off_pp_sum_r = o; o += pp;
+    w.off_pp_max_c = o; o += pp;
+    w.off_pp_sum_c = o; o += pp;
+    w.off_colpart = o; o += up((size_t)2 * f.row_blocks * (size_t)f.ld_colpart);
+    w.off_colref = o; o += up((size_t)2 * f.row_blocks * 2 * (size_t)f.col_tiles);
+    w.off_flag = o; o += 64;
   }
   w.total = o * sizeof(float);
   return w;
@@ -303,6 +390,65 @@ extern "C" int latte_clip_fwd(const void* img_loc, int64_t ld_img_loc, const voi
   ClipFwdArgs a;
   a.dtype = dtype; a.n_loc = n_loc; a.n_all = n_all; a.dim = dim;
   a.label_offset = label_offset; a.logit_scale = logit_scale; a.nparts = nparts;
+  a.gate = nullptr;
+
+  // ---- CTA-pair path (clip_pair.cu): TS-mode sweep; for one rank the column sums come from
+  // the same logit tiles as the row sums, so S is computed once.
+  if (tc && w.pair_fwd &&
+      clip_pair_supported(dtype, dim, ld_img_loc, ld_txt_all, img_loc, txt_all) &&
+      clip_pair_supported(dtype, dim, ld_txt_loc, ld_img_all, txt_loc, img_all)) {
+    const PairFwdGeom f = clip_pair_fwd_geom(n_loc, n_all);
+    const bool single = n_loc == n_all && img_loc == img_all && txt_loc == txt_all;
+    const unsigned rblocks = (unsigned)((n_loc + 255) / 256);
+    double* lossp = reinterpret_cast<double*>(ws + w.off_lossp);
+    PairFwdArgs pa;
+    pa.dtype = dtype; pa.n_loc = n_loc; pa.n_all = n_all; pa.dim = dim;
+    pa.label_offset = label_offset; pa.logit_scale = logit_scale;
+    pa.x = img_loc; pa.ldx = ld_img_loc; pa.y = txt_all; pa.ldy = ld_txt_all;
+    pa.part_max = ws + w.off_pp_max_r; pa.part_sum = ws + w.off_pp_sum_r; pa.diag = ws + w.off_diag_r;
+    pa.col_part = single ? ws + w.off_colpart : nullptr;
+    pa.col_ref = ws + w.off_colref;
+    int rc = clip_pair_fwd_sweep(pa, st);
+    if (rc) return rc;
+    pair_row_finalize_kernel<<<rblocks, 256, 0, st>>>(pa.part_max, pa.part_sum, n_loc, f.col_tiles,
+                                                      f.total, f.ncl, row_lse);
+    LATTE_LAUNCH_OK();
+    const float* diag_c = ws + w.off_diag_r;
+    if (single) {
+      int* flag = reinterpret_cast<int*>(ws + w.off_flag);
+      LATTE_CUDA_OK(cudaMemsetAsync(flag, 0, sizeof(int), st));
+      pair_col_finalize_kernel<<<(unsigned)((n_all + 255) / 256), 256, 0, st>>>(
+          ws + w.off_colpart, ws + w.off_colref, f.ld_colpart, 2 * f.row_blocks, f.col_tiles, n_all,
+          col_lse, flag);
+      LATTE_LAUNCH_OK();
+      // exact fallback for columns whose partial sums may have lost flushed terms: the row
+      // kernel on the transposed problem; it and the merge return at once unless flagged
+      a.gate = flag;
+      a.x = txt_loc; a.ldx = ld_txt_loc; a.y = img_all; a.ldy = ld_img_all;
+      a.part_max = ws + w.off_pmax_c; a.part_sum = ws + w.off_psum_c; a.diag = ws + w.off_diag_c;
+      rc = clip_fwd_rows_tc(a, st);
+      if (rc) return rc;
+      gated_merge_kernel<<<rblocks, 256, 0, st>>>(flag, a.part_max, a.part_sum, nparts, n_loc, col_lse);
+      LATTE_LAUNCH_OK();
+    } else {
+      pa.x = txt_loc; pa.ldx = ld_txt_loc; pa.y = img_all; pa.ldy = ld_img_all;
+      pa.part_max = ws + w.off_pp_max_c; pa.part_sum = ws + w.off_pp_sum_c; pa.diag = ws + w.off_diag_c;
+      pa.col_part = nullptr;
+      rc = clip_pair_fwd_sweep(pa, st);
+      if (rc) return rc;
+      pair_row_finalize_kernel<<<rblocks, 256, 0, st>>>(pa.part_max, pa.part_sum, n_loc, f.col_tiles,
+                                                        f.total, f.ncl, col_lse);
+      LATTE_LAUNCH_OK();
+      diag_c = ws + w.off_diag_c;
+    }
+    lse_loss_partial_kernel<<<rblocks, 256, 0, st>>>(row_lse, col_lse, ws + w.off_diag_r, diag_c,
+                                                     logit_scale, n_loc, lossp);
+    LATTE_LAUNCH_OK();
+    loss_reduce_kernel<<<1, 256, 0, st>>>(lossp, (int)rblocks, n_loc, loss);
+    LATTE_LAUNCH_OK();
+    return LATTE_OK;
+  }
+
   // image -> text: rows of logits_per_image (loss.py:109 / :115)
   a.x = img_loc; a.ldx = ld_img_loc; a.y = txt_all; a.ldy = ld_txt_all;
   a.part_max = ws + w.off_pmax_r; a.part_sum = ws + w.off_psum_r; a.diag = ws + w.off_diag_r;

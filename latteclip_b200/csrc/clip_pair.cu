@@ -4,7 +4,7 @@
 // execute 6*n*N*D FLOP for the 4*n*N*D credited to the backward (one logit recompute, no
 // feature-slab recompute as in clip_tc.cu):
 //
-//   pair_sweep_grad_kernel : persistent CTA pairs sweep tiles of S = X . Y^T (256 x 128 per
+//   pair_sweep_kernel<Grad>: persistent CTA pairs sweep tiles of S = X . Y^T (256 x 128 per
 //       pair).  The X row block lives in TMEM as the A operand (tcgen05.mma "TS" form, so
 //       shared memory only streams Y), S accumulates in a double-buffered TMEM tile, the
 //       epilogue warps turn it into the gradient weights
@@ -66,6 +66,14 @@ struct SweepParams {
   float cb, cd;
   float ds_cb, ds_cd;                // weights of the same terms inside d loss / d s
   float* ds_partial;                 // [gridDim.x]
+  // forward modes: per-(slot, half) online-softmax partials of the rows, raw label dots,
+  // and (kModeFwdBoth) per-128-row-block column partial sums with their reference exponents
+  float* part_max;                   // [2 * slots, n_loc]
+  float* part_sum;
+  float* diag;                       // [n_loc]
+  float* col_part;                   // [2 * row_blocks, ld_colpart]
+  float* col_ref;                    // [2 * row_blocks, 2 * col_tiles]
+  int64_t ld_colpart;
   int kch;                           // ceil(dim / 64)
   int col_tiles;                     // tiles of 128 columns (even: columns padded to 256)
   int row_blocks;                    // blocks of 256 rows
@@ -73,9 +81,14 @@ struct SweepParams {
   uint32_t idesc;
 };
 
+constexpr int kModeGrad = 0;      // backward: gradient weights G
+constexpr int kModeFwdRows = 1;   // forward: row log-sum-exp partials
+constexpr int kModeFwdBoth = 2;   // forward, world size 1: row partials + column partials of the same tile
+
+template <int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
-pair_sweep_grad_kernel(const __grid_constant__ CUtensorMap tmy, const __grid_constant__ CUtensorMap tmg,
-                       const SweepParams p) {
+pair_sweep_kernel(const __grid_constant__ CUtensorMap tmy, const __grid_constant__ CUtensorMap tmg,
+                  const SweepParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t smem_base = smem_u32(smem);
   const int warp = threadIdx.x >> 5;
@@ -186,6 +199,7 @@ pair_sweep_grad_kernel(const __grid_constant__ CUtensorMap tmy, const __grid_con
     }
   } else if (warp >= kEpiWarp0) {
     // ------------------------------------------------------------ epilogue (both CTAs)
+    if constexpr (MODE == kModeGrad) {
     const int q = warp & 3;
     const int half = (warp - kEpiWarp0) >> 2;
     const int row = q * 32 + lane;
@@ -364,6 +378,172 @@ pair_sweep_grad_kernel(const __grid_constant__ CUtensorMap tmy, const __grid_con
       float tot = 0.f;
       for (int w = 0; w < kNumEpiWarps; ++w) tot += red_ptr[w];
       p.ds_partial[blockIdx.x] = tot;
+    }
+  
+    } else {
+      // ======================================================== forward epilogue
+      const int q = warp & 3;
+      const int half = (warp - kEpiWarp0) >> 2;
+      const int row = q * 32 + lane;
+      const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+      const float c2 = __ldg(p.logit_scale) * kLog2e;
+      const uint32_t lead_tempty = mapa_rank(bar_tempty, 0);
+      const uint32_t lead_aready = mapa_rank(bar_aready, 0);
+      // column-partial exchange between the four lane-quarter warps of one tile half
+      float* colbuf = reinterpret_cast<float*>(smem + (stage_base - smem_base));   // [2][2][4][64]
+      float* refbuf = colbuf + 2 * 2 * 4 * 64;                                      // [2][2][4]
+      int64_t cur_rb = -1;
+      int64_t grow = 0, label = 0, warp_label0 = 0;
+      bool row_ok = false;
+      float m = -INFINITY, l = 0.f;
+      auto flush_rows = [&]() {
+        if (cur_rb >= 0 && row_ok) {
+          const int64_t slot = cl - cluster_of_tile(cur_rb * p.col_tiles, total, ncl);
+          const int64_t idx = (slot * 2 + half) * p.n_loc + grow;
+          p.part_max[idx] = m;
+          p.part_sum[idx] = l;
+        }
+      };
+      int it = 0;
+      for (int64_t t = u0; t < u1; ++t, ++it) {
+        const int64_t rb = t / p.col_tiles;
+        const int ct = (int)(t % p.col_tiles);
+        if (rb != cur_rb) {
+          flush_rows();
+          cur_rb = rb;
+          grow = rb * 256 + (int64_t)rank * kPM + row;
+          row_ok = grow < p.n_loc;
+          label = p.label_offset + grow;
+          warp_label0 = p.label_offset + rb * 256 + (int64_t)rank * kPM + q * 32;
+          m = -INFINITY;
+          l = 0.f;
+          const uint16_t* xrow =
+              reinterpret_cast<const uint16_t*>(p.x) + (row_ok ? grow : 0) * p.ldx;
+          const int groups = p.kch * 2;
+          for (int g = half; g < groups; g += 2) {
+            uint32_t w[16];
+#pragma unroll
+            for (int v4 = 0; v4 < 4; ++v4) {
+              const int e0 = g * 32 + v4 * 8;
+              uint4 val = make_uint4(0u, 0u, 0u, 0u);
+              if (row_ok && e0 < p.dim) val = __ldg(reinterpret_cast<const uint4*>(xrow + e0));
+              w[v4 * 4 + 0] = val.x; w[v4 * 4 + 1] = val.y;
+              w[v4 * 4 + 2] = val.z; w[v4 * 4 + 3] = val.w;
+            }
+            tmem_st_32x16(tmem_a + lane_base + g * 16, w);
+          }
+          tmem_st_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(lead_aready);
+        }
+
+        const int buf = it & 1;
+        mbar_wait(bar_tfull + 8 * buf, (it >> 1) & 1);
+        tc_fence_after();
+        const uint32_t taddr = tmem_s + lane_base + buf * kTN + half * 64;
+        uint32_t r[2][32];
+        tmem_ld_32x32(taddr, r[0]);
+        tmem_ld_32x32(taddr + 32, r[1]);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(lead_tempty + 8 * buf);
+
+        const int64_t col0 = (int64_t)ct * kTN + half * 64;
+        if (col0 + 64 > p.n_all) {
+#pragma unroll
+          for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (col0 + h * 32 + i >= p.n_all) r[h][i] = 0xff800000u;  // -inf
+        }
+        if (warp_label0 < col0 + 64 && warp_label0 + 32 > col0) {      // warp-uniform
+          if (row_ok && label >= col0 && label < col0 + 64) {
+            const int want = (int)(label - col0);
+            float dv = 0.f;
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (h * 32 + i == want) dv = __uint_as_float(r[h][i]);
+            p.diag[grow] = dv;
+          }
+        }
+        float tmax0 = -INFINITY, tmax1 = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          tmax0 = fmaxf(tmax0, __uint_as_float(r[0][i]));
+          tmax1 = fmaxf(tmax1, __uint_as_float(r[1][i]));
+        }
+        const float m_new = fmaxf(m, fmaxf(tmax0, tmax1) * c2);
+        if (m_new > -INFINITY) {
+          float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float e0 = fast_exp2(fmaf(__uint_as_float(r[0][i]), c2, -m_new));
+            const float e1 = fast_exp2(fmaf(__uint_as_float(r[1][i]), c2, -m_new));
+            acc0 += e0;
+            acc1 += e1;
+            if constexpr (MODE == kModeFwdBoth) {
+              r[0][i] = __float_as_uint(e0);
+              r[1][i] = __float_as_uint(e1);
+            }
+          }
+          l = l * fast_exp2(m - m_new) + (acc0 + acc1);
+          m = m_new;
+        } else if constexpr (MODE == kModeFwdBoth) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) { r[0][i] = 0u; r[1][i] = 0u; }
+        }
+
+        if constexpr (MODE == kModeFwdBoth) {
+          // Column sums of the same exponentials: weight row i by 2^(m_i - M_w) (M_w = largest
+          // running max of the warp's rows), add over the 32 lanes with a halving butterfly
+          // (lane c ends with column c), then merge the four lane-quarter warps in smem.
+          float mw = row_ok ? m : -INFINITY;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) mw = fmaxf(mw, __shfl_xor_sync(0xffffffffu, mw, o));
+          const float w = (row_ok && m > -INFINITY) ? fast_exp2(m - mw) : 0.f;
+          float cs[2];
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            float v[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[h][i]) * w;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+              const bool up = (lane & o) != 0;
+#pragma unroll
+              for (int k = 0; k < o; ++k) {
+                const float send = up ? v[k] : v[k + o];
+                const float keep = up ? v[k + o] : v[k];
+                v[k] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+              }
+            }
+            cs[h] = v[0];
+          }
+          const int par = it & 1;
+          float* cb_w = colbuf + ((par * 2 + half) * 4 + q) * 64;
+          cb_w[lane] = cs[0];
+          cb_w[32 + lane] = cs[1];
+          if (lane == 0) refbuf[(par * 2 + half) * 4 + q] = mw;
+          named_bar_sync(1 + half, 128);
+          if (lane < 16) {
+            const float* rf = refbuf + (par * 2 + half) * 4;
+            const float* cbh = colbuf + (par * 2 + half) * 4 * 64;
+            const float M = fmaxf(fmaxf(rf[0], rf[1]), fmaxf(rf[2], rf[3]));
+            float c = 0.f;
+#pragma unroll
+            for (int qq = 0; qq < 4; ++qq)
+              if (rf[qq] > -INFINITY) c = fmaf(cbh[qq * 64 + q * 16 + lane], fast_exp2(rf[qq] - M), c);
+            const int64_t rblk = rb * 2 + rank;
+            p.col_part[rblk * p.ld_colpart + col0 + q * 16 + lane] = c;
+            if (q == 0 && lane == 0) p.col_ref[rblk * (2 * p.col_tiles) + ct * 2 + half] = M;
+          }
+        }
+      }
+      flush_rows();
     }
   }
 
@@ -662,6 +842,51 @@ PairGeom clip_pair_geom(int64_t n_loc, int64_t n_all) {
 
 int clip_pair_ds_count() { return device_sm_count() / 2 * 2; }
 
+PairFwdGeom clip_pair_fwd_geom(int64_t n_loc, int64_t n_all) {
+  const PairGeom geo = clip_pair_geom(n_loc, n_all);
+  PairFwdGeom f;
+  f.row_blocks = geo.row_blocks;
+  f.col_tiles = geo.col_tiles;
+  f.total = (int64_t)geo.row_blocks * geo.col_tiles;
+  f.ncl = device_sm_count() / 2;
+  if (f.total < f.ncl) f.ncl = (int)f.total;
+  const int64_t tpc = f.total / f.ncl;              // >= 1 tiles per cluster
+  f.slots = (int)((geo.col_tiles + tpc - 1) / tpc + 1);
+  f.ld_colpart = (int64_t)geo.col_tiles * kTN;
+  return f;
+}
+
+int clip_pair_fwd_sweep(const PairFwdArgs& a, cudaStream_t stream) {
+  if (!clip_pair_supported(a.dtype, a.dim, a.ldx, a.ldy, a.x, a.y)) return LATTE_ERR_UNSUPPORTED;
+  const PairFwdGeom f = clip_pair_fwd_geom(a.n_loc, a.n_all);
+  CUtensorMap tmy;
+  int rc = make_map16(&tmy, a.y, a.dtype, a.n_all, a.dim, a.ldy, 64);
+  if (rc) return rc;
+  SweepParams p = {};
+  p.x = a.x; p.ldx = a.ldx;
+  p.n_loc = a.n_loc; p.n_all = a.n_all; p.dim = a.dim;
+  p.label_offset = a.label_offset;
+  p.logit_scale = a.logit_scale;
+  p.part_max = a.part_max; p.part_sum = a.part_sum; p.diag = a.diag;
+  p.col_part = a.col_part; p.col_ref = a.col_ref; p.ld_colpart = f.ld_colpart;
+  p.kch = (int)((a.dim + kBK - 1) / kBK);
+  p.col_tiles = f.col_tiles;
+  p.row_blocks = f.row_blocks;
+  p.ncb = f.col_tiles * 2;
+  p.idesc = make_idesc_f16(256, kTN, a.dtype == LATTE_BF16 ? 1u : 0u, 0, 0);
+  if (a.col_part) {
+    LATTE_CUDA_OK(cudaFuncSetAttribute(pair_sweep_kernel<kModeFwdBoth>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, kSweepSmem));
+    pair_sweep_kernel<kModeFwdBoth><<<2 * f.ncl, kThreads, kSweepSmem, stream>>>(tmy, tmy, p);
+  } else {
+    LATTE_CUDA_OK(cudaFuncSetAttribute(pair_sweep_kernel<kModeFwdRows>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, kSweepSmem));
+    pair_sweep_kernel<kModeFwdRows><<<2 * f.ncl, kThreads, kSweepSmem, stream>>>(tmy, tmy, p);
+  }
+  LATTE_LAUNCH_OK();
+  return LATTE_OK;
+}
+
 int clip_pair_sweep(const PairSweepArgs& a, cudaStream_t stream) {
   if (!clip_pair_supported(a.dtype, a.dim, a.ldx, a.ldy, a.x, a.y)) return LATTE_ERR_UNSUPPORTED;
   const PairGeom geo = clip_pair_geom(a.n_loc, a.n_all);
@@ -672,7 +897,7 @@ int clip_pair_sweep(const PairSweepArgs& a, cudaStream_t stream) {
   const int64_t g_rows = (int64_t)geo.row_blocks * 2 * geo.ncb * 128;
   rc = make_map16(&tmg, a.g, LATTE_F16, g_rows, 64, 64, 32);
   if (rc) return rc;
-  SweepParams p;
+  SweepParams p = {};
   p.x = a.x; p.ldx = a.ldx;
   p.n_loc = a.n_loc; p.n_all = a.n_all; p.dim = a.dim;
   p.label_offset = a.label_offset;
@@ -693,10 +918,10 @@ int clip_pair_sweep(const PairSweepArgs& a, cudaStream_t stream) {
   int ncl = device_sm_count() / 2;
   const int64_t total = (int64_t)geo.row_blocks * geo.col_tiles;
   if (total < ncl) ncl = (int)total;
-  LATTE_CUDA_OK(cudaFuncSetAttribute(pair_sweep_grad_kernel,
+  LATTE_CUDA_OK(cudaFuncSetAttribute(pair_sweep_kernel<kModeGrad>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, kSweepSmem));
   // every CTA of the launch writes its ds partial; unused slots are zeroed by the caller
-  pair_sweep_grad_kernel<<<2 * ncl, kThreads, kSweepSmem, stream>>>(tmy, tmg, p);
+  pair_sweep_kernel<kModeGrad><<<2 * ncl, kThreads, kSweepSmem, stream>>>(tmy, tmg, p);
   LATTE_LAUNCH_OK();
   return LATTE_OK;
 }

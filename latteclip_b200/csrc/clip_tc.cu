@@ -53,6 +53,7 @@ struct FwdParams {
   int tiles_total;  // ceil(n_all / 128)
   int splits;       // column splits (gridDim.y)
   uint32_t idesc;
+  const int* gate;  // nullable: run only when *gate != 0 (exact fallback of the pair forward)
 };
 
 struct BwdParams {
@@ -83,6 +84,7 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 __global__ void __launch_bounds__(kThreads, 1)
 clip_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmy,
                    const FwdParams p) {
+  if (p.gate != nullptr && *p.gate == 0) return;
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t smem_base = smem_u32(smem);
   const int warp = threadIdx.x >> 5;
@@ -618,6 +620,7 @@ int clip_fwd_rows_tc(const ClipFwdArgs& a, cudaStream_t stream) {
   p.tiles_total = (int)((a.n_all + kBN - 1) / kBN);
   p.splits = a.nparts / 2;
   p.idesc = make_idesc_f16(kBM, kBN, a.dtype == LATTE_BF16 ? 1u : 0u, 0, 0);
+  p.gate = a.gate;
   const int smem = smem_bytes_for(p.kch, p.stages);
   LATTE_CUDA_OK(cudaFuncSetAttribute(clip_fwd_tc_kernel,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, smem));

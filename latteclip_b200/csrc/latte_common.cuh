@@ -51,6 +51,7 @@ struct ClipFwdArgs {
   float* part_sum;            // [nparts, n_loc]
   float* diag;                // [n_loc]  raw dot of the label pair (unscaled)
   int nparts;                 // partial slots per row (tc: 2 * column splits, simt: 1)
+  const int* gate;            // tc only, nullable: the kernel returns at once when *gate == 0
 };
 
 struct ClipBwdArgs {
@@ -112,6 +113,35 @@ struct PairGemmArgs {
   float* dy32;                      // [n_all, ld32] zeroed (with x16)
   int64_t ld32;
 };
+// Forward on the same sweep: rows dealt to clusters as contiguous tile ranges; a row block
+// split over several clusters gets one partial slot per cluster.
+struct PairFwdGeom {
+  int row_blocks, col_tiles;
+  int64_t total;          // row_blocks * col_tiles
+  int ncl;                // clusters launched
+  int slots;              // upper bound of partial slots per row (x2 tile halves)
+  int64_t ld_colpart;     // row pitch of the column-partial matrix
+};
+struct PairFwdArgs {
+  const void* x; int64_t ldx;
+  const void* y; int64_t ldy;
+  int dtype;
+  int64_t n_loc, n_all, dim;
+  int64_t label_offset;
+  const float* logit_scale;
+  float* part_max;            // [2 * slots, n_loc]
+  float* part_sum;
+  float* diag;                // [n_loc]
+  float* col_part;            // [2 * row_blocks, ld_colpart] or NULL (rows only)
+  float* col_ref;             // [2 * row_blocks, 2 * col_tiles]
+};
+PairFwdGeom clip_pair_fwd_geom(int64_t n_loc, int64_t n_all);
+int clip_pair_fwd_sweep(const PairFwdArgs& a, cudaStream_t stream);
+// cluster that owns tile t when `total` tiles are dealt to `ncl` clusters as [c*total/ncl, ...)
+__host__ __device__ inline int64_t cluster_of_tile(int64_t t, int64_t total, int64_t ncl) {
+  return ((t + 1) * ncl - 1) / total;
+}
+
 bool clip_pair_supported(int dtype, int64_t dim, int64_t ldx, int64_t ldy, const void* x, const void* y);
 PairGeom clip_pair_geom(int64_t n_loc, int64_t n_all);
 int clip_pair_ds_count();
