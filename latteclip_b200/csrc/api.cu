@@ -67,7 +67,7 @@ pair_row_finalize_kernel(const float* pmax, const float* psum, int64_t n_loc, in
   const int64_t rb = i / 256;
   const int64_t c0 = cluster_of_tile(rb * col_tiles, total, ncl);
   const int64_t c1 = cluster_of_tile(rb * col_tiles + col_tiles - 1, total, ncl);
-  const int nparts = 2 * (int)(c1 - c0 + 1);
+  const int nparts = 4 * (int)(c1 - c0 + 1);      // slots x 2 epilogue groups x 2 tile halves
   lse_out[i] = merge_parts(pmax, psum, nparts, n_loc, i) * kLn2;
 }
 
@@ -77,25 +77,47 @@ pair_row_finalize_kernel(const float* pmax, const float* psum, int64_t n_loc, in
 __global__ void __launch_bounds__(256)
 pair_col_finalize_kernel(const float* col_part, const float* col_ref, int64_t ld, int nblk,
                          int col_tiles, int64_t n_all, float* col_lse, int* flag) {
-  const int64_t j = (int64_t)blockIdx.x * 256 + threadIdx.x;
-  if (j >= n_all) return;
-  const int64_t ht = j / 64;
+  // 64 columns x 4 interleaved groups of row blocks per CTA; loads are batched 8 deep so the
+  // merge is not a chain of dependent L2 round trips.
+  __shared__ float sm_m[4][64], sm_l[4][64];
+  const int cx = threadIdx.x & 63, grp = threadIdx.x >> 6;
+  const int64_t j = (int64_t)blockIdx.x * 64 + cx;
+  const int64_t jc = j < n_all ? j : n_all - 1;
+  const int64_t ht = jc / 32;
   float M = -INFINITY, L = 0.f;
-  for (int b = 0; b < nblk; ++b) {
-    const float mb = col_ref[(int64_t)b * 2 * col_tiles + ht];
-    if (!(mb > -INFINITY)) continue;
-    const float c = col_part[(int64_t)b * ld + j];
-    if (mb > M) {
-      L = L * exp2f(M - mb) + c;
-      M = mb;
-    } else {
-      L = fmaf(c, exp2f(mb - M), L);
+  for (int b0 = grp; b0 < nblk; b0 += 32) {
+    float mb[8], c[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int b = b0 + 4 * u;
+      mb[u] = b < nblk ? col_ref[(int64_t)b * 4 * col_tiles + ht] : -INFINITY;
+      c[u] = b < nblk ? col_part[(int64_t)b * ld + jc] : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      if (!(mb[u] > -INFINITY)) continue;
+      if (mb[u] > M) {
+        L = L * exp2f(M - mb[u]) + c[u];
+        M = mb[u];
+      } else {
+        L = fmaf(c[u], exp2f(mb[u] - M), L);
+      }
     }
   }
-  const float lse2 = M + log2f(L);
-  col_lse[j] = lse2 * kLn2;
-  const bool ok = (M - lse2) + log2f((float)nblk) < 95.0f;    // false for NaN / -inf too
-  if (!ok) atomicOr(flag, 1);
+  sm_m[grp][cx] = M;
+  sm_l[grp][cx] = L;
+  __syncthreads();
+  if (grp == 0 && j < n_all) {
+    float Mt = fmaxf(fmaxf(sm_m[0][cx], sm_m[1][cx]), fmaxf(sm_m[2][cx], sm_m[3][cx]));
+    float Lt = 0.f;
+#pragma unroll
+    for (int g = 0; g < 4; ++g)
+      if (sm_m[g][cx] > -INFINITY) Lt = fmaf(sm_l[g][cx], exp2f(sm_m[g][cx] - Mt), Lt);
+    const float lse2 = Mt + log2f(Lt);
+    col_lse[j] = lse2 * kLn2;
+    const bool ok = (Mt - lse2) + log2f((float)nblk) < 95.0f;    // false for NaN / -inf too
+    if (!ok) atomicOr(flag, 1);
+  }
 }
 
 // Fallback only: overwrite col_lse with the exact row-kernel result when requested.
@@ -210,8 +232,11 @@ ds_reduce_kernel(const float* partial, int count, const float* grad_loss, float 
 }
 
 // bf16 -> fp16 copy of a feature matrix (second GEMM of the tc backward, see clip_tc.cu)
-__global__ void bf16_to_fp16_kernel(const __nv_bfloat16* in, int64_t ld_in, __half* out,
+__global__ void bf16_to_fp16_kernel(const __nv_bfloat16* in0, __half* out0,
+                                    const __nv_bfloat16* in1, __half* out1, int64_t ld_in,
                                     int64_t ld_out, int64_t rows, int64_t dim) {
+  const __nv_bfloat16* in = blockIdx.y ? in1 : in0;
+  __half* out = blockIdx.y ? out1 : out0;
   const int64_t per_row = (dim + 7) / 8;
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= rows * per_row) return;
@@ -297,13 +322,13 @@ WsLayout ws_layout(int64_t n_loc, int64_t n_all, int64_t dim, int dtype, bool bw
   w.off_colpart = w.off_colref = w.off_flag = o;
   if (w.pair_fwd) {
     const PairFwdGeom f = clip_pair_fwd_geom(n_loc, n_all);
-    const size_t pp = up((size_t)2 * f.slots * (size_t)n_loc);
+    const size_t pp = up((size_t)4 * f.slots * (size_t)n_loc);
     w.off_pp_max_r = o; o += pp;
     w.off_pp_sum_r = o; o += pp;
     w.off_pp_max_c = o; o += pp;
     w.off_pp_sum_c = o; o += pp;
     w.off_colpart = o; o += up((size_t)2 * f.row_blocks * (size_t)f.ld_colpart);
-    w.off_colref = o; o += up((size_t)2 * f.row_blocks * 2 * (size_t)f.col_tiles);
+    w.off_colref = o; o += up((size_t)2 * f.row_blocks * 4 * (size_t)f.col_tiles);
     w.off_flag = o; o += 64;
   }
   w.total = o * sizeof(float);
@@ -408,6 +433,9 @@ extern "C" int latte_clip_fwd(const void* img_loc, int64_t ld_img_loc, const voi
     pa.part_max = ws + w.off_pp_max_r; pa.part_sum = ws + w.off_pp_sum_r; pa.diag = ws + w.off_diag_r;
     pa.col_part = single ? ws + w.off_colpart : nullptr;
     pa.col_ref = ws + w.off_colref;
+    // 0xFF bytes = NaN = "slot not written" (an epilogue group may own no tile of a row block)
+    const size_t pp_bytes = (size_t)4 * f.slots * (size_t)n_loc * sizeof(float);
+    LATTE_CUDA_OK(cudaMemsetAsync(pa.part_max, 0xFF, pp_bytes, st));
     int rc = clip_pair_fwd_sweep(pa, st);
     if (rc) return rc;
     pair_row_finalize_kernel<<<rblocks, 256, 0, st>>>(pa.part_max, pa.part_sum, n_loc, f.col_tiles,
@@ -417,7 +445,7 @@ extern "C" int latte_clip_fwd(const void* img_loc, int64_t ld_img_loc, const voi
     if (single) {
       int* flag = reinterpret_cast<int*>(ws + w.off_flag);
       LATTE_CUDA_OK(cudaMemsetAsync(flag, 0, sizeof(int), st));
-      pair_col_finalize_kernel<<<(unsigned)((n_all + 255) / 256), 256, 0, st>>>(
+      pair_col_finalize_kernel<<<(unsigned)((n_all + 63) / 64), 256, 0, st>>>(
           ws + w.off_colpart, ws + w.off_colref, f.ld_colpart, 2 * f.row_blocks, f.col_tiles, n_all,
           col_lse, flag);
       LATTE_LAUNCH_OK();
@@ -434,6 +462,7 @@ extern "C" int latte_clip_fwd(const void* img_loc, int64_t ld_img_loc, const voi
       pa.x = txt_loc; pa.ldx = ld_txt_loc; pa.y = img_all; pa.ldy = ld_img_all;
       pa.part_max = ws + w.off_pp_max_c; pa.part_sum = ws + w.off_pp_sum_c; pa.diag = ws + w.off_diag_c;
       pa.col_part = nullptr;
+      LATTE_CUDA_OK(cudaMemsetAsync(pa.part_max, 0xFF, pp_bytes, st));
       rc = clip_pair_fwd_sweep(pa, st);
       if (rc) return rc;
       pair_row_finalize_kernel<<<rblocks, 256, 0, st>>>(pa.part_max, pa.part_sum, n_loc, f.col_tiles,
@@ -519,14 +548,21 @@ extern "C" int latte_clip_bwd(const void* img_loc, int64_t ld_img_loc, const voi
     __half* yb = reinterpret_cast<__half*>(ws + w.off_y16b);
     const int64_t work = n_all * ((dim + 7) / 8);
     const unsigned blocks = (unsigned)((work + 255) / 256);
-    bf16_to_fp16_kernel<<<blocks, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(txt_all),
-                                                ld_txt_all, ya, (int64_t)w.ld16, n_all, dim);
-    LATTE_LAUNCH_OK();
-    if (img_all == txt_all) {
-      yb = ya;
+    const bool same = img_all == txt_all;
+    if (same || ld_img_all == ld_txt_all) {
+      if (same) yb = ya;
+      bf16_to_fp16_kernel<<<dim3(blocks, same ? 1 : 2), 256, 0, st>>>(
+          static_cast<const __nv_bfloat16*>(txt_all), ya, static_cast<const __nv_bfloat16*>(img_all),
+          yb, ld_txt_all, (int64_t)w.ld16, n_all, dim);
+      LATTE_LAUNCH_OK();
     } else {
-      bf16_to_fp16_kernel<<<blocks, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(img_all),
-                                                  ld_img_all, yb, (int64_t)w.ld16, n_all, dim);
+      bf16_to_fp16_kernel<<<dim3(blocks, 1), 256, 0, st>>>(
+          static_cast<const __nv_bfloat16*>(txt_all), ya, nullptr, nullptr, ld_txt_all,
+          (int64_t)w.ld16, n_all, dim);
+      LATTE_LAUNCH_OK();
+      bf16_to_fp16_kernel<<<dim3(blocks, 1), 256, 0, st>>>(
+          static_cast<const __nv_bfloat16*>(img_all), yb, nullptr, nullptr, ld_img_all,
+          (int64_t)w.ld16, n_all, dim);
       LATTE_LAUNCH_OK();
     }
     txt16 = ya; ld_txt16 = (int64_t)w.ld16;
@@ -578,11 +614,8 @@ extern "C" int latte_clip_bwd(const void* img_loc, int64_t ld_img_loc, const voi
       rc = clip_pair_gemm(ga, st);
       if (rc) return rc;
     }
-    rc = clip_pair_scale_cast(acc_i, (int64_t)w.ld32, d_img, grad_dtype, ld_grad, n_loc, dim,
-                              grad_loss, grad_mult, logit_scale, n_loc, st);
-    if (rc) return rc;
-    rc = clip_pair_scale_cast(acc_t, (int64_t)w.ld32, d_txt, grad_dtype, ld_grad, n_loc, dim,
-                              grad_loss, grad_mult, logit_scale, n_loc, st);
+    rc = clip_pair_scale_cast(acc_i, acc_t, (int64_t)w.ld32, d_img, d_txt, grad_dtype, ld_grad, n_loc,
+                              dim, grad_loss, grad_mult, logit_scale, n_loc, st);
     if (rc) return rc;
     ds_reduce_kernel<<<1, 256, 0, st>>>(dsp, 2 * dsn, grad_loss, grad_mult, n_loc, d_scale);
     LATTE_LAUNCH_OK();

@@ -24,18 +24,22 @@ using namespace ptx;
 
 namespace {
 
-constexpr int kThreads = 384;
+constexpr int kThreads = 384;           // stream-K GEMM: 4 service warps + 8 epilogue warps
 constexpr int kEpiWarp0 = 4;
-constexpr int kNumEpiWarps = 8;
+constexpr int kGemmEpiWarps = 8;
+constexpr int kSweepThreads = 640;      // sweep: 4 service warps + 2 groups of 8 epilogue warps
+constexpr int kNumEpiWarps = 16;
 constexpr int kPM = 128;              // rows per CTA (256 per pair)
 constexpr int kTN = 128;              // S tile columns (pair MMA N)
 constexpr int kBK = 64;               // feature columns per smem chunk (128 bytes)
 constexpr int kYChunkBytes = 64 * kBK * 2;      // this CTA's half of a Y chunk: 64 rows
-constexpr int kSweepStages = 16;
+constexpr int kChunksPerStage = 4;               // one barrier round trip per 4 chunks (K = 256)
+constexpr int kSweepStages = 4;
+constexpr int kRingStageBytes = kChunksPerStage * kYChunkBytes;   // 32 KB
 constexpr int kStageBytes = 32 * 128;           // one epilogue warp's G staging: 32 rows x 128 B
 constexpr int kMiscBytes = 1024;
 constexpr int kVecBytes = 64 * 4;               // one epilogue warp's column factors of a tile
-constexpr int kSweepSmem = kSweepStages * kYChunkBytes + kNumEpiWarps * (kStageBytes + kVecBytes) +
+constexpr int kSweepSmem = kSweepStages * kRingStageBytes + kNumEpiWarps * (kStageBytes + kVecBytes) +
                            kMiscBytes;
 
 constexpr int kGBlockElems = 128 * 64;          // one G block: 128 rows x 64 cols fp16
@@ -68,11 +72,11 @@ struct SweepParams {
   float* ds_partial;                 // [gridDim.x]
   // forward modes: per-(slot, half) online-softmax partials of the rows, raw label dots,
   // and (kModeFwdBoth) per-128-row-block column partial sums with their reference exponents
-  float* part_max;                   // [2 * slots, n_loc]
+  float* part_max;                   // [4 * slots, n_loc]  (slot, epilogue group, tile half)
   float* part_sum;
   float* diag;                       // [n_loc]
   float* col_part;                   // [2 * row_blocks, ld_colpart]
-  float* col_ref;                    // [2 * row_blocks, 2 * col_tiles]
+  float* col_ref;                    // [2 * row_blocks, 4 * col_tiles]  (one per 32 columns)
   int64_t ld_colpart;
   int kch;                           // ceil(dim / 64)
   int col_tiles;                     // tiles of 128 columns (even: columns padded to 256)
@@ -86,7 +90,7 @@ constexpr int kModeFwdRows = 1;   // forward: row log-sum-exp partials
 constexpr int kModeFwdBoth = 2;   // forward, world size 1: row partials + column partials of the same tile
 
 template <int MODE>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kSweepThreads, 1)
 pair_sweep_kernel(const __grid_constant__ CUtensorMap tmy, const __grid_constant__ CUtensorMap tmg,
                   const SweepParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -96,7 +100,7 @@ pair_sweep_kernel(const __grid_constant__ CUtensorMap tmy, const __grid_constant
   const uint32_t rank = cluster_ctarank();
 
   const uint32_t ring = smem_base;
-  const uint32_t stage_base = ring + kSweepStages * kYChunkBytes;
+  const uint32_t stage_base = ring + kSweepStages * kRingStageBytes;
   const uint32_t vec_base = stage_base + kNumEpiWarps * kStageBytes;
   const uint32_t misc = vec_base + kNumEpiWarps * kVecBytes;
   const uint32_t bar_full = misc;                         // [kSweepStages]
@@ -118,6 +122,10 @@ pair_sweep_kernel(const __grid_constant__ CUtensorMap tmy, const __grid_constant
   const int64_t cl = blockIdx.x >> 1;
   const int64_t u0 = cl * total / ncl;
   const int64_t u1 = (cl + 1) * total / ncl;
+  // (row block, column tile) of the first tile; the loops below step them without dividing
+  const int ntile = (int)(u1 - u0);
+  const int rb0 = (int)(u0 / p.col_tiles);
+  const int ct0 = (int)(u0 % p.col_tiles);
 
   if (warp == 0 && elect_one()) {
     prefetch_tensormap(&tmy);
@@ -130,9 +138,9 @@ pair_sweep_kernel(const __grid_constant__ CUtensorMap tmy, const __grid_constant
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(bar_tfull + 8 * b, 1);
-      mbar_init(bar_tempty + 8 * b, 2 * kNumEpiWarps);
+      mbar_init(bar_tempty + 8 * b, 16);      // one group (8 warps) of each CTA drains a buffer
     }
-    mbar_init(bar_aready, 2 * kNumEpiWarps);
+    mbar_init(bar_aready, 16);                // group 0 (8 warps) of each CTA loads X
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -153,13 +161,16 @@ pair_sweep_kernel(const __grid_constant__ CUtensorMap tmy, const __grid_constant
       const uint64_t keep = policy_evict_last();      // features are re-read by every pair
       int stage = 0;
       uint32_t phase = 0;
-      for (int64_t t = u0; t < u1; ++t) {
-        const int ct = (int)(t % p.col_tiles);
-        for (int c = 0; c < p.kch; ++c) {
+      int ct = ct0;
+      for (int it = 0; it < ntile; ++it, ct = (ct + 1 == p.col_tiles) ? 0 : ct + 1) {
+        for (int c0 = 0; c0 < p.kch; c0 += kChunksPerStage) {
+          const int nc = min(kChunksPerStage, p.kch - c0);
           mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-          if (rank == 0) mbar_arrive_expect_tx(bar_full + 8 * stage, 2 * kYChunkBytes);
-          tma_load_2d_pair_hint(ring + stage * kYChunkBytes, &tmy, lead_full + 8 * stage, c * kBK,
-                                ct * kTN + (int)rank * 64, keep);
+          if (rank == 0) mbar_arrive_expect_tx(bar_full + 8 * stage, 2 * nc * kYChunkBytes);
+          for (int c = 0; c < nc; ++c)
+            tma_load_2d_pair_hint(ring + stage * kRingStageBytes + c * kYChunkBytes, &tmy,
+                                  lead_full + 8 * stage, (c0 + c) * kBK, ct * kTN + (int)rank * 64,
+                                  keep);
           if (++stage == kSweepStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -169,27 +180,29 @@ pair_sweep_kernel(const __grid_constant__ CUtensorMap tmy, const __grid_constant
     if (rank == 0 && elect_one()) {
       int stage = 0;
       uint32_t phase = 0, a_phase = 0;
-      int64_t cur_rb = -1;
-      int it = 0;
-      for (int64_t t = u0; t < u1; ++t, ++it) {
-        const int64_t rb = t / p.col_tiles;
-        if (rb != cur_rb) {
+      int ct = ct0;
+      for (int it = 0; it < ntile; ++it) {
+        if (it == 0 || ct == 0) {          // first tile of a row block: wait for its X block
           mbar_wait(bar_aready, a_phase);
           a_phase ^= 1;
-          cur_rb = rb;
         }
+        ct = (ct + 1 == p.col_tiles) ? 0 : ct + 1;
         const int buf = it & 1;
         mbar_wait(bar_tempty + 8 * buf, ((it >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_s + buf * kTN;
-        for (int c = 0; c < p.kch; ++c) {
+        for (int c0 = 0; c0 < p.kch; c0 += kChunksPerStage) {
+          const int nc = min(kChunksPerStage, p.kch - c0);
           mbar_wait(bar_full + 8 * stage, phase);
           tc_fence_after();
-          const uint32_t b_addr = ring + stage * kYChunkBytes;
+          // descriptor of the stage base; the start-address field counts 16-byte units
+          const uint64_t db0 = make_smem_desc_sw128(ring + stage * kRingStageBytes, 16, 1024);
+          for (int c = 0; c < nc; ++c) {
 #pragma unroll
-          for (int k = 0; k < kBK / 16; ++k) {
-            const uint64_t db = make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
-            mma2_ts(tmem_d, tmem_a + c * 32 + k * 8, db, p.idesc, (c | k) != 0);
+            for (int k = 0; k < kBK / 16; ++k) {
+              const uint64_t db = db0 + (uint64_t)((c * kYChunkBytes + k * 32) >> 4);
+              mma2_ts(tmem_d, tmem_a + (c0 + c) * 32 + k * 8, db, p.idesc, (c0 | c | k) != 0);
+            }
           }
           tc_commit_pair(bar_empty + 8 * stage, 3);
           if (++stage == kSweepStages) { stage = 0; phase ^= 1; }
@@ -199,347 +212,332 @@ pair_sweep_kernel(const __grid_constant__ CUtensorMap tmy, const __grid_constant
     }
   } else if (warp >= kEpiWarp0) {
     // ------------------------------------------------------------ epilogue (both CTAs)
-    if constexpr (MODE == kModeGrad) {
+    // Two groups of eight warps take alternate tiles (group g owns TMEM buffer g), so each
+    // group has two tile times for its tile; inside a group, warp%4 selects the 32-lane TMEM
+    // quarter and the next bit the 64-column half of the tile.
+    const int e = warp - kEpiWarp0;
+    const int group = e >> 3;
+    const int half = (e >> 2) & 1;
     const int q = warp & 3;
-    const int half = (warp - kEpiWarp0) >> 2;
     const int row = q * 32 + lane;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
-    const float s = __ldg(p.logit_scale);
-    const float c2 = s * kLog2e;
-    const float cd_scaled = p.cd * 8192.0f;
-    const float ds_cd_scaled = p.ds_cd * 8192.0f;
-    const uint32_t lead_tempty = mapa_rank(bar_tempty, 0);
+    const float c2 = __ldg(p.logit_scale) * kLog2e;
+    const uint32_t lead_tempty = mapa_rank(bar_tempty, 0) + 8 * group;
     const uint32_t lead_aready = mapa_rank(bar_aready, 0);
-    const uint32_t my_stage = stage_base + (warp - kEpiWarp0) * kStageBytes;
-    const uint64_t stream_pol = policy_evict_first();   // G is written once, read once
-    float ds_acc = 0.f;
-    int64_t cur_rb = -1;
-    int64_t grow = 0, label = 0;
-    bool row_ok = false;
-    float a2 = 0.f, cb = 0.f, ds_cb = 0.f;
-    float off_h = 0.f, cbA = 0.f;
-    int64_t warp_label0 = 0;
-    const float c2h = 0.5f * c2;
-    const bool fast = __ldg(p.fast_flag) != 0;
-    const bool ds_both = p.ds_cb != 0.f;
-    // column factors B_j of the current half tile, staged per warp in shared memory one tile
-    // ahead (a broadcast LDG inside the loop would expose the global-load latency)
-    float* my_vec = reinterpret_cast<float*>(smem + (vec_base - smem_base) +
-                                             (warp - kEpiWarp0) * kVecBytes);
-    if (u0 < u1) {
-      const int64_t c0 = (u0 % p.col_tiles) * kTN + half * 64;
-      my_vec[lane] = __ldg(p.einv_b + c0 + lane);
-      my_vec[32 + lane] = __ldg(p.einv_b + c0 + 32 + lane);
-      __syncwarp();
-    }
-    int it = 0;
-    for (int64_t t = u0; t < u1; ++t, ++it) {
-      const int64_t rb = t / p.col_tiles;
-      const int ct = (int)(t % p.col_tiles);
-      if (rb != cur_rb) {
-        // ---- new row block: this CTA's 128 rows of X -> TMEM (A operand of the TS MMA)
-        cur_rb = rb;
-        grow = rb * 256 + (int64_t)rank * kPM + row;
-        row_ok = grow < p.n_loc;
-        label = p.label_offset + grow;
-        // rows past the end: huge LSE and no cross term -> G = 0
-        a2 = row_ok ? __ldg(p.lse_a2 + label) - kGScaleLog2 : 1.0e30f;
-        cb = row_ok ? p.cb : 0.f;
-        ds_cb = row_ok ? p.ds_cb : 0.f;
-        warp_label0 = p.label_offset + rb * 256 + (int64_t)rank * kPM + q * 32;
-        off_h = row_ok ? 0.5f * (kGScaleLog2 - __ldg(p.lse_a2 + label)) : -1.0e30f;
-        cbA = (row_ok && fast) ? p.cb * __ldg(p.e_a + label) : 0.f;
-        const uint16_t* xrow =
-            reinterpret_cast<const uint16_t*>(p.x) + (row_ok ? grow : 0) * p.ldx;
-        const int groups = p.kch * 2;              // groups of 32 features = 16 packed columns
-        for (int g = half; g < groups; g += 2) {
-          uint32_t w[16];
-#pragma unroll
-          for (int v4 = 0; v4 < 4; ++v4) {
-            const int e0 = g * 32 + v4 * 8;
-            uint4 val = make_uint4(0u, 0u, 0u, 0u);
-            if (row_ok && e0 < p.dim) val = __ldg(reinterpret_cast<const uint4*>(xrow + e0));
-            w[v4 * 4 + 0] = val.x; w[v4 * 4 + 1] = val.y;
-            w[v4 * 4 + 2] = val.z; w[v4 * 4 + 3] = val.w;
-          }
-          tmem_st_32x16(tmem_a + lane_base + g * 16, w);
-        }
-        tmem_st_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(lead_aready);
-      }
+    const uint32_t my_tfull = bar_tfull + 8 * group;
+    const uint32_t tmem_tile = tmem_s + lane_base + group * kTN + half * 64;
 
-      float bn0 = 0.f, bn1 = 0.f;
-      if (t + 1 < u1) {
-        const int64_t cn = ((t + 1) % p.col_tiles) * kTN + half * 64;
-        bn0 = __ldg(p.einv_b + cn + lane);
-        bn1 = __ldg(p.einv_b + cn + 32 + lane);
+    // tile `group` of the range, then every second tile
+    int rb_i = rb0, ct = ct0;
+    auto step_tile = [&]() {
+      if (++ct == p.col_tiles) { ct = 0; ++rb_i; }
+    };
+    if (group == 1) step_tile();
+    int cur_rb = -1;
+    int64_t grow = 0, label = 0, warp_label0 = 0;
+    bool row_ok = false;
+
+    // New row block: refresh the row constants; group 0 also writes this CTA's 128 rows of X
+    // into TMEM (the A operand of the TS MMA) once every MMA of the previous block is done.
+    auto enter_row_block = [&](int it) {
+      cur_rb = rb_i;
+      grow = (int64_t)rb_i * 256 + (int64_t)rank * kPM + row;
+      row_ok = grow < p.n_loc;
+      label = p.label_offset + grow;
+      warp_label0 = p.label_offset + (int64_t)rb_i * 256 + (int64_t)rank * kPM + q * 32;
+      if (group != 0) return;
+      const int first = it - ct;                 // first tile of this row block (ct is 0 or 1 here)
+      if (first > 0) {
+        const int last = first - 1;              // last tile of the previous row block
+        mbar_wait(bar_tfull + 8 * (last & 1), (last >> 1) & 1);
+        tc_fence_after();
       }
-      const int buf = it & 1;
-      mbar_wait(bar_tfull + 8 * buf, (it >> 1) & 1);
-      tc_fence_after();
-      const uint32_t taddr = tmem_s + lane_base + buf * kTN + half * 64;
-      uint32_t r[2][32];
-      tmem_ld_32x32(taddr, r[0]);
-      tmem_ld_32x32(taddr + 32, r[1]);
-      tmem_ld_wait();
+      const uint16_t* xrow = reinterpret_cast<const uint16_t*>(p.x) + (row_ok ? grow : 0) * p.ldx;
+      const int groups = p.kch * 2;              // groups of 32 features = 16 packed columns
+      for (int g = half; g < groups; g += 2) {
+        uint32_t w[16];
+#pragma unroll
+        for (int v4 = 0; v4 < 4; ++v4) {
+          const int e0 = g * 32 + v4 * 8;
+          uint4 val = make_uint4(0u, 0u, 0u, 0u);
+          if (row_ok && e0 < p.dim) val = __ldg(reinterpret_cast<const uint4*>(xrow + e0));
+          w[v4 * 4 + 0] = val.x; w[v4 * 4 + 1] = val.y;
+          w[v4 * 4 + 2] = val.z; w[v4 * 4 + 3] = val.w;
+        }
+        tmem_st_32x16(tmem_a + lane_base + g * 16, w);
+      }
+      tmem_st_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(lead_tempty + 8 * buf);
+      if (lane == 0) mbar_arrive_cluster(lead_aready);
+    };
 
-      const int64_t col0 = (int64_t)ct * kTN + half * 64;
-      const bool ragged = col0 + 64 > p.n_all;
-      // labels of this warp's 32 rows are consecutive: does this half tile hold any of them?
-      const bool diag_tile = warp_label0 < col0 + 64 && warp_label0 + 32 > col0;
-      uint32_t packed[32];
-      if (fast && !ragged && !diag_tile) {
-        // One ex2 per logit: ea = h*h with h = 2^((x - a_i + 13)/2); the y-side softmax term
-        // is ea * 2^(a_i - b_j) = ea * A_i * B_j (rank one; the vectors come from the prep
-        // kernel, which also verified that the LSE range keeps every factor in fp32 range).
-        const float4* pB = reinterpret_cast<const float4*>(my_vec);
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-#pragma unroll
-          for (int i4 = 0; i4 < 8; ++i4) {
-            const float4 b4 = pB[h * 8 + i4];
-            const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
-            float g[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float v = __uint_as_float(r[h][i4 * 4 + e]);
-              const float hh = fast_exp2(fmaf(v, c2h, off_h));
-              const float ea = hh * hh;
-              g[e] = ea * fmaf(cbA, bb[e], 1.0f);
-              ds_acc = fmaf(ds_both ? g[e] : ea, v, ds_acc);
-            }
-            packed[h * 16 + i4 * 2 + 0] = pack2(g[0], g[1]);
-            packed[h * 16 + i4 * 2 + 1] = pack2(g[2], g[3]);
-          }
+    if constexpr (MODE == kModeGrad) {
+      // ======================================================== gradient weights
+      const float s = __ldg(p.logit_scale);
+      (void)s;
+      const float cd_scaled = p.cd * 8192.0f;
+      const float ds_cd_scaled = p.ds_cd * 8192.0f;
+      const float c2h = 0.5f * c2;
+      const bool fast = __ldg(p.fast_flag) != 0;
+      const bool ds_both = p.ds_cb != 0.f;
+      const uint32_t my_stage = stage_base + e * kStageBytes;
+      const uint64_t stream_pol = policy_evict_first();   // G is written once, read once
+      // column factors B_j of this warp's half tile, staged in shared memory one tile ahead
+      float* my_vec = reinterpret_cast<float*>(smem + (vec_base - smem_base) + e * kVecBytes);
+      if (group < ntile) {
+        const int64_t c0 = (int64_t)ct * kTN + half * 64;
+        my_vec[lane] = __ldg(p.einv_b + c0 + lane);
+        my_vec[32 + lane] = __ldg(p.einv_b + c0 + 32 + lane);
+        __syncwarp();
+      }
+      float ds_acc = 0.f;
+      float a2 = 0.f, cb = 0.f, ds_cb = 0.f, off_h = 0.f, cbA = 0.f;
+      for (int it = group, k = 0; it < ntile; it += 2, ++k) {
+        if (rb_i != cur_rb) {
+          enter_row_block(it);
+          // rows past the end: huge LSE and no cross term -> G = 0
+          a2 = row_ok ? __ldg(p.lse_a2 + label) - kGScaleLog2 : 1.0e30f;
+          cb = row_ok ? p.cb : 0.f;
+          ds_cb = row_ok ? p.ds_cb : 0.f;
+          off_h = row_ok ? 0.5f * (kGScaleLog2 - __ldg(p.lse_a2 + label)) : -1.0e30f;
+          cbA = (row_ok && fast) ? p.cb * __ldg(p.e_a + label) : 0.f;
         }
-      } else {
-        int want = -1;
-        if (row_ok && label >= col0 && label < col0 + 64) want = (int)(label - col0);
-        const float4* pb = reinterpret_cast<const float4*>(p.lse_b2 + col0);
+        const int ct_cur = ct;
+        const int rb_cur = rb_i;
+        step_tile();
+        step_tile();                              // (rb_i, ct) now name this group's next tile
+        float bn0 = 0.f, bn1 = 0.f;
+        if (it + 2 < ntile) {
+          const int64_t cn = (int64_t)ct * kTN + half * 64;
+          bn0 = __ldg(p.einv_b + cn + lane);
+          bn1 = __ldg(p.einv_b + cn + 32 + lane);
+        }
+        const int64_t col0 = (int64_t)ct_cur * kTN + half * 64;
+        const bool ragged = col0 + 64 > p.n_all;
+        const bool diag_tile = warp_label0 < col0 + 64 && warp_label0 + 32 > col0;
+        const bool plain = fast && !ragged && !diag_tile;
+        const uint32_t row_addr = my_stage + lane * 128;
+
+        mbar_wait(my_tfull, k & 1);
+        tc_fence_after();
+        if (lane == 0) bulk_wait_group_read<0>();   // previous store has left the staging buffer
+        __syncwarp();
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
+          uint32_t r[32];
+          tmem_ld_32x32(tmem_tile + h * 32, r);
+          tmem_ld_wait();
+          if (h == 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(lead_tempty);
+          }
+          uint32_t packed[16];
+          if (plain) {
+            // One ex2 per logit: ea = hh*hh with hh = 2^((x - a_i + 13)/2); the y-side softmax
+            // term is ea * 2^(a_i - b_j) = ea * A_i * B_j (rank one; the prep kernel checked
+            // that the LSE range keeps every factor inside fp32 range).
+            const float4* pB = reinterpret_cast<const float4*>(my_vec) + h * 8;
 #pragma unroll
-          for (int i4 = 0; i4 < 8; ++i4) {
-            const float4 b4 = __ldg(pb + h * 8 + i4);
-            const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
-            float g[4];
+            for (int i4 = 0; i4 < 8; ++i4) {
+              const float4 b4 = pB[i4];
+              const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+              float g[4];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int i = i4 * 4 + e;
-              const float v = __uint_as_float(r[h][i]);
-              float ea = fast_exp2(fmaf(v, c2, -a2));
-              float eb = fast_exp2(fmaf(v, c2, kGScaleLog2 - bb[e]));
-              if (ragged && col0 + h * 32 + i >= p.n_all) { ea = 0.f; eb = 0.f; }
-              float dw = fmaf(ds_cb, eb, ea);
-              g[e] = fmaf(cb, eb, ea);
-              if (h * 32 + i == want) {
-                g[e] -= cd_scaled;
-                dw -= ds_cd_scaled;
+              for (int x = 0; x < 4; ++x) {
+                const float v = __uint_as_float(r[i4 * 4 + x]);
+                const float hh = fast_exp2(fmaf(v, c2h, off_h));
+                const float ea = hh * hh;
+                g[x] = ea * fmaf(cbA, bb[x], 1.0f);
+                ds_acc = fmaf(ds_both ? g[x] : ea, v, ds_acc);
               }
-              ds_acc = fmaf(dw, v, ds_acc);
+              packed[i4 * 2 + 0] = pack2(g[0], g[1]);
+              packed[i4 * 2 + 1] = pack2(g[2], g[3]);
             }
-            packed[h * 16 + i4 * 2 + 0] = pack2(g[0], g[1]);
-            packed[h * 16 + i4 * 2 + 1] = pack2(g[2], g[3]);
+          } else {
+            int want = -1;
+            if (row_ok && label >= col0 + h * 32 && label < col0 + h * 32 + 32)
+              want = (int)(label - col0) - h * 32;
+            const float4* pb = reinterpret_cast<const float4*>(p.lse_b2 + col0) + h * 8;
+#pragma unroll
+            for (int i4 = 0; i4 < 8; ++i4) {
+              const float4 b4 = __ldg(pb + i4);
+              const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+              float g[4];
+#pragma unroll
+              for (int x = 0; x < 4; ++x) {
+                const int i = i4 * 4 + x;
+                const float v = __uint_as_float(r[i]);
+                float ea = fast_exp2(fmaf(v, c2, -a2));
+                float eb = fast_exp2(fmaf(v, c2, kGScaleLog2 - bb[x]));
+                if (ragged && col0 + h * 32 + i >= p.n_all) { ea = 0.f; eb = 0.f; }
+                float dw = fmaf(ds_cb, eb, ea);
+                g[x] = fmaf(cb, eb, ea);
+                if (i == want) {
+                  g[x] -= cd_scaled;
+                  dw -= ds_cd_scaled;
+                }
+                ds_acc = fmaf(dw, v, ds_acc);
+              }
+              packed[i4 * 2 + 0] = pack2(g[0], g[1]);
+              packed[i4 * 2 + 1] = pack2(g[2], g[3]);
+            }
           }
+          // 32 columns = four 16-byte chunks of this row of the 128B-swizzled staging piece
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            st_shared_v4(row_addr + ((uint32_t)((h * 4 + j) ^ (lane & 7)) << 4), packed[4 * j],
+                         packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+        }
+        my_vec[lane] = bn0;            // column factors of this group's next tile
+        my_vec[32 + lane] = bn1;
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          const int64_t block = ((int64_t)rb_cur * 2 + rank) * (int64_t)p.ncb + (ct_cur * 2 + half);
+          tma_store_2d_hint(&tmg, my_stage, 0, (int32_t)(block * 128 + q * 32), stream_pol);
+          bulk_commit_group();
         }
       }
-      // ---- stage the 32 x 64 fp16 piece (128B-swizzled) and TMA-store it into its G block
-      if (lane == 0) bulk_wait_group_read<0>();
-      __syncwarp();
-      my_vec[lane] = bn0;            // column factors of the next tile
-      my_vec[32 + lane] = bn1;
-      const uint32_t row_addr = my_stage + lane * 128;
-#pragma unroll
-      for (int j = 0; j < 8; ++j)
-        st_shared_v4(row_addr + ((uint32_t)(j ^ (lane & 7)) << 4), packed[4 * j], packed[4 * j + 1],
-                     packed[4 * j + 2], packed[4 * j + 3]);
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) {
-        const int64_t block = (rb * 2 + rank) * (int64_t)p.ncb + (ct * 2 + half);
-        tma_store_2d_hint(&tmg, my_stage, 0, (int32_t)(block * 128 + q * 32), stream_pol);
-        bulk_commit_group();
-      }
-    }
-    if (lane == 0) bulk_wait_group<0>();
+      if (lane == 0) bulk_wait_group<0>();
 
-    // ---- d loss / d s partial of this CTA
-    float v = ds_acc * kGScaleInv;
+      // ---- d loss / d s partial of this CTA
+      float v = ds_acc * kGScaleInv;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if (lane == 0) red_ptr[warp - kEpiWarp0] = v;
-    named_bar_sync(1, kNumEpiWarps * 32);
-    if (warp == kEpiWarp0 && lane == 0) {
-      float tot = 0.f;
-      for (int w = 0; w < kNumEpiWarps; ++w) tot += red_ptr[w];
-      p.ds_partial[blockIdx.x] = tot;
-    }
-  
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) red_ptr[e] = v;
+      named_bar_sync(1, kNumEpiWarps * 32);
+      if (e == 0 && lane == 0) {
+        float tot = 0.f;
+        for (int w = 0; w < kNumEpiWarps; ++w) tot += red_ptr[w];
+        p.ds_partial[blockIdx.x] = tot;
+      }
     } else {
-      // ======================================================== forward epilogue
-      const int q = warp & 3;
-      const int half = (warp - kEpiWarp0) >> 2;
-      const int row = q * 32 + lane;
-      const uint32_t lane_base = (uint32_t)(q * 32) << 16;
-      const float c2 = __ldg(p.logit_scale) * kLog2e;
-      const uint32_t lead_tempty = mapa_rank(bar_tempty, 0);
-      const uint32_t lead_aready = mapa_rank(bar_aready, 0);
-      // column-partial exchange between the four lane-quarter warps of one tile half
-      float* colbuf = reinterpret_cast<float*>(smem + (stage_base - smem_base));   // [2][2][4][64]
-      float* refbuf = colbuf + 2 * 2 * 4 * 64;                                      // [2][2][4]
-      int64_t cur_rb = -1;
-      int64_t grow = 0, label = 0, warp_label0 = 0;
-      bool row_ok = false;
+      // ======================================================== forward
+      // column-partial exchange between the four lane-quarter warps of one half tile
+      float* colbuf = reinterpret_cast<float*>(smem + (stage_base - smem_base));   // [2][2][2][4][64]
+      float* refbuf = colbuf + 2 * 2 * 2 * 4 * 64;                                  // [2][2][2][4][2]
       float m = -INFINITY, l = 0.f;
       auto flush_rows = [&]() {
         if (cur_rb >= 0 && row_ok) {
-          const int64_t slot = cl - cluster_of_tile(cur_rb * p.col_tiles, total, ncl);
-          const int64_t idx = (slot * 2 + half) * p.n_loc + grow;
+          const int64_t slot = cl - cluster_of_tile((int64_t)cur_rb * p.col_tiles, total, ncl);
+          const int64_t idx = ((slot * 2 + group) * 2 + half) * p.n_loc + grow;
           p.part_max[idx] = m;
           p.part_sum[idx] = l;
         }
       };
-      int it = 0;
-      for (int64_t t = u0; t < u1; ++t, ++it) {
-        const int64_t rb = t / p.col_tiles;
-        const int ct = (int)(t % p.col_tiles);
-        if (rb != cur_rb) {
+      for (int it = group, k = 0; it < ntile; it += 2, ++k) {
+        if (rb_i != cur_rb) {
           flush_rows();
-          cur_rb = rb;
-          grow = rb * 256 + (int64_t)rank * kPM + row;
-          row_ok = grow < p.n_loc;
-          label = p.label_offset + grow;
-          warp_label0 = p.label_offset + rb * 256 + (int64_t)rank * kPM + q * 32;
+          enter_row_block(it);
           m = -INFINITY;
           l = 0.f;
-          const uint16_t* xrow =
-              reinterpret_cast<const uint16_t*>(p.x) + (row_ok ? grow : 0) * p.ldx;
-          const int groups = p.kch * 2;
-          for (int g = half; g < groups; g += 2) {
-            uint32_t w[16];
-#pragma unroll
-            for (int v4 = 0; v4 < 4; ++v4) {
-              const int e0 = g * 32 + v4 * 8;
-              uint4 val = make_uint4(0u, 0u, 0u, 0u);
-              if (row_ok && e0 < p.dim) val = __ldg(reinterpret_cast<const uint4*>(xrow + e0));
-              w[v4 * 4 + 0] = val.x; w[v4 * 4 + 1] = val.y;
-              w[v4 * 4 + 2] = val.z; w[v4 * 4 + 3] = val.w;
-            }
-            tmem_st_32x16(tmem_a + lane_base + g * 16, w);
-          }
-          tmem_st_wait();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive_cluster(lead_aready);
         }
+        const int ct_cur = ct;
+        const int rb_cur = rb_i;
+        step_tile();
+        step_tile();
+        const int64_t col0 = (int64_t)ct_cur * kTN + half * 64;
+        const bool diag_tile = warp_label0 < col0 + 64 && warp_label0 + 32 > col0;
+        const int par = k & 1;
+        float* cb_w = colbuf + (((par * 2 + group) * 2 + half) * 4 + q) * 64;
+        float* rf_w = refbuf + (((par * 2 + group) * 2 + half) * 4 + q) * 2;
 
-        const int buf = it & 1;
-        mbar_wait(bar_tfull + 8 * buf, (it >> 1) & 1);
+        mbar_wait(my_tfull, k & 1);
         tc_fence_after();
-        const uint32_t taddr = tmem_s + lane_base + buf * kTN + half * 64;
-        uint32_t r[2][32];
-        tmem_ld_32x32(taddr, r[0]);
-        tmem_ld_32x32(taddr + 32, r[1]);
-        tmem_ld_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(lead_tempty + 8 * buf);
-
-        const int64_t col0 = (int64_t)ct * kTN + half * 64;
-        if (col0 + 64 > p.n_all) {
 #pragma unroll
-          for (int h = 0; h < 2; ++h)
+        for (int h = 0; h < 2; ++h) {
+          uint32_t r[32];
+          tmem_ld_32x32(tmem_tile + h * 32, r);
+          tmem_ld_wait();
+          if (h == 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(lead_tempty);
+          }
+          const int64_t colh = col0 + h * 32;
+          if (colh + 32 > p.n_all) {
 #pragma unroll
             for (int i = 0; i < 32; ++i)
-              if (col0 + h * 32 + i >= p.n_all) r[h][i] = 0xff800000u;  // -inf
-        }
-        if (warp_label0 < col0 + 64 && warp_label0 + 32 > col0) {      // warp-uniform
-          if (row_ok && label >= col0 && label < col0 + 64) {
-            const int want = (int)(label - col0);
+              if (colh + i >= p.n_all) r[i] = 0xff800000u;  // -inf
+          }
+          if (diag_tile && row_ok && label >= colh && label < colh + 32) {
+            const int want = (int)(label - colh);
             float dv = 0.f;
 #pragma unroll
-            for (int h = 0; h < 2; ++h)
-#pragma unroll
-              for (int i = 0; i < 32; ++i)
-                if (h * 32 + i == want) dv = __uint_as_float(r[h][i]);
+            for (int i = 0; i < 32; ++i)
+              if (i == want) dv = __uint_as_float(r[i]);
             p.diag[grow] = dv;
           }
-        }
-        float tmax0 = -INFINITY, tmax1 = -INFINITY;
+          float tmax0 = -INFINITY, tmax1 = -INFINITY;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          tmax0 = fmaxf(tmax0, __uint_as_float(r[0][i]));
-          tmax1 = fmaxf(tmax1, __uint_as_float(r[1][i]));
-        }
-        const float m_new = fmaxf(m, fmaxf(tmax0, tmax1) * c2);
-        if (m_new > -INFINITY) {
-          float acc0 = 0.f, acc1 = 0.f;
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float e0 = fast_exp2(fmaf(__uint_as_float(r[0][i]), c2, -m_new));
-            const float e1 = fast_exp2(fmaf(__uint_as_float(r[1][i]), c2, -m_new));
-            acc0 += e0;
-            acc1 += e1;
-            if constexpr (MODE == kModeFwdBoth) {
-              r[0][i] = __float_as_uint(e0);
-              r[1][i] = __float_as_uint(e1);
-            }
+          for (int i = 0; i < 32; i += 2) {
+            tmax0 = fmaxf(tmax0, __uint_as_float(r[i]));
+            tmax1 = fmaxf(tmax1, __uint_as_float(r[i + 1]));
           }
-          l = l * fast_exp2(m - m_new) + (acc0 + acc1);
-          m = m_new;
-        } else if constexpr (MODE == kModeFwdBoth) {
+          const float m_new = fmaxf(m, fmaxf(tmax0, tmax1) * c2);
+          if (m_new > -INFINITY) {
+            float acc0 = 0.f, acc1 = 0.f;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) { r[0][i] = 0u; r[1][i] = 0u; }
-        }
-
-        if constexpr (MODE == kModeFwdBoth) {
-          // Column sums of the same exponentials: weight row i by 2^(m_i - M_w) (M_w = largest
-          // running max of the warp's rows), add over the 32 lanes with a halving butterfly
-          // (lane c ends with column c), then merge the four lane-quarter warps in smem.
-          float mw = row_ok ? m : -INFINITY;
+            for (int i = 0; i < 32; i += 2) {
+              const float e0 = fast_exp2(fmaf(__uint_as_float(r[i]), c2, -m_new));
+              const float e1 = fast_exp2(fmaf(__uint_as_float(r[i + 1]), c2, -m_new));
+              acc0 += e0;
+              acc1 += e1;
+              if constexpr (MODE == kModeFwdBoth) {
+                r[i] = __float_as_uint(e0);
+                r[i + 1] = __float_as_uint(e1);
+              }
+            }
+            l = l * fast_exp2(m - m_new) + (acc0 + acc1);
+            m = m_new;
+          } else if constexpr (MODE == kModeFwdBoth) {
 #pragma unroll
-          for (int o = 16; o > 0; o >>= 1) mw = fmaxf(mw, __shfl_xor_sync(0xffffffffu, mw, o));
-          const float w = (row_ok && m > -INFINITY) ? fast_exp2(m - mw) : 0.f;
-          float cs[2];
+            for (int i = 0; i < 32; ++i) r[i] = 0u;
+          }
+          if constexpr (MODE == kModeFwdBoth) {
+            // Column sums of the same exponentials: weight row i by 2^(m_i - M_w) (M_w = the
+            // largest running max among the warp's rows), add over the 32 lanes with a halving
+            // butterfly (lane c ends with column c).
+            float mw = row_ok ? m : -INFINITY;
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
+            for (int o = 16; o > 0; o >>= 1) mw = fmaxf(mw, __shfl_xor_sync(0xffffffffu, mw, o));
+            const float w = (row_ok && m > -INFINITY) ? fast_exp2(m - mw) : 0.f;
             float v[32];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[h][i]) * w;
+            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * w;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
               const bool up = (lane & o) != 0;
 #pragma unroll
-              for (int k = 0; k < o; ++k) {
-                const float send = up ? v[k] : v[k + o];
-                const float keep = up ? v[k + o] : v[k];
-                v[k] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+              for (int kk = 0; kk < o; ++kk) {
+                const float send = up ? v[kk] : v[kk + o];
+                const float keep = up ? v[kk + o] : v[kk];
+                v[kk] = keep + __shfl_xor_sync(0xffffffffu, send, o);
               }
             }
-            cs[h] = v[0];
+            cb_w[h * 32 + lane] = v[0];
+            if (lane == 0) rf_w[h] = mw;
           }
-          const int par = it & 1;
-          float* cb_w = colbuf + ((par * 2 + half) * 4 + q) * 64;
-          cb_w[lane] = cs[0];
-          cb_w[32 + lane] = cs[1];
-          if (lane == 0) refbuf[(par * 2 + half) * 4 + q] = mw;
-          named_bar_sync(1 + half, 128);
+        }
+        if constexpr (MODE == kModeFwdBoth) {
+          // merge the four lane-quarter warps: warp q finishes columns [16q, 16q + 16)
+          named_bar_sync(1 + group * 2 + half, 128);
           if (lane < 16) {
-            const float* rf = refbuf + (par * 2 + half) * 4;
-            const float* cbh = colbuf + (par * 2 + half) * 4 * 64;
-            const float M = fmaxf(fmaxf(rf[0], rf[1]), fmaxf(rf[2], rf[3]));
+            const int piece = q >> 1;
+            const float* rf = refbuf + ((par * 2 + group) * 2 + half) * 4 * 2 + piece;
+            const float* cbh = colbuf + ((par * 2 + group) * 2 + half) * 4 * 64;
+            const float M = fmaxf(fmaxf(rf[0], rf[2]), fmaxf(rf[4], rf[6]));
             float c = 0.f;
 #pragma unroll
             for (int qq = 0; qq < 4; ++qq)
-              if (rf[qq] > -INFINITY) c = fmaf(cbh[qq * 64 + q * 16 + lane], fast_exp2(rf[qq] - M), c);
-            const int64_t rblk = rb * 2 + rank;
+              if (rf[qq * 2] > -INFINITY)
+                c = fmaf(cbh[qq * 64 + q * 16 + lane], fast_exp2(rf[qq * 2] - M), c);
+            const int64_t rblk = (int64_t)rb_cur * 2 + rank;
             p.col_part[rblk * p.ld_colpart + col0 + q * 16 + lane] = c;
-            if (q == 0 && lane == 0) p.col_ref[rblk * (2 * p.col_tiles) + ct * 2 + half] = M;
+            if ((q & 1) == 0 && lane == 0)
+              p.col_ref[rblk * (4 * p.col_tiles) + ct_cur * 4 + half * 2 + piece] = M;
           }
         }
       }
@@ -618,7 +616,7 @@ pair_gemm_kernel(const __grid_constant__ CUtensorMap tma0, const __grid_constant
       mbar_init(bar_empty + 8 * s, 1);
     }
     mbar_init(bar_tfull, 1);
-    mbar_init(bar_tempty, 2 * kNumEpiWarps);
+    mbar_init(bar_tempty, 2 * kGemmEpiWarps);
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -759,10 +757,13 @@ pair_gemm_kernel(const __grid_constant__ CUtensorMap tma0, const __grid_constant
 }
 
 // out[i, d] = coef * s * 2^-13 * acc[i, d]   (coef = grad_loss * grad_mult / (2 n_loc))
-__global__ void grad_scale_cast_kernel(const float* acc, int64_t ld_acc, void* out, int out_dtype,
+__global__ void grad_scale_cast_kernel(const float* acc0, const float* acc1, int64_t ld_acc,
+                                       void* out0, void* out1, int out_dtype,
                                        int64_t ld_out, int64_t rows, int64_t dim,
                                        const float* grad_loss, float grad_mult,
                                        const float* logit_scale, int64_t n_loc) {
+  const float* acc = blockIdx.y ? acc1 : acc0;
+  void* out = blockIdx.y ? out1 : out0;
   const int64_t per_row = dim / 4;
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= rows * per_row) return;
@@ -877,11 +878,11 @@ int clip_pair_fwd_sweep(const PairFwdArgs& a, cudaStream_t stream) {
   if (a.col_part) {
     LATTE_CUDA_OK(cudaFuncSetAttribute(pair_sweep_kernel<kModeFwdBoth>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, kSweepSmem));
-    pair_sweep_kernel<kModeFwdBoth><<<2 * f.ncl, kThreads, kSweepSmem, stream>>>(tmy, tmy, p);
+    pair_sweep_kernel<kModeFwdBoth><<<2 * f.ncl, kSweepThreads, kSweepSmem, stream>>>(tmy, tmy, p);
   } else {
     LATTE_CUDA_OK(cudaFuncSetAttribute(pair_sweep_kernel<kModeFwdRows>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, kSweepSmem));
-    pair_sweep_kernel<kModeFwdRows><<<2 * f.ncl, kThreads, kSweepSmem, stream>>>(tmy, tmy, p);
+    pair_sweep_kernel<kModeFwdRows><<<2 * f.ncl, kSweepThreads, kSweepSmem, stream>>>(tmy, tmy, p);
   }
   LATTE_LAUNCH_OK();
   return LATTE_OK;
@@ -921,7 +922,7 @@ int clip_pair_sweep(const PairSweepArgs& a, cudaStream_t stream) {
   LATTE_CUDA_OK(cudaFuncSetAttribute(pair_sweep_kernel<kModeGrad>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, kSweepSmem));
   // every CTA of the launch writes its ds partial; unused slots are zeroed by the caller
-  pair_sweep_kernel<kModeGrad><<<2 * ncl, kThreads, kSweepSmem, stream>>>(tmy, tmg, p);
+  pair_sweep_kernel<kModeGrad><<<2 * ncl, kSweepThreads, kSweepSmem, stream>>>(tmy, tmg, p);
   LATTE_LAUNCH_OK();
   return LATTE_OK;
 }
@@ -974,12 +975,14 @@ int clip_pair_gemm(const PairGemmArgs& a, cudaStream_t stream) {
   return LATTE_OK;
 }
 
-int clip_pair_scale_cast(const float* acc, int64_t ld_acc, void* out, int out_dtype, int64_t ld_out,
-                         int64_t rows, int64_t dim, const float* grad_loss, float grad_mult,
-                         const float* logit_scale, int64_t n_loc, cudaStream_t stream) {
+int clip_pair_scale_cast(const float* acc0, const float* acc1, int64_t ld_acc, void* out0, void* out1,
+                         int out_dtype, int64_t ld_out, int64_t rows, int64_t dim,
+                         const float* grad_loss, float grad_mult, const float* logit_scale,
+                         int64_t n_loc, cudaStream_t stream) {
   const int64_t work = rows * (dim / 4);
-  grad_scale_cast_kernel<<<(unsigned)((work + 255) / 256), 256, 0, stream>>>(
-      acc, ld_acc, out, out_dtype, ld_out, rows, dim, grad_loss, grad_mult, logit_scale, n_loc);
+  grad_scale_cast_kernel<<<dim3((unsigned)((work + 255) / 256), 2), 256, 0, stream>>>(
+      acc0, acc1, ld_acc, out0, out1, out_dtype, ld_out, rows, dim, grad_loss, grad_mult, logit_scale,
+      n_loc);
   LATTE_LAUNCH_OK();
   return LATTE_OK;
 }

@@ -119,7 +119,7 @@ struct PairFwdGeom {
   int row_blocks, col_tiles;
   int64_t total;          // row_blocks * col_tiles
   int ncl;                // clusters launched
-  int slots;              // upper bound of partial slots per row (x2 tile halves)
+  int slots;              // upper bound of partial slots per row (x2 groups x2 tile halves)
   int64_t ld_colpart;     // row pitch of the column-partial matrix
 };
 struct PairFwdArgs {
@@ -129,11 +129,11 @@ struct PairFwdArgs {
   int64_t n_loc, n_all, dim;
   int64_t label_offset;
   const float* logit_scale;
-  float* part_max;            // [2 * slots, n_loc]
+  float* part_max;            // [4 * slots, n_loc], pre-filled with 0xFF bytes (= empty)
   float* part_sum;
   float* diag;                // [n_loc]
   float* col_part;            // [2 * row_blocks, ld_colpart] or NULL (rows only)
-  float* col_ref;             // [2 * row_blocks, 2 * col_tiles]
+  float* col_ref;             // [2 * row_blocks, 4 * col_tiles]
 };
 PairFwdGeom clip_pair_fwd_geom(int64_t n_loc, int64_t n_all);
 int clip_pair_fwd_sweep(const PairFwdArgs& a, cudaStream_t stream);
@@ -147,9 +147,10 @@ PairGeom clip_pair_geom(int64_t n_loc, int64_t n_all);
 int clip_pair_ds_count();
 int clip_pair_sweep(const PairSweepArgs& a, cudaStream_t stream);
 int clip_pair_gemm(const PairGemmArgs& a, cudaStream_t stream);
-int clip_pair_scale_cast(const float* acc, int64_t ld_acc, void* out, int out_dtype, int64_t ld_out,
-                         int64_t rows, int64_t dim, const float* grad_loss, float grad_mult,
-                         const float* logit_scale, int64_t n_loc, cudaStream_t stream);
+int clip_pair_scale_cast(const float* acc0, const float* acc1, int64_t ld_acc, void* out0, void* out1,
+                         int out_dtype, int64_t ld_out, int64_t rows, int64_t dim,
+                         const float* grad_loss, float grad_mult, const float* logit_scale,
+                         int64_t n_loc, cudaStream_t stream);
 
 // fp32 SIMT path (fp32 features; exact fp32 products).
 int clip_fwd_rows_simt(const ClipFwdArgs& a, cudaStream_t stream);
