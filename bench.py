@@ -36,9 +36,10 @@ DIM = 512
 SCALE = 100.0
 METRIC = "clip_loss_fwd_bwd_samples_per_sec"
 UNIT = "samples/s"
-# DRAM traffic of the dominant kernel per launch, from the committed ncu capture
-# (profiles/r1_clip_32k_ncu_summary.md: dram__bytes_read.sum + dram__bytes_write.sum)
-NCU_TRAFFIC_BWD_BYTES = 264.0e6
+# DRAM traffic of the dominant kernel (pair_gemm_kernel) per launch at N = 1, from the
+# committed ncu capture (profiles/r1_pair_32k_ncu_summary.md: dram__bytes_read.sum +
+# dram__bytes_write.sum)
+NCU_TRAFFIC_GEMM_BYTES = 5.98e9
 
 
 def synth_shard(n_global, dim, rank, world, set_id=0):
@@ -279,11 +280,13 @@ def run_ours(args):
     h2d = 2 * n_loc * DIM * 2
     d2h = 4
 
-    # ---- roofline of the dominant kernel (the tcgen05 backward row kernel), timed live ------
+    # ---- roofline of the dominant kernel, timed live ------------------------------------------
+    # The library records CUDA events on the launching stream around every kernel stage of
+    # fwd + bwd (latte_clip_stage_times); the dominant stage is the stream-K gradient GEMM
+    # (pair_gemm_kernel: dI = G.T and dT = G^T.I; at N > 1 two launches, one per direction).
     i, t = dev_sets[0]
     idet, tdet = i.detach(), t.detach()
     sc = torch.tensor(SCALE, device=dev)
-    one = torch.ones(1, device=dev)
     if world > 1:
         all_i = torch.empty(N_GLOBAL, DIM, dtype=torch.bfloat16, device=dev)
         all_t = torch.empty(N_GLOBAL, DIM, dtype=torch.bfloat16, device=dev)
@@ -299,47 +302,44 @@ def run_ours(args):
         row_all, col_all = both[:, 0].contiguous(), both[:, 1].contiguous()
     else:
         row_all, col_all = row, col
-    reps = 5
-    for _ in range(2):
-        _lib.clip_bwd(idet, tdet, all_i, all_t, off, sc, row_all, col_all, one, 1.0, True)
-    torch.cuda.synchronize()
-    e0.record()
-    for _ in range(reps):
-        _lib.clip_bwd(idet, tdet, all_i, all_t, off, sc, row_all, col_all, one, 1.0, True)
-    e1.record()
-    torch.cuda.synchronize()
-    bwd_call_ms = e0.elapsed_time(e1) / reps
-    e0.record()
-    for _ in range(reps):
-        _lib.clip_fwd(idet, tdet, all_i, all_t, off, sc)
-    e1.record()
-    torch.cuda.synchronize()
-    fwd_call_ms = e0.elapsed_time(e1) / reps
-    # one backward call = 2 launches of clip_bwd_tc_kernel (+ ~3 tiny kernels); each launch is
-    # credited with ONE gradient GEMM: 2 * n_loc * N * D FLOP (recomputing S is not credited)
-    alg_flop_per_launch = 2.0 * n_loc * N_GLOBAL * DIM
-    launch_ms = bwd_call_ms / 2.0
-    achieved_tf = alg_flop_per_launch / (launch_ms * 1e-3) / 1e12
+    _lib.clip_stage_times(idet, tdet, all_i, all_t, off, sc, row_all, col_all, reps=2)   # warm-up
+    stages = _lib.clip_stage_times(idet, tdet, all_i, all_t, off, sc, row_all, col_all, reps=8)
+    gemm_launches = 1 if world == 1 else 2
+    gemm_ms = stages["bwd_gemm"]
+    # algorithmic work of the stage: the two gradient GEMMs, 2 * n_loc * N * D FLOP each
+    # (every FLOP of this kernel is credited work: it recomputes nothing)
+    alg_flop_stage = 4.0 * n_loc * N_GLOBAL * DIM
+    achieved_tf = alg_flop_stage / (gemm_ms * 1e-3) / 1e12
     step_tf = 6.0 * n_loc * N_GLOBAL * DIM / (ms_step * 1e-3) / 1e12
     roofline = {
-        "bound": "tensor", "kernel": "clip_bwd_tc_kernel", "achieved": achieved_tf,
-        "peak": peaks["burst"], "unit": "TFLOP/s", "frac": achieved_tf / peaks["burst"],
-        "traffic": NCU_TRAFFIC_BWD_BYTES if world == 1 else None,
-        "peak_source": peaks["source"] + ", burst bf16 figure (kernel timed alone)",
-        "launch_ms": launch_ms, "alg_flop_per_launch": alg_flop_per_launch,
-        "executed_flop_per_launch": 6.0 * n_loc * N_GLOBAL * DIM,
+        "bound": "tensor", "kernel": "pair_gemm_kernel", "achieved": achieved_tf,
+        "peak": peaks["sustained"], "unit": "TFLOP/s", "frac": achieved_tf / peaks["sustained"],
+        "frac_of_burst": achieved_tf / peaks["burst"],
+        "traffic": NCU_TRAFFIC_GEMM_BYTES if world == 1 else None,
+        "peak_source": peaks["source"] + ", sustained bf16 figure (the kernel is timed inside "
+                       "back-to-back fwd+bwd steps, under the power cap); burst figure "
+                       f"{peaks['burst']:g} in frac_of_burst",
+        "launch_ms": gemm_ms / gemm_launches, "launches_per_step": gemm_launches,
+        "alg_flop_per_launch": alg_flop_stage / gemm_launches,
+        # G read once per product (fp16), the fp16 features, the fp32 accumulators
+        "alg_bytes_per_launch": (n_loc * N_GLOBAL * 2.0 + N_GLOBAL * DIM * 2.0 + n_loc * DIM * 4.0)
+                                * (2 if world == 1 else 1),
+        "stage_ms": stages,
         "step_alg_tflops_per_gpu": step_tf,
+        "step_frac_of_burst": step_tf / peaks["burst"],
         "step_frac_of_sustained": step_tf / peaks["sustained"],
-        "fwd_call_ms": fwd_call_ms, "bwd_call_ms": bwd_call_ms,
+        "executed_flop_per_step": (8.0 if world == 1 else 10.0) * n_loc * N_GLOBAL * DIM,
     }
 
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu_base, _ = cpu_reference_sample(2, 1, target_s=12.0)
 
-    # kernels of ours per step: forward 2 row kernels + finalize; backward lse->base2,
-    # 2 bf16->fp16 copies, 2 row kernels, ds reduce
-    launches_per_step = 3 + 6
+    # kernels of ours per step (memset nodes not counted).  N = 1: forward sweep, row finalize,
+    # column finalize, gated fallback sweep + merge, loss partial + reduce (7); backward LSE
+    # range + vectors, fp16 copy, sweep, GEMM, cast, ds reduce (7).  N > 1: forward 2 sweeps,
+    # 2 finalizes, loss partial + reduce (6); backward as above with 2 sweeps and 2 GEMMs (9).
+    launches_per_step = 14 if world == 1 else 15
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,

@@ -122,6 +122,37 @@ int latte_clip_bwd(const void* img_loc, int64_t ld_img_loc,
                    float* d_scale,               /* device scalar out (d loss / d s)      */
                    void* workspace, size_t workspace_bytes, void* stream);
 
+/*
+ * Diagnostic for bench.py: runs latte_clip_fwd then latte_clip_bwd `reps` times on `stream`
+ * with CUDA events recorded on that stream around every kernel stage, synchronises the
+ * stream, and returns the mean milliseconds per stage in stage_ms[LATTE_NUM_STAGES] (host
+ * memory).  Arguments are those of the two calls (row_lse_all / col_lse_all are the inputs of
+ * the backward, row_lse / col_lse / loss the outputs of the forward).
+ */
+typedef enum {
+  LATTE_STAGE_FWD_SWEEP = 0,     /* logit sweep(s) of the forward (tcgen05)                  */
+  LATTE_STAGE_FWD_FINALIZE = 1,  /* partial merges, loss reduction, scratch initialisation   */
+  LATTE_STAGE_BWD_PREP = 2,      /* LSE vectors, fp16 feature copies, accumulator zeroing    */
+  LATTE_STAGE_BWD_SWEEP = 3,     /* logit recompute -> gradient weights G (tcgen05)          */
+  LATTE_STAGE_BWD_GEMM = 4,      /* dI = G.T, dT = G^T.I stream-K GEMM (tcgen05)             */
+  LATTE_STAGE_BWD_FINISH = 5,    /* scale + cast of the gradients, d loss / d logit_scale    */
+  LATTE_NUM_STAGES = 6
+} latte_stage_t;
+int latte_clip_stage_times(const void* img_loc, int64_t ld_img_loc,
+                           const void* txt_loc, int64_t ld_txt_loc,
+                           const void* img_all, int64_t ld_img_all,
+                           const void* txt_all, int64_t ld_txt_all,
+                           int dtype, int64_t n_loc, int64_t n_all, int64_t dim,
+                           int64_t label_offset, const float* logit_scale,
+                           const float* row_lse_all, const float* col_lse_all,
+                           float* row_lse, float* col_lse, float* loss,
+                           const float* grad_loss, float grad_mult, int cross_terms,
+                           void* d_img, void* d_txt, int grad_dtype, int64_t ld_grad,
+                           float* d_scale,
+                           void* fwd_workspace, size_t fwd_workspace_bytes,
+                           void* bwd_workspace, size_t bwd_workspace_bytes,
+                           void* stream, int reps, float* stage_ms);
+
 /* ---- prototype / pseudo-label path: src/training/train.py ---------------------------- */
 
 /* out[c,:] = in[c,:] / max(||in[c,:]||_2, 1e-12)   (F.normalize(dim=1), train.py:388;

@@ -67,6 +67,9 @@ def _declare(lib):
                                    vp, vp, vp, vp, vp, sz, vp]
     lib.latte_clip_bwd.argtypes = [vp, i64, vp, i64, vp, i64, vp, i64, i32, i64, i64, i64, i64,
                                    vp, vp, vp, vp, f32, i32, vp, vp, i32, i64, vp, vp, sz, vp]
+    lib.latte_clip_stage_times.argtypes = [vp, i64, vp, i64, vp, i64, vp, i64, i32, i64, i64, i64, i64,
+                                           vp, vp, vp, vp, vp, vp, vp, f32, i32, vp, vp, i32, i64,
+                                           vp, vp, sz, vp, sz, vp, i32, c.POINTER(f32)]
     lib.latte_normalize_rows.argtypes = [vp, i64, vp, i64, i64, i64, vp]
     lib.latte_nxc_argmax_margin.argtypes = [vp, i64, i32, vp, i64, i64, vp, i64, i64, f32,
                                             vp, vp, vp, vp]
@@ -84,7 +87,7 @@ def _declare(lib):
 
 EXPORTS = [
     "latte_version", "latte_status_string", "latte_device_info", "latte_clip_workspace_bytes",
-    "latte_clip_bwd_workspace_bytes",
+    "latte_clip_bwd_workspace_bytes", "latte_clip_stage_times",
     "latte_clip_fwd", "latte_clip_bwd", "latte_normalize_rows", "latte_nxc_argmax_margin",
     "latte_nxc_topk", "latte_mix_ema_fwd", "latte_mix_ema_bwd", "latte_bank_accumulate",
     "latte_bank_finalize",
@@ -225,6 +228,46 @@ def clip_bwd(img_loc, txt_loc, img_all, txt_all, label_offset: int, logit_scale,
                                   _stream(img_loc)),
                "latte_clip_bwd")
     return d_img, d_txt, d_scale
+
+
+STAGES = ("fwd_sweep", "fwd_finalize", "bwd_prep", "bwd_sweep", "bwd_gemm", "bwd_finish")
+
+
+def clip_stage_times(img_loc, txt_loc, img_all, txt_all, label_offset: int, logit_scale,
+                     row_lse_all, col_lse_all, reps: int = 5, cross_terms: bool = True):
+    """Mean milliseconds of every kernel stage of one fwd + bwd (CUDA events on the launching
+    stream, recorded inside the library): dict stage name -> ms."""
+    lib = load()
+    img_loc, txt_loc = _rows(img_loc, "image_features"), _rows(txt_loc, "text_features")
+    img_all, txt_all = _rows(img_all, "all_image_features"), _rows(txt_all, "all_text_features")
+    dt = _dt(img_loc)
+    n_loc, dim = img_loc.shape
+    n_all = img_all.shape[0]
+    dev = img_loc.device
+    s = _scalar_f32(logit_scale)
+    g = torch.ones(1, dtype=torch.float32, device=dev)
+    row_lse_all = _vec(row_lse_all, torch.float32, "row_lse")
+    col_lse_all = _vec(col_lse_all, torch.float32, "col_lse")
+    row = torch.empty(n_loc, dtype=torch.float32, device=dev)
+    col = torch.empty(n_loc, dtype=torch.float32, device=dev)
+    loss = torch.empty(1, dtype=torch.float32, device=dev)
+    d_img = torch.empty(n_loc, dim, dtype=img_loc.dtype, device=dev)
+    d_txt = torch.empty(n_loc, dim, dtype=img_loc.dtype, device=dev)
+    d_scale = torch.empty(1, dtype=torch.float32, device=dev)
+    wf = _workspace(n_loc, n_all, dim, dt, dev)
+    wb = _workspace(n_loc, n_all, dim, dt, dev, bwd=True)
+    wfp, wfn = _aligned_ptr(wf)
+    wbp, wbn = _aligned_ptr(wb)
+    out = (ctypes.c_float * len(STAGES))()
+    with torch.cuda.device(dev):
+        _check(lib.latte_clip_stage_times(
+            _ptr(img_loc), img_loc.stride(0), _ptr(txt_loc), txt_loc.stride(0), _ptr(img_all),
+            img_all.stride(0), _ptr(txt_all), txt_all.stride(0), dt, n_loc, n_all, dim, label_offset,
+            _ptr(s), _ptr(row_lse_all), _ptr(col_lse_all), _ptr(row), _ptr(col), _ptr(loss), _ptr(g),
+            1.0, int(bool(cross_terms)), _ptr(d_img), _ptr(d_txt), _DTYPES[img_loc.dtype], dim,
+            _ptr(d_scale), wfp, wfn, wbp, wbn, _stream(img_loc), int(reps), out),
+            "latte_clip_stage_times")
+    return {name: float(out[k]) for k, name in enumerate(STAGES)}
 
 
 # ------------------------------------------------------------------------------ prototypes

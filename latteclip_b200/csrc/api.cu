@@ -13,6 +13,32 @@ int device_sm_count() {
 
 namespace {
 
+// Optional per-stage CUDA-event timing (latte_clip_stage_times).  mark(id) closes the interval
+// since the previous mark and charges it to stage `id`.
+struct StageTimer {
+  static constexpr int kMaxMarks = 64;
+  cudaEvent_t ev[kMaxMarks];
+  int id[kMaxMarks];
+  int n = 0;
+  bool failed = false;
+  void mark(cudaStream_t st, int stage) {
+    if (n >= kMaxMarks) { failed = true; return; }
+    if (cudaEventCreate(&ev[n]) != cudaSuccess) { failed = true; return; }
+    if (cudaEventRecord(ev[n], st) != cudaSuccess) failed = true;
+    id[n++] = stage;
+  }
+  void collect(float* ms) {          // after a stream synchronise
+    for (int k = 1; k < n; ++k) {
+      float t = 0.f;
+      if (cudaEventElapsedTime(&t, ev[k - 1], ev[k]) != cudaSuccess) failed = true;
+      if (id[k] >= 0 && id[k] < LATTE_NUM_STAGES) ms[id[k]] += t;
+    }
+    for (int k = 0; k < n; ++k) cudaEventDestroy(ev[k]);
+    n = 0;
+  }
+};
+#define LATTE_MARK(stage) do { if (tm) tm->mark(st, (stage)); } while (0)
+
 constexpr int kMaxParts = 16;
 
 // Merge the per-(split, half) online-softmax partials of one row into a base-2 LSE.
@@ -386,13 +412,13 @@ extern "C" int latte_clip_bwd_workspace_bytes(int64_t n_loc, int64_t n_all, int6
   return LATTE_OK;
 }
 
-extern "C" int latte_clip_fwd(const void* img_loc, int64_t ld_img_loc, const void* txt_loc,
-                              int64_t ld_txt_loc, const void* img_all, int64_t ld_img_all,
-                              const void* txt_all, int64_t ld_txt_all, int dtype, int64_t n_loc,
-                              int64_t n_all, int64_t dim, int64_t label_offset,
-                              const float* logit_scale, float* row_lse, float* col_lse,
-                              float* loss, void* workspace, size_t workspace_bytes,
-                              void* stream) {
+static int clip_fwd_impl(const void* img_loc, int64_t ld_img_loc, const void* txt_loc,
+                         int64_t ld_txt_loc, const void* img_all, int64_t ld_img_all,
+                         const void* txt_all, int64_t ld_txt_all, int dtype, int64_t n_loc,
+                         int64_t n_all, int64_t dim, int64_t label_offset,
+                         const float* logit_scale, float* row_lse, float* col_lse,
+                         float* loss, void* workspace, size_t workspace_bytes,
+                         void* stream, StageTimer* tm) {
   LATTE_CHECK_ARG(img_loc && txt_loc && img_all && txt_all && logit_scale && row_lse && col_lse &&
                   loss && workspace);
   LATTE_CHECK_ARG(n_loc > 0 && n_all >= n_loc && dim > 0);
@@ -435,9 +461,12 @@ extern "C" int latte_clip_fwd(const void* img_loc, int64_t ld_img_loc, const voi
     pa.col_ref = ws + w.off_colref;
     // 0xFF bytes = NaN = "slot not written" (an epilogue group may own no tile of a row block)
     const size_t pp_bytes = (size_t)4 * f.slots * (size_t)n_loc * sizeof(float);
+    LATTE_MARK(-1);
     LATTE_CUDA_OK(cudaMemsetAsync(pa.part_max, 0xFF, pp_bytes, st));
+    LATTE_MARK(LATTE_STAGE_FWD_FINALIZE);
     int rc = clip_pair_fwd_sweep(pa, st);
     if (rc) return rc;
+    LATTE_MARK(LATTE_STAGE_FWD_SWEEP);
     pair_row_finalize_kernel<<<rblocks, 256, 0, st>>>(pa.part_max, pa.part_sum, n_loc, f.col_tiles,
                                                       f.total, f.ncl, row_lse);
     LATTE_LAUNCH_OK();
@@ -463,8 +492,10 @@ extern "C" int latte_clip_fwd(const void* img_loc, int64_t ld_img_loc, const voi
       pa.part_max = ws + w.off_pp_max_c; pa.part_sum = ws + w.off_pp_sum_c; pa.diag = ws + w.off_diag_c;
       pa.col_part = nullptr;
       LATTE_CUDA_OK(cudaMemsetAsync(pa.part_max, 0xFF, pp_bytes, st));
+      LATTE_MARK(LATTE_STAGE_FWD_FINALIZE);
       rc = clip_pair_fwd_sweep(pa, st);
       if (rc) return rc;
+      LATTE_MARK(LATTE_STAGE_FWD_SWEEP);
       pair_row_finalize_kernel<<<rblocks, 256, 0, st>>>(pa.part_max, pa.part_sum, n_loc, f.col_tiles,
                                                         f.total, f.ncl, col_lse);
       LATTE_LAUNCH_OK();
@@ -475,8 +506,10 @@ extern "C" int latte_clip_fwd(const void* img_loc, int64_t ld_img_loc, const voi
     LATTE_LAUNCH_OK();
     loss_reduce_kernel<<<1, 256, 0, st>>>(lossp, (int)rblocks, n_loc, loss);
     LATTE_LAUNCH_OK();
+    LATTE_MARK(LATTE_STAGE_FWD_FINALIZE);
     return LATTE_OK;
   }
+  LATTE_MARK(-1);
 
   // image -> text: rows of logits_per_image (loss.py:109 / :115)
   a.x = img_loc; a.ldx = ld_img_loc; a.y = txt_all; a.ldy = ld_txt_all;
@@ -488,6 +521,7 @@ extern "C" int latte_clip_fwd(const void* img_loc, int64_t ld_img_loc, const voi
   a.part_max = ws + w.off_pmax_c; a.part_sum = ws + w.off_psum_c; a.diag = ws + w.off_diag_c;
   rc = tc ? clip_fwd_rows_tc(a, st) : clip_fwd_rows_simt(a, st);
   if (rc) return rc;
+  LATTE_MARK(LATTE_STAGE_FWD_SWEEP);
   const int fblocks = (int)((n_loc + kFinalRows - 1) / kFinalRows);
   double* lossp = reinterpret_cast<double*>(ws + w.off_lossp);
   clip_finalize_kernel<<<fblocks, kFinalRows, 0, st>>>(
@@ -496,18 +530,31 @@ extern "C" int latte_clip_fwd(const void* img_loc, int64_t ld_img_loc, const voi
   LATTE_LAUNCH_OK();
   loss_reduce_kernel<<<1, 256, 0, st>>>(lossp, fblocks, n_loc, loss);
   LATTE_LAUNCH_OK();
+  LATTE_MARK(LATTE_STAGE_FWD_FINALIZE);
   return LATTE_OK;
 }
 
-extern "C" int latte_clip_bwd(const void* img_loc, int64_t ld_img_loc, const void* txt_loc,
+extern "C" int latte_clip_fwd(const void* img_loc, int64_t ld_img_loc, const void* txt_loc,
                               int64_t ld_txt_loc, const void* img_all, int64_t ld_img_all,
                               const void* txt_all, int64_t ld_txt_all, int dtype, int64_t n_loc,
                               int64_t n_all, int64_t dim, int64_t label_offset,
-                              const float* logit_scale, const float* row_lse_all,
-                              const float* col_lse_all, const float* grad_loss, float grad_mult,
-                              int cross_terms, void* d_img, void* d_txt, int grad_dtype,
-                              int64_t ld_grad, float* d_scale, void* workspace,
-                              size_t workspace_bytes, void* stream) {
+                              const float* logit_scale, float* row_lse, float* col_lse,
+                              float* loss, void* workspace, size_t workspace_bytes,
+                              void* stream) {
+  return clip_fwd_impl(img_loc, ld_img_loc, txt_loc, ld_txt_loc, img_all, ld_img_all, txt_all,
+                       ld_txt_all, dtype, n_loc, n_all, dim, label_offset, logit_scale, row_lse,
+                       col_lse, loss, workspace, workspace_bytes, stream, nullptr);
+}
+
+static int clip_bwd_impl(const void* img_loc, int64_t ld_img_loc, const void* txt_loc,
+                         int64_t ld_txt_loc, const void* img_all, int64_t ld_img_all,
+                         const void* txt_all, int64_t ld_txt_all, int dtype, int64_t n_loc,
+                         int64_t n_all, int64_t dim, int64_t label_offset,
+                         const float* logit_scale, const float* row_lse_all,
+                         const float* col_lse_all, const float* grad_loss, float grad_mult,
+                         int cross_terms, void* d_img, void* d_txt, int grad_dtype,
+                         int64_t ld_grad, float* d_scale, void* workspace,
+                         size_t workspace_bytes, void* stream, StageTimer* tm) {
   LATTE_CHECK_ARG(img_loc && txt_loc && img_all && txt_all && logit_scale && row_lse_all &&
                   col_lse_all && grad_loss && d_img && d_txt && d_scale && workspace);
   LATTE_CHECK_ARG(n_loc > 0 && n_all >= n_loc && dim > 0);
@@ -524,6 +571,7 @@ extern "C" int latte_clip_bwd(const void* img_loc, int64_t ld_img_loc, const voi
 
   float* row2 = ws + w.off_row2;
   float* col2 = ws + w.off_col2;
+  LATTE_MARK(-1);
   float* rho = ws + w.off_rho;
   int* fast_flag = reinterpret_cast<int*>(ws + w.off_rho + 1);
   if (w.pair) {
@@ -595,13 +643,16 @@ extern "C" int latte_clip_bwd(const void* img_loc, int64_t ld_img_loc, const voi
     sa.x = img_loc; sa.ldx = ld_img_loc; sa.y = txt_all; sa.ldy = ld_txt_all;
     sa.lse_a2 = row2; sa.lse_b2 = col2; sa.ds_partial = dsp;
     sa.e_a = ws + w.off_erow; sa.einv_b = ws + w.off_einvcol; sa.fast_flag = fast_flag;
+    LATTE_MARK(LATTE_STAGE_BWD_PREP);
     int rc = clip_pair_sweep(sa, st);
     if (rc) return rc;
+    LATTE_MARK(LATTE_STAGE_BWD_SWEEP);
     ga.y16 = txt16; ga.ldy16 = ld_txt16;
     ga.x16 = single ? img16 : nullptr; ga.ldx16 = ld_img16;
     ga.dx32 = acc_i; ga.dy32 = acc_t;
     rc = clip_pair_gemm(ga, st);
     if (rc) return rc;
+    LATTE_MARK(LATTE_STAGE_BWD_GEMM);
     if (!single) {
       // text side: the transposed block G'[loc cols, :] and d_txt = G' . img_all
       sa.x = txt_loc; sa.ldx = ld_txt_loc; sa.y = img_all; sa.ldy = ld_img_all;
@@ -609,18 +660,22 @@ extern "C" int latte_clip_bwd(const void* img_loc, int64_t ld_img_loc, const voi
       sa.e_a = ws + w.off_ecol; sa.einv_b = ws + w.off_einvrow;
       rc = clip_pair_sweep(sa, st);
       if (rc) return rc;
+      LATTE_MARK(LATTE_STAGE_BWD_SWEEP);
       ga.y16 = img16; ga.ldy16 = ld_img16; ga.x16 = nullptr;
       ga.dx32 = acc_t; ga.dy32 = nullptr;
       rc = clip_pair_gemm(ga, st);
       if (rc) return rc;
+      LATTE_MARK(LATTE_STAGE_BWD_GEMM);
     }
     rc = clip_pair_scale_cast(acc_i, acc_t, (int64_t)w.ld32, d_img, d_txt, grad_dtype, ld_grad, n_loc,
                               dim, grad_loss, grad_mult, logit_scale, n_loc, st);
     if (rc) return rc;
     ds_reduce_kernel<<<1, 256, 0, st>>>(dsp, 2 * dsn, grad_loss, grad_mult, n_loc, d_scale);
     LATTE_LAUNCH_OK();
+    LATTE_MARK(LATTE_STAGE_BWD_FINISH);
     return LATTE_OK;
   }
+  LATTE_MARK(LATTE_STAGE_BWD_PREP);
 
   ClipBwdArgs a;
   a.dtype = dtype; a.n_loc = n_loc; a.n_all = n_all; a.dim = dim;
@@ -642,5 +697,56 @@ extern "C" int latte_clip_bwd(const void* img_loc, int64_t ld_img_loc, const voi
   ds_reduce_kernel<<<1, 256, 0, st>>>(ws + w.off_ds, 2 * ds_count, grad_loss, grad_mult, n_loc,
                                       d_scale);
   LATTE_LAUNCH_OK();
+  LATTE_MARK(LATTE_STAGE_BWD_SWEEP);      // legacy row kernels: sweep and gradient GEMM are fused
+  return LATTE_OK;
+}
+
+extern "C" int latte_clip_bwd(const void* img_loc, int64_t ld_img_loc, const void* txt_loc,
+                              int64_t ld_txt_loc, const void* img_all, int64_t ld_img_all,
+                              const void* txt_all, int64_t ld_txt_all, int dtype, int64_t n_loc,
+                              int64_t n_all, int64_t dim, int64_t label_offset,
+                              const float* logit_scale, const float* row_lse_all,
+                              const float* col_lse_all, const float* grad_loss, float grad_mult,
+                              int cross_terms, void* d_img, void* d_txt, int grad_dtype,
+                              int64_t ld_grad, float* d_scale, void* workspace,
+                              size_t workspace_bytes, void* stream) {
+  return clip_bwd_impl(img_loc, ld_img_loc, txt_loc, ld_txt_loc, img_all, ld_img_all, txt_all,
+                       ld_txt_all, dtype, n_loc, n_all, dim, label_offset, logit_scale, row_lse_all,
+                       col_lse_all, grad_loss, grad_mult, cross_terms, d_img, d_txt, grad_dtype,
+                       ld_grad, d_scale, workspace, workspace_bytes, stream, nullptr);
+}
+
+extern "C" int latte_clip_stage_times(const void* img_loc, int64_t ld_img_loc, const void* txt_loc,
+                                      int64_t ld_txt_loc, const void* img_all, int64_t ld_img_all,
+                                      const void* txt_all, int64_t ld_txt_all, int dtype,
+                                      int64_t n_loc, int64_t n_all, int64_t dim,
+                                      int64_t label_offset, const float* logit_scale,
+                                      const float* row_lse_all, const float* col_lse_all,
+                                      float* row_lse, float* col_lse, float* loss,
+                                      const float* grad_loss, float grad_mult, int cross_terms,
+                                      void* d_img, void* d_txt, int grad_dtype, int64_t ld_grad,
+                                      float* d_scale, void* fwd_workspace, size_t fwd_workspace_bytes,
+                                      void* bwd_workspace, size_t bwd_workspace_bytes, void* stream,
+                                      int reps, float* stage_ms) {
+  LATTE_CHECK_ARG(stage_ms && reps > 0);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  for (int k = 0; k < LATTE_NUM_STAGES; ++k) stage_ms[k] = 0.f;
+  for (int r = 0; r < reps; ++r) {
+    StageTimer tm;
+    int rc = clip_fwd_impl(img_loc, ld_img_loc, txt_loc, ld_txt_loc, img_all, ld_img_all, txt_all,
+                           ld_txt_all, dtype, n_loc, n_all, dim, label_offset, logit_scale, row_lse,
+                           col_lse, loss, fwd_workspace, fwd_workspace_bytes, stream, &tm);
+    if (rc == LATTE_OK)
+      rc = clip_bwd_impl(img_loc, ld_img_loc, txt_loc, ld_txt_loc, img_all, ld_img_all, txt_all,
+                         ld_txt_all, dtype, n_loc, n_all, dim, label_offset, logit_scale,
+                         row_lse_all, col_lse_all, grad_loss, grad_mult, cross_terms, d_img, d_txt,
+                         grad_dtype, ld_grad, d_scale, bwd_workspace, bwd_workspace_bytes, stream,
+                         &tm);
+    const cudaError_t e = cudaStreamSynchronize(st);
+    tm.collect(stage_ms);
+    if (rc) return rc;
+    if (e != cudaSuccess || tm.failed) return LATTE_ERR_CUDA;
+  }
+  for (int k = 0; k < LATTE_NUM_STAGES; ++k) stage_ms[k] /= (float)reps;
   return LATTE_OK;
 }
