@@ -172,6 +172,21 @@ def run_reference(args):
 
 
 def run_ours(args):
+    # NCCL prints its version banner on fd 1; keep stdout for the single JSON line
+    sys.stdout.flush()
+    saved_stdout_fd = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        line = _run_ours(args)
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved_stdout_fd, 1)
+        os.close(saved_stdout_fd)
+    if line is not None:
+        print(json.dumps(line), flush=True)
+
+
+def _run_ours(args):
     import torch.distributed as dist
     import latteclip_b200 as lb
     from latteclip_b200 import _lib
@@ -249,28 +264,47 @@ def run_ours(args):
     last_loss = float(loss.detach())
 
     # ---- end to end: host (pinned) buffers -> public API -> loss back on the host ----------
-    stage_i = torch.empty(n_loc, DIM, dtype=torch.bfloat16, device=dev)
-    stage_t = torch.empty(n_loc, DIM, dtype=torch.bfloat16, device=dev)
+    # Every step copies its own inputs from pinned host memory and reads its loss back; like a
+    # pinned-memory data loader, the copy of step k+1 is issued on a copy stream while step k
+    # computes (two staging slots, events both ways).  All K copies lie inside the timed region.
+    copy_stream = torch.cuda.Stream(device=dev)
+    slots = [(torch.empty(n_loc, DIM, dtype=torch.bfloat16, device=dev),
+              torch.empty(n_loc, DIM, dtype=torch.bfloat16, device=dev)) for _ in range(2)]
+    ready = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
     host_loss = torch.empty((), dtype=torch.float32).pin_memory()
 
-    def step_e2e(k):
+    def prefetch(k):
         hi, ht = host_sets[k % n_sets]
-        stage_i.copy_(hi, non_blocking=True)
-        stage_t.copy_(ht, non_blocking=True)
-        i = stage_i.detach().requires_grad_(True)
-        t = stage_t.detach().requires_grad_(True)
-        log_s.grad = None
-        loss = loss_fn(i, t, log_s.exp())
-        loss.backward()
-        host_loss.copy_(loss.detach(), non_blocking=True)
-        return i.grad
+        slot = k % 2
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[slot])
+            slots[slot][0].copy_(hi, non_blocking=True)
+            slots[slot][1].copy_(ht, non_blocking=True)
+            ready[slot].record(copy_stream)
 
-    for k in range(3):
-        step_e2e(k)
+    def run_e2e(nsteps):
+        cur = torch.cuda.current_stream(dev)
+        for slot in range(2):
+            consumed[slot].record(cur)
+        prefetch(0)
+        for k in range(nsteps):
+            if k + 1 < nsteps:
+                prefetch(k + 1)
+            slot = k % 2
+            cur.wait_event(ready[slot])
+            i = slots[slot][0].detach().requires_grad_(True)
+            t = slots[slot][1].detach().requires_grad_(True)
+            log_s.grad = None
+            loss = loss_fn(i, t, log_s.exp())
+            loss.backward()
+            host_loss.copy_(loss.detach(), non_blocking=True)
+            consumed[slot].record(cur)
+
+    run_e2e(3)
     barrier()
     e0.record()
-    for k in range(args.steps):
-        step_e2e(k)
+    run_e2e(args.steps)
     e1.record()
     barrier()
     t_e = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -283,7 +317,8 @@ def run_ours(args):
     # ---- roofline of the dominant kernel, timed live ------------------------------------------
     # The library records CUDA events on the launching stream around every kernel stage of
     # fwd + bwd (latte_clip_stage_times); the dominant stage is the stream-K gradient GEMM
-    # (pair_gemm_kernel: dI = G.T and dT = G^T.I; at N > 1 two launches, one per direction).
+    # (pair_gemm_kernel: dI = G.T_all and the text-side product G^T.I in ONE launch; at N > 1
+    # the text side is an fp32 [N, D] partial that NCCL reduce-scatters).
     i, t = dev_sets[0]
     idet, tdet = i.detach(), t.detach()
     sc = torch.tensor(SCALE, device=dev)
@@ -302,9 +337,12 @@ def run_ours(args):
         row_all, col_all = both[:, 0].contiguous(), both[:, 1].contiguous()
     else:
         row_all, col_all = row, col
-    _lib.clip_stage_times(idet, tdet, all_i, all_t, off, sc, row_all, col_all, reps=2)   # warm-up
-    stages = _lib.clip_stage_times(idet, tdet, all_i, all_t, off, sc, row_all, col_all, reps=8)
-    gemm_launches = 1 if world == 1 else 2
+    # N > 1 runs the one-sweep-per-rank flow (loss.py:_FusedClipLoss): time that flow
+    partial = world > 1 and _lib.rank_sweep_supported(torch.bfloat16, DIM)
+    _lib.clip_stage_times(idet, tdet, all_i, all_t, off, sc, row_all, col_all, reps=2, partial=partial)
+    stages = _lib.clip_stage_times(idet, tdet, all_i, all_t, off, sc, row_all, col_all, reps=8,
+                                   partial=partial)
+    gemm_launches = 1
     gemm_ms = stages["bwd_gemm"]
     # algorithmic work of the stage: the two gradient GEMMs, 2 * n_loc * N * D FLOP each
     # (every FLOP of this kernel is credited work: it recomputes nothing)
@@ -322,23 +360,22 @@ def run_ours(args):
         "launch_ms": gemm_ms / gemm_launches, "launches_per_step": gemm_launches,
         "alg_flop_per_launch": alg_flop_stage / gemm_launches,
         # G read once per product (fp16), the fp16 features, the fp32 accumulators
-        "alg_bytes_per_launch": (n_loc * N_GLOBAL * 2.0 + N_GLOBAL * DIM * 2.0 + n_loc * DIM * 4.0)
-                                * (2 if world == 1 else 1),
+        "alg_bytes_per_launch": 2.0 * n_loc * N_GLOBAL * 2.0 + (N_GLOBAL + n_loc) * DIM * 2.0
+                                + (N_GLOBAL + n_loc) * DIM * 4.0,
         "stage_ms": stages,
         "step_alg_tflops_per_gpu": step_tf,
         "step_frac_of_burst": step_tf / peaks["burst"],
         "step_frac_of_sustained": step_tf / peaks["sustained"],
-        "executed_flop_per_step": (8.0 if world == 1 else 10.0) * n_loc * N_GLOBAL * DIM,
+        "executed_flop_per_step": 8.0 * n_loc * N_GLOBAL * DIM,
     }
 
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu_base, _ = cpu_reference_sample(2, 1, target_s=12.0)
 
-    # kernels of ours per step (memset nodes not counted).  N = 1: forward sweep, row finalize,
-    # column finalize, gated fallback sweep + merge, loss partial + reduce (7); backward LSE
-    # range + vectors, fp16 copy, sweep, GEMM, cast, ds reduce (7).  N > 1: forward 2 sweeps,
-    # 2 finalizes, loss partial + reduce (6); backward as above with 2 sweeps and 2 GEMMs (9).
+    # kernels of ours per step (memset nodes and NCCL kernels not counted).  Forward: sweep, row
+    # finalize, column finalize (+ column merge at N > 1), gated fallback sweep + merge, loss
+    # partial + reduce; backward: feature prep, LSE range + vectors, sweep, GEMM, cast, ds reduce.
     launches_per_step = 14 if world == 1 else 15
     if rank == 0:
         line = {
@@ -359,9 +396,11 @@ def run_ours(args):
         }
         if cpu_base is not None:
             line["cpu_baseline"] = cpu_base
-        print(json.dumps(line), flush=True)
+    else:
+        line = None
     if world > 1:
         dist.destroy_process_group()
+    return line
 
 
 def main():

@@ -91,8 +91,41 @@ int latte_clip_fwd(const void* img_loc, int64_t ld_img_loc,
                    int64_t label_offset,
                    const float* logit_scale,     /* device scalar s                       */
                    float* row_lse, float* col_lse, /* [n_loc] each                        */
+                   float* row_nll, float* col_nll, /* [n_loc] each, nullable: the per-sample
+                                                    loss terms lse - label logit, formed as
+                                                    (max - label logit) + log(sum) so they keep
+                                                    full relative accuracy near convergence  */
                    float* loss,                  /* device scalar out                     */
                    void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * Multi-rank forward with ONE logit sweep per rank (16-bit features, dim <= 512; ask
+ * latte_clip_rank_sweep_supported).  Step 1 on each rank: rows of this rank against all
+ * gathered text features ->
+ *   row_lse / row_nll / label_logit [n_loc]   (label_logit[i] = s * <img_loc[i], txt_all[off+i]>)
+ *   col_ml [n_all, 2]                         base-2 (max, sum) of every column over THIS rank's rows
+ * The caller all-gathers col_ml (and label_logit) across ranks; step 2 merges them:
+ *   col_lse_all / col_nll_all [n_all], *loss = (mean_i row_nll[i] + mean_i col_nll_all[off+i]) / 2.
+ * If a column's partial sums may have lost flushed terms, step 2 recomputes every column exactly
+ * from the gathered features (device-side decision, no host sync).
+ */
+int latte_clip_rank_sweep_supported(int dtype, int64_t dim);
+int latte_clip_fwd_rows(const void* img_loc, int64_t ld_img_loc,
+                        const void* txt_all, int64_t ld_txt_all,
+                        int dtype, int64_t n_loc, int64_t n_all, int64_t dim,
+                        int64_t label_offset, const float* logit_scale,
+                        float* row_lse, float* row_nll, float* label_logit, float* col_ml,
+                        void* workspace, size_t workspace_bytes, void* stream);
+int latte_clip_fwd_cols_workspace_bytes(int64_t n_all, int64_t dim, int dtype, size_t* bytes);
+int latte_clip_fwd_cols(const float* col_ml_all /* [world, n_all, 2] */, int world,
+                        const float* label_logit_all /* [n_all] */,
+                        const float* row_nll /* [n_loc], this rank */,
+                        const void* img_all, int64_t ld_img_all,
+                        const void* txt_all, int64_t ld_txt_all,
+                        int dtype, int64_t n_loc, int64_t n_all, int64_t dim,
+                        int64_t label_offset, const float* logit_scale,
+                        float* col_lse_all, float* col_nll_all, float* loss,
+                        void* workspace, size_t workspace_bytes, void* stream);
 
 /*
  * Backward of ClipLoss on one rank (the autograd of loss.py:109-116 + 126-129, and the
@@ -107,6 +140,13 @@ int latte_clip_fwd(const void* img_loc, int64_t ld_img_loc,
  * row_lse_all / col_lse_all are the all-gathered LSE vectors [n_all] (== the local ones
  * when world_size is 1).  d_img / d_txt are [n_loc, dim] in `grad_dtype`.
  * `workspace` is sized by latte_clip_bwd_workspace_bytes.
+ * row_nll_all / col_nll_all (nullable, both or neither): the forward's per-sample loss terms
+ * [n_all]; with them the label entry of G is expm1(-nll) instead of exp(S - lse) - 1.
+ * d_txt_partial (nullable, fp32 [n_all, dim], 16-bit features with dim <= 512 and
+ * cross_terms = 1 only): one-sweep multi-rank mode -- d_txt is not written; instead
+ * d_txt_partial = coef * s * G[loc rows, :]^T @ img_loc for ALL columns, which the caller
+ * reduce-scatters (SUM) over the ranks; *d_scale then covers this rank's rows x all columns
+ * (a different partition of the same global sum than the reference's per-rank value).
  */
 int latte_clip_bwd(const void* img_loc, int64_t ld_img_loc,
                    const void* txt_loc, int64_t ld_txt_loc,
@@ -116,9 +156,11 @@ int latte_clip_bwd(const void* img_loc, int64_t ld_img_loc,
                    int64_t label_offset,
                    const float* logit_scale,
                    const float* row_lse_all, const float* col_lse_all,   /* [n_all]  */
+                   const float* row_nll_all, const float* col_nll_all,   /* [n_all], nullable */
                    const float* grad_loss,       /* device scalar dL/dloss                */
                    float grad_mult, int cross_terms,
                    void* d_img, void* d_txt, int grad_dtype, int64_t ld_grad,
+                   float* d_txt_partial,         /* nullable, see above                   */
                    float* d_scale,               /* device scalar out (d loss / d s)      */
                    void* workspace, size_t workspace_bytes, void* stream);
 
@@ -148,7 +190,7 @@ int latte_clip_stage_times(const void* img_loc, int64_t ld_img_loc,
                            float* row_lse, float* col_lse, float* loss,
                            const float* grad_loss, float grad_mult, int cross_terms,
                            void* d_img, void* d_txt, int grad_dtype, int64_t ld_grad,
-                           float* d_scale,
+                           float* d_txt_partial, float* d_scale,
                            void* fwd_workspace, size_t fwd_workspace_bytes,
                            void* bwd_workspace, size_t bwd_workspace_bytes,
                            void* stream, int reps, float* stage_ms);

@@ -64,12 +64,19 @@ def _declare(lib):
     lib.latte_clip_workspace_bytes.argtypes = [i64, i64, i64, i32, c.POINTER(sz)]
     lib.latte_clip_bwd_workspace_bytes.argtypes = [i64, i64, i64, i32, c.POINTER(sz)]
     lib.latte_clip_fwd.argtypes = [vp, i64, vp, i64, vp, i64, vp, i64, i32, i64, i64, i64, i64,
-                                   vp, vp, vp, vp, vp, sz, vp]
+                                   vp, vp, vp, vp, vp, vp, vp, sz, vp]
+    lib.latte_clip_rank_sweep_supported.argtypes = [i32, i64]
+    lib.latte_clip_fwd_rows.argtypes = [vp, i64, vp, i64, i32, i64, i64, i64, i64, vp,
+                                        vp, vp, vp, vp, vp, sz, vp]
+    lib.latte_clip_fwd_cols_workspace_bytes.argtypes = [i64, i64, i32, c.POINTER(sz)]
+    lib.latte_clip_fwd_cols.argtypes = [vp, i32, vp, vp, vp, i64, vp, i64, i32, i64, i64, i64, i64,
+                                        vp, vp, vp, vp, vp, sz, vp]
     lib.latte_clip_bwd.argtypes = [vp, i64, vp, i64, vp, i64, vp, i64, i32, i64, i64, i64, i64,
-                                   vp, vp, vp, vp, f32, i32, vp, vp, i32, i64, vp, vp, sz, vp]
+                                   vp, vp, vp, vp, vp, vp, f32, i32, vp, vp, i32, i64, vp, vp, vp,
+                                   sz, vp]
     lib.latte_clip_stage_times.argtypes = [vp, i64, vp, i64, vp, i64, vp, i64, i32, i64, i64, i64, i64,
                                            vp, vp, vp, vp, vp, vp, vp, f32, i32, vp, vp, i32, i64,
-                                           vp, vp, sz, vp, sz, vp, i32, c.POINTER(f32)]
+                                           vp, vp, vp, sz, vp, sz, vp, i32, c.POINTER(f32)]
     lib.latte_normalize_rows.argtypes = [vp, i64, vp, i64, i64, i64, vp]
     lib.latte_nxc_argmax_margin.argtypes = [vp, i64, i32, vp, i64, i64, vp, i64, i64, f32,
                                             vp, vp, vp, vp]
@@ -87,7 +94,8 @@ def _declare(lib):
 
 EXPORTS = [
     "latte_version", "latte_status_string", "latte_device_info", "latte_clip_workspace_bytes",
-    "latte_clip_bwd_workspace_bytes", "latte_clip_stage_times",
+    "latte_clip_bwd_workspace_bytes", "latte_clip_stage_times", "latte_clip_rank_sweep_supported",
+    "latte_clip_fwd_rows", "latte_clip_fwd_cols_workspace_bytes", "latte_clip_fwd_cols",
     "latte_clip_fwd", "latte_clip_bwd", "latte_normalize_rows", "latte_nxc_argmax_margin",
     "latte_nxc_topk", "latte_mix_ema_fwd", "latte_mix_ema_bwd", "latte_bank_accumulate",
     "latte_bank_finalize",
@@ -169,8 +177,9 @@ def _aligned_ptr(ws: torch.Tensor) -> Tuple[ctypes.c_void_p, int]:
 
 
 # ------------------------------------------------------------------------------ ClipLoss
-def clip_fwd(img_loc, txt_loc, img_all, txt_all, label_offset: int, logit_scale):
-    """-> (row_lse[n_loc], col_lse[n_loc], loss[1]) fp32 device tensors."""
+def clip_fwd(img_loc, txt_loc, img_all, txt_all, label_offset: int, logit_scale, with_nll: bool = False):
+    """-> (row_lse[n_loc], col_lse[n_loc], loss[1]) fp32 device tensors; with_nll appends
+    (row_nll[n_loc], col_nll[n_loc]), the per-sample loss terms lse - label logit."""
     lib = load()
     img_loc, txt_loc = _rows(img_loc, "image_features"), _rows(txt_loc, "text_features")
     img_all, txt_all = _rows(img_all, "all_image_features"), _rows(txt_all, "all_text_features")
@@ -184,22 +193,94 @@ def clip_fwd(img_loc, txt_loc, img_all, txt_all, label_offset: int, logit_scale)
     row_lse = torch.empty(n_loc, dtype=torch.float32, device=dev)
     col_lse = torch.empty(n_loc, dtype=torch.float32, device=dev)
     loss = torch.empty(1, dtype=torch.float32, device=dev)
+    row_nll = torch.empty(n_loc, dtype=torch.float32, device=dev) if with_nll else None
+    col_nll = torch.empty(n_loc, dtype=torch.float32, device=dev) if with_nll else None
     ws = _workspace(n_loc, n_all, dim, dt, dev)
     wp, wn = _aligned_ptr(ws)
     with torch.cuda.device(dev):
         _check(lib.latte_clip_fwd(_ptr(img_loc), img_loc.stride(0), _ptr(txt_loc), txt_loc.stride(0),
                                   _ptr(img_all), img_all.stride(0), _ptr(txt_all), txt_all.stride(0),
                                   dt, n_loc, n_all, dim, label_offset, _ptr(s), _ptr(row_lse),
-                                  _ptr(col_lse), _ptr(loss), wp, wn, _stream(img_loc)),
+                                  _ptr(col_lse), _ptr(row_nll), _ptr(col_nll), _ptr(loss), wp, wn,
+                                  _stream(img_loc)),
                "latte_clip_fwd")
+    if with_nll:
+        return row_lse, col_lse, loss, row_nll, col_nll
     return row_lse, col_lse, loss
+
+
+def rank_sweep_supported(dtype: torch.dtype, dim: int) -> bool:
+    """True when the one-sweep-per-rank multi-rank path (clip_fwd_rows / clip_fwd_cols /
+    clip_bwd(partial=True)) can run these features."""
+    if dtype not in _DTYPES:
+        return False
+    return bool(load().latte_clip_rank_sweep_supported(_DTYPES[dtype], dim))
+
+
+def clip_fwd_rows(img_loc, txt_all, label_offset: int, logit_scale):
+    """Step 1 of the multi-rank forward -> (row_lse[n_loc], row_nll[n_loc], label_logit[n_loc],
+    col_ml[n_all, 2])."""
+    lib = load()
+    img_loc, txt_all = _rows(img_loc, "image_features"), _rows(txt_all, "all_text_features")
+    dt = _dt(img_loc)
+    n_loc, dim = img_loc.shape
+    n_all = txt_all.shape[0]
+    dev = img_loc.device
+    s = _scalar_f32(logit_scale)
+    row_lse = torch.empty(n_loc, dtype=torch.float32, device=dev)
+    row_nll = torch.empty(n_loc, dtype=torch.float32, device=dev)
+    label_logit = torch.empty(n_loc, dtype=torch.float32, device=dev)
+    col_ml = torch.empty(n_all, 2, dtype=torch.float32, device=dev)
+    ws = _workspace(n_loc, n_all, dim, dt, dev)
+    wp, wn = _aligned_ptr(ws)
+    with torch.cuda.device(dev):
+        _check(lib.latte_clip_fwd_rows(_ptr(img_loc), img_loc.stride(0), _ptr(txt_all), txt_all.stride(0),
+                                       dt, n_loc, n_all, dim, label_offset, _ptr(s), _ptr(row_lse),
+                                       _ptr(row_nll), _ptr(label_logit), _ptr(col_ml), wp, wn,
+                                       _stream(img_loc)),
+               "latte_clip_fwd_rows")
+    return row_lse, row_nll, label_logit, col_ml
+
+
+def clip_fwd_cols(col_ml_all, label_logit_all, row_nll, img_all, txt_all, n_loc: int,
+                  label_offset: int, logit_scale):
+    """Step 2 of the multi-rank forward -> (col_lse_all[n_all], col_nll_all[n_all], loss[1])."""
+    lib = load()
+    img_all, txt_all = _rows(img_all, "all_image_features"), _rows(txt_all, "all_text_features")
+    dt = _dt(img_all)
+    n_all, dim = img_all.shape
+    dev = img_all.device
+    world = col_ml_all.shape[0]
+    col_ml_all = _vec(col_ml_all, torch.float32, "col_ml_all")
+    label_logit_all = _vec(label_logit_all, torch.float32, "label_logit_all")
+    row_nll = _vec(row_nll, torch.float32, "row_nll")
+    if col_ml_all.numel() != world * n_all * 2 or label_logit_all.numel() != n_all:
+        raise RuntimeError("clip_fwd_cols: gathered vectors have the wrong size")
+    s = _scalar_f32(logit_scale)
+    col_lse_all = torch.empty(n_all, dtype=torch.float32, device=dev)
+    col_nll_all = torch.empty(n_all, dtype=torch.float32, device=dev)
+    loss = torch.empty(1, dtype=torch.float32, device=dev)
+    nbytes = ctypes.c_size_t(0)
+    _check(lib.latte_clip_fwd_cols_workspace_bytes(n_all, dim, dt, ctypes.byref(nbytes)),
+           "latte_clip_fwd_cols_workspace_bytes")
+    ws = torch.empty(nbytes.value + 256, dtype=torch.uint8, device=dev)
+    wp, wn = _aligned_ptr(ws)
+    with torch.cuda.device(dev):
+        _check(lib.latte_clip_fwd_cols(_ptr(col_ml_all), world, _ptr(label_logit_all), _ptr(row_nll),
+                                       _ptr(img_all), img_all.stride(0), _ptr(txt_all), txt_all.stride(0),
+                                       dt, n_loc, n_all, dim, label_offset, _ptr(s), _ptr(col_lse_all),
+                                       _ptr(col_nll_all), _ptr(loss), wp, wn, _stream(img_all)),
+               "latte_clip_fwd_cols")
+    return col_lse_all, col_nll_all, loss
 
 
 def clip_bwd(img_loc, txt_loc, img_all, txt_all, label_offset: int, logit_scale,
              row_lse_all, col_lse_all, grad_loss, grad_mult: float, cross_terms: bool,
-             grad_dtype=None):
+             grad_dtype=None, row_nll_all=None, col_nll_all=None, partial: bool = False):
     """-> (d_img[n_loc, dim], d_txt[n_loc, dim], d_scale[1] fp32).  The feature gradients
-    come back in ``grad_dtype`` (default: the feature dtype, what autograd needs)."""
+    come back in ``grad_dtype`` (default: the feature dtype, what autograd needs).
+    ``partial=True`` (one-sweep multi-rank mode): the second result is instead the fp32
+    partial [n_all, dim] of the text gradient over ALL columns, to be reduce-scattered."""
     lib = load()
     img_loc, txt_loc = _rows(img_loc, "image_features"), _rows(txt_loc, "text_features")
     img_all, txt_all = _rows(img_all, "all_image_features"), _rows(txt_all, "all_text_features")
@@ -214,8 +295,16 @@ def clip_bwd(img_loc, txt_loc, img_all, txt_all, label_offset: int, logit_scale,
     if row_lse_all.numel() != n_all or col_lse_all.numel() != n_all:
         raise RuntimeError("clip_bwd: LSE vectors must have n_all entries")
     gdt = img_loc.dtype if grad_dtype is None else grad_dtype
+    if (row_nll_all is None) != (col_nll_all is None):
+        raise RuntimeError("clip_bwd: pass both nll vectors or neither")
+    if row_nll_all is not None:
+        row_nll_all = _vec(row_nll_all, torch.float32, "row_nll")
+        col_nll_all = _vec(col_nll_all, torch.float32, "col_nll")
+        if row_nll_all.numel() != n_all or col_nll_all.numel() != n_all:
+            raise RuntimeError("clip_bwd: nll vectors must have n_all entries")
     d_img = torch.empty(n_loc, dim, dtype=gdt, device=dev)
-    d_txt = torch.empty(n_loc, dim, dtype=gdt, device=dev)
+    d_txt = None if partial else torch.empty(n_loc, dim, dtype=gdt, device=dev)
+    d_part = torch.empty(n_all, dim, dtype=torch.float32, device=dev) if partial else None
     d_scale = torch.empty(1, dtype=torch.float32, device=dev)
     ws = _workspace(n_loc, n_all, dim, dt, dev, bwd=True)
     wp, wn = _aligned_ptr(ws)
@@ -223,18 +312,20 @@ def clip_bwd(img_loc, txt_loc, img_all, txt_all, label_offset: int, logit_scale,
         _check(lib.latte_clip_bwd(_ptr(img_loc), img_loc.stride(0), _ptr(txt_loc), txt_loc.stride(0),
                                   _ptr(img_all), img_all.stride(0), _ptr(txt_all), txt_all.stride(0),
                                   dt, n_loc, n_all, dim, label_offset, _ptr(s), _ptr(row_lse_all),
-                                  _ptr(col_lse_all), _ptr(g), float(grad_mult), int(bool(cross_terms)),
-                                  _ptr(d_img), _ptr(d_txt), _DTYPES[gdt], dim, _ptr(d_scale), wp, wn,
-                                  _stream(img_loc)),
+                                  _ptr(col_lse_all), _ptr(row_nll_all), _ptr(col_nll_all), _ptr(g),
+                                  float(grad_mult), int(bool(cross_terms)),
+                                  _ptr(d_img), _ptr(d_txt), _DTYPES[gdt], dim, _ptr(d_part),
+                                  _ptr(d_scale), wp, wn, _stream(img_loc)),
                "latte_clip_bwd")
-    return d_img, d_txt, d_scale
+    return d_img, (d_part if partial else d_txt), d_scale
 
 
 STAGES = ("fwd_sweep", "fwd_finalize", "bwd_prep", "bwd_sweep", "bwd_gemm", "bwd_finish")
 
 
 def clip_stage_times(img_loc, txt_loc, img_all, txt_all, label_offset: int, logit_scale,
-                     row_lse_all, col_lse_all, reps: int = 5, cross_terms: bool = True):
+                     row_lse_all, col_lse_all, reps: int = 5, cross_terms: bool = True,
+                     partial: bool = False):
     """Mean milliseconds of every kernel stage of one fwd + bwd (CUDA events on the launching
     stream, recorded inside the library): dict stage name -> ms."""
     lib = load()
@@ -253,6 +344,7 @@ def clip_stage_times(img_loc, txt_loc, img_all, txt_all, label_offset: int, logi
     loss = torch.empty(1, dtype=torch.float32, device=dev)
     d_img = torch.empty(n_loc, dim, dtype=img_loc.dtype, device=dev)
     d_txt = torch.empty(n_loc, dim, dtype=img_loc.dtype, device=dev)
+    d_part = torch.empty(n_all, dim, dtype=torch.float32, device=dev) if partial else None
     d_scale = torch.empty(1, dtype=torch.float32, device=dev)
     wf = _workspace(n_loc, n_all, dim, dt, dev)
     wb = _workspace(n_loc, n_all, dim, dt, dev, bwd=True)
@@ -265,7 +357,7 @@ def clip_stage_times(img_loc, txt_loc, img_all, txt_all, label_offset: int, logi
             img_all.stride(0), _ptr(txt_all), txt_all.stride(0), dt, n_loc, n_all, dim, label_offset,
             _ptr(s), _ptr(row_lse_all), _ptr(col_lse_all), _ptr(row), _ptr(col), _ptr(loss), _ptr(g),
             1.0, int(bool(cross_terms)), _ptr(d_img), _ptr(d_txt), _DTYPES[img_loc.dtype], dim,
-            _ptr(d_scale), wfp, wfn, wbp, wbn, _stream(img_loc), int(reps), out),
+            _ptr(d_part), _ptr(d_scale), wfp, wfn, wbp, wbn, _stream(img_loc), int(reps), out),
             "latte_clip_stage_times")
     return {name: float(out[k]) for k, name in enumerate(STAGES)}
 

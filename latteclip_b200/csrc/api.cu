@@ -42,16 +42,25 @@ struct StageTimer {
 constexpr int kMaxParts = 16;
 
 // Merge the per-(split, half) online-softmax partials of one row into a base-2 LSE.
-__device__ __forceinline__ float merge_parts(const float* pmax, const float* psum, int nparts,
-                                             int64_t n_loc, int64_t i) {
-  float M = -INFINITY;
+// -> M (largest partial max) and log2 of the sum relative to it; LSE (base 2) = M + logL.
+// Kept apart because the per-sample loss term (M - label logit) + logL is far more accurate
+// than LSE - label logit when the label dominates (M == label logit, logL ~ 1e-4).
+__device__ __forceinline__ void merge_parts2(const float* pmax, const float* psum, int nparts,
+                                             int64_t n_loc, int64_t i, float& M, float& logL) {
+  M = -INFINITY;
   for (int k = 0; k < nparts; ++k) M = fmaxf(M, pmax[(int64_t)k * n_loc + i]);
   float L = 0.f;
   for (int k = 0; k < nparts; ++k) {
     const float m = pmax[(int64_t)k * n_loc + i];
     if (m > -INFINITY) L += psum[(int64_t)k * n_loc + i] * exp2f(m - M);
   }
-  return M + log2f(L);
+  logL = log2f(L);
+}
+__device__ __forceinline__ float merge_parts(const float* pmax, const float* psum, int nparts,
+                                             int64_t n_loc, int64_t i) {
+  float M, logL;
+  merge_parts2(pmax, psum, nparts, n_loc, i, M, logL);
+  return M + logL;
 }
 
 // row_lse / col_lse in natural-log units and per-block partial sums of the loss terms
@@ -61,17 +70,23 @@ __global__ void __launch_bounds__(kFinalRows)
 clip_finalize_kernel(const float* pmax_r, const float* psum_r, const float* diag_r,
                      const float* pmax_c, const float* psum_c, const float* diag_c, int nparts,
                      int64_t n_loc, const float* logit_scale, float* row_lse, float* col_lse,
-                     double* loss_partial) {
+                     float* row_nll, float* col_nll, double* loss_partial) {
   __shared__ double red[kFinalRows / 32];
   const float s = __ldg(logit_scale);
+  const float c2 = s * kLog2e;
   double acc = 0.0;
   const int64_t i = (int64_t)blockIdx.x * kFinalRows + threadIdx.x;
   if (i < n_loc) {
-    const float lr = merge_parts(pmax_r, psum_r, nparts, n_loc, i) * kLn2;
-    const float lc = merge_parts(pmax_c, psum_c, nparts, n_loc, i) * kLn2;
-    row_lse[i] = lr;
-    col_lse[i] = lc;
-    acc = (double)(lr - s * diag_r[i]) + (double)(lc - s * diag_c[i]);
+    float Mr, Lr, Mc, Lc;
+    merge_parts2(pmax_r, psum_r, nparts, n_loc, i, Mr, Lr);
+    merge_parts2(pmax_c, psum_c, nparts, n_loc, i, Mc, Lc);
+    row_lse[i] = (Mr + Lr) * kLn2;
+    col_lse[i] = (Mc + Lc) * kLn2;
+    const float nr = ((Mr - c2 * diag_r[i]) + Lr) * kLn2;
+    const float nc = ((Mc - c2 * diag_c[i]) + Lc) * kLn2;
+    if (row_nll) row_nll[i] = nr;
+    if (col_nll) col_nll[i] = nc;
+    acc = (double)nr + (double)nc;
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
@@ -87,22 +102,32 @@ clip_finalize_kernel(const float* pmax_r, const float* psum_r, const float* diag
 // ---- CTA-pair forward (clip_pair.cu): merge the slot partials of a row
 __global__ void __launch_bounds__(256)
 pair_row_finalize_kernel(const float* pmax, const float* psum, int64_t n_loc, int col_tiles,
-                         int64_t total, int ncl, float* lse_out) {
+                         int64_t total, int ncl, const float* diag, const float* logit_scale,
+                         float* lse_out, float* nll_out, float* label_logit_out) {
   const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
   if (i >= n_loc) return;
   const int64_t rb = i / 256;
   const int64_t c0 = cluster_of_tile(rb * col_tiles, total, ncl);
   const int64_t c1 = cluster_of_tile(rb * col_tiles + col_tiles - 1, total, ncl);
   const int nparts = 4 * (int)(c1 - c0 + 1);      // slots x 2 epilogue groups x 2 tile halves
-  lse_out[i] = merge_parts(pmax, psum, nparts, n_loc, i) * kLn2;
+  float M, logL;
+  merge_parts2(pmax, psum, nparts, n_loc, i, M, logL);
+  lse_out[i] = (M + logL) * kLn2;
+  const float s = __ldg(logit_scale);
+  // fma(-c2, dot, M): the exact residual the sweep's own fma(dot, c2, -M) saw for the label
+  if (nll_out) nll_out[i] = (fmaf(-(s * kLog2e), diag[i], M) + logL) * kLn2;
+  if (label_logit_out) label_logit_out[i] = s * diag[i];
 }
 
-// Column LSE from the per-128-row-block partial sums.  Terms below 2^-126 of a block's
-// reference were flushed; if that could matter for a column (its LSE sits more than ~95
-// binary orders below the largest block reference) the exact fallback is requested.
+// Column (max, sum) from the per-128-row-block partial sums of this rank's rows.  With col_ml
+// the pair is written out (another rank merges); otherwise the LSE, the per-sample loss term
+// and the exactness check are finished here (world size 1).  Terms below 2^-126 of a block's
+// reference were flushed; if that could matter for a column (its LSE sits more than ~95 binary
+// orders below the largest block reference) the exact fallback is requested.
 __global__ void __launch_bounds__(256)
 pair_col_finalize_kernel(const float* col_part, const float* col_ref, int64_t ld, int nblk,
-                         int col_tiles, int64_t n_all, float* col_lse, int* flag) {
+                         int col_tiles, int64_t n_all, const float* diag, const float* logit_scale,
+                         float* col_lse, float* col_nll, float* col_ml, int* flag) {
   // 64 columns x 4 interleaved groups of row blocks per CTA; loads are batched 8 deep so the
   // merge is not a chain of dependent L2 round trips.
   __shared__ float sm_m[4][64], sm_l[4][64];
@@ -139,32 +164,74 @@ pair_col_finalize_kernel(const float* col_part, const float* col_ref, int64_t ld
 #pragma unroll
     for (int g = 0; g < 4; ++g)
       if (sm_m[g][cx] > -INFINITY) Lt = fmaf(sm_l[g][cx], exp2f(sm_m[g][cx] - Mt), Lt);
-    const float lse2 = Mt + log2f(Lt);
+    if (col_ml) {
+      col_ml[2 * j] = Mt;
+      col_ml[2 * j + 1] = Lt;
+      return;
+    }
+    const float logL = log2f(Lt);
+    const float lse2 = Mt + logL;
     col_lse[j] = lse2 * kLn2;
+    if (col_nll) col_nll[j] = (fmaf(-(__ldg(logit_scale) * kLog2e), diag[j], Mt) + logL) * kLn2;
     const bool ok = (Mt - lse2) + log2f((float)nblk) < 95.0f;    // false for NaN / -inf too
     if (!ok) atomicOr(flag, 1);
   }
 }
 
-// Fallback only: overwrite col_lse with the exact row-kernel result when requested.
+// Multi-rank forward: merge the per-rank column (max, sum) pairs [world, n_all, 2] into the
+// column LSE and per-sample loss term of every column; same exactness check as above.
+__global__ void __launch_bounds__(256)
+col_merge_kernel(const float* col_ml_all, int world, int64_t n_all, const float* label_logit_all,
+                 int nblk_total, float* col_lse_all, float* col_nll_all, int* flag) {
+  const int64_t j = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (j >= n_all) return;
+  float M = -INFINITY, L = 0.f;
+  for (int w = 0; w < world; ++w) {
+    const float mw = col_ml_all[((int64_t)w * n_all + j) * 2];
+    const float lw = col_ml_all[((int64_t)w * n_all + j) * 2 + 1];
+    if (!(mw > -INFINITY)) continue;
+    if (mw > M) {
+      L = L * exp2f(M - mw) + lw;
+      M = mw;
+    } else {
+      L = fmaf(lw, exp2f(mw - M), L);
+    }
+  }
+  const float logL = log2f(L);
+  const float lse2 = M + logL;
+  col_lse_all[j] = lse2 * kLn2;
+  col_nll_all[j] = ((M - kLog2e * label_logit_all[j]) + logL) * kLn2;
+  const bool ok = (M - lse2) + log2f((float)nblk_total) < 95.0f;
+  if (!ok) atomicOr(flag, 1);
+}
+
+// Fallback only: overwrite the column LSE (and loss term) with the exact row-kernel result
+// when requested.  label logit = label_scale * label_dot (pass logit_scale = NULL if
+// label_dot already holds the scaled logit).
 __global__ void __launch_bounds__(256)
 gated_merge_kernel(const int* gate, const float* pmax, const float* psum, int nparts,
-                   int64_t n_loc, float* lse_out) {
+                   int64_t n_loc, const float* label_dot, const float* logit_scale, float* lse_out,
+                   float* nll_out) {
   if (*gate == 0) return;
   const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
   if (i >= n_loc) return;
-  lse_out[i] = merge_parts(pmax, psum, nparts, n_loc, i) * kLn2;
+  float M, logL;
+  merge_parts2(pmax, psum, nparts, n_loc, i, M, logL);
+  lse_out[i] = (M + logL) * kLn2;
+  if (nll_out) {
+    const float s = logit_scale ? __ldg(logit_scale) : 1.f;
+    nll_out[i] = ((M - s * kLog2e * label_dot[i]) + logL) * kLn2;
+  }
 }
 
+// partial sums of the per-sample loss terms: sum_i row_nll[i] + col_nll[i]
 __global__ void __launch_bounds__(256)
-lse_loss_partial_kernel(const float* row_lse, const float* col_lse, const float* diag_r,
-                        const float* diag_c, const float* logit_scale, int64_t n_loc,
+nll_loss_partial_kernel(const float* row_nll, const float* col_nll, int64_t n_loc,
                         double* loss_partial) {
   __shared__ double red[8];
-  const float s = __ldg(logit_scale);
   const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
   double acc = 0.0;
-  if (i < n_loc) acc = (double)(row_lse[i] - s * diag_r[i]) + (double)(col_lse[i] - s * diag_c[i]);
+  if (i < n_loc) acc = (double)row_nll[i] + (double)col_nll[i];
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
@@ -192,11 +259,70 @@ loss_reduce_kernel(const double* partial, int count, int64_t n_loc, float* loss)
   }
 }
 
+// One warp per gathered row k: fp16 copies of both feature rows (bf16 input only) and the label
+// logit d_k = s * <img_k, txt_k>, from which u = max_k max(1 - P^row_kk, 1 - P^col_kk) bounds
+// every |G_ij| by 2u (off-diagonal softmax weights of a row / column sum to 1 - P_kk).
+__global__ void __launch_bounds__(256)
+pair_prep_features_kernel(const void* img, int64_t ld_img, const void* txt, int64_t ld_txt,
+                          int is_bf16, __half* img16, __half* txt16, int64_t ld16, int64_t rows,
+                          int64_t dim, const float* logit_scale, const float* row_lse,
+                          const float* col_lse, unsigned int* u_bits) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const float s = __ldg(logit_scale);
+  float umax = 0.f;
+  for (int64_t k = warp0; k < rows; k += nwarps) {
+    float dot = 0.f;
+    for (int64_t c = lane * 8; c < dim; c += 256) {
+      float fi[8], ft[8];
+      if (is_bf16) {
+        const uint4 ri = *reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(img) + k * ld_img + c);
+        const uint4 rt = *reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(txt) + k * ld_txt + c);
+        const __nv_bfloat162* vi = reinterpret_cast<const __nv_bfloat162*>(&ri);
+        const __nv_bfloat162* vt = reinterpret_cast<const __nv_bfloat162*>(&rt);
+        uint4 oi, ot;
+        __half2* hi = reinterpret_cast<__half2*>(&oi);
+        __half2* ht = reinterpret_cast<__half2*>(&ot);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 a = __bfloat1622float2(vi[e]), b = __bfloat1622float2(vt[e]);
+          fi[2 * e] = a.x; fi[2 * e + 1] = a.y; ft[2 * e] = b.x; ft[2 * e + 1] = b.y;
+          hi[e] = __float22half2_rn(a);
+          ht[e] = __float22half2_rn(b);
+        }
+        *reinterpret_cast<uint4*>(img16 + k * ld16 + c) = oi;
+        if (txt16 != img16) *reinterpret_cast<uint4*>(txt16 + k * ld16 + c) = ot;
+      } else {
+        const uint4 ri = *reinterpret_cast<const uint4*>(static_cast<const __half*>(img) + k * ld_img + c);
+        const uint4 rt = *reinterpret_cast<const uint4*>(static_cast<const __half*>(txt) + k * ld_txt + c);
+        const __half2* vi = reinterpret_cast<const __half2*>(&ri);
+        const __half2* vt = reinterpret_cast<const __half2*>(&rt);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 a = __half22float2(vi[e]), b = __half22float2(vt[e]);
+          fi[2 * e] = a.x; fi[2 * e + 1] = a.y; ft[2 * e] = b.x; ft[2 * e + 1] = b.y;
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) dot = fmaf(fi[e], ft[e], dot);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+    const float d = s * dot;
+    const float u = fmaxf(-expm1f(d - row_lse[k]), -expm1f(d - col_lse[k]));
+    umax = fmaxf(umax, u);            // NaN-free inputs assumed; fmaxf drops a NaN operand
+  }
+  if (lane == 0 && umax > 0.f) atomicMax(u_bits, __float_as_uint(umax));
+}
+
 // Range of all LSE values (base 2): rho = mid-point; flag = 1 when max - min <= 64, so that
 // 2^(lse - rho) and products of two such factors stay well inside fp32 range (clip_pair.cu's
 // one-ex2 epilogue); otherwise the sweep uses its two-ex2 epilogue.
 __global__ void __launch_bounds__(1024)
-lse_range_kernel(const float* row_lse, const float* col_lse, int64_t n_all, float* rho, int* flag) {
+lse_range_kernel(const float* row_lse, const float* col_lse, int64_t n_all, float* rho, int* flag,
+                 const unsigned int* u_bits, float* gscale_log2, const float* grad_loss,
+                 float grad_mult, const float* logit_scale, int64_t n_loc, float* out_scale) {
   __shared__ float smin[32], smax[32];
   float lo = INFINITY, hi = -INFINITY;
   for (int64_t i = threadIdx.x; i < n_all; i += 1024) {
@@ -217,6 +343,13 @@ lse_range_kernel(const float* row_lse, const float* col_lse, int64_t n_all, floa
     const bool ok = (hi - lo) <= 64.0f && hi < 3.0e38f && lo > -3.0e38f;   // also rejects NaN / inf
     *rho = ok ? 0.5f * (lo + hi) : 0.f;
     *flag = ok ? 1 : 0;
+    // |G| <= 2u; the LSE / label-logit inputs carry ~5e-5 of fp32 error, so pad u by 1e-3:
+    // 2 (u + 1e-3) 2^gs <= 2^14 keeps fp16 G finite.  gs = 13 for u ~ 1, up to 22 when converged.
+    const float u = fminf(__uint_as_float(*u_bits), 1.0f) + 1.0e-3f;
+    const float gs = fminf(fmaxf(13.0f - ceilf(log2f(u)), 13.0f), 22.0f);
+    *gscale_log2 = gs;
+    // gradient = out_scale * (accumulated G . features)
+    *out_scale = __ldg(grad_loss) * grad_mult / (2.0f * (float)n_loc) * __ldg(logit_scale) * exp2f(-gs);
   }
 }
 
@@ -284,7 +417,7 @@ __global__ void bf16_to_fp16_kernel(const __nv_bfloat16* in0, __half* out0,
 struct WsLayout {
   size_t part;      // floats per partial array (kMaxParts * n_loc)
   size_t off_pmax_r, off_psum_r, off_diag_r, off_pmax_c, off_psum_c, off_diag_c;
-  size_t off_row2, off_col2, off_ds, off_lossp;
+  size_t off_row2, off_col2, off_ds, off_lossp, off_nll_r, off_nll_c;
   size_t off_y16a, off_y16b;    // fp16 copies of txt_all / img_all (bf16 features only)
   size_t ld16;
   size_t n_pad, ds_cap;
@@ -320,6 +453,8 @@ WsLayout ws_layout(int64_t n_loc, int64_t n_all, int64_t dim, int dtype, bool bw
   w.ds_cap = up(2 * (((size_t)n_loc + 63) / 64) + 2 * 160);
   w.off_ds = o; o += w.ds_cap;
   w.off_lossp = o; o += up(2 * (((size_t)n_loc + 255) / 256) + 2);   // doubles
+  w.off_nll_r = o; o += nl;
+  w.off_nll_c = o; o += nl;
   w.ld16 = ((size_t)dim + 7) / 8 * 8;
   w.off_y16a = w.off_y16b = o;
   if (dtype == LATTE_BF16) {
@@ -417,8 +552,8 @@ static int clip_fwd_impl(const void* img_loc, int64_t ld_img_loc, const void* tx
                          const void* txt_all, int64_t ld_txt_all, int dtype, int64_t n_loc,
                          int64_t n_all, int64_t dim, int64_t label_offset,
                          const float* logit_scale, float* row_lse, float* col_lse,
-                         float* loss, void* workspace, size_t workspace_bytes,
-                         void* stream, StageTimer* tm) {
+                         float* row_nll, float* col_nll, float* loss, void* workspace,
+                         size_t workspace_bytes, void* stream, StageTimer* tm) {
   LATTE_CHECK_ARG(img_loc && txt_loc && img_all && txt_all && logit_scale && row_lse && col_lse &&
                   loss && workspace);
   LATTE_CHECK_ARG(n_loc > 0 && n_all >= n_loc && dim > 0);
@@ -430,6 +565,8 @@ static int clip_fwd_impl(const void* img_loc, int64_t ld_img_loc, const void* tx
   if ((reinterpret_cast<uintptr_t>(workspace) & 255) != 0) return LATTE_ERR_BAD_ARG;
   float* ws = static_cast<float*>(workspace);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (!row_nll) row_nll = ws + w.off_nll_r;
+  if (!col_nll) col_nll = ws + w.off_nll_c;
 
   const bool tc = use_tc(dtype, dim, img_loc, ld_img_loc, txt_all, ld_txt_all, txt_loc,
                          ld_txt_loc, img_all, ld_img_all);
@@ -442,6 +579,8 @@ static int clip_fwd_impl(const void* img_loc, int64_t ld_img_loc, const void* tx
   a.dtype = dtype; a.n_loc = n_loc; a.n_all = n_all; a.dim = dim;
   a.label_offset = label_offset; a.logit_scale = logit_scale; a.nparts = nparts;
   a.gate = nullptr;
+  const unsigned rblocks = (unsigned)((n_loc + 255) / 256);
+  double* lossp = reinterpret_cast<double*>(ws + w.off_lossp);
 
   // ---- CTA-pair path (clip_pair.cu): TS-mode sweep; for one rank the column sums come from
   // the same logit tiles as the row sums, so S is computed once.
@@ -450,8 +589,6 @@ static int clip_fwd_impl(const void* img_loc, int64_t ld_img_loc, const void* tx
       clip_pair_supported(dtype, dim, ld_txt_loc, ld_img_all, txt_loc, img_all)) {
     const PairFwdGeom f = clip_pair_fwd_geom(n_loc, n_all);
     const bool single = n_loc == n_all && img_loc == img_all && txt_loc == txt_all;
-    const unsigned rblocks = (unsigned)((n_loc + 255) / 256);
-    double* lossp = reinterpret_cast<double*>(ws + w.off_lossp);
     PairFwdArgs pa;
     pa.dtype = dtype; pa.n_loc = n_loc; pa.n_all = n_all; pa.dim = dim;
     pa.label_offset = label_offset; pa.logit_scale = logit_scale;
@@ -468,15 +605,15 @@ static int clip_fwd_impl(const void* img_loc, int64_t ld_img_loc, const void* tx
     if (rc) return rc;
     LATTE_MARK(LATTE_STAGE_FWD_SWEEP);
     pair_row_finalize_kernel<<<rblocks, 256, 0, st>>>(pa.part_max, pa.part_sum, n_loc, f.col_tiles,
-                                                      f.total, f.ncl, row_lse);
+                                                      f.total, f.ncl, pa.diag, logit_scale, row_lse,
+                                                      row_nll, nullptr);
     LATTE_LAUNCH_OK();
-    const float* diag_c = ws + w.off_diag_r;
     if (single) {
       int* flag = reinterpret_cast<int*>(ws + w.off_flag);
       LATTE_CUDA_OK(cudaMemsetAsync(flag, 0, sizeof(int), st));
       pair_col_finalize_kernel<<<(unsigned)((n_all + 63) / 64), 256, 0, st>>>(
           ws + w.off_colpart, ws + w.off_colref, f.ld_colpart, 2 * f.row_blocks, f.col_tiles, n_all,
-          col_lse, flag);
+          pa.diag, logit_scale, col_lse, col_nll, nullptr, flag);
       LATTE_LAUNCH_OK();
       // exact fallback for columns whose partial sums may have lost flushed terms: the row
       // kernel on the transposed problem; it and the merge return at once unless flagged
@@ -485,7 +622,8 @@ static int clip_fwd_impl(const void* img_loc, int64_t ld_img_loc, const void* tx
       a.part_max = ws + w.off_pmax_c; a.part_sum = ws + w.off_psum_c; a.diag = ws + w.off_diag_c;
       rc = clip_fwd_rows_tc(a, st);
       if (rc) return rc;
-      gated_merge_kernel<<<rblocks, 256, 0, st>>>(flag, a.part_max, a.part_sum, nparts, n_loc, col_lse);
+      gated_merge_kernel<<<rblocks, 256, 0, st>>>(flag, a.part_max, a.part_sum, nparts, n_loc,
+                                                  pa.diag, logit_scale, col_lse, col_nll);
       LATTE_LAUNCH_OK();
     } else {
       pa.x = txt_loc; pa.ldx = ld_txt_loc; pa.y = img_all; pa.ldy = ld_img_all;
@@ -497,12 +635,11 @@ static int clip_fwd_impl(const void* img_loc, int64_t ld_img_loc, const void* tx
       if (rc) return rc;
       LATTE_MARK(LATTE_STAGE_FWD_SWEEP);
       pair_row_finalize_kernel<<<rblocks, 256, 0, st>>>(pa.part_max, pa.part_sum, n_loc, f.col_tiles,
-                                                        f.total, f.ncl, col_lse);
+                                                        f.total, f.ncl, pa.diag, logit_scale, col_lse,
+                                                        col_nll, nullptr);
       LATTE_LAUNCH_OK();
-      diag_c = ws + w.off_diag_c;
     }
-    lse_loss_partial_kernel<<<rblocks, 256, 0, st>>>(row_lse, col_lse, ws + w.off_diag_r, diag_c,
-                                                     logit_scale, n_loc, lossp);
+    nll_loss_partial_kernel<<<rblocks, 256, 0, st>>>(row_nll, col_nll, n_loc, lossp);
     LATTE_LAUNCH_OK();
     loss_reduce_kernel<<<1, 256, 0, st>>>(lossp, (int)rblocks, n_loc, loss);
     LATTE_LAUNCH_OK();
@@ -523,10 +660,10 @@ static int clip_fwd_impl(const void* img_loc, int64_t ld_img_loc, const void* tx
   if (rc) return rc;
   LATTE_MARK(LATTE_STAGE_FWD_SWEEP);
   const int fblocks = (int)((n_loc + kFinalRows - 1) / kFinalRows);
-  double* lossp = reinterpret_cast<double*>(ws + w.off_lossp);
   clip_finalize_kernel<<<fblocks, kFinalRows, 0, st>>>(
       ws + w.off_pmax_r, ws + w.off_psum_r, ws + w.off_diag_r, ws + w.off_pmax_c,
-      ws + w.off_psum_c, ws + w.off_diag_c, nparts, n_loc, logit_scale, row_lse, col_lse, lossp);
+      ws + w.off_psum_c, ws + w.off_diag_c, nparts, n_loc, logit_scale, row_lse, col_lse, row_nll,
+      col_nll, lossp);
   LATTE_LAUNCH_OK();
   loss_reduce_kernel<<<1, 256, 0, st>>>(lossp, fblocks, n_loc, loss);
   LATTE_LAUNCH_OK();
@@ -539,11 +676,129 @@ extern "C" int latte_clip_fwd(const void* img_loc, int64_t ld_img_loc, const voi
                               const void* txt_all, int64_t ld_txt_all, int dtype, int64_t n_loc,
                               int64_t n_all, int64_t dim, int64_t label_offset,
                               const float* logit_scale, float* row_lse, float* col_lse,
-                              float* loss, void* workspace, size_t workspace_bytes,
-                              void* stream) {
+                              float* row_nll, float* col_nll, float* loss, void* workspace,
+                              size_t workspace_bytes, void* stream) {
   return clip_fwd_impl(img_loc, ld_img_loc, txt_loc, ld_txt_loc, img_all, ld_img_all, txt_all,
                        ld_txt_all, dtype, n_loc, n_all, dim, label_offset, logit_scale, row_lse,
-                       col_lse, loss, workspace, workspace_bytes, stream, nullptr);
+                       col_lse, row_nll, col_nll, loss, workspace, workspace_bytes, stream, nullptr);
+}
+
+// ---- multi-rank forward with ONE logit sweep per rank ---------------------------------------
+extern "C" int latte_clip_rank_sweep_supported(int dtype, int64_t dim) {
+  return pair_shape_ok(dtype, dim) ? 1 : 0;
+}
+
+static int clip_fwd_rows_impl(const void* img_loc, int64_t ld_img_loc, const void* txt_all,
+                                   int64_t ld_txt_all, int dtype, int64_t n_loc, int64_t n_all,
+                                   int64_t dim, int64_t label_offset, const float* logit_scale,
+                                   float* row_lse, float* row_nll, float* label_logit,
+                                   float* col_ml, void* workspace, size_t workspace_bytes,
+                                   void* stream, StageTimer* tm) {
+  LATTE_CHECK_ARG(img_loc && txt_all && logit_scale && row_lse && row_nll && label_logit && col_ml &&
+                  workspace);
+  LATTE_CHECK_ARG(n_loc > 0 && n_all >= n_loc && dim > 0);
+  LATTE_CHECK_ARG(label_offset >= 0 && label_offset + n_loc <= n_all);
+  LATTE_CHECK_ARG(ld_img_loc >= dim && ld_txt_all >= dim);
+  if (!pair_shape_ok(dtype, dim) ||
+      !clip_pair_supported(dtype, dim, ld_img_loc, ld_txt_all, img_loc, txt_all))
+    return LATTE_ERR_UNSUPPORTED;
+  const WsLayout w = ws_layout(n_loc, n_all, dim, dtype);
+  if (workspace_bytes < w.total) return LATTE_ERR_WORKSPACE;
+  if ((reinterpret_cast<uintptr_t>(workspace) & 255) != 0) return LATTE_ERR_BAD_ARG;
+  float* ws = static_cast<float*>(workspace);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const PairFwdGeom f = clip_pair_fwd_geom(n_loc, n_all);
+  PairFwdArgs pa;
+  pa.dtype = dtype; pa.n_loc = n_loc; pa.n_all = n_all; pa.dim = dim;
+  pa.label_offset = label_offset; pa.logit_scale = logit_scale;
+  pa.x = img_loc; pa.ldx = ld_img_loc; pa.y = txt_all; pa.ldy = ld_txt_all;
+  pa.part_max = ws + w.off_pp_max_r; pa.part_sum = ws + w.off_pp_sum_r; pa.diag = ws + w.off_diag_r;
+  pa.col_part = ws + w.off_colpart;
+  pa.col_ref = ws + w.off_colref;
+  const size_t pp_bytes = (size_t)4 * f.slots * (size_t)n_loc * sizeof(float);
+  LATTE_MARK(-1);
+  LATTE_CUDA_OK(cudaMemsetAsync(pa.part_max, 0xFF, pp_bytes, st));
+  LATTE_MARK(LATTE_STAGE_FWD_FINALIZE);
+  int rc = clip_pair_fwd_sweep(pa, st);
+  if (rc) return rc;
+  LATTE_MARK(LATTE_STAGE_FWD_SWEEP);
+  pair_row_finalize_kernel<<<(unsigned)((n_loc + 255) / 256), 256, 0, st>>>(
+      pa.part_max, pa.part_sum, n_loc, f.col_tiles, f.total, f.ncl, pa.diag, logit_scale, row_lse,
+      row_nll, label_logit);
+  LATTE_LAUNCH_OK();
+  pair_col_finalize_kernel<<<(unsigned)((n_all + 63) / 64), 256, 0, st>>>(
+      ws + w.off_colpart, ws + w.off_colref, f.ld_colpart, 2 * f.row_blocks, f.col_tiles, n_all,
+      nullptr, logit_scale, nullptr, nullptr, col_ml, nullptr);
+  LATTE_LAUNCH_OK();
+  LATTE_MARK(LATTE_STAGE_FWD_FINALIZE);
+  return LATTE_OK;
+}
+
+extern "C" int latte_clip_fwd_rows(const void* img_loc, int64_t ld_img_loc, const void* txt_all,
+                                   int64_t ld_txt_all, int dtype, int64_t n_loc, int64_t n_all,
+                                   int64_t dim, int64_t label_offset, const float* logit_scale,
+                                   float* row_lse, float* row_nll, float* label_logit,
+                                   float* col_ml, void* workspace, size_t workspace_bytes,
+                                   void* stream) {
+  return clip_fwd_rows_impl(img_loc, ld_img_loc, txt_all, ld_txt_all, dtype, n_loc, n_all, dim,
+                            label_offset, logit_scale, row_lse, row_nll, label_logit, col_ml,
+                            workspace, workspace_bytes, stream, nullptr);
+}
+
+extern "C" int latte_clip_fwd_cols_workspace_bytes(int64_t n_all, int64_t dim, int dtype,
+                                                   size_t* bytes) {
+  LATTE_CHECK_ARG(bytes && n_all > 0 && dim > 0);
+  LATTE_CHECK_ARG(dtype >= LATTE_F32 && dtype <= LATTE_F16);
+  *bytes = ws_layout(n_all, n_all, dim, dtype).total;
+  return LATTE_OK;
+}
+
+extern "C" int latte_clip_fwd_cols(const float* col_ml_all, int world, const float* label_logit_all,
+                                   const float* row_nll, const void* img_all, int64_t ld_img_all,
+                                   const void* txt_all, int64_t ld_txt_all, int dtype,
+                                   int64_t n_loc, int64_t n_all, int64_t dim, int64_t label_offset,
+                                   const float* logit_scale, float* col_lse_all, float* col_nll_all,
+                                   float* loss, void* workspace, size_t workspace_bytes,
+                                   void* stream) {
+  LATTE_CHECK_ARG(col_ml_all && label_logit_all && row_nll && img_all && txt_all && logit_scale &&
+                  col_lse_all && col_nll_all && loss && workspace);
+  LATTE_CHECK_ARG(world > 0 && n_loc > 0 && n_all >= n_loc && dim > 0);
+  LATTE_CHECK_ARG(label_offset >= 0 && label_offset + n_loc <= n_all);
+  if (!pair_shape_ok(dtype, dim) || !clip_tc_supported(dtype, dim, ld_txt_all, ld_img_all, txt_all, img_all))
+    return LATTE_ERR_UNSUPPORTED;
+  const WsLayout w = ws_layout(n_all, n_all, dim, dtype);
+  if (workspace_bytes < w.total) return LATTE_ERR_WORKSPACE;
+  if ((reinterpret_cast<uintptr_t>(workspace) & 255) != 0) return LATTE_ERR_BAD_ARG;
+  float* ws = static_cast<float*>(workspace);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int* flag = reinterpret_cast<int*>(ws + w.off_flag);
+  LATTE_CUDA_OK(cudaMemsetAsync(flag, 0, sizeof(int), st));
+  const int nblk_total = (int)((n_all + 127) / 128);
+  col_merge_kernel<<<(unsigned)((n_all + 255) / 256), 256, 0, st>>>(
+      col_ml_all, world, n_all, label_logit_all, nblk_total, col_lse_all, col_nll_all, flag);
+  LATTE_LAUNCH_OK();
+  // exact fallback (every column, from the gathered features): gated on the flag
+  int nparts = clip_tc_nparts(n_all, n_all, device_sm_count());
+  if (nparts > kMaxParts) nparts = kMaxParts;
+  ClipFwdArgs a;
+  a.dtype = dtype; a.n_loc = n_all; a.n_all = n_all; a.dim = dim;
+  a.label_offset = 0; a.logit_scale = logit_scale; a.nparts = nparts;
+  a.gate = flag;
+  a.x = txt_all; a.ldx = ld_txt_all; a.y = img_all; a.ldy = ld_img_all;
+  a.part_max = ws + w.off_pmax_c; a.part_sum = ws + w.off_psum_c; a.diag = ws + w.off_diag_c;
+  int rc = clip_fwd_rows_tc(a, st);
+  if (rc) return rc;
+  gated_merge_kernel<<<(unsigned)((n_all + 255) / 256), 256, 0, st>>>(
+      flag, a.part_max, a.part_sum, nparts, n_all, label_logit_all, nullptr, col_lse_all,
+      col_nll_all);
+  LATTE_LAUNCH_OK();
+  const unsigned rblocks = (unsigned)((n_loc + 255) / 256);
+  double* lossp = reinterpret_cast<double*>(ws + w.off_lossp);
+  nll_loss_partial_kernel<<<rblocks, 256, 0, st>>>(row_nll, col_nll_all + label_offset, n_loc, lossp);
+  LATTE_LAUNCH_OK();
+  loss_reduce_kernel<<<1, 256, 0, st>>>(lossp, (int)rblocks, n_loc, loss);
+  LATTE_LAUNCH_OK();
+  return LATTE_OK;
 }
 
 static int clip_bwd_impl(const void* img_loc, int64_t ld_img_loc, const void* txt_loc,
@@ -551,12 +806,14 @@ static int clip_bwd_impl(const void* img_loc, int64_t ld_img_loc, const void* tx
                          const void* txt_all, int64_t ld_txt_all, int dtype, int64_t n_loc,
                          int64_t n_all, int64_t dim, int64_t label_offset,
                          const float* logit_scale, const float* row_lse_all,
-                         const float* col_lse_all, const float* grad_loss, float grad_mult,
+                         const float* col_lse_all, const float* row_nll_all,
+                         const float* col_nll_all, const float* grad_loss, float grad_mult,
                          int cross_terms, void* d_img, void* d_txt, int grad_dtype,
-                         int64_t ld_grad, float* d_scale, void* workspace,
+                         int64_t ld_grad, float* d_txt_partial, float* d_scale, void* workspace,
                          size_t workspace_bytes, void* stream, StageTimer* tm) {
   LATTE_CHECK_ARG(img_loc && txt_loc && img_all && txt_all && logit_scale && row_lse_all &&
-                  col_lse_all && grad_loss && d_img && d_txt && d_scale && workspace);
+                  col_lse_all && grad_loss && d_img && (d_txt || d_txt_partial) && d_scale && workspace);
+  LATTE_CHECK_ARG((row_nll_all == nullptr) == (col_nll_all == nullptr));
   LATTE_CHECK_ARG(n_loc > 0 && n_all >= n_loc && dim > 0);
   LATTE_CHECK_ARG(label_offset >= 0 && label_offset + n_loc <= n_all);
   LATTE_CHECK_ARG(dtype >= LATTE_F32 && dtype <= LATTE_F16);
@@ -574,13 +831,33 @@ static int clip_bwd_impl(const void* img_loc, int64_t ld_img_loc, const void* tx
   LATTE_MARK(-1);
   float* rho = ws + w.off_rho;
   int* fast_flag = reinterpret_cast<int*>(ws + w.off_rho + 1);
-  if (w.pair) {
-    lse_range_kernel<<<1, 1024, 0, st>>>(row_lse_all, col_lse_all, n_all, rho, fast_flag);
+  unsigned int* u_bits = reinterpret_cast<unsigned int*>(ws + w.off_rho + 2);
+  float* gscale = ws + w.off_rho + 3;
+  float* out_scale = ws + w.off_rho + 4;
+  const bool pair_ok =
+      w.pair && clip_pair_supported(dtype, dim, ld_img_loc, ld_txt_all, img_loc, txt_all) &&
+      clip_pair_supported(dtype, dim, ld_txt_loc, ld_img_all, txt_loc, img_all) &&
+      clip_pair_supported(dtype, dim, ld_img_all, ld_txt_all, img_all, txt_all);
+  if (pair_ok) {
+    // fp16 copies of the gathered features (bf16 input) + bound on |G| -> fp16 scale of G
+    LATTE_CUDA_OK(cudaMemsetAsync(u_bits, 0, sizeof(unsigned int), st));
+    __half* ya = reinterpret_cast<__half*>(ws + w.off_y16a);      // txt
+    __half* yb = img_all == txt_all ? ya : reinterpret_cast<__half*>(ws + w.off_y16b);   // img
+    const int64_t warps_needed = n_all;
+    const unsigned blocks = (unsigned)((warps_needed * 32 + 255) / 256 < 4096
+                                           ? (warps_needed * 32 + 255) / 256 : 4096);
+    pair_prep_features_kernel<<<blocks, 256, 0, st>>>(img_all, ld_img_all, txt_all, ld_txt_all,
+                                                      dtype == LATTE_BF16 ? 1 : 0, yb, ya,
+                                                      (int64_t)w.ld16, n_all, dim, logit_scale,
+                                                      row_lse_all, col_lse_all, u_bits);
+    LATTE_LAUNCH_OK();
+    lse_range_kernel<<<1, 1024, 0, st>>>(row_lse_all, col_lse_all, n_all, rho, fast_flag, u_bits,
+                                         gscale, grad_loss, grad_mult, logit_scale, n_loc, out_scale);
     LATTE_LAUNCH_OK();
   }
   lse_vectors_kernel<<<(unsigned)((w.n_pad + 255) / 256), 256, 0, st>>>(
       row_lse_all, col_lse_all, n_all, (int64_t)w.n_pad, rho, row2, col2,
-      w.pair ? ws + w.off_erow : nullptr, ws + w.off_einvrow, ws + w.off_ecol, ws + w.off_einvcol);
+      pair_ok ? ws + w.off_erow : nullptr, ws + w.off_einvrow, ws + w.off_ecol, ws + w.off_einvcol);
   LATTE_LAUNCH_OK();
 
   const bool tc = use_tc(dtype, dim, img_loc, ld_img_loc, txt_all, ld_txt_all, txt_loc,
@@ -591,7 +868,11 @@ static int clip_bwd_impl(const void* img_loc, int64_t ld_img_loc, const void* tx
   // fp16 operands for the second GEMM of the tc path
   const void* txt16 = txt_all; int64_t ld_txt16 = ld_txt_all;
   const void* img16 = img_all; int64_t ld_img16 = ld_img_all;
-  if (tc && dtype == LATTE_BF16) {
+  if (pair_ok && dtype == LATTE_BF16) {
+    txt16 = ws + w.off_y16a; ld_txt16 = (int64_t)w.ld16;
+    img16 = img_all == txt_all ? txt16 : static_cast<const void*>(ws + w.off_y16b);
+    ld_img16 = (int64_t)w.ld16;
+  } else if (tc && dtype == LATTE_BF16) {
     __half* ya = reinterpret_cast<__half*>(ws + w.off_y16a);
     __half* yb = reinterpret_cast<__half*>(ws + w.off_y16b);
     const int64_t work = n_all * ((dim + 7) / 8);
@@ -618,10 +899,7 @@ static int clip_bwd_impl(const void* img_loc, int64_t ld_img_loc, const void* tx
   }
 
   // ---- CTA-pair path: one logit recompute -> G, then the gradient GEMMs (clip_pair.cu)
-  if (tc && w.pair &&
-      clip_pair_supported(dtype, dim, ld_img_loc, ld_txt_all, img_loc, txt_all) &&
-      clip_pair_supported(dtype, dim, ld_txt_loc, ld_img_all, txt_loc, img_all) &&
-      clip_pair_supported(LATTE_F16, dim, ld_txt16, ld_img16, txt16, img16)) {
+  if (tc && pair_ok && clip_pair_supported(LATTE_F16, dim, ld_txt16, ld_img16, txt16, img16)) {
     const int dsn = clip_pair_ds_count();
     if ((size_t)(2 * dsn) > w.ds_cap) return LATTE_ERR_WORKSPACE;
     float* dsp = ws + w.off_ds;
@@ -630,19 +908,30 @@ static int clip_bwd_impl(const void* img_loc, int64_t ld_img_loc, const void* tx
     float* acc_t = ws + w.off_acc1;
     const size_t acc_bytes = (size_t)n_loc * w.ld32 * sizeof(float);
     LATTE_CUDA_OK(cudaMemsetAsync(dsp, 0, (size_t)2 * dsn * sizeof(float), st));
-    LATTE_CUDA_OK(cudaMemsetAsync(acc_i, 0, acc_bytes, st));
-    LATTE_CUDA_OK(cudaMemsetAsync(acc_t, 0, acc_bytes, st));
     const bool single = n_loc == n_all && img_loc == img_all && txt_loc == txt_all && cross_terms;
+    // one sweep per rank: the text-side product G^T . img_loc is returned as an fp32 partial
+    // over ALL columns for the caller to reduce-scatter (loss.py:49-50's backward)
+    const bool rank_sweep = !single && d_txt_partial != nullptr && cross_terms;
+    if (d_txt_partial && !rank_sweep) return LATTE_ERR_BAD_ARG;
+    if (!rank_sweep && !d_txt) return LATTE_ERR_BAD_ARG;
+    LATTE_CUDA_OK(cudaMemsetAsync(acc_i, 0, acc_bytes, st));
+    if (rank_sweep) {
+      LATTE_CUDA_OK(cudaMemsetAsync(d_txt_partial, 0, (size_t)n_all * (size_t)dim * sizeof(float), st));
+    } else {
+      LATTE_CUDA_OK(cudaMemsetAsync(acc_t, 0, acc_bytes, st));
+    }
     PairSweepArgs sa;
     sa.dtype = dtype; sa.n_loc = n_loc; sa.n_all = n_all; sa.dim = dim;
     sa.label_offset = label_offset; sa.logit_scale = logit_scale; sa.cross_terms = cross_terms;
-    sa.g = gbuf; sa.ds_both = single ? 1 : 0;
+    sa.g = gbuf; sa.ds_both = (single || rank_sweep) ? 1 : 0;
+    sa.nll_a = row_nll_all; sa.nll_b = col_nll_all;
     PairGemmArgs ga;
     ga.g = gbuf; ga.n_loc = n_loc; ga.n_all = n_all; ga.dim = dim; ga.ld32 = (int64_t)w.ld32;
     // image side: G[loc rows, :] and d_img = G . txt_all  (+ d_txt = G^T . img for one rank)
     sa.x = img_loc; sa.ldx = ld_img_loc; sa.y = txt_all; sa.ldy = ld_txt_all;
     sa.lse_a2 = row2; sa.lse_b2 = col2; sa.ds_partial = dsp;
     sa.e_a = ws + w.off_erow; sa.einv_b = ws + w.off_einvcol; sa.fast_flag = fast_flag;
+    sa.gscale_log2 = gscale;
     LATTE_MARK(LATTE_STAGE_BWD_PREP);
     int rc = clip_pair_sweep(sa, st);
     if (rc) return rc;
@@ -650,14 +939,21 @@ static int clip_bwd_impl(const void* img_loc, int64_t ld_img_loc, const void* tx
     ga.y16 = txt16; ga.ldy16 = ld_txt16;
     ga.x16 = single ? img16 : nullptr; ga.ldx16 = ld_img16;
     ga.dx32 = acc_i; ga.dy32 = acc_t;
+    ga.ld_dy32 = (int64_t)w.ld32; ga.dy_scale = nullptr;
+    if (rank_sweep) {
+      // rows [label_offset, label_offset + n_loc) of the gathered fp16 images are this rank's
+      ga.x16 = static_cast<const __half*>(img16) + label_offset * ld_img16;
+      ga.dy32 = d_txt_partial; ga.ld_dy32 = dim; ga.dy_scale = out_scale;
+    }
     rc = clip_pair_gemm(ga, st);
     if (rc) return rc;
     LATTE_MARK(LATTE_STAGE_BWD_GEMM);
-    if (!single) {
+    if (!single && !rank_sweep) {
       // text side: the transposed block G'[loc cols, :] and d_txt = G' . img_all
       sa.x = txt_loc; sa.ldx = ld_txt_loc; sa.y = img_all; sa.ldy = ld_img_all;
       sa.lse_a2 = col2; sa.lse_b2 = row2; sa.ds_partial = dsp + dsn;
       sa.e_a = ws + w.off_ecol; sa.einv_b = ws + w.off_einvrow;
+      sa.nll_a = col_nll_all; sa.nll_b = row_nll_all;
       rc = clip_pair_sweep(sa, st);
       if (rc) return rc;
       LATTE_MARK(LATTE_STAGE_BWD_SWEEP);
@@ -667,8 +963,8 @@ static int clip_bwd_impl(const void* img_loc, int64_t ld_img_loc, const void* tx
       if (rc) return rc;
       LATTE_MARK(LATTE_STAGE_BWD_GEMM);
     }
-    rc = clip_pair_scale_cast(acc_i, acc_t, (int64_t)w.ld32, d_img, d_txt, grad_dtype, ld_grad, n_loc,
-                              dim, grad_loss, grad_mult, logit_scale, n_loc, st);
+    rc = clip_pair_scale_cast(acc_i, rank_sweep ? nullptr : acc_t, (int64_t)w.ld32, d_img, d_txt,
+                              grad_dtype, ld_grad, n_loc, dim, out_scale, st);
     if (rc) return rc;
     ds_reduce_kernel<<<1, 256, 0, st>>>(dsp, 2 * dsn, grad_loss, grad_mult, n_loc, d_scale);
     LATTE_LAUNCH_OK();
@@ -676,6 +972,7 @@ static int clip_bwd_impl(const void* img_loc, int64_t ld_img_loc, const void* tx
     return LATTE_OK;
   }
   LATTE_MARK(LATTE_STAGE_BWD_PREP);
+  if (d_txt_partial || !d_txt) return LATTE_ERR_UNSUPPORTED;
 
   ClipBwdArgs a;
   a.dtype = dtype; a.n_loc = n_loc; a.n_all = n_all; a.dim = dim;
@@ -706,14 +1003,16 @@ extern "C" int latte_clip_bwd(const void* img_loc, int64_t ld_img_loc, const voi
                               const void* txt_all, int64_t ld_txt_all, int dtype, int64_t n_loc,
                               int64_t n_all, int64_t dim, int64_t label_offset,
                               const float* logit_scale, const float* row_lse_all,
-                              const float* col_lse_all, const float* grad_loss, float grad_mult,
+                              const float* col_lse_all, const float* row_nll_all,
+                              const float* col_nll_all, const float* grad_loss, float grad_mult,
                               int cross_terms, void* d_img, void* d_txt, int grad_dtype,
-                              int64_t ld_grad, float* d_scale, void* workspace,
-                              size_t workspace_bytes, void* stream) {
+                              int64_t ld_grad, float* d_txt_partial, float* d_scale,
+                              void* workspace, size_t workspace_bytes, void* stream) {
   return clip_bwd_impl(img_loc, ld_img_loc, txt_loc, ld_txt_loc, img_all, ld_img_all, txt_all,
                        ld_txt_all, dtype, n_loc, n_all, dim, label_offset, logit_scale, row_lse_all,
-                       col_lse_all, grad_loss, grad_mult, cross_terms, d_img, d_txt, grad_dtype,
-                       ld_grad, d_scale, workspace, workspace_bytes, stream, nullptr);
+                       col_lse_all, row_nll_all, col_nll_all, grad_loss, grad_mult, cross_terms, d_img,
+                       d_txt, grad_dtype, ld_grad, d_txt_partial, d_scale, workspace, workspace_bytes,
+                       stream, nullptr);
 }
 
 extern "C" int latte_clip_stage_times(const void* img_loc, int64_t ld_img_loc, const void* txt_loc,
@@ -725,7 +1024,8 @@ extern "C" int latte_clip_stage_times(const void* img_loc, int64_t ld_img_loc, c
                                       float* row_lse, float* col_lse, float* loss,
                                       const float* grad_loss, float grad_mult, int cross_terms,
                                       void* d_img, void* d_txt, int grad_dtype, int64_t ld_grad,
-                                      float* d_scale, void* fwd_workspace, size_t fwd_workspace_bytes,
+                                      float* d_txt_partial, float* d_scale, void* fwd_workspace,
+                                      size_t fwd_workspace_bytes,
                                       void* bwd_workspace, size_t bwd_workspace_bytes, void* stream,
                                       int reps, float* stage_ms) {
   LATTE_CHECK_ARG(stage_ms && reps > 0);
@@ -733,15 +1033,29 @@ extern "C" int latte_clip_stage_times(const void* img_loc, int64_t ld_img_loc, c
   for (int k = 0; k < LATTE_NUM_STAGES; ++k) stage_ms[k] = 0.f;
   for (int r = 0; r < reps; ++r) {
     StageTimer tm;
-    int rc = clip_fwd_impl(img_loc, ld_img_loc, txt_loc, ld_txt_loc, img_all, ld_img_all, txt_all,
-                           ld_txt_all, dtype, n_loc, n_all, dim, label_offset, logit_scale, row_lse,
-                           col_lse, loss, fwd_workspace, fwd_workspace_bytes, stream, &tm);
+    int rc;
+    if (d_txt_partial) {
+      // one-sweep multi-rank flow: step 1 of the forward (the merge step after the all-gather
+      // is a few microseconds and is not timed here), scratch outputs from the stream pool
+      float* tmp = nullptr;
+      const size_t tmp_floats = (size_t)3 * n_loc + (size_t)2 * n_all;
+      if (cudaMallocAsync(&tmp, tmp_floats * sizeof(float), st) != cudaSuccess) return LATTE_ERR_CUDA;
+      rc = clip_fwd_rows_impl(img_loc, ld_img_loc, txt_all, ld_txt_all, dtype, n_loc, n_all, dim,
+                              label_offset, logit_scale, tmp, tmp + n_loc, tmp + 2 * n_loc,
+                              tmp + 3 * n_loc, fwd_workspace, fwd_workspace_bytes, stream, &tm);
+      cudaFreeAsync(tmp, st);
+    } else {
+      rc = clip_fwd_impl(img_loc, ld_img_loc, txt_loc, ld_txt_loc, img_all, ld_img_all, txt_all,
+                         ld_txt_all, dtype, n_loc, n_all, dim, label_offset, logit_scale, row_lse,
+                         col_lse, nullptr, nullptr, loss, fwd_workspace, fwd_workspace_bytes, stream,
+                         &tm);
+    }
     if (rc == LATTE_OK)
       rc = clip_bwd_impl(img_loc, ld_img_loc, txt_loc, ld_txt_loc, img_all, ld_img_all, txt_all,
                          ld_txt_all, dtype, n_loc, n_all, dim, label_offset, logit_scale,
-                         row_lse_all, col_lse_all, grad_loss, grad_mult, cross_terms, d_img, d_txt,
-                         grad_dtype, ld_grad, d_scale, bwd_workspace, bwd_workspace_bytes, stream,
-                         &tm);
+                         row_lse_all, col_lse_all, nullptr, nullptr, grad_loss, grad_mult, cross_terms,
+                         d_img, d_txt, grad_dtype, ld_grad, d_txt_partial, d_scale, bwd_workspace,
+                         bwd_workspace_bytes, stream, &tm);
     const cudaError_t e = cudaStreamSynchronize(st);
     tm.collect(stage_ms);
     if (rc) return rc;

@@ -44,8 +44,8 @@ constexpr int kSweepSmem = kSweepStages * kRingStageBytes + kNumEpiWarps * (kSta
 
 constexpr int kGBlockElems = 128 * 64;          // one G block: 128 rows x 64 cols fp16
 
-constexpr float kGScaleLog2 = 13.0f;
-constexpr float kGScaleInv = 1.0f / 8192.0f;
+// G is stored as fp16 scaled by 2^gs; gs (>= 13) is chosen per call by the prep kernels from a
+// bound on max |G| so that a nearly converged batch (all weights tiny) keeps fp16 precision.
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
@@ -67,6 +67,9 @@ struct SweepParams {
   const float* e_a;                  // 2^(lse_a2 - rho)   (x side, indexed like lse_a2)
   const float* einv_b;               // 2^(rho - lse_b2)   (y side, indexed j)
   const int* fast_flag;              // 1: the LSE range allows the one-ex2 epilogue
+  const float* gscale_log2;          // log2 of the fp16 scale of G
+  const float* nll_a;                // nullable: lse - label logit of the x / y side
+  const float* nll_b;
   float cb, cd;
   float ds_cb, ds_cd;                // weights of the same terms inside d loss / d s
   float* ds_partial;                 // [gridDim.x]
@@ -276,8 +279,10 @@ pair_sweep_kernel(const __grid_constant__ CUtensorMap tmy, const __grid_constant
       // ======================================================== gradient weights
       const float s = __ldg(p.logit_scale);
       (void)s;
-      const float cd_scaled = p.cd * 8192.0f;
-      const float ds_cd_scaled = p.ds_cd * 8192.0f;
+      const float gs = __ldg(p.gscale_log2);
+      const float gscale = exp2f(gs);
+      const float cd_scaled = p.cd * gscale;
+      const float ds_cd_scaled = p.ds_cd * gscale;
       const float c2h = 0.5f * c2;
       const bool fast = __ldg(p.fast_flag) != 0;
       const bool ds_both = p.ds_cb != 0.f;
@@ -297,10 +302,10 @@ pair_sweep_kernel(const __grid_constant__ CUtensorMap tmy, const __grid_constant
         if (rb_i != cur_rb) {
           enter_row_block(it);
           // rows past the end: huge LSE and no cross term -> G = 0
-          a2 = row_ok ? __ldg(p.lse_a2 + label) - kGScaleLog2 : 1.0e30f;
+          a2 = row_ok ? __ldg(p.lse_a2 + label) - gs : 1.0e30f;
           cb = row_ok ? p.cb : 0.f;
           ds_cb = row_ok ? p.ds_cb : 0.f;
-          off_h = row_ok ? 0.5f * (kGScaleLog2 - __ldg(p.lse_a2 + label)) : -1.0e30f;
+          off_h = row_ok ? 0.5f * (gs - __ldg(p.lse_a2 + label)) : -1.0e30f;
           cbA = (row_ok && fast) ? p.cb * __ldg(p.e_a + label) : 0.f;
         }
         const int ct_cur = ct;
@@ -370,13 +375,21 @@ pair_sweep_kernel(const __grid_constant__ CUtensorMap tmy, const __grid_constant
                 const int i = i4 * 4 + x;
                 const float v = __uint_as_float(r[i]);
                 float ea = fast_exp2(fmaf(v, c2, -a2));
-                float eb = fast_exp2(fmaf(v, c2, kGScaleLog2 - bb[x]));
+                float eb = fast_exp2(fmaf(v, c2, gs - bb[x]));
                 if (ragged && col0 + h * 32 + i >= p.n_all) { ea = 0.f; eb = 0.f; }
                 float dw = fmaf(ds_cb, eb, ea);
                 g[x] = fmaf(cb, eb, ea);
                 if (i == want) {
-                  g[x] -= cd_scaled;
-                  dw -= ds_cd_scaled;
+                  if (p.nll_a != nullptr) {
+                    // P - 1 = expm1(-nll): no cancellation when the label dominates
+                    const float pa1 = expm1f(-__ldg(p.nll_a + label)) * gscale;
+                    const float pb1 = expm1f(-__ldg(p.nll_b + label)) * gscale;
+                    g[x] = fmaf(cb, pb1, pa1);
+                    dw = fmaf(ds_cb, pb1, pa1);
+                  } else {
+                    g[x] -= cd_scaled;
+                    dw -= ds_cd_scaled;
+                  }
                 }
                 ds_acc = fmaf(dw, v, ds_acc);
               }
@@ -403,7 +416,7 @@ pair_sweep_kernel(const __grid_constant__ CUtensorMap tmy, const __grid_constant
       if (lane == 0) bulk_wait_group<0>();
 
       // ---- d loss / d s partial of this CTA
-      float v = ds_acc * kGScaleInv;
+      float v = ds_acc * exp2f(-gs);
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
       if (lane == 0) red_ptr[e] = v;
@@ -564,6 +577,7 @@ struct GemmProblem {
   int64_t m_rows;      // valid output rows
   float* out;          // [m_rows, ld_out] fp32, accumulated with red.add
   int64_t ld_out;
+  const float* scale;  // nullable device scalar applied to every partial before the red.add
 };
 
 struct GemmParams {
@@ -728,6 +742,7 @@ pair_gemm_kernel(const __grid_constant__ CUtensorMap tma0, const __grid_constant
       const int64_t m = (int64_t)mt * 256 + (int64_t)rank * kPM + q * 32 + lane;
       const bool m_ok = m < pr.m_rows;
       float* orow = pr.out + (m_ok ? m : 0) * pr.ld_out;
+      const float osc = pr.scale ? __ldg(pr.scale) : 1.0f;
       mbar_wait(bar_tfull, seg & 1);
       tc_fence_after();
       for (int cc = 0; cc < cols_half; cc += 32) {
@@ -739,8 +754,8 @@ pair_gemm_kernel(const __grid_constant__ CUtensorMap tma0, const __grid_constant
 #pragma unroll
           for (int i = 0; i < 32; i += 4) {
             if (col + i < p.dim)
-              red_add_v4(orow + col + i, __uint_as_float(v[i]), __uint_as_float(v[i + 1]),
-                         __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
+              red_add_v4(orow + col + i, osc * __uint_as_float(v[i]), osc * __uint_as_float(v[i + 1]),
+                         osc * __uint_as_float(v[i + 2]), osc * __uint_as_float(v[i + 3]));
           }
         }
       }
@@ -760,15 +775,14 @@ pair_gemm_kernel(const __grid_constant__ CUtensorMap tma0, const __grid_constant
 __global__ void grad_scale_cast_kernel(const float* acc0, const float* acc1, int64_t ld_acc,
                                        void* out0, void* out1, int out_dtype,
                                        int64_t ld_out, int64_t rows, int64_t dim,
-                                       const float* grad_loss, float grad_mult,
-                                       const float* logit_scale, int64_t n_loc) {
+                                       const float* out_scale) {
   const float* acc = blockIdx.y ? acc1 : acc0;
   void* out = blockIdx.y ? out1 : out0;
   const int64_t per_row = dim / 4;
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= rows * per_row) return;
   const int64_t r = idx / per_row, c = (idx % per_row) * 4;
-  const float cs = __ldg(grad_loss) * grad_mult / (2.0f * (float)n_loc) * __ldg(logit_scale) * kGScaleInv;
+  const float cs = __ldg(out_scale);
   const float4 a = *reinterpret_cast<const float4*>(acc + r * ld_acc + c);
   const float o[4] = {a.x * cs, a.y * cs, a.z * cs, a.w * cs};
   if (out_dtype == LATTE_F32) {
@@ -904,7 +918,8 @@ int clip_pair_sweep(const PairSweepArgs& a, cudaStream_t stream) {
   p.label_offset = a.label_offset;
   p.logit_scale = a.logit_scale;
   p.lse_a2 = a.lse_a2; p.lse_b2 = a.lse_b2;
-  p.e_a = a.e_a; p.einv_b = a.einv_b; p.fast_flag = a.fast_flag;
+  p.e_a = a.e_a; p.einv_b = a.einv_b; p.fast_flag = a.fast_flag; p.gscale_log2 = a.gscale_log2;
+  p.nll_a = a.nll_a; p.nll_b = a.nll_b;
   p.cb = a.cross_terms ? 1.f : 0.f;
   p.cd = a.cross_terms ? 2.f : 1.f;
   // one sweep standing for both directions (world size 1) carries both softmax terms in ds
@@ -952,13 +967,15 @@ int clip_pair_gemm(const PairGemmArgs& a, cudaStream_t stream) {
   p.prob[0].m_rows = a.n_loc;
   p.prob[0].out = a.dx32;
   p.prob[0].ld_out = a.ld32;
+  p.prob[0].scale = nullptr;
   // dY = G^T . X : (world size 1) rows = columns of G, contraction over the rows of G
   p.prob[1].mode = 1;
   p.prob[1].m_tiles = geo.col_tiles / 2;
   p.prob[1].k_chunks = (int)((a.n_loc + 63) / 64);
   p.prob[1].m_rows = a.n_all;
   p.prob[1].out = a.dy32;
-  p.prob[1].ld_out = a.ld32;
+  p.prob[1].ld_out = a.ld_dy32;
+  p.prob[1].scale = a.dy_scale;
   for (int mode = 0; mode < 2; ++mode)
     for (int g = 0; g < 2; ++g) {
       const int cnt = p.nhalf - 2 * g >= 2 ? 2 : (p.nhalf - 2 * g == 1 ? 1 : 0);
@@ -977,12 +994,10 @@ int clip_pair_gemm(const PairGemmArgs& a, cudaStream_t stream) {
 
 int clip_pair_scale_cast(const float* acc0, const float* acc1, int64_t ld_acc, void* out0, void* out1,
                          int out_dtype, int64_t ld_out, int64_t rows, int64_t dim,
-                         const float* grad_loss, float grad_mult, const float* logit_scale,
-                         int64_t n_loc, cudaStream_t stream) {
+                         const float* out_scale, cudaStream_t stream) {
   const int64_t work = rows * (dim / 4);
-  grad_scale_cast_kernel<<<dim3((unsigned)((work + 255) / 256), 2), 256, 0, stream>>>(
-      acc0, acc1, ld_acc, out0, out1, out_dtype, ld_out, rows, dim, grad_loss, grad_mult, logit_scale,
-      n_loc);
+  grad_scale_cast_kernel<<<dim3((unsigned)((work + 255) / 256), acc1 ? 2 : 1), 256, 0, stream>>>(
+      acc0, acc1, ld_acc, out0, out1, out_dtype, ld_out, rows, dim, out_scale);
   LATTE_LAUNCH_OK();
   return LATTE_OK;
 }

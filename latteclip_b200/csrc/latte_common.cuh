@@ -99,6 +99,9 @@ struct PairSweepArgs {
   const float* e_a;           // 2^(lse_a2 - rho)
   const float* einv_b;        // 2^(rho - lse_b2)
   const int* fast_flag;       // device flag: LSE range small enough for the one-ex2 epilogue
+  const float* gscale_log2;   // device scalar: log2 of the fp16 scale of G
+  const float* nll_a;         // nullable: per-sample loss terms lse - label logit of the x side
+  const float* nll_b;         //           and the y side (accurate 1 - P_label near convergence)
   int cross_terms;
   int ds_both;                // 1: d loss / d s takes both softmax terms from this sweep
   void* g;                    // blocked fp16 G scratch (PairGeom::g_elems)
@@ -110,8 +113,10 @@ struct PairGemmArgs {
   const void* x16; int64_t ldx16;   // fp16 [n_loc, dim] or NULL (no transposed product)
   int64_t n_loc, n_all, dim;
   float* dx32;                      // [n_loc, ld32] zeroed
-  float* dy32;                      // [n_all, ld32] zeroed (with x16)
+  float* dy32;                      // [n_all, ld_dy32] zeroed (with x16)
   int64_t ld32;
+  int64_t ld_dy32;
+  const float* dy_scale;            // nullable device scalar multiplied into dy32's partials
 };
 // Forward on the same sweep: rows dealt to clusters as contiguous tile ranges; a row block
 // split over several clusters gets one partial slot per cluster.
@@ -149,8 +154,7 @@ int clip_pair_sweep(const PairSweepArgs& a, cudaStream_t stream);
 int clip_pair_gemm(const PairGemmArgs& a, cudaStream_t stream);
 int clip_pair_scale_cast(const float* acc0, const float* acc1, int64_t ld_acc, void* out0, void* out1,
                          int out_dtype, int64_t ld_out, int64_t rows, int64_t dim,
-                         const float* grad_loss, float grad_mult, const float* logit_scale,
-                         int64_t n_loc, cudaStream_t stream);
+                         const float* out_scale, cudaStream_t stream);
 
 // fp32 SIMT path (fp32 features; exact fp32 products).
 int clip_fwd_rows_simt(const ClipFwdArgs& a, cudaStream_t stream);

@@ -8,9 +8,7 @@ Mirrors the reference interface (same names, arguments, defaults and error behav
 
 ``ClipLoss.forward`` is the hot path: it never materialises the logit matrices.  It calls
 the CUDA extension (C ABI in include/latte_b200.h) through ``latteclip_b200._lib`` inside a
-``torch.autograd.Function``; the cross-rank exchange is one all-gather of the feature
-shards in forward and one all-gather of the two LSE vectors in backward (instead of the
-reference's reduce-scatter of [N, D] gradients, loss.py:49-50).  ``get_logits`` /
+``torch.autograd.Function``; the cross-rank exchanges are listed in ``_FusedClipLoss``.  ``get_logits`` /
 ``get_ground_truth`` remain as materialising utilities for subclasses
 (DistillClipLoss, loss.py:341-345); they are plain torch and not on the fused path.
 """
@@ -104,12 +102,35 @@ def gather_features(
 # ------------------------------------------------------------------------------------------
 # fused ClipLoss
 # ------------------------------------------------------------------------------------------
+def _reduce_scatter_sum(x: torch.Tensor, n: int, rank: int, group=None) -> torch.Tensor:
+    """rows [rank*n, (rank+1)*n) of the sum over ranks of x [W*n, D] (the backward of the
+    reference's differentiable all-gather, torch/distributed/nn/functional.py:343-354)."""
+    if dist.get_backend(group) == "nccl":
+        out = torch.empty((n,) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+        dist.reduce_scatter_tensor(out, x.contiguous(), op=dist.ReduceOp.SUM, group=group)
+        return out
+    x = x.contiguous()      # gloo has no reduce_scatter
+    dist.all_reduce(x, op=dist.ReduceOp.SUM, group=group)
+    return x[rank * n:(rank + 1) * n].clone()
+
+
 class _FusedClipLoss(torch.autograd.Function):
     """loss.py:102-130 fused.  Gradient contract:
          local_loss & gather_with_grad : grads = d(sum_r L_r)/dx_local   (W x global-mean grad)
          !local_loss & gather_with_grad: loss = L_global on every rank, same feature grads
          !local_loss & !gather_with_grad: grads = 1 x local slice of dL_global
          local_loss & !gather_with_grad : own-block terms only (gathered copies carry no grad)
+
+    Multi-rank, 16-bit features with dim <= 512 (every mode but the last): ONE logit sweep per
+    rank.  Forward: rows of this rank x all columns give the row LSEs and, from the same tiles,
+    per-column (max, sum) partials; one all-gather of [2N + 3n] floats per rank merges them into
+    every column's LSE.  Backward: one recompute sweep -> G[rows of this rank, :]; d_img is
+    local, the text gradient is an fp32 [N, D] partial that is reduce-scattered -- the
+    reference's own collective (the backward of its all_gather).  d loss / d logit_scale then
+    covers this rank's rows x all columns: a different partition over ranks of the same global
+    sum as the reference's (identical after DDP's all-reduce of the parameter gradient).
+    Other cases: each rank sweeps its row block and its column block (two sweeps) and the
+    backward exchanges only the LSE vectors.
     """
 
     @staticmethod
@@ -117,40 +138,66 @@ class _FusedClipLoss(torch.autograd.Function):
                 rank, world_size, group):
         img = image_features.detach()
         txt = text_features.detach()
+        cross_terms = not (world_size > 1 and local_loss and not gather_with_grad)
+        rank_sweep = False
         if world_size > 1:
             all_img = _all_gather_cat(img, group)
             all_txt = _all_gather_cat(txt, group)
             label_offset = rank * img.shape[0]
+            rank_sweep = cross_terms and _lib.rank_sweep_supported(img.dtype, img.shape[1])
         else:
             all_img, all_txt, label_offset = img, txt, 0
-        row_lse, col_lse, loss = _lib.clip_fwd(img, txt, all_img, all_txt, label_offset, logit_scale)
+        if rank_sweep:
+            n, big_n = img.shape[0], all_img.shape[0]
+            row_lse, row_nll, label_logit, col_ml = _lib.clip_fwd_rows(img, all_txt, label_offset,
+                                                                       logit_scale)
+            payload = torch.cat([col_ml.reshape(-1), row_lse, row_nll, label_logit])
+            gathered = _all_gather_cat(payload.reshape(1, -1), group)            # [W, 2N + 3n]
+            col_ml_all = gathered[:, :2 * big_n].reshape(world_size, big_n, 2)
+            row_lse_all = gathered[:, 2 * big_n:2 * big_n + n].reshape(-1)
+            row_nll_all = gathered[:, 2 * big_n + n:2 * big_n + 2 * n].reshape(-1)
+            label_logit_all = gathered[:, 2 * big_n + 2 * n:].reshape(-1)
+            col_lse_all, col_nll_all, loss = _lib.clip_fwd_cols(
+                col_ml_all, label_logit_all, row_nll, all_img, all_txt, n, label_offset, logit_scale)
+            stats = (row_lse_all, col_lse_all, row_nll_all, col_nll_all)
+        else:
+            row_lse, col_lse, loss, row_nll, col_nll = _lib.clip_fwd(
+                img, txt, all_img, all_txt, label_offset, logit_scale, with_nll=True)
+            stats = (row_lse, col_lse, row_nll, col_nll)
         loss = loss.reshape(())
         if world_size > 1 and not local_loss:
             # L_global = mean over ranks of the per-rank block losses (equal shard sizes)
             loss = loss.clone()
             dist.all_reduce(loss, op=dist.ReduceOp.SUM, group=group)
             loss = loss / world_size
-        ctx.save_for_backward(img, txt, all_img, all_txt, logit_scale.detach(), row_lse, col_lse)
-        ctx.cfg = (local_loss, gather_with_grad, rank, world_size, group, label_offset)
+        ctx.save_for_backward(img, txt, all_img, all_txt, logit_scale.detach(), *stats)
+        ctx.cfg = (local_loss, gather_with_grad, rank, world_size, group, label_offset, rank_sweep)
         ctx.scale_meta = (logit_scale.dtype, logit_scale.shape)
         ctx.feat_dtypes = (image_features.dtype, text_features.dtype)
         return loss
 
     @staticmethod
     def backward(ctx, grad_out):
-        img, txt, all_img, all_txt, scale, row_lse, col_lse = ctx.saved_tensors
-        local_loss, gather_with_grad, rank, world_size, group, label_offset = ctx.cfg
-        if world_size > 1:
-            both = _all_gather_cat(torch.stack([row_lse, col_lse], dim=1), group)   # [N, 2]
-            row_all, col_all = both[:, 0].contiguous(), both[:, 1].contiguous()
-        else:
-            row_all, col_all = row_lse, col_lse
+        img, txt, all_img, all_txt, scale, row_lse, col_lse, row_nll, col_nll = ctx.saved_tensors
+        local_loss, gather_with_grad, rank, world_size, group, label_offset, rank_sweep = ctx.cfg
         cross_terms = not (world_size > 1 and local_loss and not gather_with_grad)
         grad_mult = 1.0
         if world_size > 1 and not local_loss and not gather_with_grad:
             grad_mult = 1.0 / world_size
-        d_img, d_txt, d_scale = _lib.clip_bwd(img, txt, all_img, all_txt, label_offset, scale,
-                                              row_all, col_all, grad_out, grad_mult, cross_terms)
+        if rank_sweep:
+            d_img, d_part, d_scale = _lib.clip_bwd(
+                img, txt, all_img, all_txt, label_offset, scale, row_lse, col_lse, grad_out,
+                grad_mult, True, row_nll_all=row_nll, col_nll_all=col_nll, partial=True)
+            d_txt = _reduce_scatter_sum(d_part, img.shape[0], rank, group).to(img.dtype)
+        else:
+            if world_size > 1:
+                four = _all_gather_cat(torch.stack([row_lse, col_lse, row_nll, col_nll], dim=1), group)
+                row_all, col_all, rown_all, coln_all = (four[:, k].contiguous() for k in range(4))
+            else:
+                row_all, col_all, rown_all, coln_all = row_lse, col_lse, row_nll, col_nll
+            d_img, d_txt, d_scale = _lib.clip_bwd(
+                img, txt, all_img, all_txt, label_offset, scale, row_all, col_all, grad_out,
+                grad_mult, cross_terms, row_nll_all=rown_all, col_nll_all=coln_all)
         if world_size > 1 and not local_loss:
             # every rank differentiates the same L_global: d/ds is the rank mean of the block sums
             d_scale = d_scale / grad_mult

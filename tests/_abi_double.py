@@ -9,7 +9,40 @@ header's formulas, not the reference's code."""
 import torch
 
 
-def clip_fwd(img_loc, txt_loc, img_all, txt_all, label_offset, logit_scale):
+def rank_sweep_supported(dtype, dim):
+    return True      # exercise the one-sweep multi-rank host logic on the CPU
+
+
+def clip_fwd_rows(img_loc, txt_all, label_offset, logit_scale):
+    s = logit_scale.detach().double().reshape(())
+    il, ta = img_loc.detach().double(), txt_all.detach().double()
+    n = il.shape[0]
+    sm = s * il @ ta.T                                   # [n, N]
+    row_lse = torch.logsumexp(sm, 1)
+    label_logit = sm[torch.arange(n), torch.arange(n) + label_offset]
+    row_nll = row_lse - label_logit
+    x2 = sm * LOG2E
+    m = x2.max(0).values
+    col_ml = torch.stack([m, torch.exp2(x2 - m[None, :]).sum(0)], dim=1)     # [N, 2] base 2
+    return row_lse.float(), row_nll.float(), label_logit.float(), col_ml.float()
+
+
+def clip_fwd_cols(col_ml_all, label_logit_all, row_nll, img_all, txt_all, n_loc, label_offset,
+                  logit_scale):
+    ml = col_ml_all.double()                              # [W, N, 2]
+    m = ml[:, :, 0].max(0).values
+    big_l = (ml[:, :, 1] * torch.exp2(ml[:, :, 0] - m[None, :])).sum(0)
+    col_lse_all = (m + torch.log2(big_l)) / LOG2E
+    col_nll_all = col_lse_all - label_logit_all.double()
+    own = slice(label_offset, label_offset + n_loc)
+    loss = (row_nll.double().mean() + col_nll_all[own].mean()) / 2
+    return col_lse_all.float(), col_nll_all.float(), loss.float().reshape(1)
+
+
+LOG2E = 1.4426950408889634
+
+
+def clip_fwd(img_loc, txt_loc, img_all, txt_all, label_offset, logit_scale, with_nll=False):
     s = logit_scale.detach().double().reshape(())
     il, tl, ia, ta = (x.detach().double() for x in (img_loc, txt_loc, img_all, txt_all))
     n = il.shape[0]
@@ -21,11 +54,15 @@ def clip_fwd(img_loc, txt_loc, img_all, txt_all, label_offset, logit_scale):
     diag_r = s_r[torch.arange(n), idx]
     diag_c = s_c[torch.arange(n), idx]
     loss = ((row_lse - diag_r).mean() + (col_lse - diag_c).mean()) / 2
+    if with_nll:
+        return (row_lse.float(), col_lse.float(), loss.float().reshape(1),
+                (row_lse - diag_r).float(), (col_lse - diag_c).float())
     return row_lse.float(), col_lse.float(), loss.float().reshape(1)
 
 
 def clip_bwd(img_loc, txt_loc, img_all, txt_all, label_offset, logit_scale, row_lse_all,
-             col_lse_all, grad_loss, grad_mult, cross_terms):
+             col_lse_all, grad_loss, grad_mult, cross_terms, grad_dtype=None, row_nll_all=None,
+             col_nll_all=None, partial=False):
     s = logit_scale.detach().double().reshape(())
     il, tl, ia, ta = (x.detach().double() for x in (img_loc, txt_loc, img_all, txt_all))
     n = il.shape[0]
@@ -44,6 +81,16 @@ def clip_bwd(img_loc, txt_loc, img_all, txt_all, label_offset, logit_scale, row_
         ea[torch.arange(n), idx] -= 1.0
         ds = coef * (ea * (sm / s)).sum()
         return dx, ds
+    if partial:
+        # one-sweep mode: G of this rank's rows x all columns; the text gradient is the partial
+        # G^T @ img_loc over every column, d_scale covers rows of this rank x all columns
+        sm = s * il @ ta.T
+        g = torch.exp(sm - row_all[idx][:, None]) + torch.exp(sm - col_all[None, :])
+        g[torch.arange(n), idx] -= 2.0
+        d_img = coef * s * g @ ta
+        d_part = coef * s * g.T @ il
+        ds = coef * (g * (sm / s)).sum()
+        return d_img.to(img_loc.dtype), d_part.float(), ds.float().reshape(1)
     d_img, ds_a = side(il, ta, row_all, col_all)
     d_txt, ds_b = side(tl, ia, col_all, row_all)
     return d_img.to(img_loc.dtype), d_txt.to(img_loc.dtype), (ds_a + ds_b).float().reshape(1)

@@ -271,3 +271,69 @@ def test_full_size_32k_properties():
     dI_ref = scale / (2 * n) * G @ Tf
     assert rel(di[rows], dI_ref) < GRAD_RTOL_BF16_OUT
     assert math.isfinite(float(full))
+
+
+# ------------------------------------------------------------------ one logit sweep per rank
+@pytest.mark.parametrize("world,n,d,sigma", [(2, 512, 512, 4.0), (4, 300, 256, 4.0), (3, 130, 64, 3.0)])
+def test_one_sweep_per_rank_path_emulated_on_one_gpu(world, n, d, sigma):
+    """latte_clip_fwd_rows / _fwd_cols / _bwd(partial) -- the multi-rank path of 16-bit features
+    with dim <= 512 -- driven for every rank on one GPU: the column partials are stacked instead
+    of all-gathered and the text-gradient partials summed instead of reduce-scattered.  Checked
+    against the fp64 oracle of the reference's local_loss + gather_with_grad mode."""
+    from latteclip_b200 import _lib
+    from oracle.clip_loss import clip_loss_all_ranks
+    dev = torch.device("cuda:0")
+    i_all, t_all = synth(n * world, d, sigma, 7 + n)
+    ib, tb = i_all.to(dev).bfloat16(), t_all.to(dev).bfloat16()
+    ir, tr = ib.float().cpu(), tb.float().cpu()
+    ish = [ir[r * n:(r + 1) * n] for r in range(world)]
+    tsh = [tr[r * n:(r + 1) * n] for r in range(world)]
+    lo, di, dt, ds = clip_loss_all_ranks(ish, tsh, 100.0, True, True)
+    sc = torch.tensor(100.0, device=dev)
+    one = torch.ones(1, device=dev)
+    assert _lib.rank_sweep_supported(torch.bfloat16, d)
+    rows = [_lib.clip_fwd_rows(ib[r * n:(r + 1) * n], tb, r * n, sc) for r in range(world)]
+    col_ml_all = torch.stack([x[3] for x in rows])
+    row_lse_all = torch.cat([x[0] for x in rows])
+    row_nll_all = torch.cat([x[1] for x in rows])
+    label_all = torch.cat([x[2] for x in rows])
+    parts, d_imgs, d_scales = [], [], []
+    for r in range(world):
+        sl = slice(r * n, (r + 1) * n)
+        col_lse_all, col_nll_all, loss_r = _lib.clip_fwd_cols(col_ml_all, label_all, rows[r][1], ib, tb,
+                                                              n, r * n, sc)
+        assert abs(float(loss_r) - float(lo[r])) <= LOSS_RTOL * abs(float(lo[r])) + 2e-5
+        d_img, d_part, d_s = _lib.clip_bwd(ib[sl], tb[sl], ib, tb, r * n, sc, row_lse_all, col_lse_all,
+                                           one, 1.0, True, grad_dtype=torch.float32,
+                                           row_nll_all=row_nll_all, col_nll_all=col_nll_all, partial=True)
+        assert d_part.shape == (n * world, d) and d_part.dtype == torch.float32
+        parts.append(d_part)
+        d_imgs.append(d_img)
+        d_scales.append(float(d_s))
+    d_txt = sum(parts)                                       # what the reduce-scatter delivers
+    for r in range(world):
+        assert rel(d_imgs[r], di[r]) < GRAD_RTOL_16
+        assert rel(d_txt[r * n:(r + 1) * n], dt[r]) < GRAD_RTOL_16
+    ref_ds = sum(float(x) for x in ds)
+    assert abs(sum(d_scales) - ref_ds) <= 2e-3 * abs(ref_ds) + 1e-6
+
+
+def test_flushed_column_triggers_exact_fallback():
+    """A text whose best logit sits far below its block's row maxima: its column sum is built
+    from terms the one-ex2 column path flushes, so the forward must take the exact fallback."""
+    from latteclip_b200 import _lib
+    dev = torch.device("cuda:0")
+    n, d = 512, 256
+    g = torch.Generator().manual_seed(3)
+    i = F.normalize(torch.randn(n, d, generator=g), dim=1)
+    t = i.clone()                                  # perfectly matched pairs: logits 100 on the diagonal
+    t[5] = -i[5]                                   # one anti-correlated pair: column 5 peaks near 0
+    ib, tb = i.to(dev).bfloat16(), t.to(dev).bfloat16()
+    sc = torch.tensor(100.0, device=dev)
+    row, col, loss = _lib.clip_fwd(ib, tb, ib, tb, 0, sc)
+    S = 100.0 * ib.double() @ tb.double().T
+    assert torch.allclose(row.double(), torch.logsumexp(S, 1), rtol=0, atol=2e-4)
+    assert torch.allclose(col.double(), torch.logsumexp(S.T, 1), rtol=0, atol=2e-4)
+    lab = torch.arange(n, device=dev)
+    ref = 0.5 * (F.cross_entropy(S, lab) + F.cross_entropy(S.T, lab))
+    assert abs(float(loss) - float(ref)) <= 1e-5 * abs(float(ref)) + 2e-5

@@ -70,14 +70,29 @@ def test_nccl_cliploss_matches_oracle(dtype_name, n, d):
     ish = [ir[r * n:(r + 1) * n] for r in range(world)]
     tsh = [tr[r * n:(r + 1) * n] for r in range(world)]
     gtol = 2.6e-3 if dtype_name == "bfloat16" else 5e-5   # bf16 outputs: see test_gpu_clip.py
+    report = []
     for key in ((True, True), (True, False), (False, True), (False, False)):
         lo, di, dt, ds = clip_loss_all_ranks(ish, tsh, 100.0, key[0], key[1])
         for r in range(world):
             got = ret[r][key]
-            assert abs(got["loss"] - float(lo[r])) <= 1e-5 * abs(float(lo[r])) + 2e-5
-            assert float((got["dI"].double() - di[r]).norm() / di[r].norm()) < gtol
-            assert float((got["dT"].double() - dt[r]).norm() / dt[r].norm()) < gtol
-            assert abs(got["ds"] - float(ds[r])) <= 2e-3 * abs(float(ds[r])) + 1e-6
+            e_i = float((got["dI"].double() - di[r]).norm() / di[r].norm())
+            e_t = float((got["dT"].double() - dt[r]).norm() / dt[r].norm())
+            report.append((key, r, got["loss"], float(lo[r]), e_i, e_t, float(di[r].norm()), got["ds"], float(ds[r])))
+    for row in report:
+        print("local_loss=%s gwg=%s rank %d loss %.6f ref %.6f dI %.3e dT %.3e |dI| %.3e ds %.4e ref %.4e" %
+              (row[0][0], row[0][1], *row[1:]))
+    one_sweep = dtype_name == "bfloat16"     # 16-bit, dim <= 512: one logit sweep per rank
+    for key, r, loss, lref, e_i, e_t, _, dsv, dsr in report:
+        assert abs(loss - lref) <= 1e-5 * abs(lref) + 2e-5, (key, r)
+        assert e_i < gtol and e_t < gtol, (key, r, e_i, e_t)
+        if one_sweep and key == (True, True):
+            # d loss / d s covers rows-of-this-rank x all columns: the sum over ranks (what
+            # DDP's all-reduce of the parameter gradient sees) is the reference's
+            got = sum(x[7] for x in report if x[0] == key)
+            ref_sum = sum(x[8] for x in report if x[0] == key)
+            assert abs(got - ref_sum) <= 2e-3 * abs(ref_sum) + 1e-6, (key, r)
+        else:
+            assert abs(dsv - dsr) <= 2e-3 * abs(dsr) + 1e-6, (key, r)
     c = 11
     bank = F.normalize(torch.randn(c, d, generator=g), dim=1)
     preds = torch.randint(0, c, (n * world,), generator=g)
