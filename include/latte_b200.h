@@ -104,7 +104,8 @@ int latte_clip_fwd(const void* img_loc, int64_t ld_img_loc,
  * gathered text features ->
  *   row_lse / row_nll / label_logit [n_loc]   (label_logit[i] = s * <img_loc[i], txt_all[off+i]>)
  *   col_ml [n_all, 2]                         base-2 (max, sum) of every column over THIS rank's rows
- * The caller all-gathers col_ml (and label_logit) across ranks; step 2 merges them:
+ * The four outputs may be views of ONE packed buffer [2 n_all + 3 n_loc] in that order
+ * (col_ml first); the caller all-gathers that buffer across ranks and step 2 merges it:
  *   col_lse_all / col_nll_all [n_all], *loss = (mean_i row_nll[i] + mean_i col_nll_all[off+i]) / 2.
  * If a column's partial sums may have lost flushed terms, step 2 recomputes every column exactly
  * from the gathered features (device-side decision, no host sync).
@@ -117,14 +118,16 @@ int latte_clip_fwd_rows(const void* img_loc, int64_t ld_img_loc,
                         float* row_lse, float* row_nll, float* label_logit, float* col_ml,
                         void* workspace, size_t workspace_bytes, void* stream);
 int latte_clip_fwd_cols_workspace_bytes(int64_t n_all, int64_t dim, int dtype, size_t* bytes);
-int latte_clip_fwd_cols(const float* col_ml_all /* [world, n_all, 2] */, int world,
-                        const float* label_logit_all /* [n_all] */,
-                        const float* row_nll /* [n_loc], this rank */,
+int latte_clip_fwd_cols(const float* gathered /* [world, stride]: per rank col_ml [n_all, 2] |
+                                                    row_lse | row_nll | label_logit [n_loc] each */,
+                        int64_t stride, int world,
                         const void* img_all, int64_t ld_img_all,
                         const void* txt_all, int64_t ld_txt_all,
                         int dtype, int64_t n_loc, int64_t n_all, int64_t dim,
                         int64_t label_offset, const float* logit_scale,
-                        float* col_lse_all, float* col_nll_all, float* loss,
+                        float* row_lse_all, float* row_nll_all,      /* [n_all] unpacked     */
+                        float* col_lse_all, float* col_nll_all,      /* [n_all] merged       */
+                        float* loss,
                         void* workspace, size_t workspace_bytes, void* stream);
 
 /*

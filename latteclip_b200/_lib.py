@@ -69,8 +69,8 @@ def _declare(lib):
     lib.latte_clip_fwd_rows.argtypes = [vp, i64, vp, i64, i32, i64, i64, i64, i64, vp,
                                         vp, vp, vp, vp, vp, sz, vp]
     lib.latte_clip_fwd_cols_workspace_bytes.argtypes = [i64, i64, i32, c.POINTER(sz)]
-    lib.latte_clip_fwd_cols.argtypes = [vp, i32, vp, vp, vp, i64, vp, i64, i32, i64, i64, i64, i64,
-                                        vp, vp, vp, vp, vp, sz, vp]
+    lib.latte_clip_fwd_cols.argtypes = [vp, i64, i32, vp, i64, vp, i64, i32, i64, i64, i64, i64,
+                                        vp, vp, vp, vp, vp, vp, vp, sz, vp]
     lib.latte_clip_bwd.argtypes = [vp, i64, vp, i64, vp, i64, vp, i64, i32, i64, i64, i64, i64,
                                    vp, vp, vp, vp, vp, vp, f32, i32, vp, vp, i32, i64, vp, vp, vp,
                                    sz, vp]
@@ -195,7 +195,8 @@ def clip_fwd(img_loc, txt_loc, img_all, txt_all, label_offset: int, logit_scale,
     loss = torch.empty(1, dtype=torch.float32, device=dev)
     row_nll = torch.empty(n_loc, dtype=torch.float32, device=dev) if with_nll else None
     col_nll = torch.empty(n_loc, dtype=torch.float32, device=dev) if with_nll else None
-    ws = _workspace(n_loc, n_all, dim, dt, dev)
+    ws = _cached_workspace(("fwd", n_loc, n_all, dim, dt),
+                           lambda: _workspace(n_loc, n_all, dim, dt, dev).numel(), dev)
     wp, wn = _aligned_ptr(ws)
     with torch.cuda.device(dev):
         _check(lib.latte_clip_fwd(_ptr(img_loc), img_loc.stride(0), _ptr(txt_loc), txt_loc.stride(0),
@@ -217,9 +218,25 @@ def rank_sweep_supported(dtype: torch.dtype, dim: int) -> bool:
     return bool(load().latte_clip_rank_sweep_supported(_DTYPES[dtype], dim))
 
 
+_WS_CACHE = {}
+
+
+def _cached_workspace(key, nbytes_fn, device):
+    """Scratch reused across calls (one buffer per device, stream and shape key): the kernels
+    of one call are stream-ordered before the next call's on the same stream."""
+    k = (key, device.index, torch.cuda.current_stream(device).cuda_stream)
+    ws = _WS_CACHE.get(k)
+    if ws is None:
+        ws = torch.empty(nbytes_fn() + 256, dtype=torch.uint8, device=device)
+        if len(_WS_CACHE) > 64:
+            _WS_CACHE.clear()
+        _WS_CACHE[k] = ws
+    return ws
+
+
 def clip_fwd_rows(img_loc, txt_all, label_offset: int, logit_scale):
-    """Step 1 of the multi-rank forward -> (row_lse[n_loc], row_nll[n_loc], label_logit[n_loc],
-    col_ml[n_all, 2])."""
+    """Step 1 of the multi-rank forward -> packed fp32 payload [2 n_all + 3 n_loc]:
+    col_ml [n_all, 2] | row_lse | row_nll | label_logit  (what the ranks all-gather)."""
     lib = load()
     img_loc, txt_all = _rows(img_loc, "image_features"), _rows(txt_all, "all_text_features")
     dt = _dt(img_loc)
@@ -227,51 +244,62 @@ def clip_fwd_rows(img_loc, txt_all, label_offset: int, logit_scale):
     n_all = txt_all.shape[0]
     dev = img_loc.device
     s = _scalar_f32(logit_scale)
-    row_lse = torch.empty(n_loc, dtype=torch.float32, device=dev)
-    row_nll = torch.empty(n_loc, dtype=torch.float32, device=dev)
-    label_logit = torch.empty(n_loc, dtype=torch.float32, device=dev)
-    col_ml = torch.empty(n_all, 2, dtype=torch.float32, device=dev)
-    ws = _workspace(n_loc, n_all, dim, dt, dev)
+    payload = torch.empty(2 * n_all + 3 * n_loc, dtype=torch.float32, device=dev)
+    base = payload.data_ptr()
+    col_ml = ctypes.c_void_p(base)
+    row_lse = ctypes.c_void_p(base + 8 * n_all)
+    row_nll = ctypes.c_void_p(base + 8 * n_all + 4 * n_loc)
+    label_logit = ctypes.c_void_p(base + 8 * n_all + 8 * n_loc)
+
+    def need():
+        nbytes = ctypes.c_size_t(0)
+        _check(lib.latte_clip_workspace_bytes(n_loc, n_all, dim, dt, ctypes.byref(nbytes)),
+               "latte_clip_workspace_bytes")
+        return nbytes.value
+    ws = _cached_workspace(("fwd", n_loc, n_all, dim, dt), need, dev)
     wp, wn = _aligned_ptr(ws)
     with torch.cuda.device(dev):
         _check(lib.latte_clip_fwd_rows(_ptr(img_loc), img_loc.stride(0), _ptr(txt_all), txt_all.stride(0),
-                                       dt, n_loc, n_all, dim, label_offset, _ptr(s), _ptr(row_lse),
-                                       _ptr(row_nll), _ptr(label_logit), _ptr(col_ml), wp, wn,
-                                       _stream(img_loc)),
+                                       dt, n_loc, n_all, dim, label_offset, _ptr(s), row_lse,
+                                       row_nll, label_logit, col_ml, wp, wn, _stream(img_loc)),
                "latte_clip_fwd_rows")
-    return row_lse, row_nll, label_logit, col_ml
+    return payload
 
 
-def clip_fwd_cols(col_ml_all, label_logit_all, row_nll, img_all, txt_all, n_loc: int,
-                  label_offset: int, logit_scale):
-    """Step 2 of the multi-rank forward -> (col_lse_all[n_all], col_nll_all[n_all], loss[1])."""
+def clip_fwd_cols(gathered, img_all, txt_all, n_loc: int, label_offset: int, logit_scale):
+    """Step 2 of the multi-rank forward.  ``gathered``: the all-gathered payloads
+    [world, 2 n_all + 3 n_loc] -> (row_lse_all, row_nll_all, col_lse_all, col_nll_all) [n_all]
+    each and loss[1]."""
     lib = load()
     img_all, txt_all = _rows(img_all, "all_image_features"), _rows(txt_all, "all_text_features")
     dt = _dt(img_all)
     n_all, dim = img_all.shape
     dev = img_all.device
-    world = col_ml_all.shape[0]
-    col_ml_all = _vec(col_ml_all, torch.float32, "col_ml_all")
-    label_logit_all = _vec(label_logit_all, torch.float32, "label_logit_all")
-    row_nll = _vec(row_nll, torch.float32, "row_nll")
-    if col_ml_all.numel() != world * n_all * 2 or label_logit_all.numel() != n_all:
-        raise RuntimeError("clip_fwd_cols: gathered vectors have the wrong size")
+    if gathered.dim() != 2 or gathered.dtype != torch.float32 or gathered.stride(1) != 1:
+        raise RuntimeError("clip_fwd_cols: gathered must be a 2-D fp32 tensor")
+    world = gathered.shape[0]
+    if gathered.shape[1] != 2 * n_all + 3 * n_loc or n_all != n_loc * world:
+        raise RuntimeError("clip_fwd_cols: gathered payload has the wrong size")
     s = _scalar_f32(logit_scale)
-    col_lse_all = torch.empty(n_all, dtype=torch.float32, device=dev)
-    col_nll_all = torch.empty(n_all, dtype=torch.float32, device=dev)
+    out = torch.empty(4, n_all, dtype=torch.float32, device=dev)
     loss = torch.empty(1, dtype=torch.float32, device=dev)
-    nbytes = ctypes.c_size_t(0)
-    _check(lib.latte_clip_fwd_cols_workspace_bytes(n_all, dim, dt, ctypes.byref(nbytes)),
-           "latte_clip_fwd_cols_workspace_bytes")
-    ws = torch.empty(nbytes.value + 256, dtype=torch.uint8, device=dev)
+    optr = out.data_ptr()
+    vecs = [ctypes.c_void_p(optr + 4 * n_all * k) for k in range(4)]
+
+    def need():
+        nbytes = ctypes.c_size_t(0)
+        _check(lib.latte_clip_fwd_cols_workspace_bytes(n_all, dim, dt, ctypes.byref(nbytes)),
+               "latte_clip_fwd_cols_workspace_bytes")
+        return nbytes.value
+    ws = _cached_workspace(("cols", n_all, dim, dt), need, dev)
     wp, wn = _aligned_ptr(ws)
     with torch.cuda.device(dev):
-        _check(lib.latte_clip_fwd_cols(_ptr(col_ml_all), world, _ptr(label_logit_all), _ptr(row_nll),
+        _check(lib.latte_clip_fwd_cols(_ptr(gathered), gathered.stride(0), world,
                                        _ptr(img_all), img_all.stride(0), _ptr(txt_all), txt_all.stride(0),
-                                       dt, n_loc, n_all, dim, label_offset, _ptr(s), _ptr(col_lse_all),
-                                       _ptr(col_nll_all), _ptr(loss), wp, wn, _stream(img_all)),
+                                       dt, n_loc, n_all, dim, label_offset, _ptr(s), vecs[0], vecs[1],
+                                       vecs[2], vecs[3], _ptr(loss), wp, wn, _stream(img_all)),
                "latte_clip_fwd_cols")
-    return col_lse_all, col_nll_all, loss
+    return out[0], out[1], out[2], out[3], loss
 
 
 def clip_bwd(img_loc, txt_loc, img_all, txt_all, label_offset: int, logit_scale,
@@ -306,7 +334,8 @@ def clip_bwd(img_loc, txt_loc, img_all, txt_all, label_offset: int, logit_scale,
     d_txt = None if partial else torch.empty(n_loc, dim, dtype=gdt, device=dev)
     d_part = torch.empty(n_all, dim, dtype=torch.float32, device=dev) if partial else None
     d_scale = torch.empty(1, dtype=torch.float32, device=dev)
-    ws = _workspace(n_loc, n_all, dim, dt, dev, bwd=True)
+    ws = _cached_workspace(("bwd", n_loc, n_all, dim, dt),
+                           lambda: _workspace(n_loc, n_all, dim, dt, dev, bwd=True).numel(), dev)
     wp, wn = _aligned_ptr(ws)
     with torch.cuda.device(dev):
         _check(lib.latte_clip_bwd(_ptr(img_loc), img_loc.stride(0), _ptr(txt_loc), txt_loc.stride(0),

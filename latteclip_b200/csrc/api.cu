@@ -178,29 +178,36 @@ pair_col_finalize_kernel(const float* col_part, const float* col_ref, int64_t ld
   }
 }
 
-// Multi-rank forward: merge the per-rank column (max, sum) pairs [world, n_all, 2] into the
-// column LSE and per-sample loss term of every column; same exactness check as above.
+// Multi-rank forward: `gathered` is the all-gathered per-rank payload [world, stride] with
+// col_ml [n_all, 2] | row_lse [n_loc] | row_nll [n_loc] | label_logit [n_loc] per rank.  Merges
+// the column (max, sum) pairs into every column's LSE and per-sample loss term (same exactness
+// check as above) and unpacks the row vectors into contiguous [n_all] arrays.
 __global__ void __launch_bounds__(256)
-col_merge_kernel(const float* col_ml_all, int world, int64_t n_all, const float* label_logit_all,
-                 int nblk_total, float* col_lse_all, float* col_nll_all, int* flag) {
+col_merge_kernel(const float* gathered, int64_t stride, int world, int64_t n_loc, int64_t n_all,
+                 int nblk_total, float* row_lse_all, float* row_nll_all, float* label_logit_all,
+                 float* col_lse_all, float* col_nll_all, int* flag) {
   const int64_t j = (int64_t)blockIdx.x * 256 + threadIdx.x;
   if (j >= n_all) return;
+  const float* own = gathered + (j / n_loc) * stride + 2 * n_all + (j % n_loc);
+  const float label_logit = own[2 * n_loc];
+  row_lse_all[j] = own[0];
+  row_nll_all[j] = own[n_loc];
+  label_logit_all[j] = label_logit;
   float M = -INFINITY, L = 0.f;
   for (int w = 0; w < world; ++w) {
-    const float mw = col_ml_all[((int64_t)w * n_all + j) * 2];
-    const float lw = col_ml_all[((int64_t)w * n_all + j) * 2 + 1];
-    if (!(mw > -INFINITY)) continue;
-    if (mw > M) {
-      L = L * exp2f(M - mw) + lw;
-      M = mw;
+    const float2 ml = *reinterpret_cast<const float2*>(gathered + (int64_t)w * stride + 2 * j);
+    if (!(ml.x > -INFINITY)) continue;
+    if (ml.x > M) {
+      L = L * exp2f(M - ml.x) + ml.y;
+      M = ml.x;
     } else {
-      L = fmaf(lw, exp2f(mw - M), L);
+      L = fmaf(ml.y, exp2f(ml.x - M), L);
     }
   }
   const float logL = log2f(L);
   const float lse2 = M + logL;
   col_lse_all[j] = lse2 * kLn2;
-  col_nll_all[j] = ((M - kLog2e * label_logit_all[j]) + logL) * kLn2;
+  col_nll_all[j] = (fmaf(-kLog2e, label_logit, M) + logL) * kLn2;
   const bool ok = (M - lse2) + log2f((float)nblk_total) < 95.0f;
   if (!ok) atomicOr(flag, 1);
 }
@@ -753,16 +760,18 @@ extern "C" int latte_clip_fwd_cols_workspace_bytes(int64_t n_all, int64_t dim, i
   return LATTE_OK;
 }
 
-extern "C" int latte_clip_fwd_cols(const float* col_ml_all, int world, const float* label_logit_all,
-                                   const float* row_nll, const void* img_all, int64_t ld_img_all,
-                                   const void* txt_all, int64_t ld_txt_all, int dtype,
-                                   int64_t n_loc, int64_t n_all, int64_t dim, int64_t label_offset,
-                                   const float* logit_scale, float* col_lse_all, float* col_nll_all,
-                                   float* loss, void* workspace, size_t workspace_bytes,
-                                   void* stream) {
-  LATTE_CHECK_ARG(col_ml_all && label_logit_all && row_nll && img_all && txt_all && logit_scale &&
+extern "C" int latte_clip_fwd_cols(const float* gathered, int64_t stride, int world,
+                                   const void* img_all, int64_t ld_img_all, const void* txt_all,
+                                   int64_t ld_txt_all, int dtype, int64_t n_loc, int64_t n_all,
+                                   int64_t dim, int64_t label_offset, const float* logit_scale,
+                                   float* row_lse_all, float* row_nll_all, float* col_lse_all,
+                                   float* col_nll_all, float* loss, void* workspace,
+                                   size_t workspace_bytes, void* stream) {
+  LATTE_CHECK_ARG(gathered && img_all && txt_all && logit_scale && row_lse_all && row_nll_all &&
                   col_lse_all && col_nll_all && loss && workspace);
-  LATTE_CHECK_ARG(world > 0 && n_loc > 0 && n_all >= n_loc && dim > 0);
+  LATTE_CHECK_ARG(world > 0 && n_loc > 0 && n_all == n_loc * world && dim > 0);
+  LATTE_CHECK_ARG(stride >= 2 * n_all + 3 * n_loc && (stride % 2) == 0);
+  LATTE_CHECK_ARG((reinterpret_cast<uintptr_t>(gathered) & 7) == 0);
   LATTE_CHECK_ARG(label_offset >= 0 && label_offset + n_loc <= n_all);
   if (!pair_shape_ok(dtype, dim) || !clip_tc_supported(dtype, dim, ld_txt_all, ld_img_all, txt_all, img_all))
     return LATTE_ERR_UNSUPPORTED;
@@ -772,10 +781,12 @@ extern "C" int latte_clip_fwd_cols(const float* col_ml_all, int world, const flo
   float* ws = static_cast<float*>(workspace);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int* flag = reinterpret_cast<int*>(ws + w.off_flag);
+  float* label_logit_all = ws + w.off_nll_r;           // [n_all] scratch of this layout
   LATTE_CUDA_OK(cudaMemsetAsync(flag, 0, sizeof(int), st));
   const int nblk_total = (int)((n_all + 127) / 128);
   col_merge_kernel<<<(unsigned)((n_all + 255) / 256), 256, 0, st>>>(
-      col_ml_all, world, n_all, label_logit_all, nblk_total, col_lse_all, col_nll_all, flag);
+      gathered, stride, world, n_loc, n_all, nblk_total, row_lse_all, row_nll_all, label_logit_all,
+      col_lse_all, col_nll_all, flag);
   LATTE_LAUNCH_OK();
   // exact fallback (every column, from the gathered features): gated on the flag
   int nparts = clip_tc_nparts(n_all, n_all, device_sm_count());
@@ -794,7 +805,8 @@ extern "C" int latte_clip_fwd_cols(const float* col_ml_all, int world, const flo
   LATTE_LAUNCH_OK();
   const unsigned rblocks = (unsigned)((n_loc + 255) / 256);
   double* lossp = reinterpret_cast<double*>(ws + w.off_lossp);
-  nll_loss_partial_kernel<<<rblocks, 256, 0, st>>>(row_nll, col_nll_all + label_offset, n_loc, lossp);
+  nll_loss_partial_kernel<<<rblocks, 256, 0, st>>>(row_nll_all + label_offset,
+                                                   col_nll_all + label_offset, n_loc, lossp);
   LATTE_LAUNCH_OK();
   loss_reduce_kernel<<<1, 256, 0, st>>>(lossp, (int)rblocks, n_loc, loss);
   LATTE_LAUNCH_OK();

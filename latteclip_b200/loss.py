@@ -148,17 +148,10 @@ class _FusedClipLoss(torch.autograd.Function):
         else:
             all_img, all_txt, label_offset = img, txt, 0
         if rank_sweep:
-            n, big_n = img.shape[0], all_img.shape[0]
-            row_lse, row_nll, label_logit, col_ml = _lib.clip_fwd_rows(img, all_txt, label_offset,
-                                                                       logit_scale)
-            payload = torch.cat([col_ml.reshape(-1), row_lse, row_nll, label_logit])
+            payload = _lib.clip_fwd_rows(img, all_txt, label_offset, logit_scale)
             gathered = _all_gather_cat(payload.reshape(1, -1), group)            # [W, 2N + 3n]
-            col_ml_all = gathered[:, :2 * big_n].reshape(world_size, big_n, 2)
-            row_lse_all = gathered[:, 2 * big_n:2 * big_n + n].reshape(-1)
-            row_nll_all = gathered[:, 2 * big_n + n:2 * big_n + 2 * n].reshape(-1)
-            label_logit_all = gathered[:, 2 * big_n + 2 * n:].reshape(-1)
-            col_lse_all, col_nll_all, loss = _lib.clip_fwd_cols(
-                col_ml_all, label_logit_all, row_nll, all_img, all_txt, n, label_offset, logit_scale)
+            row_lse_all, row_nll_all, col_lse_all, col_nll_all, loss = _lib.clip_fwd_cols(
+                gathered, all_img, all_txt, img.shape[0], label_offset, logit_scale)
             stats = (row_lse_all, col_lse_all, row_nll_all, col_nll_all)
         else:
             row_lse, col_lse, loss, row_nll, col_nll = _lib.clip_fwd(

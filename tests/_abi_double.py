@@ -24,19 +24,24 @@ def clip_fwd_rows(img_loc, txt_all, label_offset, logit_scale):
     x2 = sm * LOG2E
     m = x2.max(0).values
     col_ml = torch.stack([m, torch.exp2(x2 - m[None, :]).sum(0)], dim=1)     # [N, 2] base 2
-    return row_lse.float(), row_nll.float(), label_logit.float(), col_ml.float()
+    return torch.cat([col_ml.reshape(-1), row_lse, row_nll, label_logit]).float()
 
 
-def clip_fwd_cols(col_ml_all, label_logit_all, row_nll, img_all, txt_all, n_loc, label_offset,
-                  logit_scale):
-    ml = col_ml_all.double()                              # [W, N, 2]
+def clip_fwd_cols(gathered, img_all, txt_all, n_loc, label_offset, logit_scale):
+    world, big_n = gathered.shape[0], img_all.shape[0]
+    gd = gathered.double()
+    ml = gd[:, :2 * big_n].reshape(world, big_n, 2)
+    row_lse_all = gd[:, 2 * big_n:2 * big_n + n_loc].reshape(-1)
+    row_nll_all = gd[:, 2 * big_n + n_loc:2 * big_n + 2 * n_loc].reshape(-1)
+    label_logit_all = gd[:, 2 * big_n + 2 * n_loc:].reshape(-1)
     m = ml[:, :, 0].max(0).values
     big_l = (ml[:, :, 1] * torch.exp2(ml[:, :, 0] - m[None, :])).sum(0)
     col_lse_all = (m + torch.log2(big_l)) / LOG2E
-    col_nll_all = col_lse_all - label_logit_all.double()
+    col_nll_all = col_lse_all - label_logit_all
     own = slice(label_offset, label_offset + n_loc)
-    loss = (row_nll.double().mean() + col_nll_all[own].mean()) / 2
-    return col_lse_all.float(), col_nll_all.float(), loss.float().reshape(1)
+    loss = (row_nll_all[own].mean() + col_nll_all[own].mean()) / 2
+    return (row_lse_all.float(), row_nll_all.float(), col_lse_all.float(), col_nll_all.float(),
+            loss.float().reshape(1))
 
 
 LOG2E = 1.4426950408889634

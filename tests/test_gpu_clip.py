@@ -292,16 +292,14 @@ def test_one_sweep_per_rank_path_emulated_on_one_gpu(world, n, d, sigma):
     sc = torch.tensor(100.0, device=dev)
     one = torch.ones(1, device=dev)
     assert _lib.rank_sweep_supported(torch.bfloat16, d)
-    rows = [_lib.clip_fwd_rows(ib[r * n:(r + 1) * n], tb, r * n, sc) for r in range(world)]
-    col_ml_all = torch.stack([x[3] for x in rows])
-    row_lse_all = torch.cat([x[0] for x in rows])
-    row_nll_all = torch.cat([x[1] for x in rows])
-    label_all = torch.cat([x[2] for x in rows])
+    gathered = torch.stack([_lib.clip_fwd_rows(ib[r * n:(r + 1) * n], tb, r * n, sc)
+                            for r in range(world)])          # what the all-gather delivers
+    assert gathered.shape == (world, 2 * n * world + 3 * n)
     parts, d_imgs, d_scales = [], [], []
     for r in range(world):
         sl = slice(r * n, (r + 1) * n)
-        col_lse_all, col_nll_all, loss_r = _lib.clip_fwd_cols(col_ml_all, label_all, rows[r][1], ib, tb,
-                                                              n, r * n, sc)
+        row_lse_all, row_nll_all, col_lse_all, col_nll_all, loss_r = _lib.clip_fwd_cols(
+            gathered, ib, tb, n, r * n, sc)
         assert abs(float(loss_r) - float(lo[r])) <= LOSS_RTOL * abs(float(lo[r])) + 2e-5
         d_img, d_part, d_s = _lib.clip_bwd(ib[sl], tb[sl], ib, tb, r * n, sc, row_lse_all, col_lse_all,
                                            one, 1.0, True, grad_dtype=torch.float32,

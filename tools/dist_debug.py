@@ -52,27 +52,18 @@ print(f"W=1: dI rel {float((di.double() - g1I).norm() / g1I.norm()):.3e} dT rel 
 
 # ---- one-sweep-per-rank path, emulated: fwd_rows per rank -> merge -> bwd partials -> sum
 print("one-sweep path:")
-rows_out = [_lib.clip_fwd_rows(ib[r * n:(r + 1) * n], tb, r * n, sc) for r in range(world)]
-col_ml_all = torch.stack([x[3] for x in rows_out])                  # [W, N, 2]
-row_lse_all = torch.cat([x[0] for x in rows_out])
-row_nll_all = torch.cat([x[1] for x in rows_out])
-label_all = torch.cat([x[2] for x in rows_out])
-print("row lse err", float((row_lse_all - ref_row).abs().max()))
-parts = []
-dIs = []
-losses = []
+gathered = torch.stack([_lib.clip_fwd_rows(ib[r * n:(r + 1) * n], tb, r * n, sc) for r in range(world)])
+parts, dIs, losses = [], [], []
 for r in range(world):
     sl = slice(r * n, (r + 1) * n)
-    col_lse_all, col_nll_all, loss_r = _lib.clip_fwd_cols(col_ml_all, label_all, rows_out[r][1], ib, tb, n, r * n, sc)
+    row_lse_all, row_nll_all, col_lse_all, col_nll_all, loss_r = _lib.clip_fwd_cols(gathered, ib, tb, n, r * n, sc)
     losses.append(float(loss_r))
     di, dpart, ds = _lib.clip_bwd(ib[sl], tb[sl], ib, tb, r * n, sc, row_lse_all, col_lse_all, one, 1.0, True,
                                   grad_dtype=torch.float32, row_nll_all=row_nll_all, col_nll_all=col_nll_all,
                                   partial=True)
     parts.append(dpart)
     dIs.append(di)
-print("col lse err", float((col_lse_all - ref_col).abs().max()))
-ref_nll_r = ref_row - S.diagonal(); ref_nll_c = ref_col - S.diagonal()
-print("nll rel err", float(((row_nll_all - ref_nll_r) / ref_nll_r).abs().max()), float(((col_nll_all - ref_nll_c) / ref_nll_c).abs().max()))
+print("row lse err", float((row_lse_all - ref_row).abs().max()), "col lse err", float((col_lse_all - ref_col).abs().max()))
 dT_sum = sum(parts)
 for r in range(world):
     sl = slice(r * n, (r + 1) * n)

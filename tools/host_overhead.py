@@ -31,9 +31,4 @@ torch.cuda.synchronize()
 t2 = time.perf_counter()
 if rank == 0:
     print(f"world {world}: host enqueue {1e3*(t1-t0)/K:.3f} ms/step, total {1e3*(t2-t0)/K:.3f} ms/step")
-    import cProfile, pstats
-    pr = cProfile.Profile(); pr.enable()
-    for _ in range(20): step()
-    pr.disable(); torch.cuda.synchronize()
-    st = pstats.Stats(pr); st.sort_stats("tottime").print_stats(18)
 if world > 1: dist.destroy_process_group()
