@@ -20,7 +20,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO_DIR = os.path.join(_HERE, "_C")
 SO_PATH = os.path.join(_SO_DIR, "liblatte_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
-SOURCES = ["api.cu", "clip_tc.cu", "clip_pair.cu", "clip_simt.cu", "nxc.cu", "proto.cu"]
+SOURCES = ["api.cu", "clip_tc.cu", "clip_pair.cu", "clip_simt.cu", "nxc.cu", "nxc_tc.cu", "proto.cu"]
 
 F32, BF16, F16 = 0, 1, 2
 LABEL_AXIS = {"row": 0, "quirk": 1}

@@ -136,6 +136,15 @@ __global__ void __launch_bounds__(kT) nxc_kernel(NxcArgs a) {
 }  // namespace
 }  // namespace latte
 
+namespace latte {
+// tcgen05 path with split-bf16 operands (nxc_tc.cu); LATTE_ERR_UNSUPPORTED -> use the SIMT tiles
+int nxc_tc_run(const void* x, int64_t ldx, int x_dtype, const int64_t* row_index, int64_t n,
+               int64_t dim, const float* protos, int64_t ldp, int64_t num_classes, float scale,
+               int64_t* argmax_out, float* margin_out, float* top1_out, int k, int64_t* topk_idx,
+               float* topk_val, cudaStream_t st);
+constexpr int64_t kTcMinRows = 128;      // below this the launch of the plane split dominates
+}  // namespace latte
+
 using namespace latte;
 
 extern "C" int latte_nxc_argmax_margin(const void* x, int64_t ldx_, int x_dtype,
@@ -147,6 +156,12 @@ extern "C" int latte_nxc_argmax_margin(const void* x, int64_t ldx_, int x_dtype,
   LATTE_CHECK_ARG(x_dtype >= LATTE_F32 && x_dtype <= LATTE_F16);
   LATTE_CHECK_ARG(ldx_ >= dim && ldp >= dim);
   if (n == 0) return LATTE_OK;
+  if (n >= kTcMinRows) {
+    const int rc = nxc_tc_run(x, ldx_, x_dtype, row_index, n, dim, protos, ldp, num_classes, scale,
+                              argmax_out, margin_out, top1_out, 0, nullptr, nullptr,
+                              static_cast<cudaStream_t>(stream));
+    if (rc != LATTE_ERR_UNSUPPORTED) return rc;
+  }
   NxcArgs a{x, ldx_, x_dtype, row_index, n, dim, protos, ldp, num_classes, scale,
             argmax_out, margin_out, top1_out, 0, nullptr, nullptr};
   dim3 grid((unsigned)((n + kR - 1) / kR));
@@ -163,6 +178,12 @@ extern "C" int latte_nxc_topk(const void* x, int64_t ldx_, int x_dtype, int64_t 
   LATTE_CHECK_ARG(ldx_ >= dim && ldp >= dim);
   if (k < 1 || k > kMaxTopK || k > num_classes) return LATTE_ERR_UNSUPPORTED;
   if (n == 0) return LATTE_OK;
+  if (n >= kTcMinRows) {
+    const int rc = nxc_tc_run(x, ldx_, x_dtype, nullptr, n, dim, protos, ldp, num_classes, scale,
+                              nullptr, nullptr, nullptr, k, topk_idx, topk_val,
+                              static_cast<cudaStream_t>(stream));
+    if (rc != LATTE_ERR_UNSUPPORTED) return rc;
+  }
   NxcArgs a{x, ldx_, x_dtype, nullptr, n, dim, protos, ldp, num_classes, scale,
             nullptr, nullptr, nullptr, k, topk_idx, topk_val};
   dim3 grid((unsigned)((n + kR - 1) / kR));

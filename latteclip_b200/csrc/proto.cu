@@ -3,8 +3,8 @@
 // Replaces the ~20 elementwise launches of train.py:460-488, the per-sample Python loops
 // of train.py:415-431 (gathers) and :508-530 (bank update), and F.normalize at :388/:530.
 // All kernels: 128-bit vectorised, coalesced access where the layout allows it,
-// warp-shuffle reductions, no atomics (deterministic; per-class accumulation follows the
-// reference's sample order).
+// warp-shuffle reductions, no floating-point atomics (deterministic; per-class accumulation
+// follows the reference's sample order).
 #include "latte_common.cuh"
 
 namespace latte {
@@ -173,16 +173,24 @@ __global__ void __launch_bounds__(128) mix_ema_bwd_rows_kernel(MixBwdArgs a) {
 }
 
 // ------------------------------------------------------------------ per-class segment sums
-// One CTA per class c scans the sample indices in order; for every sample i (ascending)
-// it adds row_zs(i) if zs[i] == c and then row_ft(i) if preds[i] == c -- the order of the
-// reference loop (train.py:511-527).  Each thread owns columns tid, tid + 256, ...
-constexpr int kSegThreads = 256;
-constexpr int kSegMaxCols = 8;   // dim <= 2048
+// sums[c] = sum over the entries of class c, in the order of the reference loop
+// (train.py:511-527: for every sample i ascending, row_zs(i) into class zs[i], then row_ft(i)
+// into class preds[i]).  Entry e = 2 i + kind (kind 0 = zs list, 1 = ft list).
+// Deterministic and parallel over the batch:
+//   1. seg_hist    : per-slice class histograms of the 2B entries
+//   2. seg_scan    : exclusive scans -> slice bases, class offsets, piece offsets, counts
+//   3. seg_scatter : stable counting-sort placement -> order[] (entries grouped by class)
+//   4. seg_piece   : one CTA per piece of <= 32 entries of one class: ordered partial row sum
+//   5. seg_final   : per class, ordered sum of its pieces (+ column weights, accumulate)
+// Every feature row is read once (step 4); no atomics on floating-point data.
+constexpr int kSegSlice = 512;       // entries per slice
+constexpr int kSegPiece = 32;        // entries per piece
 
 struct SegArgs {
   const void* src_ft; const void* src_zs; int64_t ld_src; int dtype;
   const int64_t* preds; const int64_t* zs;
   int64_t batch, dim;
+  int num_classes;
   // Optional factors (class-text gradient of the mixture, train.py:476-488):
   //   row from the ft list is scaled by alpha / (w_lbl[i]    + w_img[i] + w_grp[i]) * wl
   //   row from the zs list is scaled by alpha / (w_lbl_zs[i] + w_img[i] + w_grp[i]) * wl
@@ -192,77 +200,223 @@ struct SegArgs {
   float* out; int64_t ld_out; int accumulate;
   float* counts;            // nullable
   float post_scale;
+  // scratch (one stream-ordered allocation)
+  int* hist;                // [slices, C] -> exclusive slice bases
+  int* class_off;           // [C + 1]
+  int* piece_off;           // [C + 1]
+  int* order;               // [2 B]
+  float* partial;           // [max_pieces, dim]
+  int slices, max_pieces, vec;
 };
 
-__global__ void __launch_bounds__(kSegThreads) segment_sum_kernel(SegArgs a) {
-  __shared__ unsigned mz_s[kSegThreads / 32], mp_s[kSegThreads / 32];
-  const int c = blockIdx.x;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  float acc[kSegMaxCols];
-#pragma unroll
-  for (int j = 0; j < kSegMaxCols; ++j) acc[j] = 0.f;
-  float colw[kSegMaxCols];
-  const bool quirk = a.w_lbl && a.label_axis == LATTE_LABEL_AXIS_QUIRK;
-#pragma unroll
-  for (int j = 0; j < kSegMaxCols; ++j) {
-    const int64_t d = tid + (int64_t)j * kSegThreads;
-    colw[j] = (quirk && d < a.dim) ? a.w_lbl[d] : 1.f;
+__device__ __forceinline__ int seg_class_of(const SegArgs& a, int64_t e) {
+  const int64_t i = e >> 1;
+  const int64_t c = (e & 1) ? a.preds[i] : a.zs[i];
+  return (c >= 0 && c < a.num_classes) ? (int)c : -1;     // out-of-range ids are dropped
+}
+
+__global__ void __launch_bounds__(256) seg_hist_kernel(SegArgs a) {
+  extern __shared__ int sh[];
+  for (int c = threadIdx.x; c < a.num_classes; c += 256) sh[c] = 0;
+  __syncthreads();
+  const int64_t e0 = (int64_t)blockIdx.x * kSegSlice;
+  for (int k = threadIdx.x; k < kSegSlice; k += 256) {
+    const int64_t e = e0 + k;
+    if (e < 2 * a.batch) {
+      const int c = seg_class_of(a, e);
+      if (c >= 0) atomicAdd(&sh[c], 1);
+    }
   }
-  int count = 0;
-  for (int64_t base = 0; base < a.batch; base += kSegThreads) {
-    const int64_t i = base + tid;
-    const bool mz = i < a.batch && a.zs[i] == c;
-    const bool mp = i < a.batch && a.preds[i] == c;
-    const unsigned bz = __ballot_sync(0xffffffffu, mz);
-    const unsigned bp = __ballot_sync(0xffffffffu, mp);
-    __syncthreads();           // previous chunk fully consumed
-    if (lane == 0) { mz_s[warp] = bz; mp_s[warp] = bp; }
-    __syncthreads();
-    for (int w = 0; w < kSegThreads / 32; ++w) {
-      const unsigned z = mz_s[w], pm = mp_s[w];
-      unsigned any = z | pm;
-      count += __popc(z) + __popc(pm);
-      while (any) {
-        const int b = __ffs(any) - 1;
-        any &= any - 1;
-        const int64_t ii = base + w * 32 + b;
-        if (z & (1u << b)) {
-          float sc = 1.f;
-          if (a.w_lbl) {
-            sc = a.alpha / (a.w_lbl_zs[ii] + a.w_img[ii] + a.w_grp[ii]);
-            if (!quirk) sc *= a.w_lbl[ii];
-          }
+  __syncthreads();
+  for (int c = threadIdx.x; c < a.num_classes; c += 256)
+    a.hist[(int64_t)blockIdx.x * a.num_classes + c] = sh[c];
+}
+
+__global__ void __launch_bounds__(1024) seg_scan_kernel(SegArgs a) {
+  // one warp per class: exclusive scan over the slices (in place), 32 slices per step
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int c = warp; c < a.num_classes; c += 32) {
+    int carry = 0;
+    for (int s0 = 0; s0 < a.slices; s0 += 32) {
+      const int s = s0 + lane;
+      const int64_t idx = (int64_t)s * a.num_classes + c;
+      const int v = s < a.slices ? a.hist[idx] : 0;
+      int inc = v;
 #pragma unroll
-          for (int j = 0; j < kSegMaxCols; ++j) {
-            const int64_t d = tid + (int64_t)j * kSegThreads;
-            if (d < a.dim) acc[j] += ld1(a.src_zs, ii * a.ld_src + d, a.dtype) * sc * colw[j];
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+      }
+      if (s < a.slices) a.hist[idx] = carry + inc - v;
+      carry += __shfl_sync(0xffffffffu, inc, 31);
+    }
+    if (lane == 0) a.class_off[c + 1] = carry;          // class totals for now
+  }
+  __syncthreads();
+  // exclusive scans over the classes (entries and pieces): warp 0, 32 classes per step
+  if (warp == 0) {
+    int eo = 0, po = 0;
+    for (int c0 = 0; c0 < a.num_classes; c0 += 32) {
+      const int c = c0 + lane;
+      const int n = c < a.num_classes ? a.class_off[c + 1] : 0;
+      const int pc = (n + kSegPiece - 1) / kSegPiece;
+      int ie = n, ip = pc;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int te = __shfl_up_sync(0xffffffffu, ie, o);
+        const int tp = __shfl_up_sync(0xffffffffu, ip, o);
+        if (lane >= o) { ie += te; ip += tp; }
+      }
+      __syncwarp();
+      if (c < a.num_classes) {
+        if (a.counts) a.counts[c] = (float)n;
+        a.class_off[c + 1] = eo + ie;
+        a.piece_off[c + 1] = po + ip;
+      }
+      eo += __shfl_sync(0xffffffffu, ie, 31);
+      po += __shfl_sync(0xffffffffu, ip, 31);
+    }
+    if (lane == 0) { a.class_off[0] = 0; a.piece_off[0] = 0; }
+  }
+}
+
+__global__ void __launch_bounds__(256) seg_scatter_kernel(SegArgs a) {
+  __shared__ int cls[kSegSlice];
+  const int64_t e0 = (int64_t)blockIdx.x * kSegSlice;
+  for (int k = threadIdx.x; k < kSegSlice; k += 256) {
+    const int64_t e = e0 + k;
+    cls[k] = e < 2 * a.batch ? seg_class_of(a, e) : -1;
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < kSegSlice; k += 256) {
+    const int c = cls[k];
+    if (c < 0) continue;
+    int rank = 0;                       // earlier entries of this slice with the same class
+    for (int j = 0; j < k; ++j) rank += (cls[j] == c);
+    const int pos = a.class_off[c] + a.hist[(int64_t)blockIdx.x * a.num_classes + c] + rank;
+    a.order[pos] = (int)(e0 + k);
+  }
+}
+
+__device__ __forceinline__ float seg_row_scale(const SegArgs& a, int64_t i, int kind, bool quirk) {
+  if (!a.w_lbl) return 1.f;
+  float sc = a.alpha / ((kind ? a.w_lbl[i] : a.w_lbl_zs[i]) + a.w_img[i] + a.w_grp[i]);
+  if (!quirk) sc *= a.w_lbl[i];
+  return sc;
+}
+
+__global__ void __launch_bounds__(128) seg_piece_kernel(SegArgs a) {
+  const int b = blockIdx.x;
+  if (b >= a.piece_off[a.num_classes]) return;
+  int lo = 0, hi = a.num_classes;       // class c with piece_off[c] <= b < piece_off[c + 1]
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (a.piece_off[mid] <= b) lo = mid; else hi = mid;
+  }
+  const int c = lo;
+  const int first = a.class_off[c] + (b - a.piece_off[c]) * kSegPiece;
+  const int last = min(first + kSegPiece, a.class_off[c + 1]);
+  const bool quirk = a.w_lbl && a.label_axis == LATTE_LABEL_AXIS_QUIRK;
+  float* dst = a.partial + (int64_t)b * a.dim;
+  if (a.vec) {
+    for (int64_t d = (int64_t)threadIdx.x * 4; d < a.dim; d += 512) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int k0 = first; k0 < last; k0 += 4) {
+        float4 v[4];
+        float sc[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int k = k0 + u;
+          if (k < last) {
+            const int e = a.order[k];
+            const int64_t i = e >> 1;
+            const int kind = e & 1;
+            v[u] = ld4(kind ? a.src_ft : a.src_zs, i * a.ld_src + d, a.dtype);
+            sc[u] = seg_row_scale(a, i, kind, quirk);
+          } else {
+            v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            sc[u] = 0.f;
           }
         }
-        if (pm & (1u << b)) {
-          float sc = 1.f;
-          if (a.w_lbl) {
-            sc = a.alpha / (a.w_lbl[ii] + a.w_img[ii] + a.w_grp[ii]);
-            if (!quirk) sc *= a.w_lbl[ii];
-          }
 #pragma unroll
-          for (int j = 0; j < kSegMaxCols; ++j) {
-            const int64_t d = tid + (int64_t)j * kSegThreads;
-            if (d < a.dim) acc[j] += ld1(a.src_ft, ii * a.ld_src + d, a.dtype) * sc * colw[j];
-          }
+        for (int u = 0; u < 4; ++u) {
+          acc.x = fmaf(v[u].x, sc[u], acc.x); acc.y = fmaf(v[u].y, sc[u], acc.y);
+          acc.z = fmaf(v[u].z, sc[u], acc.z); acc.w = fmaf(v[u].w, sc[u], acc.w);
         }
       }
+      *reinterpret_cast<float4*>(dst + d) = acc;
+    }
+  } else {
+    for (int64_t d = threadIdx.x; d < a.dim; d += 128) {
+      float acc = 0.f;
+      for (int k = first; k < last; ++k) {
+        const int e = a.order[k];
+        const int64_t i = e >> 1;
+        const int kind = e & 1;
+        acc = fmaf(ld1(kind ? a.src_ft : a.src_zs, i * a.ld_src + d, a.dtype),
+                   seg_row_scale(a, i, kind, quirk), acc);
+      }
+      dst[d] = acc;
     }
   }
-#pragma unroll
-  for (int j = 0; j < kSegMaxCols; ++j) {
-    const int64_t d = tid + (int64_t)j * kSegThreads;
-    if (d < a.dim) {
-      float* o = a.out + (int64_t)c * a.ld_out + d;
-      const float v = acc[j] * a.post_scale;
-      *o = a.accumulate ? *o + v : v;
+}
+
+__global__ void __launch_bounds__(128) seg_final_kernel(SegArgs a) {
+  const int c = blockIdx.x;
+  const int p0 = a.piece_off[c], p1 = a.piece_off[c + 1];
+  const bool quirk = a.w_lbl && a.label_axis == LATTE_LABEL_AXIS_QUIRK;
+  for (int64_t d = threadIdx.x; d < a.dim; d += 128) {
+    float acc = 0.f;
+    for (int pb = p0; pb < p1; ++pb) acc += a.partial[(int64_t)pb * a.dim + d];
+    if (quirk) acc *= a.w_lbl[d];
+    acc *= a.post_scale;
+    float* o = a.out + (int64_t)c * a.ld_out + d;
+    *o = a.accumulate ? *o + acc : acc;
+  }
+}
+
+inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+// Runs the five steps on `stream`; scratch comes from the stream-ordered allocator.
+int segment_sums(SegArgs a, cudaStream_t st) {
+  const int64_t entries = 2 * a.batch;
+  a.slices = (int)((entries + kSegSlice - 1) / kSegSlice);
+  if (a.slices < 1) a.slices = 1;
+  a.max_pieces = (int)((entries + kSegPiece - 1) / kSegPiece) + a.num_classes;
+  const size_t n_hist = (size_t)a.slices * a.num_classes;
+  const size_t n_int = n_hist + 2 * ((size_t)a.num_classes + 1) + (size_t)entries + 8;
+  const size_t int_bytes = (n_int * sizeof(int) + 255) / 256 * 256;
+  const size_t part_bytes = (size_t)a.max_pieces * (size_t)a.dim * sizeof(float);
+  // keep freed scratch in the stream-ordered pool instead of returning it at every sync
+  {
+    int dev = 0;
+    cudaMemPool_t pool;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+      uint64_t keep = 1ull << 30;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
     }
   }
-  if (a.counts && tid == 0) a.counts[c] = (float)count;
+  char* buf = nullptr;
+  LATTE_CUDA_OK(cudaMallocAsync(&buf, int_bytes + part_bytes, st));
+  int* ip = reinterpret_cast<int*>(buf);
+  a.hist = ip; ip += n_hist;
+  a.class_off = ip; ip += a.num_classes + 1;
+  a.piece_off = ip; ip += a.num_classes + 1;
+  a.order = ip;
+  a.partial = reinterpret_cast<float*>(buf + int_bytes);
+  const int64_t esz = (int64_t)dtype_size(a.dtype);
+  a.vec = (a.dim % 4 == 0) && (a.ld_src % 4 == 0) &&
+          (reinterpret_cast<uintptr_t>(a.src_ft) % (4 * esz) == 0) &&
+          (reinterpret_cast<uintptr_t>(a.src_zs) % (4 * esz) == 0);
+  int rc = LATTE_OK;
+  seg_hist_kernel<<<a.slices, 256, (size_t)a.num_classes * sizeof(int), st>>>(a);
+  seg_scan_kernel<<<1, 1024, 0, st>>>(a);
+  seg_scatter_kernel<<<a.slices, 256, 0, st>>>(a);
+  seg_piece_kernel<<<a.max_pieces, 128, 0, st>>>(a);
+  seg_final_kernel<<<a.num_classes, 128, 0, st>>>(a);
+  if (cudaGetLastError() != cudaSuccess) rc = LATTE_ERR_CUDA;
+  cudaFreeAsync(buf, st);
+  return rc;
 }
 
 // ------------------------------------------------------------------ bank finalize
@@ -283,8 +437,6 @@ bank_finalize_kernel(const float* sums, int64_t ld_sums, const float* counts, fl
   const float denom = fmaxf(sqrtf(tot), 1e-12f);  // F.normalize eps, train.py:530
   for (int64_t d = threadIdx.x; d < dim; d += blockDim.x) bank[c * ld_bank + d] = (s[d] / cnt) / denom;
 }
-
-inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 }  // namespace
 }  // namespace latte
@@ -344,7 +496,7 @@ extern "C" int latte_mix_ema_bwd(const void* d_t_ft, const void* d_t_zs, int64_t
   LATTE_CHECK_ARG(batch >= 0 && dim > 0 && num_classes > 0);
   LATTE_CHECK_ARG(dtype >= LATTE_F32 && dtype <= LATTE_F16);
   if (label_axis == LATTE_LABEL_AXIS_QUIRK && batch != dim) return LATTE_ERR_UNSUPPORTED;
-  if (dim > (int64_t)kSegThreads * kSegMaxCols) return LATTE_ERR_UNSUPPORTED;
+  if (num_classes > 12000) return LATTE_ERR_UNSUPPORTED;     // class histogram lives in smem
   if (batch == 0) return LATTE_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (d_per_image && d_per_group) {
@@ -355,19 +507,25 @@ extern "C" int latte_mix_ema_bwd(const void* d_t_ft, const void* d_t_zs, int64_t
   }
   if (d_class_text) {
     // d_class_text[c] += sum_{zs_i=c} wl * alpha/totz_i * dT_zs[i] + sum_{preds_i=c} wl * alpha/tot_i * dT_ft[i]
-    SegArgs s{d_t_ft, d_t_zs, ld_dt, dtype, preds, zs, batch, dim,
-              w_lbl, w_lbl_zs, w_img, w_grp, alpha, label_axis,
-              d_class_text, ld_dct, 1, nullptr, 1.f};
-    segment_sum_kernel<<<(unsigned)num_classes, kSegThreads, 0, st>>>(s);
-    LATTE_LAUNCH_OK();
+    SegArgs s{};
+    s.src_ft = d_t_ft; s.src_zs = d_t_zs; s.ld_src = ld_dt; s.dtype = dtype;
+    s.preds = preds; s.zs = zs; s.batch = batch; s.dim = dim; s.num_classes = (int)num_classes;
+    s.w_lbl = w_lbl; s.w_lbl_zs = w_lbl_zs; s.w_img = w_img; s.w_grp = w_grp;
+    s.alpha = alpha; s.label_axis = label_axis;
+    s.out = d_class_text; s.ld_out = ld_dct; s.accumulate = 1; s.counts = nullptr; s.post_scale = 1.f;
+    const int rc = segment_sums(s, st);
+    if (rc) return rc;
   }
   if (d_bank) {
     // (1 - alpha) * d_t scattered by class (train.py:487-488 wrt membank_features)
-    SegArgs s{d_t_ft, d_t_zs, ld_dt, dtype, preds, zs, batch, dim,
-              nullptr, nullptr, nullptr, nullptr, 0.f, LATTE_LABEL_AXIS_ROW,
-              d_bank, ld_dbank, 1, nullptr, 1.f - alpha};
-    segment_sum_kernel<<<(unsigned)num_classes, kSegThreads, 0, st>>>(s);
-    LATTE_LAUNCH_OK();
+    SegArgs s{};
+    s.src_ft = d_t_ft; s.src_zs = d_t_zs; s.ld_src = ld_dt; s.dtype = dtype;
+    s.preds = preds; s.zs = zs; s.batch = batch; s.dim = dim; s.num_classes = (int)num_classes;
+    s.label_axis = LATTE_LABEL_AXIS_ROW;
+    s.out = d_bank; s.ld_out = ld_dbank; s.accumulate = 1; s.counts = nullptr;
+    s.post_scale = 1.f - alpha;
+    const int rc = segment_sums(s, st);
+    if (rc) return rc;
   }
   return LATTE_OK;
 }
@@ -379,13 +537,13 @@ extern "C" int latte_bank_accumulate(const void* t_ft, const void* t_zs, int64_t
   LATTE_CHECK_ARG(t_ft && t_zs && preds && zs && sums && counts);
   LATTE_CHECK_ARG(batch >= 0 && dim > 0 && num_classes > 0 && ld_t >= dim && ld_sums >= dim);
   LATTE_CHECK_ARG(dtype >= LATTE_F32 && dtype <= LATTE_F16);
-  if (dim > (int64_t)kSegThreads * kSegMaxCols) return LATTE_ERR_UNSUPPORTED;
-  SegArgs s{t_ft, t_zs, ld_t, dtype, preds, zs, batch, dim,
-            nullptr, nullptr, nullptr, nullptr, 0.f, LATTE_LABEL_AXIS_ROW,
-            sums, ld_sums, 0, counts, 1.f};
-  segment_sum_kernel<<<(unsigned)num_classes, kSegThreads, 0, static_cast<cudaStream_t>(stream)>>>(s);
-  LATTE_LAUNCH_OK();
-  return LATTE_OK;
+  if (num_classes > 12000) return LATTE_ERR_UNSUPPORTED;       // class histogram lives in smem
+  SegArgs s{};
+  s.src_ft = t_ft; s.src_zs = t_zs; s.ld_src = ld_t; s.dtype = dtype;
+  s.preds = preds; s.zs = zs; s.batch = batch; s.dim = dim; s.num_classes = (int)num_classes;
+  s.label_axis = LATTE_LABEL_AXIS_ROW;
+  s.out = sums; s.ld_out = ld_sums; s.accumulate = 0; s.counts = counts; s.post_scale = 1.f;
+  return segment_sums(s, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int latte_bank_finalize(const float* sums, int64_t ld_sums, const float* counts,
