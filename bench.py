@@ -152,6 +152,60 @@ def cpu_reference_sample(steps, warmup, target_s=6.0):
                        f"D={DIM} fp32 problem, {steps} steps, {dt * 1e3:.1f} ms/step"), dt
 
 
+def prototype_kernel_rates(dev, peaks, batch=N_GLOBAL, dim=DIM, classes=47):
+    """Achieved HBM GB/s of the prototype-path kernels at the headline batch (fp32 features,
+    47 DTD classes), CUDA events over rotating inputs larger than L2.  Algorithmic bytes per
+    launch as in SURVEY 8d."""
+    from latteclip_b200 import _lib
+    g = torch.Generator().manual_seed(4321)
+    sets = 6
+    bank = F.normalize(torch.randn(classes, dim, generator=g), dim=1).to(dev)
+    cls = F.normalize(torch.randn(classes, dim, generator=g), dim=1).to(dev)
+    xs = [F.normalize(torch.randn(batch, dim, generator=g), dim=1).to(dev) for _ in range(sets)]
+    ps = [F.normalize(torch.randn(batch, dim, generator=g), dim=1).to(dev) for _ in range(sets)]
+    preds = torch.randint(0, classes, (batch,), generator=g).to(dev)
+    zs = torch.randint(0, classes, (batch,), generator=g).to(dev)
+    w = [torch.rand(batch, generator=g).to(dev) + 0.1 for _ in range(4)]
+
+    def timeit(fn, reps=10):
+        for k in range(3):
+            fn(k)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for k in range(reps):
+            fn(k)
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+
+    fb = 4
+    rows = [
+        ("nxc_tc_kernel (pseudo-label argmax, train.py:410-411)",
+         batch * dim * fb + classes * dim * 4 + batch * 8,
+         lambda k: _lib.nxc_argmax_margin(xs[k % sets], bank, scale=100.0, want_argmax=True, want_margin=False)),
+        ("nxc_tc_kernel (top-2 margin, train.py:292-303)",
+         batch * dim * fb + classes * dim * 4 + batch * 4,
+         lambda k: _lib.nxc_argmax_margin(xs[k % sets], bank, scale=1.0, want_argmax=False, want_margin=True)),
+        ("mix_ema_fwd_kernel (train.py:472-488)",
+         8 * batch * dim * fb + 6 * batch * 4 + 2 * batch * 8,
+         lambda k: _lib.mix_ema_fwd(cls, xs[k % sets], ps[k % sets], bank, preds, zs, w[0], w[1], w[2], w[3], 0.01, "row")),
+        ("mix_ema_bwd (rows kernel + per-class segment sums)",
+         4 * batch * dim * fb + classes * dim * 4 + 6 * batch * 4,
+         lambda k: _lib.mix_ema_bwd(xs[k % sets], ps[k % sets], preds, zs, w[0], w[1], w[2], w[3], 0.01, "row", classes)),
+        ("bank_accumulate (per-class segment sums, train.py:508-526)",
+         2 * batch * dim * fb + 2 * batch * 8 + classes * dim * 4,
+         lambda k: _lib.bank_accumulate(xs[k % sets], ps[k % sets], preds, zs, classes)),
+    ]
+    out = []
+    for name, nbytes, fn in rows:
+        ms = timeit(fn)
+        gbs = nbytes / (ms * 1e-3) / 1e9
+        out.append({"kernel": name, "ms": ms, "alg_bytes": nbytes, "achieved_gbs": gbs,
+                    "frac_of_measured_hbm": gbs / peaks["hbm"]})
+    return {"batch": batch, "dim": dim, "classes": classes, "dtype": "f32", "rows": out}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -369,6 +423,11 @@ def _run_ours(args):
         "executed_flop_per_step": 8.0 * n_loc * N_GLOBAL * DIM,
     }
 
+    # ---- prototype / pseudo-label kernels (HBM-bound rows of SURVEY 8a): achieved GB/s ------
+    proto = None
+    if rank == 0 and world == 1:
+        proto = prototype_kernel_rates(dev, peaks)
+
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu_base, _ = cpu_reference_sample(2, 1, target_s=12.0)
@@ -396,6 +455,8 @@ def _run_ours(args):
         }
         if cpu_base is not None:
             line["cpu_baseline"] = cpu_base
+        if proto is not None:
+            line["prototype_kernels"] = proto
     else:
         line = None
     if world > 1:
