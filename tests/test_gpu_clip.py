@@ -335,3 +335,52 @@ def test_flushed_column_triggers_exact_fallback():
     lab = torch.arange(n, device=dev)
     ref = 0.5 * (F.cross_entropy(S, lab) + F.cross_entropy(S.T, lab))
     assert abs(float(loss) - float(ref)) <= 1e-5 * abs(float(ref)) + 2e-5
+
+
+# ------------------------------------------------------------------ full-size properties
+@pytest.mark.parametrize("n,d", [(32768, 512)])
+def test_full_size_properties_32k(n, d):
+    """BASELINE cfg3 size on one GPU, checked through size-independent properties (no oracle):
+      * role swap: col_lse(I, T) == row_lse(T, I) -- the column sums built from the shared logit
+        tiles against the row sums of the transposed problem;
+      * Euler identities of the bilinear logits: sum_i <dI_i, I_i> = sum_j <dT_j, T_j> = s * dL/ds;
+      * sample permutation: the loss is invariant and the gradients permute with the samples."""
+    from latteclip_b200 import _lib
+    dev = torch.device("cuda:0")
+    i, t = synth(n, d, 4.0, 99)
+    ib, tb = i.to(dev).bfloat16(), t.to(dev).bfloat16()
+    sc = torch.tensor(100.0, device=dev)
+    one = torch.ones(1, device=dev)
+    row, col, loss, rn, cn = _lib.clip_fwd(ib, tb, ib, tb, 0, sc, with_nll=True)
+    row_t, col_t, loss_t = _lib.clip_fwd(tb, ib, tb, ib, 0, sc)
+    assert torch.allclose(col, row_t, rtol=0, atol=2e-4) and torch.allclose(row, col_t, rtol=0, atol=2e-4)
+    assert abs(float(loss) - float(loss_t)) <= 1e-5 * abs(float(loss))
+    assert abs(float(loss) - 0.5 * float((rn + cn).double().mean())) <= 1e-5 * abs(float(loss))
+    assert float(loss) > 0 and bool((rn > -1e-6).all()) and bool((cn > -1e-6).all())
+    di, dt, ds = _lib.clip_bwd(ib, tb, ib, tb, 0, sc, row, col, one, 1.0, True, grad_dtype=torch.float32,
+                               row_nll_all=rn, col_nll_all=cn)
+    eul_i = float((di.double() * ib.double()).sum())
+    eul_t = float((dt.double() * tb.double()).sum())
+    sds = 100.0 * float(ds)
+    assert abs(eul_i - sds) <= 2e-3 * abs(sds) and abs(eul_t - sds) <= 2e-3 * abs(sds)
+    # every row of G sums to (row softmax mass 1 - 1) + (column part): the gradient of the
+    # loss w.r.t. a common shift of all logits is zero => sum_ij G_ij = 0 => sum_i dI_i . tbar = ...
+    perm = torch.randperm(n, generator=torch.Generator().manual_seed(5)).to(dev)
+    ip, tp = ib[perm].contiguous(), tb[perm].contiguous()
+    row_p, col_p, loss_p = _lib.clip_fwd(ip, tp, ip, tp, 0, sc)
+    assert abs(float(loss_p) - float(loss)) <= 1e-5 * abs(float(loss))
+    assert torch.allclose(row_p, row[perm], rtol=0, atol=2e-4)
+    dip, dtp, dsp = _lib.clip_bwd(ip, tp, ip, tp, 0, sc, row_p, col_p, one, 1.0, True,
+                                  grad_dtype=torch.float32)
+    assert rel(dip, di[perm]) < 1e-3 and rel(dtp, dt[perm]) < 1e-3
+    assert abs(float(dsp) - float(ds)) <= 2e-3 * abs(float(ds))
+    # spot check of 64 random rows against fp64 on the same rounded inputs
+    rows = torch.randint(0, n, (64,), generator=torch.Generator().manual_seed(6)).to(dev)
+    S_r = 100.0 * ib[rows].double() @ tb.double().T
+    S_c = 100.0 * tb[rows].double() @ ib.double().T
+    assert torch.allclose(row[rows].double(), torch.logsumexp(S_r, 1), rtol=0, atol=2e-4)
+    assert torch.allclose(col[rows].double(), torch.logsumexp(S_c, 1), rtol=0, atol=2e-4)
+    G_r = torch.exp(S_r - row[rows].double()[:, None]) + torch.exp(S_r - col.double()[None, :])
+    G_r[torch.arange(64), rows] -= 2.0
+    ref_di = (100.0 / (2 * n)) * G_r @ tb.double()
+    assert rel(di[rows], ref_di) < GRAD_RTOL_16
