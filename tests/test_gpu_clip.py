@@ -384,3 +384,34 @@ def test_full_size_properties_32k(n, d):
     G_r[torch.arange(64), rows] -= 2.0
     ref_di = (100.0 / (2 * n)) * G_r @ tb.double()
     assert rel(di[rows], ref_di) < GRAD_RTOL_16
+
+
+@pytest.mark.parametrize("n,d", [(1, 8), (7, 24), (129, 40), (513, 72), (300, 504), (1000, 512), (257, 16)])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_cta_pair_path_odd_shapes(n, d, dtype):
+    """Edge shapes of the CTA-pair kernels (dim <= 512): a single row, ragged row blocks and
+    column tiles, feature counts that are not a multiple of the 64-wide chunks."""
+    from latteclip_b200 import _lib
+    dev = torch.device("cuda:0")
+    i, t = synth(n, d, 2.0, n + d)
+    ib, tb = i.to(dev).to(dtype), t.to(dev).to(dtype)
+    for scale in (100.0, 1.0 / 0.07):
+        sc = torch.tensor(scale, device=dev)
+        row, col, loss, rn, cn = _lib.clip_fwd(ib, tb, ib, tb, 0, sc, with_nll=True)
+        I = ib.double().requires_grad_(True)
+        T = tb.double().requires_grad_(True)
+        S = scale * I @ T.T
+        lab = torch.arange(n, device=dev)
+        ref = 0.5 * (F.cross_entropy(S, lab) + F.cross_entropy(S.T, lab))
+        gi, gt = torch.autograd.grad(ref, (I, T))
+        assert torch.allclose(row.double(), torch.logsumexp(S, 1).detach(), rtol=0, atol=2e-4)
+        assert torch.allclose(col.double(), torch.logsumexp(S.T, 1).detach(), rtol=0, atol=2e-4)
+        assert abs(float(loss) - float(ref)) <= LOSS_RTOL * abs(float(ref)) + 2e-5
+        di, dt, ds = _lib.clip_bwd(ib, tb, ib, tb, 0, sc, row, col, torch.ones(1, device=dev), 1.0, True,
+                                   grad_dtype=torch.float32, row_nll_all=rn, col_nll_all=cn)
+        if float(gi.norm()) > 1e-6 * scale:
+            assert rel(di, gi) < GRAD_RTOL_16 and rel(dt, gt) < GRAD_RTOL_16
+        else:
+            # n = 1 (gradient exactly zero) or a fully converged batch (loss ~ 1e-15): only
+            # rounding of exp(0) is left, far below any gradient that matters
+            assert float(di.abs().max()) < 1e-6 * scale and float(dt.abs().max()) < 1e-6 * scale
