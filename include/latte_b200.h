@@ -164,6 +164,16 @@ int latte_clip_bwd(const void* img_loc, int64_t ld_img_loc,
                    float grad_mult, int cross_terms,
                    void* d_img, void* d_txt, int grad_dtype, int64_t ld_grad,
                    float* d_txt_partial,         /* nullable, see above                   */
+                   void* const* d_txt_peers,     /* nullable HOST array of n_peers device pointers:
+                                                    rank w's fp32 text-gradient accumulator
+                                                    [n_loc, dim], peer-mapped into this process.
+                                                    Fused reduce-scatter: instead of d_txt_partial,
+                                                    every row of G^T @ img_loc is added straight
+                                                    into its owner's accumulator over NVLink
+                                                    (red.global.add from the GEMM epilogue).  The
+                                                    caller zeroes its accumulator and runs a
+                                                    cross-rank barrier before and after the call */
+                   int n_peers,
                    float* d_scale,               /* device scalar out (d loss / d s)      */
                    void* workspace, size_t workspace_bytes, void* stream);
 

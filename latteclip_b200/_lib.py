@@ -72,8 +72,8 @@ def _declare(lib):
     lib.latte_clip_fwd_cols.argtypes = [vp, i64, i32, vp, i64, vp, i64, i32, i64, i64, i64, i64,
                                         vp, vp, vp, vp, vp, vp, vp, sz, vp]
     lib.latte_clip_bwd.argtypes = [vp, i64, vp, i64, vp, i64, vp, i64, i32, i64, i64, i64, i64,
-                                   vp, vp, vp, vp, vp, vp, f32, i32, vp, vp, i32, i64, vp, vp, vp,
-                                   sz, vp]
+                                   vp, vp, vp, vp, vp, vp, f32, i32, vp, vp, i32, i64, vp, vp, i32, vp,
+                                   vp, sz, vp]
     lib.latte_clip_stage_times.argtypes = [vp, i64, vp, i64, vp, i64, vp, i64, i32, i64, i64, i64, i64,
                                            vp, vp, vp, vp, vp, vp, vp, f32, i32, vp, vp, i32, i64,
                                            vp, vp, vp, sz, vp, sz, vp, i32, c.POINTER(f32)]
@@ -304,11 +304,15 @@ def clip_fwd_cols(gathered, img_all, txt_all, n_loc: int, label_offset: int, log
 
 def clip_bwd(img_loc, txt_loc, img_all, txt_all, label_offset: int, logit_scale,
              row_lse_all, col_lse_all, grad_loss, grad_mult: float, cross_terms: bool,
-             grad_dtype=None, row_nll_all=None, col_nll_all=None, partial: bool = False):
+             grad_dtype=None, row_nll_all=None, col_nll_all=None, partial: bool = False,
+             peer_ptrs=None):
     """-> (d_img[n_loc, dim], d_txt[n_loc, dim], d_scale[1] fp32).  The feature gradients
     come back in ``grad_dtype`` (default: the feature dtype, what autograd needs).
     ``partial=True`` (one-sweep multi-rank mode): the second result is instead the fp32
-    partial [n_all, dim] of the text gradient over ALL columns, to be reduce-scattered."""
+    partial [n_all, dim] of the text gradient over ALL columns, to be reduce-scattered.
+    ``peer_ptrs`` (one-sweep mode, fused reduce-scatter): device pointers of every rank's
+    peer-mapped fp32 accumulator [n_loc, dim]; the text gradient is added straight into them
+    and the second result is None."""
     lib = load()
     img_loc, txt_loc = _rows(img_loc, "image_features"), _rows(txt_loc, "text_features")
     img_all, txt_all = _rows(img_all, "all_image_features"), _rows(txt_all, "all_text_features")
@@ -331,8 +335,10 @@ def clip_bwd(img_loc, txt_loc, img_all, txt_all, label_offset: int, logit_scale,
         if row_nll_all.numel() != n_all or col_nll_all.numel() != n_all:
             raise RuntimeError("clip_bwd: nll vectors must have n_all entries")
     d_img = torch.empty(n_loc, dim, dtype=gdt, device=dev)
-    d_txt = None if partial else torch.empty(n_loc, dim, dtype=gdt, device=dev)
+    fused = peer_ptrs is not None
+    d_txt = None if (partial or fused) else torch.empty(n_loc, dim, dtype=gdt, device=dev)
     d_part = torch.empty(n_all, dim, dtype=torch.float32, device=dev) if partial else None
+    peers = (ctypes.c_void_p * len(peer_ptrs))(*peer_ptrs) if fused else None
     d_scale = torch.empty(1, dtype=torch.float32, device=dev)
     ws = _cached_workspace(("bwd", n_loc, n_all, dim, dt),
                            lambda: _workspace(n_loc, n_all, dim, dt, dev, bwd=True).numel(), dev)
@@ -344,6 +350,7 @@ def clip_bwd(img_loc, txt_loc, img_all, txt_all, label_offset: int, logit_scale,
                                   _ptr(col_lse_all), _ptr(row_nll_all), _ptr(col_nll_all), _ptr(g),
                                   float(grad_mult), int(bool(cross_terms)),
                                   _ptr(d_img), _ptr(d_txt), _DTYPES[gdt], dim, _ptr(d_part),
+                                  peers, len(peer_ptrs) if fused else 0,
                                   _ptr(d_scale), wp, wn, _stream(img_loc)),
                "latte_clip_bwd")
     return d_img, (d_part if partial else d_txt), d_scale

@@ -821,10 +821,14 @@ static int clip_bwd_impl(const void* img_loc, int64_t ld_img_loc, const void* tx
                          const float* col_lse_all, const float* row_nll_all,
                          const float* col_nll_all, const float* grad_loss, float grad_mult,
                          int cross_terms, void* d_img, void* d_txt, int grad_dtype,
-                         int64_t ld_grad, float* d_txt_partial, float* d_scale, void* workspace,
+                         int64_t ld_grad, float* d_txt_partial, void* const* d_txt_peers,
+                         int n_peers, float* d_scale, void* workspace,
                          size_t workspace_bytes, void* stream, StageTimer* tm) {
   LATTE_CHECK_ARG(img_loc && txt_loc && img_all && txt_all && logit_scale && row_lse_all &&
-                  col_lse_all && grad_loss && d_img && (d_txt || d_txt_partial) && d_scale && workspace);
+                  col_lse_all && grad_loss && d_img && (d_txt || d_txt_partial || d_txt_peers) &&
+                  d_scale && workspace);
+  LATTE_CHECK_ARG(!(d_txt_partial && d_txt_peers));
+  LATTE_CHECK_ARG(!d_txt_peers || (n_peers > 1 && n_peers <= 8 && n_all == n_loc * n_peers));
   LATTE_CHECK_ARG((row_nll_all == nullptr) == (col_nll_all == nullptr));
   LATTE_CHECK_ARG(n_loc > 0 && n_all >= n_loc && dim > 0);
   LATTE_CHECK_ARG(label_offset >= 0 && label_offset + n_loc <= n_all);
@@ -923,12 +927,14 @@ static int clip_bwd_impl(const void* img_loc, int64_t ld_img_loc, const void* tx
     const bool single = n_loc == n_all && img_loc == img_all && txt_loc == txt_all && cross_terms;
     // one sweep per rank: the text-side product G^T . img_loc is returned as an fp32 partial
     // over ALL columns for the caller to reduce-scatter (loss.py:49-50's backward)
-    const bool rank_sweep = !single && d_txt_partial != nullptr && cross_terms;
-    if (d_txt_partial && !rank_sweep) return LATTE_ERR_BAD_ARG;
+    const bool rank_sweep = !single && (d_txt_partial != nullptr || d_txt_peers != nullptr) && cross_terms;
+    if ((d_txt_partial || d_txt_peers) && !rank_sweep) return LATTE_ERR_BAD_ARG;
     if (!rank_sweep && !d_txt) return LATTE_ERR_BAD_ARG;
     LATTE_CUDA_OK(cudaMemsetAsync(acc_i, 0, acc_bytes, st));
     if (rank_sweep) {
-      LATTE_CUDA_OK(cudaMemsetAsync(d_txt_partial, 0, (size_t)n_all * (size_t)dim * sizeof(float), st));
+      // peer accumulators are zeroed (and fenced by a cross-rank barrier) by the caller
+      if (d_txt_partial)
+        LATTE_CUDA_OK(cudaMemsetAsync(d_txt_partial, 0, (size_t)n_all * (size_t)dim * sizeof(float), st));
     } else {
       LATTE_CUDA_OK(cudaMemsetAsync(acc_t, 0, acc_bytes, st));
     }
@@ -952,10 +958,16 @@ static int clip_bwd_impl(const void* img_loc, int64_t ld_img_loc, const void* tx
     ga.x16 = single ? img16 : nullptr; ga.ldx16 = ld_img16;
     ga.dx32 = acc_i; ga.dy32 = acc_t;
     ga.ld_dy32 = (int64_t)w.ld32; ga.dy_scale = nullptr;
+    ga.dy_peers = nullptr; ga.n_peers = 0;
     if (rank_sweep) {
       // rows [label_offset, label_offset + n_loc) of the gathered fp16 images are this rank's
       ga.x16 = static_cast<const __half*>(img16) + label_offset * ld_img16;
       ga.dy32 = d_txt_partial; ga.ld_dy32 = dim; ga.dy_scale = out_scale;
+      if (d_txt_peers) {
+        ga.dy32 = static_cast<float*>(d_txt_peers[0]);       // unused: every row has an owner
+        ga.dy_peers = reinterpret_cast<float* const*>(d_txt_peers);
+        ga.n_peers = n_peers;
+      }
     }
     rc = clip_pair_gemm(ga, st);
     if (rc) return rc;
@@ -970,7 +982,7 @@ static int clip_bwd_impl(const void* img_loc, int64_t ld_img_loc, const void* tx
       if (rc) return rc;
       LATTE_MARK(LATTE_STAGE_BWD_SWEEP);
       ga.y16 = img16; ga.ldy16 = ld_img16; ga.x16 = nullptr;
-      ga.dx32 = acc_t; ga.dy32 = nullptr;
+      ga.dx32 = acc_t; ga.dy32 = nullptr; ga.dy_peers = nullptr; ga.n_peers = 0;
       rc = clip_pair_gemm(ga, st);
       if (rc) return rc;
       LATTE_MARK(LATTE_STAGE_BWD_GEMM);
@@ -984,7 +996,7 @@ static int clip_bwd_impl(const void* img_loc, int64_t ld_img_loc, const void* tx
     return LATTE_OK;
   }
   LATTE_MARK(LATTE_STAGE_BWD_PREP);
-  if (d_txt_partial || !d_txt) return LATTE_ERR_UNSUPPORTED;
+  if (d_txt_partial || d_txt_peers || !d_txt) return LATTE_ERR_UNSUPPORTED;
 
   ClipBwdArgs a;
   a.dtype = dtype; a.n_loc = n_loc; a.n_all = n_all; a.dim = dim;
@@ -1018,13 +1030,14 @@ extern "C" int latte_clip_bwd(const void* img_loc, int64_t ld_img_loc, const voi
                               const float* col_lse_all, const float* row_nll_all,
                               const float* col_nll_all, const float* grad_loss, float grad_mult,
                               int cross_terms, void* d_img, void* d_txt, int grad_dtype,
-                              int64_t ld_grad, float* d_txt_partial, float* d_scale,
-                              void* workspace, size_t workspace_bytes, void* stream) {
+                              int64_t ld_grad, float* d_txt_partial, void* const* d_txt_peers,
+                              int n_peers, float* d_scale, void* workspace,
+                              size_t workspace_bytes, void* stream) {
   return clip_bwd_impl(img_loc, ld_img_loc, txt_loc, ld_txt_loc, img_all, ld_img_all, txt_all,
                        ld_txt_all, dtype, n_loc, n_all, dim, label_offset, logit_scale, row_lse_all,
                        col_lse_all, row_nll_all, col_nll_all, grad_loss, grad_mult, cross_terms, d_img,
-                       d_txt, grad_dtype, ld_grad, d_txt_partial, d_scale, workspace, workspace_bytes,
-                       stream, nullptr);
+                       d_txt, grad_dtype, ld_grad, d_txt_partial, d_txt_peers, n_peers, d_scale,
+                       workspace, workspace_bytes, stream, nullptr);
 }
 
 extern "C" int latte_clip_stage_times(const void* img_loc, int64_t ld_img_loc, const void* txt_loc,
@@ -1066,8 +1079,8 @@ extern "C" int latte_clip_stage_times(const void* img_loc, int64_t ld_img_loc, c
       rc = clip_bwd_impl(img_loc, ld_img_loc, txt_loc, ld_txt_loc, img_all, ld_img_all, txt_all,
                          ld_txt_all, dtype, n_loc, n_all, dim, label_offset, logit_scale,
                          row_lse_all, col_lse_all, nullptr, nullptr, grad_loss, grad_mult, cross_terms,
-                         d_img, d_txt, grad_dtype, ld_grad, d_txt_partial, d_scale, bwd_workspace,
-                         bwd_workspace_bytes, stream, &tm);
+                         d_img, d_txt, grad_dtype, ld_grad, d_txt_partial, nullptr, 0, d_scale,
+                         bwd_workspace, bwd_workspace_bytes, stream, &tm);
     const cudaError_t e = cudaStreamSynchronize(st);
     tm.collect(stage_ms);
     if (rc) return rc;

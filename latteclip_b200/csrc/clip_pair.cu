@@ -578,6 +578,11 @@ struct GemmProblem {
   float* out;          // [m_rows, ld_out] fp32, accumulated with red.add
   int64_t ld_out;
   const float* scale;  // nullable device scalar applied to every partial before the red.add
+  // Fused reduce-scatter (multi-rank text gradient): output row m belongs to rank m / rows_per_peer
+  // and is added straight into that rank's accumulator through its peer mapping (NVLink).
+  float* peers[8];
+  int npeers;
+  int64_t rows_per_peer;
 };
 
 struct GemmParams {
@@ -742,6 +747,10 @@ pair_gemm_kernel(const __grid_constant__ CUtensorMap tma0, const __grid_constant
       const int64_t m = (int64_t)mt * 256 + (int64_t)rank * kPM + q * 32 + lane;
       const bool m_ok = m < pr.m_rows;
       float* orow = pr.out + (m_ok ? m : 0) * pr.ld_out;
+      if (pr.npeers > 0 && m_ok) {
+        const int64_t w = m / pr.rows_per_peer;
+        orow = pr.peers[w] + (m - w * pr.rows_per_peer) * pr.ld_out;
+      }
       const float osc = pr.scale ? __ldg(pr.scale) : 1.0f;
       mbar_wait(bar_tfull, seg & 1);
       tc_fence_after();
@@ -968,6 +977,8 @@ int clip_pair_gemm(const PairGemmArgs& a, cudaStream_t stream) {
   p.prob[0].out = a.dx32;
   p.prob[0].ld_out = a.ld32;
   p.prob[0].scale = nullptr;
+  p.prob[0].npeers = 0;
+  p.prob[0].rows_per_peer = 1;
   // dY = G^T . X : (world size 1) rows = columns of G, contraction over the rows of G
   p.prob[1].mode = 1;
   p.prob[1].m_tiles = geo.col_tiles / 2;
@@ -976,6 +987,15 @@ int clip_pair_gemm(const PairGemmArgs& a, cudaStream_t stream) {
   p.prob[1].out = a.dy32;
   p.prob[1].ld_out = a.ld_dy32;
   p.prob[1].scale = a.dy_scale;
+  p.prob[1].npeers = 0;
+  p.prob[1].rows_per_peer = 1;
+  for (int w = 0; w < 8; ++w) { p.prob[0].peers[w] = nullptr; p.prob[1].peers[w] = nullptr; }
+  if (a.dy_peers && a.n_peers > 1) {
+    if (a.n_peers > 8) return LATTE_ERR_UNSUPPORTED;
+    p.prob[1].npeers = a.n_peers;
+    p.prob[1].rows_per_peer = a.n_all / a.n_peers;
+    for (int w = 0; w < a.n_peers; ++w) p.prob[1].peers[w] = a.dy_peers[w];
+  }
   for (int mode = 0; mode < 2; ++mode)
     for (int g = 0; g < 2; ++g) {
       const int cnt = p.nhalf - 2 * g >= 2 ? 2 : (p.nhalf - 2 * g == 1 ? 1 : 0);

@@ -117,6 +117,8 @@ struct PairGemmArgs {
   int64_t ld32;
   int64_t ld_dy32;
   const float* dy_scale;            // nullable device scalar multiplied into dy32's partials
+  float* const* dy_peers;           // nullable HOST array: per-rank accumulators [n_all / n_peers, ld_dy32]
+  int n_peers;                      //   (peer-mapped); rows of dy go to their owner rank instead of dy32
 };
 // Forward on the same sweep: rows dealt to clusters as contiguous tile ranges; a row block
 // split over several clusters gets one partial slot per cluster.

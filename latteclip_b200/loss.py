@@ -114,6 +114,39 @@ def _reduce_scatter_sum(x: torch.Tensor, n: int, rank: int, group=None) -> torch
     return x[rank * n:(rank + 1) * n].clone()
 
 
+# fp32 text-gradient accumulators mapped into every rank of the group (torch symmetric memory):
+# the gradient GEMM of each rank adds its rows straight into their owner's accumulator over
+# NVLink, which fuses the reduce-scatter of the reference's all_gather backward into the GEMM.
+_PEER_ACC = {}
+
+
+def _peer_accumulator(n: int, dim: int, device, group):
+    """-> (acc [n, dim] fp32, symmetric-memory handle) or None when peer mapping is unavailable
+    (non-NCCL backend, no P2P, LATTE_B200_NO_P2P=1); rendezvous happens once per shape."""
+    import os
+    if os.environ.get("LATTE_B200_NO_P2P") == "1" or device.type != "cuda":
+        return None
+    key = (n, dim, device.index, id(group))
+    if key in _PEER_ACC:
+        return _PEER_ACC[key]
+    entry = None
+    try:
+        if dist.get_backend(group) == "nccl" and dist.get_world_size(group) <= 8:
+            import torch.distributed._symmetric_memory as symm
+            acc = symm.empty(n, dim, dtype=torch.float32, device=device)
+            hdl = symm.rendezvous(acc, group if group is not None else dist.group.WORLD)
+            entry = (acc, hdl, [int(p) for p in hdl.buffer_ptrs])
+    except Exception:      # no symmetric memory on this system: NCCL reduce-scatter path
+        entry = None
+    # the decision must be the same on every rank (the collectives differ)
+    ok = torch.tensor([1 if entry is not None else 0], device=device, dtype=torch.int32)
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+    if int(ok) == 0:
+        entry = None
+    _PEER_ACC[key] = entry
+    return entry
+
+
 class _FusedClipLoss(torch.autograd.Function):
     """loss.py:102-130 fused.  Gradient contract:
          local_loss & gather_with_grad : grads = d(sum_r L_r)/dx_local   (W x global-mean grad)
@@ -125,8 +158,11 @@ class _FusedClipLoss(torch.autograd.Function):
     rank.  Forward: rows of this rank x all columns give the row LSEs and, from the same tiles,
     per-column (max, sum) partials; one all-gather of [2N + 3n] floats per rank merges them into
     every column's LSE.  Backward: one recompute sweep -> G[rows of this rank, :]; d_img is
-    local, the text gradient is an fp32 [N, D] partial that is reduce-scattered -- the
-    reference's own collective (the backward of its all_gather).  d loss / d logit_scale then
+    local; the text gradient G^T.img_loc covers ALL columns and must be reduce-scattered -- the
+    reference's own collective (the backward of its all_gather).  With torch symmetric memory
+    the GEMM epilogue adds every row straight into its owner rank's peer-mapped fp32
+    accumulator (red.global.add over NVLink, two cross-rank barriers), so the reduce-scatter
+    overlaps the GEMM tile by tile; otherwise an fp32 [N, D] partial goes through NCCL.  d loss / d logit_scale then
     covers this rank's rows x all columns: a different partition over ranks of the same global
     sum as the reference's (identical after DDP's all-reduce of the parameter gradient).
     Other cases: each rank sweeps its row block and its column block (two sweeps) and the
@@ -177,7 +213,18 @@ class _FusedClipLoss(torch.autograd.Function):
         grad_mult = 1.0
         if world_size > 1 and not local_loss and not gather_with_grad:
             grad_mult = 1.0 / world_size
-        if rank_sweep:
+        peer = _peer_accumulator(img.shape[0], img.shape[1], img.device, group) if rank_sweep else None
+        if rank_sweep and peer is not None:
+            # fused reduce-scatter: every rank's GEMM adds into the owners' accumulators
+            acc, hdl, ptrs = peer
+            acc.zero_()
+            hdl.barrier(channel=0)            # all accumulators zeroed, last step's reads done
+            d_img, _, d_scale = _lib.clip_bwd(
+                img, txt, all_img, all_txt, label_offset, scale, row_lse, col_lse, grad_out,
+                grad_mult, True, row_nll_all=row_nll, col_nll_all=col_nll, peer_ptrs=ptrs)
+            hdl.barrier(channel=1)            # every rank's adds have landed
+            d_txt = acc.to(img.dtype)
+        elif rank_sweep:
             d_img, d_part, d_scale = _lib.clip_bwd(
                 img, txt, all_img, all_txt, label_offset, scale, row_lse, col_lse, grad_out,
                 grad_mult, True, row_nll_all=row_nll, col_nll_all=col_nll, partial=True)

@@ -67,7 +67,7 @@ def clip_fwd(img_loc, txt_loc, img_all, txt_all, label_offset, logit_scale, with
 
 def clip_bwd(img_loc, txt_loc, img_all, txt_all, label_offset, logit_scale, row_lse_all,
              col_lse_all, grad_loss, grad_mult, cross_terms, grad_dtype=None, row_nll_all=None,
-             col_nll_all=None, partial=False):
+             col_nll_all=None, partial=False, peer_ptrs=None):
     s = logit_scale.detach().double().reshape(())
     il, tl, ia, ta = (x.detach().double() for x in (img_loc, txt_loc, img_all, txt_all))
     n = il.shape[0]
