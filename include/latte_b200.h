@@ -178,6 +178,19 @@ int latte_clip_bwd(const void* img_loc, int64_t ld_img_loc,
                    void* workspace, size_t workspace_bytes, void* stream);
 
 /*
+ * The feature all-gather of gather_features (loss.py:49-50 / :54-55) as one NVLink store
+ * kernel: writes this rank's image and text shards ([n_loc, dim], shard_bytes each) into the
+ * gathered buffers of every rank.  peer_bases: HOST array of n_peers device pointers, rank w's
+ * buffer [2][n_all, dim] mapped into this process (torch symmetric memory); the text matrix
+ * starts tensor_stride_bytes after the image matrix.  The caller brackets the call with
+ * cross-rank barriers (before: readers of the previous contents are done; after: all shards
+ * have landed).
+ */
+int latte_push_shards(const void* img_shard, const void* txt_shard, int64_t shard_bytes,
+                      void* const* peer_bases, int n_peers, int rank,
+                      int64_t tensor_stride_bytes, void* stream);
+
+/*
  * Diagnostic for bench.py: runs latte_clip_fwd then latte_clip_bwd `reps` times on `stream`
  * with CUDA events recorded on that stream around every kernel stage, synchronises the
  * stream, and returns the mean milliseconds per stage in stage_ms[LATTE_NUM_STAGES] (host

@@ -77,6 +77,7 @@ def _declare(lib):
     lib.latte_clip_stage_times.argtypes = [vp, i64, vp, i64, vp, i64, vp, i64, i32, i64, i64, i64, i64,
                                            vp, vp, vp, vp, vp, vp, vp, f32, i32, vp, vp, i32, i64,
                                            vp, vp, vp, sz, vp, sz, vp, i32, c.POINTER(f32)]
+    lib.latte_push_shards.argtypes = [vp, vp, i64, vp, i32, i32, i64, vp]
     lib.latte_normalize_rows.argtypes = [vp, i64, vp, i64, i64, i64, vp]
     lib.latte_nxc_argmax_margin.argtypes = [vp, i64, i32, vp, i64, i64, vp, i64, i64, f32,
                                             vp, vp, vp, vp]
@@ -96,6 +97,7 @@ EXPORTS = [
     "latte_version", "latte_status_string", "latte_device_info", "latte_clip_workspace_bytes",
     "latte_clip_bwd_workspace_bytes", "latte_clip_stage_times", "latte_clip_rank_sweep_supported",
     "latte_clip_fwd_rows", "latte_clip_fwd_cols_workspace_bytes", "latte_clip_fwd_cols",
+    "latte_push_shards",
     "latte_clip_fwd", "latte_clip_bwd", "latte_normalize_rows", "latte_nxc_argmax_margin",
     "latte_nxc_topk", "latte_mix_ema_fwd", "latte_mix_ema_bwd", "latte_bank_accumulate",
     "latte_bank_finalize",
@@ -208,6 +210,20 @@ def clip_fwd(img_loc, txt_loc, img_all, txt_all, label_offset: int, logit_scale,
     if with_nll:
         return row_lse, col_lse, loss, row_nll, col_nll
     return row_lse, col_lse, loss
+
+
+def push_shards(img_shard, txt_shard, peer_ptrs, rank: int, tensor_stride_bytes: int):
+    """Write this rank's feature shards into every rank's peer-mapped gathered buffer."""
+    lib = load()
+    img_shard, txt_shard = _rows(img_shard, "image_features"), _rows(txt_shard, "text_features")
+    if not (img_shard.is_contiguous() and txt_shard.is_contiguous()):
+        img_shard, txt_shard = img_shard.contiguous(), txt_shard.contiguous()
+    nbytes = img_shard.numel() * img_shard.element_size()
+    peers = (ctypes.c_void_p * len(peer_ptrs))(*peer_ptrs)
+    with torch.cuda.device(img_shard.device):
+        _check(lib.latte_push_shards(_ptr(img_shard), _ptr(txt_shard), nbytes, peers, len(peer_ptrs),
+                                     int(rank), int(tensor_stride_bytes), _stream(img_shard)),
+               "latte_push_shards")
 
 
 def rank_sweep_supported(dtype: torch.dtype, dim: int) -> bool:

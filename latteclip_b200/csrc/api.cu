@@ -421,6 +421,25 @@ __global__ void bf16_to_fp16_kernel(const __nv_bfloat16* in0, __half* out0,
   }
 }
 
+// Push this rank's image and text shards into every rank's gathered buffers (peer-mapped):
+// the all-gather of loss.py:49-50 / :54-55 as one NVLink store kernel.  16-byte vectors.
+__global__ void __launch_bounds__(256)
+push_shards_kernel(const uint4* img, const uint4* txt, int64_t shard_vecs, int64_t tensor_vecs,
+                   int64_t rank_off_vecs, uint4* p0, uint4* p1, uint4* p2, uint4* p3, uint4* p4,
+                   uint4* p5, uint4* p6, uint4* p7, int n_peers) {
+  uint4* peers[8] = {p0, p1, p2, p3, p4, p5, p6, p7};
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < 2 * shard_vecs; v += stride) {
+    const bool is_txt = v >= shard_vecs;
+    const int64_t k = is_txt ? v - shard_vecs : v;
+    const uint4 val = is_txt ? __ldg(txt + k) : __ldg(img + k);
+    const int64_t dst = (is_txt ? tensor_vecs : 0) + rank_off_vecs + k;
+#pragma unroll
+    for (int p = 0; p < 8; ++p)
+      if (p < n_peers) peers[p][dst] = val;
+  }
+}
+
 struct WsLayout {
   size_t part;      // floats per partial array (kMaxParts * n_loc)
   size_t off_pmax_r, off_psum_r, off_diag_r, off_pmax_c, off_psum_c, off_diag_c;
@@ -1087,5 +1106,29 @@ extern "C" int latte_clip_stage_times(const void* img_loc, int64_t ld_img_loc, c
     if (e != cudaSuccess || tm.failed) return LATTE_ERR_CUDA;
   }
   for (int k = 0; k < LATTE_NUM_STAGES; ++k) stage_ms[k] /= (float)reps;
+  return LATTE_OK;
+}
+
+extern "C" int latte_push_shards(const void* img_shard, const void* txt_shard, int64_t shard_bytes,
+                                 void* const* peer_bases, int n_peers, int rank,
+                                 int64_t tensor_stride_bytes, void* stream) {
+  LATTE_CHECK_ARG(img_shard && txt_shard && peer_bases && n_peers >= 1 && n_peers <= 8);
+  LATTE_CHECK_ARG(rank >= 0 && rank < n_peers && shard_bytes > 0 && (shard_bytes % 16) == 0);
+  LATTE_CHECK_ARG((tensor_stride_bytes % 16) == 0 && tensor_stride_bytes >= shard_bytes * n_peers);
+  LATTE_CHECK_ARG((reinterpret_cast<uintptr_t>(img_shard) & 15) == 0 &&
+                  (reinterpret_cast<uintptr_t>(txt_shard) & 15) == 0);
+  uint4* p[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  for (int k = 0; k < n_peers; ++k) {
+    LATTE_CHECK_ARG(peer_bases[k] && (reinterpret_cast<uintptr_t>(peer_bases[k]) & 15) == 0);
+    p[k] = static_cast<uint4*>(peer_bases[k]);
+  }
+  const int64_t shard_vecs = shard_bytes / 16;
+  int64_t blocks = (2 * shard_vecs + 255) / 256;
+  if (blocks > 4 * device_sm_count()) blocks = 4 * device_sm_count();
+  push_shards_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint4*>(img_shard), static_cast<const uint4*>(txt_shard), shard_vecs,
+      tensor_stride_bytes / 16, (int64_t)rank * shard_vecs, p[0], p[1], p[2], p[3], p[4], p[5], p[6],
+      p[7], n_peers);
+  LATTE_LAUNCH_OK();
   return LATTE_OK;
 }

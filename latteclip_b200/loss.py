@@ -147,6 +147,55 @@ def _peer_accumulator(n: int, dim: int, device, group):
     return entry
 
 
+# Gathered feature buffers [2, N, D] in symmetric memory: every rank stores its shards straight
+# into all ranks' buffers (latte_push_shards), replacing the two NCCL all-gathers of the
+# forward.  A slot stays busy from a forward until its backward (the gathered features are
+# saved for the recompute), so several slots exist per shape; when none is free the call falls
+# back to NCCL -- every rank takes the same decision because the call sequence is the same.
+_GATHER_SLOTS = {}
+_MAX_GATHER_SLOTS = 4
+
+
+class _GatherSlot:
+    def __init__(self, buf, hdl):
+        self.buf, self.hdl = buf, hdl
+        self.ptrs = [int(p) for p in hdl.buffer_ptrs]
+        self.busy = False
+
+
+def _acquire_gather_slot(n: int, dim: int, dtype, device, group, world: int):
+    import os
+    if os.environ.get("LATTE_B200_NO_P2P") == "1" or device.type != "cuda":
+        return None
+    if dtype not in (torch.bfloat16, torch.float16) or (n * dim * 2) % 16 != 0:
+        return None
+    key = (n, dim, dtype, device.index, id(group))
+    slots = _GATHER_SLOTS.setdefault(key, [])
+    for sl in slots:
+        if sl is not None and not sl.busy:
+            sl.busy = True
+            return sl
+    if len(slots) >= _MAX_GATHER_SLOTS or (slots and slots[-1] is None):
+        return None
+    slot = None
+    try:
+        if dist.get_backend(group) == "nccl" and world <= 8:
+            import torch.distributed._symmetric_memory as symm
+            buf = symm.empty(2, n * world, dim, dtype=dtype, device=device)
+            hdl = symm.rendezvous(buf, group if group is not None else dist.group.WORLD)
+            slot = _GatherSlot(buf, hdl)
+    except Exception:
+        slot = None
+    ok = torch.tensor([1 if slot is not None else 0], device=device, dtype=torch.int32)
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+    if int(ok) == 0:
+        slot = None
+    slots.append(slot)
+    if slot is not None:
+        slot.busy = True
+    return slot
+
+
 class _FusedClipLoss(torch.autograd.Function):
     """loss.py:102-130 fused.  Gradient contract:
          local_loss & gather_with_grad : grads = d(sum_r L_r)/dx_local   (W x global-mean grad)
@@ -176,11 +225,22 @@ class _FusedClipLoss(torch.autograd.Function):
         txt = text_features.detach()
         cross_terms = not (world_size > 1 and local_loss and not gather_with_grad)
         rank_sweep = False
+        slot = None
         if world_size > 1:
-            all_img = _all_gather_cat(img, group)
-            all_txt = _all_gather_cat(txt, group)
             label_offset = rank * img.shape[0]
             rank_sweep = cross_terms and _lib.rank_sweep_supported(img.dtype, img.shape[1])
+            if rank_sweep and img.dtype == txt.dtype:
+                slot = _acquire_gather_slot(img.shape[0], img.shape[1], img.dtype, img.device, group,
+                                            world_size)
+            if slot is not None:
+                # one NVLink store kernel instead of two NCCL all-gathers
+                slot.hdl.barrier(channel=0)       # readers of the slot's previous contents are done
+                _lib.push_shards(img, txt, slot.ptrs, rank, slot.buf[0].numel() * slot.buf.element_size())
+                slot.hdl.barrier(channel=1)       # every rank's shards have landed
+                all_img, all_txt = slot.buf[0], slot.buf[1]
+            else:
+                all_img = _all_gather_cat(img, group)
+                all_txt = _all_gather_cat(txt, group)
         else:
             all_img, all_txt, label_offset = img, txt, 0
         if rank_sweep:
@@ -199,6 +259,10 @@ class _FusedClipLoss(torch.autograd.Function):
             loss = loss.clone()
             dist.all_reduce(loss, op=dist.ReduceOp.SUM, group=group)
             loss = loss / world_size
+        ctx.gather_slot = slot
+        if slot is not None and not any(ctx.needs_input_grad[:3]):
+            slot.busy = False                     # no backward will come for this call
+            ctx.gather_slot = None
         ctx.save_for_backward(img, txt, all_img, all_txt, logit_scale.detach(), *stats)
         ctx.cfg = (local_loss, gather_with_grad, rank, world_size, group, label_offset, rank_sweep)
         ctx.scale_meta = (logit_scale.dtype, logit_scale.shape)
@@ -238,6 +302,9 @@ class _FusedClipLoss(torch.autograd.Function):
             d_img, d_txt, d_scale = _lib.clip_bwd(
                 img, txt, all_img, all_txt, label_offset, scale, row_all, col_all, grad_out,
                 grad_mult, cross_terms, row_nll_all=rown_all, col_nll_all=coln_all)
+        if getattr(ctx, "gather_slot", None) is not None:
+            ctx.gather_slot.busy = False          # the next forward may overwrite the slot
+            ctx.gather_slot = None
         if world_size > 1 and not local_loss:
             # every rank differentiates the same L_global: d/ds is the rank mean of the block sums
             d_scale = d_scale / grad_mult
