@@ -65,7 +65,7 @@ int latte_clip_workspace_bytes(int64_t n_loc, int64_t n_all, int64_t dim, int dt
                                size_t* bytes);
 
 /* Bytes of scratch latte_clip_bwd needs: the forward scratch plus, for 16-bit features with
- * dim <= 512, the fp16 gradient-weight blocks G [n_loc, n_all] and two fp32 [n_loc, dim]
+ * dim <= 768, the fp16 gradient-weight blocks G [n_loc, n_all] and two fp32 [n_loc, dim]
  * accumulators of the CTA-pair backward (csrc/clip_pair.cu). */
 int latte_clip_bwd_workspace_bytes(int64_t n_loc, int64_t n_all, int64_t dim, int dtype,
                                    size_t* bytes);
@@ -99,7 +99,7 @@ int latte_clip_fwd(const void* img_loc, int64_t ld_img_loc,
                    void* workspace, size_t workspace_bytes, void* stream);
 
 /*
- * Multi-rank forward with ONE logit sweep per rank (16-bit features, dim <= 512; ask
+ * Multi-rank forward with ONE logit sweep per rank (16-bit features, dim <= 768; ask
  * latte_clip_rank_sweep_supported).  Step 1 on each rank: rows of this rank against all
  * gathered text features ->
  *   row_lse / row_nll / label_logit [n_loc]   (label_logit[i] = s * <img_loc[i], txt_all[off+i]>)
@@ -145,7 +145,7 @@ int latte_clip_fwd_cols(const float* gathered /* [world, stride]: per rank col_m
  * `workspace` is sized by latte_clip_bwd_workspace_bytes.
  * row_nll_all / col_nll_all (nullable, both or neither): the forward's per-sample loss terms
  * [n_all]; with them the label entry of G is expm1(-nll) instead of exp(S - lse) - 1.
- * d_txt_partial (nullable, fp32 [n_all, dim], 16-bit features with dim <= 512 and
+ * d_txt_partial (nullable, fp32 [n_all, dim], 16-bit features with dim <= 768 and
  * cross_terms = 1 only): one-sweep multi-rank mode -- d_txt is not written; instead
  * d_txt_partial = coef * s * G[loc rows, :]^T @ img_loc for ALL columns, which the caller
  * reduce-scatters (SUM) over the ranks; *d_scale then covers this rank's rows x all columns

@@ -458,7 +458,7 @@ struct WsLayout {
 };
 
 bool pair_shape_ok(int dtype, int64_t dim) {
-  return (dtype == LATTE_BF16 || dtype == LATTE_F16) && dim >= 8 && dim <= 512 && (dim % 8) == 0;
+  return (dtype == LATTE_BF16 || dtype == LATTE_F16) && dim >= 8 && dim <= 768 && (dim % 8) == 0;
 }
 
 WsLayout ws_layout(int64_t n_loc, int64_t n_all, int64_t dim, int dtype, bool bwd = false) {

@@ -1,4 +1,4 @@
-// ClipLoss backward on CTA pairs (tcgen05 cta_group::2), bf16 / fp16 features, dim <= 512.
+// ClipLoss backward on CTA pairs (tcgen05 cta_group::2), bf16 / fp16 features, dim <= 768.
 //
 // Replaces the autograd of open_clip/loss.py:109-116 + 126-129 with three kernels that
 // execute 6*n*N*D FLOP for the 4*n*N*D credited to the backward (one logit recompute, no
@@ -36,6 +36,9 @@ constexpr int kYChunkBytes = 64 * kBK * 2;      // this CTA's half of a Y chunk:
 constexpr int kChunksPerStage = 4;               // one barrier round trip per 4 chunks (K = 256)
 constexpr int kSweepStages = 4;
 constexpr int kRingStageBytes = kChunksPerStage * kYChunkBytes;   // 32 KB
+constexpr int kTmemChunks = 8;                   // X chunks held in TMEM (256 of the 512 columns)
+constexpr int kXTailBytes = kPM * kBK * 2;       // 16 KB: one chunk of this CTA's X rows in smem
+constexpr int kXTailOffset = 2 * kRingStageBytes;  // dim > 512: the ring keeps 64 KB, the tail gets 64 KB
 constexpr int kStageBytes = 32 * 128;           // one epilogue warp's G staging: 32 rows x 128 B
 constexpr int kMiscBytes = 1024;
 constexpr int kVecBytes = 64 * 4;               // one epilogue warp's column factors of a tile
@@ -82,6 +85,8 @@ struct SweepParams {
   float* col_ref;                    // [2 * row_blocks, 4 * col_tiles]  (one per 32 columns)
   int64_t ld_colpart;
   int kch;                           // ceil(dim / 64)
+  int cps;                           // feature chunks per ring stage (4, or 2 with an X tail)
+  int tail_chunks;                   // chunks of X beyond the 8 held in TMEM (dim > 512): smem
   int col_tiles;                     // tiles of 128 columns (even: columns padded to 256)
   int row_blocks;                    // blocks of 256 rows
   int ncb;                           // G block columns = 2 * col_tiles
@@ -95,7 +100,7 @@ constexpr int kModeFwdBoth = 2;   // forward, world size 1: row partials + colum
 template <int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kSweepThreads, 1)
 pair_sweep_kernel(const __grid_constant__ CUtensorMap tmy, const __grid_constant__ CUtensorMap tmg,
-                  const SweepParams p) {
+                  const __grid_constant__ CUtensorMap tmx, const SweepParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t smem_base = smem_u32(smem);
   const int warp = threadIdx.x >> 5;
@@ -111,7 +116,8 @@ pair_sweep_kernel(const __grid_constant__ CUtensorMap tmy, const __grid_constant
   const uint32_t bar_tfull = bar_empty + 8 * kSweepStages;  // [2]
   const uint32_t bar_tempty = bar_tfull + 16;               // [2]   (leader's are used)
   const uint32_t bar_aready = bar_tempty + 16;              // [1]   (leader's is used)
-  const uint32_t tmem_slot = bar_aready + 8;
+  const uint32_t bar_xt = bar_aready + 8;                   // [1]   X tail landed (leader's is used)
+  const uint32_t tmem_slot = bar_xt + 8;
   const uint32_t red_slot = tmem_slot + 8;
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem + (tmem_slot - smem_base));
@@ -130,9 +136,15 @@ pair_sweep_kernel(const __grid_constant__ CUtensorMap tmy, const __grid_constant
   const int rb0 = (int)(u0 / p.col_tiles);
   const int ct0 = (int)(u0 % p.col_tiles);
 
+  // ring stages of cps chunks; with dim > 512 the X columns beyond the TMEM-resident 512 live in
+  // the upper half of the ring area and their MMAs take A from shared memory ("SS" form)
+  const uint32_t ring_stage_bytes = (uint32_t)p.cps * kYChunkBytes;
+  const uint32_t xtail = ring + kXTailOffset;
+
   if (warp == 0 && elect_one()) {
     prefetch_tensormap(&tmy);
     prefetch_tensormap(&tmg);
+    prefetch_tensormap(&tmx);
   }
   if (warp == 1 && elect_one()) {
     for (int s = 0; s < kSweepStages; ++s) {
@@ -144,6 +156,7 @@ pair_sweep_kernel(const __grid_constant__ CUtensorMap tmy, const __grid_constant
       mbar_init(bar_tempty + 8 * b, 16);      // one group (8 warps) of each CTA drains a buffer
     }
     mbar_init(bar_aready, 16);                // group 0 (8 warps) of each CTA loads X
+    mbar_init(bar_xt, 1);
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -164,18 +177,32 @@ pair_sweep_kernel(const __grid_constant__ CUtensorMap tmy, const __grid_constant
       const uint64_t keep = policy_evict_last();      // features are re-read by every pair
       int stage = 0;
       uint32_t phase = 0;
-      int ct = ct0;
-      for (int it = 0; it < ntile; ++it, ct = (ct + 1 == p.col_tiles) ? 0 : ct + 1) {
-        for (int c0 = 0; c0 < p.kch; c0 += kChunksPerStage) {
-          const int nc = min(kChunksPerStage, p.kch - c0);
+      const uint32_t lead_xt = mapa_rank(bar_xt, 0);
+      int ct = ct0, rb_i = rb0;
+      for (int it = 0; it < ntile; ++it) {
+        if (p.tail_chunks > 0 && (it == 0 || ct == 0)) {
+          // new row block: its X tail replaces the previous one once every MMA of the
+          // previous block is done (tfull of its last tile)
+          if (it > 0) {
+            const int last = it - 1;
+            mbar_wait(bar_tfull + 8 * (last & 1), (last >> 1) & 1);
+          }
+          if (rank == 0) mbar_arrive_expect_tx(bar_xt, 2u * (uint32_t)p.tail_chunks * kXTailBytes);
+          for (int j = 0; j < p.tail_chunks; ++j)
+            tma_load_2d_pair_hint(xtail + j * kXTailBytes, &tmx, lead_xt, (kTmemChunks + j) * kBK,
+                                  rb_i * 256 + (int)rank * kPM, keep);
+        }
+        for (int c0 = 0; c0 < p.kch; c0 += p.cps) {
+          const int nc = min(p.cps, p.kch - c0);
           mbar_wait(bar_empty + 8 * stage, phase ^ 1);
           if (rank == 0) mbar_arrive_expect_tx(bar_full + 8 * stage, 2 * nc * kYChunkBytes);
           for (int c = 0; c < nc; ++c)
-            tma_load_2d_pair_hint(ring + stage * kRingStageBytes + c * kYChunkBytes, &tmy,
+            tma_load_2d_pair_hint(ring + stage * ring_stage_bytes + c * kYChunkBytes, &tmy,
                                   lead_full + 8 * stage, (c0 + c) * kBK, ct * kTN + (int)rank * 64,
                                   keep);
           if (++stage == kSweepStages) { stage = 0; phase ^= 1; }
         }
+        if (++ct == p.col_tiles) { ct = 0; ++rb_i; }
       }
     }
   } else if (warp == 1) {
@@ -187,6 +214,7 @@ pair_sweep_kernel(const __grid_constant__ CUtensorMap tmy, const __grid_constant
       for (int it = 0; it < ntile; ++it) {
         if (it == 0 || ct == 0) {          // first tile of a row block: wait for its X block
           mbar_wait(bar_aready, a_phase);
+          if (p.tail_chunks > 0) mbar_wait(bar_xt, a_phase);
           a_phase ^= 1;
         }
         ct = (ct + 1 == p.col_tiles) ? 0 : ct + 1;
@@ -194,17 +222,28 @@ pair_sweep_kernel(const __grid_constant__ CUtensorMap tmy, const __grid_constant
         mbar_wait(bar_tempty + 8 * buf, ((it >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_s + buf * kTN;
-        for (int c0 = 0; c0 < p.kch; c0 += kChunksPerStage) {
-          const int nc = min(kChunksPerStage, p.kch - c0);
+        for (int c0 = 0; c0 < p.kch; c0 += p.cps) {
+          const int nc = min(p.cps, p.kch - c0);
           mbar_wait(bar_full + 8 * stage, phase);
           tc_fence_after();
           // descriptor of the stage base; the start-address field counts 16-byte units
-          const uint64_t db0 = make_smem_desc_sw128(ring + stage * kRingStageBytes, 16, 1024);
+          const uint64_t db0 = make_smem_desc_sw128(ring + stage * ring_stage_bytes, 16, 1024);
           for (int c = 0; c < nc; ++c) {
+            const int gc = c0 + c;
+            if (gc < kTmemChunks) {
 #pragma unroll
-            for (int k = 0; k < kBK / 16; ++k) {
-              const uint64_t db = db0 + (uint64_t)((c * kYChunkBytes + k * 32) >> 4);
-              mma2_ts(tmem_d, tmem_a + (c0 + c) * 32 + k * 8, db, p.idesc, (c0 | c | k) != 0);
+              for (int k = 0; k < kBK / 16; ++k) {
+                const uint64_t db = db0 + (uint64_t)((c * kYChunkBytes + k * 32) >> 4);
+                mma2_ts(tmem_d, tmem_a + gc * 32 + k * 8, db, p.idesc, (gc | k) != 0);
+              }
+            } else {
+              const uint64_t da0 =
+                  make_smem_desc_sw128(xtail + (gc - kTmemChunks) * kXTailBytes, 16, 1024);
+#pragma unroll
+              for (int k = 0; k < kBK / 16; ++k) {
+                const uint64_t db = db0 + (uint64_t)((c * kYChunkBytes + k * 32) >> 4);
+                mma2_ss(tmem_d, da0 + (uint64_t)(k * 2), db, p.idesc, 1u);
+              }
             }
           }
           tc_commit_pair(bar_empty + 8 * stage, 3);
@@ -256,7 +295,7 @@ pair_sweep_kernel(const __grid_constant__ CUtensorMap tmy, const __grid_constant
         tc_fence_after();
       }
       const uint16_t* xrow = reinterpret_cast<const uint16_t*>(p.x) + (row_ok ? grow : 0) * p.ldx;
-      const int groups = p.kch * 2;              // groups of 32 features = 16 packed columns
+      const int groups = min(p.kch, kTmemChunks) * 2;   // groups of 32 features = 16 packed columns
       for (int g = half; g < groups; g += 2) {
         uint32_t w[16];
 #pragma unroll
@@ -583,15 +622,18 @@ struct GemmProblem {
   float* peers[8];
   int npeers;
   int64_t rows_per_peer;
+  // feature slab of this problem: TMEM holds 512 accumulator columns, so dim > 512 is split
+  int product;         // 0: B operand from tmb0, 1: from tmb1
+  int d_off;           // first feature column of the slab (multiple of 128)
+  int nhalf;           // 64-column feature chunks per CTA in this slab (1..4)
+  uint32_t idesc[2];   // per MMA group of the slab
 };
 
 struct GemmParams {
-  GemmProblem prob[2];
+  GemmProblem prob[4];
   int nprob;
   int ncb;             // G block columns
   int dim;
-  int nhalf;           // 64-column feature chunks per CTA = round_up(dim, 128) / 128
-  uint32_t idesc[2][2];  // [mode][mma group]
 };
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
@@ -615,9 +657,11 @@ pair_gemm_kernel(const __grid_constant__ CUtensorMap tma0, const __grid_constant
 
   if (threadIdx.x == 0 && (smem_base & 1023u) != 0) __trap();
 
-  const int64_t units0 = (int64_t)p.prob[0].m_tiles * p.prob[0].k_chunks;
-  const int64_t units1 = p.nprob > 1 ? (int64_t)p.prob[1].m_tiles * p.prob[1].k_chunks : 0;
-  const int64_t total = units0 + units1;
+  int64_t ubase[5];
+  ubase[0] = 0;
+  for (int i = 0; i < 4; ++i)
+    ubase[i + 1] = ubase[i] + (i < p.nprob ? (int64_t)p.prob[i].m_tiles * p.prob[i].k_chunks : 0);
+  const int64_t total = ubase[4];
   const int64_t ncl = gridDim.x >> 1;
   const int64_t cl = blockIdx.x >> 1;
   const int64_t u0 = cl * total / ncl;
@@ -646,12 +690,12 @@ pair_gemm_kernel(const __grid_constant__ CUtensorMap tma0, const __grid_constant
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
-  const int nmma = (p.nhalf + 1) / 2;
 
   // A segment = (problem, output tile, contiguous chunk range); all roles walk the same list.
   auto next_segment = [&](int64_t u, int& pi, int& mt, int& k0, int& k1) {
-    pi = u < units0 ? 0 : 1;
-    const int64_t local = u - (pi ? units0 : 0);
+    pi = 0;
+    while (pi + 1 < p.nprob && u >= ubase[pi + 1]) ++pi;
+    const int64_t local = u - ubase[pi];
     const int kc = p.prob[pi].k_chunks;
     mt = (int)(local / kc);
     k0 = (int)(local % kc);
@@ -663,7 +707,6 @@ pair_gemm_kernel(const __grid_constant__ CUtensorMap tma0, const __grid_constant
     // ------------------------------------------------------------ TMA producer (both CTAs)
     if (elect_one()) {
       const uint32_t lead_full = mapa_rank(bar_full, 0);
-      const uint32_t stage_tx = 2u * (uint32_t)(kGemmABytes + p.nhalf * kGemmBChunk);
       const uint64_t keep = policy_evict_last();        // features: re-read by every tile
       const uint64_t stream_pol = policy_evict_first(); // G: read once per product
       int stage = 0;
@@ -672,7 +715,10 @@ pair_gemm_kernel(const __grid_constant__ CUtensorMap tma0, const __grid_constant
         int pi, mt, k0, k1;
         next_segment(u, pi, mt, k0, k1);
         const int mode = p.prob[pi].mode;
-        const CUtensorMap* tb = pi ? &tmb1 : &tmb0;
+        const int nhalf = p.prob[pi].nhalf;
+        const int dch0 = p.prob[pi].d_off / 64;
+        const uint32_t stage_tx = 2u * (uint32_t)(kGemmABytes + nhalf * kGemmBChunk);
+        const CUtensorMap* tb = p.prob[pi].product ? &tmb1 : &tmb0;
         for (int kc = k0; kc < k1; ++kc) {
           mbar_wait(bar_empty + 8 * stage, phase ^ 1);
           const uint32_t sa = smem_base + stage * kGemmStageBytes;
@@ -688,10 +734,10 @@ pair_gemm_kernel(const __grid_constant__ CUtensorMap tma0, const __grid_constant
             tma_load_2d_pair_hint(sa, &tma1, lf, 0, r0, stream_pol);
             tma_load_2d_pair_hint(sa + 8192, &tma1, lf, 0, r0 + 128, stream_pol);
           }
-          for (int lc = 0; lc < p.nhalf; ++lc) {
+          for (int lc = 0; lc < nhalf; ++lc) {
             const int g = lc >> 1;
-            const int cnt = min(2, p.nhalf - 2 * g);
-            const int dchunk = 4 * g + (int)rank * cnt + (lc - 2 * g);
+            const int cnt = min(2, nhalf - 2 * g);
+            const int dchunk = dch0 + 4 * g + (int)rank * cnt + (lc - 2 * g);
             tma_load_2d_pair_hint(sb + lc * kGemmBChunk, tb, lf, dchunk * 64, kc * 64, keep);
           }
           if (++stage == kGemmStages) { stage = 0; phase ^= 1; }
@@ -709,6 +755,7 @@ pair_gemm_kernel(const __grid_constant__ CUtensorMap tma0, const __grid_constant
         int pi, mt, k0, k1;
         next_segment(u, pi, mt, k0, k1);
         const int mode = p.prob[pi].mode;
+        const int nmma = (p.prob[pi].nhalf + 1) / 2;
         mbar_wait(bar_tempty, (seg & 1) ^ 1);
         tc_fence_after();
         for (int kc = k0; kc < k1; ++kc) {
@@ -722,7 +769,7 @@ pair_gemm_kernel(const __grid_constant__ CUtensorMap tma0, const __grid_constant
                                           : make_smem_desc_sw128(sa + k * 2048, 8192, 1024);
             for (int g = 0; g < nmma; ++g) {
               const uint64_t db = make_smem_desc_sw128(sb + g * 2 * kGemmBChunk + k * 2048, 8192, 1024);
-              mma2_ss(tmem_base + g * 256, da, db, p.idesc[mode][g], (kc > k0 || k > 0) ? 1u : 0u);
+              mma2_ss(tmem_base + g * 256, da, db, p.prob[pi].idesc[g], (kc > k0 || k > 0) ? 1u : 0u);
             }
           }
           tc_commit_pair(bar_empty + 8 * stage, 3);
@@ -738,12 +785,12 @@ pair_gemm_kernel(const __grid_constant__ CUtensorMap tma0, const __grid_constant
     const int half = (warp - kEpiWarp0) >> 2;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     const uint32_t lead_tempty = mapa_rank(bar_tempty, 0);
-    const int cols_half = p.nhalf * 64;          // accumulator columns per epilogue half
     int seg = 0;
     for (int64_t u = u0; u < u1; ++seg) {
       int pi, mt, k0, k1;
       next_segment(u, pi, mt, k0, k1);
       const GemmProblem& pr = p.prob[pi];
+      const int cols_half = pr.nhalf * 64;        // accumulator columns per epilogue half
       const int64_t m = (int64_t)mt * 256 + (int64_t)rank * kPM + q * 32 + lane;
       const bool m_ok = m < pr.m_rows;
       float* orow = pr.out + (m_ok ? m : 0) * pr.ld_out;
@@ -762,8 +809,8 @@ pair_gemm_kernel(const __grid_constant__ CUtensorMap tma0, const __grid_constant
         if (m_ok) {
 #pragma unroll
           for (int i = 0; i < 32; i += 4) {
-            if (col + i < p.dim)
-              red_add_v4(orow + col + i, osc * __uint_as_float(v[i]), osc * __uint_as_float(v[i + 1]),
+            if (pr.d_off + col + i < p.dim)
+              red_add_v4(orow + pr.d_off + col + i, osc * __uint_as_float(v[i]), osc * __uint_as_float(v[i + 1]),
                          osc * __uint_as_float(v[i + 2]), osc * __uint_as_float(v[i + 3]));
           }
         }
@@ -849,7 +896,7 @@ int make_map16(CUtensorMap* map, const void* base, int dtype, int64_t rows, int6
 bool clip_pair_supported(int dtype, int64_t dim, int64_t ldx, int64_t ldy, const void* x,
                          const void* y) {
   if (dtype != LATTE_BF16 && dtype != LATTE_F16) return false;
-  if (dim < 8 || dim > 512 || (dim % 8) != 0) return false;
+  if (dim < 8 || dim > 768 || (dim % 8) != 0) return false;
   if ((ldx % 8) != 0 || (ldy % 8) != 0) return false;
   if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(y) & 15)) return false;
   return true;
@@ -894,6 +941,11 @@ int clip_pair_fwd_sweep(const PairFwdArgs& a, cudaStream_t stream) {
   p.part_max = a.part_max; p.part_sum = a.part_sum; p.diag = a.diag;
   p.col_part = a.col_part; p.col_ref = a.col_ref; p.ld_colpart = f.ld_colpart;
   p.kch = (int)((a.dim + kBK - 1) / kBK);
+  p.tail_chunks = p.kch > kTmemChunks ? p.kch - kTmemChunks : 0;
+  p.cps = p.tail_chunks ? 2 : kChunksPerStage;
+  CUtensorMap tmx;
+  rc = make_map16(&tmx, a.x, a.dtype, a.n_loc, a.dim, a.ldx, 128);
+  if (rc) return rc;
   p.col_tiles = f.col_tiles;
   p.row_blocks = f.row_blocks;
   p.ncb = f.col_tiles * 2;
@@ -901,11 +953,11 @@ int clip_pair_fwd_sweep(const PairFwdArgs& a, cudaStream_t stream) {
   if (a.col_part) {
     LATTE_CUDA_OK(cudaFuncSetAttribute(pair_sweep_kernel<kModeFwdBoth>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, kSweepSmem));
-    pair_sweep_kernel<kModeFwdBoth><<<2 * f.ncl, kSweepThreads, kSweepSmem, stream>>>(tmy, tmy, p);
+    pair_sweep_kernel<kModeFwdBoth><<<2 * f.ncl, kSweepThreads, kSweepSmem, stream>>>(tmy, tmy, tmx, p);
   } else {
     LATTE_CUDA_OK(cudaFuncSetAttribute(pair_sweep_kernel<kModeFwdRows>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, kSweepSmem));
-    pair_sweep_kernel<kModeFwdRows><<<2 * f.ncl, kSweepThreads, kSweepSmem, stream>>>(tmy, tmy, p);
+    pair_sweep_kernel<kModeFwdRows><<<2 * f.ncl, kSweepThreads, kSweepSmem, stream>>>(tmy, tmy, tmx, p);
   }
   LATTE_LAUNCH_OK();
   return LATTE_OK;
@@ -936,6 +988,11 @@ int clip_pair_sweep(const PairSweepArgs& a, cudaStream_t stream) {
   p.ds_cd = a.ds_both ? p.cd : 1.f;
   p.ds_partial = a.ds_partial;
   p.kch = (int)((a.dim + kBK - 1) / kBK);
+  p.tail_chunks = p.kch > kTmemChunks ? p.kch - kTmemChunks : 0;
+  p.cps = p.tail_chunks ? 2 : kChunksPerStage;
+  CUtensorMap tmx;
+  rc = make_map16(&tmx, a.x, a.dtype, a.n_loc, a.dim, a.ldx, 128);
+  if (rc) return rc;
   p.col_tiles = geo.col_tiles;
   p.row_blocks = geo.row_blocks;
   p.ncb = geo.ncb;
@@ -946,7 +1003,7 @@ int clip_pair_sweep(const PairSweepArgs& a, cudaStream_t stream) {
   LATTE_CUDA_OK(cudaFuncSetAttribute(pair_sweep_kernel<kModeGrad>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, kSweepSmem));
   // every CTA of the launch writes its ds partial; unused slots are zeroed by the caller
-  pair_sweep_kernel<kModeGrad><<<2 * ncl, kSweepThreads, kSweepSmem, stream>>>(tmy, tmg, p);
+  pair_sweep_kernel<kModeGrad><<<2 * ncl, kSweepThreads, kSweepSmem, stream>>>(tmy, tmg, tmx, p);
   LATTE_LAUNCH_OK();
   return LATTE_OK;
 }
@@ -964,45 +1021,59 @@ int clip_pair_gemm(const PairGemmArgs& a, cudaStream_t stream) {
   rc = make_map16(&tmb1, a.x16 ? a.x16 : a.y16, LATTE_F16, a.x16 ? a.n_loc : a.n_all, a.dim,
                   a.x16 ? a.ldx16 : a.ldy16, 64);
   if (rc) return rc;
-  GemmParams p;
-  p.nprob = a.x16 ? 2 : 1;
+  GemmParams p = {};
   p.ncb = geo.ncb;
   p.dim = (int)a.dim;
-  p.nhalf = (int)((a.dim + 127) / 128);
-  // dX = G . Y : rows of this rank, contraction over all columns
-  p.prob[0].mode = 0;
-  p.prob[0].m_tiles = geo.row_blocks;
-  p.prob[0].k_chunks = (int)((a.n_all + 63) / 64);
-  p.prob[0].m_rows = a.n_loc;
-  p.prob[0].out = a.dx32;
-  p.prob[0].ld_out = a.ld32;
-  p.prob[0].scale = nullptr;
-  p.prob[0].npeers = 0;
-  p.prob[0].rows_per_peer = 1;
-  // dY = G^T . X : (world size 1) rows = columns of G, contraction over the rows of G
-  p.prob[1].mode = 1;
-  p.prob[1].m_tiles = geo.col_tiles / 2;
-  p.prob[1].k_chunks = (int)((a.n_loc + 63) / 64);
-  p.prob[1].m_rows = a.n_all;
-  p.prob[1].out = a.dy32;
-  p.prob[1].ld_out = a.ld_dy32;
-  p.prob[1].scale = a.dy_scale;
-  p.prob[1].npeers = 0;
-  p.prob[1].rows_per_peer = 1;
-  for (int w = 0; w < 8; ++w) { p.prob[0].peers[w] = nullptr; p.prob[1].peers[w] = nullptr; }
-  if (a.dy_peers && a.n_peers > 1) {
-    if (a.n_peers > 8) return LATTE_ERR_UNSUPPORTED;
-    p.prob[1].npeers = a.n_peers;
-    p.prob[1].rows_per_peer = a.n_all / a.n_peers;
-    for (int w = 0; w < a.n_peers; ++w) p.prob[1].peers[w] = a.dy_peers[w];
-  }
-  for (int mode = 0; mode < 2; ++mode)
-    for (int g = 0; g < 2; ++g) {
-      const int cnt = p.nhalf - 2 * g >= 2 ? 2 : (p.nhalf - 2 * g == 1 ? 1 : 0);
-      p.idesc[mode][g] = cnt ? make_idesc_f16(256, 2 * cnt * 64, 0u, mode, 1) : 0u;
+  // feature slabs of <= 512 accumulator columns (units of 128: 64 per CTA)
+  const int units128 = (int)((a.dim + 127) / 128);
+  const int nslab = (units128 + 3) / 4;
+  const int nproducts = a.x16 ? 2 : 1;
+  if (a.dy_peers && a.n_peers > 8) return LATTE_ERR_UNSUPPORTED;
+  p.nprob = 0;
+  int64_t total = 0;
+  for (int prod = 0; prod < nproducts; ++prod) {
+    int done = 0;
+    for (int sl = 0; sl < nslab; ++sl) {
+      const int nh = (units128 - done + (nslab - sl) - 1) / (nslab - sl);   // even split
+      GemmProblem& q = p.prob[p.nprob++];
+      q.product = prod;
+      q.d_off = done * 128;
+      q.nhalf = nh;
+      done += nh;
+      for (int g = 0; g < 2; ++g) {
+        const int cnt = nh - 2 * g >= 2 ? 2 : (nh - 2 * g == 1 ? 1 : 0);
+        q.idesc[g] = cnt ? make_idesc_f16(256, 2 * cnt * 64, 0u, prod, 1) : 0u;
+      }
+      q.scale = nullptr;
+      q.npeers = 0;
+      q.rows_per_peer = 1;
+      for (int w = 0; w < 8; ++w) q.peers[w] = nullptr;
+      if (prod == 0) {
+        // dX = G . Y : rows of this rank, contraction over all columns
+        q.mode = 0;
+        q.m_tiles = geo.row_blocks;
+        q.k_chunks = (int)((a.n_all + 63) / 64);
+        q.m_rows = a.n_loc;
+        q.out = a.dx32;
+        q.ld_out = a.ld32;
+      } else {
+        // dY = G^T . X : rows = columns of G, contraction over the rows of G
+        q.mode = 1;
+        q.m_tiles = geo.col_tiles / 2;
+        q.k_chunks = (int)((a.n_loc + 63) / 64);
+        q.m_rows = a.n_all;
+        q.out = a.dy32;
+        q.ld_out = a.ld_dy32;
+        q.scale = a.dy_scale;
+        if (a.dy_peers && a.n_peers > 1) {
+          q.npeers = a.n_peers;
+          q.rows_per_peer = a.n_all / a.n_peers;
+          for (int w = 0; w < a.n_peers; ++w) q.peers[w] = a.dy_peers[w];
+        }
+      }
+      total += (int64_t)q.m_tiles * q.k_chunks;
     }
-  int64_t total = (int64_t)p.prob[0].m_tiles * p.prob[0].k_chunks;
-  if (p.nprob > 1) total += (int64_t)p.prob[1].m_tiles * p.prob[1].k_chunks;
+  }
   int ncl = device_sm_count() / 2;
   if (total < ncl) ncl = (int)total;
   LATTE_CUDA_OK(cudaFuncSetAttribute(pair_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -203,7 +203,7 @@ class _FusedClipLoss(torch.autograd.Function):
          !local_loss & !gather_with_grad: grads = 1 x local slice of dL_global
          local_loss & !gather_with_grad : own-block terms only (gathered copies carry no grad)
 
-    Multi-rank, 16-bit features with dim <= 512 (every mode but the last): ONE logit sweep per
+    Multi-rank, 16-bit features with dim <= 768 (every mode but the last): ONE logit sweep per
     rank.  Forward: rows of this rank x all columns give the row LSEs and, from the same tiles,
     per-column (max, sum) partials; one all-gather of [2N + 3n] floats per rank merges them into
     every column's LSE.  Backward: one recompute sweep -> G[rows of this rank, :]; d_img is

@@ -56,7 +56,8 @@ def test_bad_arguments_are_rejected_without_a_gpu(lib):
                                    None, 0, None) == -1
     assert lib.latte_clip_rank_sweep_supported(1, 512) == 1      # bf16, dim 512
     assert lib.latte_clip_rank_sweep_supported(0, 512) == 0      # fp32 features: two-sweep path
-    assert lib.latte_clip_rank_sweep_supported(1, 768) == 0
+    assert lib.latte_clip_rank_sweep_supported(1, 768) == 1      # ViT-L/14 width
+    assert lib.latte_clip_rank_sweep_supported(1, 1024) == 0
 
 
 def test_product_path_has_no_cpu_fallback():

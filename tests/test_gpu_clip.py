@@ -274,7 +274,8 @@ def test_full_size_32k_properties():
 
 
 # ------------------------------------------------------------------ one logit sweep per rank
-@pytest.mark.parametrize("world,n,d,sigma", [(2, 512, 512, 4.0), (4, 300, 256, 4.0), (3, 130, 64, 3.0)])
+@pytest.mark.parametrize("world,n,d,sigma", [(2, 512, 512, 4.0), (4, 300, 256, 4.0), (3, 130, 64, 3.0),
+                                             (2, 600, 768, 5.0)])
 def test_one_sweep_per_rank_path_emulated_on_one_gpu(world, n, d, sigma):
     """latte_clip_fwd_rows / _fwd_cols / _bwd(partial) -- the multi-rank path of 16-bit features
     with dim <= 512 -- driven for every rank on one GPU: the column partials are stacked instead
@@ -386,7 +387,8 @@ def test_full_size_properties_32k(n, d):
     assert rel(di[rows], ref_di) < GRAD_RTOL_16
 
 
-@pytest.mark.parametrize("n,d", [(1, 8), (7, 24), (129, 40), (513, 72), (300, 504), (1000, 512), (257, 16)])
+@pytest.mark.parametrize("n,d", [(1, 8), (7, 24), (129, 40), (513, 72), (300, 504), (1000, 512), (257, 16),
+                                 (700, 768), (300, 640), (130, 520), (1100, 704)])
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
 def test_cta_pair_path_odd_shapes(n, d, dtype):
     """Edge shapes of the CTA-pair kernels (dim <= 512): a single row, ragged row blocks and
