@@ -206,6 +206,64 @@ def prototype_kernel_rates(dev, peaks, batch=N_GLOBAL, dim=DIM, classes=47):
     return {"batch": batch, "dim": dim, "classes": classes, "dtype": "f32", "rows": out}
 
 
+def latteclip_head_times(dev, batch=512, dim=512, classes=47, reps=20):
+    """One LatteCLIP head step (train.py:384-530: pseudo-labels, margins, mixture + EMA, two
+    ClipLoss calls sharing the image features, backward, bank update) at the reference's own
+    fine-tuning shape (BASELINE cfg2: batch 512, dim 512, 47 classes, quirk label broadcast), on
+    the GPU through latteclip_b200.prototypes, and the oracle port of the same step on the host
+    cores.  Extra information beside the headline metric."""
+    import latteclip_b200 as lb
+    from latteclip_b200 import prototypes as P
+    g = torch.Generator().manual_seed(77)
+    bank = F.normalize(torch.randn(classes, dim, generator=g), dim=1)
+    cls = F.normalize(bank + 0.3 * torch.randn(classes, dim, generator=g), dim=1)
+    true = torch.randint(0, classes, (batch,), generator=g)
+    mk = lambda s: F.normalize(bank[true] + s * torch.randn(batch, dim, generator=g) * 3 / dim ** 0.5, dim=1)
+    img, pimg, pgrp = mk(1.2), mk(0.9), mk(0.7)
+    zs = torch.randint(0, classes, (batch,), generator=g)
+    loss_fn = lb.ClipLoss(local_loss=True, gather_with_grad=True, cache_labels=True)
+    dimg, dcls, dpi, dpg = (x.to(dev).bfloat16().requires_grad_(True) for x in (img, cls, pimg, pgrp))
+    log_s = torch.tensor(math.log(SCALE), device=dev, requires_grad=True)
+    bank_d, snap_d, zs_d = bank.to(dev).clone(), bank.to(dev).clone(), zs.to(dev)
+
+    def step():
+        for x in (dimg, dcls, dpi, dpg, log_s):
+            x.grad = None
+        out = P.prototype_step(dimg, log_s.exp(), bank_d, snap_d, zs_d, dcls, dpi, dpg, loss_fn,
+                               alpha=0.01, label_weight_axis="quirk")
+        out["loss"].backward()
+        P.update_bank(bank_d, out["preds"], zs_d, out["t_ft"], out["t_zs"])
+
+    for _ in range(5):
+        step()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        step()
+    b.record()
+    torch.cuda.synchronize()
+    ours_ms = a.elapsed_time(b) / reps
+    import oracle
+    torch.set_num_threads(os.cpu_count() or 1)
+    ci, cc, cpi, cpg = (x.clone().requires_grad_(True) for x in (img, cls, pimg, pgrp))
+    cl = torch.tensor(math.log(SCALE), requires_grad=True)
+
+    def cpu_step():
+        out = oracle.prototype_step(ci, cl.exp(), bank.clone(), bank.clone(), zs, cc, cpi, cpg, alpha=0.01,
+                                    label_weight_axis="quirk")
+        out["loss"].backward()
+
+    cpu_step()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        cpu_step()
+    cpu_ms = (time.perf_counter() - t0) / 3 * 1e3
+    return {"workload": f"LatteCLIP head step, batch {batch}, dim {dim}, {classes} classes, bf16 features",
+            "ms_per_step": ours_ms, "samples_per_s": batch / (ours_ms * 1e-3),
+            "cpu_oracle_ms_per_step": cpu_ms, "cpu_cores": torch.get_num_threads()}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -428,6 +486,10 @@ def _run_ours(args):
     if rank == 0 and world == 1:
         proto = prototype_kernel_rates(dev, peaks)
 
+    head = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        head = latteclip_head_times(dev)
+
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu_base, _ = cpu_reference_sample(2, 1, target_s=12.0)
@@ -457,6 +519,8 @@ def _run_ours(args):
             line["cpu_baseline"] = cpu_base
         if proto is not None:
             line["prototype_kernels"] = proto
+        if head is not None:
+            line["latteclip_head"] = head
     else:
         line = None
     if world > 1:
