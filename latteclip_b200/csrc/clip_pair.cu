@@ -97,7 +97,7 @@ constexpr int kModeGrad = 0;      // backward: gradient weights G
 constexpr int kModeFwdRows = 1;   // forward: row log-sum-exp partials
 constexpr int kModeFwdBoth = 2;   // forward, world size 1: row partials + column partials of the same tile
 
-template <int MODE>
+template <int MODE, bool TAIL>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kSweepThreads, 1)
 pair_sweep_kernel(const __grid_constant__ CUtensorMap tmy, const __grid_constant__ CUtensorMap tmg,
                   const __grid_constant__ CUtensorMap tmx, const SweepParams p) {
@@ -138,7 +138,8 @@ pair_sweep_kernel(const __grid_constant__ CUtensorMap tmy, const __grid_constant
 
   // ring stages of cps chunks; with dim > 512 the X columns beyond the TMEM-resident 512 live in
   // the upper half of the ring area and their MMAs take A from shared memory ("SS" form)
-  const uint32_t ring_stage_bytes = (uint32_t)p.cps * kYChunkBytes;
+  constexpr int kCps = TAIL ? 2 : kChunksPerStage;      // compile-time for the issue loops
+  constexpr uint32_t ring_stage_bytes = (uint32_t)kCps * kYChunkBytes;
   const uint32_t xtail = ring + kXTailOffset;
 
   if (warp == 0 && elect_one()) {
@@ -180,7 +181,7 @@ pair_sweep_kernel(const __grid_constant__ CUtensorMap tmy, const __grid_constant
       const uint32_t lead_xt = mapa_rank(bar_xt, 0);
       int ct = ct0, rb_i = rb0;
       for (int it = 0; it < ntile; ++it) {
-        if (p.tail_chunks > 0 && (it == 0 || ct == 0)) {
+        if (TAIL && (it == 0 || ct == 0)) {
           // new row block: its X tail replaces the previous one once every MMA of the
           // previous block is done (tfull of its last tile)
           if (it > 0) {
@@ -192,8 +193,8 @@ pair_sweep_kernel(const __grid_constant__ CUtensorMap tmy, const __grid_constant
             tma_load_2d_pair_hint(xtail + j * kXTailBytes, &tmx, lead_xt, (kTmemChunks + j) * kBK,
                                   rb_i * 256 + (int)rank * kPM, keep);
         }
-        for (int c0 = 0; c0 < p.kch; c0 += p.cps) {
-          const int nc = min(p.cps, p.kch - c0);
+        for (int c0 = 0; c0 < p.kch; c0 += kCps) {
+          const int nc = min(kCps, p.kch - c0);
           mbar_wait(bar_empty + 8 * stage, phase ^ 1);
           if (rank == 0) mbar_arrive_expect_tx(bar_full + 8 * stage, 2 * nc * kYChunkBytes);
           for (int c = 0; c < nc; ++c)
@@ -214,7 +215,7 @@ pair_sweep_kernel(const __grid_constant__ CUtensorMap tmy, const __grid_constant
       for (int it = 0; it < ntile; ++it) {
         if (it == 0 || ct == 0) {          // first tile of a row block: wait for its X block
           mbar_wait(bar_aready, a_phase);
-          if (p.tail_chunks > 0) mbar_wait(bar_xt, a_phase);
+          if (TAIL) mbar_wait(bar_xt, a_phase);
           a_phase ^= 1;
         }
         ct = (ct + 1 == p.col_tiles) ? 0 : ct + 1;
@@ -222,27 +223,30 @@ pair_sweep_kernel(const __grid_constant__ CUtensorMap tmy, const __grid_constant
         mbar_wait(bar_tempty + 8 * buf, ((it >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_s + buf * kTN;
-        for (int c0 = 0; c0 < p.kch; c0 += p.cps) {
-          const int nc = min(p.cps, p.kch - c0);
+        for (int c0 = 0; c0 < p.kch; c0 += kCps) {
+          const int nc = min(kCps, p.kch - c0);
           mbar_wait(bar_full + 8 * stage, phase);
           tc_fence_after();
           // descriptor of the stage base; the start-address field counts 16-byte units
           const uint64_t db0 = make_smem_desc_sw128(ring + stage * ring_stage_bytes, 16, 1024);
-          for (int c = 0; c < nc; ++c) {
-            const int gc = c0 + c;
-            if (gc < kTmemChunks) {
 #pragma unroll
-              for (int k = 0; k < kBK / 16; ++k) {
-                const uint64_t db = db0 + (uint64_t)((c * kYChunkBytes + k * 32) >> 4);
-                mma2_ts(tmem_d, tmem_a + gc * 32 + k * 8, db, p.idesc, (gc | k) != 0);
-              }
-            } else {
-              const uint64_t da0 =
-                  make_smem_desc_sw128(xtail + (gc - kTmemChunks) * kXTailBytes, 16, 1024);
+          for (int c = 0; c < kCps; ++c) {
+            if (c < nc) {
+              const int gc = c0 + c;
+              if (!TAIL || gc < kTmemChunks) {
 #pragma unroll
-              for (int k = 0; k < kBK / 16; ++k) {
-                const uint64_t db = db0 + (uint64_t)((c * kYChunkBytes + k * 32) >> 4);
-                mma2_ss(tmem_d, da0 + (uint64_t)(k * 2), db, p.idesc, 1u);
+                for (int k = 0; k < kBK / 16; ++k) {
+                  const uint64_t db = db0 + (uint64_t)((c * kYChunkBytes + k * 32) >> 4);
+                  mma2_ts(tmem_d, tmem_a + gc * 32 + k * 8, db, p.idesc, (gc | k) != 0);
+                }
+              } else {
+                const uint64_t da0 =
+                    make_smem_desc_sw128(xtail + (gc - kTmemChunks) * kXTailBytes, 16, 1024);
+#pragma unroll
+                for (int k = 0; k < kBK / 16; ++k) {
+                  const uint64_t db = db0 + (uint64_t)((c * kYChunkBytes + k * 32) >> 4);
+                  mma2_ss(tmem_d, da0 + (uint64_t)(k * 2), db, p.idesc, 1u);
+                }
               }
             }
           }
@@ -403,6 +407,15 @@ pair_sweep_kernel(const __grid_constant__ CUtensorMap tmy, const __grid_constant
             int want = -1;
             if (row_ok && label >= col0 + h * 32 && label < col0 + h * 32 + 32)
               want = (int)(label - col0) - h * 32;
+            // label entry: P - 1 = expm1(-nll), no cancellation when the label dominates
+            const bool have_nll = p.nll_a != nullptr;
+            float g_lab = 0.f, dw_lab = 0.f;
+            if (want >= 0 && have_nll) {
+              const float pa1 = expm1f(-__ldg(p.nll_a + label)) * gscale;
+              const float pb1 = expm1f(-__ldg(p.nll_b + label)) * gscale;
+              g_lab = fmaf(cb, pb1, pa1);
+              dw_lab = fmaf(ds_cb, pb1, pa1);
+            }
             const float4* pb = reinterpret_cast<const float4*>(p.lse_b2 + col0) + h * 8;
 #pragma unroll
             for (int i4 = 0; i4 < 8; ++i4) {
@@ -419,12 +432,9 @@ pair_sweep_kernel(const __grid_constant__ CUtensorMap tmy, const __grid_constant
                 float dw = fmaf(ds_cb, eb, ea);
                 g[x] = fmaf(cb, eb, ea);
                 if (i == want) {
-                  if (p.nll_a != nullptr) {
-                    // P - 1 = expm1(-nll): no cancellation when the label dominates
-                    const float pa1 = expm1f(-__ldg(p.nll_a + label)) * gscale;
-                    const float pb1 = expm1f(-__ldg(p.nll_b + label)) * gscale;
-                    g[x] = fmaf(cb, pb1, pa1);
-                    dw = fmaf(ds_cb, pb1, pa1);
+                  if (have_nll) {
+                    g[x] = g_lab;
+                    dw = dw_lab;
                   } else {
                     g[x] -= cd_scaled;
                     dw -= ds_cd_scaled;
@@ -893,6 +903,28 @@ int make_map16(CUtensorMap* map, const void* base, int dtype, int64_t rows, int6
 
 }  // namespace
 
+namespace {
+template <int MODE, bool TAIL>
+int launch_sweep_t(int grid, cudaStream_t stream, const CUtensorMap& tmy, const CUtensorMap& tmg,
+                   const CUtensorMap& tmx, const SweepParams& p) {
+  LATTE_CUDA_OK(cudaFuncSetAttribute(pair_sweep_kernel<MODE, TAIL>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, kSweepSmem));
+  pair_sweep_kernel<MODE, TAIL><<<grid, kSweepThreads, kSweepSmem, stream>>>(tmy, tmg, tmx, p);
+  return LATTE_OK;
+}
+int launch_sweep(int mode, bool tail, int grid, cudaStream_t stream, const CUtensorMap& tmy,
+                 const CUtensorMap& tmg, const CUtensorMap& tmx, const SweepParams& p) {
+  if (mode == kModeGrad)
+    return tail ? launch_sweep_t<kModeGrad, true>(grid, stream, tmy, tmg, tmx, p)
+                : launch_sweep_t<kModeGrad, false>(grid, stream, tmy, tmg, tmx, p);
+  if (mode == kModeFwdBoth)
+    return tail ? launch_sweep_t<kModeFwdBoth, true>(grid, stream, tmy, tmg, tmx, p)
+                : launch_sweep_t<kModeFwdBoth, false>(grid, stream, tmy, tmg, tmx, p);
+  return tail ? launch_sweep_t<kModeFwdRows, true>(grid, stream, tmy, tmg, tmx, p)
+              : launch_sweep_t<kModeFwdRows, false>(grid, stream, tmy, tmg, tmx, p);
+}
+}  // namespace
+
 bool clip_pair_supported(int dtype, int64_t dim, int64_t ldx, int64_t ldy, const void* x,
                          const void* y) {
   if (dtype != LATTE_BF16 && dtype != LATTE_F16) return false;
@@ -950,15 +982,9 @@ int clip_pair_fwd_sweep(const PairFwdArgs& a, cudaStream_t stream) {
   p.row_blocks = f.row_blocks;
   p.ncb = f.col_tiles * 2;
   p.idesc = make_idesc_f16(256, kTN, a.dtype == LATTE_BF16 ? 1u : 0u, 0, 0);
-  if (a.col_part) {
-    LATTE_CUDA_OK(cudaFuncSetAttribute(pair_sweep_kernel<kModeFwdBoth>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, kSweepSmem));
-    pair_sweep_kernel<kModeFwdBoth><<<2 * f.ncl, kSweepThreads, kSweepSmem, stream>>>(tmy, tmy, tmx, p);
-  } else {
-    LATTE_CUDA_OK(cudaFuncSetAttribute(pair_sweep_kernel<kModeFwdRows>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, kSweepSmem));
-    pair_sweep_kernel<kModeFwdRows><<<2 * f.ncl, kSweepThreads, kSweepSmem, stream>>>(tmy, tmy, tmx, p);
-  }
+  rc = launch_sweep(a.col_part ? kModeFwdBoth : kModeFwdRows, p.tail_chunks > 0, 2 * f.ncl, stream,
+                    tmy, tmy, tmx, p);
+  if (rc) return rc;
   LATTE_LAUNCH_OK();
   return LATTE_OK;
 }
@@ -1000,10 +1026,9 @@ int clip_pair_sweep(const PairSweepArgs& a, cudaStream_t stream) {
   int ncl = device_sm_count() / 2;
   const int64_t total = (int64_t)geo.row_blocks * geo.col_tiles;
   if (total < ncl) ncl = (int)total;
-  LATTE_CUDA_OK(cudaFuncSetAttribute(pair_sweep_kernel<kModeGrad>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, kSweepSmem));
   // every CTA of the launch writes its ds partial; unused slots are zeroed by the caller
-  pair_sweep_kernel<kModeGrad><<<2 * ncl, kSweepThreads, kSweepSmem, stream>>>(tmy, tmg, tmx, p);
+  rc = launch_sweep(kModeGrad, p.tail_chunks > 0, 2 * ncl, stream, tmy, tmg, tmx, p);
+  if (rc) return rc;
   LATTE_LAUNCH_OK();
   return LATTE_OK;
 }
