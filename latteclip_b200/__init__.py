@@ -9,6 +9,7 @@ pipeline and training driver remain the reference's PyTorch code.
 
 from .loss import ClipLoss, create_loss, gather_features  # noqa: F401
 from . import prototypes  # noqa: F401
-from ._lib import build, version  # noqa: F401
+from ._lib import build, version, clear_workspace_cache  # noqa: F401
 
-__all__ = ["ClipLoss", "create_loss", "gather_features", "prototypes", "build", "version"]
+__all__ = ["ClipLoss", "create_loss", "gather_features", "prototypes", "build", "version",
+           "clear_workspace_cache"]

@@ -250,6 +250,11 @@ def _cached_workspace(key, nbytes_fn, device):
     return ws
 
 
+def clear_workspace_cache():
+    """Drop the cached scratch buffers (e.g. 2 GiB of gradient weights at batch 32768)."""
+    _WS_CACHE.clear()
+
+
 def clip_fwd_rows(img_loc, txt_all, label_offset: int, logit_scale):
     """Step 1 of the multi-rank forward -> packed fp32 payload [2 n_all + 3 n_loc]:
     col_ml [n_all, 2] | row_lse | row_nll | label_logit  (what the ranks all-gather)."""

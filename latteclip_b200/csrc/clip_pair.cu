@@ -534,9 +534,9 @@ pair_sweep_kernel(const __grid_constant__ CUtensorMap tmy, const __grid_constant
           }
           float tmax0 = -INFINITY, tmax1 = -INFINITY;
 #pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            tmax0 = fmaxf(tmax0, __uint_as_float(r[i]));
-            tmax1 = fmaxf(tmax1, __uint_as_float(r[i + 1]));
+          for (int i = 0; i < 32; i += 4) {
+            tmax0 = fmax3(tmax0, __uint_as_float(r[i]), __uint_as_float(r[i + 1]));
+            tmax1 = fmax3(tmax1, __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3]));
           }
           const float m_new = fmaxf(m, fmaxf(tmax0, tmax1) * c2);
           if (m_new > -INFINITY) {

@@ -354,6 +354,12 @@ __host__ __device__ constexpr uint32_t make_idesc_ab(uint32_t m, uint32_t n, uin
          (b_mn_major << 16) | ((n >> 3) << 17) | ((m >> 4) << 24);
 }
 
+// three-input maximum (one FMNMX3 on sm_100)
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
 __device__ __forceinline__ float fast_exp2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));

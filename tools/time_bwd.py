@@ -28,4 +28,4 @@ for _ in range(reps):
     _lib.clip_bwd(i, t, i, t, 0, sc, row, col, one, 1.0, True)
 e[2].record()
 torch.cuda.synchronize()
-print(f"LATTE_EXP={os.environ.get('LATTE_EXP','0')} fwd {e[0].elapsed_time(e[1])/reps:.3f} ms  bwd {e[1].elapsed_time(e[2])/reps:.3f} ms")
+print(f"n={n} d={d}: fwd {e[0].elapsed_time(e[1])/reps:.3f} ms  bwd {e[1].elapsed_time(e[2])/reps:.3f} ms")
