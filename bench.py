@@ -206,7 +206,7 @@ def prototype_kernel_rates(dev, peaks, batch=N_GLOBAL, dim=DIM, classes=47):
     return {"batch": batch, "dim": dim, "classes": classes, "dtype": "f32", "rows": out}
 
 
-def latteclip_head_times(dev, batch=512, dim=512, classes=47, reps=20):
+def latteclip_head_times(dev, batch=512, dim=512, classes=47, reps=20, axis="quirk", cpu=True):
     """One LatteCLIP head step (train.py:384-530: pseudo-labels, margins, mixture + EMA, two
     ClipLoss calls sharing the image features, backward, bank update) at the reference's own
     fine-tuning shape (BASELINE cfg2: batch 512, dim 512, 47 classes, quirk label broadcast), on
@@ -230,7 +230,7 @@ def latteclip_head_times(dev, batch=512, dim=512, classes=47, reps=20):
         for x in (dimg, dcls, dpi, dpg, log_s):
             x.grad = None
         out = P.prototype_step(dimg, log_s.exp(), bank_d, snap_d, zs_d, dcls, dpi, dpg, loss_fn,
-                               alpha=0.01, label_weight_axis="quirk")
+                               alpha=0.01, label_weight_axis=axis)
         out["loss"].backward()
         P.update_bank(bank_d, out["preds"], zs_d, out["t_ft"], out["t_zs"])
 
@@ -244,6 +244,11 @@ def latteclip_head_times(dev, batch=512, dim=512, classes=47, reps=20):
     b.record()
     torch.cuda.synchronize()
     ours_ms = a.elapsed_time(b) / reps
+    res = {"workload": f"LatteCLIP head step, batch {batch}, dim {dim}, {classes} classes, bf16 features, "
+                       f"label_weight_axis={axis}",
+           "ms_per_step": ours_ms, "samples_per_s": batch / (ours_ms * 1e-3)}
+    if not cpu:
+        return res
     import oracle
     torch.set_num_threads(os.cpu_count() or 1)
     ci, cc, cpi, cpg = (x.clone().requires_grad_(True) for x in (img, cls, pimg, pgrp))
@@ -251,7 +256,7 @@ def latteclip_head_times(dev, batch=512, dim=512, classes=47, reps=20):
 
     def cpu_step():
         out = oracle.prototype_step(ci, cl.exp(), bank.clone(), bank.clone(), zs, cc, cpi, cpg, alpha=0.01,
-                                    label_weight_axis="quirk")
+                                    label_weight_axis=axis)
         out["loss"].backward()
 
     cpu_step()
@@ -259,9 +264,8 @@ def latteclip_head_times(dev, batch=512, dim=512, classes=47, reps=20):
     for _ in range(3):
         cpu_step()
     cpu_ms = (time.perf_counter() - t0) / 3 * 1e3
-    return {"workload": f"LatteCLIP head step, batch {batch}, dim {dim}, {classes} classes, bf16 features",
-            "ms_per_step": ours_ms, "samples_per_s": batch / (ours_ms * 1e-3),
-            "cpu_oracle_ms_per_step": cpu_ms, "cpu_cores": torch.get_num_threads()}
+    res.update(cpu_oracle_ms_per_step=cpu_ms, cpu_cores=torch.get_num_threads())
+    return res
 
 
 def run_reference(args):
@@ -486,9 +490,10 @@ def _run_ours(args):
     if rank == 0 and world == 1:
         proto = prototype_kernel_rates(dev, peaks)
 
-    head = None
+    head = head_big = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         head = latteclip_head_times(dev)
+        head_big = latteclip_head_times(dev, batch=N_GLOBAL, reps=5, axis="row", cpu=False)
 
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -521,6 +526,7 @@ def _run_ours(args):
             line["prototype_kernels"] = proto
         if head is not None:
             line["latteclip_head"] = head
+            line["latteclip_head_32k"] = head_big
     else:
         line = None
     if world > 1:

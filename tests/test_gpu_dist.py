@@ -16,8 +16,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 
 
-def _worker(rank, world, port, n, d, dtype_name, ret):
+def _worker(rank, world, port, n, d, dtype_name, p2p, ret):
     sys.path.insert(0, ROOT)
+    os.environ["LATTE_B200_NO_P2P"] = "0" if p2p else "1"
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -52,8 +53,12 @@ def _worker(rank, world, port, n, d, dtype_name, ret):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("dtype_name,n,d", [("bfloat16", 512, 512), ("float32", 96, 64)])
-def test_nccl_cliploss_matches_oracle(dtype_name, n, d):
+@pytest.mark.parametrize("dtype_name,n,d,p2p", [("bfloat16", 512, 512, True), ("bfloat16", 512, 512, False),
+                                                 ("bfloat16", 300, 768, True), ("float32", 96, 64, True)])
+def test_nccl_cliploss_matches_oracle(dtype_name, n, d, p2p):
+    """p2p=True: feature gather and text-gradient reduce-scatter through peer-mapped buffers
+    (latte_push_shards, fused GEMM + reduce-scatter); p2p=False: the same one-sweep flow over
+    NCCL all-gather / reduce-scatter.  fp32 features take the two-sweep flow."""
     world = min(torch.cuda.device_count(), 4)
     if world < 2:
         pytest.skip("needs >= 2 GPUs")
@@ -61,7 +66,8 @@ def test_nccl_cliploss_matches_oracle(dtype_name, n, d):
     from oracle.clip_loss import clip_loss_all_ranks
     mgr = mp.Manager()
     ret = mgr.dict()
-    mp.spawn(_worker, args=(world, 29801 + n % 7, n, d, dtype_name, ret), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, 29801 + n % 7 + 10 * int(p2p) + d % 5, n, d, dtype_name, p2p, ret),
+             nprocs=world, join=True)
     dtype = getattr(torch, dtype_name)
     g = torch.Generator().manual_seed(123)
     i_all = F.normalize(torch.randn(n * world, d, generator=g), dim=1)
