@@ -30,7 +30,8 @@ def _worker(rank, world, port, n, d, dtype_name, p2p, ret):
     dtype = getattr(torch, dtype_name)
     g = torch.Generator().manual_seed(123)
     i_all = F.normalize(torch.randn(n * world, d, generator=g), dim=1)
-    t_all = F.normalize(i_all + 3.0 * torch.randn(n * world, d, generator=g) / math.sqrt(d), dim=1)
+    sigma = 3.0 if d <= 512 else 6.0      # keep the loss away from full convergence
+    t_all = F.normalize(i_all + sigma * torch.randn(n * world, d, generator=g) / math.sqrt(d), dim=1)
     out = {}
     for local_loss, gwg in ((True, True), (True, False), (False, True), (False, False)):
         il = i_all[rank * n:(rank + 1) * n].to(dev).to(dtype).requires_grad_(True)
@@ -71,7 +72,8 @@ def test_nccl_cliploss_matches_oracle(dtype_name, n, d, p2p):
     dtype = getattr(torch, dtype_name)
     g = torch.Generator().manual_seed(123)
     i_all = F.normalize(torch.randn(n * world, d, generator=g), dim=1)
-    t_all = F.normalize(i_all + 3.0 * torch.randn(n * world, d, generator=g) / math.sqrt(d), dim=1)
+    sigma = 3.0 if d <= 512 else 6.0
+    t_all = F.normalize(i_all + sigma * torch.randn(n * world, d, generator=g) / math.sqrt(d), dim=1)
     ir, tr = i_all.to(dtype).float(), t_all.to(dtype).float()
     ish = [ir[r * n:(r + 1) * n] for r in range(world)]
     tsh = [tr[r * n:(r + 1) * n] for r in range(world)]
