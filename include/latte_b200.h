@@ -184,11 +184,12 @@ int latte_clip_bwd(const void* img_loc, int64_t ld_img_loc,
  * buffer [2][n_all, dim] mapped into this process (torch symmetric memory); the text matrix
  * starts tensor_stride_bytes after the image matrix.  The caller brackets the call with
  * cross-rank barriers (before: readers of the previous contents are done; after: all shards
- * have landed).
+ * have landed).  multicast_base (nullable): the NVSwitch multicast mapping of the same buffer;
+ * when given, every vector is stored once with multimem.st and the switch replicates it.
  */
 int latte_push_shards(const void* img_shard, const void* txt_shard, int64_t shard_bytes,
                       void* const* peer_bases, int n_peers, int rank,
-                      int64_t tensor_stride_bytes, void* stream);
+                      int64_t tensor_stride_bytes, void* multicast_base, void* stream);
 
 /*
  * Diagnostic for bench.py: runs latte_clip_fwd then latte_clip_bwd `reps` times on `stream`

@@ -77,7 +77,7 @@ def _declare(lib):
     lib.latte_clip_stage_times.argtypes = [vp, i64, vp, i64, vp, i64, vp, i64, i32, i64, i64, i64, i64,
                                            vp, vp, vp, vp, vp, vp, vp, f32, i32, vp, vp, i32, i64,
                                            vp, vp, vp, sz, vp, sz, vp, i32, c.POINTER(f32)]
-    lib.latte_push_shards.argtypes = [vp, vp, i64, vp, i32, i32, i64, vp]
+    lib.latte_push_shards.argtypes = [vp, vp, i64, vp, i32, i32, i64, vp, vp]
     lib.latte_normalize_rows.argtypes = [vp, i64, vp, i64, i64, i64, vp]
     lib.latte_nxc_argmax_margin.argtypes = [vp, i64, i32, vp, i64, i64, vp, i64, i64, f32,
                                             vp, vp, vp, vp]
@@ -212,8 +212,10 @@ def clip_fwd(img_loc, txt_loc, img_all, txt_all, label_offset: int, logit_scale,
     return row_lse, col_lse, loss
 
 
-def push_shards(img_shard, txt_shard, peer_ptrs, rank: int, tensor_stride_bytes: int):
-    """Write this rank's feature shards into every rank's peer-mapped gathered buffer."""
+def push_shards(img_shard, txt_shard, peer_ptrs, rank: int, tensor_stride_bytes: int,
+                multicast_ptr: int = 0):
+    """Write this rank's feature shards into every rank's peer-mapped gathered buffer (through
+    the NVSwitch multicast mapping when ``multicast_ptr`` is given)."""
     lib = load()
     img_shard, txt_shard = _rows(img_shard, "image_features"), _rows(txt_shard, "text_features")
     if not (img_shard.is_contiguous() and txt_shard.is_contiguous()):
@@ -222,7 +224,8 @@ def push_shards(img_shard, txt_shard, peer_ptrs, rank: int, tensor_stride_bytes:
     peers = (ctypes.c_void_p * len(peer_ptrs))(*peer_ptrs)
     with torch.cuda.device(img_shard.device):
         _check(lib.latte_push_shards(_ptr(img_shard), _ptr(txt_shard), nbytes, peers, len(peer_ptrs),
-                                     int(rank), int(tensor_stride_bytes), _stream(img_shard)),
+                                     int(rank), int(tensor_stride_bytes),
+                                     ctypes.c_void_p(int(multicast_ptr) or None), _stream(img_shard)),
                "latte_push_shards")
 
 

@@ -440,6 +440,25 @@ push_shards_kernel(const uint4* img, const uint4* txt, int64_t shard_vecs, int64
   }
 }
 
+// Same gather through the NVSwitch multicast mapping of the gathered buffer: ONE store per
+// vector lands in every rank's copy (multimem.st), so a rank sends its shard once instead of
+// once per peer.
+__global__ void __launch_bounds__(256)
+push_shards_multicast_kernel(const uint4* img, const uint4* txt, int64_t shard_vecs,
+                             int64_t tensor_vecs, int64_t rank_off_vecs, uint4* mc_base) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < 2 * shard_vecs; v += stride) {
+    const bool is_txt = v >= shard_vecs;
+    const int64_t k = is_txt ? v - shard_vecs : v;
+    const uint4 val = is_txt ? __ldg(txt + k) : __ldg(img + k);
+    uint4* dst = mc_base + (is_txt ? tensor_vecs : 0) + rank_off_vecs + k;
+    asm volatile("multimem.st.weak.global.v4.f32 [%0], {%1, %2, %3, %4};"
+                 ::"l"(dst), "f"(__uint_as_float(val.x)), "f"(__uint_as_float(val.y)),
+                   "f"(__uint_as_float(val.z)), "f"(__uint_as_float(val.w))
+                 : "memory");
+  }
+}
+
 struct WsLayout {
   size_t part;      // floats per partial array (kMaxParts * n_loc)
   size_t off_pmax_r, off_psum_r, off_diag_r, off_pmax_c, off_psum_c, off_diag_c;
@@ -1111,7 +1130,7 @@ extern "C" int latte_clip_stage_times(const void* img_loc, int64_t ld_img_loc, c
 
 extern "C" int latte_push_shards(const void* img_shard, const void* txt_shard, int64_t shard_bytes,
                                  void* const* peer_bases, int n_peers, int rank,
-                                 int64_t tensor_stride_bytes, void* stream) {
+                                 int64_t tensor_stride_bytes, void* multicast_base, void* stream) {
   LATTE_CHECK_ARG(img_shard && txt_shard && peer_bases && n_peers >= 1 && n_peers <= 8);
   LATTE_CHECK_ARG(rank >= 0 && rank < n_peers && shard_bytes > 0 && (shard_bytes % 16) == 0);
   LATTE_CHECK_ARG((tensor_stride_bytes % 16) == 0 && tensor_stride_bytes >= shard_bytes * n_peers);
@@ -1125,6 +1144,14 @@ extern "C" int latte_push_shards(const void* img_shard, const void* txt_shard, i
   const int64_t shard_vecs = shard_bytes / 16;
   int64_t blocks = (2 * shard_vecs + 255) / 256;
   if (blocks > 4 * device_sm_count()) blocks = 4 * device_sm_count();
+  if (multicast_base) {
+    LATTE_CHECK_ARG((reinterpret_cast<uintptr_t>(multicast_base) & 15) == 0);
+    push_shards_multicast_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const uint4*>(img_shard), static_cast<const uint4*>(txt_shard), shard_vecs,
+        tensor_stride_bytes / 16, (int64_t)rank * shard_vecs, static_cast<uint4*>(multicast_base));
+    LATTE_LAUNCH_OK();
+    return LATTE_OK;
+  }
   push_shards_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const uint4*>(img_shard), static_cast<const uint4*>(txt_shard), shard_vecs,
       tensor_stride_bytes / 16, (int64_t)rank * shard_vecs, p[0], p[1], p[2], p[3], p[4], p[5], p[6],
