@@ -1,20 +1,26 @@
-// ClipLoss backward on CTA pairs (tcgen05 cta_group::2), bf16 / fp16 features, dim <= 768.
+// ClipLoss on CTA pairs (tcgen05 cta_group::2), bf16 / fp16 features, dim <= 768.
 //
-// Replaces the autograd of open_clip/loss.py:109-116 + 126-129 with three kernels that
-// execute 6*n*N*D FLOP for the 4*n*N*D credited to the backward (one logit recompute, no
+// Replaces open_clip/loss.py:109-116 + 126-129 and their autograd with kernels that execute
+// 8*n*N*D FLOP for the 6*n*N*D credited to forward + backward (one logit sweep each way, no
 // feature-slab recompute as in clip_tc.cu):
 //
-//   pair_sweep_kernel<Grad>: persistent CTA pairs sweep tiles of S = X . Y^T (256 x 128 per
-//       pair).  The X row block lives in TMEM as the A operand (tcgen05.mma "TS" form, so
-//       shared memory only streams Y), S accumulates in a double-buffered TMEM tile, the
-//       epilogue warps turn it into the gradient weights
-//           G_ij = 2^13 * ( exp(S_ij - lseA_i) + cb * exp(S_ij - lseB_j) - cd * [j == label_i] )
-//       (fp16) and TMA-store them as 16 KB blocks [128 rows x 64 cols].  The logits are never
-//       stored; G is a scratch of the backward only.
-//   pair_gemm_kernel       : dX += G . Y (A K-major) and, for world size 1, dY += G^T . X
-//       (A MN-major, same G) as ONE persistent stream-K launch: 256 x 512 tiles per pair
-//       fill TMEM, partial tiles are reduced with red.global.add.v4.f32.
-//   grad_scale_cast_kernel : coef * s * 2^-13 * acc -> gradient dtype.
+//   pair_sweep_kernel<Mode, Tail> : persistent CTA pairs sweep tiles of S = X . Y^T (256 x 128
+//       per pair).  The X row block lives in TMEM as the A operand (tcgen05.mma "TS" form, so
+//       shared memory only streams Y; with dim > 512 the columns beyond 512 stay in shared
+//       memory and use the "SS" form), S accumulates in a double-buffered TMEM tile, and two
+//       ping-pong groups of eight epilogue warps consume it:
+//         FwdRows / FwdBoth : flash-style online (max, sum) per row and, for FwdBoth, the column
+//           sums of the SAME exponentials (rows re-weighted to a warp reference, 32 lanes added
+//           with a halving butterfly) -- S is computed once for both cross-entropies;
+//         Grad : the gradient weights
+//           G_ij = 2^gs * ( exp(S_ij - lseA_i) + cb * exp(S_ij - lseB_j) - cd * [j == label_i] )
+//           with one ex2 per logit (rank-one column factors), fp16, TMA-stored as 16 KB blocks
+//           [128 rows x 64 cols].  The logits are never stored; G is a scratch of the backward.
+//   pair_gemm_kernel       : dX += G . Y (A K-major) and dY += G^T . X (A MN-major, same G) as
+//       ONE persistent stream-K launch: 256 x 512 tiles per pair fill TMEM, partial tiles are
+//       reduced with red.global.add.v4.f32 -- for several ranks straight into the owner rank's
+//       peer-mapped accumulator (fused reduce-scatter over NVLink).
+//   grad_scale_cast_kernel : out_scale * acc -> gradient dtype.
 #include "latte_common.cuh"
 #include "tc_ptx.cuh"
 
