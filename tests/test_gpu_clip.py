@@ -275,7 +275,7 @@ def test_full_size_32k_properties():
 
 # ------------------------------------------------------------------ one logit sweep per rank
 @pytest.mark.parametrize("world,n,d,sigma", [(2, 512, 512, 4.0), (4, 300, 256, 4.0), (3, 130, 64, 3.0),
-                                             (2, 600, 768, 5.0)])
+                                             (2, 600, 768, 5.0), (2, 65, 128, 3.0)])
 def test_one_sweep_per_rank_path_emulated_on_one_gpu(world, n, d, sigma):
     """latte_clip_fwd_rows / _fwd_cols / _bwd(partial) -- the multi-rank path of 16-bit features
     with dim <= 512 -- driven for every rank on one GPU: the column partials are stacked instead
