@@ -503,6 +503,14 @@ def _run_ours(args):
     # finalize, column finalize (+ column merge at N > 1), gated fallback sweep + merge, loss
     # partial + reduce; backward: feature prep, LSE range + vectors, sweep, GEMM, cast, ds reduce.
     launches_per_step = 14 if world == 1 else 15
+    bwd_mode = "one recompute sweep"
+    if world > 1:
+        from latteclip_b200.loss import _bwd_sweeps
+        if _bwd_sweeps(world) == 2:
+            launches_per_step += 2       # second sweep + its GEMM
+            bwd_mode = "rows and columns recomputed per rank, no gradient exchange"
+        else:
+            bwd_mode = "one recompute sweep per rank, text gradient reduce-scattered inside the GEMM"
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -514,7 +522,7 @@ def _run_ours(args):
                             f"local_loss + gather_with_grad, {n_loc} rows per rank",
                 "global_batch": N_GLOBAL, "dim": DIM, "rows_per_rank": n_loc,
                 "l2": "rotating 4 input sets (256 MiB at N=1) larger than the 126 MiB L2",
-                "loss": last_loss,
+                "loss": last_loss, "backward": bwd_mode,
             },
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches_per_step * args.steps,

@@ -15,6 +15,8 @@ the CUDA extension (C ABI in include/latte_b200.h) through ``latteclip_b200._lib
 
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.nn as nn
 
@@ -120,10 +122,18 @@ def _reduce_scatter_sum(x: torch.Tensor, n: int, rank: int, group=None) -> torch
 _PEER_ACC = {}
 
 
+def _bwd_sweeps(world_size: int) -> int:
+    """Recompute sweeps per rank in the multi-rank backward: 1 = rows only, the text-side product
+    is reduce-scattered; 2 = rows and columns, nothing is exchanged.  LATTE_B200_BWD_SWEEPS overrides."""
+    env = os.environ.get("LATTE_B200_BWD_SWEEPS", "")
+    if env in ("1", "2"):
+        return int(env)
+    return 2 if world_size >= 8 else 1
+
+
 def _peer_accumulator(n: int, dim: int, device, group):
     """-> (acc [n, dim] fp32, symmetric-memory handle) or None when peer mapping is unavailable
     (non-NCCL backend, no P2P, LATTE_B200_NO_P2P=1); rendezvous happens once per shape."""
-    import os
     if os.environ.get("LATTE_B200_NO_P2P") == "1" or device.type != "cuda":
         return None
     key = (n, dim, device.index, id(group))
@@ -160,7 +170,6 @@ class _GatherSlot:
     def __init__(self, buf, hdl):
         self.buf, self.hdl = buf, hdl
         self.ptrs = [int(p) for p in hdl.buffer_ptrs]
-        import os
         mc = 0
         # NVSwitch multicast stores (multimem.st): measured no faster than per-peer stores at
         # 4 ranks (1.129 vs 1.116 ms/step), so opt-in
@@ -174,7 +183,6 @@ class _GatherSlot:
 
 
 def _acquire_gather_slot(n: int, dim: int, dtype, device, group, world: int):
-    import os
     if os.environ.get("LATTE_B200_NO_P2P") == "1" or device.type != "cuda":
         return None
     if dtype not in (torch.bfloat16, torch.float16) or (n * dim * 2) % 16 != 0:
@@ -288,8 +296,17 @@ class _FusedClipLoss(torch.autograd.Function):
         grad_mult = 1.0
         if world_size > 1 and not local_loss and not gather_with_grad:
             grad_mult = 1.0 / world_size
-        peer = _peer_accumulator(img.shape[0], img.shape[1], img.device, group) if rank_sweep else None
-        if rank_sweep and peer is not None:
+        # From 8 ranks on, a second recompute sweep (own texts x all images, no exchange) is cheaper
+        # than adding the text-side product into the owners' accumulators over NVLink.
+        local_dtxt = rank_sweep and _bwd_sweeps(world_size) == 2
+        peer = None
+        if rank_sweep and not local_dtxt:
+            peer = _peer_accumulator(img.shape[0], img.shape[1], img.device, group)
+        if local_dtxt:
+            d_img, d_txt, d_scale = _lib.clip_bwd(
+                img, txt, all_img, all_txt, label_offset, scale, row_lse, col_lse, grad_out,
+                grad_mult, True, row_nll_all=row_nll, col_nll_all=col_nll)
+        elif rank_sweep and peer is not None:
             # fused reduce-scatter: every rank's GEMM adds into the owners' accumulators
             acc, hdl, ptrs = peer
             acc.zero_()

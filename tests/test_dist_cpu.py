@@ -30,7 +30,8 @@ def _worker(rank, world, port, one_sweep, ret):
     _lib.clip_bwd = _abi_double.clip_bwd
     _lib.clip_fwd_rows = _abi_double.clip_fwd_rows
     _lib.clip_fwd_cols = _abi_double.clip_fwd_cols
-    _lib.rank_sweep_supported = (lambda dtype, dim: one_sweep)
+    _lib.rank_sweep_supported = (lambda dtype, dim: bool(one_sweep))
+    os.environ["LATTE_B200_BWD_SWEEPS"] = "2" if one_sweep == "fwd_only" else "1"
     _lib.bank_accumulate = _abi_double.bank_accumulate
     _lib.bank_finalize = _abi_double.bank_finalize
     g = np.load(os.path.join(HERE, "golden", f"clip_dist_w{world}.npz"))
@@ -72,12 +73,14 @@ def _worker(rank, world, port, one_sweep, ret):
 
 
 @pytest.mark.parametrize("world,port,one_sweep", [(2, 29721, False), (4, 29723, False),
-                                                   (2, 29725, True), (4, 29727, True)])
+                                                   (2, 29725, True), (4, 29727, True),
+                                                   (2, 29729, "fwd_only"), (4, 29731, "fwd_only")])
 def test_multirank_host_logic_matches_gloo_reference(world, port, one_sweep):
     """one_sweep=False: every rank sweeps its row and its column block, LSE vectors exchanged in
     backward.  one_sweep=True: one sweep per rank, column partials all-gathered in forward and
     the text gradient reduce-scattered in backward (the path 16-bit features with dim <= 512
-    take on the GPU)."""
+    take on the GPU).  one_sweep="fwd_only": that forward, but the backward sweeps rows and columns
+    and exchanges nothing (the default from 8 ranks on)."""
     mgr = mp.Manager()
     ret = mgr.dict()
     mp.spawn(_worker, args=(world, port, one_sweep, ret), nprocs=world, join=True)
@@ -91,7 +94,7 @@ def test_multirank_host_logic_matches_gloo_reference(world, port, one_sweep):
                 err = np.linalg.norm(got[nm] - ref) / max(np.linalg.norm(ref), 1e-30)
                 assert err < 2e-5, (key, r, nm, err)   # LSE vectors cross the ABI as fp32
             ref_ds = float(g[f"{key}_r{r}_ds"])
-            if one_sweep and key == "ll1_gwg1":
+            if one_sweep is True and key == "ll1_gwg1":
                 # rows-of-this-rank x all-columns partition of the same global sum: only the
                 # sum over ranks (what DDP's all-reduce of the parameter gradient sees) matches
                 got_sum = sum(ret[q][key]["ds"] for q in range(world))

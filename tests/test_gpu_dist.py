@@ -19,6 +19,7 @@ ROOT = os.path.dirname(HERE)
 def _worker(rank, world, port, n, d, dtype_name, p2p, ret):
     sys.path.insert(0, ROOT)
     os.environ["LATTE_B200_NO_P2P"] = "0" if p2p else "1"
+    os.environ["LATTE_B200_BWD_SWEEPS"] = "2" if p2p == "two_bwd_sweeps" else "1"
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -55,11 +56,14 @@ def _worker(rank, world, port, n, d, dtype_name, p2p, ret):
 
 
 @pytest.mark.parametrize("dtype_name,n,d,p2p", [("bfloat16", 512, 512, True), ("bfloat16", 512, 512, False),
-                                                 ("bfloat16", 300, 768, True), ("float32", 96, 64, True)])
+                                                 ("bfloat16", 300, 768, True), ("float32", 96, 64, True),
+                                                 ("bfloat16", 512, 512, "two_bwd_sweeps")])
 def test_nccl_cliploss_matches_oracle(dtype_name, n, d, p2p):
     """p2p=True: feature gather and text-gradient reduce-scatter through peer-mapped buffers
     (latte_push_shards, fused GEMM + reduce-scatter); p2p=False: the same one-sweep flow over
-    NCCL all-gather / reduce-scatter.  fp32 features take the two-sweep flow."""
+    NCCL all-gather / reduce-scatter; "two_bwd_sweeps": P2P gather and one forward sweep, but the
+    backward sweeps rows and columns and exchanges nothing (the default from 8 ranks on).
+    fp32 features take the two-sweep flow throughout."""
     world = min(torch.cuda.device_count(), 4)
     if world < 2:
         pytest.skip("needs >= 2 GPUs")
@@ -67,7 +71,7 @@ def test_nccl_cliploss_matches_oracle(dtype_name, n, d, p2p):
     from oracle.clip_loss import clip_loss_all_ranks
     mgr = mp.Manager()
     ret = mgr.dict()
-    mp.spawn(_worker, args=(world, 29801 + n % 7 + 10 * int(p2p) + d % 5, n, d, dtype_name, p2p, ret),
+    mp.spawn(_worker, args=(world, 29801 + n % 7 + 10 * int(p2p is True) + 20 * int(p2p == 'two_bwd_sweeps') + d % 5, n, d, dtype_name, p2p, ret),
              nprocs=world, join=True)
     dtype = getattr(torch, dtype_name)
     g = torch.Generator().manual_seed(123)
