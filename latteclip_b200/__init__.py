@@ -2,14 +2,16 @@
 
 Only the data-parallel hot path is here: open_clip's ClipLoss / gather_features /
 create_loss (``latteclip_b200.loss``) and LatteCLIP's prototype / pseudo-label / mixture /
-EMA / memory-bank path (``latteclip_b200.prototypes``), both thin Python over a C-ABI CUDA
+EMA / memory-bank path (``latteclip_b200.prototypes``) plus the zero-shot evaluation /
+feature-record row next to it (``latteclip_b200.zero_shot``), all thin Python over a C-ABI CUDA
 library (``latteclip_b200/csrc``, header ``include/latte_b200.h``).  Encoders, data
 pipeline and training driver remain the reference's PyTorch code.
 """
 
 from .loss import ClipLoss, create_loss, gather_features  # noqa: F401
 from . import prototypes  # noqa: F401
+from . import zero_shot  # noqa: F401
 from ._lib import build, version, clear_workspace_cache  # noqa: F401
 
-__all__ = ["ClipLoss", "create_loss", "gather_features", "prototypes", "build", "version",
+__all__ = ["ClipLoss", "create_loss", "gather_features", "prototypes", "zero_shot", "build", "version",
            "clear_workspace_cache"]

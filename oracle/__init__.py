@@ -32,3 +32,4 @@ from .prototypes import (  # noqa: F401
     update_bank,
     prototype_step,
 )
+from . import zero_shot  # noqa: F401,E402

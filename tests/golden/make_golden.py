@@ -20,6 +20,8 @@ What is executed is the reference's own code, imported from /root/reference/src
     driven through mock model / data / optimizer objects that only supply feature
     tables, so every arithmetic statement on the hot path is the reference's
       -> proto_step_*.npz
+  * ``training.zero_shot.accuracy`` / ``run`` and ``training.train.accuracy``
+      -> zero_shot_eval.npz
 
 The fixtures hold both the inputs and the reference outputs, so tests never need the
 reference at run time (it does not exist on the GPU box).
@@ -306,6 +308,35 @@ def gen_proto_step(open_clip, tt):
         print("proto_step", name, [float(cl["loss"]) for cl in spy.calls])
 
 
+def gen_zero_shot(tt):
+    """training.zero_shot.accuracy / run and training.train.accuracy (zero_shot.py:14-52,
+    train.py:1128-1138) on seeded features; the 'model' only hands the features through."""
+    import training.zero_shot as zs
+    g = torch.Generator().manual_seed(4242)
+    b, d, c = 192, 64, 23
+    protos = F.normalize(torch.randn(c, d, generator=g), dim=1)
+    target = torch.randint(0, c, (b,), generator=g)
+    feats = F.normalize(protos[target] + 1.2 * torch.randn(b, d, generator=g) / math.sqrt(d) * 3.0, dim=1)
+    classifier = protos.T.contiguous()
+    logits = 100.0 * feats @ classifier
+    accs_zs = zs.accuracy(logits, target, topk=(1, 5, 10))
+    accs_tt, top_logits, top_ids = tt.accuracy(logits, target, topk=(1, 5, 10))
+
+    class _Tower(nn.Module):
+        def forward(self, image=None):
+            return {"image_features": image}
+
+    batches = [(None, feats[k:k + 50], target[k:k + 50]) for k in range(0, b, 50)]   # ragged tail
+    args = SimpleNamespace(precision="fp32", device="cpu", batch_size=50)
+    rates = zs.run(_Tower(), classifier, batches, args)
+    np.savez_compressed(os.path.join(HERE, "zero_shot_eval.npz"), feats=feats.numpy(),
+                        classifier=classifier.numpy(), target=target.numpy(),
+                        accs_zero_shot=np.asarray(accs_zs), accs_train=np.asarray(accs_tt),
+                        top_logits=top_logits.numpy(), top_ids=top_ids.numpy(),
+                        rates=np.asarray(rates), batch=np.asarray(50))
+    print("zero_shot_eval", accs_zs, accs_tt, rates)
+
+
 def main():
     torch.manual_seed(0)
     torch.set_num_threads(4)
@@ -313,6 +344,7 @@ def main():
     gen_clip_w1(open_clip)
     gen_text_margins(tt)
     gen_proto_step(open_clip, tt)
+    gen_zero_shot(tt)
     gen_clip_dist()
 
 

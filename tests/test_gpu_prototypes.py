@@ -231,3 +231,51 @@ def test_bank_roundtrip_through_parameter_dict():
     bank2 = bank * 2
     P.unstack_bank(bank2, pd, names, touched=torch.tensor([1, 0, 1, 0, 0.0]))
     assert torch.equal(pd["c0"].data, bank2[0]) and torch.equal(pd["c1"].data, bank[1])
+
+
+# ------------------------------------------------------------------ zero-shot eval
+def test_zero_shot_accuracy_matches_reference_golden():
+    """zero_shot.py:14-52 / train.py:1128-1138 outputs recorded from the reference."""
+    from types import SimpleNamespace
+    from latteclip_b200 import zero_shot as zs
+    g = load_golden("zero_shot_eval.npz")
+    feats, clf = torch.from_numpy(g["feats"]).to(DEV), torch.from_numpy(g["classifier"]).to(DEV)
+    target = torch.from_numpy(g["target"]).to(DEV)
+    accs, top_logits, top_ids = zs.accuracy(feats, clf, target, topk=(1, 5, 10))
+    assert accs == list(g["accs_train"])                        # hit counts: bit-exact
+    assert np.array_equal(top_ids.cpu().numpy(), g["top_ids"])  # no ties in this fixture
+    assert top_ids.dtype == torch.int64 and top_logits.shape == (feats.shape[0], 10)
+    assert np.allclose(top_logits.cpu().numpy(), g["top_logits"], rtol=0, atol=2e-5)
+
+    class Tower(torch.nn.Module):
+        def forward(self, image=None):
+            return {"image_features": image}
+
+    b = int(g["batch"])
+    batches = [(None, feats[k:k + b].cpu(), target[k:k + b].cpu()) for k in range(0, feats.shape[0], b)]
+    rates = zs.run(Tower(), clf, batches, SimpleNamespace(precision="fp32", device=DEV))
+    assert np.allclose(rates, g["rates"], rtol=0, atol=1e-12)
+
+
+@pytest.mark.parametrize("b,d,c,dtype", [(5000, 512, 397, torch.bfloat16), (1037, 768, 1000, torch.float32),
+                                         (64, 512, 10, torch.float16)])
+def test_zero_shot_accuracy_matches_oracle(b, d, c, dtype):
+    from oracle import zero_shot as ozs
+    from latteclip_b200 import zero_shot as zs
+    bank, _, img, _, _, _ = proto_inputs(b, d, c, 5 + b)
+    clf = F.normalize(bank, dim=1).T.contiguous()               # [D, C] as zero_shot.py:145
+    img = img.to(dtype)
+    g = torch.Generator().manual_seed(b)
+    target = torch.randint(0, c, (b,), generator=g)
+    logits = ozs.zero_shot_logits(img.double(), clf.double())
+    want, want_logits, want_ids = ozs.accuracy(logits, target, (1, 5, 10))
+    accs, top_logits, top_ids = zs.accuracy(img.to(DEV), clf.to(DEV), target.to(DEV), topk=(1, 5, 10))
+    # rows whose 10th/11th (or any adjacent) logits are closer than fp32 dot-product noise may swap
+    srt = logits.sort(dim=1, descending=True).values[:, :11]
+    tie = ((srt[:, :-1] - srt[:, 1:]).min(dim=1).values <= 2e-4) if c > 10 else torch.zeros(b, dtype=torch.bool)
+    ok = ~tie
+    assert int(tie.sum()) <= max(2, b // 100)
+    assert torch.equal(top_ids.cpu()[ok], want_ids[ok])
+    assert torch.allclose(top_logits.cpu().double(), want_logits, rtol=0, atol=2e-4)
+    for a, w in zip(accs, want):
+        assert abs(a - w) <= int(tie.sum())

@@ -111,3 +111,48 @@ def test_row_mode_differs_only_in_label_term():
     with pytest.raises(RuntimeError):
         oracle.mix_and_ema(x[0][:8], x[1][:8], x[2][:8], x[3][:8], w[:8], w2[:8], w3[:8], w4[:8],
                            x[4][:8], x[5][:8], 0.01, "quirk")
+
+
+# ------------------------------------------------------------------ zero-shot eval
+def test_zero_shot_accuracy_matches_reference_functions():
+    from oracle import zero_shot as ozs
+    g = load_golden("zero_shot_eval.npz")
+    feats, clf = torch.from_numpy(g["feats"]), torch.from_numpy(g["classifier"])
+    target = torch.from_numpy(g["target"])
+    accs, top_logits, top_ids = ozs.accuracy(ozs.zero_shot_logits(feats, clf), target, (1, 5, 10))
+    assert accs == list(g["accs_zero_shot"]) == list(g["accs_train"])      # counts, bit-exact
+    assert np.array_equal(top_ids.numpy(), g["top_ids"])
+    assert np.array_equal(top_logits.numpy(), g["top_logits"])
+    b = int(g["batch"])
+    batches = [(feats[k:k + b], target[k:k + b]) for k in range(0, feats.shape[0], b)]
+    assert np.allclose(ozs.run_batches(batches, clf), g["rates"], rtol=0, atol=1e-15)
+
+
+def test_feature_record_format_round_trip(tmp_path):
+    """clip_features_{split}.pkl: the product's writer, the reference's reader contract
+    (data.py:393-396, 412-416, 448) and the zs-id mapping of train.py:412-417 (host only)."""
+    from oracle import zero_shot as ozs
+    from latteclip_b200 import zero_shot as zs
+    g = load_golden("zero_shot_eval.npz")
+    feats, target = torch.from_numpy(g["feats"]), torch.from_numpy(g["target"])
+    top_ids, top_logits = torch.from_numpy(g["top_ids"]), torch.from_numpy(g["top_logits"])
+    class_names = [f"class {c}" for c in range(int(g["classifier"].shape[1]))]
+    image_ids = [f"img_{k:05d}" for k in range(feats.shape[0])]
+    want = ozs.feature_records(image_ids, feats, top_ids, top_logits, target, class_names)
+    got = zs.feature_records(image_ids, feats, top_ids, top_logits, target, class_names)
+    path = zs.save_feature_records(got, str(tmp_path), "train")
+    assert path.endswith("clip_features_train.pkl")
+    back = zs.load_key_to_clip_prediction(path)
+    assert list(back) == image_ids
+    for k in image_ids:
+        assert set(back[k]) == {"image", "top_class_ids", "class_names", "top_logit", "gt_classname", "gt_class_id"}
+        for f in ("image", "top_class_ids", "top_logit"):
+            assert np.array_equal(back[k][f], want[k][f]) and back[k][f].dtype == want[k][f].dtype
+        assert back[k]["class_names"] == want[k]["class_names"]
+        assert back[k]["gt_classname"] == want[k]["gt_classname"]
+        assert back[k]["gt_class_id"] == want[k]["gt_class_id"] and isinstance(back[k]["gt_class_id"], int)
+    names = [zs.zeroshot_classnames(back[k], 3) for k in image_ids]
+    ids = zs.zeroshot_class_ids(names, class_names)
+    assert ids.dtype == torch.int64
+    assert np.array_equal(ids.numpy(), ozs.zeroshot_class_ids(names, class_names))
+    assert np.array_equal(ids.numpy(), g["top_ids"][:, 0])
