@@ -387,6 +387,55 @@ def test_full_size_properties_32k(n, d):
     assert rel(di[rows], ref_di) < GRAD_RTOL_16
 
 
+def test_full_size_rank_block_cfg4():
+    """BASELINE cfg4 shape (N = 65536, D = 768, W = 8, n = 8192) on one GPU: all eight ranks' forward
+    sweeps (their column partials are what the all-gather would deliver), then rank 3's merge and
+    backward.  Checked on sampled rows / columns against fp64 on the same rounded inputs."""
+    from latteclip_b200 import _lib
+    dev = torch.device("cuda:0")
+    world, n, d, r = 8, 8192, 768, 3
+    N = world * n
+    i, t = synth(N, d, 6.0, 404)
+    ib, tb = i.to(dev).bfloat16(), t.to(dev).bfloat16()
+    del i, t
+    sc = torch.tensor(100.0, device=dev)
+    one = torch.ones(1, device=dev)
+    assert _lib.rank_sweep_supported(torch.bfloat16, d)
+    gathered = torch.stack([_lib.clip_fwd_rows(ib[q * n:(q + 1) * n], tb, q * n, sc) for q in range(world)])
+    row_all, rown_all, col_all, coln_all, loss_r = _lib.clip_fwd_cols(gathered, ib, tb, n, r * n, sc)
+    g = torch.Generator().manual_seed(8)
+    rows = torch.randint(0, N, (48,), generator=g).to(dev)
+    S_r = 100.0 * ib[rows].double() @ tb.double().T                 # [48, N]
+    S_c = 100.0 * tb[rows].double() @ ib.double().T
+    assert torch.allclose(row_all[rows].double(), torch.logsumexp(S_r, 1), rtol=0, atol=2e-4)
+    assert torch.allclose(col_all[rows].double(), torch.logsumexp(S_c, 1), rtol=0, atol=2e-4)
+    diag = 100.0 * (ib.float() * tb.float()).sum(1).double()
+    sl = slice(r * n, (r + 1) * n)
+    want_loss = 0.5 * ((row_all.double() - diag)[sl].mean() + (col_all.double() - diag)[sl].mean())
+    assert abs(float(loss_r) - float(want_loss)) <= 1e-5 * abs(float(want_loss)) + 2e-5
+    assert abs(float(loss_r) - 0.5 * float((rown_all[sl] + coln_all[sl]).double().mean())) <= 1e-5 * abs(float(loss_r))
+    d_img, d_part, d_s = _lib.clip_bwd(ib[sl], tb[sl], ib, tb, r * n, sc, row_all, col_all, one, 1.0, True,
+                                       grad_dtype=torch.float32, row_nll_all=rown_all, col_nll_all=coln_all,
+                                       partial=True)
+    assert d_part.shape == (N, d)
+    # image side: rows of this rank, all columns
+    own = (r * n + torch.randint(0, n, (48,), generator=g)).to(dev)
+    S_o = 100.0 * ib[own].double() @ tb.double().T
+    G_o = torch.exp(S_o - row_all[own].double()[:, None]) + torch.exp(S_o - col_all.double()[None, :])
+    G_o[torch.arange(48), own] -= 2.0
+    assert rel(d_img[own - r * n], (100.0 / (2 * n)) * G_o @ tb.double()) < GRAD_RTOL_16
+    # text side: this rank's rows only, sampled columns from every rank
+    cols = torch.randint(0, N, (48,), generator=g).to(dev)
+    S_k = 100.0 * ib[sl].double() @ tb[cols].double().T             # [n, 48]
+    G_k = torch.exp(S_k - row_all[sl].double()[:, None]) + torch.exp(S_k - col_all[cols].double()[None, :])
+    hit = (torch.arange(r * n, (r + 1) * n, device=dev)[:, None] == cols[None, :])
+    G_k = G_k - 2.0 * hit.double()
+    assert rel(d_part[cols], (100.0 / (2 * n)) * G_k.T @ ib[sl].double()) < GRAD_RTOL_16
+    # Euler identity on this rank's sweep: s * ds = sum <d_img, I_own> (both cover own rows x all columns)
+    eul = float((d_img.double() * ib[sl].double()).sum())
+    assert abs(eul - 100.0 * float(d_s)) <= 2e-3 * abs(eul) + 1e-6
+
+
 @pytest.mark.parametrize("n,d", [(1, 8), (7, 24), (129, 40), (513, 72), (300, 504), (1000, 512), (257, 16),
                                  (700, 768), (300, 640), (130, 520), (1100, 704)])
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
