@@ -192,6 +192,33 @@ int latte_push_shards(const void* img_shard, const void* txt_shard, int64_t shar
                       int64_t tensor_stride_bytes, void* multicast_base, void* stream);
 
 /*
+ * SigLipLoss (open_clip loss.py:453-560; factory.py:337-342 selects it on args.siglip).
+ * z_ij = logit_scale * <img_i, txt_j> + logit_bias;  per rank
+ *   loss = sum_{i in own rows, j in ALL columns} -logsigmoid(label_ij * z_ij) / n_loc,
+ * label_ij = +1 iff j == label_offset + i else -1 (loss.py:500-519; the reference reaches the
+ * other ranks' texts by passing them round the ring, :521-558, with identical pairs).
+ * 16-bit features, 8 <= dim <= 768, dim % 8 == 0 (latte_siglip_supported); logit_bias nullable.
+ * Backward: d_img [n_loc, dim]; the text-side product G^T . img_loc either as d_txt [n_all, dim]
+ * (only when n_loc == n_all), or as an fp32 partial over all n_all rows for the caller's
+ * reduce-scatter (the backward of the ring exchange, loss.py:419-428), or added straight into
+ * the owners' peer-mapped fp32 accumulators (d_txt_peers, as in latte_clip_bwd).  d_scale,
+ * d_bias: this rank's d loss / d logit_scale and d loss / d logit_bias (nullable).
+ */
+int latte_siglip_supported(int dtype, int64_t dim);
+int latte_siglip_workspace_bytes(int64_t n_loc, int64_t n_all, int64_t dim, int dtype, int backward,
+                                 int own_d_txt, size_t* bytes);
+int latte_siglip_fwd(const void* img_loc, int64_t ld_img, const void* txt_all, int64_t ld_txt,
+                     int dtype, int64_t n_loc, int64_t n_all, int64_t dim, int64_t label_offset,
+                     const float* logit_scale, const float* logit_bias, float* loss,
+                     void* workspace, size_t workspace_bytes, void* stream);
+int latte_siglip_bwd(const void* img_loc, int64_t ld_img, const void* txt_all, int64_t ld_txt,
+                     int dtype, int64_t n_loc, int64_t n_all, int64_t dim, int64_t label_offset,
+                     const float* logit_scale, const float* logit_bias, const float* grad_loss,
+                     void* d_img, void* d_txt, int grad_dtype, int64_t ld_grad, float* d_txt_partial,
+                     void* const* d_txt_peers, int n_peers, float* d_scale, float* d_bias,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
+/*
  * Diagnostic for bench.py: runs latte_clip_fwd then latte_clip_bwd `reps` times on `stream`
  * with CUDA events recorded on that stream around every kernel stage, synchronises the
  * stream, and returns the mean milliseconds per stage in stage_ms[LATTE_NUM_STAGES] (host

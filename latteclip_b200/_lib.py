@@ -20,7 +20,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO_DIR = os.path.join(_HERE, "_C")
 SO_PATH = os.path.join(_SO_DIR, "liblatte_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
-SOURCES = ["api.cu", "clip_tc.cu", "clip_pair.cu", "clip_simt.cu", "nxc.cu", "nxc_tc.cu", "proto.cu"]
+SOURCES = ["api.cu", "clip_tc.cu", "clip_pair.cu", "clip_simt.cu", "nxc.cu", "nxc_tc.cu", "proto.cu", "siglip.cu"]
 
 F32, BF16, F16 = 0, 1, 2
 LABEL_AXIS = {"row": 0, "quirk": 1}
@@ -78,6 +78,11 @@ def _declare(lib):
                                            vp, vp, vp, vp, vp, vp, vp, f32, i32, vp, vp, i32, i64,
                                            vp, vp, vp, sz, vp, sz, vp, i32, c.POINTER(f32)]
     lib.latte_push_shards.argtypes = [vp, vp, i64, vp, i32, i32, i64, vp, vp]
+    lib.latte_siglip_supported.argtypes = [i32, i64]
+    lib.latte_siglip_workspace_bytes.argtypes = [i64, i64, i64, i32, i32, i32, c.POINTER(sz)]
+    lib.latte_siglip_fwd.argtypes = [vp, i64, vp, i64, i32, i64, i64, i64, i64, vp, vp, vp, vp, sz, vp]
+    lib.latte_siglip_bwd.argtypes = [vp, i64, vp, i64, i32, i64, i64, i64, i64, vp, vp, vp, vp, vp,
+                                     i32, i64, vp, vp, i32, vp, vp, vp, sz, vp]
     lib.latte_normalize_rows.argtypes = [vp, i64, vp, i64, i64, i64, vp]
     lib.latte_nxc_argmax_margin.argtypes = [vp, i64, i32, vp, i64, i64, vp, i64, i64, f32,
                                             vp, vp, vp, vp]
@@ -97,7 +102,8 @@ EXPORTS = [
     "latte_version", "latte_status_string", "latte_device_info", "latte_clip_workspace_bytes",
     "latte_clip_bwd_workspace_bytes", "latte_clip_stage_times", "latte_clip_rank_sweep_supported",
     "latte_clip_fwd_rows", "latte_clip_fwd_cols_workspace_bytes", "latte_clip_fwd_cols",
-    "latte_push_shards",
+    "latte_push_shards", "latte_siglip_supported", "latte_siglip_workspace_bytes",
+    "latte_siglip_fwd", "latte_siglip_bwd",
     "latte_clip_fwd", "latte_clip_bwd", "latte_normalize_rows", "latte_nxc_argmax_margin",
     "latte_nxc_topk", "latte_mix_ema_fwd", "latte_mix_ema_bwd", "latte_bank_accumulate",
     "latte_bank_finalize",
@@ -378,6 +384,82 @@ def clip_bwd(img_loc, txt_loc, img_all, txt_all, label_offset: int, logit_scale,
                                   _ptr(d_scale), wp, wn, _stream(img_loc)),
                "latte_clip_bwd")
     return d_img, (d_part if partial else d_txt), d_scale
+
+
+def siglip_supported(dtype: torch.dtype, dim: int) -> bool:
+    """True when the SigLIP kernels take features of this dtype / width (16-bit, dim <= 768, % 8)."""
+    if dtype not in _DTYPES:
+        return False
+    return bool(load().latte_siglip_supported(_DTYPES[dtype], int(dim)))
+
+
+def _siglip_workspace(n_loc: int, n_all: int, dim: int, dt: int, dev, bwd: bool, own: bool):
+    def nbytes():
+        need = ctypes.c_size_t()
+        _check(load().latte_siglip_workspace_bytes(n_loc, n_all, dim, dt, int(bwd), int(own),
+                                                   ctypes.byref(need)), "latte_siglip_workspace_bytes")
+        return need.value + 256
+    return _cached_workspace(("siglip", bwd, own, n_loc, n_all, dim, dt), nbytes, dev)
+
+
+def siglip_fwd(img_loc, txt_all, label_offset: int, logit_scale, logit_bias=None):
+    """-> loss[1] fp32 of this rank: sum over own image rows x ALL text columns of
+    -logsigmoid(label * (s <i, t> + b)) / n_loc  (open_clip loss.py:509-519)."""
+    lib = load()
+    img_loc, txt_all = _rows(img_loc, "image_features"), _rows(txt_all, "all_text_features")
+    if img_loc.dtype != txt_all.dtype or img_loc.shape[1] != txt_all.shape[1]:
+        raise RuntimeError("siglip_fwd: image and text features must share dtype and width")
+    dt = _dt(img_loc)
+    n_loc, dim = img_loc.shape
+    n_all = txt_all.shape[0]
+    dev = img_loc.device
+    s = _scalar_f32(logit_scale)
+    b = _scalar_f32(logit_bias) if logit_bias is not None else None
+    loss = torch.empty(1, dtype=torch.float32, device=dev)
+    ws = _siglip_workspace(n_loc, n_all, dim, dt, dev, False, False)
+    wp, wn = _aligned_ptr(ws)
+    with torch.cuda.device(dev):
+        _check(lib.latte_siglip_fwd(_ptr(img_loc), img_loc.stride(0), _ptr(txt_all), txt_all.stride(0),
+                                    dt, n_loc, n_all, dim, int(label_offset), _ptr(s), _ptr(b),
+                                    _ptr(loss), wp, wn, _stream(img_loc)), "latte_siglip_fwd")
+    return loss
+
+
+def siglip_bwd(img_loc, txt_all, label_offset: int, logit_scale, logit_bias, grad_loss,
+               grad_dtype=None, partial: bool = False, peer_ptrs=None):
+    """-> (d_img [n_loc, dim], d_txt, d_scale[1], d_bias[1]).  d_txt is [n_all, dim] in
+    ``grad_dtype`` when this rank holds every text row (n_loc == n_all); with ``partial=True`` the
+    fp32 partial [n_all, dim] for the caller's reduce-scatter; with ``peer_ptrs`` None (the product
+    was added into the peers' accumulators)."""
+    lib = load()
+    img_loc, txt_all = _rows(img_loc, "image_features"), _rows(txt_all, "all_text_features")
+    dt = _dt(img_loc)
+    n_loc, dim = img_loc.shape
+    n_all = txt_all.shape[0]
+    dev = img_loc.device
+    s = _scalar_f32(logit_scale)
+    b = _scalar_f32(logit_bias) if logit_bias is not None else None
+    g = _scalar_f32(grad_loss)
+    gdt = img_loc.dtype if grad_dtype is None else grad_dtype
+    fused = peer_ptrs is not None
+    own = not (partial or fused)
+    if own and n_loc != n_all:
+        raise RuntimeError("siglip_bwd: d_txt needs partial=True or peer_ptrs when n_loc < n_all")
+    d_img = torch.empty(n_loc, dim, dtype=gdt, device=dev)
+    d_txt = torch.empty(n_all, dim, dtype=gdt, device=dev) if own else None
+    d_part = torch.empty(n_all, dim, dtype=torch.float32, device=dev) if partial else None
+    peers = (ctypes.c_void_p * len(peer_ptrs))(*peer_ptrs) if fused else None
+    d_scale = torch.empty(1, dtype=torch.float32, device=dev)
+    d_bias = torch.empty(1, dtype=torch.float32, device=dev)
+    ws = _siglip_workspace(n_loc, n_all, dim, dt, dev, True, own)
+    wp, wn = _aligned_ptr(ws)
+    with torch.cuda.device(dev):
+        _check(lib.latte_siglip_bwd(_ptr(img_loc), img_loc.stride(0), _ptr(txt_all), txt_all.stride(0),
+                                    dt, n_loc, n_all, dim, int(label_offset), _ptr(s), _ptr(b), _ptr(g),
+                                    _ptr(d_img), _ptr(d_txt), _DTYPES[gdt], dim, _ptr(d_part), peers,
+                                    len(peer_ptrs) if fused else 0, _ptr(d_scale), _ptr(d_bias),
+                                    wp, wn, _stream(img_loc)), "latte_siglip_bwd")
+    return d_img, (d_part if partial else d_txt), d_scale, d_bias
 
 
 STAGES = ("fwd_sweep", "fwd_finalize", "bwd_prep", "bwd_sweep", "bwd_gemm", "bwd_finish")

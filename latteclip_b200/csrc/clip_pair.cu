@@ -82,6 +82,8 @@ struct SweepParams {
   float cb, cd;
   float ds_cb, ds_cd;                // weights of the same terms inside d loss / d s
   float* ds_partial;                 // [gridDim.x]
+  const float* logit_bias;           // SigLIP modes: nullable device scalar added to every logit
+  float* aux_partial;                // [gridDim.x] SigLIP: loss partial (forward) / d bias partial (backward)
   // forward modes: per-(slot, half) online-softmax partials of the rows, raw label dots,
   // and (kModeFwdBoth) per-128-row-block column partial sums with their reference exponents
   float* part_max;                   // [4 * slots, n_loc]  (slot, epilogue group, tile half)
@@ -102,6 +104,24 @@ struct SweepParams {
 constexpr int kModeGrad = 0;      // backward: gradient weights G
 constexpr int kModeFwdRows = 1;   // forward: row log-sum-exp partials
 constexpr int kModeFwdBoth = 2;   // forward, world size 1: row partials + column partials of the same tile
+constexpr int kModeSigFwd = 3;    // SigLIP forward: sum of softplus(-label * z) over the tile range
+constexpr int kModeSigGrad = 4;   // SigLIP backward: G = sigmoid(z) - delta
+
+// log1p(t) = t * q(t) on [0, 1]: degree-8 Chebyshev fit of log1p(t)/t, relative error 2e-7 in fp32
+// Horner form (MUFU lg2 near 1 has an ABSOLUTE error of 2^-22, useless for the small terms that
+// make up most of a sigmoid loss).
+__device__ __forceinline__ float log1p_unit(float t) {
+  float q = 0.00525352f;
+  q = fmaf(q, t, -0.02958887f);
+  q = fmaf(q, t, 0.07836246f);
+  q = fmaf(q, t, -0.13674858f);
+  q = fmaf(q, t, 0.19111485f);
+  q = fmaf(q, t, -0.24844388f);
+  q = fmaf(q, t, 0.33319275f);
+  q = fmaf(q, t, -0.49999502f);
+  q = fmaf(q, t, 0.99999997f);
+  return t * q;
+}
 
 template <int MODE, bool TAIL>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kSweepThreads, 1)
@@ -324,6 +344,15 @@ pair_sweep_kernel(const __grid_constant__ CUtensorMap tmy, const __grid_constant
       if (lane == 0) mbar_arrive_cluster(lead_aready);
     };
 
+    // A row block that starts at the LAST tile of this range when that tile has an odd local index
+    // belongs to group 1 alone: group 0 has no later tile at whose top it would load the block's X,
+    // and the MMA issuer would wait for it forever.  Called by every mode after its tile loop
+    // (group 0's (rb_i, ct) then name tile `ntile`, one past the end).
+    auto trailing_row_block = [&]() {
+      if (group == 0 && ntile >= 2 && (ntile & 1) == 0 && ct == 1 && rb_i != cur_rb)
+        enter_row_block(ntile);
+    };
+
     if constexpr (MODE == kModeGrad) {
       // ======================================================== gradient weights
       const float s = __ldg(p.logit_scale);
@@ -469,6 +498,7 @@ pair_sweep_kernel(const __grid_constant__ CUtensorMap tmy, const __grid_constant
         }
       }
       if (lane == 0) bulk_wait_group<0>();
+      trailing_row_block();
 
       // ---- d loss / d s partial of this CTA
       float v = ds_acc * exp2f(-gs);
@@ -480,6 +510,153 @@ pair_sweep_kernel(const __grid_constant__ CUtensorMap tmy, const __grid_constant
         float tot = 0.f;
         for (int w = 0; w < kNumEpiWarps; ++w) tot += red_ptr[w];
         p.ds_partial[blockIdx.x] = tot;
+      }
+    } else if constexpr (MODE == kModeSigGrad) {
+      // ======================================================== SigLIP gradient weights
+      // z = s * <x_i, y_j> + b;  d softplus(-label z) / dz = sigmoid(z) - [j == label_i]
+      // (loss.py:509-519).  Stored as fp16 scaled by 2^13 like the softmax weights.
+      const float b2 = p.logit_bias ? __ldg(p.logit_bias) * kLog2e : 0.f;
+      constexpr float kSigScale = 8192.0f;
+      const uint32_t my_stage = stage_base + e * kStageBytes;
+      const uint64_t stream_pol = policy_evict_first();
+      float ds_acc = 0.f, db_acc = 0.f;
+      for (int it = group, k = 0; it < ntile; it += 2, ++k) {
+        if (rb_i != cur_rb) enter_row_block(it);
+        const int ct_cur = ct;
+        const int rb_cur = rb_i;
+        step_tile();
+        step_tile();
+        const int64_t col0 = (int64_t)ct_cur * kTN + half * 64;
+        const uint32_t row_addr = my_stage + lane * 128;
+        mbar_wait(my_tfull, k & 1);
+        tc_fence_after();
+        if (lane == 0) bulk_wait_group_read<0>();
+        __syncwarp();
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint32_t r[32];
+          tmem_ld_32x32(tmem_tile + h * 32, r);
+          tmem_ld_wait();
+          if (h == 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(lead_tempty);
+          }
+          const int64_t colh = col0 + h * 32;
+          int want = -1;
+          if (row_ok && label >= colh && label < colh + 32) want = (int)(label - colh);
+          const int valid = !row_ok ? 0 : (colh + 32 <= p.n_all ? 32 : (colh >= p.n_all ? 0 : (int)(p.n_all - colh)));
+          uint32_t packed[16];
+          float dsh = 0.f, dbh = 0.f;
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            float g[2];
+#pragma unroll
+            for (int x = 0; x < 2; ++x) {
+              const float v = __uint_as_float(r[i + x]);
+              const float z2 = fmaf(v, c2, b2);
+              const float t = fast_exp2(-fabsf(z2));
+              const float rr = __fdividef(1.0f, 1.0f + t);
+              const float tr = t * rr;
+              const bool pos = z2 >= 0.f;
+              float sg = pos ? rr : tr;                      // sigmoid(z)
+              if (i + x == want) sg = pos ? -tr : -rr;       // sigmoid(z) - 1 without cancellation
+              if (i + x >= valid) sg = 0.f;
+              dsh = fmaf(sg, v, dsh);
+              dbh += sg;
+              g[x] = sg * kSigScale;
+            }
+            packed[i >> 1] = pack2(g[0], g[1]);
+          }
+          ds_acc += dsh;
+          db_acc += dbh;
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            st_shared_v4(row_addr + ((uint32_t)((h * 4 + j) ^ (lane & 7)) << 4), packed[4 * j],
+                         packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          const int64_t block = ((int64_t)rb_cur * 2 + rank) * (int64_t)p.ncb + (ct_cur * 2 + half);
+          tma_store_2d_hint(&tmg, my_stage, 0, (int32_t)(block * 128 + q * 32), stream_pol);
+          bulk_commit_group();
+        }
+      }
+      if (lane == 0) bulk_wait_group<0>();
+      trailing_row_block();
+      float v0 = ds_acc, v1 = db_acc;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        v0 += __shfl_xor_sync(0xffffffffu, v0, o);
+        v1 += __shfl_xor_sync(0xffffffffu, v1, o);
+      }
+      if (lane == 0) { red_ptr[e] = v0; red_ptr[kNumEpiWarps + e] = v1; }
+      named_bar_sync(1, kNumEpiWarps * 32);
+      if (e == 0 && lane == 0) {
+        double t0 = 0.0, t1 = 0.0;
+        for (int w = 0; w < kNumEpiWarps; ++w) { t0 += red_ptr[w]; t1 += red_ptr[kNumEpiWarps + w]; }
+        p.ds_partial[blockIdx.x] = (float)t0;
+        p.aux_partial[blockIdx.x] = (float)t1;
+      }
+    } else if constexpr (MODE == kModeSigFwd) {
+      // ======================================================== SigLIP loss terms
+      // -logsigmoid(label * z) = softplus(z) for the negatives and softplus(z) - z for the label
+      // entry; softplus(z) = max(z, 0) + log1p(exp(-|z|))  (loss.py:515-519)
+      const float b2 = p.logit_bias ? __ldg(p.logit_bias) * kLog2e : 0.f;
+      float sum = 0.f, comp = 0.f;                 // compensated running sum of this thread
+      for (int it = group, k = 0; it < ntile; it += 2, ++k) {
+        if (rb_i != cur_rb) enter_row_block(it);
+        const int ct_cur = ct;
+        step_tile();
+        step_tile();
+        const int64_t col0 = (int64_t)ct_cur * kTN + half * 64;
+        mbar_wait(my_tfull, k & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint32_t r[32];
+          tmem_ld_32x32(tmem_tile + h * 32, r);
+          tmem_ld_wait();
+          if (h == 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(lead_tempty);
+          }
+          const int64_t colh = col0 + h * 32;
+          int want = -1;
+          if (row_ok && label >= colh && label < colh + 32) want = (int)(label - colh);
+          const int valid = !row_ok ? 0 : (colh + 32 <= p.n_all ? 32 : (colh >= p.n_all ? 0 : (int)(p.n_all - colh)));
+          float small0 = 0.f, small1 = 0.f, big = 0.f;      // ln units / log2 units
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            float z0 = fmaf(__uint_as_float(r[i]), c2, b2);
+            float z1 = fmaf(__uint_as_float(r[i + 1]), c2, b2);
+            if (i >= valid) z0 = -INFINITY;
+            if (i + 1 >= valid) z1 = -INFINITY;
+            small0 += log1p_unit(fast_exp2(-fabsf(z0)));
+            small1 += log1p_unit(fast_exp2(-fabsf(z1)));
+            big += fmaxf(z0, 0.f) + fmaxf(z1, 0.f);
+            if (i == want) big -= z0;
+            if (i + 1 == want) big -= z1;
+          }
+          const float term = fmaf(big, kLn2, small0 + small1);
+          const float y = term - comp;               // Kahan
+          const float tsum = sum + y;
+          comp = (tsum - sum) - y;
+          sum = tsum;
+        }
+      }
+      trailing_row_block();
+      float v0 = sum;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v0 += __shfl_xor_sync(0xffffffffu, v0, o);
+      if (lane == 0) red_ptr[e] = v0;
+      named_bar_sync(1, kNumEpiWarps * 32);
+      if (e == 0 && lane == 0) {
+        double t0 = 0.0;
+        for (int w = 0; w < kNumEpiWarps; ++w) t0 += red_ptr[w];
+        p.aux_partial[blockIdx.x] = (float)t0;
       }
     } else {
       // ======================================================== forward
@@ -610,6 +787,7 @@ pair_sweep_kernel(const __grid_constant__ CUtensorMap tmy, const __grid_constant
         }
       }
       flush_rows();
+      trailing_row_block();
     }
   }
 
@@ -926,6 +1104,12 @@ int launch_sweep(int mode, bool tail, int grid, cudaStream_t stream, const CUten
   if (mode == kModeFwdBoth)
     return tail ? launch_sweep_t<kModeFwdBoth, true>(grid, stream, tmy, tmg, tmx, p)
                 : launch_sweep_t<kModeFwdBoth, false>(grid, stream, tmy, tmg, tmx, p);
+  if (mode == kModeSigFwd)
+    return tail ? launch_sweep_t<kModeSigFwd, true>(grid, stream, tmy, tmg, tmx, p)
+                : launch_sweep_t<kModeSigFwd, false>(grid, stream, tmy, tmg, tmx, p);
+  if (mode == kModeSigGrad)
+    return tail ? launch_sweep_t<kModeSigGrad, true>(grid, stream, tmy, tmg, tmx, p)
+                : launch_sweep_t<kModeSigGrad, false>(grid, stream, tmy, tmg, tmx, p);
   return tail ? launch_sweep_t<kModeFwdRows, true>(grid, stream, tmy, tmg, tmx, p)
               : launch_sweep_t<kModeFwdRows, false>(grid, stream, tmy, tmg, tmx, p);
 }
@@ -1034,6 +1218,46 @@ int clip_pair_sweep(const PairSweepArgs& a, cudaStream_t stream) {
   if (total < ncl) ncl = (int)total;
   // every CTA of the launch writes its ds partial; unused slots are zeroed by the caller
   rc = launch_sweep(kModeGrad, p.tail_chunks > 0, 2 * ncl, stream, tmy, tmg, tmx, p);
+  if (rc) return rc;
+  LATTE_LAUNCH_OK();
+  return LATTE_OK;
+}
+
+// SigLIP sweeps (loss.py:509-519): forward = per-CTA partial sums of the loss terms, backward = G
+// (fp16, scaled by 2^13) + per-CTA partials of d loss / d logit_scale and d loss / d logit_bias.
+int clip_pair_sig_sweep(const PairSigArgs& a, cudaStream_t stream) {
+  if (!clip_pair_supported(a.dtype, a.dim, a.ldx, a.ldy, a.x, a.y)) return LATTE_ERR_UNSUPPORTED;
+  const PairGeom geo = clip_pair_geom(a.n_loc, a.n_all);
+  CUtensorMap tmy, tmg, tmx;
+  int rc = make_map16(&tmy, a.y, a.dtype, a.n_all, a.dim, a.ldy, 64);
+  if (rc) return rc;
+  tmg = tmy;
+  if (a.g) {
+    const int64_t g_rows = (int64_t)geo.row_blocks * 2 * geo.ncb * 128;
+    rc = make_map16(&tmg, a.g, LATTE_F16, g_rows, 64, 64, 32);
+    if (rc) return rc;
+  }
+  rc = make_map16(&tmx, a.x, a.dtype, a.n_loc, a.dim, a.ldx, 128);
+  if (rc) return rc;
+  SweepParams p = {};
+  p.x = a.x; p.ldx = a.ldx;
+  p.n_loc = a.n_loc; p.n_all = a.n_all; p.dim = a.dim;
+  p.label_offset = a.label_offset;
+  p.logit_scale = a.logit_scale;
+  p.logit_bias = a.logit_bias;
+  p.ds_partial = a.ds_partial;
+  p.aux_partial = a.aux_partial;
+  p.kch = (int)((a.dim + kBK - 1) / kBK);
+  p.tail_chunks = p.kch > kTmemChunks ? p.kch - kTmemChunks : 0;
+  p.cps = p.tail_chunks ? 2 : kChunksPerStage;
+  p.col_tiles = geo.col_tiles;
+  p.row_blocks = geo.row_blocks;
+  p.ncb = geo.ncb;
+  p.idesc = make_idesc_f16(256, kTN, a.dtype == LATTE_BF16 ? 1u : 0u, 0, 0);
+  int ncl = device_sm_count() / 2;
+  const int64_t total = (int64_t)geo.row_blocks * geo.col_tiles;
+  if (total < ncl) ncl = (int)total;
+  rc = launch_sweep(a.g ? kModeSigGrad : kModeSigFwd, p.tail_chunks > 0, 2 * ncl, stream, tmy, tmg, tmx, p);
   if (rc) return rc;
   LATTE_LAUNCH_OK();
   return LATTE_OK;

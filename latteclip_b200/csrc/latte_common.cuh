@@ -107,6 +107,19 @@ struct PairSweepArgs {
   void* g;                    // blocked fp16 G scratch (PairGeom::g_elems)
   float* ds_partial;          // [clip_pair_ds_count()] zeroed by the caller
 };
+struct PairSigArgs {
+  const void* x; int64_t ldx;       // [n_loc, dim] image rows of this rank
+  const void* y; int64_t ldy;       // [n_all, dim] all text rows
+  int dtype;
+  int64_t n_loc, n_all, dim;
+  int64_t label_offset;
+  const float* logit_scale;
+  const float* logit_bias;          // nullable
+  void* g;                          // NULL: forward (loss partials); else blocked fp16 G scratch
+  float* ds_partial;                // backward: [clip_pair_ds_count()] zeroed by the caller
+  float* aux_partial;               // forward: loss partials; backward: d bias partials (same size)
+};
+int clip_pair_sig_sweep(const PairSigArgs& a, cudaStream_t stream);
 struct PairGemmArgs {
   const void* g;
   const void* y16; int64_t ldy16;   // fp16 [n_all, dim]

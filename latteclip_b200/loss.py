@@ -424,13 +424,16 @@ class ClipLoss(nn.Module):
 
 
 def create_loss(args):
-    """ClipLoss branch of the reference factory (factory.py:344-351).  CoCa / SigLIP /
-    distillation losses are outside the accelerated path and are not provided here."""
-    if "coca" in getattr(args, "model", "").lower() or getattr(args, "siglip", False) \
-            or getattr(args, "distill", False):
+    """The reference factory (factory.py:323-351): SigLipLoss on ``args.siglip`` (:337-342), else
+    ClipLoss (:344-351).  CoCa / distillation losses are outside the accelerated path."""
+    if "coca" in getattr(args, "model", "").lower() or getattr(args, "distill", False):
         raise NotImplementedError(
-            "latteclip_b200.create_loss only provides ClipLoss; use the reference factory for "
-            "CoCa / SigLIP / distillation losses")
+            "latteclip_b200.create_loss provides ClipLoss and SigLipLoss; use the reference factory "
+            "for CoCa / distillation losses")
+    if getattr(args, "siglip", False):
+        assert not args.horovod, "Horovod not currently supported for SigLip"
+        from .siglip import SigLipLoss
+        return SigLipLoss(rank=args.rank, world_size=args.world_size)
     return ClipLoss(
         local_loss=args.local_loss,
         gather_with_grad=args.gather_with_grad,

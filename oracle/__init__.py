@@ -33,3 +33,4 @@ from .prototypes import (  # noqa: F401
     prototype_step,
 )
 from . import zero_shot  # noqa: F401,E402
+from . import siglip  # noqa: F401,E402

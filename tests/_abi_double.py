@@ -115,3 +115,38 @@ def bank_finalize(sums, counts, bank):
     mean = sums[m] / counts[m][:, None]
     bank[m] = torch.nn.functional.normalize(mean, dim=1)
     return bank
+
+
+# ------------------------------------------------------------------ SigLIP entry points
+def siglip_supported(dtype, dim):
+    return True
+
+
+def _siglip_terms(img_loc, txt_all, label_offset, logit_scale, logit_bias):
+    s = logit_scale.detach().double().reshape(())
+    b = logit_bias.detach().double().reshape(()) if logit_bias is not None else torch.zeros((), dtype=torch.float64)
+    il, ta = img_loc.detach().double(), txt_all.detach().double()
+    n = il.shape[0]
+    dots = il @ ta.T
+    z = s * dots + b
+    lab = -torch.ones_like(z)
+    lab[torch.arange(n), torch.arange(n) + label_offset] = 1.0
+    return il, ta, dots, z, lab, s
+
+
+def siglip_fwd(img_loc, txt_all, label_offset, logit_scale, logit_bias=None):
+    il, ta, dots, z, lab, s = _siglip_terms(img_loc, txt_all, label_offset, logit_scale, logit_bias)
+    return (torch.nn.functional.softplus(-lab * z).sum() / il.shape[0]).float().reshape(1)
+
+
+def siglip_bwd(img_loc, txt_all, label_offset, logit_scale, logit_bias, grad_loss, grad_dtype=None,
+               partial=False, peer_ptrs=None):
+    assert peer_ptrs is None
+    il, ta, dots, z, lab, s = _siglip_terms(img_loc, txt_all, label_offset, logit_scale, logit_bias)
+    n = il.shape[0]
+    g = (torch.sigmoid(z) - (lab > 0).double()) * (grad_loss.detach().double().reshape(()) / n)
+    gdt = img_loc.dtype if grad_dtype is None else grad_dtype
+    d_img = (s * g @ ta).to(gdt)
+    d_txt = s * g.T @ il
+    d_txt = d_txt.float() if partial else d_txt.to(gdt)
+    return d_img, d_txt, (g * dots).sum().float().reshape(1), g.sum().float().reshape(1)

@@ -22,6 +22,9 @@ What is executed is the reference's own code, imported from /root/reference/src
       -> proto_step_*.npz
   * ``training.zero_shot.accuracy`` / ``run`` and ``training.train.accuracy``
       -> zero_shot_eval.npz
+  * ``open_clip.loss.SigLipLoss`` forward + backward, world size 1 and with its ring exchange
+    on real gloo process groups of 2, 3 and 4 ranks
+      -> siglip.npz
 
 The fixtures hold both the inputs and the reference outputs, so tests never need the
 reference at run time (it does not exist on the GPU box).
@@ -337,6 +340,67 @@ def gen_zero_shot(tt):
     print("zero_shot_eval", accs_zs, accs_tt, rates)
 
 
+# ----------------------------------------------------------------------------------
+# 6. SigLipLoss (loss.py:453-560), world size 1 and on real gloo rings (world 2, 3, 4)
+# ----------------------------------------------------------------------------------
+def _siglip_once(open_clip, il, tl, scale, bias, rank, world):
+    il = il.clone().requires_grad_(True)
+    tl = tl.clone().requires_grad_(True)
+    s = torch.tensor(scale, dtype=il.dtype, requires_grad=True)
+    b = torch.tensor(bias, dtype=il.dtype, requires_grad=True)
+    mod = open_clip.loss.SigLipLoss(rank=rank, world_size=world)
+    loss = mod(il, tl, s, b)
+    loss.backward()
+    return dict(loss=loss.detach().numpy(), dI=il.grad.numpy(), dT=tl.grad.numpy(),
+                ds=s.grad.numpy(), db=b.grad.numpy())
+
+
+def _siglip_worker(rank, world, port, i_all, t_all, scale, bias, ret):
+    import torch.distributed as dist
+    sys.modules.setdefault("ftfy", types.ModuleType("ftfy"))
+    sys.path.insert(0, REF_SRC)
+    import open_clip
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    n = i_all.shape[0] // world
+    ret[rank] = _siglip_once(open_clip, i_all[rank * n:(rank + 1) * n], t_all[rank * n:(rank + 1) * n],
+                             scale, bias, rank, world)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def gen_siglip(open_clip):
+    import torch.multiprocessing as mp
+    out = {}
+    # world size 1: the init operating point (s = 10, b = -10, main.py:225-227) and a trained-like one
+    for name, n, d, sigma, scale, bias in (("init", 96, 64, 1.5, 10.0, -10.0),
+                                           ("hot", 130, 40, 3.0, 80.0, -12.0)):
+        i, t = synth_pairs(n, d, sigma, 900 + n, torch.float64)
+        i, t = i.bfloat16().double(), t.bfloat16().double()      # exactly representable in bf16
+        r = _siglip_once(open_clip, i, t, scale, bias, 0, 1)
+        r32 = _siglip_once(open_clip, i.float(), t.float(), scale, bias, 0, 1)
+        out.update({f"{name}_I": i.numpy(), f"{name}_T": t.numpy(), f"{name}_scale": np.float64(scale),
+                    f"{name}_bias": np.float64(bias)})
+        out.update({f"{name}_{k}_f64": v for k, v in r.items()})
+        out.update({f"{name}_{k}_f32": v for k, v in r32.items()})
+        print("siglip", name, float(r["loss"]), float(r32["loss"]))
+    for world, port in ((2, 29641), (3, 29643), (4, 29645)):
+        n_glob, d, scale, bias = 24 * world, 32, 20.0, -6.0
+        i, t = synth_pairs(n_glob, d, 2.0, 977 + world, torch.float64)
+        i, t = i.bfloat16().double(), t.bfloat16().double()
+        mgr = mp.Manager()
+        ret = mgr.dict()
+        mp.spawn(_siglip_worker, args=(world, port, i, t, scale, bias, ret), nprocs=world, join=True)
+        out.update({f"w{world}_I": i.numpy(), f"w{world}_T": t.numpy(), f"w{world}_scale": np.float64(scale),
+                    f"w{world}_bias": np.float64(bias)})
+        for r in range(world):
+            for k, v in ret[r].items():
+                out[f"w{world}_r{r}_{k}"] = v
+        print("siglip ring", world, [float(ret[r]["loss"]) for r in range(world)])
+    np.savez_compressed(os.path.join(HERE, "siglip.npz"), **out)
+
+
 def main():
     torch.manual_seed(0)
     torch.set_num_threads(4)
@@ -345,6 +409,7 @@ def main():
     gen_text_margins(tt)
     gen_proto_step(open_clip, tt)
     gen_zero_shot(tt)
+    gen_siglip(open_clip)
     gen_clip_dist()
 
 

@@ -103,3 +103,50 @@ def test_multirank_host_logic_matches_gloo_reference(world, port, one_sweep):
             else:
                 assert abs(got["ds"] - ref_ds) < 2e-5 * max(1.0, abs(ref_ds)), (key, r)
         assert ret[r]["bank_err"] < 1e-6 and ret[r]["bank_untouched"]
+
+
+def _siglip_worker(rank, world, port, ret):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, HERE)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import _abi_double
+    import latteclip_b200 as lb
+    from latteclip_b200 import _lib
+    _lib.siglip_fwd = _abi_double.siglip_fwd
+    _lib.siglip_bwd = _abi_double.siglip_bwd
+    g = np.load(os.path.join(HERE, "golden", "siglip.npz"))
+    i_all, t_all = torch.from_numpy(g[f"w{world}_I"]), torch.from_numpy(g[f"w{world}_T"])
+    n = i_all.shape[0] // world
+    il = i_all[rank * n:(rank + 1) * n].clone().requires_grad_(True)
+    tl = t_all[rank * n:(rank + 1) * n].clone().requires_grad_(True)
+    s = torch.tensor(float(g[f"w{world}_scale"]), dtype=torch.float64, requires_grad=True)
+    b = torch.tensor(float(g[f"w{world}_bias"]), dtype=torch.float64, requires_grad=True)
+    loss = lb.siglip._FusedSigLip.apply(il, tl, s, b, rank, world, None)
+    loss.backward()
+    ret[rank] = dict(loss=float(loss), dI=il.grad.numpy(), dT=tl.grad.numpy(), ds=float(s.grad),
+                     db=float(b.grad))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,port", [(2, 29741), (3, 29743), (4, 29745)])
+def test_siglip_host_logic_matches_gloo_ring_reference(world, port):
+    """One text all-gather + reduce-scatter of the text-side product against the reference's
+    neighbour-exchange ring (loss.py:521-558) recorded on gloo."""
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_siglip_worker, args=(world, port, ret), nprocs=world, join=True)
+    g = np.load(os.path.join(HERE, "golden", "siglip.npz"))
+    for r in range(world):
+        got = ret[r]
+        ref_loss = float(g[f"w{world}_r{r}_loss"])
+        assert abs(got["loss"] - ref_loss) < 1e-5 * abs(ref_loss)            # fp32 across the ABI
+        for nm in ("dI", "dT"):
+            ref = g[f"w{world}_r{r}_{nm}"]
+            err = np.linalg.norm(got[nm] - ref) / np.linalg.norm(ref)
+            assert err < 2e-5, (r, nm, err)
+        for nm in ("ds", "db"):
+            ref = float(g[f"w{world}_r{r}_{nm}"])
+            assert abs(got[nm] - ref) < 2e-5 * max(1.0, abs(ref)), (r, nm)

@@ -112,6 +112,10 @@ TC_CASES = [
     (200, 200, 3.0, 100.0, 0.0),        # ragged rows and ragged feature tail
     (1000, 768, 4.0, 100.0, 0.005),     # ViT-L width, rows not a tile multiple
     (4096, 512, 4.0, 100.0, 0.005),
+    # tile ranges whose last tile opens a new row block at an odd local index (the X block of that
+    # row block used to be loaded by nobody: regression test of the trailing-row-block load)
+    (2048, 256, 4.0, 100.0, 0.0),
+    (3000, 64, 4.0, 100.0, 0.0),
 ]
 
 

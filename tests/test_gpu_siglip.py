@@ -1,0 +1,171 @@
+"""GPU parity tests of the SigLipLoss kernels through the C ABI: against the golden
+vectors recorded from the reference's own SigLipLoss (world size 1 and its gloo ring) and against
+the fp64 oracle on the same rounded inputs.
+
+Tolerances (north_star): loss rel <= 1e-5; 16-bit-input gradients rel <= 2e-3 computed in fp32
+(2.6e-3 once rounded to bf16 outputs, as in test_gpu_clip.py)."""
+
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+LOSS_RTOL = 1e-5
+GRAD_RTOL_16 = 2e-3
+GRAD_RTOL_BF16_OUT = 2.6e-3
+
+
+def _f64(x):
+    if torch.is_tensor(x):
+        return x.detach().to(torch.float64).cpu()
+    return torch.as_tensor(np.asarray(x), dtype=torch.float64)
+
+
+def rel(a, b):
+    a, b = _f64(a), _f64(b)
+    return float((a - b).norm() / b.norm().clamp_min(1e-300))
+
+
+def synth(n, d, sigma, seed):
+    g = torch.Generator().manual_seed(seed)
+    i = F.normalize(torch.randn(n, d, generator=g), dim=1)
+    t = F.normalize(i + sigma * torch.randn(n, d, generator=g) / math.sqrt(d), dim=1)
+    return i, t
+
+
+@pytest.mark.parametrize("name", ["init", "hot"])
+def test_module_matches_reference_golden(name):
+    """latteclip_b200.SigLipLoss against open_clip's SigLipLoss outputs (inputs exact in bf16)."""
+    import latteclip_b200 as lb
+    g = load_golden("siglip.npz")
+    il = torch.from_numpy(g[f"{name}_I"]).to(DEV).bfloat16().requires_grad_(True)
+    tl = torch.from_numpy(g[f"{name}_T"]).to(DEV).bfloat16().requires_grad_(True)
+    assert torch.equal(il.detach().double().cpu(), torch.from_numpy(g[f"{name}_I"]))
+    s = torch.tensor(float(g[f"{name}_scale"]), device=DEV, requires_grad=True)
+    b = torch.tensor(float(g[f"{name}_bias"]), device=DEV, requires_grad=True)
+    out = lb.SigLipLoss()(il, tl, s, b, output_dict=True)
+    loss = out["contrastive_loss"]
+    assert loss.dim() == 0
+    loss.backward()
+    ref = float(g[f"{name}_loss_f64"])
+    assert abs(float(loss) - ref) <= LOSS_RTOL * abs(ref)
+    assert rel(il.grad, g[f"{name}_dI_f64"]) < GRAD_RTOL_BF16_OUT
+    assert rel(tl.grad, g[f"{name}_dT_f64"]) < GRAD_RTOL_BF16_OUT
+    assert abs(float(s.grad) - float(g[f"{name}_ds_f64"])) <= 2e-3 * abs(float(g[f"{name}_ds_f64"]))
+    assert abs(float(b.grad) - float(g[f"{name}_db_f64"])) <= 2e-3 * abs(float(g[f"{name}_db_f64"]))
+    # positional call without a bias and the materialising utilities
+    mod = lb.SigLipLoss()
+    l0 = mod(il.detach(), tl.detach(), s.detach(), None)
+    z = mod.get_logits(il.detach().float(), tl.detach().float(), s.detach())
+    lab = mod.get_ground_truth(z.device, z.dtype, z.shape[0])
+    want = -F.logsigmoid(lab * z).sum() / z.shape[0]
+    assert abs(float(l0) - float(want)) <= 1e-4 * abs(float(want))
+
+
+CASES = [(1, 8, 10.0, -10.0), (7, 24, 10.0, -10.0), (129, 40, 20.0, -5.0), (513, 72, 100.0, -12.0),
+         (300, 504, 30.0, 0.0), (1000, 512, 10.0, -10.0), (600, 768, 50.0, -8.0), (2048, 256, 117.0, -12.9)]
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("n,d,scale,bias", CASES)
+def test_kernels_match_oracle(n, d, scale, bias, dtype):
+    from latteclip_b200 import _lib
+    from oracle.siglip import siglip_all_ranks
+    i, t = synth(n, d, 2.0, 31 + n + d)
+    ib, tb = i.to(DEV).to(dtype), t.to(DEV).to(dtype)
+    lo, di, dt, ds, db = siglip_all_ranks([ib.float().cpu()], [tb.float().cpu()], scale, bias)
+    s, b = torch.tensor(scale, device=DEV), torch.tensor(bias, device=DEV)
+    one = torch.ones(1, device=DEV)
+    loss = _lib.siglip_fwd(ib, tb, 0, s, b)
+    assert abs(float(loss) - float(lo[0])) <= LOSS_RTOL * abs(float(lo[0]))
+    d_img, d_txt, d_s, d_b = _lib.siglip_bwd(ib, tb, 0, s, b, one, grad_dtype=torch.float32)
+    scale_i, scale_t = float(di[0].norm()), float(dt[0].norm())
+    assert rel(d_img, di[0]) < GRAD_RTOL_16 or float((d_img.double().cpu() - di[0]).norm()) < 1e-6 * max(scale_i, 1e-3)
+    assert rel(d_txt, dt[0]) < GRAD_RTOL_16 or float((d_txt.double().cpu() - dt[0]).norm()) < 1e-6 * max(scale_t, 1e-3)
+    assert abs(float(d_s) - float(ds[0])) <= 2e-3 * abs(float(ds[0])) + 1e-7
+    assert abs(float(d_b) - float(db[0])) <= 2e-3 * abs(float(db[0])) + 1e-7
+
+
+@pytest.mark.parametrize("world", [2, 3, 4])
+def test_rank_blocks_match_gloo_ring_golden(world):
+    """Every rank's C-ABI calls on one GPU (text rows stacked instead of all-gathered, text-side
+    partials summed instead of reduce-scattered) against the reference's ring run on gloo."""
+    from latteclip_b200 import _lib
+    g = load_golden("siglip.npz")
+    ib = torch.from_numpy(g[f"w{world}_I"]).to(DEV).bfloat16()
+    tb = torch.from_numpy(g[f"w{world}_T"]).to(DEV).bfloat16()
+    s = torch.tensor(float(g[f"w{world}_scale"]), device=DEV)
+    b = torch.tensor(float(g[f"w{world}_bias"]), device=DEV)
+    one = torch.ones(1, device=DEV)
+    n = ib.shape[0] // world
+    parts = []
+    for r in range(world):
+        sl = slice(r * n, (r + 1) * n)
+        loss = _lib.siglip_fwd(ib[sl], tb, r * n, s, b)
+        ref = float(g[f"w{world}_r{r}_loss"])
+        assert abs(float(loss) - ref) <= LOSS_RTOL * abs(ref)
+        d_img, d_part, d_s, d_b = _lib.siglip_bwd(ib[sl], tb, r * n, s, b, one, grad_dtype=torch.float32,
+                                                  partial=True)
+        assert d_part.shape == tuple(tb.shape) and d_part.dtype == torch.float32
+        parts.append(d_part)
+        assert rel(d_img, g[f"w{world}_r{r}_dI"]) < GRAD_RTOL_16
+        assert abs(float(d_s) - float(g[f"w{world}_r{r}_ds"])) <= 2e-3 * abs(float(g[f"w{world}_r{r}_ds"]))
+        assert abs(float(d_b) - float(g[f"w{world}_r{r}_db"])) <= 2e-3 * abs(float(g[f"w{world}_r{r}_db"]))
+    d_txt = sum(parts)
+    for r in range(world):
+        assert rel(d_txt[r * n:(r + 1) * n], g[f"w{world}_r{r}_dT"]) < GRAD_RTOL_16
+
+
+def test_unsupported_inputs_fail_loudly():
+    import latteclip_b200 as lb
+    i, t = synth(64, 64, 2.0, 1)
+    s, b = torch.tensor(10.0, device=DEV), torch.tensor(-10.0, device=DEV)
+    with pytest.raises(RuntimeError):
+        lb.SigLipLoss()(i.to(DEV), t.to(DEV), s, b)                  # fp32 features
+    with pytest.raises(RuntimeError):
+        lb.SigLipLoss()(i.to(DEV).bfloat16()[:, :60], t.to(DEV).bfloat16()[:, :60], s, b)   # dim % 8
+    with pytest.raises(RuntimeError):
+        lb.SigLipLoss()(i.to(DEV).bfloat16(), t.to(DEV).bfloat16()[:32], s, b)
+
+
+def test_full_size_32k_properties():
+    """N = 32768, D = 512: a row block against fp64, additivity over row blocks, and the Euler
+    identities of the bilinear logits (s * ds = sum <dI, I> = sum <dT, T>); db = sum of G."""
+    from latteclip_b200 import _lib
+    n, d = 32768, 512
+    i, t = synth(n, d, 4.0, 99)
+    ib, tb = i.to(DEV).bfloat16(), t.to(DEV).bfloat16()
+    s, b = torch.tensor(20.0, device=DEV), torch.tensor(-8.0, device=DEV)
+    one = torch.ones(1, device=DEV)
+    loss = float(_lib.siglip_fwd(ib, tb, 0, s, b))
+    blk = 4096
+    tot = 0.0
+    for r0 in range(0, n, blk):
+        lb_ = float(_lib.siglip_fwd(ib[r0:r0 + blk], tb, r0, s, b))
+        tot += lb_ * blk / n
+        if r0 == 3 * blk:
+            z = 20.0 * ib[r0:r0 + blk].double() @ tb.double().T - 8.0
+            z[torch.arange(blk), torch.arange(blk) + r0] *= -1.0
+            want = float(F.softplus(z).sum() / blk)
+            assert abs(lb_ - want) <= LOSS_RTOL * abs(want)
+    assert abs(tot - loss) <= LOSS_RTOL * abs(loss)
+    d_img, d_txt, d_s, d_b = _lib.siglip_bwd(ib, tb, 0, s, b, one, grad_dtype=torch.float32)
+    eul_i = float((d_img.double() * ib.double()).sum())
+    eul_t = float((d_txt.double() * tb.double()).sum())
+    sds = 20.0 * float(d_s)
+    assert abs(eul_i - sds) <= 2e-3 * abs(sds) and abs(eul_t - sds) <= 2e-3 * abs(sds)
+    rows = torch.randint(0, n, (64,), generator=torch.Generator().manual_seed(6)).to(DEV)
+    z = 20.0 * ib[rows].double() @ tb.double().T - 8.0
+    G = torch.sigmoid(z)
+    G[torch.arange(64), rows] -= 1.0
+    assert rel(d_img[rows], (20.0 / n) * G @ tb.double()) < GRAD_RTOL_16
+    zc = 20.0 * ib.double() @ tb[rows].double().T - 8.0           # [n, 64]
+    Gc = torch.sigmoid(zc)
+    Gc[rows, torch.arange(64)] -= 1.0
+    assert rel(d_txt[rows], (20.0 / n) * Gc.T @ ib.double()) < GRAD_RTOL_16

@@ -156,3 +156,35 @@ def test_feature_record_format_round_trip(tmp_path):
     assert ids.dtype == torch.int64
     assert np.array_equal(ids.numpy(), ozs.zeroshot_class_ids(names, class_names))
     assert np.array_equal(ids.numpy(), g["top_ids"][:, 0])
+
+
+# ------------------------------------------------------------------ SigLipLoss
+@pytest.mark.parametrize("name", ["init", "hot"])
+def test_siglip_w1_matches_reference(name):
+    from oracle.siglip import siglip_all_ranks
+    g = load_golden("siglip.npz")
+    i, t = torch.from_numpy(g[f"{name}_I"]), torch.from_numpy(g[f"{name}_T"])
+    s, b = float(g[f"{name}_scale"]), float(g[f"{name}_bias"])
+    for tag, dt, tol in (("f64", torch.float64, 1e-12), ("f32", torch.float32, 3e-6)):
+        lo, di, dt_, ds, db = siglip_all_ranks([i], [t], s, b, dt)
+        assert abs(float(lo[0]) - float(g[f"{name}_loss_{tag}"])) <= tol * abs(float(g[f"{name}_loss_{tag}"]))
+        gt = 1e-10 if tag == "f64" else 2e-5
+        assert rel(di[0], g[f"{name}_dI_{tag}"]) < gt and rel(dt_[0], g[f"{name}_dT_{tag}"]) < gt
+        assert abs(float(ds[0]) - float(g[f"{name}_ds_{tag}"])) <= max(gt, 2e-4 if tag == "f32" else 0) * abs(float(g[f"{name}_ds_{tag}"]))
+        assert abs(float(db[0]) - float(g[f"{name}_db_{tag}"])) <= max(gt, 2e-4 if tag == "f32" else 0) * abs(float(g[f"{name}_db_{tag}"]))
+
+
+@pytest.mark.parametrize("world", [2, 3, 4])
+def test_siglip_ring_emulation_matches_gloo_reference(world):
+    from oracle.siglip import siglip_all_ranks
+    g = load_golden("siglip.npz")
+    i, t = torch.from_numpy(g[f"w{world}_I"]), torch.from_numpy(g[f"w{world}_T"])
+    s, b = float(g[f"w{world}_scale"]), float(g[f"w{world}_bias"])
+    n = i.shape[0] // world
+    lo, di, dt_, ds, db = siglip_all_ranks([i[r * n:(r + 1) * n] for r in range(world)],
+                                           [t[r * n:(r + 1) * n] for r in range(world)], s, b)
+    for r in range(world):
+        assert abs(float(lo[r]) - float(g[f"w{world}_r{r}_loss"])) <= 1e-12 * abs(float(lo[r]))
+        assert rel(di[r], g[f"w{world}_r{r}_dI"]) < 1e-10 and rel(dt_[r], g[f"w{world}_r{r}_dT"]) < 1e-10
+        assert abs(float(ds[r]) - float(g[f"w{world}_r{r}_ds"])) <= 1e-10 * abs(float(ds[r]))
+        assert abs(float(db[r]) - float(g[f"w{world}_r{r}_db"])) <= 1e-10 * abs(float(db[r]))
