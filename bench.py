@@ -206,6 +206,41 @@ def prototype_kernel_rates(dev, peaks, batch=N_GLOBAL, dim=DIM, classes=47):
     return {"batch": batch, "dim": dim, "classes": classes, "dtype": "f32", "rows": out}
 
 
+def siglip_times(dev, n=None, dim=None, reps=10):
+    """SigLipLoss fwd + bwd (open_clip loss.py:453-560) at the headline shape on one GPU through the
+    drop-in module, split into forward sweep and backward (sweep + gradient GEMMs) by CUDA events.
+    Extra information beside the headline metric (same 6 n N D algorithmic FLOP per call)."""
+    import latteclip_b200 as lb
+    n = n or N_GLOBAL
+    dim = dim or DIM
+    i, t = synth_shard(n, dim, 0, 1, set_id=9)
+    il = i.to(dev).bfloat16().requires_grad_(True)
+    tl = t.to(dev).bfloat16().requires_grad_(True)
+    s = torch.tensor(10.0, device=dev, requires_grad=True)      # SigLIP init operating point,
+    b = torch.tensor(-10.0, device=dev, requires_grad=True)     # training/main.py:225-227
+    mod = lb.SigLipLoss()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    fwd_ms = bwd_ms = 0.0
+    last = 0.0
+    for k in range(3 + reps):
+        for x in (il, tl, s, b):
+            x.grad = None
+        ev[0].record()
+        loss = mod(il, tl, s, b)
+        ev[1].record()
+        loss.backward()
+        ev[2].record()
+        torch.cuda.synchronize()
+        if k >= 3:
+            fwd_ms += ev[0].elapsed_time(ev[1]) / reps
+            bwd_ms += ev[1].elapsed_time(ev[2]) / reps
+        last = float(loss.detach())
+    ms = fwd_ms + bwd_ms
+    return {"workload": f"SigLipLoss fwd+bwd, batch {n}, dim {dim}, bf16 features, scale 10, bias -10",
+            "ms_per_step": ms, "fwd_ms": fwd_ms, "bwd_ms": bwd_ms, "samples_per_s": n / (ms * 1e-3),
+            "alg_tflops": 6.0 * n * n * dim / (ms * 1e-3) / 1e12, "loss": last}
+
+
 def latteclip_head_times(dev, batch=512, dim=512, classes=47, reps=20, axis="quirk", cpu=True):
     """One LatteCLIP head step (train.py:384-530: pseudo-labels, margins, mixture + EMA, two
     ClipLoss calls sharing the image features, backward, bank update) at the reference's own
@@ -490,6 +525,12 @@ def _run_ours(args):
     if rank == 0 and world == 1:
         proto = prototype_kernel_rates(dev, peaks)
 
+    sig = None
+    if rank == 0 and world == 1:
+        _lib.clear_workspace_cache()
+        sig = siglip_times(dev)
+        _lib.clear_workspace_cache()
+
     head = head_big = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         head = latteclip_head_times(dev)
@@ -532,6 +573,8 @@ def _run_ours(args):
             line["cpu_baseline"] = cpu_base
         if proto is not None:
             line["prototype_kernels"] = proto
+        if sig is not None:
+            line["siglip"] = sig
         if head is not None:
             line["latteclip_head"] = head
             line["latteclip_head_32k"] = head_big

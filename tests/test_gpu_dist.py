@@ -42,6 +42,16 @@ def _worker(rank, world, port, n, d, dtype_name, p2p, ret):
         loss.backward()
         out[(local_loss, gwg)] = dict(loss=float(loss.detach()), dI=il.grad.float().cpu(),
                                       dT=tl.grad.float().cpu(), ds=float(s.grad))
+    if dtype != torch.float32:
+        # SigLipLoss: text all-gather, one sweep, text gradient reduce-scattered (P2P or NCCL)
+        il = i_all[rank * n:(rank + 1) * n].to(dev).to(dtype).requires_grad_(True)
+        tl = t_all[rank * n:(rank + 1) * n].to(dev).to(dtype).requires_grad_(True)
+        s = torch.tensor(20.0, device=dev, requires_grad=True)
+        b = torch.tensor(-6.0, device=dev, requires_grad=True)
+        loss = lb.SigLipLoss(rank=rank, world_size=world)(il, tl, s, b)
+        loss.backward()
+        out["siglip"] = dict(loss=float(loss.detach()), dI=il.grad.float().cpu(), dT=tl.grad.float().cpu(),
+                             ds=float(s.grad), db=float(b.grad))
     c = 11
     bank = F.normalize(torch.randn(c, d, generator=g), dim=1)
     preds = torch.randint(0, c, (n * world,), generator=g)
@@ -105,6 +115,19 @@ def test_nccl_cliploss_matches_oracle(dtype_name, n, d, p2p):
             assert abs(got - ref_sum) <= 2e-3 * abs(ref_sum) + 1e-6, (key, r)
         else:
             assert abs(dsv - dsr) <= 2e-3 * abs(dsr) + 1e-6, (key, r)
+    if dtype_name != "float32":
+        from oracle.siglip import siglip_all_ranks
+        lo, di, dt, ds, db = siglip_all_ranks(ish, tsh, 20.0, -6.0)
+        for r in range(world):
+            got = ret[r]["siglip"]
+            assert abs(got["loss"] - float(lo[r])) <= 1e-5 * abs(float(lo[r])), ("siglip", r)
+            e_i = float((got["dI"].double() - di[r]).norm() / di[r].norm())
+            e_t = float((got["dT"].double() - dt[r]).norm() / dt[r].norm())
+            print("siglip rank %d loss %.6f ref %.6f dI %.3e dT %.3e ds %.4e ref %.4e db %.4e ref %.4e" %
+                  (r, got["loss"], float(lo[r]), e_i, e_t, got["ds"], float(ds[r]), got["db"], float(db[r])))
+            assert e_i < gtol and e_t < gtol, ("siglip", r, e_i, e_t)
+            assert abs(got["ds"] - float(ds[r])) <= 2e-3 * abs(float(ds[r])) + 1e-6
+            assert abs(got["db"] - float(db[r])) <= 2e-3 * abs(float(db[r])) + 1e-6
     c = 11
     bank = F.normalize(torch.randn(c, d, generator=g), dim=1)
     preds = torch.randint(0, c, (n * world,), generator=g)
