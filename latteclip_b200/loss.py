@@ -4,7 +4,8 @@ Mirrors the reference interface (same names, arguments, defaults and error behav
   * ``gather_features``  -- /root/reference/src/open_clip/loss.py:19-63
   * ``ClipLoss``         -- loss.py:66-130 (``__init__`` :68-87, ``get_ground_truth`` :89-100,
                             ``get_logits`` :102-118, ``forward`` :120-130)
-  * ``create_loss``      -- /root/reference/src/open_clip/factory.py:323-351 (ClipLoss branch)
+  * ``create_loss``      -- /root/reference/src/open_clip/factory.py:323-351 (ClipLoss and SigLipLoss
+                            branches; ``SigLipLoss`` itself is in ``siglip.py``)
 
 ``ClipLoss.forward`` is the hot path: it never materialises the logit matrices.  It calls
 the CUDA extension (C ABI in include/latte_b200.h) through ``latteclip_b200._lib`` inside a
