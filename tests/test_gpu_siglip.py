@@ -169,3 +169,43 @@ def test_full_size_32k_properties():
     Gc = torch.sigmoid(zc)
     Gc[rows, torch.arange(64)] -= 1.0
     assert rel(d_txt[rows], (20.0 / n) * Gc.T @ ib.double()) < GRAD_RTOL_16
+
+
+def test_tile_range_shapes_fuzz():
+    """Random (rows of this rank, all columns) shapes: the 74 CTA pairs cut the (row block, column
+    tile) space at arbitrary places, including right after the first tile of a row block (the case
+    that used to leave the MMA issuer waiting).  ClipLoss rows-forward, SigLIP forward and SigLIP
+    backward against torch fp64 on the GPU."""
+    from latteclip_b200 import _lib
+    rng = np.random.default_rng(20260)
+    shapes = [(2048, 2048), (3000, 3000), (2304, 2304), (768, 3072), (1280, 6400)]
+    for _ in range(19):
+        world = int(rng.integers(1, 5))
+        n_loc = int(rng.integers(1, 2600))
+        shapes.append((n_loc, n_loc * world))
+    d = 64
+    s, b = torch.tensor(25.0, device=DEV), torch.tensor(-7.0, device=DEV)
+    one = torch.ones(1, device=DEV)
+    for n_loc, n_all in shapes:
+        i, t = synth(n_all, d, 3.0, n_loc + n_all)
+        ib, tb = i.to(DEV).bfloat16(), t.to(DEV).bfloat16()
+        off = (n_all // n_loc - 1) * n_loc
+        il = ib[off:off + n_loc]
+        z = 25.0 * il.double() @ tb.double().T
+        idx = torch.arange(n_loc, device=DEV)
+        # ClipLoss row sweep (payload: 2N column partials, then row LSE / nll / label logit)
+        payload = _lib.clip_fwd_rows(il, tb, off, s)
+        row_lse = payload[2 * n_all:2 * n_all + n_loc]
+        assert torch.allclose(row_lse.double(), torch.logsumexp(z, 1), rtol=0, atol=2e-4), (n_loc, n_all)
+        # SigLIP
+        zs = z - 7.0
+        lab = -torch.ones_like(zs)
+        lab[idx, idx + off] = 1.0
+        want = float(F.softplus(-lab * zs).sum() / n_loc)
+        got = float(_lib.siglip_fwd(il, tb, off, s, b))
+        assert abs(got - want) <= LOSS_RTOL * abs(want), (n_loc, n_all, got, want)
+        d_img, d_part, d_s, d_b = _lib.siglip_bwd(il, tb, off, s, b, one, grad_dtype=torch.float32, partial=True)
+        G = (torch.sigmoid(zs) - (lab > 0).double()) / n_loc
+        assert rel(d_img, 25.0 * G @ tb.double()) < GRAD_RTOL_16, (n_loc, n_all)
+        assert rel(d_part, 25.0 * G.T @ il.double()) < GRAD_RTOL_16, (n_loc, n_all)
+        assert abs(float(d_b) - float(G.sum())) <= 2e-3 * abs(float(G.sum())) + 1e-7
