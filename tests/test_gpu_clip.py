@@ -470,3 +470,35 @@ def test_cta_pair_path_odd_shapes(n, d, dtype):
             # n = 1 (gradient exactly zero) or a fully converged batch (loss ~ 1e-15): only
             # rounding of exp(0) is left, far below any gradient that matters
             assert float(di.abs().max()) < 1e-6 * scale and float(dt.abs().max()) < 1e-6 * scale
+
+
+def test_clip_shape_fuzz_w1():
+    """Random batch sizes and feature widths through the whole world-size-1 path (shared-tile forward,
+    gradient sweep, stream-K GEMMs) against torch fp64 on the GPU: the tile ranges of the 74 CTA
+    pairs, the ragged last row block / column tile and the feature tail all move with the shape."""
+    import latteclip_b200 as lb
+    rng = np.random.default_rng(777)
+    dev = torch.device("cuda:0")
+    shapes = [(2304, 64), (1965, 520), (2545, 768)]
+    for _ in range(17):
+        shapes.append((int(rng.integers(2, 3600)), int(rng.integers(1, 97)) * 8))
+    for n, d in shapes:
+        dtype = torch.bfloat16 if (n + d) % 2 == 0 else torch.float16
+        i, t = synth(n, d, 4.0, n * 7 + d)
+        il = i.to(dev).to(dtype).requires_grad_(True)
+        tl = t.to(dev).to(dtype).requires_grad_(True)
+        s = torch.tensor(100.0, device=dev, requires_grad=True)
+        loss = lb.ClipLoss()(il, tl, s)
+        loss.backward()
+        I, T = il.detach().double().requires_grad_(True), tl.detach().double().requires_grad_(True)
+        S = torch.tensor(100.0, device=dev, dtype=torch.float64, requires_grad=True)
+        z = S * I @ T.T
+        lab = torch.arange(n, device=dev)
+        ref = 0.5 * (F.cross_entropy(z, lab) + F.cross_entropy(z.T, lab))
+        ref.backward()
+        assert abs(float(loss.detach()) - float(ref)) <= LOSS_RTOL * abs(float(ref)) + 2e-5, (n, d)
+        tol = GRAD_RTOL_BF16_OUT if dtype == torch.bfloat16 else GRAD_RTOL_16
+        for got, want in ((il.grad, I.grad), (tl.grad, T.grad)):
+            err = float((got.double() - want).norm())
+            assert err <= tol * float(want.norm()) + 1e-6 * float(want.norm()) + 1e-9, (n, d, err, float(want.norm()))
+        assert abs(float(s.grad) - float(S.grad)) <= 2e-3 * abs(float(S.grad)) + 1e-6, (n, d)
