@@ -107,20 +107,48 @@ constexpr int kModeFwdBoth = 2;   // forward, world size 1: row partials + colum
 constexpr int kModeSigFwd = 3;    // SigLIP forward: sum of softplus(-label * z) over the tile range
 constexpr int kModeSigGrad = 4;   // SigLIP backward: G = sigmoid(z) - delta
 
-// log1p(t) = t * q(t) on [0, 1]: degree-8 Chebyshev fit of log1p(t)/t, relative error 2e-7 in fp32
-// Horner form (MUFU lg2 near 1 has an ABSOLUTE error of 2^-22, useless for the small terms that
-// make up most of a sigmoid loss).
-__device__ __forceinline__ float log1p_unit(float t) {
-  float q = 0.00525352f;
-  q = fmaf(q, t, -0.02958887f);
-  q = fmaf(q, t, 0.07836246f);
-  q = fmaf(q, t, -0.13674858f);
-  q = fmaf(q, t, 0.19111485f);
-  q = fmaf(q, t, -0.24844388f);
-  q = fmaf(q, t, 0.33319275f);
-  q = fmaf(q, t, -0.49999502f);
-  q = fmaf(q, t, 0.99999997f);
-  return t * q;
+// two fp32 lanes per instruction (FFMA2 on sm_100a)
+__device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack_f32x2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t add_f32x2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t mul_f32x2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+// log1p(t0) + log1p(t1) for arguments in [0, 1]: log1p(t) = t * q(t) with q the degree-8 Chebyshev
+// fit of log1p(t)/t (relative error 2e-7 in fp32 Horner form; MUFU lg2 near 1 only has an ABSOLUTE
+// error of 2^-22, useless for the small terms that make up most of a sigmoid loss), both arguments
+// in one chain of FFMA2.
+__device__ __forceinline__ float log1p_unit_pair_sum(float t0, float t1) {
+  const uint64_t t = pack_f32x2(t0, t1);
+  uint64_t q = pack_f32x2(0.00525352f, 0.00525352f);
+  q = fma_f32x2(q, t, pack_f32x2(-0.02958887f, -0.02958887f));
+  q = fma_f32x2(q, t, pack_f32x2(0.07836246f, 0.07836246f));
+  q = fma_f32x2(q, t, pack_f32x2(-0.13674858f, -0.13674858f));
+  q = fma_f32x2(q, t, pack_f32x2(0.19111485f, 0.19111485f));
+  q = fma_f32x2(q, t, pack_f32x2(-0.24844388f, -0.24844388f));
+  q = fma_f32x2(q, t, pack_f32x2(0.33319275f, 0.33319275f));
+  q = fma_f32x2(q, t, pack_f32x2(-0.49999502f, -0.49999502f));
+  q = fma_f32x2(q, t, pack_f32x2(0.99999997f, 0.99999997f));
+  float r0, r1;
+  unpack_f32x2(mul_f32x2(q, t), r0, r1);
+  return r0 + r1;
 }
 
 template <int MODE, bool TAIL>
@@ -548,25 +576,41 @@ pair_sweep_kernel(const __grid_constant__ CUtensorMap tmy, const __grid_constant
           const int valid = !row_ok ? 0 : (colh + 32 <= p.n_all ? 32 : (colh >= p.n_all ? 0 : (int)(p.n_all - colh)));
           uint32_t packed[16];
           float dsh = 0.f, dbh = 0.f;
+          const uint64_t c2p = pack_f32x2(c2, c2), b2p = pack_f32x2(b2, b2), onep = pack_f32x2(1.f, 1.f);
+          const uint64_t scp = pack_f32x2(kSigScale, kSigScale);
+          uint64_t dsp = pack_f32x2(0.f, 0.f), dbp = pack_f32x2(0.f, 0.f);
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
-            float g[2];
+            // packed fp32 pairs (FFMA2 / FADD2 / FMUL2) wherever both lanes do the same thing
+            const uint64_t vp = pack_f32x2(__uint_as_float(r[i]), __uint_as_float(r[i + 1]));
+            float z[2], t[2], den[2], tr[2], sg[2];
+            unpack_f32x2(fma_f32x2(vp, c2p, b2p), z[0], z[1]);
+            t[0] = fast_exp2(-fabsf(z[0]));
+            t[1] = fast_exp2(-fabsf(z[1]));
+            const uint64_t tp = pack_f32x2(t[0], t[1]);
+            unpack_f32x2(add_f32x2(tp, onep), den[0], den[1]);
+            const float rr[2] = {__fdividef(1.0f, den[0]), __fdividef(1.0f, den[1])};
+            unpack_f32x2(mul_f32x2(tp, pack_f32x2(rr[0], rr[1])), tr[0], tr[1]);
 #pragma unroll
             for (int x = 0; x < 2; ++x) {
-              const float v = __uint_as_float(r[i + x]);
-              const float z2 = fmaf(v, c2, b2);
-              const float t = fast_exp2(-fabsf(z2));
-              const float rr = __fdividef(1.0f, 1.0f + t);
-              const float tr = t * rr;
-              const bool pos = z2 >= 0.f;
-              float sg = pos ? rr : tr;                      // sigmoid(z)
-              if (i + x == want) sg = pos ? -tr : -rr;       // sigmoid(z) - 1 without cancellation
-              if (i + x >= valid) sg = 0.f;
-              dsh = fmaf(sg, v, dsh);
-              dbh += sg;
-              g[x] = sg * kSigScale;
+              const bool pos = z[x] >= 0.f;
+              sg[x] = pos ? rr[x] : tr[x];                        // sigmoid(z)
+              if (i + x == want) sg[x] = pos ? -tr[x] : -rr[x];   // sigmoid(z) - 1 without cancellation
+              if (i + x >= valid) sg[x] = 0.f;
             }
-            packed[i >> 1] = pack2(g[0], g[1]);
+            const uint64_t sgp = pack_f32x2(sg[0], sg[1]);
+            dsp = fma_f32x2(sgp, vp, dsp);
+            dbp = add_f32x2(dbp, sgp);
+            float g0, g1;
+            unpack_f32x2(mul_f32x2(sgp, scp), g0, g1);
+            packed[i >> 1] = pack2(g0, g1);
+          }
+          {
+            float a0, a1, b0, b1;
+            unpack_f32x2(dsp, a0, a1);
+            unpack_f32x2(dbp, b0, b1);
+            dsh = a0 + a1;
+            dbh = b0 + b1;
           }
           ds_acc += dsh;
           db_acc += dbh;
@@ -627,20 +671,19 @@ pair_sweep_kernel(const __grid_constant__ CUtensorMap tmy, const __grid_constant
           int want = -1;
           if (row_ok && label >= colh && label < colh + 32) want = (int)(label - colh);
           const int valid = !row_ok ? 0 : (colh + 32 <= p.n_all ? 32 : (colh >= p.n_all ? 0 : (int)(p.n_all - colh)));
-          float small0 = 0.f, small1 = 0.f, big = 0.f;      // ln units / log2 units
+          float small0 = 0.f, big = 0.f;                    // ln units / log2 units
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
             float z0 = fmaf(__uint_as_float(r[i]), c2, b2);
             float z1 = fmaf(__uint_as_float(r[i + 1]), c2, b2);
             if (i >= valid) z0 = -INFINITY;
             if (i + 1 >= valid) z1 = -INFINITY;
-            small0 += log1p_unit(fast_exp2(-fabsf(z0)));
-            small1 += log1p_unit(fast_exp2(-fabsf(z1)));
+            small0 += log1p_unit_pair_sum(fast_exp2(-fabsf(z0)), fast_exp2(-fabsf(z1)));
             big += fmaxf(z0, 0.f) + fmaxf(z1, 0.f);
             if (i == want) big -= z0;
             if (i + 1 == want) big -= z1;
           }
-          const float term = fmaf(big, kLn2, small0 + small1);
+          const float term = fmaf(big, kLn2, small0);
           const float y = term - comp;               // Kahan
           const float tsum = sum + y;
           comp = (tsum - sum) - y;
@@ -660,6 +703,10 @@ pair_sweep_kernel(const __grid_constant__ CUtensorMap tmy, const __grid_constant
       }
     } else {
       // ======================================================== forward
+      constexpr bool kBothSides = MODE == kModeFwdBoth;
+      // exponent FMA, sums and column weights on packed fp32 pairs (FFMA2 / FADD2 / FMUL2: same
+      // roundings, half the issue slots; the epilogue is issue-bound).  false = scalar reference form
+      constexpr bool kPackedMath = true;
       // column-partial exchange between the four lane-quarter warps of one half tile
       float* colbuf = reinterpret_cast<float*>(smem + (stage_base - smem_base));   // [2][2][2][4][64]
       float* refbuf = colbuf + 2 * 2 * 2 * 4 * 64;                                  // [2][2][2][4][2]
@@ -723,25 +770,44 @@ pair_sweep_kernel(const __grid_constant__ CUtensorMap tmy, const __grid_constant
           }
           const float m_new = fmaxf(m, fmaxf(tmax0, tmax1) * c2);
           if (m_new > -INFINITY) {
-            float acc0 = 0.f, acc1 = 0.f;
+            if constexpr (kPackedMath) {
+              // same roundings as the scalar form, two lanes per FFMA2 / FADD2
+              const uint64_t c2p = pack_f32x2(c2, c2), nmp = pack_f32x2(-m_new, -m_new);
+              uint64_t accp = pack_f32x2(0.f, 0.f);
 #pragma unroll
-            for (int i = 0; i < 32; i += 2) {
-              const float e0 = fast_exp2(fmaf(__uint_as_float(r[i]), c2, -m_new));
-              const float e1 = fast_exp2(fmaf(__uint_as_float(r[i + 1]), c2, -m_new));
-              acc0 += e0;
-              acc1 += e1;
-              if constexpr (MODE == kModeFwdBoth) {
+              for (int i = 0; i < 32; i += 2) {
+                float x0, x1;
+                unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(r[i]), __uint_as_float(r[i + 1])), c2p, nmp),
+                             x0, x1);
+                const float e0 = fast_exp2(x0), e1 = fast_exp2(x1);
+                accp = add_f32x2(accp, pack_f32x2(e0, e1));
                 r[i] = __float_as_uint(e0);
                 r[i + 1] = __float_as_uint(e1);
               }
+              float acc0, acc1;
+              unpack_f32x2(accp, acc0, acc1);
+              l = l * fast_exp2(m - m_new) + (acc0 + acc1);
+            } else {
+              float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll
+              for (int i = 0; i < 32; i += 2) {
+                const float e0 = fast_exp2(fmaf(__uint_as_float(r[i]), c2, -m_new));
+                const float e1 = fast_exp2(fmaf(__uint_as_float(r[i + 1]), c2, -m_new));
+                acc0 += e0;
+                acc1 += e1;
+                if constexpr (kBothSides) {
+                  r[i] = __float_as_uint(e0);
+                  r[i + 1] = __float_as_uint(e1);
+                }
+              }
+              l = l * fast_exp2(m - m_new) + (acc0 + acc1);
             }
-            l = l * fast_exp2(m - m_new) + (acc0 + acc1);
             m = m_new;
-          } else if constexpr (MODE == kModeFwdBoth) {
+          } else if constexpr (kBothSides) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) r[i] = 0u;
           }
-          if constexpr (MODE == kModeFwdBoth) {
+          if constexpr (kBothSides) {
             // Column sums of the same exponentials: weight row i by 2^(m_i - M_w) (M_w = the
             // largest running max among the warp's rows), add over the 32 lanes with a halving
             // butterfly (lane c ends with column c).
@@ -750,23 +816,49 @@ pair_sweep_kernel(const __grid_constant__ CUtensorMap tmy, const __grid_constant
             for (int o = 16; o > 0; o >>= 1) mw = fmaxf(mw, __shfl_xor_sync(0xffffffffu, mw, o));
             const float w = (row_ok && m > -INFINITY) ? fast_exp2(m - mw) : 0.f;
             float v[32];
+            if constexpr (kPackedMath) {
+              const uint64_t wp = pack_f32x2(w, w);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * w;
+              for (int i = 0; i < 32; i += 2)
+                unpack_f32x2(mul_f32x2(pack_f32x2(__uint_as_float(r[i]), __uint_as_float(r[i + 1])), wp),
+                             v[i], v[i + 1]);
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-              const bool up = (lane & o) != 0;
+              for (int o = 16; o > 1; o >>= 1) {
+                const bool up = (lane & o) != 0;
 #pragma unroll
-              for (int kk = 0; kk < o; ++kk) {
-                const float send = up ? v[kk] : v[kk + o];
-                const float keep = up ? v[kk + o] : v[kk];
-                v[kk] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+                for (int kk = 0; kk < o; kk += 2) {
+                  const float s0 = up ? v[kk] : v[kk + o], s1 = up ? v[kk + 1] : v[kk + 1 + o];
+                  const float k0 = up ? v[kk + o] : v[kk], k1 = up ? v[kk + 1 + o] : v[kk + 1];
+                  const float g0 = __shfl_xor_sync(0xffffffffu, s0, o);
+                  const float g1 = __shfl_xor_sync(0xffffffffu, s1, o);
+                  unpack_f32x2(add_f32x2(pack_f32x2(k0, k1), pack_f32x2(g0, g1)), v[kk], v[kk + 1]);
+                }
+              }
+              {
+                const bool up = (lane & 1) != 0;
+                const float send = up ? v[0] : v[1];
+                const float keep = up ? v[1] : v[0];
+                v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * w;
+#pragma unroll
+              for (int o = 16; o > 0; o >>= 1) {
+                const bool up = (lane & o) != 0;
+#pragma unroll
+                for (int kk = 0; kk < o; ++kk) {
+                  const float send = up ? v[kk] : v[kk + o];
+                  const float keep = up ? v[kk + o] : v[kk];
+                  v[kk] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+                }
               }
             }
             cb_w[h * 32 + lane] = v[0];
             if (lane == 0) rf_w[h] = mw;
           }
         }
-        if constexpr (MODE == kModeFwdBoth) {
+        if constexpr (kBothSides) {
           // merge the four lane-quarter warps: warp q finishes columns [16q, 16q + 16)
           named_bar_sync(1 + group * 2 + half, 128);
           if (lane < 16) {
