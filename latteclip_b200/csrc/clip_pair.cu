@@ -707,6 +707,9 @@ pair_sweep_kernel(const __grid_constant__ CUtensorMap tmy, const __grid_constant
       // exponent FMA, sums and column weights on packed fp32 pairs (FFMA2 / FADD2 / FMUL2: same
       // roundings, half the issue slots; the epilogue is issue-bound).  false = scalar reference form
       constexpr bool kPackedMath = true;
+      // (Column sums through shared memory -- 8 STS.128 + 8 LDS.128 + 2 shuffle steps per half tile
+      // instead of the 31-shuffle butterfly below -- were measured 11 % SLOWER on the same box:
+      // the MMA's B-operand reads and the TMA ring already take most of the shared-memory bandwidth.)
       // column-partial exchange between the four lane-quarter warps of one half tile
       float* colbuf = reinterpret_cast<float*>(smem + (stage_base - smem_base));   // [2][2][2][4][64]
       float* refbuf = colbuf + 2 * 2 * 2 * 4 * 64;                                  // [2][2][2][4][2]
