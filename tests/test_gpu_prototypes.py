@@ -279,3 +279,37 @@ def test_zero_shot_accuracy_matches_oracle(b, d, c, dtype):
     assert torch.allclose(top_logits.cpu().double(), want_logits, rtol=0, atol=2e-4)
     for a, w in zip(accs, want):
         assert abs(a - w) <= int(tie.sum())
+
+
+def test_extract_feature_records_with_mock_tower(tmp_path):
+    """train.py:1336-1381 through the drop-in: a pass-through image tower, records written in the
+    reference's pkl format and read back the way data.py:393-396 does."""
+    from types import SimpleNamespace
+    from latteclip_b200 import zero_shot as zs
+    from oracle import zero_shot as ozs
+    g = load_golden("zero_shot_eval.npz")
+    feats, clf = torch.from_numpy(g["feats"]), torch.from_numpy(g["classifier"]).to(DEV)
+    target = torch.from_numpy(g["target"])
+    class_names = [f"class {c}" for c in range(clf.shape[1])]
+    ids = [f"img_{k:05d}" for k in range(feats.shape[0])]
+
+    class Tower(torch.nn.Module):
+        def encode_image(self, images, normalize=True):
+            return images
+
+    b = int(g["batch"])
+    batches = [(ids[k:k + b], feats[k:k + b], target[k:k + b]) for k in range(0, feats.shape[0], b)]
+    args = SimpleNamespace(precision="fp32", device=DEV)
+    records, rates = zs.extract_feature_records(Tower(), clf, batches, args, class_names)
+    assert np.allclose(rates, g["rates"], rtol=0, atol=1e-12)
+    want = ozs.feature_records(ids, feats, torch.from_numpy(g["top_ids"]), torch.from_numpy(g["top_logits"]),
+                               target, class_names)
+    path = zs.save_feature_records(records, str(tmp_path), "train")
+    back = zs.load_key_to_clip_prediction(path)
+    assert list(back) == ids
+    for k in ids:
+        assert np.array_equal(back[k]["top_class_ids"], want[k]["top_class_ids"])
+        assert back[k]["class_names"] == want[k]["class_names"]
+        assert back[k]["gt_classname"] == want[k]["gt_classname"] and back[k]["gt_class_id"] == want[k]["gt_class_id"]
+        assert np.array_equal(back[k]["image"], want[k]["image"])
+        assert np.allclose(back[k]["top_logit"], want[k]["top_logit"], rtol=0, atol=2e-5)
