@@ -76,3 +76,51 @@ def test_product_code_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src, f
+
+
+def test_siglip_entry_points_reject_bad_arguments_without_a_gpu(lib):
+    n = ctypes.c_size_t(0)
+    assert lib.latte_siglip_supported(1, 512) == 1 and lib.latte_siglip_supported(2, 768) == 1
+    assert lib.latte_siglip_supported(0, 512) == 0          # fp32 features
+    assert lib.latte_siglip_supported(1, 60) == 0 and lib.latte_siglip_supported(1, 1024) == 0
+    assert lib.latte_siglip_workspace_bytes(256, 1024, 512, 1, 1, 0, ctypes.byref(n)) == 0 and n.value > 0
+    fwd_only = ctypes.c_size_t(0)
+    assert lib.latte_siglip_workspace_bytes(256, 1024, 512, 1, 0, 0, ctypes.byref(fwd_only)) == 0
+    assert fwd_only.value < n.value
+    assert lib.latte_siglip_workspace_bytes(256, 128, 512, 1, 0, 0, ctypes.byref(n)) == -1    # n_all < n_loc
+    assert lib.latte_siglip_workspace_bytes(256, 256, 512, 0, 0, 0, ctypes.byref(n)) != 0     # fp32
+    assert lib.latte_siglip_fwd(None, 0, None, 0, 1, 1, 1, 8, 0, None, None, None, None, 0, None) == -1
+    assert lib.latte_siglip_bwd(None, 0, None, 0, 1, 1, 1, 8, 0, None, None, None, None, None, 1, 8,
+                                None, None, 0, None, None, None, 0, None) == -1
+
+
+def test_factory_and_module_contracts_on_cpu():
+    """create_loss mirrors factory.py:323-351; argument errors surface before any kernel launch."""
+    from types import SimpleNamespace
+    import torch
+    import latteclip_b200 as lb
+    base = dict(model="ViT-B-32", siglip=False, distill=False, local_loss=True, gather_with_grad=True,
+                rank=0, world_size=1, horovod=False)
+    loss = lb.create_loss(SimpleNamespace(**base))
+    assert isinstance(loss, lb.ClipLoss) and loss.local_loss and loss.gather_with_grad and loss.cache_labels
+    assert len(list(loss.parameters())) == 0
+    sig = lb.create_loss(SimpleNamespace(**dict(base, siglip=True, rank=3, world_size=8)))
+    assert isinstance(sig, lb.SigLipLoss) and sig.rank == 3 and sig.world_size == 8
+    assert len(list(sig.parameters())) == 0
+    with pytest.raises(NotImplementedError):
+        lb.create_loss(SimpleNamespace(**dict(base, model="coca_ViT-B-32")))
+    with pytest.raises(AssertionError):
+        lb.create_loss(SimpleNamespace(**dict(base, siglip=True, horovod=True)))
+    with pytest.raises(AssertionError):
+        lb.SigLipLoss(use_horovod=True)
+    x = torch.nn.functional.normalize(torch.randn(16, 64), dim=1)
+    with pytest.raises(RuntimeError):                       # fp32 features: no silent cast, no fallback
+        sig(x, x, torch.tensor(10.0), torch.tensor(-10.0))
+    with pytest.raises(RuntimeError):                       # shape mismatch
+        sig(x.bfloat16(), x.bfloat16()[:8], torch.tensor(10.0), torch.tensor(-10.0))
+    with pytest.raises(RuntimeError):
+        loss(x, x[:8], torch.tensor(100.0))
+    # materialising utilities stay plain torch
+    z = sig.get_logits(x, x, torch.tensor(10.0), torch.tensor(-10.0))
+    lab = sig.get_ground_truth(z.device, z.dtype, 16)
+    assert z.shape == (16, 16) and float(lab.diagonal().min()) == 1.0 and float(lab.sum()) == 16 - 240
