@@ -209,3 +209,42 @@ def test_tile_range_shapes_fuzz():
         assert rel(d_img, 25.0 * G @ tb.double()) < GRAD_RTOL_16, (n_loc, n_all)
         assert rel(d_part, 25.0 * G.T @ il.double()) < GRAD_RTOL_16, (n_loc, n_all)
         assert abs(float(d_b) - float(G.sum())) <= 2e-3 * abs(float(G.sum())) + 1e-7
+
+
+def test_full_size_rank_block_cfg4_shape():
+    """BASELINE cfg4 shape (N = 65536, D = 768, 8 ranks, n = 8192): rank 5's forward and backward
+    (fp32 partial of the text-side product) against fp64 on sampled rows / columns."""
+    from latteclip_b200 import _lib
+    world, n, d, r = 8, 8192, 768, 5
+    N = world * n
+    i, t = synth(N, d, 6.0, 505)
+    ib, tb = i.to(DEV).bfloat16(), t.to(DEV).bfloat16()
+    del i, t
+    s, b = torch.tensor(30.0, device=DEV), torch.tensor(-9.0, device=DEV)
+    one = torch.ones(1, device=DEV)
+    sl = slice(r * n, (r + 1) * n)
+    loss = float(_lib.siglip_fwd(ib[sl], tb, r * n, s, b))
+    # the loss of a 1024-row sub-block is an independent call with its own label offset
+    sub = slice(r * n + 2048, r * n + 3072)
+    z = 30.0 * ib[sub].double() @ tb.double().T - 9.0
+    idx = torch.arange(1024, device=DEV)
+    z[idx, idx + r * n + 2048] *= -1.0
+    want = float(F.softplus(z).sum() / 1024)
+    got = float(_lib.siglip_fwd(ib[sub], tb, r * n + 2048, s, b))
+    assert abs(got - want) <= LOSS_RTOL * abs(want)
+    parts = sum(float(_lib.siglip_fwd(ib[r * n + k:r * n + k + 1024], tb, r * n + k, s, b)) for k in range(0, n, 1024))
+    assert abs(parts / 8 - loss) <= LOSS_RTOL * abs(loss)
+    d_img, d_part, d_s, d_b = _lib.siglip_bwd(ib[sl], tb, r * n, s, b, one, grad_dtype=torch.float32, partial=True)
+    assert d_part.shape == (N, d)
+    g = torch.Generator().manual_seed(9)
+    own = (r * n + torch.randint(0, n, (48,), generator=g)).to(DEV)
+    zo = 30.0 * ib[own].double() @ tb.double().T - 9.0
+    G = torch.sigmoid(zo)
+    G[torch.arange(48), own] -= 1.0
+    assert rel(d_img[own - r * n], (30.0 / n) * G @ tb.double()) < GRAD_RTOL_16
+    cols = torch.randint(0, N, (48,), generator=g).to(DEV)
+    zc = 30.0 * ib[sl].double() @ tb[cols].double().T - 9.0            # [n, 48]
+    Gc = torch.sigmoid(zc) - (torch.arange(r * n, (r + 1) * n, device=DEV)[:, None] == cols[None, :]).double()
+    assert rel(d_part[cols], (30.0 / n) * Gc.T @ ib[sl].double()) < GRAD_RTOL_16
+    eul = float((d_img.double() * ib[sl].double()).sum())
+    assert abs(eul - 30.0 * float(d_s)) <= 2e-3 * abs(eul) + 1e-6
