@@ -107,6 +107,9 @@ constexpr int kModeFwdBoth = 2;   // forward, world size 1: row partials + colum
 constexpr int kModeSigFwd = 3;    // SigLIP forward: sum of softplus(-label * z) over the tile range
 constexpr int kModeSigGrad = 4;   // SigLIP backward: G = sigmoid(z) - delta
 
+struct TrueTag { static constexpr bool value = true; };
+struct FalseTag { static constexpr bool value = false; };
+
 // two fp32 lanes per instruction (FFMA2 on sm_100a)
 __device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi) {
   uint64_t r;
@@ -574,37 +577,46 @@ pair_sweep_kernel(const __grid_constant__ CUtensorMap tmy, const __grid_constant
           int want = -1;
           if (row_ok && label >= colh && label < colh + 32) want = (int)(label - colh);
           const int valid = !row_ok ? 0 : (colh + 32 <= p.n_all ? 32 : (colh >= p.n_all ? 0 : (int)(p.n_all - colh)));
+          // warp-uniform: no label entry, no ragged column, no row past the end in this 32x32 piece
+          const bool plain = !(warp_label0 < colh + 32 && warp_label0 + 32 > colh) && colh + 32 <= p.n_all &&
+                             __all_sync(0xffffffffu, row_ok);
           uint32_t packed[16];
           float dsh = 0.f, dbh = 0.f;
           const uint64_t c2p = pack_f32x2(c2, c2), b2p = pack_f32x2(b2, b2), onep = pack_f32x2(1.f, 1.f);
           const uint64_t scp = pack_f32x2(kSigScale, kSigScale);
           uint64_t dsp = pack_f32x2(0.f, 0.f), dbp = pack_f32x2(0.f, 0.f);
+          auto piece = [&](auto plain_tag) {
+            constexpr bool kPlain = decltype(plain_tag)::value;
 #pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            // packed fp32 pairs (FFMA2 / FADD2 / FMUL2) wherever both lanes do the same thing
-            const uint64_t vp = pack_f32x2(__uint_as_float(r[i]), __uint_as_float(r[i + 1]));
-            float z[2], t[2], den[2], tr[2], sg[2];
-            unpack_f32x2(fma_f32x2(vp, c2p, b2p), z[0], z[1]);
-            t[0] = fast_exp2(-fabsf(z[0]));
-            t[1] = fast_exp2(-fabsf(z[1]));
-            const uint64_t tp = pack_f32x2(t[0], t[1]);
-            unpack_f32x2(add_f32x2(tp, onep), den[0], den[1]);
-            const float rr[2] = {__fdividef(1.0f, den[0]), __fdividef(1.0f, den[1])};
-            unpack_f32x2(mul_f32x2(tp, pack_f32x2(rr[0], rr[1])), tr[0], tr[1]);
+            for (int i = 0; i < 32; i += 2) {
+              // packed fp32 pairs (FFMA2 / FADD2 / FMUL2) wherever both lanes do the same thing
+              const uint64_t vp = pack_f32x2(__uint_as_float(r[i]), __uint_as_float(r[i + 1]));
+              float z[2], t[2], den[2], tr[2], sg[2];
+              unpack_f32x2(fma_f32x2(vp, c2p, b2p), z[0], z[1]);
+              t[0] = fast_exp2(-fabsf(z[0]));
+              t[1] = fast_exp2(-fabsf(z[1]));
+              const uint64_t tp = pack_f32x2(t[0], t[1]);
+              unpack_f32x2(add_f32x2(tp, onep), den[0], den[1]);
+              const float rr[2] = {__fdividef(1.0f, den[0]), __fdividef(1.0f, den[1])};
+              unpack_f32x2(mul_f32x2(tp, pack_f32x2(rr[0], rr[1])), tr[0], tr[1]);
 #pragma unroll
-            for (int x = 0; x < 2; ++x) {
-              const bool pos = z[x] >= 0.f;
-              sg[x] = pos ? rr[x] : tr[x];                        // sigmoid(z)
-              if (i + x == want) sg[x] = pos ? -tr[x] : -rr[x];   // sigmoid(z) - 1 without cancellation
-              if (i + x >= valid) sg[x] = 0.f;
+              for (int x = 0; x < 2; ++x) {
+                const bool pos = z[x] >= 0.f;
+                sg[x] = pos ? rr[x] : tr[x];                        // sigmoid(z)
+                if constexpr (!kPlain) {
+                  if (i + x == want) sg[x] = pos ? -tr[x] : -rr[x]; // sigmoid(z) - 1 without cancellation
+                  if (i + x >= valid) sg[x] = 0.f;
+                }
+              }
+              const uint64_t sgp = pack_f32x2(sg[0], sg[1]);
+              dsp = fma_f32x2(sgp, vp, dsp);
+              dbp = add_f32x2(dbp, sgp);
+              float g0, g1;
+              unpack_f32x2(mul_f32x2(sgp, scp), g0, g1);
+              packed[i >> 1] = pack2(g0, g1);
             }
-            const uint64_t sgp = pack_f32x2(sg[0], sg[1]);
-            dsp = fma_f32x2(sgp, vp, dsp);
-            dbp = add_f32x2(dbp, sgp);
-            float g0, g1;
-            unpack_f32x2(mul_f32x2(sgp, scp), g0, g1);
-            packed[i >> 1] = pack2(g0, g1);
-          }
+          };
+          if (plain) piece(TrueTag{}); else piece(FalseTag{});
           {
             float a0, a1, b0, b1;
             unpack_f32x2(dsp, a0, a1);
@@ -672,17 +684,29 @@ pair_sweep_kernel(const __grid_constant__ CUtensorMap tmy, const __grid_constant
           if (row_ok && label >= colh && label < colh + 32) want = (int)(label - colh);
           const int valid = !row_ok ? 0 : (colh + 32 <= p.n_all ? 32 : (colh >= p.n_all ? 0 : (int)(p.n_all - colh)));
           float small0 = 0.f, big = 0.f;                    // ln units / log2 units
+          // warp-uniform: no label entry, no ragged column, no row past the end in this 32x32 piece
+          const bool plain = !(warp_label0 < colh + 32 && warp_label0 + 32 > colh) && colh + 32 <= p.n_all &&
+                             __all_sync(0xffffffffu, row_ok);
+          const uint64_t c2p = pack_f32x2(c2, c2), b2p = pack_f32x2(b2, b2);
+          auto piece = [&](auto plain_tag) {
+            constexpr bool kPlain = decltype(plain_tag)::value;
 #pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            float z0 = fmaf(__uint_as_float(r[i]), c2, b2);
-            float z1 = fmaf(__uint_as_float(r[i + 1]), c2, b2);
-            if (i >= valid) z0 = -INFINITY;
-            if (i + 1 >= valid) z1 = -INFINITY;
-            small0 += log1p_unit_pair_sum(fast_exp2(-fabsf(z0)), fast_exp2(-fabsf(z1)));
-            big += fmaxf(z0, 0.f) + fmaxf(z1, 0.f);
-            if (i == want) big -= z0;
-            if (i + 1 == want) big -= z1;
-          }
+            for (int i = 0; i < 32; i += 2) {
+              float z0, z1;
+              unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(r[i]), __uint_as_float(r[i + 1])), c2p, b2p), z0, z1);
+              if constexpr (!kPlain) {
+                if (i >= valid) z0 = -INFINITY;
+                if (i + 1 >= valid) z1 = -INFINITY;
+              }
+              small0 += log1p_unit_pair_sum(fast_exp2(-fabsf(z0)), fast_exp2(-fabsf(z1)));
+              big += fmaxf(z0, 0.f) + fmaxf(z1, 0.f);
+              if constexpr (!kPlain) {
+                if (i == want) big -= z0;
+                if (i + 1 == want) big -= z1;
+              }
+            }
+          };
+          if (plain) piece(TrueTag{}); else piece(FalseTag{});
           const float term = fmaf(big, kLn2, small0);
           const float y = term - comp;               // Kahan
           const float tsum = sum + y;
