@@ -303,6 +303,48 @@ def latteclip_head_times(dev, batch=512, dim=512, classes=47, reps=20, axis="qui
     return res
 
 
+def gpu_eager_reference(dev, reps=3):
+    """The reference's GPU path restated op for op in eager PyTorch on this GPU (loss.py:102-130:
+    two logit GEMMs with the scale on the A operand, two F.cross_entropy over materialised [N, N]
+    logits, autograd backward) at the headline shape -- the like-for-like bar SURVEY 8d asks for,
+    reported beside the CPU measurement of the reference arm.  None of our kernels run here."""
+    i, t = synth_shard(N_GLOBAL, DIM, 0, 1)
+    out = {}
+    for name, ac in (("amp_bf16", torch.bfloat16), ("fp32", None)):
+        try:
+            il = i.to(dev).requires_grad_(True)
+            tl = t.to(dev).requires_grad_(True)
+            s = torch.tensor(SCALE, device=dev, requires_grad=True)
+            labels = torch.arange(N_GLOBAL, device=dev)
+
+            def step():
+                il.grad = tl.grad = s.grad = None
+                with torch.autocast("cuda", dtype=ac or torch.bfloat16, enabled=ac is not None):
+                    logits_per_image = s * il @ tl.T
+                    logits_per_text = s * tl @ il.T
+                    loss = (F.cross_entropy(logits_per_image, labels) + F.cross_entropy(logits_per_text, labels)) / 2
+                loss.backward()
+                return loss
+
+            torch.cuda.reset_peak_memory_stats(dev)
+            step()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                loss = step()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / reps
+            out[name] = {"ms_per_step": ms, "samples_per_s": N_GLOBAL / (ms * 1e-3), "loss": float(loss.detach()),
+                         "peak_mem_gib": torch.cuda.max_memory_allocated(dev) / 2 ** 30}
+            del il, tl, s, loss
+            torch.cuda.empty_cache()
+        except Exception as exc:      # e.g. out of memory on a smaller part: report, do not fail the arm
+            out[name] = {"error": str(exc).splitlines()[0][:200]}
+    return out
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -319,6 +361,10 @@ def run_reference(args):
         "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    if torch.cuda.is_available():
+        line["gpu_eager"] = dict(gpu_eager_reference(torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))),
+                                 note="the same algorithm in eager PyTorch on this GPU (materialised logits); "
+                                      "extra information, the arm's value is the CPU measurement")
     print(json.dumps(line), flush=True)
 
 
