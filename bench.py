@@ -124,6 +124,16 @@ class ClockSampler:
                 "reasons": sorted(reasons)}
 
 
+def cpu_model_name():
+    try:
+        for ln in open("/proc/cpuinfo"):
+            if ln.lower().startswith("model name"):
+                return ln.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
 def cpu_reference_sample(steps, warmup, target_s=6.0):
     """The reference algorithm on the host cores (oracle port, fp32, all threads): forward +
     backward of the loss terms owned by the first R rows of the N = 32768 problem (what one
@@ -147,7 +157,7 @@ def cpu_reference_sample(steps, warmup, target_s=6.0):
     for _ in range(steps):
         clip_loss_row_block_sample(i, t, SCALE, rows)
     dt = (time.perf_counter() - t0) / steps
-    return dict(value=rows / dt, unit=UNIT, cores=torch.get_num_threads(), kind="port",
+    return dict(value=rows / dt, unit=UNIT, cores=torch.get_num_threads(), cpu_model=cpu_model_name(), kind="port",
                 sample=f"fwd+bwd of the first {rows} rows (both CE directions) of the N={N_GLOBAL}, "
                        f"D={DIM} fp32 problem, {steps} steps, {dt * 1e3:.1f} ms/step"), dt
 
