@@ -107,6 +107,13 @@ constexpr int kModeFwdBoth = 2;   // forward, world size 1: row partials + colum
 constexpr int kModeSigFwd = 3;    // SigLIP forward: sum of softplus(-label * z) over the tile range
 constexpr int kModeSigGrad = 4;   // SigLIP backward: G = sigmoid(z) - delta
 
+// MUFU.RCP alone (__fdividef adds range fix-ups that a denominator in [1, 2] never needs)
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
 struct TrueTag { static constexpr bool value = true; };
 struct FalseTag { static constexpr bool value = false; };
 
@@ -137,8 +144,8 @@ __device__ __forceinline__ uint64_t mul_f32x2(uint64_t a, uint64_t b) {
 // log1p(t0) + log1p(t1) for arguments in [0, 1]: log1p(t) = t * q(t) with q the degree-8 Chebyshev
 // fit of log1p(t)/t (relative error 2e-7 in fp32 Horner form; MUFU lg2 near 1 only has an ABSOLUTE
 // error of 2^-22, useless for the small terms that make up most of a sigmoid loss), both arguments
-// in one chain of FFMA2.
-__device__ __forceinline__ float log1p_unit_pair_sum(float t0, float t1) {
+// in one chain of FFMA2.  Returns the pair (log1p(t0), log1p(t1)).
+__device__ __forceinline__ uint64_t log1p_unit_pair(float t0, float t1) {
   const uint64_t t = pack_f32x2(t0, t1);
   uint64_t q = pack_f32x2(0.00525352f, 0.00525352f);
   q = fma_f32x2(q, t, pack_f32x2(-0.02958887f, -0.02958887f));
@@ -149,9 +156,7 @@ __device__ __forceinline__ float log1p_unit_pair_sum(float t0, float t1) {
   q = fma_f32x2(q, t, pack_f32x2(0.33319275f, 0.33319275f));
   q = fma_f32x2(q, t, pack_f32x2(-0.49999502f, -0.49999502f));
   q = fma_f32x2(q, t, pack_f32x2(0.99999997f, 0.99999997f));
-  float r0, r1;
-  unpack_f32x2(mul_f32x2(q, t), r0, r1);
-  return r0 + r1;
+  return mul_f32x2(q, t);
 }
 
 template <int MODE, bool TAIL>
@@ -597,7 +602,7 @@ pair_sweep_kernel(const __grid_constant__ CUtensorMap tmy, const __grid_constant
               t[1] = fast_exp2(-fabsf(z[1]));
               const uint64_t tp = pack_f32x2(t[0], t[1]);
               unpack_f32x2(add_f32x2(tp, onep), den[0], den[1]);
-              const float rr[2] = {__fdividef(1.0f, den[0]), __fdividef(1.0f, den[1])};
+              const float rr[2] = {rcp_approx(den[0]), rcp_approx(den[1])};   // den in [1, 2]
               unpack_f32x2(mul_f32x2(tp, pack_f32x2(rr[0], rr[1])), tr[0], tr[1]);
 #pragma unroll
               for (int x = 0; x < 2; ++x) {
@@ -683,7 +688,8 @@ pair_sweep_kernel(const __grid_constant__ CUtensorMap tmy, const __grid_constant
           int want = -1;
           if (row_ok && label >= colh && label < colh + 32) want = (int)(label - colh);
           const int valid = !row_ok ? 0 : (colh + 32 <= p.n_all ? 32 : (colh >= p.n_all ? 0 : (int)(p.n_all - colh)));
-          float small0 = 0.f, big = 0.f;                    // ln units / log2 units
+          float big = 0.f;                                   // log2 units
+          uint64_t smallp = pack_f32x2(0.f, 0.f), bigp = pack_f32x2(0.f, 0.f);   // ln units / log2 units
           // warp-uniform: no label entry, no ragged column, no row past the end in this 32x32 piece
           const bool plain = !(warp_label0 < colh + 32 && warp_label0 + 32 > colh) && colh + 32 <= p.n_all &&
                              __all_sync(0xffffffffu, row_ok);
@@ -698,8 +704,8 @@ pair_sweep_kernel(const __grid_constant__ CUtensorMap tmy, const __grid_constant
                 if (i >= valid) z0 = -INFINITY;
                 if (i + 1 >= valid) z1 = -INFINITY;
               }
-              small0 += log1p_unit_pair_sum(fast_exp2(-fabsf(z0)), fast_exp2(-fabsf(z1)));
-              big += fmaxf(z0, 0.f) + fmaxf(z1, 0.f);
+              smallp = add_f32x2(smallp, log1p_unit_pair(fast_exp2(-fabsf(z0)), fast_exp2(-fabsf(z1))));
+              bigp = add_f32x2(bigp, pack_f32x2(fmaxf(z0, 0.f), fmaxf(z1, 0.f)));
               if constexpr (!kPlain) {
                 if (i == want) big -= z0;
                 if (i + 1 == want) big -= z1;
@@ -707,7 +713,10 @@ pair_sweep_kernel(const __grid_constant__ CUtensorMap tmy, const __grid_constant
             }
           };
           if (plain) piece(TrueTag{}); else piece(FalseTag{});
-          const float term = fmaf(big, kLn2, small0);
+          float s0, s1, b0, b1;
+          unpack_f32x2(smallp, s0, s1);
+          unpack_f32x2(bigp, b0, b1);
+          const float term = fmaf(big + (b0 + b1), kLn2, s0 + s1);
           const float y = term - comp;               // Kahan
           const float tsum = sum + y;
           comp = (tsum - sum) - y;
