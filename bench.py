@@ -36,10 +36,21 @@ DIM = 512
 SCALE = 100.0
 METRIC = "clip_loss_fwd_bwd_samples_per_sec"
 UNIT = "samples/s"
-# DRAM traffic of the dominant kernel (pair_gemm_kernel) per launch at N = 1, from the
-# committed ncu capture (profiles/r1_pair_32k_ncu_summary.md: dram__bytes_read.sum +
-# dram__bytes_write.sum)
-NCU_TRAFFIC_GEMM_BYTES = 5.98e9
+# One CPU row block for both the cpu_baseline leg and the --impl reference arm
+CPU_BLOCK_ROWS = 4096
+# weak-scaling operating point: rows per GPU
+WEAK_ROWS_PER_GPU = 4096
+
+
+def ncu_traffic_bytes():
+    """DRAM traffic of the dominant kernel (pair_gemm_kernel) per launch at N = 1, read from the
+    committed ncu capture of the shipped kernel (profiles/gemm_traffic.json: dram__bytes_read.sum +
+    dram__bytes_write.sum of one `ncu --set full` launch); None when no capture is committed."""
+    path = os.path.join(ROOT, "profiles", "gemm_traffic.json")
+    try:
+        return float(json.load(open(path))["dram_bytes_per_launch"])
+    except (OSError, KeyError, ValueError):
+        return None
 
 
 def synth_shard(n_global, dim, rank, world, set_id=0):
@@ -134,24 +145,18 @@ def cpu_model_name():
     return "unknown"
 
 
-def cpu_reference_sample(steps, warmup, target_s=6.0):
+def cpu_reference_sample(steps, warmup):
     """The reference algorithm on the host cores (oracle port, fp32, all threads): forward +
-    backward of the loss terms owned by the first R rows of the N = 32768 problem (what one
-    rank of a local_loss run computes, loss.py:108-110).  Per-sample cost equals the full
-    batch's, so samples/s = R / time."""
+    backward of the loss terms owned by the first CPU_BLOCK_ROWS rows of the N = 32768 problem
+    (what one rank of a local_loss run computes, loss.py:108-110).  Per-sample cost equals the full
+    batch's, so samples/s = rows / time.  The same block size serves the cpu_baseline leg of our
+    arm and the --impl reference arm."""
     from oracle.clip_loss import clip_loss_row_block_sample
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     i, t = synth_shard(N_GLOBAL, DIM, 0, 1)
-    rows = 256
-    t0 = time.perf_counter()
-    clip_loss_row_block_sample(i, t, SCALE, rows)
-    dt = time.perf_counter() - t0
-    # scale the row block so one step takes about target_s / steps seconds (bounded)
-    per_row = max(dt / rows, 1e-7)
-    rows = int(min(8192, max(256, (target_s / max(steps, 1)) / per_row)))
-    rows = max(256, rows // 256 * 256)
-    for _ in range(warmup):
+    rows = CPU_BLOCK_ROWS
+    for _ in range(max(warmup, 1)):
         clip_loss_row_block_sample(i, t, SCALE, rows)
     t0 = time.perf_counter()
     for _ in range(steps):
@@ -160,6 +165,43 @@ def cpu_reference_sample(steps, warmup, target_s=6.0):
     return dict(value=rows / dt, unit=UNIT, cores=torch.get_num_threads(), cpu_model=cpu_model_name(), kind="port",
                 sample=f"fwd+bwd of the first {rows} rows (both CE directions) of the N={N_GLOBAL}, "
                        f"D={DIM} fp32 problem, {steps} steps, {dt * 1e3:.1f} ms/step"), dt
+
+
+def load_reference_loss_module():
+    """The reference's own open_clip/loss.py, unmodified, from baseline/_ref (installed by
+    baseline/install_ref.sh with pip --target; the file imports with torch alone).  None when the
+    install is absent."""
+    path = os.path.join(ROOT, "baseline", "_ref", "open_clip", "loss.py")
+    if not os.path.exists(path):
+        return None
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_ref_open_clip_loss", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def cpu_reference_module(n=8192, reps=2):
+    """The reference's ClipLoss MODULE itself (baseline/_ref, world_size 1) on the host cores at a
+    batch it finishes in about a second.  Extra information: a batch of n costs n/N of the headline
+    batch per sample, so this is NOT the headline workload (the row-block sample is)."""
+    mod = load_reference_loss_module()
+    if mod is None:
+        return None
+    torch.set_num_threads(os.cpu_count() or 1)
+    i, t = synth_shard(n, DIM, 0, 1)
+    il, tl = i.clone().requires_grad_(True), t.clone().requires_grad_(True)
+    s = torch.tensor(SCALE, requires_grad=True)
+    loss_fn = mod.ClipLoss()
+    loss_fn(il, tl, s).backward()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        il.grad = tl.grad = s.grad = None
+        loss = loss_fn(il, tl, s)
+        loss.backward()
+    dt = (time.perf_counter() - t0) / reps
+    return {"batch": n, "ms_per_step": dt * 1e3, "samples_per_s": n / dt, "loss": float(loss.detach()),
+            "kind": "reference (baseline/_ref/open_clip/loss.py ClipLoss, unmodified)"}
 
 
 def prototype_kernel_rates(dev, peaks, batch=N_GLOBAL, dim=DIM, classes=47):
@@ -197,8 +239,10 @@ def prototype_kernel_rates(dev, peaks, batch=N_GLOBAL, dim=DIM, classes=47):
         ("nxc_tc_kernel (top-2 margin, train.py:292-303)",
          batch * dim * fb + classes * dim * 4 + batch * 4,
          lambda k: _lib.nxc_argmax_margin(xs[k % sets], bank, scale=1.0, want_argmax=False, want_margin=True)),
+        # per_image + per_group read, t_ft + t_zs written; the label-text / bank rows are gathers
+        # from [C, D] tables (96 KB each at C = 47) that stay in L2
         ("mix_ema_fwd_kernel (train.py:472-488)",
-         8 * batch * dim * fb + 6 * batch * 4 + 2 * batch * 8,
+         4 * batch * dim * fb + 2 * classes * dim * 4 + 6 * batch * 4 + 2 * batch * 8,
          lambda k: _lib.mix_ema_fwd(cls, xs[k % sets], ps[k % sets], bank, preds, zs, w[0], w[1], w[2], w[3], 0.01, "row")),
         ("mix_ema_bwd (rows kernel + per-class segment sums)",
          4 * batch * dim * fb + classes * dim * 4 + 6 * batch * 4,
@@ -319,20 +363,26 @@ def gpu_eager_reference(dev, reps=3):
     logits, autograd backward) at the headline shape -- the like-for-like bar SURVEY 8d asks for,
     reported beside the CPU measurement of the reference arm.  None of our kernels run here."""
     i, t = synth_shard(N_GLOBAL, DIM, 0, 1)
-    out = {}
+    ref_mod = load_reference_loss_module()
+    out = {"implementation": "baseline/_ref/open_clip/loss.py ClipLoss (unmodified reference module)"
+           if ref_mod is not None else "restatement of loss.py:102-130 (baseline/_ref not installed)"}
     for name, ac in (("amp_bf16", torch.bfloat16), ("fp32", None)):
         try:
             il = i.to(dev).requires_grad_(True)
             tl = t.to(dev).requires_grad_(True)
             s = torch.tensor(SCALE, device=dev, requires_grad=True)
             labels = torch.arange(N_GLOBAL, device=dev)
+            ref_loss = ref_mod.ClipLoss(cache_labels=True).to(dev) if ref_mod is not None else None
 
             def step():
                 il.grad = tl.grad = s.grad = None
                 with torch.autocast("cuda", dtype=ac or torch.bfloat16, enabled=ac is not None):
-                    logits_per_image = s * il @ tl.T
-                    logits_per_text = s * tl @ il.T
-                    loss = (F.cross_entropy(logits_per_image, labels) + F.cross_entropy(logits_per_text, labels)) / 2
+                    if ref_loss is not None:
+                        loss = ref_loss(il, tl, s)
+                    else:
+                        logits_per_image = s * il @ tl.T
+                        logits_per_text = s * tl @ il.T
+                        loss = (F.cross_entropy(logits_per_image, labels) + F.cross_entropy(logits_per_text, labels)) / 2
                 loss.backward()
                 return loss
 
@@ -359,7 +409,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    base, dt = cpu_reference_sample(max(args.steps, 1), min(args.warmup, 1), target_s=20.0)
+    base, dt = cpu_reference_sample(max(args.steps, 1), min(args.warmup, 1))
     line = {
         "impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT,
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
@@ -371,11 +421,145 @@ def run_reference(args):
         "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    module = cpu_reference_module()
+    if module is not None:
+        line["reference_module_cpu"] = module
     if torch.cuda.is_available():
         line["gpu_eager"] = dict(gpu_eager_reference(torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))),
                                  note="the same algorithm in eager PyTorch on this GPU (materialised logits); "
                                       "extra information, the arm's value is the CPU measurement")
     print(json.dumps(line), flush=True)
+
+
+def fp64_reference(all_i, all_t, scale, n_loc, off, rows_idx, chunk=2048):
+    """fp64 torch restatement of loss.py:102-130 + autograd on the GPU for the parity check of
+    every bench run (the checker, outside every timed region): from the gathered features (the
+    same bf16-rounded values the kernels read) -> per-rank loss of the rank that owns rows
+    [off, off + n_loc) under local_loss + gather_with_grad, the gradient rows `rows_idx` (global
+    indices) of dI and dT, and the GLOBAL d loss / d logit_scale (sum over ranks)."""
+    n = all_i.shape[0]
+    I = all_i.double()
+    T = all_t.double()
+    row_lse = torch.empty(n, dtype=torch.float64, device=I.device)
+    col_lse = torch.full((n,), -float("inf"), dtype=torch.float64, device=I.device)
+    for c0 in range(0, n, chunk):
+        S = scale * (I[c0:c0 + chunk] @ T.T)
+        row_lse[c0:c0 + chunk] = torch.logsumexp(S, dim=1)
+        col_lse = torch.logaddexp(col_lse, torch.logsumexp(S, dim=0))
+    diag = scale * (I * T).sum(dim=1)
+    sl = slice(off, off + n_loc)
+    loss = ((row_lse[sl] - diag[sl]).mean() + (col_lse[sl] - diag[sl]).mean()) / 2
+    # d(sum_r L_r)/dS_ij = (P^row_ij + P^col_ij - 2 delta_ij) / (2 n_loc)
+    ds = torch.zeros((), dtype=torch.float64, device=I.device)
+    for c0 in range(0, n, chunk):
+        S = scale * (I[c0:c0 + chunk] @ T.T)
+        G = torch.exp(S - row_lse[c0:c0 + chunk, None]) + torch.exp(S - col_lse[None, :])
+        G[torch.arange(G.shape[0]), torch.arange(c0, c0 + G.shape[0])] -= 2.0
+        ds += (G * S).sum() / scale
+    ds = ds / (2.0 * n_loc)
+    Sr = scale * (I[rows_idx] @ T.T)                                   # [R, N]
+    Gr = torch.exp(Sr - row_lse[rows_idx, None]) + torch.exp(Sr - col_lse[None, :])
+    Gr[torch.arange(len(rows_idx)), rows_idx] -= 2.0
+    dI = (scale / (2.0 * n_loc)) * (Gr @ T)
+    Sc = scale * (T[rows_idx] @ I.T)                                   # [R, N] = S[:, rows]^T
+    Gc = torch.exp(Sc - row_lse[None, :]) + torch.exp(Sc - col_lse[rows_idx, None])
+    Gc[torch.arange(len(rows_idx)), rows_idx] -= 2.0
+    dT = (scale / (2.0 * n_loc)) * (Gc @ I)
+    return loss, dI, dT, ds
+
+
+def parity_check(loss_fn, il, tl, log_s, rank, world, dev, n_rows=64):
+    """One step through the product path, compared with fp64_reference on this rank: loss, n_rows
+    sampled rows of dI and dT (bf16 outputs: rel <= 2.6e-3, the north_star's 2e-3 on the fp32 values
+    plus the 1.63e-3 rms of rounding any gradient to bf16, see tests/test_gpu_clip.py), and the
+    rank-summed d loss / d logit_scale (rel <= 2e-3).  Worst case over ranks is reported."""
+    import torch.distributed as dist
+    il.grad = None; tl.grad = None; log_s.grad = None
+    loss = loss_fn(il, tl, log_s.exp())
+    loss.backward()
+    n_loc = il.shape[0]
+    n_all = n_loc * world
+    if world > 1:
+        all_i = torch.empty(n_all, il.shape[1], dtype=il.dtype, device=dev)
+        all_t = torch.empty(n_all, il.shape[1], dtype=il.dtype, device=dev)
+        dist.all_gather_into_tensor(all_i, il.detach())
+        dist.all_gather_into_tensor(all_t, tl.detach())
+    else:
+        all_i, all_t = il.detach(), tl.detach()
+    off = rank * n_loc
+    g = torch.Generator().manual_seed(99 + rank)
+    rows = (torch.randperm(n_loc, generator=g)[:n_rows].sort().values + off).to(dev)
+    ref_loss, ref_di, ref_dt, ref_ds = fp64_reference(all_i, all_t, SCALE, n_loc, off, rows)
+    rel = lambda a, b: float((a.double() - b).norm() / b.norm())
+    e_loss = abs(float(loss.detach()) - float(ref_loss)) / abs(float(ref_loss))
+    e_di = rel(il.grad[rows - off], ref_di)
+    e_dt = rel(tl.grad[rows - off], ref_dt)
+    # log_s.grad = s * d loss / d s of this rank's rows x all columns; the sum over ranks is the
+    # reference's global sum (what DDP's all-reduce of the parameter gradient sees)
+    ds = log_s.grad.detach().double().clone() / SCALE
+    if world > 1:
+        dist.all_reduce(ds, op=dist.ReduceOp.SUM)
+    e_ds = abs(float(ds) - float(ref_ds)) / abs(float(ref_ds))
+    errs = torch.tensor([e_loss, e_di, e_dt, e_ds], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(errs, op=dist.ReduceOp.MAX)
+    e_loss, e_di, e_dt, e_ds = (float(x) for x in errs)
+    loss_tol = 1e-5 + 2e-5 / abs(float(ref_loss))
+    ok = e_loss <= loss_tol and e_di <= 2.6e-3 and e_dt <= 2.6e-3 and e_ds <= 2e-3
+    return {"loss_rel": e_loss, "dI_rel": e_di, "dT_rel": e_dt, "dscale_rel": e_ds,
+            "rows_checked_per_rank": n_rows, "loss_tol": loss_tol, "grad_tol": 2.6e-3,
+            "dscale_tol": 2e-3, "reference": "fp64 torch on the gathered bf16 features (all ranks)",
+            "ok": bool(ok)}
+
+
+def weak_scaling_point(lb, rank, world, dev, steps):
+    """SURVEY 8d's weak-scaling datum: WEAK_ROWS_PER_GPU rows per GPU (global batch = rows * W),
+    per-GPU credited FLOP/s = 6 n N D / t, beside the same GPU running the one-rank problem
+    (n = N = WEAK_ROWS_PER_GPU) so the efficiency refers to the same box."""
+    import torch.distributed as dist
+    n = WEAK_ROWS_PER_GPU
+    n_glob = n * world
+    sets = []
+    for sidx in range(4):
+        i, t = synth_shard(n_glob, DIM, rank, world, 20 + sidx)
+        sets.append((i.bfloat16().to(dev).requires_grad_(True), t.bfloat16().to(dev).requires_grad_(True)))
+    log_s = torch.tensor(math.log(SCALE), device=dev, requires_grad=True)
+
+    def run(fn, k_steps):
+        for k in range(3):
+            i, t = sets[k % 4]
+            i.grad = None; t.grad = None; log_s.grad = None
+            fn(i, t, log_s.exp()).backward()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for k in range(k_steps):
+            i, t = sets[k % 4]
+            i.grad = None; t.grad = None; log_s.grad = None
+            fn(i, t, log_s.exp()).backward()
+        e1.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1) / k_steps], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms)
+
+    ms_w = run(lb.ClipLoss(local_loss=True, gather_with_grad=True, cache_labels=True, rank=rank,
+                           world_size=world), steps)
+    ms_1 = run(lb.ClipLoss(local_loss=True, gather_with_grad=True, cache_labels=True), steps) \
+        if world > 1 else ms_w
+    tf_w = 6.0 * n * n_glob * DIM / (ms_w * 1e-3) / 1e12
+    tf_1 = 6.0 * n * n * DIM / (ms_1 * 1e-3) / 1e12
+    return {"rows_per_gpu": n, "global_batch": n_glob, "ms_per_step": ms_w,
+            "samples_per_s": n_glob / (ms_w * 1e-3), "alg_tflops_per_gpu": tf_w,
+            "single_gpu_same_box": {"global_batch": n, "ms_per_step": ms_1, "alg_tflops_per_gpu": tf_1},
+            "efficiency_vs_single_gpu": tf_w / tf_1,
+            "definition": "per-GPU credited FLOP/s (6 n N D / t) at n rows per GPU over W GPUs, divided by "
+                          "the same GPU's at W = 1 (n = N), max over ranks"}
 
 
 def run_ours(args):
@@ -384,13 +568,16 @@ def run_ours(args):
     saved_stdout_fd = os.dup(1)
     os.dup2(2, 1)
     try:
-        line = _run_ours(args)
+        line, parity_ok = _run_ours(args)
     finally:
         sys.stdout.flush()
         os.dup2(saved_stdout_fd, 1)
         os.close(saved_stdout_fd)
     if line is not None:
         print(json.dumps(line), flush=True)
+    if not parity_ok:
+        sys.stderr.write("PARITY FAILURE (see the \"parity\" key of the JSON line)\n")
+        sys.exit(1)
 
 
 def _run_ours(args):
@@ -521,6 +708,10 @@ def _run_ours(args):
     h2d = 2 * n_loc * DIM * 2
     d2h = 4
 
+    # ---- parity of this very configuration (outside the timed regions) -----------------------
+    pi, pt = dev_sets[1]
+    parity = parity_check(loss_fn, pi, pt, log_s, rank, world, dev)
+
     # ---- roofline of the dominant kernel, timed live ------------------------------------------
     # The library records CUDA events on the launching stream around every kernel stage of
     # fwd + bwd (latte_clip_stage_times); the dominant stage is the stream-K gradient GEMM
@@ -560,7 +751,7 @@ def _run_ours(args):
         "bound": "tensor", "kernel": "pair_gemm_kernel", "achieved": achieved_tf,
         "peak": peaks["burst"], "unit": "TFLOP/s", "frac": achieved_tf / peaks["burst"],
         "frac_of_sustained": achieved_tf / peaks["sustained"],
-        "traffic": NCU_TRAFFIC_GEMM_BYTES if world == 1 else None,
+        "traffic": ncu_traffic_bytes() if world == 1 else None,
         "peak_source": peaks["source"] + ", burst bf16 figure (the stage is timed over 8 back-to-back "
                        "fwd+bwd repetitions, ~30 ms: too short for the power cap to pull clocks to the "
                        f"sustained level); sustained figure {peaks['sustained']:g} in frac_of_sustained",
@@ -575,6 +766,8 @@ def _run_ours(args):
         "step_frac_of_sustained": step_tf / peaks["sustained"],
         "executed_flop_per_step": 8.0 * n_loc * N_GLOBAL * DIM,
     }
+
+    weak = weak_scaling_point(lb, rank, world, dev, args.steps)
 
     # ---- prototype / pseudo-label kernels (HBM-bound rows of SURVEY 8a): achieved GB/s ------
     proto = None
@@ -594,17 +787,18 @@ def _run_ours(args):
 
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu_base, _ = cpu_reference_sample(2, 1, target_s=12.0)
+        cpu_base, _ = cpu_reference_sample(4, 1)
 
-    # kernels of ours per step (memset nodes and NCCL kernels not counted).  Forward: sweep, row
-    # finalize, column finalize (+ column merge at N > 1), gated fallback sweep + merge, loss
-    # partial + reduce; backward: feature prep, LSE range + vectors, sweep, GEMM, cast, ds reduce.
-    launches_per_step = 14 if world == 1 else 15
+    # kernels of ours per step (memset nodes and NCCL kernels not counted).  Forward: sweep,
+    # finalize (rows + columns), gated fallback sweep, finish (gated merge + loss) (+ shard push
+    # and column merge at N > 1); backward: LSE range + vectors, split-tile zeroing, sweep, GEMM,
+    # split-tile cast, ds reduce.
+    launches_per_step = 11 if world == 1 else 14
     bwd_mode = "one recompute sweep"
     if world > 1:
         from latteclip_b200.loss import _bwd_sweeps
         if _bwd_sweeps(world) == 2:
-            launches_per_step += 2       # second sweep + its GEMM
+            launches_per_step += 4       # second sweep + its GEMM + the two fix-up kernels
             bwd_mode = "rows and columns recomputed per rank, no gradient exchange"
         else:
             bwd_mode = "one recompute sweep per rank, text gradient reduce-scattered inside the GEMM"
@@ -623,7 +817,7 @@ def _run_ours(args):
             },
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches_per_step * args.steps,
-            "clocks": clocks, "roofline": roofline,
+            "clocks": clocks, "roofline": roofline, "parity": parity, "weak_scaling": weak,
         }
         if cpu_base is not None:
             line["cpu_baseline"] = cpu_base
@@ -638,7 +832,7 @@ def _run_ours(args):
         line = None
     if world > 1:
         dist.destroy_process_group()
-    return line
+    return line, parity["ok"]
 
 
 def main():

@@ -264,25 +264,29 @@ int latte_normalize_rows(const float* in, int64_t ld_in, float* out, int64_t ld_
  *   top1_out[i]   = scale * max_c sim[i,c]
  * Any of the three outputs may be NULL.  x is [n, dim] in x_dtype; protos is fp32 [C, dim].
  * If row_index is not NULL, row i of x is x[row_index[i], :] (class-text gather,
- * train.py:420-438).
+ * train.py:420-438).  workspace: caller-owned scratch of latte_nxc_workspace_bytes()
+ * bytes (bf16 operand planes of the tensor-core path; 0 bytes below 128 rows).
  */
+int latte_nxc_workspace_bytes(int x_dtype, int gathered, int64_t n, int64_t dim,
+                              int64_t num_classes, size_t* bytes);
 int latte_nxc_argmax_margin(const void* x, int64_t ldx, int x_dtype,
                             const int64_t* row_index,
                             int64_t n, int64_t dim,
                             const float* protos, int64_t ldp, int64_t num_classes,
                             float scale,
                             int64_t* argmax_out, float* margin_out, float* top1_out,
-                            void* stream);
+                            void* workspace, size_t workspace_bytes, void* stream);
 
 /*
  * Fused N x C similarity + top-k class ids (k <= 16), for the zero-shot evaluator
  * (zero_shot.py:14-20,40: logits.topk(max(topk)); train.py:1352-1358).
  * topk_idx is [n, k] int64, topk_val [n, k] fp32 (scale * sim), sorted descending,
- * lowest index first among equal values.
+ * lowest index first among equal values.  workspace: latte_nxc_workspace_bytes(x_dtype, 0, ...).
  */
 int latte_nxc_topk(const void* x, int64_t ldx, int x_dtype, int64_t n, int64_t dim,
                    const float* protos, int64_t ldp, int64_t num_classes, float scale,
-                   int k, int64_t* topk_idx, float* topk_val, void* stream);
+                   int k, int64_t* topk_idx, float* topk_val, void* workspace,
+                   size_t workspace_bytes, void* stream);
 
 /*
  * Text mixture + EMA toward the memory-bank rows (train.py:472-488), gathers fused:
@@ -312,7 +316,10 @@ int latte_mix_ema_fwd(const void* class_text, int64_t ld_ct,
  * fp32 [C, dim], accumulated) receives (1 - alpha) * d_t scattered by preds / zs -- the
  * reference sends that gradient into memory-bank Parameters that the optimizer no
  * longer owns, so callers normally pass NULL.
+ * workspace: caller-owned scratch of latte_seg_workspace_bytes(batch, dim, num_classes) bytes
+ * (class-sorted entry order + per-piece partial sums of the segment sums).
  */
+int latte_seg_workspace_bytes(int64_t batch, int64_t dim, int64_t num_classes, size_t* bytes);
 int latte_mix_ema_bwd(const void* d_t_ft, const void* d_t_zs, int64_t ld_dt,
                       const int64_t* preds, const int64_t* zs,
                       const float* w_lbl, const float* w_lbl_zs,
@@ -321,19 +328,21 @@ int latte_mix_ema_bwd(const void* d_t_ft, const void* d_t_zs, int64_t ld_dt,
                       int64_t batch, int64_t dim, int64_t num_classes,
                       float* d_class_text, int64_t ld_dct,
                       void* d_per_image, void* d_per_group, int64_t ld_dp,
-                      float* d_bank, int64_t ld_dbank, void* stream);
+                      float* d_bank, int64_t ld_dbank,
+                      void* workspace, size_t workspace_bytes, void* stream);
 
 /*
  * Memory-bank update, step 1 (train.py:508-526): per-class sums and counts, accumulated
  * in the reference's order (for each sample i ascending: t_zs[i] into class zs[i], then
  * t_ft[i] into class preds[i]).  sums [C, dim] fp32 and counts [C] fp32 are OVERWRITTEN.
  * Deterministic (no atomics).  On several ranks the caller all-reduces sums and counts
- * between step 1 and step 2.
+ * between step 1 and step 2.  workspace: latte_seg_workspace_bytes(batch, dim, num_classes).
  */
 int latte_bank_accumulate(const void* t_ft, const void* t_zs, int64_t ld_t, int dtype,
                           const int64_t* preds, const int64_t* zs,
                           int64_t batch, int64_t dim, int64_t num_classes,
-                          float* sums, int64_t ld_sums, float* counts, void* stream);
+                          float* sums, int64_t ld_sums, float* counts,
+                          void* workspace, size_t workspace_bytes, void* stream);
 
 /*
  * Memory-bank update, step 2 (train.py:528-530): for every class with counts[c] > 0,

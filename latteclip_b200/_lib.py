@@ -84,14 +84,17 @@ def _declare(lib):
     lib.latte_siglip_bwd.argtypes = [vp, i64, vp, i64, i32, i64, i64, i64, i64, vp, vp, vp, vp, vp,
                                      i32, i64, vp, vp, i32, vp, vp, vp, sz, vp]
     lib.latte_normalize_rows.argtypes = [vp, i64, vp, i64, i64, i64, vp]
+    lib.latte_nxc_workspace_bytes.argtypes = [i32, i32, i64, i64, i64, c.POINTER(sz)]
     lib.latte_nxc_argmax_margin.argtypes = [vp, i64, i32, vp, i64, i64, vp, i64, i64, f32,
-                                            vp, vp, vp, vp]
-    lib.latte_nxc_topk.argtypes = [vp, i64, i32, i64, i64, vp, i64, i64, f32, i32, vp, vp, vp]
+                                            vp, vp, vp, vp, sz, vp]
+    lib.latte_nxc_topk.argtypes = [vp, i64, i32, i64, i64, vp, i64, i64, f32, i32, vp, vp, vp, sz, vp]
+    lib.latte_seg_workspace_bytes.argtypes = [i64, i64, i64, c.POINTER(sz)]
     lib.latte_mix_ema_fwd.argtypes = [vp, i64, vp, i64, vp, i64, vp, i64, vp, vp, vp, vp, vp, vp,
                                       f32, i32, i32, i64, i64, i64, vp, vp, i64, vp]
     lib.latte_mix_ema_bwd.argtypes = [vp, vp, i64, vp, vp, vp, vp, vp, vp, f32, i32, i32, i64,
-                                      i64, i64, vp, i64, vp, vp, i64, vp, i64, vp]
-    lib.latte_bank_accumulate.argtypes = [vp, vp, i64, i32, vp, vp, i64, i64, i64, vp, i64, vp, vp]
+                                      i64, i64, vp, i64, vp, vp, i64, vp, i64, vp, sz, vp]
+    lib.latte_bank_accumulate.argtypes = [vp, vp, i64, i32, vp, vp, i64, i64, i64, vp, i64, vp,
+                                          vp, sz, vp]
     lib.latte_bank_finalize.argtypes = [vp, i64, vp, vp, i64, i64, i64, vp]
     for name in EXPORTS:
         if name not in ("latte_version", "latte_status_string"):
@@ -104,8 +107,8 @@ EXPORTS = [
     "latte_clip_fwd_rows", "latte_clip_fwd_cols_workspace_bytes", "latte_clip_fwd_cols",
     "latte_push_shards", "latte_siglip_supported", "latte_siglip_workspace_bytes",
     "latte_siglip_fwd", "latte_siglip_bwd",
-    "latte_clip_fwd", "latte_clip_bwd", "latte_normalize_rows", "latte_nxc_argmax_margin",
-    "latte_nxc_topk", "latte_mix_ema_fwd", "latte_mix_ema_bwd", "latte_bank_accumulate",
+    "latte_clip_fwd", "latte_clip_bwd", "latte_normalize_rows", "latte_nxc_workspace_bytes",
+    "latte_nxc_argmax_margin", "latte_nxc_topk", "latte_seg_workspace_bytes", "latte_mix_ema_fwd", "latte_mix_ema_bwd", "latte_bank_accumulate",
     "latte_bank_finalize",
 ]
 
@@ -171,17 +174,48 @@ def _scalar_f32(t: torch.Tensor) -> torch.Tensor:
     return t.detach().to(torch.float32).reshape(1).contiguous()
 
 
-def _workspace(n_loc: int, n_all: int, dim: int, dtype: int, device, bwd: bool = False) -> torch.Tensor:
+def _clip_ws_bytes(n_loc: int, n_all: int, dim: int, dtype: int, bwd: bool = False) -> int:
     nbytes = ctypes.c_size_t(0)
     fn = load().latte_clip_bwd_workspace_bytes if bwd else load().latte_clip_workspace_bytes
     _check(fn(n_loc, n_all, dim, dtype, ctypes.byref(nbytes)), "latte_clip_workspace_bytes")
-    return torch.empty(nbytes.value + 256, dtype=torch.uint8, device=device)
+    return nbytes.value
 
 
 def _aligned_ptr(ws: torch.Tensor) -> Tuple[ctypes.c_void_p, int]:
     p = ws.data_ptr()
     off = (-p) % 256
     return ctypes.c_void_p(p + off), ws.numel() - off
+
+
+# Scratch for the C ABI's caller-provided workspaces: ONE growable buffer per (kind, device,
+# stream).  The kernels of one call are stream-ordered before the next call's on the same
+# stream, so a kind's buffer can be reused by every call of that kind; a larger request
+# replaces the buffer (the old one goes back to the caching allocator, which keeps it alive for
+# the work already enqueued on that stream).  Sizes come from the *_workspace_bytes functions
+# -- nothing is allocated to measure.  The backward buffer holds the fp16 gradient weights
+# G [n_loc, N] (2 GiB at N = 32768 on one GPU); clear_workspace_cache() drops everything.
+_WS_CACHE = {}
+
+
+def _scratch(kind: str, nbytes: int, device) -> torch.Tensor:
+    k = (kind, device.index, torch.cuda.current_stream(device).cuda_stream)
+    ws = _WS_CACHE.get(k)
+    need = int(nbytes) + 256
+    if ws is None or ws.numel() < need:
+        _WS_CACHE.pop(k, None)
+        ws = None                      # release the old buffer before allocating the new one
+        ws = torch.empty(need, dtype=torch.uint8, device=device)
+        _WS_CACHE[k] = ws
+    return ws
+
+
+def clear_workspace_cache():
+    """Drop the cached scratch buffers (e.g. 2 GiB of gradient weights at batch 32768)."""
+    _WS_CACHE.clear()
+
+
+def workspace_cache_bytes() -> int:
+    return sum(int(t.numel()) for t in _WS_CACHE.values())
 
 
 # ------------------------------------------------------------------------------ ClipLoss
@@ -203,8 +237,7 @@ def clip_fwd(img_loc, txt_loc, img_all, txt_all, label_offset: int, logit_scale,
     loss = torch.empty(1, dtype=torch.float32, device=dev)
     row_nll = torch.empty(n_loc, dtype=torch.float32, device=dev) if with_nll else None
     col_nll = torch.empty(n_loc, dtype=torch.float32, device=dev) if with_nll else None
-    ws = _cached_workspace(("fwd", n_loc, n_all, dim, dt),
-                           lambda: _workspace(n_loc, n_all, dim, dt, dev).numel(), dev)
+    ws = _scratch("fwd", _clip_ws_bytes(n_loc, n_all, dim, dt), dev)
     wp, wn = _aligned_ptr(ws)
     with torch.cuda.device(dev):
         _check(lib.latte_clip_fwd(_ptr(img_loc), img_loc.stride(0), _ptr(txt_loc), txt_loc.stride(0),
@@ -243,27 +276,6 @@ def rank_sweep_supported(dtype: torch.dtype, dim: int) -> bool:
     return bool(load().latte_clip_rank_sweep_supported(_DTYPES[dtype], dim))
 
 
-_WS_CACHE = {}
-
-
-def _cached_workspace(key, nbytes_fn, device):
-    """Scratch reused across calls (one buffer per device, stream and shape key): the kernels
-    of one call are stream-ordered before the next call's on the same stream."""
-    k = (key, device.index, torch.cuda.current_stream(device).cuda_stream)
-    ws = _WS_CACHE.get(k)
-    if ws is None:
-        ws = torch.empty(nbytes_fn() + 256, dtype=torch.uint8, device=device)
-        if len(_WS_CACHE) > 64:
-            _WS_CACHE.clear()
-        _WS_CACHE[k] = ws
-    return ws
-
-
-def clear_workspace_cache():
-    """Drop the cached scratch buffers (e.g. 2 GiB of gradient weights at batch 32768)."""
-    _WS_CACHE.clear()
-
-
 def clip_fwd_rows(img_loc, txt_all, label_offset: int, logit_scale):
     """Step 1 of the multi-rank forward -> packed fp32 payload [2 n_all + 3 n_loc]:
     col_ml [n_all, 2] | row_lse | row_nll | label_logit  (what the ranks all-gather)."""
@@ -281,12 +293,7 @@ def clip_fwd_rows(img_loc, txt_all, label_offset: int, logit_scale):
     row_nll = ctypes.c_void_p(base + 8 * n_all + 4 * n_loc)
     label_logit = ctypes.c_void_p(base + 8 * n_all + 8 * n_loc)
 
-    def need():
-        nbytes = ctypes.c_size_t(0)
-        _check(lib.latte_clip_workspace_bytes(n_loc, n_all, dim, dt, ctypes.byref(nbytes)),
-               "latte_clip_workspace_bytes")
-        return nbytes.value
-    ws = _cached_workspace(("fwd", n_loc, n_all, dim, dt), need, dev)
+    ws = _scratch("fwd", _clip_ws_bytes(n_loc, n_all, dim, dt), dev)
     wp, wn = _aligned_ptr(ws)
     with torch.cuda.device(dev):
         _check(lib.latte_clip_fwd_rows(_ptr(img_loc), img_loc.stride(0), _ptr(txt_all), txt_all.stride(0),
@@ -316,12 +323,10 @@ def clip_fwd_cols(gathered, img_all, txt_all, n_loc: int, label_offset: int, log
     optr = out.data_ptr()
     vecs = [ctypes.c_void_p(optr + 4 * n_all * k) for k in range(4)]
 
-    def need():
-        nbytes = ctypes.c_size_t(0)
-        _check(lib.latte_clip_fwd_cols_workspace_bytes(n_all, dim, dt, ctypes.byref(nbytes)),
-               "latte_clip_fwd_cols_workspace_bytes")
-        return nbytes.value
-    ws = _cached_workspace(("cols", n_all, dim, dt), need, dev)
+    nbytes = ctypes.c_size_t(0)
+    _check(lib.latte_clip_fwd_cols_workspace_bytes(n_all, dim, dt, ctypes.byref(nbytes)),
+           "latte_clip_fwd_cols_workspace_bytes")
+    ws = _scratch("cols", nbytes.value, dev)
     wp, wn = _aligned_ptr(ws)
     with torch.cuda.device(dev):
         _check(lib.latte_clip_fwd_cols(_ptr(gathered), gathered.stride(0), world,
@@ -370,8 +375,7 @@ def clip_bwd(img_loc, txt_loc, img_all, txt_all, label_offset: int, logit_scale,
     d_part = torch.empty(n_all, dim, dtype=torch.float32, device=dev) if partial else None
     peers = (ctypes.c_void_p * len(peer_ptrs))(*peer_ptrs) if fused else None
     d_scale = torch.empty(1, dtype=torch.float32, device=dev)
-    ws = _cached_workspace(("bwd", n_loc, n_all, dim, dt),
-                           lambda: _workspace(n_loc, n_all, dim, dt, dev, bwd=True).numel(), dev)
+    ws = _scratch("bwd", _clip_ws_bytes(n_loc, n_all, dim, dt, bwd=True), dev)
     wp, wn = _aligned_ptr(ws)
     with torch.cuda.device(dev):
         _check(lib.latte_clip_bwd(_ptr(img_loc), img_loc.stride(0), _ptr(txt_loc), txt_loc.stride(0),
@@ -394,12 +398,10 @@ def siglip_supported(dtype: torch.dtype, dim: int) -> bool:
 
 
 def _siglip_workspace(n_loc: int, n_all: int, dim: int, dt: int, dev, bwd: bool, own: bool):
-    def nbytes():
-        need = ctypes.c_size_t()
-        _check(load().latte_siglip_workspace_bytes(n_loc, n_all, dim, dt, int(bwd), int(own),
-                                                   ctypes.byref(need)), "latte_siglip_workspace_bytes")
-        return need.value + 256
-    return _cached_workspace(("siglip", bwd, own, n_loc, n_all, dim, dt), nbytes, dev)
+    need = ctypes.c_size_t()
+    _check(load().latte_siglip_workspace_bytes(n_loc, n_all, dim, dt, int(bwd), int(own),
+                                               ctypes.byref(need)), "latte_siglip_workspace_bytes")
+    return _scratch("siglip_bwd" if bwd else "siglip_fwd", need.value + 256, dev)
 
 
 def siglip_fwd(img_loc, txt_all, label_offset: int, logit_scale, logit_bias=None):
@@ -488,8 +490,8 @@ def clip_stage_times(img_loc, txt_loc, img_all, txt_all, label_offset: int, logi
     d_txt = torch.empty(n_loc, dim, dtype=img_loc.dtype, device=dev)
     d_part = torch.empty(n_all, dim, dtype=torch.float32, device=dev) if partial else None
     d_scale = torch.empty(1, dtype=torch.float32, device=dev)
-    wf = _workspace(n_loc, n_all, dim, dt, dev)
-    wb = _workspace(n_loc, n_all, dim, dt, dev, bwd=True)
+    wf = _scratch("fwd", _clip_ws_bytes(n_loc, n_all, dim, dt), dev)
+    wb = _scratch("bwd", _clip_ws_bytes(n_loc, n_all, dim, dt, bwd=True), dev)
     wfp, wfn = _aligned_ptr(wf)
     wbp, wbn = _aligned_ptr(wb)
     out = (ctypes.c_float * len(STAGES))()
@@ -531,13 +533,30 @@ def nxc_argmax_margin(x, protos, scale: float = 1.0, row_index=None, want_argmax
     am = torch.empty(n, dtype=torch.int64, device=dev) if want_argmax else None
     mg = torch.empty(n, dtype=torch.float32, device=dev) if want_margin else None
     t1 = torch.empty(n, dtype=torch.float32, device=dev) if want_top1 else None
+    wp, wn = _nxc_workspace(_dt(x), row_index is not None, n, x.shape[1], protos.shape[0], dev)
     with torch.cuda.device(dev):
         _check(load().latte_nxc_argmax_margin(_ptr(x), x.stride(0), _dt(x), _ptr(row_index), n,
                                               x.shape[1], _ptr(protos), protos.stride(0),
                                               protos.shape[0], float(scale), _ptr(am), _ptr(mg),
-                                              _ptr(t1), _stream(x)),
+                                              _ptr(t1), wp, wn, _stream(x)),
                "latte_nxc_argmax_margin")
     return am, mg, t1
+
+
+def _nxc_workspace(dt: int, gathered: bool, n: int, dim: int, classes: int, dev):
+    need = ctypes.c_size_t()
+    _check(load().latte_nxc_workspace_bytes(dt, int(gathered), n, dim, classes, ctypes.byref(need)),
+           "latte_nxc_workspace_bytes")
+    if need.value == 0:
+        return ctypes.c_void_p(0), 0
+    return _aligned_ptr(_scratch("nxc", need.value, dev))
+
+
+def _seg_workspace(batch: int, dim: int, classes: int, dev):
+    need = ctypes.c_size_t()
+    _check(load().latte_seg_workspace_bytes(batch, dim, classes, ctypes.byref(need)),
+           "latte_seg_workspace_bytes")
+    return _aligned_ptr(_scratch("seg", need.value, dev))
 
 
 def nxc_topk(x, protos, k: int, scale: float = 1.0):
@@ -546,10 +565,11 @@ def nxc_topk(x, protos, k: int, scale: float = 1.0):
     n = x.shape[0]
     idx = torch.empty(n, k, dtype=torch.int64, device=x.device)
     val = torch.empty(n, k, dtype=torch.float32, device=x.device)
+    wp, wn = _nxc_workspace(_dt(x), False, n, x.shape[1], protos.shape[0], x.device)
     with torch.cuda.device(x.device):
         _check(load().latte_nxc_topk(_ptr(x), x.stride(0), _dt(x), n, x.shape[1], _ptr(protos),
                                      protos.stride(0), protos.shape[0], float(scale), int(k),
-                                     _ptr(idx), _ptr(val), _stream(x)),
+                                     _ptr(idx), _ptr(val), wp, wn, _stream(x)),
                "latte_nxc_topk")
     return idx, val
 
@@ -597,12 +617,13 @@ def mix_ema_bwd(d_t_ft, d_t_zs, preds, zs, w_lbl, w_lbl_zs, w_img, w_grp, alpha:
     d_pi = torch.empty(b, d, dtype=d_t_ft.dtype, device=dev)
     d_pg = torch.empty(b, d, dtype=d_t_ft.dtype, device=dev)
     d_bank = torch.zeros(num_classes, d, dtype=torch.float32, device=dev) if want_bank else None
+    wp, wn = _seg_workspace(b, d, num_classes, dev)
     with torch.cuda.device(dev):
         _check(load().latte_mix_ema_bwd(_ptr(d_t_ft), _ptr(d_t_zs), d_t_ft.stride(0), _ptr(preds),
                                         _ptr(zs), _ptr(ws[0]), _ptr(ws[1]), _ptr(ws[2]), _ptr(ws[3]),
                                         float(alpha), LABEL_AXIS[label_axis], dt, b, d, num_classes,
                                         _ptr(d_ct), d, _ptr(d_pi), _ptr(d_pg), d, _ptr(d_bank), d,
-                                        _stream(d_t_ft)),
+                                        wp, wn, _stream(d_t_ft)),
                "latte_mix_ema_bwd")
     return d_ct, d_pi, d_pg, d_bank
 
@@ -618,10 +639,11 @@ def bank_accumulate(t_ft, t_zs, preds, zs, num_classes: int):
     preds, zs = _vec(preds, torch.int64, "preds"), _vec(zs, torch.int64, "zs")
     sums = torch.empty(num_classes, d, dtype=torch.float32, device=dev)
     counts = torch.empty(num_classes, dtype=torch.float32, device=dev)
+    wp, wn = _seg_workspace(b, d, num_classes, dev)
     with torch.cuda.device(dev):
         _check(load().latte_bank_accumulate(_ptr(t_ft), _ptr(t_zs), t_ft.stride(0), _dt(t_ft),
                                             _ptr(preds), _ptr(zs), b, d, num_classes, _ptr(sums), d,
-                                            _ptr(counts), _stream(t_ft)),
+                                            _ptr(counts), wp, wn, _stream(t_ft)),
                "latte_bank_accumulate")
     return sums, counts
 

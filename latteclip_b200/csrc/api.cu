@@ -2,7 +2,19 @@
 // (row kernels in clip_tc.cu / clip_simt.cu, small finalize kernels here).
 #include "latte_common.cuh"
 
+#include <stdlib.h>
+
 namespace latte {
+
+// Debug switch: LATTE_B200_FP16_COPIES=1 restores fp16 copies of bf16 features as the operands
+// of the gradient GEMMs (the default feeds the bf16 features themselves).
+bool want_fp16_copies() {
+  static const bool on = []() {
+    const char* e = getenv("LATTE_B200_FP16_COPIES");
+    return e != nullptr && e[0] == '1';
+  }();
+  return on;
+}
 
 int device_sm_count() {
   int dev = 0, sms = 0;
@@ -99,85 +111,6 @@ clip_finalize_kernel(const float* pmax_r, const float* psum_r, const float* diag
   }
 }
 
-// ---- CTA-pair forward (clip_pair.cu): merge the slot partials of a row
-__global__ void __launch_bounds__(256)
-pair_row_finalize_kernel(const float* pmax, const float* psum, int64_t n_loc, int col_tiles,
-                         int64_t total, int ncl, const float* diag, const float* logit_scale,
-                         float* lse_out, float* nll_out, float* label_logit_out) {
-  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
-  if (i >= n_loc) return;
-  const int64_t rb = i / 256;
-  const int64_t c0 = cluster_of_tile(rb * col_tiles, total, ncl);
-  const int64_t c1 = cluster_of_tile(rb * col_tiles + col_tiles - 1, total, ncl);
-  const int nparts = 4 * (int)(c1 - c0 + 1);      // slots x 2 epilogue groups x 2 tile halves
-  float M, logL;
-  merge_parts2(pmax, psum, nparts, n_loc, i, M, logL);
-  lse_out[i] = (M + logL) * kLn2;
-  const float s = __ldg(logit_scale);
-  // fma(-c2, dot, M): the exact residual the sweep's own fma(dot, c2, -M) saw for the label
-  if (nll_out) nll_out[i] = (fmaf(-(s * kLog2e), diag[i], M) + logL) * kLn2;
-  if (label_logit_out) label_logit_out[i] = s * diag[i];
-}
-
-// Column (max, sum) from the per-128-row-block partial sums of this rank's rows.  With col_ml
-// the pair is written out (another rank merges); otherwise the LSE, the per-sample loss term
-// and the exactness check are finished here (world size 1).  Terms below 2^-126 of a block's
-// reference were flushed; if that could matter for a column (its LSE sits more than ~95 binary
-// orders below the largest block reference) the exact fallback is requested.
-__global__ void __launch_bounds__(256)
-pair_col_finalize_kernel(const float* col_part, const float* col_ref, int64_t ld, int nblk,
-                         int col_tiles, int64_t n_all, const float* diag, const float* logit_scale,
-                         float* col_lse, float* col_nll, float* col_ml, int* flag) {
-  // 64 columns x 4 interleaved groups of row blocks per CTA; loads are batched 8 deep so the
-  // merge is not a chain of dependent L2 round trips.
-  __shared__ float sm_m[4][64], sm_l[4][64];
-  const int cx = threadIdx.x & 63, grp = threadIdx.x >> 6;
-  const int64_t j = (int64_t)blockIdx.x * 64 + cx;
-  const int64_t jc = j < n_all ? j : n_all - 1;
-  const int64_t ht = jc / 32;
-  float M = -INFINITY, L = 0.f;
-  for (int b0 = grp; b0 < nblk; b0 += 32) {
-    float mb[8], c[8];
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const int b = b0 + 4 * u;
-      mb[u] = b < nblk ? col_ref[(int64_t)b * 4 * col_tiles + ht] : -INFINITY;
-      c[u] = b < nblk ? col_part[(int64_t)b * ld + jc] : 0.f;
-    }
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      if (!(mb[u] > -INFINITY)) continue;
-      if (mb[u] > M) {
-        L = L * exp2f(M - mb[u]) + c[u];
-        M = mb[u];
-      } else {
-        L = fmaf(c[u], exp2f(mb[u] - M), L);
-      }
-    }
-  }
-  sm_m[grp][cx] = M;
-  sm_l[grp][cx] = L;
-  __syncthreads();
-  if (grp == 0 && j < n_all) {
-    float Mt = fmaxf(fmaxf(sm_m[0][cx], sm_m[1][cx]), fmaxf(sm_m[2][cx], sm_m[3][cx]));
-    float Lt = 0.f;
-#pragma unroll
-    for (int g = 0; g < 4; ++g)
-      if (sm_m[g][cx] > -INFINITY) Lt = fmaf(sm_l[g][cx], exp2f(sm_m[g][cx] - Mt), Lt);
-    if (col_ml) {
-      col_ml[2 * j] = Mt;
-      col_ml[2 * j + 1] = Lt;
-      return;
-    }
-    const float logL = log2f(Lt);
-    const float lse2 = Mt + logL;
-    col_lse[j] = lse2 * kLn2;
-    if (col_nll) col_nll[j] = (fmaf(-(__ldg(logit_scale) * kLog2e), diag[j], Mt) + logL) * kLn2;
-    const bool ok = (Mt - lse2) + log2f((float)nblk) < 95.0f;    // false for NaN / -inf too
-    if (!ok) atomicOr(flag, 1);
-  }
-}
-
 // Multi-rank forward: `gathered` is the all-gathered per-rank payload [world, stride] with
 // col_ml [n_all, 2] | row_lse [n_loc] | row_nll [n_loc] | label_logit [n_loc] per rank.  Merges
 // the column (max, sum) pairs into every column's LSE and per-sample loss term (same exactness
@@ -215,33 +148,143 @@ col_merge_kernel(const float* gathered, int64_t stride, int world, int64_t n_loc
   if (!ok) atomicOr(flag, 1);
 }
 
-// Fallback only: overwrite the column LSE (and loss term) with the exact row-kernel result
-// when requested.  label logit = label_scale * label_dot (pass logit_scale = NULL if
-// label_dot already holds the scaled logit).
-__global__ void __launch_bounds__(256)
-gated_merge_kernel(const int* gate, const float* pmax, const float* psum, int nparts,
-                   int64_t n_loc, const float* label_dot, const float* logit_scale, float* lse_out,
-                   float* nll_out) {
-  if (*gate == 0) return;
-  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
-  if (i >= n_loc) return;
-  float M, logL;
-  merge_parts2(pmax, psum, nparts, n_loc, i, M, logL);
-  lse_out[i] = (M + logL) * kLn2;
-  if (nll_out) {
-    const float s = logit_scale ? __ldg(logit_scale) : 1.f;
-    nll_out[i] = ((M - s * kLog2e * label_dot[i]) + logL) * kLn2;
+// ---- one launch for everything the pair forward sweep leaves to finish ------------------------
+// Rows: merge the (slot, epilogue group, tile half) partials of every row.  Which slots hold data
+// follows from the tile schedule alone (a group owns every second tile of its cluster's range), so
+// the partial arrays need no "empty" fill beforehand.  Columns: per-128-row-block partial sums -> (max, sum) per column (see below).
+struct PairFinalizeArgs {
+  const float* pmax; const float* psum; int64_t n_loc; int col_tiles; int64_t total; int64_t ncl;
+  const float* diag; const float* logit_scale;
+  float* row_lse; float* row_nll; float* label_logit;         // label_logit nullable
+  const float* col_part; const float* col_ref; int64_t ld; int nblk; int64_t n_all;   // col_part nullable
+  float* col_lse; float* col_nll; float* col_ml; int* flag;
+};
+
+__device__ __forceinline__ bool pair_group_has_tile(int64_t cl, int64_t rb, int col_tiles, int64_t total,
+                                                    int64_t ncl, int group) {
+  const int64_t u0 = cl * total / ncl, u1 = (cl + 1) * total / ncl;
+  const int64_t t0 = rb * col_tiles, t1 = t0 + col_tiles;
+  const int64_t a = u0 > t0 ? u0 : t0, b = u1 < t1 ? u1 : t1;
+  if (b - a >= 2) return true;
+  if (b - a <= 0) return false;
+  return ((a - u0) & 1) == group;
+}
+
+__device__ __forceinline__ void pair_finalize_row(const PairFinalizeArgs& a, int64_t i) {
+  const int64_t rb = i / 256;
+  const int64_t c0 = cluster_of_tile(rb * a.col_tiles, a.total, a.ncl);
+  const int64_t c1 = cluster_of_tile(rb * a.col_tiles + a.col_tiles - 1, a.total, a.ncl);
+  float M = -INFINITY;
+  for (int64_t c = c0; c <= c1; ++c)
+#pragma unroll
+    for (int g = 0; g < 2; ++g)
+      if (pair_group_has_tile(c, rb, a.col_tiles, a.total, a.ncl, g)) {
+        const int64_t base = ((c - c0) * 2 + g) * 2 * a.n_loc + i;
+        M = fmaxf(M, fmaxf(a.pmax[base], a.pmax[base + a.n_loc]));
+      }
+  float L = 0.f;
+  for (int64_t c = c0; c <= c1; ++c)
+#pragma unroll
+    for (int g = 0; g < 2; ++g)
+      if (pair_group_has_tile(c, rb, a.col_tiles, a.total, a.ncl, g)) {
+        const int64_t base = ((c - c0) * 2 + g) * 2 * a.n_loc + i;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const float m = a.pmax[base + h * a.n_loc];
+          if (m > -INFINITY) L += a.psum[base + h * a.n_loc] * exp2f(m - M);
+        }
+      }
+  const float logL = log2f(L);
+  a.row_lse[i] = (M + logL) * kLn2;
+  const float s = __ldg(a.logit_scale);
+  // fma(-c2, dot, M): the exact residual the sweep's own fma(dot, c2, -M) saw for the label
+  if (a.row_nll) a.row_nll[i] = (fmaf(-(s * kLog2e), a.diag[i], M) + logL) * kLn2;
+  if (a.label_logit) a.label_logit[i] = s * a.diag[i];
+}
+
+__global__ void __launch_bounds__(256) pair_fwd_finalize_kernel(const PairFinalizeArgs a) {
+  if (!a.col_part) {                       // rows only: 256 rows per CTA
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i < a.n_loc) pair_finalize_row(a, i);
+    return;
+  }
+  // 64 columns x 4 interleaved groups of row blocks per CTA; loads are batched 8 deep so the
+  // merge is not a chain of dependent L2 round trips.
+  __shared__ float sm_m[4][64], sm_l[4][64];
+  const int cx = threadIdx.x & 63, grp = threadIdx.x >> 6;
+  const int64_t j = (int64_t)blockIdx.x * 64 + cx;
+  const int64_t jc = j < a.n_all ? j : a.n_all - 1;
+  const int64_t ht = jc / 32;
+  float M = -INFINITY, L = 0.f;
+  for (int b0 = grp; b0 < a.nblk; b0 += 32) {
+    float mb[8], c[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int b = b0 + 4 * u;
+      mb[u] = b < a.nblk ? a.col_ref[(int64_t)b * 4 * a.col_tiles + ht] : -INFINITY;
+      c[u] = b < a.nblk ? a.col_part[(int64_t)b * a.ld + jc] : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      if (!(mb[u] > -INFINITY)) continue;
+      if (mb[u] > M) {
+        L = L * exp2f(M - mb[u]) + c[u];
+        M = mb[u];
+      } else {
+        L = fmaf(c[u], exp2f(mb[u] - M), L);
+      }
+    }
+  }
+  sm_m[grp][cx] = M;
+  sm_l[grp][cx] = L;
+  __syncthreads();
+  if (grp == 1 && j < a.n_loc) pair_finalize_row(a, j);      // this CTA's 64 rows
+  if (grp == 0 && j < a.n_all) {
+    float Mt = fmaxf(fmaxf(sm_m[0][cx], sm_m[1][cx]), fmaxf(sm_m[2][cx], sm_m[3][cx]));
+    float Lt = 0.f;
+#pragma unroll
+    for (int g = 0; g < 4; ++g)
+      if (sm_m[g][cx] > -INFINITY) Lt = fmaf(sm_l[g][cx], exp2f(sm_m[g][cx] - Mt), Lt);
+    if (a.col_ml) {
+      a.col_ml[2 * j] = Mt;
+      a.col_ml[2 * j + 1] = Lt;
+      return;
+    }
+    const float logL = log2f(Lt);
+    const float lse2 = Mt + logL;
+    a.col_lse[j] = lse2 * kLn2;
+    if (a.col_nll) a.col_nll[j] = (fmaf(-(__ldg(a.logit_scale) * kLog2e), a.diag[j], Mt) + logL) * kLn2;
+    const bool ok = (Mt - lse2) + log2f((float)a.nblk) < 95.0f;    // false for NaN / -inf too
+    if (!ok) atomicOr(a.flag, 1);
   }
 }
 
-// partial sums of the per-sample loss terms: sum_i row_nll[i] + col_nll[i]
+// Last kernel of a forward: (gated) overwrite of the column LSE / loss term with the exact
+// row-kernel result, then the loss = sum over rows [loss_off, loss_off + n_loss) of
+// row_nll + col_nll, / (2 n_loss)  (loss.py:126-129).  Per-CTA partials, added in order by the
+// last CTA to arrive (counter must be 0 on entry and is 0 again on exit).
 __global__ void __launch_bounds__(256)
-nll_loss_partial_kernel(const float* row_nll, const float* col_nll, int64_t n_loc,
-                        double* loss_partial) {
+pair_fwd_finish_kernel(const int* gate, const float* pmax, const float* psum, int nparts,
+                       int64_t n_merge, const float* label_dot, const float* logit_scale,
+                       float* lse_out, float* nll_out, const float* row_nll, const float* col_nll,
+                       int64_t loss_off, int64_t n_loss, double* loss_partial, unsigned int* counter,
+                       float* loss) {
   __shared__ double red[8];
+  __shared__ bool last;
   const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
   double acc = 0.0;
-  if (i < n_loc) acc = (double)row_nll[i] + (double)col_nll[i];
+  if (i < n_merge) {
+    float cn = col_nll[i];
+    if (gate && *gate != 0) {
+      float M, logL;
+      merge_parts2(pmax, psum, nparts, n_merge, i, M, logL);
+      lse_out[i] = (M + logL) * kLn2;
+      const float s = logit_scale ? __ldg(logit_scale) : 1.f;
+      cn = ((M - s * kLog2e * label_dot[i]) + logL) * kLn2;
+      nll_out[i] = cn;
+    }
+    if (i >= loss_off && i < loss_off + n_loss) acc = (double)row_nll[i] + (double)cn;
+  }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
@@ -250,6 +293,22 @@ nll_loss_partial_kernel(const float* row_nll, const float* col_nll, int64_t n_lo
     double tot = 0.0;
     for (int w = 0; w < 8; ++w) tot += red[w];
     loss_partial[blockIdx.x] = tot;
+    __threadfence();
+    last = atomicInc(counter, gridDim.x - 1) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  double v = 0.0;
+  for (int b = threadIdx.x; b < (int)gridDim.x; b += 256) v += __ldcg(loss_partial + b);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tot = 0.0;
+    for (int w = 0; w < 8; ++w) tot += red[w];
+    *loss = (float)(tot / (2.0 * (double)n_loss));
   }
 }
 
@@ -301,8 +360,10 @@ pair_prep_features_kernel(const void* img, int64_t ld_img, const void* txt, int6
           hi[e] = __float22half2_rn(a);
           ht[e] = __float22half2_rn(b);
         }
-        *reinterpret_cast<uint4*>(img16 + k * ld16 + c) = oi;
-        if (txt16 != img16) *reinterpret_cast<uint4*>(txt16 + k * ld16 + c) = ot;
+        if (img16) {
+          *reinterpret_cast<uint4*>(img16 + k * ld16 + c) = oi;
+          if (txt16 != img16) *reinterpret_cast<uint4*>(txt16 + k * ld16 + c) = ot;
+        }
       } else {
         const uint4 ri = *reinterpret_cast<const uint4*>(static_cast<const __half*>(img) + k * ld_img + c);
         const uint4 rt = *reinterpret_cast<const uint4*>(static_cast<const __half*>(txt) + k * ld_txt + c);
@@ -331,31 +392,42 @@ pair_prep_features_kernel(const void* img, int64_t ld_img, const void* txt, int6
 // one-ex2 epilogue); otherwise the sweep uses its two-ex2 epilogue.
 __global__ void __launch_bounds__(1024)
 lse_range_kernel(const float* row_lse, const float* col_lse, int64_t n_all, float* rho, int* flag,
-                 const unsigned int* u_bits, float* gscale_log2, const float* grad_loss,
+                 const unsigned int* u_bits, const float* row_nll, const float* col_nll,
+                 float* gscale_log2, const float* grad_loss,
                  float grad_mult, const float* logit_scale, int64_t n_loc, float* out_scale) {
-  __shared__ float smin[32], smax[32];
-  float lo = INFINITY, hi = -INFINITY;
+  __shared__ float smin[32], smax[32], sneg[32];
+  float lo = INFINITY, hi = -INFINITY, nmin = INFINITY;
   for (int64_t i = threadIdx.x; i < n_all; i += 1024) {
     const float a = row_lse[i], b = col_lse[i];
     lo = fminf(lo, fminf(a, b));
     hi = fmaxf(hi, fmaxf(a, b));
+    // 1 - P_kk = -expm1(-nll_k) grows with nll_k: the largest nll gives the bound on |G|
+    if (row_nll) nmin = fminf(nmin, fminf(-row_nll[i], -col_nll[i]));
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
     hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    nmin = fminf(nmin, __shfl_xor_sync(0xffffffffu, nmin, o));
   }
-  if ((threadIdx.x & 31) == 0) { smin[threadIdx.x >> 5] = lo; smax[threadIdx.x >> 5] = hi; }
+  if ((threadIdx.x & 31) == 0) {
+    smin[threadIdx.x >> 5] = lo; smax[threadIdx.x >> 5] = hi; sneg[threadIdx.x >> 5] = nmin;
+  }
   __syncthreads();
   if (threadIdx.x == 0) {
-    for (int w = 0; w < 32; ++w) { lo = fminf(lo, smin[w]); hi = fmaxf(hi, smax[w]); }
+    for (int w = 0; w < 32; ++w) {
+      lo = fminf(lo, smin[w]); hi = fmaxf(hi, smax[w]); nmin = fminf(nmin, sneg[w]);
+    }
     lo *= kLog2e; hi *= kLog2e;
     const bool ok = (hi - lo) <= 64.0f && hi < 3.0e38f && lo > -3.0e38f;   // also rejects NaN / inf
     *rho = ok ? 0.5f * (lo + hi) : 0.f;
     *flag = ok ? 1 : 0;
     // |G| <= 2u; the LSE / label-logit inputs carry ~5e-5 of fp32 error, so pad u by 1e-3:
     // 2 (u + 1e-3) 2^gs <= 2^14 keeps fp16 G finite.  gs = 13 for u ~ 1, up to 22 when converged.
-    const float u = fminf(__uint_as_float(*u_bits), 1.0f) + 1.0e-3f;
+    // nmin = -max nll (clamped at 0: an nll can come out slightly negative); NaN -> u = 1
+    float u_raw = row_nll ? -expm1f(fminf(nmin, 0.f)) : __uint_as_float(*u_bits);
+    if (!(u_raw >= 0.f)) u_raw = 1.0f;
+    const float u = fminf(u_raw, 1.0f) + 1.0e-3f;
     const float gs = fminf(fmaxf(13.0f - ceilf(log2f(u)), 13.0f), 22.0f);
     *gscale_log2 = gs;
     // gradient = out_scale * (accumulated G . features)
@@ -637,6 +709,8 @@ static int clip_fwd_impl(const void* img_loc, int64_t ld_img_loc, const void* tx
       clip_pair_supported(dtype, dim, ld_txt_loc, ld_img_all, txt_loc, img_all)) {
     const PairFwdGeom f = clip_pair_fwd_geom(n_loc, n_all);
     const bool single = n_loc == n_all && img_loc == img_all && txt_loc == txt_all;
+    int* flag = reinterpret_cast<int*>(ws + w.off_flag);
+    unsigned int* counter = reinterpret_cast<unsigned int*>(flag + 1);
     PairFwdArgs pa;
     pa.dtype = dtype; pa.n_loc = n_loc; pa.n_all = n_all; pa.dim = dim;
     pa.label_offset = label_offset; pa.logit_scale = logit_scale;
@@ -644,24 +718,20 @@ static int clip_fwd_impl(const void* img_loc, int64_t ld_img_loc, const void* tx
     pa.part_max = ws + w.off_pp_max_r; pa.part_sum = ws + w.off_pp_sum_r; pa.diag = ws + w.off_diag_r;
     pa.col_part = single ? ws + w.off_colpart : nullptr;
     pa.col_ref = ws + w.off_colref;
-    // 0xFF bytes = NaN = "slot not written" (an epilogue group may own no tile of a row block)
-    const size_t pp_bytes = (size_t)4 * f.slots * (size_t)n_loc * sizeof(float);
+    pa.zero2 = flag;                       // the sweep clears the fallback flag and the loss counter
     LATTE_MARK(-1);
-    LATTE_CUDA_OK(cudaMemsetAsync(pa.part_max, 0xFF, pp_bytes, st));
-    LATTE_MARK(LATTE_STAGE_FWD_FINALIZE);
     int rc = clip_pair_fwd_sweep(pa, st);
     if (rc) return rc;
     LATTE_MARK(LATTE_STAGE_FWD_SWEEP);
-    pair_row_finalize_kernel<<<rblocks, 256, 0, st>>>(pa.part_max, pa.part_sum, n_loc, f.col_tiles,
-                                                      f.total, f.ncl, pa.diag, logit_scale, row_lse,
-                                                      row_nll, nullptr);
-    LATTE_LAUNCH_OK();
+    PairFinalizeArgs fa = {};
+    fa.pmax = pa.part_max; fa.psum = pa.part_sum; fa.n_loc = n_loc; fa.col_tiles = f.col_tiles;
+    fa.total = f.total; fa.ncl = f.ncl; fa.diag = pa.diag; fa.logit_scale = logit_scale;
+    fa.row_lse = row_lse; fa.row_nll = row_nll; fa.label_logit = nullptr;
     if (single) {
-      int* flag = reinterpret_cast<int*>(ws + w.off_flag);
-      LATTE_CUDA_OK(cudaMemsetAsync(flag, 0, sizeof(int), st));
-      pair_col_finalize_kernel<<<(unsigned)((n_all + 63) / 64), 256, 0, st>>>(
-          ws + w.off_colpart, ws + w.off_colref, f.ld_colpart, 2 * f.row_blocks, f.col_tiles, n_all,
-          pa.diag, logit_scale, col_lse, col_nll, nullptr, flag);
+      fa.col_part = ws + w.off_colpart; fa.col_ref = ws + w.off_colref; fa.ld = f.ld_colpart;
+      fa.nblk = 2 * f.row_blocks; fa.n_all = n_all;
+      fa.col_lse = col_lse; fa.col_nll = col_nll; fa.col_ml = nullptr; fa.flag = flag;
+      pair_fwd_finalize_kernel<<<(unsigned)((n_all + 63) / 64), 256, 0, st>>>(fa);
       LATTE_LAUNCH_OK();
       // exact fallback for columns whose partial sums may have lost flushed terms: the row
       // kernel on the transposed problem; it and the merge return at once unless flagged
@@ -670,27 +740,30 @@ static int clip_fwd_impl(const void* img_loc, int64_t ld_img_loc, const void* tx
       a.part_max = ws + w.off_pmax_c; a.part_sum = ws + w.off_psum_c; a.diag = ws + w.off_diag_c;
       rc = clip_fwd_rows_tc(a, st);
       if (rc) return rc;
-      gated_merge_kernel<<<rblocks, 256, 0, st>>>(flag, a.part_max, a.part_sum, nparts, n_loc,
-                                                  pa.diag, logit_scale, col_lse, col_nll);
+      pair_fwd_finish_kernel<<<rblocks, 256, 0, st>>>(flag, a.part_max, a.part_sum, nparts, n_loc,
+                                                      pa.diag, logit_scale, col_lse, col_nll, row_nll,
+                                                      col_nll, 0, n_loc, lossp, counter, loss);
       LATTE_LAUNCH_OK();
     } else {
+      pair_fwd_finalize_kernel<<<rblocks, 256, 0, st>>>(fa);
+      LATTE_LAUNCH_OK();
+      LATTE_MARK(LATTE_STAGE_FWD_FINALIZE);
       pa.x = txt_loc; pa.ldx = ld_txt_loc; pa.y = img_all; pa.ldy = ld_img_all;
       pa.part_max = ws + w.off_pp_max_c; pa.part_sum = ws + w.off_pp_sum_c; pa.diag = ws + w.off_diag_c;
       pa.col_part = nullptr;
-      LATTE_CUDA_OK(cudaMemsetAsync(pa.part_max, 0xFF, pp_bytes, st));
-      LATTE_MARK(LATTE_STAGE_FWD_FINALIZE);
+      pa.zero2 = nullptr;
       rc = clip_pair_fwd_sweep(pa, st);
       if (rc) return rc;
       LATTE_MARK(LATTE_STAGE_FWD_SWEEP);
-      pair_row_finalize_kernel<<<rblocks, 256, 0, st>>>(pa.part_max, pa.part_sum, n_loc, f.col_tiles,
-                                                        f.total, f.ncl, pa.diag, logit_scale, col_lse,
-                                                        col_nll, nullptr);
+      fa.pmax = pa.part_max; fa.psum = pa.part_sum; fa.diag = pa.diag;
+      fa.row_lse = col_lse; fa.row_nll = col_nll;
+      pair_fwd_finalize_kernel<<<rblocks, 256, 0, st>>>(fa);
+      LATTE_LAUNCH_OK();
+      pair_fwd_finish_kernel<<<rblocks, 256, 0, st>>>(nullptr, nullptr, nullptr, 0, n_loc, nullptr,
+                                                      nullptr, nullptr, nullptr, row_nll, col_nll, 0,
+                                                      n_loc, lossp, counter, loss);
       LATTE_LAUNCH_OK();
     }
-    nll_loss_partial_kernel<<<rblocks, 256, 0, st>>>(row_nll, col_nll, n_loc, lossp);
-    LATTE_LAUNCH_OK();
-    loss_reduce_kernel<<<1, 256, 0, st>>>(lossp, (int)rblocks, n_loc, loss);
-    LATTE_LAUNCH_OK();
     LATTE_MARK(LATTE_STAGE_FWD_FINALIZE);
     return LATTE_OK;
   }
@@ -763,20 +836,19 @@ static int clip_fwd_rows_impl(const void* img_loc, int64_t ld_img_loc, const voi
   pa.part_max = ws + w.off_pp_max_r; pa.part_sum = ws + w.off_pp_sum_r; pa.diag = ws + w.off_diag_r;
   pa.col_part = ws + w.off_colpart;
   pa.col_ref = ws + w.off_colref;
-  const size_t pp_bytes = (size_t)4 * f.slots * (size_t)n_loc * sizeof(float);
+  pa.zero2 = nullptr;
   LATTE_MARK(-1);
-  LATTE_CUDA_OK(cudaMemsetAsync(pa.part_max, 0xFF, pp_bytes, st));
-  LATTE_MARK(LATTE_STAGE_FWD_FINALIZE);
   int rc = clip_pair_fwd_sweep(pa, st);
   if (rc) return rc;
   LATTE_MARK(LATTE_STAGE_FWD_SWEEP);
-  pair_row_finalize_kernel<<<(unsigned)((n_loc + 255) / 256), 256, 0, st>>>(
-      pa.part_max, pa.part_sum, n_loc, f.col_tiles, f.total, f.ncl, pa.diag, logit_scale, row_lse,
-      row_nll, label_logit);
-  LATTE_LAUNCH_OK();
-  pair_col_finalize_kernel<<<(unsigned)((n_all + 63) / 64), 256, 0, st>>>(
-      ws + w.off_colpart, ws + w.off_colref, f.ld_colpart, 2 * f.row_blocks, f.col_tiles, n_all,
-      nullptr, logit_scale, nullptr, nullptr, col_ml, nullptr);
+  PairFinalizeArgs fa = {};
+  fa.pmax = pa.part_max; fa.psum = pa.part_sum; fa.n_loc = n_loc; fa.col_tiles = f.col_tiles;
+  fa.total = f.total; fa.ncl = f.ncl; fa.diag = pa.diag; fa.logit_scale = logit_scale;
+  fa.row_lse = row_lse; fa.row_nll = row_nll; fa.label_logit = label_logit;
+  fa.col_part = ws + w.off_colpart; fa.col_ref = ws + w.off_colref; fa.ld = f.ld_colpart;
+  fa.nblk = 2 * f.row_blocks; fa.n_all = n_all;
+  fa.col_lse = nullptr; fa.col_nll = nullptr; fa.col_ml = col_ml; fa.flag = nullptr;
+  pair_fwd_finalize_kernel<<<(unsigned)((n_all + 63) / 64), 256, 0, st>>>(fa);
   LATTE_LAUNCH_OK();
   LATTE_MARK(LATTE_STAGE_FWD_FINALIZE);
   return LATTE_OK;
@@ -822,7 +894,8 @@ extern "C" int latte_clip_fwd_cols(const float* gathered, int64_t stride, int wo
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int* flag = reinterpret_cast<int*>(ws + w.off_flag);
   float* label_logit_all = ws + w.off_nll_r;           // [n_all] scratch of this layout
-  LATTE_CUDA_OK(cudaMemsetAsync(flag, 0, sizeof(int), st));
+  LATTE_CUDA_OK(cudaMemsetAsync(flag, 0, 2 * sizeof(int), st));     // fallback flag + loss counter
+  unsigned int* counter = reinterpret_cast<unsigned int*>(flag + 1);
   const int nblk_total = (int)((n_all + 127) / 128);
   col_merge_kernel<<<(unsigned)((n_all + 255) / 256), 256, 0, st>>>(
       gathered, stride, world, n_loc, n_all, nblk_total, row_lse_all, row_nll_all, label_logit_all,
@@ -839,16 +912,10 @@ extern "C" int latte_clip_fwd_cols(const float* gathered, int64_t stride, int wo
   a.part_max = ws + w.off_pmax_c; a.part_sum = ws + w.off_psum_c; a.diag = ws + w.off_diag_c;
   int rc = clip_fwd_rows_tc(a, st);
   if (rc) return rc;
-  gated_merge_kernel<<<(unsigned)((n_all + 255) / 256), 256, 0, st>>>(
-      flag, a.part_max, a.part_sum, nparts, n_all, label_logit_all, nullptr, col_lse_all,
-      col_nll_all);
-  LATTE_LAUNCH_OK();
-  const unsigned rblocks = (unsigned)((n_loc + 255) / 256);
   double* lossp = reinterpret_cast<double*>(ws + w.off_lossp);
-  nll_loss_partial_kernel<<<rblocks, 256, 0, st>>>(row_nll_all + label_offset,
-                                                   col_nll_all + label_offset, n_loc, lossp);
-  LATTE_LAUNCH_OK();
-  loss_reduce_kernel<<<1, 256, 0, st>>>(lossp, (int)rblocks, n_loc, loss);
+  pair_fwd_finish_kernel<<<(unsigned)((n_all + 255) / 256), 256, 0, st>>>(
+      flag, a.part_max, a.part_sum, nparts, n_all, label_logit_all, nullptr, col_lse_all, col_nll_all,
+      row_nll_all, col_nll_all, label_offset, n_loc, lossp, counter, loss);
   LATTE_LAUNCH_OK();
   return LATTE_OK;
 }
@@ -894,21 +961,31 @@ static int clip_bwd_impl(const void* img_loc, int64_t ld_img_loc, const void* tx
       w.pair && clip_pair_supported(dtype, dim, ld_img_loc, ld_txt_all, img_loc, txt_all) &&
       clip_pair_supported(dtype, dim, ld_txt_loc, ld_img_all, txt_loc, img_all) &&
       clip_pair_supported(dtype, dim, ld_img_all, ld_txt_all, img_all, txt_all);
+  // bf16 features feed the gradient GEMMs directly (A = fp16 G, B = bf16 features); fp16 copies are
+  // only made when LATTE_B200_FP16_COPIES=1 asks for the round-1 operand format
+  const bool copies16 = pair_ok && dtype == LATTE_BF16 && want_fp16_copies();
+  const bool have_nll = row_nll_all != nullptr;
   if (pair_ok) {
-    // fp16 copies of the gathered features (bf16 input) + bound on |G| -> fp16 scale of G
-    LATTE_CUDA_OK(cudaMemsetAsync(u_bits, 0, sizeof(unsigned int), st));
-    __half* ya = reinterpret_cast<__half*>(ws + w.off_y16a);      // txt
-    __half* yb = img_all == txt_all ? ya : reinterpret_cast<__half*>(ws + w.off_y16b);   // img
-    const int64_t warps_needed = n_all;
-    const unsigned blocks = (unsigned)((warps_needed * 32 + 255) / 256 < 4096
-                                           ? (warps_needed * 32 + 255) / 256 : 4096);
-    pair_prep_features_kernel<<<blocks, 256, 0, st>>>(img_all, ld_img_all, txt_all, ld_txt_all,
-                                                      dtype == LATTE_BF16 ? 1 : 0, yb, ya,
-                                                      (int64_t)w.ld16, n_all, dim, logit_scale,
-                                                      row_lse_all, col_lse_all, u_bits);
-    LATTE_LAUNCH_OK();
+    // bound on |G| -> fp16 scale of G: from the per-sample loss terms when the caller has them,
+    // else from the label logits (one pass over the gathered features)
+    if (copies16 || !have_nll) {
+      LATTE_CUDA_OK(cudaMemsetAsync(u_bits, 0, sizeof(unsigned int), st));
+      __half* ya = copies16 ? reinterpret_cast<__half*>(ws + w.off_y16a) : nullptr;      // txt
+      __half* yb = !copies16 ? nullptr
+                             : (img_all == txt_all ? ya : reinterpret_cast<__half*>(ws + w.off_y16b));
+      const int64_t warps_needed = n_all;
+      const unsigned blocks = (unsigned)((warps_needed * 32 + 255) / 256 < 4096
+                                             ? (warps_needed * 32 + 255) / 256 : 4096);
+      pair_prep_features_kernel<<<blocks, 256, 0, st>>>(img_all, ld_img_all, txt_all, ld_txt_all,
+                                                        dtype == LATTE_BF16 ? 1 : 0, yb, ya,
+                                                        (int64_t)w.ld16, n_all, dim, logit_scale,
+                                                        row_lse_all, col_lse_all, u_bits);
+      LATTE_LAUNCH_OK();
+    }
     lse_range_kernel<<<1, 1024, 0, st>>>(row_lse_all, col_lse_all, n_all, rho, fast_flag, u_bits,
-                                         gscale, grad_loss, grad_mult, logit_scale, n_loc, out_scale);
+                                         have_nll ? row_nll_all : nullptr,
+                                         have_nll ? col_nll_all : nullptr, gscale, grad_loss,
+                                         grad_mult, logit_scale, n_loc, out_scale);
     LATTE_LAUNCH_OK();
   }
   lse_vectors_kernel<<<(unsigned)((w.n_pad + 255) / 256), 256, 0, st>>>(
@@ -924,7 +1001,9 @@ static int clip_bwd_impl(const void* img_loc, int64_t ld_img_loc, const void* tx
   // fp16 operands for the second GEMM of the tc path
   const void* txt16 = txt_all; int64_t ld_txt16 = ld_txt_all;
   const void* img16 = img_all; int64_t ld_img16 = ld_img_all;
-  if (pair_ok && dtype == LATTE_BF16) {
+  if (pair_ok && dtype == LATTE_BF16 && !copies16) {
+    // mixed-format MMA: the bf16 features are the GEMM operands as they are
+  } else if (pair_ok && dtype == LATTE_BF16) {
     txt16 = ws + w.off_y16a; ld_txt16 = (int64_t)w.ld16;
     img16 = img_all == txt_all ? txt16 : static_cast<const void*>(ws + w.off_y16b);
     ld_img16 = (int64_t)w.ld16;
@@ -970,66 +1049,96 @@ static int clip_bwd_impl(const void* img_loc, int64_t ld_img_loc, const void* tx
     const bool rank_sweep = !single && (d_txt_partial != nullptr || d_txt_peers != nullptr) && cross_terms;
     if ((d_txt_partial || d_txt_peers) && !rank_sweep) return LATTE_ERR_BAD_ARG;
     if (!rank_sweep && !d_txt) return LATTE_ERR_BAD_ARG;
-    LATTE_CUDA_OK(cudaMemsetAsync(acc_i, 0, acc_bytes, st));
-    if (rank_sweep) {
-      // peer accumulators are zeroed (and fenced by a cross-rank barrier) by the caller
-      if (d_txt_partial)
-        LATTE_CUDA_OK(cudaMemsetAsync(d_txt_partial, 0, (size_t)n_all * (size_t)dim * sizeof(float), st));
-    } else {
-      LATTE_CUDA_OK(cudaMemsetAsync(acc_t, 0, acc_bytes, st));
-    }
     PairSweepArgs sa;
     sa.dtype = dtype; sa.n_loc = n_loc; sa.n_all = n_all; sa.dim = dim;
     sa.label_offset = label_offset; sa.logit_scale = logit_scale; sa.cross_terms = cross_terms;
     sa.g = gbuf; sa.ds_both = (single || rank_sweep) ? 1 : 0;
     sa.nll_a = row_nll_all; sa.nll_b = col_nll_all;
-    PairGemmArgs ga;
+    PairGemmArgs ga = {};
     ga.g = gbuf; ga.n_loc = n_loc; ga.n_all = n_all; ga.dim = dim; ga.ld32 = (int64_t)w.ld32;
+    ga.feat_dtype = copies16 ? LATTE_F16 : dtype;
+    // Gradients of tiles owned by one cluster are written by the GEMM epilogue itself (scaled, in
+    // the gradient dtype); the fp32 accumulators only serve the tiles the schedule splits.
+    ga.out_dtype = grad_dtype; ga.ld_out = ld_grad; ga.out_scale = out_scale;
     // image side: G[loc rows, :] and d_img = G . txt_all  (+ d_txt = G^T . img for one rank)
     sa.x = img_loc; sa.ldx = ld_img_loc; sa.y = txt_all; sa.ldy = ld_txt_all;
     sa.lse_a2 = row2; sa.lse_b2 = col2; sa.ds_partial = dsp;
     sa.e_a = ws + w.off_erow; sa.einv_b = ws + w.off_einvcol; sa.fast_flag = fast_flag;
     sa.gscale_log2 = gscale;
-    LATTE_MARK(LATTE_STAGE_BWD_PREP);
-    int rc = clip_pair_sweep(sa, st);
-    if (rc) return rc;
-    LATTE_MARK(LATTE_STAGE_BWD_SWEEP);
     ga.y16 = txt16; ga.ldy16 = ld_txt16;
     ga.x16 = single ? img16 : nullptr; ga.ldx16 = ld_img16;
     ga.dx32 = acc_i; ga.dy32 = acc_t;
     ga.ld_dy32 = (int64_t)w.ld32; ga.dy_scale = nullptr;
     ga.dy_peers = nullptr; ga.n_peers = 0;
+    ga.dx_out = d_img; ga.dy_out = single ? d_txt : nullptr;
     if (rank_sweep) {
-      // rows [label_offset, label_offset + n_loc) of the gathered fp16 images are this rank's
-      ga.x16 = static_cast<const __half*>(img16) + label_offset * ld_img16;
+      // rows [label_offset, label_offset + n_loc) of the gathered features are this rank's
+      ga.x16 = static_cast<const uint16_t*>(img16) + label_offset * ld_img16;
       ga.dy32 = d_txt_partial; ga.ld_dy32 = dim; ga.dy_scale = out_scale;
       if (d_txt_peers) {
         ga.dy32 = static_cast<float*>(d_txt_peers[0]);       // unused: every row has an owner
         ga.dy_peers = reinterpret_cast<float* const*>(d_txt_peers);
         ga.n_peers = n_peers;
       }
+      // peer accumulators are zeroed (and fenced by a cross-rank barrier) by the caller
+      if (d_txt_partial)
+        LATTE_CUDA_OK(cudaMemsetAsync(d_txt_partial, 0, (size_t)n_all * (size_t)dim * sizeof(float), st));
     }
+    const bool direct_i = clip_pair_gemm_direct(ga, 0);
+    const bool direct_t = single && clip_pair_gemm_direct(ga, 1);
+    if (!direct_i) LATTE_CUDA_OK(cudaMemsetAsync(acc_i, 0, acc_bytes, st));
+    if (single && !direct_t) LATTE_CUDA_OK(cudaMemsetAsync(acc_t, 0, acc_bytes, st));
+    int rc = clip_pair_gemm_fixup(ga, 0, st);
+    if (rc) return rc;
+    LATTE_MARK(LATTE_STAGE_BWD_PREP);
+    rc = clip_pair_sweep(sa, st);
+    if (rc) return rc;
+    LATTE_MARK(LATTE_STAGE_BWD_SWEEP);
     rc = clip_pair_gemm(ga, st);
     if (rc) return rc;
     LATTE_MARK(LATTE_STAGE_BWD_GEMM);
+    rc = clip_pair_gemm_fixup(ga, 1, st);
+    if (rc) return rc;
+    if (!direct_i) {
+      rc = clip_pair_scale_cast(acc_i, nullptr, (int64_t)w.ld32, d_img, nullptr, grad_dtype, ld_grad,
+                                n_loc, dim, out_scale, st);
+      if (rc) return rc;
+    }
+    if (single && !direct_t) {
+      rc = clip_pair_scale_cast(acc_t, nullptr, (int64_t)w.ld32, d_txt, nullptr, grad_dtype, ld_grad,
+                                n_loc, dim, out_scale, st);
+      if (rc) return rc;
+    }
+    bool direct_t2 = false;
     if (!single && !rank_sweep) {
       // text side: the transposed block G'[loc cols, :] and d_txt = G' . img_all
+      LATTE_MARK(LATTE_STAGE_BWD_FINISH);
       sa.x = txt_loc; sa.ldx = ld_txt_loc; sa.y = img_all; sa.ldy = ld_img_all;
       sa.lse_a2 = col2; sa.lse_b2 = row2; sa.ds_partial = dsp + dsn;
       sa.e_a = ws + w.off_ecol; sa.einv_b = ws + w.off_einvrow;
       sa.nll_a = col_nll_all; sa.nll_b = row_nll_all;
+      ga.y16 = img16; ga.ldy16 = ld_img16; ga.x16 = nullptr;
+      ga.dx32 = acc_t; ga.dy32 = nullptr; ga.dy_peers = nullptr; ga.n_peers = 0;
+      ga.dy_scale = nullptr; ga.dx_out = d_txt; ga.dy_out = nullptr;
+      direct_t2 = clip_pair_gemm_direct(ga, 0);
+      if (!direct_t2) LATTE_CUDA_OK(cudaMemsetAsync(acc_t, 0, acc_bytes, st));
+      rc = clip_pair_gemm_fixup(ga, 0, st);
+      if (rc) return rc;
+      LATTE_MARK(LATTE_STAGE_BWD_PREP);
       rc = clip_pair_sweep(sa, st);
       if (rc) return rc;
       LATTE_MARK(LATTE_STAGE_BWD_SWEEP);
-      ga.y16 = img16; ga.ldy16 = ld_img16; ga.x16 = nullptr;
-      ga.dx32 = acc_t; ga.dy32 = nullptr; ga.dy_peers = nullptr; ga.n_peers = 0;
       rc = clip_pair_gemm(ga, st);
       if (rc) return rc;
       LATTE_MARK(LATTE_STAGE_BWD_GEMM);
+      rc = clip_pair_gemm_fixup(ga, 1, st);
+      if (rc) return rc;
+      if (!direct_t2) {
+        rc = clip_pair_scale_cast(acc_t, nullptr, (int64_t)w.ld32, d_txt, nullptr, grad_dtype, ld_grad,
+                                  n_loc, dim, out_scale, st);
+        if (rc) return rc;
+      }
     }
-    rc = clip_pair_scale_cast(acc_i, rank_sweep ? nullptr : acc_t, (int64_t)w.ld32, d_img, d_txt,
-                              grad_dtype, ld_grad, n_loc, dim, out_scale, st);
-    if (rc) return rc;
     ds_reduce_kernel<<<1, 256, 0, st>>>(dsp, 2 * dsn, grad_loss, grad_mult, n_loc, d_scale);
     LATTE_LAUNCH_OK();
     LATTE_MARK(LATTE_STAGE_BWD_FINISH);
@@ -1101,14 +1210,15 @@ extern "C" int latte_clip_stage_times(const void* img_loc, int64_t ld_img_loc, c
     int rc;
     if (d_txt_partial) {
       // one-sweep multi-rank flow: step 1 of the forward (the merge step after the all-gather
-      // is a few microseconds and is not timed here), scratch outputs from the stream pool
-      float* tmp = nullptr;
-      const size_t tmp_floats = (size_t)3 * n_loc + (size_t)2 * n_all;
-      if (cudaMallocAsync(&tmp, tmp_floats * sizeof(float), st) != cudaSuccess) return LATTE_ERR_CUDA;
+      // is a few microseconds and is not timed here); its outputs land in the legacy partial
+      // arrays of the forward workspace, which this flow does not use
+      const WsLayout wl = ws_layout(n_loc, n_all, dim, dtype);
+      if ((size_t)3 * n_loc + (size_t)2 * n_all > 2 * wl.part || fwd_workspace_bytes < wl.total)
+        return LATTE_ERR_WORKSPACE;
+      float* tmp = static_cast<float*>(fwd_workspace) + wl.off_pmax_r;
       rc = clip_fwd_rows_impl(img_loc, ld_img_loc, txt_all, ld_txt_all, dtype, n_loc, n_all, dim,
                               label_offset, logit_scale, tmp, tmp + n_loc, tmp + 2 * n_loc,
                               tmp + 3 * n_loc, fwd_workspace, fwd_workspace_bytes, stream, &tm);
-      cudaFreeAsync(tmp, st);
     } else {
       rc = clip_fwd_impl(img_loc, ld_img_loc, txt_loc, ld_txt_loc, img_all, ld_img_all, txt_all,
                          ld_txt_all, dtype, n_loc, n_all, dim, label_offset, logit_scale, row_lse,

@@ -92,6 +92,7 @@ struct SweepParams {
   float* col_part;                   // [2 * row_blocks, ld_colpart]
   float* col_ref;                    // [2 * row_blocks, 4 * col_tiles]  (one per 32 columns)
   int64_t ld_colpart;
+  int* zero2;                        // nullable: two ints cleared by the first CTA (forward modes)
   int kch;                           // ceil(dim / 64)
   int cps;                           // feature chunks per ring stage (4, or 2 with an X tail)
   int tail_chunks;                   // chunks of X beyond the 8 held in TMEM (dim > 512): smem
@@ -186,6 +187,7 @@ pair_sweep_kernel(const __grid_constant__ CUtensorMap tmy, const __grid_constant
   float* red_ptr = reinterpret_cast<float*>(smem + (red_slot - smem_base));
 
   if (threadIdx.x == 0 && (smem_base & 1023u) != 0) __trap();
+  if (blockIdx.x == 0 && threadIdx.x == 0 && p.zero2) { p.zero2[0] = 0; p.zero2[1] = 0; }
 
   // contiguous range of the flattened (row block, column tile) space for this pair
   const int64_t total = (int64_t)p.row_blocks * p.col_tiles;
@@ -949,6 +951,14 @@ struct GemmProblem {
   int d_off;           // first feature column of the slab (multiple of 128)
   int nhalf;           // 64-column feature chunks per CTA in this slab (1..4)
   uint32_t idesc[2];   // per MMA group of the slab
+  // A segment that covers a WHOLE tile (every k chunk) never meets another cluster's partial sum:
+  // its epilogue writes direct_scale * acc straight into the gradient (nullable) and the fp32
+  // accumulator `out` is only used -- zeroed, added to and cast by gemm_fixup_kernel -- for tiles
+  // that the stream-K schedule splits between clusters.
+  void* direct;        // [m_rows, ld_direct] in direct_dtype, or NULL: always red.add into `out`
+  int direct_dtype;
+  int64_t ld_direct;
+  const float* direct_scale;
 };
 
 struct GemmParams {
@@ -1121,19 +1131,61 @@ pair_gemm_kernel(const __grid_constant__ CUtensorMap tma0, const __grid_constant
         orow = pr.peers[w] + (m - w * pr.rows_per_peer) * pr.ld_out;
       }
       const float osc = pr.scale ? __ldg(pr.scale) : 1.0f;
+      const bool whole = pr.direct != nullptr && k0 == 0 && k1 == pr.k_chunks;
       mbar_wait(bar_tfull, seg & 1);
       tc_fence_after();
-      for (int cc = 0; cc < cols_half; cc += 32) {
-        const int col = half * cols_half + cc;
-        uint32_t v[32];
-        tmem_ld_32x32(tmem_base + lane_base + col, v);
-        tmem_ld_wait();
-        if (m_ok) {
+      if (whole) {
+        const float dsc = __ldg(pr.direct_scale);
+        const int64_t mrow = m_ok ? m : 0;
+        for (int cc = 0; cc < cols_half; cc += 32) {
+          const int col = half * cols_half + cc;
+          uint32_t v[32];
+          tmem_ld_32x32(tmem_base + lane_base + col, v);
+          tmem_ld_wait();
+          if (!m_ok) continue;
+          const int dcol = pr.d_off + col;
+          if (pr.direct_dtype == LATTE_F32) {
+            float* o = static_cast<float*>(pr.direct) + mrow * pr.ld_direct + dcol;
 #pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            if (pr.d_off + col + i < p.dim)
-              red_add_v4(orow + pr.d_off + col + i, osc * __uint_as_float(v[i]), osc * __uint_as_float(v[i + 1]),
-                         osc * __uint_as_float(v[i + 2]), osc * __uint_as_float(v[i + 3]));
+            for (int i = 0; i < 32; i += 4)
+              if (dcol + i < p.dim)
+                *reinterpret_cast<float4*>(o + i) =
+                    make_float4(dsc * __uint_as_float(v[i]), dsc * __uint_as_float(v[i + 1]),
+                                dsc * __uint_as_float(v[i + 2]), dsc * __uint_as_float(v[i + 3]));
+          } else {
+            uint16_t* o = static_cast<uint16_t*>(pr.direct) + mrow * pr.ld_direct + dcol;
+            const bool bf = pr.direct_dtype == LATTE_BF16;
+#pragma unroll
+            for (int i = 0; i < 32; i += 8) {
+              uint32_t w[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float lo = dsc * __uint_as_float(v[i + 2 * e]);
+                const float hi = dsc * __uint_as_float(v[i + 2 * e + 1]);
+                if (bf) {
+                  __nv_bfloat162 b = __floats2bfloat162_rn(lo, hi);
+                  w[e] = *reinterpret_cast<uint32_t*>(&b);
+                } else {
+                  w[e] = pack2(lo, hi);
+                }
+              }
+              if (dcol + i < p.dim) *reinterpret_cast<uint4*>(o + i) = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+          }
+        }
+      } else {
+        for (int cc = 0; cc < cols_half; cc += 32) {
+          const int col = half * cols_half + cc;
+          uint32_t v[32];
+          tmem_ld_32x32(tmem_base + lane_base + col, v);
+          tmem_ld_wait();
+          if (m_ok) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              if (pr.d_off + col + i < p.dim)
+                red_add_v4(orow + pr.d_off + col + i, osc * __uint_as_float(v[i]), osc * __uint_as_float(v[i + 1]),
+                           osc * __uint_as_float(v[i + 2]), osc * __uint_as_float(v[i + 3]));
+            }
           }
         }
       }
@@ -1147,6 +1199,65 @@ pair_gemm_kernel(const __grid_constant__ CUtensorMap tma0, const __grid_constant
   tc_fence_before();
   cluster_sync_all();
   if (warp == 2) tmem_dealloc_pair(tmem_base, 512);
+}
+
+// Tiles that the stream-K schedule splits between clusters go through the fp32 accumulators:
+// kFixZero clears them before the GEMM, kFixCast turns them into gradients after it (whole tiles
+// were written by the GEMM epilogue itself).  One CTA per (problem, tile); a tile is split when its
+// first and last unit belong to different clusters of the contiguous schedule.
+constexpr int kFixZero = 0;
+constexpr int kFixCast = 1;
+struct FixupParams {
+  int nprob;
+  int64_t ubase[5];
+  int64_t total, ncl;
+  int m_tiles[4], k_chunks[4], d_off[4], ncols[4];
+  int64_t m_rows[4];
+  float* acc[4];
+  int64_t ld_acc;
+  void* out[4];
+  int out_dtype;
+  int64_t ld_out;
+  const float* out_scale;
+  int dim;
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(256) gemm_fixup_kernel(const FixupParams p) {
+  int pi = 0, t = blockIdx.x;
+  while (pi < p.nprob && t >= p.m_tiles[pi]) { t -= p.m_tiles[pi]; ++pi; }
+  if (pi >= p.nprob || p.out[pi] == nullptr) return;
+  const int64_t u_first = p.ubase[pi] + (int64_t)t * p.k_chunks[pi];
+  const int64_t u_last = u_first + p.k_chunks[pi] - 1;
+  if (cluster_of_tile(u_first, p.total, p.ncl) == cluster_of_tile(u_last, p.total, p.ncl)) return;
+  const int c0 = p.d_off[pi];
+  const int c1 = min(p.dim, c0 + p.ncols[pi]);
+  const int per_row = (c1 - c0) / 4;
+  const int64_t r0 = (int64_t)t * 256;
+  const int rows = (int)min((int64_t)256, p.m_rows[pi] - r0);
+  const float cs = MODE == kFixCast ? __ldg(p.out_scale) : 0.f;
+  for (int idx = threadIdx.x; idx < rows * per_row; idx += 256) {
+    const int64_t r = r0 + idx / per_row;
+    const int c = c0 + (idx % per_row) * 4;
+    float4* a = reinterpret_cast<float4*>(p.acc[pi] + r * p.ld_acc + c);
+    if (MODE == kFixZero) {
+      *a = make_float4(0.f, 0.f, 0.f, 0.f);
+    } else {
+      const float4 v = *a;
+      const float o[4] = {v.x * cs, v.y * cs, v.z * cs, v.w * cs};
+      if (p.out_dtype == LATTE_F32) {
+        *reinterpret_cast<float4*>(static_cast<float*>(p.out[pi]) + r * p.ld_out + c) =
+            make_float4(o[0], o[1], o[2], o[3]);
+      } else if (p.out_dtype == LATTE_BF16) {
+        __nv_bfloat162 lo = __floats2bfloat162_rn(o[0], o[1]), hi = __floats2bfloat162_rn(o[2], o[3]);
+        *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(p.out[pi]) + r * p.ld_out + c) =
+            make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+      } else {
+        *reinterpret_cast<uint2*>(static_cast<__half*>(p.out[pi]) + r * p.ld_out + c) =
+            make_uint2(pack2(o[0], o[1]), pack2(o[2], o[3]));
+      }
+    }
+  }
 }
 
 // out[i, d] = coef * s * 2^-13 * acc[i, d]   (coef = grad_loss * grad_mult / (2 n_loc))
@@ -1290,6 +1401,7 @@ int clip_pair_fwd_sweep(const PairFwdArgs& a, cudaStream_t stream) {
   p.logit_scale = a.logit_scale;
   p.part_max = a.part_max; p.part_sum = a.part_sum; p.diag = a.diag;
   p.col_part = a.col_part; p.col_ref = a.col_ref; p.ld_colpart = f.ld_colpart;
+  p.zero2 = a.zero2;
   p.kch = (int)((a.dim + kBK - 1) / kBK);
   p.tail_chunks = p.kch > kTmemChunks ? p.kch - kTmemChunks : 0;
   p.cps = p.tail_chunks ? 2 : kChunksPerStage;
@@ -1391,29 +1503,26 @@ int clip_pair_sig_sweep(const PairSigArgs& a, cudaStream_t stream) {
   return LATTE_OK;
 }
 
-int clip_pair_gemm(const PairGemmArgs& a, cudaStream_t stream) {
+namespace {
+// Problem list of one gradient-GEMM launch (shared by the GEMM and the fix-up kernels): one
+// problem per (product, feature slab of <= 512 accumulator columns).
+int build_gemm_problems(const PairGemmArgs& a, GemmParams& p, int64_t& total, int& ncl) {
   const PairGeom geo = clip_pair_geom(a.n_loc, a.n_all);
-  const int64_t g_rows = (int64_t)geo.row_blocks * 2 * geo.ncb * 128;
-  CUtensorMap tma0, tma1, tmb0, tmb1;
-  int rc = make_map16(&tma0, a.g, LATTE_F16, g_rows, 64, 64, 128);
-  if (rc) return rc;
-  rc = make_map16(&tma1, a.g, LATTE_F16, g_rows, 64, 64, 64);
-  if (rc) return rc;
-  rc = make_map16(&tmb0, a.y16, LATTE_F16, a.n_all, a.dim, a.ldy16, 64);
-  if (rc) return rc;
-  rc = make_map16(&tmb1, a.x16 ? a.x16 : a.y16, LATTE_F16, a.x16 ? a.n_loc : a.n_all, a.dim,
-                  a.x16 ? a.ldx16 : a.ldy16, 64);
-  if (rc) return rc;
-  GemmParams p = {};
+  p = GemmParams{};
   p.ncb = geo.ncb;
   p.dim = (int)a.dim;
-  // feature slabs of <= 512 accumulator columns (units of 128: 64 per CTA)
   const int units128 = (int)((a.dim + 127) / 128);
   const int nslab = (units128 + 3) / 4;
   const int nproducts = a.x16 ? 2 : 1;
   if (a.dy_peers && a.n_peers > 8) return LATTE_ERR_UNSUPPORTED;
+  // the B operand (features) may be bf16 while A (G) is fp16: kind::f16 takes the two formats
+  // independently
+  const uint32_t bfmt = a.feat_dtype == LATTE_BF16 ? 1u : 0u;
+  // direct stores need 16-byte vectors on the output rows
+  const bool direct_ok = a.out_scale != nullptr && (a.ld_out % 8) == 0;
+  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   p.nprob = 0;
-  int64_t total = 0;
+  total = 0;
   for (int prod = 0; prod < nproducts; ++prod) {
     int done = 0;
     for (int sl = 0; sl < nslab; ++sl) {
@@ -1425,11 +1534,13 @@ int clip_pair_gemm(const PairGemmArgs& a, cudaStream_t stream) {
       done += nh;
       for (int g = 0; g < 2; ++g) {
         const int cnt = nh - 2 * g >= 2 ? 2 : (nh - 2 * g == 1 ? 1 : 0);
-        q.idesc[g] = cnt ? make_idesc_f16(256, 2 * cnt * 64, 0u, prod, 1) : 0u;
+        q.idesc[g] = cnt ? make_idesc_ab(256, 2 * cnt * 64, 0u, bfmt, prod, 1) : 0u;
       }
       q.scale = nullptr;
       q.npeers = 0;
       q.rows_per_peer = 1;
+      q.direct = nullptr; q.direct_dtype = a.out_dtype; q.ld_direct = a.ld_out;
+      q.direct_scale = a.out_scale;
       for (int w = 0; w < 8; ++w) q.peers[w] = nullptr;
       if (prod == 0) {
         // dX = G . Y : rows of this rank, contraction over all columns
@@ -1439,6 +1550,7 @@ int clip_pair_gemm(const PairGemmArgs& a, cudaStream_t stream) {
         q.m_rows = a.n_loc;
         q.out = a.dx32;
         q.ld_out = a.ld32;
+        if (direct_ok && a.dx_out && al16(a.dx_out)) q.direct = a.dx_out;
       } else {
         // dY = G^T . X : rows = columns of G, contraction over the rows of G
         q.mode = 1;
@@ -1452,18 +1564,85 @@ int clip_pair_gemm(const PairGemmArgs& a, cudaStream_t stream) {
           q.npeers = a.n_peers;
           q.rows_per_peer = a.n_all / a.n_peers;
           for (int w = 0; w < a.n_peers; ++w) q.peers[w] = a.dy_peers[w];
+        } else if (direct_ok && a.dy_out && al16(a.dy_out) && !a.dy_scale) {
+          q.direct = a.dy_out;
         }
       }
       total += (int64_t)q.m_tiles * q.k_chunks;
     }
   }
-  int ncl = device_sm_count() / 2;
+  ncl = device_sm_count() / 2;
   if (total < ncl) ncl = (int)total;
+  return LATTE_OK;
+}
+}  // namespace
+
+int clip_pair_gemm(const PairGemmArgs& a, cudaStream_t stream) {
+  const PairGeom geo = clip_pair_geom(a.n_loc, a.n_all);
+  const int64_t g_rows = (int64_t)geo.row_blocks * 2 * geo.ncb * 128;
+  CUtensorMap tma0, tma1, tmb0, tmb1;
+  int rc = make_map16(&tma0, a.g, LATTE_F16, g_rows, 64, 64, 128);
+  if (rc) return rc;
+  rc = make_map16(&tma1, a.g, LATTE_F16, g_rows, 64, 64, 64);
+  if (rc) return rc;
+  rc = make_map16(&tmb0, a.y16, a.feat_dtype, a.n_all, a.dim, a.ldy16, 64);
+  if (rc) return rc;
+  rc = make_map16(&tmb1, a.x16 ? a.x16 : a.y16, a.feat_dtype, a.x16 ? a.n_loc : a.n_all, a.dim,
+                  a.x16 ? a.ldx16 : a.ldy16, 64);
+  if (rc) return rc;
+  GemmParams p;
+  int64_t total;
+  int ncl;
+  rc = build_gemm_problems(a, p, total, ncl);
+  if (rc) return rc;
   LATTE_CUDA_OK(cudaFuncSetAttribute(pair_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      kGemmSmem));
   pair_gemm_kernel<<<2 * ncl, kThreads, kGemmSmem, stream>>>(tma0, tma1, tmb0, tmb1, p);
   LATTE_LAUNCH_OK();
   return LATTE_OK;
+}
+
+// cast = 0: clear the fp32 accumulators of the tiles the GEMM's schedule splits (before the GEMM);
+// cast = 1: turn those tiles into gradients (after it).  No-op for problems without direct output.
+int clip_pair_gemm_fixup(const PairGemmArgs& a, int cast, cudaStream_t stream) {
+  GemmParams g;
+  int64_t total;
+  int ncl;
+  int rc = build_gemm_problems(a, g, total, ncl);
+  if (rc) return rc;
+  FixupParams f = {};
+  f.nprob = g.nprob;
+  f.total = total; f.ncl = ncl;
+  f.ld_acc = a.ld32; f.out_dtype = a.out_dtype; f.ld_out = a.ld_out; f.out_scale = a.out_scale;
+  f.dim = (int)a.dim;
+  int tiles = 0;
+  bool any = false;
+  f.ubase[0] = 0;
+  for (int i = 0; i < g.nprob; ++i) {
+    const GemmProblem& q = g.prob[i];
+    f.m_tiles[i] = q.m_tiles; f.k_chunks[i] = q.k_chunks; f.d_off[i] = q.d_off;
+    f.ncols[i] = q.nhalf * 128; f.m_rows[i] = q.m_rows; f.acc[i] = q.out; f.out[i] = q.direct;
+    f.ubase[i + 1] = f.ubase[i] + (int64_t)q.m_tiles * q.k_chunks;
+    if (q.direct && q.ld_out != a.ld32) return LATTE_ERR_BAD_ARG;
+    any = any || q.direct != nullptr;
+    tiles += q.m_tiles;
+  }
+  if (!any || tiles == 0) return LATTE_OK;
+  if (cast) gemm_fixup_kernel<kFixCast><<<tiles, 256, 0, stream>>>(f);
+  else gemm_fixup_kernel<kFixZero><<<tiles, 256, 0, stream>>>(f);
+  LATTE_LAUNCH_OK();
+  return LATTE_OK;
+}
+
+// true when clip_pair_gemm writes this product's whole tiles itself (fix-up kernels handle the rest)
+bool clip_pair_gemm_direct(const PairGemmArgs& a, int product) {
+  GemmParams g;
+  int64_t total;
+  int ncl;
+  if (build_gemm_problems(a, g, total, ncl)) return false;
+  for (int i = 0; i < g.nprob; ++i)
+    if (g.prob[i].product == product && g.prob[i].direct) return true;
+  return false;
 }
 
 int clip_pair_scale_cast(const float* acc0, const float* acc1, int64_t ld_acc, void* out0, void* out1,

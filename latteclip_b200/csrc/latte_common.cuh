@@ -132,6 +132,15 @@ struct PairGemmArgs {
   const float* dy_scale;            // nullable device scalar multiplied into dy32's partials
   float* const* dy_peers;           // nullable HOST array: per-rank accumulators [n_all / n_peers, ld_dy32]
   int n_peers;                      //   (peer-mapped); rows of dy go to their owner rank instead of dy32
+  int feat_dtype;                   // LATTE_F16 or LATTE_BF16: element type of y16 / x16 (G itself is fp16)
+  // Direct outputs (nullable): tiles owned by one cluster are written as out_scale * acc in out_dtype
+  // straight from the GEMM epilogue; dx32 / dy32 then only serve the tiles split between clusters
+  // (clip_pair_gemm_fixup before and after the GEMM).  dy_out is ignored with dy_scale / dy_peers.
+  void* dx_out;
+  void* dy_out;
+  int out_dtype;
+  int64_t ld_out;
+  const float* out_scale;
 };
 // Forward on the same sweep: rows dealt to clusters as contiguous tile ranges; a row block
 // split over several clusters gets one partial slot per cluster.
@@ -149,11 +158,12 @@ struct PairFwdArgs {
   int64_t n_loc, n_all, dim;
   int64_t label_offset;
   const float* logit_scale;
-  float* part_max;            // [4 * slots, n_loc], pre-filled with 0xFF bytes (= empty)
+  float* part_max;            // [4 * slots, n_loc]; which slots are written follows from the schedule
   float* part_sum;
   float* diag;                // [n_loc]
   float* col_part;            // [2 * row_blocks, ld_colpart] or NULL (rows only)
   float* col_ref;             // [2 * row_blocks, 4 * col_tiles]
+  int* zero2;                 // nullable: two ints the sweep clears (fallback flag, loss counter)
 };
 PairFwdGeom clip_pair_fwd_geom(int64_t n_loc, int64_t n_all);
 int clip_pair_fwd_sweep(const PairFwdArgs& a, cudaStream_t stream);
@@ -167,6 +177,8 @@ PairGeom clip_pair_geom(int64_t n_loc, int64_t n_all);
 int clip_pair_ds_count();
 int clip_pair_sweep(const PairSweepArgs& a, cudaStream_t stream);
 int clip_pair_gemm(const PairGemmArgs& a, cudaStream_t stream);
+int clip_pair_gemm_fixup(const PairGemmArgs& a, int cast, cudaStream_t stream);
+bool clip_pair_gemm_direct(const PairGemmArgs& a, int product);
 int clip_pair_scale_cast(const float* acc0, const float* acc1, int64_t ld_acc, void* out0, void* out1,
                          int out_dtype, int64_t ld_out, int64_t rows, int64_t dim,
                          const float* out_scale, cudaStream_t stream);
@@ -177,5 +189,6 @@ int clip_bwd_rows_simt(const ClipBwdArgs& a, cudaStream_t stream);
 int clip_simt_ds_count(int64_t n_loc);
 
 int device_sm_count();
+bool want_fp16_copies();
 
 }  // namespace latte

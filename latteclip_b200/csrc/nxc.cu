@@ -141,25 +141,35 @@ namespace latte {
 int nxc_tc_run(const void* x, int64_t ldx, int x_dtype, const int64_t* row_index, int64_t n,
                int64_t dim, const float* protos, int64_t ldp, int64_t num_classes, float scale,
                int64_t* argmax_out, float* margin_out, float* top1_out, int k, int64_t* topk_idx,
-               float* topk_val, cudaStream_t st);
+               float* topk_val, void* workspace, size_t workspace_bytes, cudaStream_t st);
+size_t nxc_tc_workspace_bytes(int x_dtype, bool gathered, int64_t n, int64_t dim, int64_t num_classes);
 constexpr int64_t kTcMinRows = 128;      // below this the launch of the plane split dominates
 }  // namespace latte
 
 using namespace latte;
 
+extern "C" int latte_nxc_workspace_bytes(int x_dtype, int gathered, int64_t n, int64_t dim,
+                                         int64_t num_classes, size_t* bytes) {
+  LATTE_CHECK_ARG(bytes && n >= 0 && dim > 0 && num_classes > 0);
+  LATTE_CHECK_ARG(x_dtype >= LATTE_F32 && x_dtype <= LATTE_F16);
+  *bytes = n >= kTcMinRows ? nxc_tc_workspace_bytes(x_dtype, gathered != 0, n, dim, num_classes) : 0;
+  return LATTE_OK;
+}
+
 extern "C" int latte_nxc_argmax_margin(const void* x, int64_t ldx_, int x_dtype,
                                        const int64_t* row_index, int64_t n, int64_t dim,
                                        const float* protos, int64_t ldp, int64_t num_classes,
                                        float scale, int64_t* argmax_out, float* margin_out,
-                                       float* top1_out, void* stream) {
+                                       float* top1_out, void* workspace, size_t workspace_bytes,
+                                       void* stream) {
   LATTE_CHECK_ARG(x && protos && n >= 0 && dim > 0 && num_classes > 0);
   LATTE_CHECK_ARG(x_dtype >= LATTE_F32 && x_dtype <= LATTE_F16);
   LATTE_CHECK_ARG(ldx_ >= dim && ldp >= dim);
   if (n == 0) return LATTE_OK;
   if (n >= kTcMinRows) {
     const int rc = nxc_tc_run(x, ldx_, x_dtype, row_index, n, dim, protos, ldp, num_classes, scale,
-                              argmax_out, margin_out, top1_out, 0, nullptr, nullptr,
-                              static_cast<cudaStream_t>(stream));
+                              argmax_out, margin_out, top1_out, 0, nullptr, nullptr, workspace,
+                              workspace_bytes, static_cast<cudaStream_t>(stream));
     if (rc != LATTE_ERR_UNSUPPORTED) return rc;
   }
   NxcArgs a{x, ldx_, x_dtype, row_index, n, dim, protos, ldp, num_classes, scale,
@@ -172,7 +182,8 @@ extern "C" int latte_nxc_argmax_margin(const void* x, int64_t ldx_, int x_dtype,
 
 extern "C" int latte_nxc_topk(const void* x, int64_t ldx_, int x_dtype, int64_t n, int64_t dim,
                               const float* protos, int64_t ldp, int64_t num_classes, float scale,
-                              int k, int64_t* topk_idx, float* topk_val, void* stream) {
+                              int k, int64_t* topk_idx, float* topk_val, void* workspace,
+                              size_t workspace_bytes, void* stream) {
   LATTE_CHECK_ARG(x && protos && topk_idx && topk_val && n >= 0 && dim > 0 && num_classes > 0);
   LATTE_CHECK_ARG(x_dtype >= LATTE_F32 && x_dtype <= LATTE_F16);
   LATTE_CHECK_ARG(ldx_ >= dim && ldp >= dim);
@@ -180,8 +191,8 @@ extern "C" int latte_nxc_topk(const void* x, int64_t ldx_, int x_dtype, int64_t 
   if (n == 0) return LATTE_OK;
   if (n >= kTcMinRows) {
     const int rc = nxc_tc_run(x, ldx_, x_dtype, nullptr, n, dim, protos, ldp, num_classes, scale,
-                              nullptr, nullptr, nullptr, k, topk_idx, topk_val,
-                              static_cast<cudaStream_t>(stream));
+                              nullptr, nullptr, nullptr, k, topk_idx, topk_val, workspace,
+                              workspace_bytes, static_cast<cudaStream_t>(stream));
     if (rc != LATTE_ERR_UNSUPPORTED) return rc;
   }
   NxcArgs a{x, ldx_, x_dtype, nullptr, n, dim, protos, ldp, num_classes, scale,

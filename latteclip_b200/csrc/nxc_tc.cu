@@ -309,32 +309,49 @@ int nxc_make_map(CUtensorMap* map, const void* base, int64_t rows, int64_t cols,
 
 }  // namespace
 
+namespace {
+struct NxcWsLayout { size_t x_elems, x_al, p_elems, total; int64_t dim_pad; int x_planes; bool direct_x; };
+NxcWsLayout nxc_ws_layout(const void* x, int64_t ldx, int x_dtype, bool gathered, int64_t n, int64_t dim,
+                          int64_t num_classes) {
+  NxcWsLayout w;
+  w.dim_pad = (dim + kBK - 1) / kBK * kBK;
+  // x == NULL (size query): assume the planes of x have to be materialised unless bf16 rows are used as is
+  w.direct_x = x_dtype == LATTE_BF16 && !gathered && (ldx % 8) == 0 &&
+               (reinterpret_cast<uintptr_t>(x) & 15) == 0;
+  w.x_planes = x_dtype == LATTE_BF16 ? 1 : (x_dtype == LATTE_F16 ? 2 : 3);
+  w.x_elems = w.direct_x ? 0 : (size_t)w.x_planes * (size_t)n * (size_t)w.dim_pad;
+  w.p_elems = (size_t)3 * (size_t)num_classes * (size_t)w.dim_pad;
+  w.x_al = (w.x_elems + 127) / 128 * 128;
+  w.total = (w.x_al + w.p_elems) * sizeof(__nv_bfloat16);
+  return w;
+}
+}  // namespace
+
+// Scratch of one N x C call: bf16 planes of the prototypes and (unless bf16 rows are read in place)
+// of x.  Upper bound over pointer alignments of x.
+size_t nxc_tc_workspace_bytes(int x_dtype, bool gathered, int64_t n, int64_t dim, int64_t num_classes) {
+  // an unaligned bf16 x also needs its plane: query with direct_x = false
+  NxcWsLayout w = nxc_ws_layout(reinterpret_cast<const void*>(1), 1, x_dtype, gathered, n, dim, num_classes);
+  return w.total + 256;
+}
+
 // Returns LATTE_ERR_UNSUPPORTED when the caller should use the SIMT kernel instead.
 int nxc_tc_run(const void* x, int64_t ldx, int x_dtype, const int64_t* row_index, int64_t n,
                int64_t dim, const float* protos, int64_t ldp, int64_t num_classes, float scale,
                int64_t* argmax_out, float* margin_out, float* top1_out, int k, int64_t* topk_idx,
-               float* topk_val, cudaStream_t st) {
+               float* topk_val, void* workspace, size_t workspace_bytes, cudaStream_t st) {
   // plane row offsets are 32-bit TMA coordinates
   if (3 * n >= (1ll << 31) || 3 * num_classes >= (1ll << 31)) return LATTE_ERR_UNSUPPORTED;
-  const int64_t dim_pad = (dim + kBK - 1) / kBK * kBK;
-  const bool direct_x = x_dtype == LATTE_BF16 && !row_index && (ldx % 8) == 0 &&
-                        (reinterpret_cast<uintptr_t>(x) & 15) == 0;
-  const int x_planes = x_dtype == LATTE_BF16 ? 1 : (x_dtype == LATTE_F16 ? 2 : 3);
-  const size_t x_elems = direct_x ? 0 : (size_t)x_planes * (size_t)n * (size_t)dim_pad;
-  const size_t p_elems = (size_t)3 * (size_t)num_classes * (size_t)dim_pad;
-  {
-    int dev = 0;
-    cudaMemPool_t pool;
-    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-      uint64_t keep = 1ull << 30;
-      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-    }
-  }
-  __nv_bfloat16* buf = nullptr;
-  const size_t x_al = (x_elems + 127) / 128 * 128;
-  LATTE_CUDA_OK(cudaMallocAsync(&buf, (x_al + p_elems) * sizeof(__nv_bfloat16), st));
+  const NxcWsLayout w = nxc_ws_layout(x, ldx, x_dtype, row_index != nullptr, n, dim, num_classes);
+  const int64_t dim_pad = w.dim_pad;
+  const bool direct_x = w.direct_x;
+  const int x_planes = w.x_planes;
+  if (!workspace) return LATTE_ERR_BAD_ARG;
+  const uintptr_t base = (reinterpret_cast<uintptr_t>(workspace) + 255) / 256 * 256;
+  if (base - reinterpret_cast<uintptr_t>(workspace) + w.total > workspace_bytes) return LATTE_ERR_WORKSPACE;
+  __nv_bfloat16* buf = reinterpret_cast<__nv_bfloat16*>(base);
   __nv_bfloat16* xp = buf;
-  __nv_bfloat16* pp = buf + x_al;
+  __nv_bfloat16* pp = buf + w.x_al;
   int rc = LATTE_OK;
   if (!direct_x) {
     const int64_t work = n * (dim_pad / 8);
@@ -373,7 +390,6 @@ int nxc_tc_run(const void* x, int64_t ldx, int x_dtype, const int64_t* row_index
     }
     if (!rc && cudaGetLastError() != cudaSuccess) rc = LATTE_ERR_CUDA;
   }
-  cudaFreeAsync(buf, st);
   return rc;
 }
 

@@ -377,27 +377,31 @@ __global__ void __launch_bounds__(128) seg_final_kernel(SegArgs a) {
 
 inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
-// Runs the five steps on `stream`; scratch comes from the stream-ordered allocator.
-int segment_sums(SegArgs a, cudaStream_t st) {
-  const int64_t entries = 2 * a.batch;
-  a.slices = (int)((entries + kSegSlice - 1) / kSegSlice);
-  if (a.slices < 1) a.slices = 1;
-  a.max_pieces = (int)((entries + kSegPiece - 1) / kSegPiece) + a.num_classes;
-  const size_t n_hist = (size_t)a.slices * a.num_classes;
-  const size_t n_int = n_hist + 2 * ((size_t)a.num_classes + 1) + (size_t)entries + 8;
-  const size_t int_bytes = (n_int * sizeof(int) + 255) / 256 * 256;
-  const size_t part_bytes = (size_t)a.max_pieces * (size_t)a.dim * sizeof(float);
-  // keep freed scratch in the stream-ordered pool instead of returning it at every sync
-  {
-    int dev = 0;
-    cudaMemPool_t pool;
-    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-      uint64_t keep = 1ull << 30;
-      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-    }
-  }
-  char* buf = nullptr;
-  LATTE_CUDA_OK(cudaMallocAsync(&buf, int_bytes + part_bytes, st));
+struct SegWs { size_t n_hist, int_bytes, part_bytes; int slices, max_pieces; };
+SegWs seg_ws(int64_t batch, int64_t dim, int64_t num_classes) {
+  SegWs w;
+  const int64_t entries = 2 * batch;
+  w.slices = (int)((entries + kSegSlice - 1) / kSegSlice);
+  if (w.slices < 1) w.slices = 1;
+  w.max_pieces = (int)((entries + kSegPiece - 1) / kSegPiece) + (int)num_classes;
+  w.n_hist = (size_t)w.slices * (size_t)num_classes;
+  const size_t n_int = w.n_hist + 2 * ((size_t)num_classes + 1) + (size_t)entries + 8;
+  w.int_bytes = (n_int * sizeof(int) + 255) / 256 * 256;
+  w.part_bytes = (size_t)w.max_pieces * (size_t)dim * sizeof(float);
+  return w;
+}
+
+// Runs the five steps on `stream` in the caller's workspace (latte_seg_workspace_bytes).
+int segment_sums(SegArgs a, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  const SegWs w = seg_ws(a.batch, a.dim, a.num_classes);
+  a.slices = w.slices;
+  a.max_pieces = w.max_pieces;
+  const size_t n_hist = w.n_hist, int_bytes = w.int_bytes;
+  if (!workspace) return LATTE_ERR_BAD_ARG;
+  const uintptr_t base = (reinterpret_cast<uintptr_t>(workspace) + 255) / 256 * 256;
+  if (base - reinterpret_cast<uintptr_t>(workspace) + w.int_bytes + w.part_bytes > workspace_bytes)
+    return LATTE_ERR_WORKSPACE;
+  char* buf = reinterpret_cast<char*>(base);
   int* ip = reinterpret_cast<int*>(buf);
   a.hist = ip; ip += n_hist;
   a.class_off = ip; ip += a.num_classes + 1;
@@ -415,7 +419,6 @@ int segment_sums(SegArgs a, cudaStream_t st) {
   seg_piece_kernel<<<a.max_pieces, 128, 0, st>>>(a);
   seg_final_kernel<<<a.num_classes, 128, 0, st>>>(a);
   if (cudaGetLastError() != cudaSuccess) rc = LATTE_ERR_CUDA;
-  cudaFreeAsync(buf, st);
   return rc;
 }
 
@@ -442,6 +445,14 @@ bank_finalize_kernel(const float* sums, int64_t ld_sums, const float* counts, fl
 }  // namespace latte
 
 using namespace latte;
+
+extern "C" int latte_seg_workspace_bytes(int64_t batch, int64_t dim, int64_t num_classes,
+                                         size_t* bytes) {
+  LATTE_CHECK_ARG(bytes && batch >= 0 && dim > 0 && num_classes > 0);
+  const SegWs w = seg_ws(batch, dim, num_classes);
+  *bytes = w.int_bytes + w.part_bytes + 256;
+  return LATTE_OK;
+}
 
 extern "C" int latte_normalize_rows(const float* in, int64_t ld_in, float* out, int64_t ld_out,
                                     int64_t rows, int64_t dim, void* stream) {
@@ -491,7 +502,8 @@ extern "C" int latte_mix_ema_bwd(const void* d_t_ft, const void* d_t_zs, int64_t
                                  float alpha, int label_axis, int dtype, int64_t batch,
                                  int64_t dim, int64_t num_classes, float* d_class_text,
                                  int64_t ld_dct, void* d_per_image, void* d_per_group,
-                                 int64_t ld_dp, float* d_bank, int64_t ld_dbank, void* stream) {
+                                 int64_t ld_dp, float* d_bank, int64_t ld_dbank, void* workspace,
+                                 size_t workspace_bytes, void* stream) {
   LATTE_CHECK_ARG(d_t_ft && d_t_zs && preds && zs && w_lbl && w_lbl_zs && w_img && w_grp);
   LATTE_CHECK_ARG(batch >= 0 && dim > 0 && num_classes > 0);
   LATTE_CHECK_ARG(dtype >= LATTE_F32 && dtype <= LATTE_F16);
@@ -513,7 +525,7 @@ extern "C" int latte_mix_ema_bwd(const void* d_t_ft, const void* d_t_zs, int64_t
     s.w_lbl = w_lbl; s.w_lbl_zs = w_lbl_zs; s.w_img = w_img; s.w_grp = w_grp;
     s.alpha = alpha; s.label_axis = label_axis;
     s.out = d_class_text; s.ld_out = ld_dct; s.accumulate = 1; s.counts = nullptr; s.post_scale = 1.f;
-    const int rc = segment_sums(s, st);
+    const int rc = segment_sums(s, workspace, workspace_bytes, st);
     if (rc) return rc;
   }
   if (d_bank) {
@@ -524,7 +536,7 @@ extern "C" int latte_mix_ema_bwd(const void* d_t_ft, const void* d_t_zs, int64_t
     s.label_axis = LATTE_LABEL_AXIS_ROW;
     s.out = d_bank; s.ld_out = ld_dbank; s.accumulate = 1; s.counts = nullptr;
     s.post_scale = 1.f - alpha;
-    const int rc = segment_sums(s, st);
+    const int rc = segment_sums(s, workspace, workspace_bytes, st);
     if (rc) return rc;
   }
   return LATTE_OK;
@@ -533,7 +545,8 @@ extern "C" int latte_mix_ema_bwd(const void* d_t_ft, const void* d_t_zs, int64_t
 extern "C" int latte_bank_accumulate(const void* t_ft, const void* t_zs, int64_t ld_t, int dtype,
                                      const int64_t* preds, const int64_t* zs, int64_t batch,
                                      int64_t dim, int64_t num_classes, float* sums,
-                                     int64_t ld_sums, float* counts, void* stream) {
+                                     int64_t ld_sums, float* counts, void* workspace,
+                                     size_t workspace_bytes, void* stream) {
   LATTE_CHECK_ARG(t_ft && t_zs && preds && zs && sums && counts);
   LATTE_CHECK_ARG(batch >= 0 && dim > 0 && num_classes > 0 && ld_t >= dim && ld_sums >= dim);
   LATTE_CHECK_ARG(dtype >= LATTE_F32 && dtype <= LATTE_F16);
@@ -543,7 +556,7 @@ extern "C" int latte_bank_accumulate(const void* t_ft, const void* t_zs, int64_t
   s.preds = preds; s.zs = zs; s.batch = batch; s.dim = dim; s.num_classes = (int)num_classes;
   s.label_axis = LATTE_LABEL_AXIS_ROW;
   s.out = sums; s.ld_out = ld_sums; s.accumulate = 0; s.counts = counts; s.post_scale = 1.f;
-  return segment_sums(s, static_cast<cudaStream_t>(stream));
+  return segment_sums(s, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int latte_bank_finalize(const float* sums, int64_t ld_sums, const float* counts,

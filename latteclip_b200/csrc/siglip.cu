@@ -179,16 +179,16 @@ extern "C" int latte_siglip_bwd(const void* img_loc, int64_t ld_img, const void*
   float* acc_i = ws + w.off_acc0;
   float* acc_t = ws + w.off_acc1;
   LATTE_CUDA_OK(cudaMemsetAsync(ws + w.off_part0, 0, 2 * w.parts * sizeof(float), st));
-  LATTE_CUDA_OK(cudaMemsetAsync(acc_i, 0, (size_t)n_loc * w.ld32 * sizeof(float), st));
-  if (own) LATTE_CUDA_OK(cudaMemsetAsync(acc_t, 0, (size_t)n_all * w.ld32 * sizeof(float), st));
   if (d_txt_partial)
     LATTE_CUDA_OK(cudaMemsetAsync(d_txt_partial, 0, (size_t)n_all * (size_t)dim * sizeof(float), st));
   sig_scale_kernel<<<1, 1, 0, st>>>(grad_loss, logit_scale, n_loc, out_scale);
   LATTE_LAUNCH_OK();
-  // fp16 operands of the gradient GEMMs (bf16 x fp16 is not a legal MMA pair)
+  // operands of the gradient GEMMs: the features as they are (A = fp16 G, B = bf16 or fp16
+  // features), or fp16 copies with LATTE_B200_FP16_COPIES=1
   const void* x16 = img_loc; int64_t ldx16 = ld_img;
   const void* y16 = txt_all; int64_t ldy16 = ld_txt;
-  if (dtype == LATTE_BF16) {
+  const bool copies16 = dtype == LATTE_BF16 && want_fp16_copies();
+  if (copies16) {
     __half* xh = reinterpret_cast<__half*>(ws + w.off_x16);
     __half* yh = reinterpret_cast<__half*>(ws + w.off_y16);
     const int64_t per_row = dim / 8;
@@ -211,6 +211,9 @@ extern "C" int latte_siglip_bwd(const void* img_loc, int64_t ld_img, const void*
   PairGemmArgs ga = {};
   ga.g = ws + w.off_g; ga.n_loc = n_loc; ga.n_all = n_all; ga.dim = dim; ga.ld32 = (int64_t)w.ld32;
   ga.y16 = y16; ga.ldy16 = ldy16; ga.x16 = x16; ga.ldx16 = ldx16;
+  ga.feat_dtype = copies16 ? LATTE_F16 : dtype;
+  ga.out_dtype = grad_dtype; ga.ld_out = ld_grad; ga.out_scale = out_scale;
+  ga.dx_out = d_img; ga.dy_out = own ? d_txt : nullptr;
   ga.dx32 = acc_i;
   ga.dy32 = acc_t; ga.ld_dy32 = (int64_t)w.ld32; ga.dy_scale = nullptr;
   ga.dy_peers = nullptr; ga.n_peers = 0;
@@ -221,11 +224,27 @@ extern "C" int latte_siglip_bwd(const void* img_loc, int64_t ld_img, const void*
     ga.dy_peers = reinterpret_cast<float* const*>(d_txt_peers);
     ga.n_peers = n_peers;
   }
+  const bool direct_i = clip_pair_gemm_direct(ga, 0);
+  const bool direct_t = own && clip_pair_gemm_direct(ga, 1);
+  if (!direct_i) LATTE_CUDA_OK(cudaMemsetAsync(acc_i, 0, (size_t)n_loc * w.ld32 * sizeof(float), st));
+  if (own && !direct_t)
+    LATTE_CUDA_OK(cudaMemsetAsync(acc_t, 0, (size_t)n_all * w.ld32 * sizeof(float), st));
+  rc = clip_pair_gemm_fixup(ga, 0, st);
+  if (rc) return rc;
   rc = clip_pair_gemm(ga, st);
   if (rc) return rc;
-  rc = clip_pair_scale_cast(acc_i, own ? acc_t : nullptr, (int64_t)w.ld32, d_img, d_txt, grad_dtype,
-                            ld_grad, n_loc, dim, out_scale, st);
+  rc = clip_pair_gemm_fixup(ga, 1, st);
   if (rc) return rc;
+  if (!direct_i) {
+    rc = clip_pair_scale_cast(acc_i, nullptr, (int64_t)w.ld32, d_img, nullptr, grad_dtype, ld_grad,
+                              n_loc, dim, out_scale, st);
+    if (rc) return rc;
+  }
+  if (own && !direct_t) {
+    rc = clip_pair_scale_cast(acc_t, nullptr, (int64_t)w.ld32, d_txt, nullptr, grad_dtype, ld_grad,
+                              n_all, dim, out_scale, st);
+    if (rc) return rc;
+  }
   sig_scalar_grads_kernel<<<1, 256, 0, st>>>(ws + w.off_part0, ws + w.off_part1, parts, grad_loss,
                                              n_loc, d_scale, d_bias);
   LATTE_LAUNCH_OK();

@@ -16,6 +16,23 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 
 
+def _sigma(d):
+    """Pair noise that leaves the loss at a few tenths (a nearly converged batch would make the
+    relative loss / d logit_scale checks vacuous)."""
+    return 5.0 if d <= 512 else 6.0
+
+
+def _worlds():
+    """Every world size of {2, 4, 8} that fits the visible GPUs (LATTE_TEST_WORLDS=8 or 2,8
+    restricts the list, e.g. to keep an 8-GPU lease short)."""
+    fit = [w for w in (2, 4, 8) if w <= torch.cuda.device_count()]
+    env = os.environ.get("LATTE_TEST_WORLDS")
+    if env:
+        want = {int(x) for x in env.split(",") if x.strip()}
+        fit = [w for w in fit if w in want]
+    return fit
+
+
 def _worker(rank, world, port, n, d, dtype_name, p2p, ret):
     sys.path.insert(0, ROOT)
     os.environ["LATTE_B200_NO_P2P"] = "0" if p2p else "1"
@@ -31,7 +48,7 @@ def _worker(rank, world, port, n, d, dtype_name, p2p, ret):
     dtype = getattr(torch, dtype_name)
     g = torch.Generator().manual_seed(123)
     i_all = F.normalize(torch.randn(n * world, d, generator=g), dim=1)
-    sigma = 3.0 if d <= 512 else 6.0      # keep the loss away from full convergence
+    sigma = _sigma(d)
     t_all = F.normalize(i_all + sigma * torch.randn(n * world, d, generator=g) / math.sqrt(d), dim=1)
     out = {}
     for local_loss, gwg in ((True, True), (True, False), (False, True), (False, False)):
@@ -65,28 +82,29 @@ def _worker(rank, world, port, n, d, dtype_name, p2p, ret):
     dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("world", [2, 4, 8])
 @pytest.mark.parametrize("dtype_name,n,d,p2p", [("bfloat16", 512, 512, True), ("bfloat16", 512, 512, False),
                                                  ("bfloat16", 300, 768, True), ("float32", 96, 64, True),
                                                  ("bfloat16", 512, 512, "two_bwd_sweeps")])
-def test_nccl_cliploss_matches_oracle(dtype_name, n, d, p2p):
+def test_nccl_cliploss_matches_oracle(dtype_name, n, d, p2p, world):
     """p2p=True: feature gather and text-gradient reduce-scatter through peer-mapped buffers
     (latte_push_shards, fused GEMM + reduce-scatter); p2p=False: the same one-sweep flow over
     NCCL all-gather / reduce-scatter; "two_bwd_sweeps": P2P gather and one forward sweep, but the
     backward sweeps rows and columns and exchanges nothing (the default from 8 ranks on).
     fp32 features take the two-sweep flow throughout."""
-    world = min(torch.cuda.device_count(), 4)
-    if world < 2:
-        pytest.skip("needs >= 2 GPUs")
+    if world not in _worlds():
+        pytest.skip(f"needs {world} GPUs (visible: {torch.cuda.device_count()}, "
+                    f"LATTE_TEST_WORLDS={os.environ.get('LATTE_TEST_WORLDS', '')})")
     import oracle
     from oracle.clip_loss import clip_loss_all_ranks
     mgr = mp.Manager()
     ret = mgr.dict()
-    mp.spawn(_worker, args=(world, 29801 + n % 7 + 10 * int(p2p is True) + 20 * int(p2p == 'two_bwd_sweeps') + d % 5, n, d, dtype_name, p2p, ret),
+    mp.spawn(_worker, args=(world, 29801 + n % 7 + 10 * int(p2p is True) + 20 * int(p2p == 'two_bwd_sweeps') + d % 5 + 40 * world, n, d, dtype_name, p2p, ret),
              nprocs=world, join=True)
     dtype = getattr(torch, dtype_name)
     g = torch.Generator().manual_seed(123)
     i_all = F.normalize(torch.randn(n * world, d, generator=g), dim=1)
-    sigma = 3.0 if d <= 512 else 6.0
+    sigma = _sigma(d)
     t_all = F.normalize(i_all + sigma * torch.randn(n * world, d, generator=g) / math.sqrt(d), dim=1)
     ir, tr = i_all.to(dtype).float(), t_all.to(dtype).float()
     ish = [ir[r * n:(r + 1) * n] for r in range(world)]
@@ -105,16 +123,17 @@ def test_nccl_cliploss_matches_oracle(dtype_name, n, d, p2p):
               (row[0][0], row[0][1], *row[1:]))
     one_sweep = dtype_name == "bfloat16"     # 16-bit, dim <= 512: one logit sweep per rank
     for key, r, loss, lref, e_i, e_t, _, dsv, dsr in report:
-        assert abs(loss - lref) <= 1e-5 * abs(lref) + 2e-5, (key, r)
+        assert lref > 0.05, "test data must stay away from convergence"
+        assert abs(loss - lref) <= 5e-5 * abs(lref), (key, r, loss, lref)
         assert e_i < gtol and e_t < gtol, (key, r, e_i, e_t)
         if one_sweep and key == (True, True):
             # d loss / d s covers rows-of-this-rank x all columns: the sum over ranks (what
             # DDP's all-reduce of the parameter gradient sees) is the reference's
             got = sum(x[7] for x in report if x[0] == key)
             ref_sum = sum(x[8] for x in report if x[0] == key)
-            assert abs(got - ref_sum) <= 2e-3 * abs(ref_sum) + 1e-6, (key, r)
+            assert abs(got - ref_sum) <= 2e-3 * abs(ref_sum), (key, r, got, ref_sum)
         else:
-            assert abs(dsv - dsr) <= 2e-3 * abs(dsr) + 1e-6, (key, r)
+            assert abs(dsv - dsr) <= 2e-3 * abs(dsr), (key, r, dsv, dsr)
     if dtype_name != "float32":
         from oracle.siglip import siglip_all_ranks
         lo, di, dt, ds, db = siglip_all_ranks(ish, tsh, 20.0, -6.0)
