@@ -58,6 +58,52 @@ const char* latte_status_string(int status);
 /* Fills SM count and compute capability of the current device. */
 int latte_device_info(int* sm_count, int* cc_major, int* cc_minor);
 
+/*
+ * ---- multi-rank exchange over NVLink peer memory (one process per GPU) ----------------------
+ * The reference's collectives on this path are gather_features' two all-gathers (loss.py:49-50 /
+ * :54-55) and, in backward, the reduce-scatter of torch.distributed.nn.all_gather.  Here every
+ * rank owns one symmetric allocation per slot that all ranks map (torch symmetric memory); the
+ * kernels of this library store into / add into the peers' buffers directly and synchronise with
+ * generation-numbered flags (int32, system-scope release / acquire) -- no host-side barrier, no
+ * collective call.  A slot carries generation `gen` (1, 2, ... identical on all ranks):
+ *   gather[w]   rank w's gathered-feature buffer [2][n_all, dim] (image matrix, then text matrix)
+ *   payload[w]  rank w's forward payload block: [world][payload_stride] floats (first exchange)
+ *               followed by [world][2 n_all] floats (second, exact round)
+ *   acc[w]      rank w's fp32 text-gradient accumulator [n_loc, dim]; zero when a generation starts
+ *   flags[w]    rank w's flag block, LATTE_COMM_FLAG_INTS int32 (zero-initialised once):
+ *               landed_txt[8] | landed_img[8] | payload[8] | payload2[8] | done[8] | free[8] |
+ *               counters[8] (local); entry [src] = latest generation for which rank src has
+ *               finished that step towards THIS rank.
+ * Ordering rules the caller keeps: all ranks issue the same sequence of calls; a slot's generation
+ * g may start once generation g - 1 of the same slot was released by every rank (the push waits
+ * for free[*] >= g - 1 by itself).
+ */
+#define LATTE_COMM_MAX_RANKS 8
+#define LATTE_COMM_FLAG_INTS 64
+typedef struct latte_comm {
+  int32_t rank, world, gen, reserved;
+  void* gather[LATTE_COMM_MAX_RANKS];
+  float* payload[LATTE_COMM_MAX_RANKS];
+  float* acc[LATTE_COMM_MAX_RANKS];
+  int32_t* flags[LATTE_COMM_MAX_RANKS];
+  int64_t payload_stride;          /* floats per rank row of the first payload exchange */
+} latte_comm_t;
+
+/*
+ * The feature all-gather as ONE store kernel: waits until every peer released the slot's previous
+ * generation, writes this rank's text shard ([n_loc, dim], shard_bytes) -- and image shard, if not
+ * NULL -- into every rank's gather buffer (the text matrix starts tensor_stride_bytes after the
+ * image matrix) and publishes landed_txt / landed_img = gen on every rank.  The forward sweep
+ * starts reading a shard as soon as its flag shows up (latte_clip_fwd_rank), so no rank waits for
+ * the slowest pusher before it starts.  comm == NULL-flags variant for tests: pass flags[] = NULL
+ * to skip waits and signals.
+ */
+int latte_comm_push(const latte_comm_t* comm, const void* txt_shard, const void* img_shard,
+                    int64_t shard_bytes, int64_t tensor_stride_bytes, void* stream);
+
+/* Releases the slot's generation without a backward (forward-only call): free = gen on all ranks. */
+int latte_comm_release(const latte_comm_t* comm, void* stream);
+
 /* ---- ClipLoss: open_clip/loss.py ------------------------------------------------------ */
 
 /* Bytes of scratch latte_clip_fwd / latte_clip_bwd need for these sizes. */
@@ -96,6 +142,10 @@ int latte_clip_fwd(const void* img_loc, int64_t ld_img_loc,
                                                     (max - label logit) + log(sum) so they keep
                                                     full relative accuracy near convergence  */
                    float* loss,                  /* device scalar out                     */
+                   float* stats,                 /* nullable [4] out: min / max of all LSE values
+                                                    and the largest nll -- what latte_clip_bwd
+                                                    needs to scale G (valid as `lse_stats` there
+                                                    when n_loc == n_all)                      */
                    void* workspace, size_t workspace_bytes, void* stream);
 
 /*
@@ -128,6 +178,32 @@ int latte_clip_fwd_cols(const float* gathered /* [world, stride]: per rank col_m
                         float* row_lse_all, float* row_nll_all,      /* [n_all] unpacked     */
                         float* col_lse_all, float* col_nll_all,      /* [n_all] merged       */
                         float* loss,
+                        float* stats,                 /* nullable [4] out, as latte_clip_fwd (here
+                                                         they cover all n_all rows and columns)  */
+                        void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * The same multi-rank forward with every exchange done by the kernels themselves over peer memory
+ * (after latte_comm_push of this generation): the sweep reads the gathered text matrix
+ * comm->gather[rank] + tensor_stride as the shards land; the per-rank payload is stored into every
+ * peer's payload block and merged as soon as all blocks arrived.  If (after the merge, identically
+ * on every rank) a column's partial sums may have lost flushed terms, every rank recomputes its own
+ * column partials exactly (all texts x own images -- no gathered images needed) and a second
+ * exchange replaces them; without that flag the three kernels of the second round return at once.
+ * Outputs as latte_clip_fwd_cols.  `phases` (bit mask, 7 = everything) exists so that a test can
+ * drive all ranks from ONE process on one GPU, phase by phase: 1 = sweep + finalize + payload
+ * store, 2 = merge (+ the gated exact recompute and its store), 4 = final merge + loss.
+ */
+int latte_clip_fwd_rank_workspace_bytes(int64_t n_loc, int64_t n_all, int64_t dim, int dtype,
+                                        size_t* bytes);
+int latte_clip_fwd_rank(const latte_comm_t* comm,
+                        const void* img_loc, int64_t ld_img_loc,
+                        const void* txt_all, int64_t ld_txt_all,
+                        int dtype, int64_t n_loc, int64_t n_all, int64_t dim,
+                        int64_t label_offset, const float* logit_scale,
+                        float* row_lse_all, float* row_nll_all,
+                        float* col_lse_all, float* col_nll_all,
+                        float* loss, float* stats, int phases,
                         void* workspace, size_t workspace_bytes, void* stream);
 
 /*
@@ -160,36 +236,28 @@ int latte_clip_bwd(const void* img_loc, int64_t ld_img_loc,
                    const float* logit_scale,
                    const float* row_lse_all, const float* col_lse_all,   /* [n_all]  */
                    const float* row_nll_all, const float* col_nll_all,   /* [n_all], nullable */
+                   const float* lse_stats,       /* nullable [4]: the forward's `stats` over ALL
+                                                    n_all rows and columns; NULL = recomputed
+                                                    from the vectors above                     */
                    const float* grad_loss,       /* device scalar dL/dloss                */
                    float grad_mult, int cross_terms,
                    void* d_img, void* d_txt, int grad_dtype, int64_t ld_grad,
                    float* d_txt_partial,         /* nullable, see above                   */
-                   void* const* d_txt_peers,     /* nullable HOST array of n_peers device pointers:
-                                                    rank w's fp32 text-gradient accumulator
-                                                    [n_loc, dim], peer-mapped into this process.
-                                                    Fused reduce-scatter: instead of d_txt_partial,
-                                                    every row of G^T @ img_loc is added straight
-                                                    into its owner's accumulator over NVLink
-                                                    (red.global.add from the GEMM epilogue).  The
-                                                    caller zeroes its accumulator and runs a
-                                                    cross-rank barrier before and after the call */
-                   int n_peers,
+                   const latte_comm_t* comm,     /* nullable.  Fused reduce-scatter: instead of
+                                                    d_txt_partial, every row of G^T @ img_loc is
+                                                    added straight into its owner's accumulator
+                                                    comm->acc[w] over NVLink from the GEMM
+                                                    epilogue; the kernel publishes done = gen when
+                                                    its adds are out, and a last kernel waits for
+                                                    every rank's done flag, casts this rank's
+                                                    accumulator into d_txt, clears it and releases
+                                                    the slot (free = gen).  `phases`: 1 = up to the
+                                                    GEMM, 2 = that last kernel (3 = both)        */
+                   int phases,
                    float* d_scale,               /* device scalar out (d loss / d s)      */
                    void* workspace, size_t workspace_bytes, void* stream);
 
-/*
- * The feature all-gather of gather_features (loss.py:49-50 / :54-55) as one NVLink store
- * kernel: writes this rank's image and text shards ([n_loc, dim], shard_bytes each) into the
- * gathered buffers of every rank.  peer_bases: HOST array of n_peers device pointers, rank w's
- * buffer [2][n_all, dim] mapped into this process (torch symmetric memory); the text matrix
- * starts tensor_stride_bytes after the image matrix.  The caller brackets the call with
- * cross-rank barriers (before: readers of the previous contents are done; after: all shards
- * have landed).  multicast_base (nullable): the NVSwitch multicast mapping of the same buffer;
- * when given, every vector is stored once with multimem.st and the switch replicates it.
- */
-int latte_push_shards(const void* img_shard, const void* txt_shard, int64_t shard_bytes,
-                      void* const* peer_bases, int n_peers, int rank,
-                      int64_t tensor_stride_bytes, void* multicast_base, void* stream);
+
 
 /*
  * SigLipLoss (open_clip loss.py:453-560; factory.py:337-342 selects it on args.siglip).

@@ -64,20 +64,24 @@ def _declare(lib):
     lib.latte_clip_workspace_bytes.argtypes = [i64, i64, i64, i32, c.POINTER(sz)]
     lib.latte_clip_bwd_workspace_bytes.argtypes = [i64, i64, i64, i32, c.POINTER(sz)]
     lib.latte_clip_fwd.argtypes = [vp, i64, vp, i64, vp, i64, vp, i64, i32, i64, i64, i64, i64,
-                                   vp, vp, vp, vp, vp, vp, vp, sz, vp]
+                                   vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]
     lib.latte_clip_rank_sweep_supported.argtypes = [i32, i64]
     lib.latte_clip_fwd_rows.argtypes = [vp, i64, vp, i64, i32, i64, i64, i64, i64, vp,
                                         vp, vp, vp, vp, vp, sz, vp]
     lib.latte_clip_fwd_cols_workspace_bytes.argtypes = [i64, i64, i32, c.POINTER(sz)]
     lib.latte_clip_fwd_cols.argtypes = [vp, i64, i32, vp, i64, vp, i64, i32, i64, i64, i64, i64,
-                                        vp, vp, vp, vp, vp, vp, vp, sz, vp]
+                                        vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]
     lib.latte_clip_bwd.argtypes = [vp, i64, vp, i64, vp, i64, vp, i64, i32, i64, i64, i64, i64,
-                                   vp, vp, vp, vp, vp, vp, f32, i32, vp, vp, i32, i64, vp, vp, i32, vp,
-                                   vp, sz, vp]
+                                   vp, vp, vp, vp, vp, vp, vp, f32, i32, vp, vp, i32, i64, vp, vp, i32,
+                                   vp, vp, sz, vp]    # ..., d_txt_partial, comm, phases, d_scale, ws, bytes, stream
     lib.latte_clip_stage_times.argtypes = [vp, i64, vp, i64, vp, i64, vp, i64, i32, i64, i64, i64, i64,
                                            vp, vp, vp, vp, vp, vp, vp, f32, i32, vp, vp, i32, i64,
                                            vp, vp, vp, sz, vp, sz, vp, i32, c.POINTER(f32)]
-    lib.latte_push_shards.argtypes = [vp, vp, i64, vp, i32, i32, i64, vp, vp]
+    lib.latte_comm_push.argtypes = [vp, vp, vp, i64, i64, vp]
+    lib.latte_comm_release.argtypes = [vp, vp]
+    lib.latte_clip_fwd_rank_workspace_bytes.argtypes = [i64, i64, i64, i32, c.POINTER(sz)]
+    lib.latte_clip_fwd_rank.argtypes = [vp, vp, i64, vp, i64, i32, i64, i64, i64, i64, vp,
+                                        vp, vp, vp, vp, vp, vp, i32, vp, sz, vp]
     lib.latte_siglip_supported.argtypes = [i32, i64]
     lib.latte_siglip_workspace_bytes.argtypes = [i64, i64, i64, i32, i32, i32, c.POINTER(sz)]
     lib.latte_siglip_fwd.argtypes = [vp, i64, vp, i64, i32, i64, i64, i64, i64, vp, vp, vp, vp, sz, vp]
@@ -105,7 +109,8 @@ EXPORTS = [
     "latte_version", "latte_status_string", "latte_device_info", "latte_clip_workspace_bytes",
     "latte_clip_bwd_workspace_bytes", "latte_clip_stage_times", "latte_clip_rank_sweep_supported",
     "latte_clip_fwd_rows", "latte_clip_fwd_cols_workspace_bytes", "latte_clip_fwd_cols",
-    "latte_push_shards", "latte_siglip_supported", "latte_siglip_workspace_bytes",
+    "latte_comm_push", "latte_comm_release", "latte_clip_fwd_rank_workspace_bytes",
+    "latte_clip_fwd_rank", "latte_siglip_supported", "latte_siglip_workspace_bytes",
     "latte_siglip_fwd", "latte_siglip_bwd",
     "latte_clip_fwd", "latte_clip_bwd", "latte_normalize_rows", "latte_nxc_workspace_bytes",
     "latte_nxc_argmax_margin", "latte_nxc_topk", "latte_seg_workspace_bytes", "latte_mix_ema_fwd", "latte_mix_ema_bwd", "latte_bank_accumulate",
@@ -219,9 +224,11 @@ def workspace_cache_bytes() -> int:
 
 
 # ------------------------------------------------------------------------------ ClipLoss
-def clip_fwd(img_loc, txt_loc, img_all, txt_all, label_offset: int, logit_scale, with_nll: bool = False):
+def clip_fwd(img_loc, txt_loc, img_all, txt_all, label_offset: int, logit_scale, with_nll: bool = False,
+             with_stats: bool = False):
     """-> (row_lse[n_loc], col_lse[n_loc], loss[1]) fp32 device tensors; with_nll appends
-    (row_nll[n_loc], col_nll[n_loc]), the per-sample loss terms lse - label logit."""
+    (row_nll[n_loc], col_nll[n_loc]), the per-sample loss terms lse - label logit; with_stats
+    appends stats[4] (LSE min / max, largest nll: the backward's scaling inputs)."""
     lib = load()
     img_loc, txt_loc = _rows(img_loc, "image_features"), _rows(txt_loc, "text_features")
     img_all, txt_all = _rows(img_all, "all_image_features"), _rows(txt_all, "all_text_features")
@@ -237,35 +244,103 @@ def clip_fwd(img_loc, txt_loc, img_all, txt_all, label_offset: int, logit_scale,
     loss = torch.empty(1, dtype=torch.float32, device=dev)
     row_nll = torch.empty(n_loc, dtype=torch.float32, device=dev) if with_nll else None
     col_nll = torch.empty(n_loc, dtype=torch.float32, device=dev) if with_nll else None
+    stats = torch.empty(4, dtype=torch.float32, device=dev) if with_stats else None
     ws = _scratch("fwd", _clip_ws_bytes(n_loc, n_all, dim, dt), dev)
     wp, wn = _aligned_ptr(ws)
     with torch.cuda.device(dev):
         _check(lib.latte_clip_fwd(_ptr(img_loc), img_loc.stride(0), _ptr(txt_loc), txt_loc.stride(0),
                                   _ptr(img_all), img_all.stride(0), _ptr(txt_all), txt_all.stride(0),
                                   dt, n_loc, n_all, dim, label_offset, _ptr(s), _ptr(row_lse),
-                                  _ptr(col_lse), _ptr(row_nll), _ptr(col_nll), _ptr(loss), wp, wn,
-                                  _stream(img_loc)),
+                                  _ptr(col_lse), _ptr(row_nll), _ptr(col_nll), _ptr(loss), _ptr(stats),
+                                  wp, wn, _stream(img_loc)),
                "latte_clip_fwd")
+    out = (row_lse, col_lse, loss)
     if with_nll:
-        return row_lse, col_lse, loss, row_nll, col_nll
-    return row_lse, col_lse, loss
+        out = out + (row_nll, col_nll)
+    if with_stats:
+        out = out + (stats,)
+    return out
 
 
-def push_shards(img_shard, txt_shard, peer_ptrs, rank: int, tensor_stride_bytes: int,
-                multicast_ptr: int = 0):
-    """Write this rank's feature shards into every rank's peer-mapped gathered buffer (through
-    the NVSwitch multicast mapping when ``multicast_ptr`` is given)."""
+COMM_MAX_RANKS = 8
+COMM_FLAG_INTS = 64
+
+
+class LatteComm(ctypes.Structure):
+    """latte_comm_t of include/latte_b200.h: one slot of the peer-memory exchange."""
+    _fields_ = [("rank", ctypes.c_int32), ("world", ctypes.c_int32), ("gen", ctypes.c_int32),
+                ("reserved", ctypes.c_int32),
+                ("gather", ctypes.c_void_p * COMM_MAX_RANKS),
+                ("payload", ctypes.c_void_p * COMM_MAX_RANKS),
+                ("acc", ctypes.c_void_p * COMM_MAX_RANKS),
+                ("flags", ctypes.c_void_p * COMM_MAX_RANKS),
+                ("payload_stride", ctypes.c_int64)]
+
+
+def make_comm(rank: int, world: int, gen: int, gather_ptrs, payload_ptrs, acc_ptrs, flag_ptrs,
+              payload_stride: int) -> LatteComm:
+    c = LatteComm()
+    c.rank, c.world, c.gen, c.reserved = int(rank), int(world), int(gen), 0
+    for w in range(world):
+        c.gather[w] = int(gather_ptrs[w])
+        c.payload[w] = int(payload_ptrs[w])
+        c.acc[w] = int(acc_ptrs[w])
+        c.flags[w] = int(flag_ptrs[w]) if flag_ptrs is not None else None
+    c.payload_stride = int(payload_stride)
+    return c
+
+
+def comm_push(comm: LatteComm, txt_shard, img_shard=None, tensor_stride_bytes: int = 0):
+    """The feature all-gather as a store kernel into every rank's gather buffer (text matrix at
+    ``tensor_stride_bytes``), publishing landed flags; waits for the slot's credits first."""
+    txt_shard = _rows(txt_shard, "text_features").contiguous()
+    if img_shard is not None:
+        img_shard = _rows(img_shard, "image_features").contiguous()
+    nbytes = txt_shard.numel() * txt_shard.element_size()
+    with torch.cuda.device(txt_shard.device):
+        _check(load().latte_comm_push(ctypes.byref(comm), _ptr(txt_shard), _ptr(img_shard), nbytes,
+                                      int(tensor_stride_bytes), _stream(txt_shard)),
+               "latte_comm_push")
+
+
+def comm_release(comm: LatteComm, device):
+    with torch.cuda.device(device):
+        _check(load().latte_comm_release(ctypes.byref(comm),
+                                         ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)),
+               "latte_comm_release")
+
+
+def clip_fwd_rank(comm: LatteComm, img_loc, txt_all, label_offset: int, logit_scale, phases: int = 7,
+                  out=None):
+    """Multi-rank forward over peer memory (after comm_push of this generation) ->
+    (row_lse_all, row_nll_all, col_lse_all, col_nll_all [n_all each], loss[1], stats[4])."""
     lib = load()
-    img_shard, txt_shard = _rows(img_shard, "image_features"), _rows(txt_shard, "text_features")
-    if not (img_shard.is_contiguous() and txt_shard.is_contiguous()):
-        img_shard, txt_shard = img_shard.contiguous(), txt_shard.contiguous()
-    nbytes = img_shard.numel() * img_shard.element_size()
-    peers = (ctypes.c_void_p * len(peer_ptrs))(*peer_ptrs)
-    with torch.cuda.device(img_shard.device):
-        _check(lib.latte_push_shards(_ptr(img_shard), _ptr(txt_shard), nbytes, peers, len(peer_ptrs),
-                                     int(rank), int(tensor_stride_bytes),
-                                     ctypes.c_void_p(int(multicast_ptr) or None), _stream(img_shard)),
-               "latte_push_shards")
+    img_loc, txt_all = _rows(img_loc, "image_features"), _rows(txt_all, "all_text_features")
+    dt = _dt(img_loc)
+    n_loc, dim = img_loc.shape
+    n_all = txt_all.shape[0]
+    dev = img_loc.device
+    s = _scalar_f32(logit_scale)
+    if out is None:
+        vec = torch.empty(4, n_all, dtype=torch.float32, device=dev)
+        loss = torch.empty(1, dtype=torch.float32, device=dev)
+        stats = torch.empty(4, dtype=torch.float32, device=dev)
+    else:
+        vec, loss, stats = out
+    optr = vec.data_ptr()
+    vecs = [ctypes.c_void_p(optr + 4 * n_all * k) for k in range(4)]
+    nbytes = ctypes.c_size_t(0)
+    _check(lib.latte_clip_fwd_rank_workspace_bytes(n_loc, n_all, dim, dt, ctypes.byref(nbytes)),
+           "latte_clip_fwd_rank_workspace_bytes")
+    ws = _scratch("fwd_rank" if phases == 7 else f"fwd_rank{comm.rank}", nbytes.value, dev)
+    wp, wn = _aligned_ptr(ws)
+    with torch.cuda.device(dev):
+        _check(lib.latte_clip_fwd_rank(ctypes.byref(comm), _ptr(img_loc), img_loc.stride(0),
+                                       _ptr(txt_all), txt_all.stride(0), dt, n_loc, n_all, dim,
+                                       int(label_offset), _ptr(s), vecs[0], vecs[1], vecs[2], vecs[3],
+                                       _ptr(loss), _ptr(stats), int(phases), wp, wn, _stream(img_loc)),
+               "latte_clip_fwd_rank")
+    return vec[0], vec[1], vec[2], vec[3], loss, stats, (vec, loss, stats)
 
 
 def rank_sweep_supported(dtype: torch.dtype, dim: int) -> bool:
@@ -320,6 +395,7 @@ def clip_fwd_cols(gathered, img_all, txt_all, n_loc: int, label_offset: int, log
     s = _scalar_f32(logit_scale)
     out = torch.empty(4, n_all, dtype=torch.float32, device=dev)
     loss = torch.empty(1, dtype=torch.float32, device=dev)
+    stats = torch.empty(4, dtype=torch.float32, device=dev)
     optr = out.data_ptr()
     vecs = [ctypes.c_void_p(optr + 4 * n_all * k) for k in range(4)]
 
@@ -332,28 +408,35 @@ def clip_fwd_cols(gathered, img_all, txt_all, n_loc: int, label_offset: int, log
         _check(lib.latte_clip_fwd_cols(_ptr(gathered), gathered.stride(0), world,
                                        _ptr(img_all), img_all.stride(0), _ptr(txt_all), txt_all.stride(0),
                                        dt, n_loc, n_all, dim, label_offset, _ptr(s), vecs[0], vecs[1],
-                                       vecs[2], vecs[3], _ptr(loss), wp, wn, _stream(img_all)),
+                                       vecs[2], vecs[3], _ptr(loss), _ptr(stats), wp, wn,
+                                       _stream(img_all)),
                "latte_clip_fwd_cols")
-    return out[0], out[1], out[2], out[3], loss
+    return out[0], out[1], out[2], out[3], loss, stats
 
 
 def clip_bwd(img_loc, txt_loc, img_all, txt_all, label_offset: int, logit_scale,
              row_lse_all, col_lse_all, grad_loss, grad_mult: float, cross_terms: bool,
              grad_dtype=None, row_nll_all=None, col_nll_all=None, partial: bool = False,
-             peer_ptrs=None):
+             comm: Optional[LatteComm] = None, phases: int = 3, lse_stats=None, out=None):
     """-> (d_img[n_loc, dim], d_txt[n_loc, dim], d_scale[1] fp32).  The feature gradients
     come back in ``grad_dtype`` (default: the feature dtype, what autograd needs).
     ``partial=True`` (one-sweep multi-rank mode): the second result is instead the fp32
     partial [n_all, dim] of the text gradient over ALL columns, to be reduce-scattered.
-    ``peer_ptrs`` (one-sweep mode, fused reduce-scatter): device pointers of every rank's
-    peer-mapped fp32 accumulator [n_loc, dim]; the text gradient is added straight into them
-    and the second result is None."""
+    ``comm`` (one-sweep mode, fused reduce-scatter over peer memory): the text-side product is added
+    straight into the owners' accumulators from the GEMM epilogue and the call's last kernel turns
+    this rank's accumulator into d_txt once every rank's adds have landed.  In the one-sweep modes
+    ``img_all`` may be None (only this rank's images are read).  ``phases`` / ``out`` let a
+    single-process test drive the ranks phase by phase (out = the result tensors of phase 1)."""
     lib = load()
     img_loc, txt_loc = _rows(img_loc, "image_features"), _rows(txt_loc, "text_features")
-    img_all, txt_all = _rows(img_all, "all_image_features"), _rows(txt_all, "all_text_features")
+    txt_all = _rows(txt_all, "all_text_features")
+    if img_all is not None:
+        img_all = _rows(img_all, "all_image_features")
+    elif not (partial or comm is not None):
+        raise RuntimeError("clip_bwd: img_all is required outside the one-sweep modes")
     dt = _dt(img_loc)
     n_loc, dim = img_loc.shape
-    n_all = img_all.shape[0]
+    n_all = txt_all.shape[0]
     dev = img_loc.device
     s = _scalar_f32(logit_scale)
     g = _scalar_f32(grad_loss)
@@ -369,24 +452,30 @@ def clip_bwd(img_loc, txt_loc, img_all, txt_all, label_offset: int, logit_scale,
         col_nll_all = _vec(col_nll_all, torch.float32, "col_nll")
         if row_nll_all.numel() != n_all or col_nll_all.numel() != n_all:
             raise RuntimeError("clip_bwd: nll vectors must have n_all entries")
-    d_img = torch.empty(n_loc, dim, dtype=gdt, device=dev)
-    fused = peer_ptrs is not None
-    d_txt = None if (partial or fused) else torch.empty(n_loc, dim, dtype=gdt, device=dev)
-    d_part = torch.empty(n_all, dim, dtype=torch.float32, device=dev) if partial else None
-    peers = (ctypes.c_void_p * len(peer_ptrs))(*peer_ptrs) if fused else None
-    d_scale = torch.empty(1, dtype=torch.float32, device=dev)
-    ws = _scratch("bwd", _clip_ws_bytes(n_loc, n_all, dim, dt, bwd=True), dev)
+    if out is None:
+        d_img = torch.empty(n_loc, dim, dtype=gdt, device=dev)
+        d_txt = None if partial else torch.empty(n_loc, dim, dtype=gdt, device=dev)
+        d_part = torch.empty(n_all, dim, dtype=torch.float32, device=dev) if partial else None
+        d_scale = torch.empty(1, dtype=torch.float32, device=dev)
+    else:
+        d_img, d_txt, d_part, d_scale = out
+    ws = _scratch("bwd" if phases == 3 else f"bwd{0 if comm is None else comm.rank}",
+                  _clip_ws_bytes(n_loc, n_all, dim, dt, bwd=True), dev)
     wp, wn = _aligned_ptr(ws)
     with torch.cuda.device(dev):
         _check(lib.latte_clip_bwd(_ptr(img_loc), img_loc.stride(0), _ptr(txt_loc), txt_loc.stride(0),
-                                  _ptr(img_all), img_all.stride(0), _ptr(txt_all), txt_all.stride(0),
+                                  _ptr(img_all), 0 if img_all is None else img_all.stride(0),
+                                  _ptr(txt_all), txt_all.stride(0),
                                   dt, n_loc, n_all, dim, label_offset, _ptr(s), _ptr(row_lse_all),
-                                  _ptr(col_lse_all), _ptr(row_nll_all), _ptr(col_nll_all), _ptr(g),
+                                  _ptr(col_lse_all), _ptr(row_nll_all), _ptr(col_nll_all),
+                                  _ptr(lse_stats), _ptr(g),
                                   float(grad_mult), int(bool(cross_terms)),
                                   _ptr(d_img), _ptr(d_txt), _DTYPES[gdt], dim, _ptr(d_part),
-                                  peers, len(peer_ptrs) if fused else 0,
+                                  ctypes.byref(comm) if comm is not None else None, int(phases),
                                   _ptr(d_scale), wp, wn, _stream(img_loc)),
                "latte_clip_bwd")
+    if out is not None or phases != 3:
+        return d_img, (d_part if partial else d_txt), d_scale, (d_img, d_txt, d_part, d_scale)
     return d_img, (d_part if partial else d_txt), d_scale
 
 

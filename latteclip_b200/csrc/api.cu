@@ -1,20 +1,9 @@
 // C ABI of liblatte_b200: library info + the ClipLoss forward / backward orchestration
 // (row kernels in clip_tc.cu / clip_simt.cu, small finalize kernels here).
 #include "latte_common.cuh"
-
-#include <stdlib.h>
+#include "tc_ptx.cuh"
 
 namespace latte {
-
-// Debug switch: LATTE_B200_FP16_COPIES=1 restores fp16 copies of bf16 features as the operands
-// of the gradient GEMMs (the default feeds the bf16 features themselves).
-bool want_fp16_copies() {
-  static const bool on = []() {
-    const char* e = getenv("LATTE_B200_FP16_COPIES");
-    return e != nullptr && e[0] == '1';
-  }();
-  return on;
-}
 
 int device_sm_count() {
   int dev = 0, sms = 0;
@@ -118,26 +107,35 @@ clip_finalize_kernel(const float* pmax_r, const float* psum_r, const float* diag
 __global__ void __launch_bounds__(256)
 col_merge_kernel(const float* gathered, int64_t stride, int world, int64_t n_loc, int64_t n_all,
                  int nblk_total, float* row_lse_all, float* row_nll_all, float* label_logit_all,
-                 float* col_lse_all, float* col_nll_all, int* flag) {
+                 float* col_lse_all, float* col_nll_all, int* flag, const int* wait_flags,
+                 int wait_gen) {
+  if (wait_flags) {          // peer-memory exchange: every rank's payload row must have landed
+    if ((int)threadIdx.x < world) ptx::flag_wait_ge(wait_flags + threadIdx.x, wait_gen);
+    __syncthreads();
+  }
   const int64_t j = (int64_t)blockIdx.x * 256 + threadIdx.x;
   if (j >= n_all) return;
   const float* own = gathered + (j / n_loc) * stride + 2 * n_all + (j % n_loc);
-  const float label_logit = own[2 * n_loc];
-  row_lse_all[j] = own[0];
-  row_nll_all[j] = own[n_loc];
+  const float label_logit = __ldcv(own + 2 * n_loc);
+  row_lse_all[j] = __ldcv(own);
+  row_nll_all[j] = __ldcv(own + n_loc);
   label_logit_all[j] = label_logit;
-  float M = -INFINITY, L = 0.f;
-  for (int w = 0; w < world; ++w) {
+  float mx[LATTE_COMM_MAX_RANKS], lx[LATTE_COMM_MAX_RANKS];
+#pragma unroll
+  for (int w = 0; w < LATTE_COMM_MAX_RANKS; ++w) {
     // scalar loads: the rank stride 2 N + 3 n is odd for odd shard sizes
-    float2 ml;
-    ml.x = gathered[(int64_t)w * stride + 2 * j];
-    ml.y = gathered[(int64_t)w * stride + 2 * j + 1];
-    if (!(ml.x > -INFINITY)) continue;
-    if (ml.x > M) {
-      L = L * exp2f(M - ml.x) + ml.y;
-      M = ml.x;
+    mx[w] = w < world ? __ldcv(gathered + (int64_t)w * stride + 2 * j) : -INFINITY;
+    lx[w] = w < world ? __ldcv(gathered + (int64_t)w * stride + 2 * j + 1) : 0.f;
+  }
+  float M = -INFINITY, L = 0.f;
+#pragma unroll
+  for (int w = 0; w < LATTE_COMM_MAX_RANKS; ++w) {
+    if (!(mx[w] > -INFINITY)) continue;
+    if (mx[w] > M) {
+      L = L * exp2f(M - mx[w]) + lx[w];
+      M = mx[w];
     } else {
-      L = fmaf(ml.y, exp2f(ml.x - M), L);
+      L = fmaf(lx[w], exp2f(mx[w] - M), L);
     }
   }
   const float logL = log2f(L);
@@ -146,6 +144,36 @@ col_merge_kernel(const float* gathered, int64_t stride, int world, int64_t n_loc
   col_nll_all[j] = (fmaf(-kLog2e, label_logit, M) + logL) * kLn2;
   const bool ok = (M - lse2) + log2f((float)nblk_total) < 95.0f;
   if (!ok) atomicOr(flag, 1);
+}
+
+// Second (exact) round of the peer-memory forward, gated: merge the exact (max, sum) pairs of all
+// ranks ([world][2 n_all]) into the column LSE and loss term.
+__global__ void __launch_bounds__(256)
+col_merge_exact_kernel(const int* gate, const float* exact, int world, int64_t n_all,
+                       const float* label_logit_all, float* col_lse_all, float* col_nll_all,
+                       const int* wait_flags, int wait_gen) {
+  if (*gate == 0) return;
+  if (wait_flags) {
+    if ((int)threadIdx.x < world) ptx::flag_wait_ge(wait_flags + threadIdx.x, wait_gen);
+    __syncthreads();
+  }
+  const int64_t j = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (j >= n_all) return;
+  float M = -INFINITY, L = 0.f;
+  for (int w = 0; w < world; ++w) {
+    const float m = __ldcv(exact + (int64_t)w * 2 * n_all + 2 * j);
+    const float l = __ldcv(exact + (int64_t)w * 2 * n_all + 2 * j + 1);
+    if (!(m > -INFINITY)) continue;
+    if (m > M) {
+      L = L * exp2f(M - m) + l;
+      M = m;
+    } else {
+      L = fmaf(l, exp2f(m - M), L);
+    }
+  }
+  const float logL = log2f(L);
+  col_lse_all[j] = (M + logL) * kLn2;
+  col_nll_all[j] = (fmaf(-kLog2e, label_logit_all[j], M) + logL) * kLn2;
 }
 
 // ---- one launch for everything the pair forward sweep leaves to finish ------------------------
@@ -266,33 +294,54 @@ __global__ void __launch_bounds__(256) pair_fwd_finalize_kernel(const PairFinali
 __global__ void __launch_bounds__(256)
 pair_fwd_finish_kernel(const int* gate, const float* pmax, const float* psum, int nparts,
                        int64_t n_merge, const float* label_dot, const float* logit_scale,
-                       float* lse_out, float* nll_out, const float* row_nll, const float* col_nll,
-                       int64_t loss_off, int64_t n_loss, double* loss_partial, unsigned int* counter,
-                       float* loss) {
+                       const float* row_lse, float* lse_out, float* nll_out, const float* row_nll,
+                       const float* col_nll, int64_t loss_off, int64_t n_loss, double* loss_partial,
+                       float* stat_partial, unsigned int* counter, float* loss, float* stats) {
   __shared__ double red[8];
+  __shared__ float rlo[8], rhi[8], rnl[8];
   __shared__ bool last;
   const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  const int nb = (int)gridDim.x;
   double acc = 0.0;
+  float lo = INFINITY, hi = -INFINITY, nmax = -INFINITY;
   if (i < n_merge) {
     float cn = col_nll[i];
+    float cl = lse_out[i];
     if (gate && *gate != 0) {
       float M, logL;
       merge_parts2(pmax, psum, nparts, n_merge, i, M, logL);
-      lse_out[i] = (M + logL) * kLn2;
+      cl = (M + logL) * kLn2;
+      lse_out[i] = cl;
       const float s = logit_scale ? __ldg(logit_scale) : 1.f;
       cn = ((M - s * kLog2e * label_dot[i]) + logL) * kLn2;
       nll_out[i] = cn;
     }
-    if (i >= loss_off && i < loss_off + n_loss) acc = (double)row_nll[i] + (double)cn;
+    const float rl = row_lse[i], rn = row_nll[i];
+    lo = fminf(rl, cl); hi = fmaxf(rl, cl); nmax = fmaxf(rn, cn);
+    if (i >= loss_off && i < loss_off + n_loss) acc = (double)rn + (double)cn;
   }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  for (int o = 16; o > 0; o >>= 1) {
+    acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    nmax = fmaxf(nmax, __shfl_xor_sync(0xffffffffu, nmax, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    const int w = threadIdx.x >> 5;
+    red[w] = acc; rlo[w] = lo; rhi[w] = hi; rnl[w] = nmax;
+  }
   __syncthreads();
   if (threadIdx.x == 0) {
     double tot = 0.0;
-    for (int w = 0; w < 8; ++w) tot += red[w];
+    for (int w = 0; w < 8; ++w) {
+      tot += red[w];
+      lo = fminf(lo, rlo[w]); hi = fmaxf(hi, rhi[w]); nmax = fmaxf(nmax, rnl[w]);
+    }
     loss_partial[blockIdx.x] = tot;
+    stat_partial[blockIdx.x] = lo;
+    stat_partial[nb + blockIdx.x] = hi;
+    stat_partial[2 * nb + blockIdx.x] = nmax;
     __threadfence();
     last = atomicInc(counter, gridDim.x - 1) == gridDim.x - 1;
   }
@@ -300,15 +349,33 @@ pair_fwd_finish_kernel(const int* gate, const float* pmax, const float* psum, in
   if (!last) return;
   __threadfence();
   double v = 0.0;
-  for (int b = threadIdx.x; b < (int)gridDim.x; b += 256) v += __ldcg(loss_partial + b);
+  lo = INFINITY; hi = -INFINITY; nmax = -INFINITY;
+  for (int b = threadIdx.x; b < nb; b += 256) {
+    v += __ldcg(loss_partial + b);
+    lo = fminf(lo, __ldcg(stat_partial + b));
+    hi = fmaxf(hi, __ldcg(stat_partial + nb + b));
+    nmax = fmaxf(nmax, __ldcg(stat_partial + 2 * nb + b));
+  }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  for (int o = 16; o > 0; o >>= 1) {
+    v += __shfl_xor_sync(0xffffffffu, v, o);
+    lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    nmax = fmaxf(nmax, __shfl_xor_sync(0xffffffffu, nmax, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    const int w = threadIdx.x >> 5;
+    red[w] = v; rlo[w] = lo; rhi[w] = hi; rnl[w] = nmax;
+  }
   __syncthreads();
   if (threadIdx.x == 0) {
     double tot = 0.0;
-    for (int w = 0; w < 8; ++w) tot += red[w];
+    for (int w = 0; w < 8; ++w) {
+      tot += red[w];
+      lo = fminf(lo, rlo[w]); hi = fmaxf(hi, rhi[w]); nmax = fmaxf(nmax, rnl[w]);
+    }
     *loss = (float)(tot / (2.0 * (double)n_loss));
+    if (stats) { stats[0] = lo; stats[1] = hi; stats[2] = nmax; stats[3] = 0.f; }
   }
 }
 
@@ -387,59 +454,89 @@ pair_prep_features_kernel(const void* img, int64_t ld_img, const void* txt, int6
   if (lane == 0 && umax > 0.f) atomicMax(u_bits, __float_as_uint(umax));
 }
 
-// Range of all LSE values (base 2): rho = mid-point; flag = 1 when max - min <= 64, so that
-// 2^(lse - rho) and products of two such factors stay well inside fp32 range (clip_pair.cu's
-// one-ex2 epilogue); otherwise the sweep uses its two-ex2 epilogue.
+// Statistics the backward's scaling needs: stats[0] = min, stats[1] = max of all LSE values
+// (natural log), stats[2] = the largest per-sample loss term nll (bounds |G|: 1 - P_kk =
+// -expm1(-nll_k)); without nll vectors stats[2] = -log1p(-u) from the label-logit bound u.
+// The forward produces the same three numbers for free (pair_fwd_finish_kernel); this kernel
+// serves callers that only hand over the LSE vectors.
 __global__ void __launch_bounds__(1024)
-lse_range_kernel(const float* row_lse, const float* col_lse, int64_t n_all, float* rho, int* flag,
+lse_stats_kernel(const float* row_lse, const float* col_lse, int64_t n_all,
                  const unsigned int* u_bits, const float* row_nll, const float* col_nll,
-                 float* gscale_log2, const float* grad_loss,
-                 float grad_mult, const float* logit_scale, int64_t n_loc, float* out_scale) {
-  __shared__ float smin[32], smax[32], sneg[32];
-  float lo = INFINITY, hi = -INFINITY, nmin = INFINITY;
+                 float* stats) {
+  __shared__ float smin[32], smax[32], snll[32];
+  float lo = INFINITY, hi = -INFINITY, nmax = -INFINITY;
   for (int64_t i = threadIdx.x; i < n_all; i += 1024) {
     const float a = row_lse[i], b = col_lse[i];
     lo = fminf(lo, fminf(a, b));
     hi = fmaxf(hi, fmaxf(a, b));
-    // 1 - P_kk = -expm1(-nll_k) grows with nll_k: the largest nll gives the bound on |G|
-    if (row_nll) nmin = fminf(nmin, fminf(-row_nll[i], -col_nll[i]));
+    if (row_nll) nmax = fmaxf(nmax, fmaxf(row_nll[i], col_nll[i]));
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
     hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
-    nmin = fminf(nmin, __shfl_xor_sync(0xffffffffu, nmin, o));
+    nmax = fmaxf(nmax, __shfl_xor_sync(0xffffffffu, nmax, o));
   }
   if ((threadIdx.x & 31) == 0) {
-    smin[threadIdx.x >> 5] = lo; smax[threadIdx.x >> 5] = hi; sneg[threadIdx.x >> 5] = nmin;
+    smin[threadIdx.x >> 5] = lo; smax[threadIdx.x >> 5] = hi; snll[threadIdx.x >> 5] = nmax;
   }
   __syncthreads();
   if (threadIdx.x == 0) {
     for (int w = 0; w < 32; ++w) {
-      lo = fminf(lo, smin[w]); hi = fmaxf(hi, smax[w]); nmin = fminf(nmin, sneg[w]);
+      lo = fminf(lo, smin[w]); hi = fmaxf(hi, smax[w]); nmax = fmaxf(nmax, snll[w]);
     }
-    lo *= kLog2e; hi *= kLog2e;
-    const bool ok = (hi - lo) <= 64.0f && hi < 3.0e38f && lo > -3.0e38f;   // also rejects NaN / inf
-    *rho = ok ? 0.5f * (lo + hi) : 0.f;
-    *flag = ok ? 1 : 0;
-    // |G| <= 2u; the LSE / label-logit inputs carry ~5e-5 of fp32 error, so pad u by 1e-3:
-    // 2 (u + 1e-3) 2^gs <= 2^14 keeps fp16 G finite.  gs = 13 for u ~ 1, up to 22 when converged.
-    // nmin = -max nll (clamped at 0: an nll can come out slightly negative); NaN -> u = 1
-    float u_raw = row_nll ? -expm1f(fminf(nmin, 0.f)) : __uint_as_float(*u_bits);
-    if (!(u_raw >= 0.f)) u_raw = 1.0f;
-    const float u = fminf(u_raw, 1.0f) + 1.0e-3f;
-    const float gs = fminf(fmaxf(13.0f - ceilf(log2f(u)), 13.0f), 22.0f);
-    *gscale_log2 = gs;
-    // gradient = out_scale * (accumulated G . features)
-    *out_scale = __ldg(grad_loss) * grad_mult / (2.0f * (float)n_loc) * __ldg(logit_scale) * exp2f(-gs);
+    if (!row_nll) {
+      // no loss terms: the label-logit bound u of the prep kernel, or no bound at all (u = 1)
+      const float u = fminf(u_bits ? __uint_as_float(*u_bits) : 1.0f, 0.9999999f);
+      nmax = -log1pf(-u);
+    }
+    stats[0] = lo; stats[1] = hi; stats[2] = nmax;
   }
 }
 
-// natural-log LSE -> base-2 units (zero padded to the tile grid) and the rank-one factors
+// Scalars of the backward from the LSE statistics (every thread derives the same values):
+//   rho = mid-point of the LSE range (base 2); fast = 1 when max - min <= 64 binary orders, so that
+//   2^(lse - rho) and products of two such factors stay well inside fp32 range (clip_pair.cu's
+//   one-ex2 epilogue), otherwise the sweep uses its two-ex2 epilogue;
+//   gs = log2 of the fp16 scale of G: |G| <= 2u with u = max_k (1 - P_kk); the inputs carry ~5e-5 of
+//   fp32 error, so u is padded by 1e-3: 2 (u + 1e-3) 2^gs <= 2^14 keeps fp16 G finite (gs = 13 for
+//   u ~ 1, up to 22 when converged);  out_scale: gradient = out_scale * (accumulated G . features).
+struct BwdScalars { float rho; int fast; float gs; float out_scale; };
+__device__ __forceinline__ BwdScalars bwd_scalars(const float* stats, const float* grad_loss,
+                                                  float grad_mult, const float* logit_scale,
+                                                  int64_t n_loc) {
+  BwdScalars o;
+  const float lo = __ldg(stats) * kLog2e, hi = __ldg(stats + 1) * kLog2e;
+  const bool ok = (hi - lo) <= 64.0f && hi < 3.0e38f && lo > -3.0e38f;   // also rejects NaN / inf
+  o.rho = ok ? 0.5f * (lo + hi) : 0.f;
+  o.fast = ok ? 1 : 0;
+  // an nll can come out slightly negative; NaN -> u = 1
+  float u_raw = -expm1f(-fmaxf(__ldg(stats + 2), 0.f));
+  if (!(u_raw >= 0.f)) u_raw = 1.0f;
+  const float u = fminf(u_raw, 1.0f) + 1.0e-3f;
+  o.gs = fminf(fmaxf(13.0f - ceilf(log2f(u)), 13.0f), 22.0f);
+  o.out_scale = __ldg(grad_loss) * grad_mult / (2.0f * (float)n_loc) * __ldg(logit_scale) * exp2f(-o.gs);
+  return o;
+}
+
+// natural-log LSE -> base-2 units (zero padded to the tile grid) and the rank-one factors; the
+// first thread also publishes the scalars (scal = {rho, fast flag, u bits (unused), gs, out_scale})
 __global__ void lse_vectors_kernel(const float* row_lse, const float* col_lse, int64_t n_all,
-                                   int64_t n_pad, const float* rho_p, float* row2, float* col2,
+                                   int64_t n_pad, const float* stats, const float* grad_loss,
+                                   float grad_mult, const float* logit_scale, int64_t n_loc,
+                                   float* scal, float* row2, float* col2,
                                    float* e_row, float* einv_row, float* e_col, float* einv_col) {
   const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  BwdScalars sc = {0.f, 0, 13.f, 0.f};
+  if (stats) {
+    sc = bwd_scalars(stats, grad_loss, grad_mult, logit_scale, n_loc);
+    if (j == 0) {
+      scal[0] = sc.rho;
+      reinterpret_cast<int*>(scal)[1] = sc.fast;
+      scal[3] = sc.gs;
+      scal[4] = sc.out_scale;
+    }
+  }
   if (j >= n_pad) return;
   const bool in = j < n_all;
   const float r2 = in ? row_lse[j] * kLog2e : 0.f;
@@ -447,7 +544,7 @@ __global__ void lse_vectors_kernel(const float* row_lse, const float* col_lse, i
   row2[j] = r2;
   col2[j] = c2;
   if (e_row) {
-    const float rho = *rho_p;
+    const float rho = sc.rho;
     e_row[j] = in ? exp2f(r2 - rho) : 0.f;
     einv_row[j] = in ? exp2f(rho - r2) : 0.f;
     e_col[j] = in ? exp2f(c2 - rho) : 0.f;
@@ -496,42 +593,134 @@ __global__ void bf16_to_fp16_kernel(const __nv_bfloat16* in0, __half* out0,
   }
 }
 
-// Push this rank's image and text shards into every rank's gathered buffers (peer-mapped):
-// the all-gather of loss.py:49-50 / :54-55 as one NVLink store kernel.  16-byte vectors.
-__global__ void __launch_bounds__(256)
-push_shards_kernel(const uint4* img, const uint4* txt, int64_t shard_vecs, int64_t tensor_vecs,
-                   int64_t rank_off_vecs, uint4* p0, uint4* p1, uint4* p2, uint4* p3, uint4* p4,
-                   uint4* p5, uint4* p6, uint4* p7, int n_peers) {
-  uint4* peers[8] = {p0, p1, p2, p3, p4, p5, p6, p7};
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < 2 * shard_vecs; v += stride) {
-    const bool is_txt = v >= shard_vecs;
-    const int64_t k = is_txt ? v - shard_vecs : v;
-    const uint4 val = is_txt ? __ldg(txt + k) : __ldg(img + k);
-    const int64_t dst = (is_txt ? tensor_vecs : 0) + rank_off_vecs + k;
-#pragma unroll
-    for (int p = 0; p < 8; ++p)
-      if (p < n_peers) peers[p][dst] = val;
+// =========================================================================== peer-memory exchange
+// Flag block of one slot on one rank (int32, LATTE_COMM_FLAG_INTS): entry [kind * 8 + src].
+constexpr int kFlagLandedTxt = 0, kFlagLandedImg = 8, kFlagPayload = 16, kFlagPayload2 = 24,
+              kFlagDone = 32, kFlagFree = 40, kFlagCounter = 48;
+constexpr int kCntPush = 0, kCntPayload = 1, kCntPayload2 = 2, kCntGemm = 3, kCntFinish = 4, kCntPushImg = 5;
+
+struct PeerPtrs {
+  void* p[LATTE_COMM_MAX_RANKS];
+};
+struct PeerFlags {
+  int* p[LATTE_COMM_MAX_RANKS];      // NULL entries: no signalling (single-process tests)
+};
+
+// All threads call this after their (peer) stores; returns true in every thread of the last CTA
+// of the grid to get here.  `counter` wraps back to 0.
+__device__ __forceinline__ bool grid_last_cta(unsigned int* counter) {
+  __shared__ bool s_last;
+  __threadfence_system();            // this thread's stores before the counter bump, system-wide
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicInc(counter, gridDim.x - 1) == gridDim.x - 1;
+  __syncthreads();
+  return s_last;
+}
+// flag[kind + rank] = gen on every rank (called by the last CTA)
+__device__ __forceinline__ void signal_all(const PeerFlags& f, int world, int kind, int rank, int gen) {
+  if ((int)threadIdx.x < world && f.p[threadIdx.x]) {
+    __threadfence_system();
+    ptx::st_release_sys(f.p[threadIdx.x] + kind + rank, gen);
   }
 }
 
-// Same gather through the NVSwitch multicast mapping of the gathered buffer: ONE store per
-// vector lands in every rank's copy (multimem.st), so a rank sends its shard once instead of
-// once per peer.
+// Push this rank's text (and image) shard into every rank's gathered buffer: the all-gather of
+// loss.py:49-50 / :54-55 as one NVLink store kernel, 16-byte vectors.  Before storing, wait until
+// every peer released the previous generation of this slot (its readers are done).
 __global__ void __launch_bounds__(256)
-push_shards_multicast_kernel(const uint4* img, const uint4* txt, int64_t shard_vecs,
-                             int64_t tensor_vecs, int64_t rank_off_vecs, uint4* mc_base) {
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < 2 * shard_vecs; v += stride) {
-    const bool is_txt = v >= shard_vecs;
-    const int64_t k = is_txt ? v - shard_vecs : v;
-    const uint4 val = is_txt ? __ldg(txt + k) : __ldg(img + k);
-    uint4* dst = mc_base + (is_txt ? tensor_vecs : 0) + rank_off_vecs + k;
-    asm volatile("multimem.st.weak.global.v4.f32 [%0], {%1, %2, %3, %4};"
-                 ::"l"(dst), "f"(__uint_as_float(val.x)), "f"(__uint_as_float(val.y)),
-                   "f"(__uint_as_float(val.z)), "f"(__uint_as_float(val.w))
-                 : "memory");
+comm_push_kernel(const uint4* shard, int64_t shard_vecs, int64_t dst_off_vecs, PeerPtrs dst,
+                 PeerFlags flags, int* my_flags, int world, int rank, int gen, int kind, int cnt) {
+  if (my_flags) {
+    if ((int)threadIdx.x < world && kind == kFlagLandedTxt)
+      ptx::flag_wait_ge(my_flags + kFlagFree + threadIdx.x, gen - 1);
+    __syncthreads();
   }
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < shard_vecs; v += stride) {
+    const uint4 val = __ldg(shard + v);
+#pragma unroll
+    for (int w = 0; w < LATTE_COMM_MAX_RANKS; ++w)
+      if (w < world) static_cast<uint4*>(dst.p[w])[dst_off_vecs + v] = val;
+  }
+  if (!my_flags) return;
+  if (grid_last_cta(reinterpret_cast<unsigned int*>(my_flags + kFlagCounter + cnt)))
+    signal_all(flags, world, kind, rank, gen);
+}
+
+__global__ void comm_release_kernel(PeerFlags flags, int world, int rank, int gen) {
+  signal_all(flags, world, kFlagFree, rank, gen);
+}
+
+// Store this rank's forward payload (already in its own block row `rank`) into row `rank` of every
+// peer's payload block, then publish `kind` = gen.  With `gate` the kernel only acts when *gate != 0
+// (second, exact round: every rank takes the same decision because the merged statistics are
+// bit-identical on all ranks), after rebuilding the (max, sum) pairs from the exact row kernel.
+__global__ void __launch_bounds__(256)
+comm_payload_kernel(const int* gate, const float* pmax, const float* psum, int nparts, int64_t n_cols,
+                    float* row_local, int64_t len, int64_t row_off, PeerPtrs blocks, PeerFlags flags,
+                    int* my_flags, int world, int rank, int gen, int kind, int cnt) {
+  if (gate && *gate == 0) return;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < len; v += stride) {
+    float val;
+    if (gate) {
+      // exact column partial of this rank: merge the row kernel's parts of text row v / 2
+      const int64_t j = v >> 1;
+      float M = -INFINITY;
+      for (int k = 0; k < nparts; ++k) M = fmaxf(M, pmax[(int64_t)k * n_cols + j]);
+      float L = 0.f;
+      for (int k = 0; k < nparts; ++k) {
+        const float m = pmax[(int64_t)k * n_cols + j];
+        if (m > -INFINITY) L += psum[(int64_t)k * n_cols + j] * exp2f(m - M);
+      }
+      val = (v & 1) ? L : M;
+      row_local[v] = val;
+    } else {
+      val = row_local[v];
+    }
+#pragma unroll
+    for (int w = 0; w < LATTE_COMM_MAX_RANKS; ++w)
+      if (w < world && w != rank) static_cast<float*>(blocks.p[w])[row_off + v] = val;
+  }
+  if (!my_flags) return;
+  if (grid_last_cta(reinterpret_cast<unsigned int*>(my_flags + kFlagCounter + cnt)))
+    signal_all(flags, world, kind, rank, gen);
+}
+
+// Last kernel of the fused reduce-scatter: wait until every rank's GEMM has published its adds,
+// turn this rank's accumulator into d_txt (the adders applied the scale), clear it for the slot's
+// next generation and release the slot.
+__global__ void __launch_bounds__(256)
+comm_acc_finish_kernel(float* acc, int64_t n_loc, int64_t dim, void* d_txt, int out_dtype,
+                       int64_t ld_out, PeerFlags flags, int* my_flags, int world, int rank, int gen) {
+  if (my_flags) {
+    if ((int)threadIdx.x < world) ptx::flag_wait_ge(my_flags + kFlagDone + threadIdx.x, gen);
+    __syncthreads();
+  }
+  const int64_t per_row = dim / 4;
+  const int64_t total = n_loc * per_row;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride) {
+    const int64_t r = idx / per_row, c = (idx % per_row) * 4;
+    float4* a = reinterpret_cast<float4*>(acc + r * dim + c);
+    const float4 v = __ldcv(a);          // written by peer GPUs: bypass any stale line
+    *a = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (out_dtype == LATTE_F32) {
+      float* po = static_cast<float*>(d_txt) + r * ld_out + c;
+      po[0] = v.x; po[1] = v.y; po[2] = v.z; po[3] = v.w;
+    } else if (out_dtype == LATTE_BF16) {
+      __nv_bfloat16* po = static_cast<__nv_bfloat16*>(d_txt) + r * ld_out + c;
+      po[0] = __float2bfloat16_rn(v.x); po[1] = __float2bfloat16_rn(v.y);
+      po[2] = __float2bfloat16_rn(v.z); po[3] = __float2bfloat16_rn(v.w);
+    } else {
+      __half* po = static_cast<__half*>(d_txt) + r * ld_out + c;
+      po[0] = __float2half_rn(v.x); po[1] = __float2half_rn(v.y);
+      po[2] = __float2half_rn(v.z); po[3] = __float2half_rn(v.w);
+    }
+  }
+  if (!my_flags) return;
+  if (grid_last_cta(reinterpret_cast<unsigned int*>(my_flags + kFlagCounter + kCntFinish)))
+    signal_all(flags, world, kFlagFree, rank, gen);
 }
 
 struct WsLayout {
@@ -572,7 +761,8 @@ WsLayout ws_layout(int64_t n_loc, int64_t n_all, int64_t dim, int dtype, bool bw
   w.off_col2 = o; o += up(w.n_pad);
   w.ds_cap = up(2 * (((size_t)n_loc + 63) / 64) + 2 * 160);
   w.off_ds = o; o += w.ds_cap;
-  w.off_lossp = o; o += up(2 * (((size_t)n_loc + 255) / 256) + 2);   // doubles
+  // per finish-CTA partials: one double (loss) + three floats (LSE min / max, nll max)
+  w.off_lossp = o; o += up(5 * (((size_t)n_loc + 255) / 256) + 8);
   w.off_nll_r = o; o += nl;
   w.off_nll_c = o; o += nl;
   w.ld16 = ((size_t)dim + 7) / 8 * 8;
@@ -667,12 +857,26 @@ extern "C" int latte_clip_bwd_workspace_bytes(int64_t n_loc, int64_t n_all, int6
   return LATTE_OK;
 }
 
+namespace {
+bool comm_ok(const latte_comm_t* c) {
+  if (!c || c->world < 2 || c->world > LATTE_COMM_MAX_RANKS || c->rank < 0 || c->rank >= c->world ||
+      c->gen < 1)
+    return false;
+  return true;
+}
+PeerFlags comm_flags(const latte_comm_t* c) {
+  PeerFlags f;
+  for (int w = 0; w < LATTE_COMM_MAX_RANKS; ++w) f.p[w] = w < c->world ? c->flags[w] : nullptr;
+  return f;
+}
+}  // namespace
+
 static int clip_fwd_impl(const void* img_loc, int64_t ld_img_loc, const void* txt_loc,
                          int64_t ld_txt_loc, const void* img_all, int64_t ld_img_all,
                          const void* txt_all, int64_t ld_txt_all, int dtype, int64_t n_loc,
                          int64_t n_all, int64_t dim, int64_t label_offset,
                          const float* logit_scale, float* row_lse, float* col_lse,
-                         float* row_nll, float* col_nll, float* loss, void* workspace,
+                         float* row_nll, float* col_nll, float* loss, float* stats, void* workspace,
                          size_t workspace_bytes, void* stream, StageTimer* tm) {
   LATTE_CHECK_ARG(img_loc && txt_loc && img_all && txt_all && logit_scale && row_lse && col_lse &&
                   loss && workspace);
@@ -740,9 +944,10 @@ static int clip_fwd_impl(const void* img_loc, int64_t ld_img_loc, const void* tx
       a.part_max = ws + w.off_pmax_c; a.part_sum = ws + w.off_psum_c; a.diag = ws + w.off_diag_c;
       rc = clip_fwd_rows_tc(a, st);
       if (rc) return rc;
-      pair_fwd_finish_kernel<<<rblocks, 256, 0, st>>>(flag, a.part_max, a.part_sum, nparts, n_loc,
-                                                      pa.diag, logit_scale, col_lse, col_nll, row_nll,
-                                                      col_nll, 0, n_loc, lossp, counter, loss);
+      pair_fwd_finish_kernel<<<rblocks, 256, 0, st>>>(
+          flag, a.part_max, a.part_sum, nparts, n_loc, pa.diag, logit_scale, row_lse, col_lse, col_nll,
+          row_nll, col_nll, 0, n_loc, lossp, reinterpret_cast<float*>(lossp + rblocks), counter, loss,
+          stats);
       LATTE_LAUNCH_OK();
     } else {
       pair_fwd_finalize_kernel<<<rblocks, 256, 0, st>>>(fa);
@@ -759,9 +964,10 @@ static int clip_fwd_impl(const void* img_loc, int64_t ld_img_loc, const void* tx
       fa.row_lse = col_lse; fa.row_nll = col_nll;
       pair_fwd_finalize_kernel<<<rblocks, 256, 0, st>>>(fa);
       LATTE_LAUNCH_OK();
-      pair_fwd_finish_kernel<<<rblocks, 256, 0, st>>>(nullptr, nullptr, nullptr, 0, n_loc, nullptr,
-                                                      nullptr, nullptr, nullptr, row_nll, col_nll, 0,
-                                                      n_loc, lossp, counter, loss);
+      // statistics of the local rows only: the caller's backward sees all-gathered vectors
+      pair_fwd_finish_kernel<<<rblocks, 256, 0, st>>>(
+          nullptr, nullptr, nullptr, 0, n_loc, nullptr, nullptr, row_lse, col_lse, nullptr, row_nll,
+          col_nll, 0, n_loc, lossp, reinterpret_cast<float*>(lossp + rblocks), counter, loss, nullptr);
       LATTE_LAUNCH_OK();
     }
     LATTE_MARK(LATTE_STAGE_FWD_FINALIZE);
@@ -797,11 +1003,12 @@ extern "C" int latte_clip_fwd(const void* img_loc, int64_t ld_img_loc, const voi
                               const void* txt_all, int64_t ld_txt_all, int dtype, int64_t n_loc,
                               int64_t n_all, int64_t dim, int64_t label_offset,
                               const float* logit_scale, float* row_lse, float* col_lse,
-                              float* row_nll, float* col_nll, float* loss, void* workspace,
-                              size_t workspace_bytes, void* stream) {
+                              float* row_nll, float* col_nll, float* loss, float* stats,
+                              void* workspace, size_t workspace_bytes, void* stream) {
   return clip_fwd_impl(img_loc, ld_img_loc, txt_loc, ld_txt_loc, img_all, ld_img_all, txt_all,
                        ld_txt_all, dtype, n_loc, n_all, dim, label_offset, logit_scale, row_lse,
-                       col_lse, row_nll, col_nll, loss, workspace, workspace_bytes, stream, nullptr);
+                       col_lse, row_nll, col_nll, loss, stats, workspace, workspace_bytes, stream,
+                       nullptr);
 }
 
 // ---- multi-rank forward with ONE logit sweep per rank ---------------------------------------
@@ -878,7 +1085,7 @@ extern "C" int latte_clip_fwd_cols(const float* gathered, int64_t stride, int wo
                                    int64_t ld_txt_all, int dtype, int64_t n_loc, int64_t n_all,
                                    int64_t dim, int64_t label_offset, const float* logit_scale,
                                    float* row_lse_all, float* row_nll_all, float* col_lse_all,
-                                   float* col_nll_all, float* loss, void* workspace,
+                                   float* col_nll_all, float* loss, float* stats, void* workspace,
                                    size_t workspace_bytes, void* stream) {
   LATTE_CHECK_ARG(gathered && img_all && txt_all && logit_scale && row_lse_all && row_nll_all &&
                   col_lse_all && col_nll_all && loss && workspace);
@@ -899,7 +1106,7 @@ extern "C" int latte_clip_fwd_cols(const float* gathered, int64_t stride, int wo
   const int nblk_total = (int)((n_all + 127) / 128);
   col_merge_kernel<<<(unsigned)((n_all + 255) / 256), 256, 0, st>>>(
       gathered, stride, world, n_loc, n_all, nblk_total, row_lse_all, row_nll_all, label_logit_all,
-      col_lse_all, col_nll_all, flag);
+      col_lse_all, col_nll_all, flag, nullptr, 0);
   LATTE_LAUNCH_OK();
   // exact fallback (every column, from the gathered features): gated on the flag
   int nparts = clip_tc_nparts(n_all, n_all, device_sm_count());
@@ -913,10 +1120,130 @@ extern "C" int latte_clip_fwd_cols(const float* gathered, int64_t stride, int wo
   int rc = clip_fwd_rows_tc(a, st);
   if (rc) return rc;
   double* lossp = reinterpret_cast<double*>(ws + w.off_lossp);
-  pair_fwd_finish_kernel<<<(unsigned)((n_all + 255) / 256), 256, 0, st>>>(
-      flag, a.part_max, a.part_sum, nparts, n_all, label_logit_all, nullptr, col_lse_all, col_nll_all,
-      row_nll_all, col_nll_all, label_offset, n_loc, lossp, counter, loss);
+  const unsigned fblocks = (unsigned)((n_all + 255) / 256);
+  pair_fwd_finish_kernel<<<fblocks, 256, 0, st>>>(
+      flag, a.part_max, a.part_sum, nparts, n_all, label_logit_all, nullptr, row_lse_all, col_lse_all,
+      col_nll_all, row_nll_all, col_nll_all, label_offset, n_loc, lossp,
+      reinterpret_cast<float*>(lossp + fblocks), counter, loss, stats);
   LATTE_LAUNCH_OK();
+  return LATTE_OK;
+}
+
+// ---- multi-rank forward over peer memory --------------------------------------------------------
+extern "C" int latte_clip_fwd_rank_workspace_bytes(int64_t n_loc, int64_t n_all, int64_t dim, int dtype,
+                                                   size_t* bytes) {
+  LATTE_CHECK_ARG(bytes && n_loc > 0 && n_all >= n_loc && dim > 0);
+  LATTE_CHECK_ARG(dtype >= LATTE_F32 && dtype <= LATTE_F16);
+  *bytes = ws_layout(n_loc, n_all, dim, dtype).total + ws_layout(n_all, n_all, dim, dtype).total;
+  return LATTE_OK;
+}
+
+extern "C" int latte_clip_fwd_rank(const latte_comm_t* comm, const void* img_loc, int64_t ld_img_loc,
+                                   const void* txt_all, int64_t ld_txt_all, int dtype, int64_t n_loc,
+                                   int64_t n_all, int64_t dim, int64_t label_offset,
+                                   const float* logit_scale, float* row_lse_all, float* row_nll_all,
+                                   float* col_lse_all, float* col_nll_all, float* loss, float* stats,
+                                   int phases, void* workspace, size_t workspace_bytes, void* stream) {
+  LATTE_CHECK_ARG(comm_ok(comm) && img_loc && txt_all && logit_scale && row_lse_all && row_nll_all &&
+                  col_lse_all && col_nll_all && loss && workspace);
+  LATTE_CHECK_ARG(n_loc > 0 && n_all == n_loc * comm->world && dim > 0);
+  LATTE_CHECK_ARG(label_offset == (int64_t)comm->rank * n_loc);
+  LATTE_CHECK_ARG(ld_img_loc >= dim && ld_txt_all >= dim);
+  LATTE_CHECK_ARG(comm->payload_stride >= 2 * n_all + 3 * n_loc);
+  if (!pair_shape_ok(dtype, dim) ||
+      !clip_pair_supported(dtype, dim, ld_img_loc, ld_txt_all, img_loc, txt_all) ||
+      !clip_tc_supported(dtype, dim, ld_txt_all, ld_img_loc, txt_all, img_loc))
+    return LATTE_ERR_UNSUPPORTED;
+  const WsLayout wa = ws_layout(n_loc, n_all, dim, dtype);
+  const WsLayout wb = ws_layout(n_all, n_all, dim, dtype);
+  if (workspace_bytes < wa.total + wb.total) return LATTE_ERR_WORKSPACE;
+  if ((reinterpret_cast<uintptr_t>(workspace) & 255) != 0) return LATTE_ERR_BAD_ARG;
+  float* ws = static_cast<float*>(workspace);
+  float* wsb = ws + wa.total / sizeof(float);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int world = comm->world, rank = comm->rank, gen = comm->gen;
+  const int64_t stride = comm->payload_stride;
+  float* my_block = comm->payload[rank];
+  LATTE_CHECK_ARG(my_block != nullptr);
+  float* my_row = my_block + (int64_t)rank * stride;          // col_ml | row_lse | row_nll | label_logit
+  float* exact_block = my_block + (int64_t)world * stride;    // [world][2 n_all]
+  int* my_flags = comm->flags[rank];                          // NULL: no waits / signals (tests)
+  const PeerFlags pflags = comm_flags(comm);
+  PeerPtrs blocks;
+  for (int w = 0; w < LATTE_COMM_MAX_RANKS; ++w) blocks.p[w] = w < world ? comm->payload[w] : nullptr;
+  int* gate = reinterpret_cast<int*>(wsb + wb.off_flag);
+  unsigned int* counter = reinterpret_cast<unsigned int*>(gate + 1);
+  float* label_logit_all = wsb + wb.off_nll_r;                // [n_all] scratch of this layout
+  const PairFwdGeom f = clip_pair_fwd_geom(n_loc, n_all);
+  int nparts = clip_tc_nparts(n_all, n_loc, device_sm_count());
+  if (nparts > kMaxParts) nparts = kMaxParts;
+
+  if (phases & 1) {
+    PairFwdArgs pa;
+    pa.dtype = dtype; pa.n_loc = n_loc; pa.n_all = n_all; pa.dim = dim;
+    pa.label_offset = label_offset; pa.logit_scale = logit_scale;
+    pa.x = img_loc; pa.ldx = ld_img_loc; pa.y = txt_all; pa.ldy = ld_txt_all;
+    pa.part_max = ws + wa.off_pp_max_r; pa.part_sum = ws + wa.off_pp_sum_r; pa.diag = ws + wa.off_diag_r;
+    pa.col_part = ws + wa.off_colpart;
+    pa.col_ref = ws + wa.off_colref;
+    pa.zero2 = gate;                         // clears the exactness flag and the loss counter
+    pa.landed = my_flags ? my_flags + kFlagLandedTxt : nullptr;
+    pa.landed_gen = gen;
+    pa.rows_per_rank = n_loc;
+    int rc = clip_pair_fwd_sweep(pa, st);
+    if (rc) return rc;
+    PairFinalizeArgs fa = {};
+    fa.pmax = pa.part_max; fa.psum = pa.part_sum; fa.n_loc = n_loc; fa.col_tiles = f.col_tiles;
+    fa.total = f.total; fa.ncl = f.ncl; fa.diag = pa.diag; fa.logit_scale = logit_scale;
+    fa.col_ml = my_row;
+    fa.row_lse = my_row + 2 * n_all; fa.row_nll = fa.row_lse + n_loc; fa.label_logit = fa.row_nll + n_loc;
+    fa.col_part = ws + wa.off_colpart; fa.col_ref = ws + wa.off_colref; fa.ld = f.ld_colpart;
+    fa.nblk = 2 * f.row_blocks; fa.n_all = n_all;
+    pair_fwd_finalize_kernel<<<(unsigned)((n_all + 63) / 64), 256, 0, st>>>(fa);
+    LATTE_LAUNCH_OK();
+    const int64_t len = 2 * n_all + 3 * n_loc;
+    comm_payload_kernel<<<(unsigned)((len + 1023) / 1024), 256, 0, st>>>(
+        nullptr, nullptr, nullptr, 0, 0, my_row, len, (int64_t)rank * stride, blocks, pflags, my_flags,
+        world, rank, gen, kFlagPayload, kCntPayload);
+    LATTE_LAUNCH_OK();
+  }
+  if (phases & 2) {
+    const int nblk_total = (int)((n_all + 127) / 128);
+    col_merge_kernel<<<(unsigned)((n_all + 255) / 256), 256, 0, st>>>(
+        my_block, stride, world, n_loc, n_all, nblk_total, row_lse_all, row_nll_all, label_logit_all,
+        col_lse_all, col_nll_all, gate, my_flags ? my_flags + kFlagPayload : nullptr, gen);
+    LATTE_LAUNCH_OK();
+    // Gated second round (the merged statistics, hence the flag, are bit-identical on all ranks):
+    // this rank's column partials again, exactly -- all texts x own images with the row kernel --
+    // and their exchange.  The three kernels return at once when the flag is clear.
+    ClipFwdArgs a;
+    a.dtype = dtype; a.n_loc = n_all; a.n_all = n_loc; a.dim = dim;
+    a.label_offset = n_loc;                  // no label column: the label logits are known already
+    a.logit_scale = logit_scale; a.nparts = nparts; a.gate = gate;
+    a.x = txt_all; a.ldx = ld_txt_all; a.y = img_loc; a.ldy = ld_img_loc;
+    a.part_max = wsb + wb.off_pmax_c; a.part_sum = wsb + wb.off_psum_c; a.diag = wsb + wb.off_diag_c;
+    int rc = clip_fwd_rows_tc(a, st);
+    if (rc) return rc;
+    const int64_t len2 = 2 * n_all;
+    comm_payload_kernel<<<(unsigned)((len2 + 1023) / 1024), 256, 0, st>>>(
+        gate, a.part_max, a.part_sum, nparts, n_all, exact_block + (int64_t)rank * len2, len2,
+        (int64_t)world * stride + (int64_t)rank * len2, blocks, pflags, my_flags, world, rank, gen,
+        kFlagPayload2, kCntPayload2);
+    LATTE_LAUNCH_OK();
+  }
+  if (phases & 4) {
+    col_merge_exact_kernel<<<(unsigned)((n_all + 255) / 256), 256, 0, st>>>(
+        gate, exact_block, world, n_all, label_logit_all, col_lse_all, col_nll_all,
+        my_flags ? my_flags + kFlagPayload2 : nullptr, gen);
+    LATTE_LAUNCH_OK();
+    double* lossp = reinterpret_cast<double*>(wsb + wb.off_lossp);
+    const unsigned fblocks = (unsigned)((n_all + 255) / 256);
+    pair_fwd_finish_kernel<<<fblocks, 256, 0, st>>>(
+        nullptr, nullptr, nullptr, 0, n_all, nullptr, nullptr, row_lse_all, col_lse_all, nullptr,
+        row_nll_all, col_nll_all, label_offset, n_loc, lossp, reinterpret_cast<float*>(lossp + fblocks),
+        counter, loss, stats);
+    LATTE_LAUNCH_OK();
+  }
   return LATTE_OK;
 }
 
@@ -926,28 +1253,42 @@ static int clip_bwd_impl(const void* img_loc, int64_t ld_img_loc, const void* tx
                          int64_t n_all, int64_t dim, int64_t label_offset,
                          const float* logit_scale, const float* row_lse_all,
                          const float* col_lse_all, const float* row_nll_all,
-                         const float* col_nll_all, const float* grad_loss, float grad_mult,
-                         int cross_terms, void* d_img, void* d_txt, int grad_dtype,
-                         int64_t ld_grad, float* d_txt_partial, void* const* d_txt_peers,
-                         int n_peers, float* d_scale, void* workspace,
+                         const float* col_nll_all, const float* lse_stats, const float* grad_loss,
+                         float grad_mult, int cross_terms, void* d_img, void* d_txt, int grad_dtype,
+                         int64_t ld_grad, float* d_txt_partial, const latte_comm_t* comm, int phases,
+                         float* d_scale, void* workspace,
                          size_t workspace_bytes, void* stream, StageTimer* tm) {
-  LATTE_CHECK_ARG(img_loc && txt_loc && img_all && txt_all && logit_scale && row_lse_all &&
-                  col_lse_all && grad_loss && d_img && (d_txt || d_txt_partial || d_txt_peers) &&
+  LATTE_CHECK_ARG(img_loc && txt_loc && txt_all && logit_scale && row_lse_all &&
+                  col_lse_all && grad_loss && d_img && (d_txt || d_txt_partial) &&
                   d_scale && workspace);
-  LATTE_CHECK_ARG(!(d_txt_partial && d_txt_peers));
-  LATTE_CHECK_ARG(!d_txt_peers || (n_peers > 1 && n_peers <= 8 && n_all == n_loc * n_peers));
+  LATTE_CHECK_ARG(!(d_txt_partial && comm));
+  LATTE_CHECK_ARG(!comm || (comm_ok(comm) && n_all == n_loc * comm->world && d_txt &&
+                            comm->acc[comm->rank] && (dim % 4) == 0));
   LATTE_CHECK_ARG((row_nll_all == nullptr) == (col_nll_all == nullptr));
   LATTE_CHECK_ARG(n_loc > 0 && n_all >= n_loc && dim > 0);
   LATTE_CHECK_ARG(label_offset >= 0 && label_offset + n_loc <= n_all);
   LATTE_CHECK_ARG(dtype >= LATTE_F32 && dtype <= LATTE_F16);
   LATTE_CHECK_ARG(grad_dtype >= LATTE_F32 && grad_dtype <= LATTE_F16);
-  LATTE_CHECK_ARG(ld_img_loc >= dim && ld_txt_loc >= dim && ld_img_all >= dim && ld_txt_all >= dim &&
-                  ld_grad >= dim);
+  LATTE_CHECK_ARG(ld_img_loc >= dim && ld_txt_loc >= dim && ld_txt_all >= dim && ld_grad >= dim);
+  // one-sweep multi-rank modes (fp32 partial for a reduce-scatter, or peer accumulators) read only
+  // this rank's images: img_all may be NULL there
+  const bool one_sweep = (d_txt_partial != nullptr || comm != nullptr) && cross_terms;
+  if ((d_txt_partial || comm) && !one_sweep) return LATTE_ERR_BAD_ARG;
+  if (!one_sweep) LATTE_CHECK_ARG(img_all && ld_img_all >= dim);
+  if (one_sweep) { img_all = img_loc; ld_img_all = ld_img_loc; }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (comm && !(phases & 1)) {
+    // second phase only (single-process tests drive the ranks phase by phase)
+    comm_acc_finish_kernel<<<(unsigned)(2 * device_sm_count()), 256, 0, st>>>(
+        comm->acc[comm->rank], n_loc, dim, d_txt, grad_dtype, ld_grad, comm_flags(comm),
+        comm->flags[comm->rank], comm->world, comm->rank, comm->gen);
+    LATTE_LAUNCH_OK();
+    return LATTE_OK;
+  }
   const WsLayout w = ws_layout(n_loc, n_all, dim, dtype, true);
   if (workspace_bytes < w.total) return LATTE_ERR_WORKSPACE;
   if ((reinterpret_cast<uintptr_t>(workspace) & 255) != 0) return LATTE_ERR_BAD_ARG;
   float* ws = static_cast<float*>(workspace);
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
 
   float* row2 = ws + w.off_row2;
   float* col2 = ws + w.off_col2;
@@ -961,35 +1302,66 @@ static int clip_bwd_impl(const void* img_loc, int64_t ld_img_loc, const void* tx
       w.pair && clip_pair_supported(dtype, dim, ld_img_loc, ld_txt_all, img_loc, txt_all) &&
       clip_pair_supported(dtype, dim, ld_txt_loc, ld_img_all, txt_loc, img_all) &&
       clip_pair_supported(dtype, dim, ld_img_all, ld_txt_all, img_all, txt_all);
-  // bf16 features feed the gradient GEMMs directly (A = fp16 G, B = bf16 features); fp16 copies are
-  // only made when LATTE_B200_FP16_COPIES=1 asks for the round-1 operand format
-  const bool copies16 = pair_ok && dtype == LATTE_BF16 && want_fp16_copies();
+  if (one_sweep && !pair_ok) return LATTE_ERR_UNSUPPORTED;
+  // G is fp16 (a bf16 G would cost 2^-9 per weight) and tcgen05.mma kind::f16 wants A and B in ONE
+  // 16-bit format (an fp16 x bf16 instruction descriptor raises "illegal instruction" on sm_100a,
+  // measured in round 2), so bf16 features get fp16 copies for the gradient GEMMs; fp16 features
+  // are used as they are
+  const bool copies16 = pair_ok && dtype == LATTE_BF16;
   const bool have_nll = row_nll_all != nullptr;
+  const bool have_bound = have_nll || lse_stats != nullptr;
+  __half* ya = reinterpret_cast<__half*>(ws + w.off_y16a);                               // txt_all
+  __half* yb = (!one_sweep && img_all == txt_all) ? ya : reinterpret_cast<__half*>(ws + w.off_y16b);
   if (pair_ok) {
-    // bound on |G| -> fp16 scale of G: from the per-sample loss terms when the caller has them,
-    // else from the label logits (one pass over the gathered features)
-    if (copies16 || !have_nll) {
+    // bound on |G| -> fp16 scale of G: from the forward's statistics or per-sample loss terms when
+    // the caller has them, else from the label logits (one pass over the gathered features;
+    // one-sweep modes without either use the bound 1)
+    const bool dots = !have_bound && !one_sweep;
+    if (dots) {
       LATTE_CUDA_OK(cudaMemsetAsync(u_bits, 0, sizeof(unsigned int), st));
-      __half* ya = copies16 ? reinterpret_cast<__half*>(ws + w.off_y16a) : nullptr;      // txt
-      __half* yb = !copies16 ? nullptr
-                             : (img_all == txt_all ? ya : reinterpret_cast<__half*>(ws + w.off_y16b));
       const int64_t warps_needed = n_all;
       const unsigned blocks = (unsigned)((warps_needed * 32 + 255) / 256 < 4096
                                              ? (warps_needed * 32 + 255) / 256 : 4096);
       pair_prep_features_kernel<<<blocks, 256, 0, st>>>(img_all, ld_img_all, txt_all, ld_txt_all,
-                                                        dtype == LATTE_BF16 ? 1 : 0, yb, ya,
+                                                        dtype == LATTE_BF16 ? 1 : 0,
+                                                        copies16 ? yb : nullptr, copies16 ? ya : nullptr,
                                                         (int64_t)w.ld16, n_all, dim, logit_scale,
                                                         row_lse_all, col_lse_all, u_bits);
       LATTE_LAUNCH_OK();
+    } else if (copies16) {
+      // pure conversions: all gathered texts, and the images the GEMMs read (this rank's rows in
+      // the one-sweep modes, all of them otherwise)
+      const int64_t img_rows = one_sweep ? n_loc : n_all;
+      const int64_t per_row = (dim + 7) / 8;
+      if (!one_sweep && ld_img_all == ld_txt_all) {
+        const bool same = img_all == txt_all;
+        bf16_to_fp16_kernel<<<dim3((unsigned)((n_all * per_row + 255) / 256), same ? 1 : 2), 256, 0, st>>>(
+            static_cast<const __nv_bfloat16*>(txt_all), ya, static_cast<const __nv_bfloat16*>(img_all),
+            yb, ld_txt_all, (int64_t)w.ld16, n_all, dim);
+        LATTE_LAUNCH_OK();
+      } else {
+        bf16_to_fp16_kernel<<<dim3((unsigned)((n_all * per_row + 255) / 256), 1), 256, 0, st>>>(
+            static_cast<const __nv_bfloat16*>(txt_all), ya, nullptr, nullptr, ld_txt_all,
+            (int64_t)w.ld16, n_all, dim);
+        LATTE_LAUNCH_OK();
+        bf16_to_fp16_kernel<<<dim3((unsigned)((img_rows * per_row + 255) / 256), 1), 256, 0, st>>>(
+            static_cast<const __nv_bfloat16*>(img_all), yb, nullptr, nullptr, ld_img_all,
+            (int64_t)w.ld16, img_rows, dim);
+        LATTE_LAUNCH_OK();
+      }
     }
-    lse_range_kernel<<<1, 1024, 0, st>>>(row_lse_all, col_lse_all, n_all, rho, fast_flag, u_bits,
-                                         have_nll ? row_nll_all : nullptr,
-                                         have_nll ? col_nll_all : nullptr, gscale, grad_loss,
-                                         grad_mult, logit_scale, n_loc, out_scale);
-    LATTE_LAUNCH_OK();
+    if (!lse_stats) {
+      float* st_buf = ws + w.off_rho + 8;
+      lse_stats_kernel<<<1, 1024, 0, st>>>(row_lse_all, col_lse_all, n_all, dots ? u_bits : nullptr,
+                                           have_nll ? row_nll_all : nullptr,
+                                           have_nll ? col_nll_all : nullptr, st_buf);
+      LATTE_LAUNCH_OK();
+      lse_stats = st_buf;
+    }
   }
   lse_vectors_kernel<<<(unsigned)((w.n_pad + 255) / 256), 256, 0, st>>>(
-      row_lse_all, col_lse_all, n_all, (int64_t)w.n_pad, rho, row2, col2,
+      row_lse_all, col_lse_all, n_all, (int64_t)w.n_pad, pair_ok ? lse_stats : nullptr, grad_loss,
+      grad_mult, logit_scale, n_loc, rho, row2, col2,
       pair_ok ? ws + w.off_erow : nullptr, ws + w.off_einvrow, ws + w.off_ecol, ws + w.off_einvcol);
   LATTE_LAUNCH_OK();
 
@@ -1001,20 +1373,14 @@ static int clip_bwd_impl(const void* img_loc, int64_t ld_img_loc, const void* tx
   // fp16 operands for the second GEMM of the tc path
   const void* txt16 = txt_all; int64_t ld_txt16 = ld_txt_all;
   const void* img16 = img_all; int64_t ld_img16 = ld_img_all;
-  if (pair_ok && dtype == LATTE_BF16 && !copies16) {
-    // mixed-format MMA: the bf16 features are the GEMM operands as they are
-  } else if (pair_ok && dtype == LATTE_BF16) {
-    txt16 = ws + w.off_y16a; ld_txt16 = (int64_t)w.ld16;
-    img16 = img_all == txt_all ? txt16 : static_cast<const void*>(ws + w.off_y16b);
-    ld_img16 = (int64_t)w.ld16;
+  if (pair_ok && dtype == LATTE_BF16) {
+    txt16 = ya; ld_txt16 = (int64_t)w.ld16;
+    img16 = yb; ld_img16 = (int64_t)w.ld16;
   } else if (tc && dtype == LATTE_BF16) {
-    __half* ya = reinterpret_cast<__half*>(ws + w.off_y16a);
-    __half* yb = reinterpret_cast<__half*>(ws + w.off_y16b);
     const int64_t work = n_all * ((dim + 7) / 8);
     const unsigned blocks = (unsigned)((work + 255) / 256);
     const bool same = img_all == txt_all;
     if (same || ld_img_all == ld_txt_all) {
-      if (same) yb = ya;
       bf16_to_fp16_kernel<<<dim3(blocks, same ? 1 : 2), 256, 0, st>>>(
           static_cast<const __nv_bfloat16*>(txt_all), ya, static_cast<const __nv_bfloat16*>(img_all),
           yb, ld_txt_all, (int64_t)w.ld16, n_all, dim);
@@ -1043,11 +1409,12 @@ static int clip_bwd_impl(const void* img_loc, int64_t ld_img_loc, const void* tx
     float* acc_t = ws + w.off_acc1;
     const size_t acc_bytes = (size_t)n_loc * w.ld32 * sizeof(float);
     LATTE_CUDA_OK(cudaMemsetAsync(dsp, 0, (size_t)2 * dsn * sizeof(float), st));
-    const bool single = n_loc == n_all && img_loc == img_all && txt_loc == txt_all && cross_terms;
-    // one sweep per rank: the text-side product G^T . img_loc is returned as an fp32 partial
-    // over ALL columns for the caller to reduce-scatter (loss.py:49-50's backward)
-    const bool rank_sweep = !single && (d_txt_partial != nullptr || d_txt_peers != nullptr) && cross_terms;
-    if ((d_txt_partial || d_txt_peers) && !rank_sweep) return LATTE_ERR_BAD_ARG;
+    const bool single = !one_sweep && n_loc == n_all && img_loc == img_all && txt_loc == txt_all &&
+                        cross_terms;
+    // one sweep per rank: the text-side product G^T . img_loc covers ALL columns; it is returned as
+    // an fp32 partial for the caller to reduce-scatter, or added into the owners' accumulators
+    // over NVLink from the GEMM epilogue (loss.py:49-50's backward)
+    const bool rank_sweep = one_sweep;
     if (!rank_sweep && !d_txt) return LATTE_ERR_BAD_ARG;
     PairSweepArgs sa;
     sa.dtype = dtype; sa.n_loc = n_loc; sa.n_all = n_all; sa.dim = dim;
@@ -1056,7 +1423,7 @@ static int clip_bwd_impl(const void* img_loc, int64_t ld_img_loc, const void* tx
     sa.nll_a = row_nll_all; sa.nll_b = col_nll_all;
     PairGemmArgs ga = {};
     ga.g = gbuf; ga.n_loc = n_loc; ga.n_all = n_all; ga.dim = dim; ga.ld32 = (int64_t)w.ld32;
-    ga.feat_dtype = copies16 ? LATTE_F16 : dtype;
+    ga.feat_dtype = LATTE_F16;
     // Gradients of tiles owned by one cluster are written by the GEMM epilogue itself (scaled, in
     // the gradient dtype); the fp32 accumulators only serve the tiles the schedule splits.
     ga.out_dtype = grad_dtype; ga.ld_out = ld_grad; ga.out_scale = out_scale;
@@ -1072,15 +1439,22 @@ static int clip_bwd_impl(const void* img_loc, int64_t ld_img_loc, const void* tx
     ga.dy_peers = nullptr; ga.n_peers = 0;
     ga.dx_out = d_img; ga.dy_out = single ? d_txt : nullptr;
     if (rank_sweep) {
-      // rows [label_offset, label_offset + n_loc) of the gathered features are this rank's
-      ga.x16 = static_cast<const uint16_t*>(img16) + label_offset * ld_img16;
+      ga.x16 = img16;                       // this rank's images (fp16 copy or the features themselves)
       ga.dy32 = d_txt_partial; ga.ld_dy32 = dim; ga.dy_scale = out_scale;
-      if (d_txt_peers) {
-        ga.dy32 = static_cast<float*>(d_txt_peers[0]);       // unused: every row has an owner
-        ga.dy_peers = reinterpret_cast<float* const*>(d_txt_peers);
-        ga.n_peers = n_peers;
+      if (comm) {
+        ga.dy32 = comm->acc[comm->rank];                     // unused: every row has an owner
+        ga.dy_peers = comm->acc;
+        ga.n_peers = comm->world;
+        // the GEMM publishes done = gen on every rank once all its adds are out
+        ga.n_done = comm->flags[comm->rank] ? comm->world : 0;
+        for (int q = 0; q < comm->world; ++q)
+          ga.done_flags[q] = comm->flags[q] ? comm->flags[q] + kFlagDone : nullptr;
+        ga.done_counter = comm->flags[comm->rank]
+                              ? reinterpret_cast<unsigned int*>(comm->flags[comm->rank] + kFlagCounter + kCntGemm)
+                              : nullptr;
+        ga.done_gen = comm->gen;
+        ga.done_slot = comm->rank;
       }
-      // peer accumulators are zeroed (and fenced by a cross-rank barrier) by the caller
       if (d_txt_partial)
         LATTE_CUDA_OK(cudaMemsetAsync(d_txt_partial, 0, (size_t)n_all * (size_t)dim * sizeof(float), st));
     }
@@ -1141,11 +1515,17 @@ static int clip_bwd_impl(const void* img_loc, int64_t ld_img_loc, const void* tx
     }
     ds_reduce_kernel<<<1, 256, 0, st>>>(dsp, 2 * dsn, grad_loss, grad_mult, n_loc, d_scale);
     LATTE_LAUNCH_OK();
+    if (comm && (phases & 2)) {
+      comm_acc_finish_kernel<<<(unsigned)(2 * device_sm_count()), 256, 0, st>>>(
+          comm->acc[comm->rank], n_loc, dim, d_txt, grad_dtype, ld_grad, comm_flags(comm),
+          comm->flags[comm->rank], comm->world, comm->rank, comm->gen);
+      LATTE_LAUNCH_OK();
+    }
     LATTE_MARK(LATTE_STAGE_BWD_FINISH);
     return LATTE_OK;
   }
   LATTE_MARK(LATTE_STAGE_BWD_PREP);
-  if (d_txt_partial || d_txt_peers || !d_txt) return LATTE_ERR_UNSUPPORTED;
+  if (d_txt_partial || comm || !d_txt) return LATTE_ERR_UNSUPPORTED;
 
   ClipBwdArgs a;
   a.dtype = dtype; a.n_loc = n_loc; a.n_all = n_all; a.dim = dim;
@@ -1177,15 +1557,17 @@ extern "C" int latte_clip_bwd(const void* img_loc, int64_t ld_img_loc, const voi
                               int64_t n_all, int64_t dim, int64_t label_offset,
                               const float* logit_scale, const float* row_lse_all,
                               const float* col_lse_all, const float* row_nll_all,
-                              const float* col_nll_all, const float* grad_loss, float grad_mult,
+                              const float* col_nll_all, const float* lse_stats,
+                              const float* grad_loss, float grad_mult,
                               int cross_terms, void* d_img, void* d_txt, int grad_dtype,
-                              int64_t ld_grad, float* d_txt_partial, void* const* d_txt_peers,
-                              int n_peers, float* d_scale, void* workspace,
+                              int64_t ld_grad, float* d_txt_partial, const latte_comm_t* comm,
+                              int phases, float* d_scale, void* workspace,
                               size_t workspace_bytes, void* stream) {
   return clip_bwd_impl(img_loc, ld_img_loc, txt_loc, ld_txt_loc, img_all, ld_img_all, txt_all,
                        ld_txt_all, dtype, n_loc, n_all, dim, label_offset, logit_scale, row_lse_all,
-                       col_lse_all, row_nll_all, col_nll_all, grad_loss, grad_mult, cross_terms, d_img,
-                       d_txt, grad_dtype, ld_grad, d_txt_partial, d_txt_peers, n_peers, d_scale,
+                       col_lse_all, row_nll_all, col_nll_all, lse_stats, grad_loss, grad_mult,
+                       cross_terms, d_img,
+                       d_txt, grad_dtype, ld_grad, d_txt_partial, comm, phases, d_scale,
                        workspace, workspace_bytes, stream, nullptr);
 }
 
@@ -1208,6 +1590,9 @@ extern "C" int latte_clip_stage_times(const void* img_loc, int64_t ld_img_loc, c
   for (int r = 0; r < reps; ++r) {
     StageTimer tm;
     int rc;
+    float* nll_r = nullptr;
+    float* nll_c = nullptr;
+    float* stats = nullptr;
     if (d_txt_partial) {
       // one-sweep multi-rank flow: step 1 of the forward (the merge step after the all-gather
       // is a few microseconds and is not timed here); its outputs land in the legacy partial
@@ -1220,17 +1605,25 @@ extern "C" int latte_clip_stage_times(const void* img_loc, int64_t ld_img_loc, c
                               label_offset, logit_scale, tmp, tmp + n_loc, tmp + 2 * n_loc,
                               tmp + 3 * n_loc, fwd_workspace, fwd_workspace_bytes, stream, &tm);
     } else {
+      // like the product path: the forward hands its per-sample loss terms and LSE statistics to
+      // the backward (one rank: they describe every row and column)
+      const WsLayout wl = ws_layout(n_loc, n_all, dim, dtype);
+      if (fwd_workspace_bytes < wl.total) return LATTE_ERR_WORKSPACE;
+      float* fws = static_cast<float*>(fwd_workspace);
+      if (n_loc == n_all && wl.pair_fwd) {
+        nll_r = fws + wl.off_nll_r; nll_c = fws + wl.off_nll_c; stats = fws + wl.off_flag + 8;
+      }
       rc = clip_fwd_impl(img_loc, ld_img_loc, txt_loc, ld_txt_loc, img_all, ld_img_all, txt_all,
                          ld_txt_all, dtype, n_loc, n_all, dim, label_offset, logit_scale, row_lse,
-                         col_lse, nullptr, nullptr, loss, fwd_workspace, fwd_workspace_bytes, stream,
+                         col_lse, nll_r, nll_c, loss, stats, fwd_workspace, fwd_workspace_bytes, stream,
                          &tm);
     }
     if (rc == LATTE_OK)
       rc = clip_bwd_impl(img_loc, ld_img_loc, txt_loc, ld_txt_loc, img_all, ld_img_all, txt_all,
                          ld_txt_all, dtype, n_loc, n_all, dim, label_offset, logit_scale,
-                         row_lse_all, col_lse_all, nullptr, nullptr, grad_loss, grad_mult, cross_terms,
-                         d_img, d_txt, grad_dtype, ld_grad, d_txt_partial, nullptr, 0, d_scale,
-                         bwd_workspace, bwd_workspace_bytes, stream, &tm);
+                         row_lse_all, col_lse_all, nll_r, nll_c, stats, grad_loss, grad_mult,
+                         cross_terms, d_img, d_txt, grad_dtype, ld_grad, d_txt_partial, nullptr, 3,
+                         d_scale, bwd_workspace, bwd_workspace_bytes, stream, &tm);
     const cudaError_t e = cudaStreamSynchronize(st);
     tm.collect(stage_ms);
     if (rc) return rc;
@@ -1240,34 +1633,43 @@ extern "C" int latte_clip_stage_times(const void* img_loc, int64_t ld_img_loc, c
   return LATTE_OK;
 }
 
-extern "C" int latte_push_shards(const void* img_shard, const void* txt_shard, int64_t shard_bytes,
-                                 void* const* peer_bases, int n_peers, int rank,
-                                 int64_t tensor_stride_bytes, void* multicast_base, void* stream) {
-  LATTE_CHECK_ARG(img_shard && txt_shard && peer_bases && n_peers >= 1 && n_peers <= 8);
-  LATTE_CHECK_ARG(rank >= 0 && rank < n_peers && shard_bytes > 0 && (shard_bytes % 16) == 0);
-  LATTE_CHECK_ARG((tensor_stride_bytes % 16) == 0 && tensor_stride_bytes >= shard_bytes * n_peers);
-  LATTE_CHECK_ARG((reinterpret_cast<uintptr_t>(img_shard) & 15) == 0 &&
-                  (reinterpret_cast<uintptr_t>(txt_shard) & 15) == 0);
-  uint4* p[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-  for (int k = 0; k < n_peers; ++k) {
-    LATTE_CHECK_ARG(peer_bases[k] && (reinterpret_cast<uintptr_t>(peer_bases[k]) & 15) == 0);
-    p[k] = static_cast<uint4*>(peer_bases[k]);
+extern "C" int latte_comm_push(const latte_comm_t* comm, const void* txt_shard, const void* img_shard,
+                               int64_t shard_bytes, int64_t tensor_stride_bytes, void* stream) {
+  LATTE_CHECK_ARG(comm_ok(comm) && txt_shard && shard_bytes > 0 && (shard_bytes % 16) == 0);
+  LATTE_CHECK_ARG((tensor_stride_bytes % 16) == 0 && tensor_stride_bytes >= shard_bytes * comm->world);
+  LATTE_CHECK_ARG((reinterpret_cast<uintptr_t>(txt_shard) & 15) == 0 &&
+                  (reinterpret_cast<uintptr_t>(img_shard) & 15) == 0);
+  PeerPtrs dst;
+  for (int w = 0; w < LATTE_COMM_MAX_RANKS; ++w) {
+    dst.p[w] = w < comm->world ? comm->gather[w] : nullptr;
+    if (w < comm->world)
+      LATTE_CHECK_ARG(dst.p[w] && (reinterpret_cast<uintptr_t>(dst.p[w]) & 15) == 0);
   }
+  const PeerFlags flags = comm_flags(comm);
+  int* my_flags = comm->flags[comm->rank];
   const int64_t shard_vecs = shard_bytes / 16;
-  int64_t blocks = (2 * shard_vecs + 255) / 256;
+  int64_t blocks = (shard_vecs + 255) / 256;
   if (blocks > 4 * device_sm_count()) blocks = 4 * device_sm_count();
-  if (multicast_base) {
-    LATTE_CHECK_ARG((reinterpret_cast<uintptr_t>(multicast_base) & 15) == 0);
-    push_shards_multicast_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        static_cast<const uint4*>(img_shard), static_cast<const uint4*>(txt_shard), shard_vecs,
-        tensor_stride_bytes / 16, (int64_t)rank * shard_vecs, static_cast<uint4*>(multicast_base));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // the text matrix first: it is what the forward sweep waits for
+  comm_push_kernel<<<(unsigned)blocks, 256, 0, st>>>(
+      static_cast<const uint4*>(txt_shard), shard_vecs,
+      tensor_stride_bytes / 16 + (int64_t)comm->rank * shard_vecs, dst, flags, my_flags, comm->world,
+      comm->rank, comm->gen, kFlagLandedTxt, kCntPush);
+  LATTE_LAUNCH_OK();
+  if (img_shard) {
+    comm_push_kernel<<<(unsigned)blocks, 256, 0, st>>>(
+        static_cast<const uint4*>(img_shard), shard_vecs, (int64_t)comm->rank * shard_vecs, dst, flags,
+        my_flags, comm->world, comm->rank, comm->gen, kFlagLandedImg, kCntPushImg);
     LATTE_LAUNCH_OK();
-    return LATTE_OK;
   }
-  push_shards_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const uint4*>(img_shard), static_cast<const uint4*>(txt_shard), shard_vecs,
-      tensor_stride_bytes / 16, (int64_t)rank * shard_vecs, p[0], p[1], p[2], p[3], p[4], p[5], p[6],
-      p[7], n_peers);
+  return LATTE_OK;
+}
+
+extern "C" int latte_comm_release(const latte_comm_t* comm, void* stream) {
+  LATTE_CHECK_ARG(comm_ok(comm));
+  comm_release_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(comm_flags(comm), comm->world,
+                                                                      comm->rank, comm->gen);
   LATTE_LAUNCH_OK();
   return LATTE_OK;
 }

@@ -93,6 +93,12 @@ struct SweepParams {
   float* col_ref;                    // [2 * row_blocks, 4 * col_tiles]  (one per 32 columns)
   int64_t ld_colpart;
   int* zero2;                        // nullable: two ints cleared by the first CTA (forward modes)
+  // Multi-rank: y is a gathered buffer whose shard of rank w (rows [w * rows_per_rank, ...)) is
+  // written by rank w's push kernel; `landed[w] >= landed_gen` (a flag in this GPU's memory, set
+  // by rank w after its stores) says the shard may be read.  NULL: y is complete at launch.
+  const int* landed;
+  int landed_gen;
+  int64_t rows_per_rank;
   int kch;                           // ceil(dim / 64)
   int cps;                           // feature chunks per ring stage (4, or 2 with an X tail)
   int tail_chunks;                   // chunks of X beyond the 8 held in TMEM (dim > 512): smem
@@ -244,7 +250,22 @@ pair_sweep_kernel(const __grid_constant__ CUtensorMap tmy, const __grid_constant
       uint32_t phase = 0;
       const uint32_t lead_xt = mapa_rank(bar_xt, 0);
       int ct = ct0, rb_i = rb0;
+      uint32_t landed_mask = p.landed ? 0u : 0xffffffffu;     // ranks whose shard is known to be here
       for (int it = 0; it < ntile; ++it) {
+        if (landed_mask != 0xffffffffu) {
+          // owners of this tile's rows of y (a tile can straddle two shards)
+          const int64_t r_first = (int64_t)ct * kTN;
+          const int64_t r_last = min(r_first + kTN, p.n_all) - 1;
+          if (r_first < p.n_all) {
+            const int w0 = (int)(r_first / p.rows_per_rank), w1 = (int)(r_last / p.rows_per_rank);
+            for (int w = w0; w <= w1; ++w)
+              if (!((landed_mask >> w) & 1u)) {
+                flag_wait_ge(p.landed + w, p.landed_gen);
+                landed_mask |= 1u << w;
+              }
+            fence_proxy_async_all();
+          }
+        }
         if (TAIL && (it == 0 || ct == 0)) {
           // new row block: its X tail replaces the previous one once every MMA of the
           // previous block is done (tfull of its last tile)
@@ -966,6 +987,13 @@ struct GemmParams {
   int nprob;
   int ncb;             // G block columns
   int dim;
+  // fused reduce-scatter: when every add of the launch is out, the last CTA publishes
+  // done_flags[w][done_slot] = done_gen on every rank w (n_done = 0: no signal)
+  int* done_flags[8];
+  int n_done;
+  unsigned int* done_counter;
+  int done_gen;
+  int done_slot;
 };
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
@@ -1180,11 +1208,21 @@ pair_gemm_kernel(const __grid_constant__ CUtensorMap tma0, const __grid_constant
           tmem_ld_32x32(tmem_base + lane_base + col, v);
           tmem_ld_wait();
           if (m_ok) {
+            if (pr.npeers > 0) {           // peer memory: the adds of several GPUs meet here
 #pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              if (pr.d_off + col + i < p.dim)
-                red_add_v4(orow + pr.d_off + col + i, osc * __uint_as_float(v[i]), osc * __uint_as_float(v[i + 1]),
-                           osc * __uint_as_float(v[i + 2]), osc * __uint_as_float(v[i + 3]));
+              for (int i = 0; i < 32; i += 4) {
+                if (pr.d_off + col + i < p.dim)
+                  red_add_v4_sys(orow + pr.d_off + col + i, osc * __uint_as_float(v[i]),
+                                 osc * __uint_as_float(v[i + 1]), osc * __uint_as_float(v[i + 2]),
+                                 osc * __uint_as_float(v[i + 3]));
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; i += 4) {
+                if (pr.d_off + col + i < p.dim)
+                  red_add_v4(orow + pr.d_off + col + i, osc * __uint_as_float(v[i]), osc * __uint_as_float(v[i + 1]),
+                             osc * __uint_as_float(v[i + 2]), osc * __uint_as_float(v[i + 3]));
+              }
             }
           }
         }
@@ -1196,9 +1234,18 @@ pair_gemm_kernel(const __grid_constant__ CUtensorMap tma0, const __grid_constant
     }
   }
 
+  // every thread's peer adds are ordered before the cluster barrier; one thread per CTA then counts
+  if (p.n_done > 0 && warp >= kEpiWarp0) __threadfence_system();
   tc_fence_before();
   cluster_sync_all();
   if (warp == 2) tmem_dealloc_pair(tmem_base, 512);
+  if (p.n_done > 0 && threadIdx.x == 0) {
+    if (atomicInc(p.done_counter, gridDim.x - 1) == gridDim.x - 1) {
+      __threadfence_system();
+      for (int w = 0; w < p.n_done; ++w)
+        if (p.done_flags[w]) st_release_sys(p.done_flags[w] + p.done_slot, p.done_gen);
+    }
+  }
 }
 
 // Tiles that the stream-K schedule splits between clusters go through the fp32 accumulators:
@@ -1222,6 +1269,8 @@ struct FixupParams {
   int dim;
 };
 
+constexpr int kFixSplit = 8;      // CTAs per tile (32 rows each)
+
 template <int MODE>
 __global__ void __launch_bounds__(256) gemm_fixup_kernel(const FixupParams p) {
   int pi = 0, t = blockIdx.x;
@@ -1233,8 +1282,10 @@ __global__ void __launch_bounds__(256) gemm_fixup_kernel(const FixupParams p) {
   const int c0 = p.d_off[pi];
   const int c1 = min(p.dim, c0 + p.ncols[pi]);
   const int per_row = (c1 - c0) / 4;
-  const int64_t r0 = (int64_t)t * 256;
-  const int rows = (int)min((int64_t)256, p.m_rows[pi] - r0);
+  constexpr int kRowsPerCta = 256 / kFixSplit;
+  const int64_t r0 = (int64_t)t * 256 + (int64_t)blockIdx.y * kRowsPerCta;
+  const int rows = (int)min((int64_t)kRowsPerCta, p.m_rows[pi] - r0);
+  if (rows <= 0) return;
   const float cs = MODE == kFixCast ? __ldg(p.out_scale) : 0.f;
   for (int idx = threadIdx.x; idx < rows * per_row; idx += 256) {
     const int64_t r = r0 + idx / per_row;
@@ -1243,7 +1294,7 @@ __global__ void __launch_bounds__(256) gemm_fixup_kernel(const FixupParams p) {
     if (MODE == kFixZero) {
       *a = make_float4(0.f, 0.f, 0.f, 0.f);
     } else {
-      const float4 v = *a;
+      const float4 v = __ldcs(a);
       const float o[4] = {v.x * cs, v.y * cs, v.z * cs, v.w * cs};
       if (p.out_dtype == LATTE_F32) {
         *reinterpret_cast<float4*>(static_cast<float*>(p.out[pi]) + r * p.ld_out + c) =
@@ -1402,6 +1453,8 @@ int clip_pair_fwd_sweep(const PairFwdArgs& a, cudaStream_t stream) {
   p.part_max = a.part_max; p.part_sum = a.part_sum; p.diag = a.diag;
   p.col_part = a.col_part; p.col_ref = a.col_ref; p.ld_colpart = f.ld_colpart;
   p.zero2 = a.zero2;
+  p.landed = a.landed; p.landed_gen = a.landed_gen;
+  p.rows_per_rank = a.rows_per_rank > 0 ? a.rows_per_rank : a.n_all;
   p.kch = (int)((a.dim + kBK - 1) / kBK);
   p.tail_chunks = p.kch > kTmemChunks ? p.kch - kTmemChunks : 0;
   p.cps = p.tail_chunks ? 2 : kChunksPerStage;
@@ -1515,9 +1568,7 @@ int build_gemm_problems(const PairGemmArgs& a, GemmParams& p, int64_t& total, in
   const int nslab = (units128 + 3) / 4;
   const int nproducts = a.x16 ? 2 : 1;
   if (a.dy_peers && a.n_peers > 8) return LATTE_ERR_UNSUPPORTED;
-  // the B operand (features) may be bf16 while A (G) is fp16: kind::f16 takes the two formats
-  // independently
-  const uint32_t bfmt = a.feat_dtype == LATTE_BF16 ? 1u : 0u;
+  if (a.feat_dtype != LATTE_F16) return LATTE_ERR_UNSUPPORTED;   // A (= G) is fp16: one format per MMA
   // direct stores need 16-byte vectors on the output rows
   const bool direct_ok = a.out_scale != nullptr && (a.ld_out % 8) == 0;
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
@@ -1534,7 +1585,7 @@ int build_gemm_problems(const PairGemmArgs& a, GemmParams& p, int64_t& total, in
       done += nh;
       for (int g = 0; g < 2; ++g) {
         const int cnt = nh - 2 * g >= 2 ? 2 : (nh - 2 * g == 1 ? 1 : 0);
-        q.idesc[g] = cnt ? make_idesc_ab(256, 2 * cnt * 64, 0u, bfmt, prod, 1) : 0u;
+        q.idesc[g] = cnt ? make_idesc_f16(256, 2 * cnt * 64, 0u, prod, 1) : 0u;
       }
       q.scale = nullptr;
       q.npeers = 0;
@@ -1573,6 +1624,12 @@ int build_gemm_problems(const PairGemmArgs& a, GemmParams& p, int64_t& total, in
   }
   ncl = device_sm_count() / 2;
   if (total < ncl) ncl = (int)total;
+  p.n_done = a.dy_peers ? a.n_done : 0;
+  for (int w = 0; w < 8; ++w) p.done_flags[w] = w < p.n_done ? a.done_flags[w] : nullptr;
+  p.done_counter = a.done_counter;
+  p.done_gen = a.done_gen;
+  p.done_slot = a.done_slot;
+  if (p.n_done > 0 && !p.done_counter) return LATTE_ERR_BAD_ARG;
   return LATTE_OK;
 }
 }  // namespace
@@ -1628,8 +1685,8 @@ int clip_pair_gemm_fixup(const PairGemmArgs& a, int cast, cudaStream_t stream) {
     tiles += q.m_tiles;
   }
   if (!any || tiles == 0) return LATTE_OK;
-  if (cast) gemm_fixup_kernel<kFixCast><<<tiles, 256, 0, stream>>>(f);
-  else gemm_fixup_kernel<kFixZero><<<tiles, 256, 0, stream>>>(f);
+  if (cast) gemm_fixup_kernel<kFixCast><<<dim3(tiles, kFixSplit), 256, 0, stream>>>(f);
+  else gemm_fixup_kernel<kFixZero><<<dim3(tiles, kFixSplit), 256, 0, stream>>>(f);
   LATTE_LAUNCH_OK();
   return LATTE_OK;
 }

@@ -132,7 +132,7 @@ struct PairGemmArgs {
   const float* dy_scale;            // nullable device scalar multiplied into dy32's partials
   float* const* dy_peers;           // nullable HOST array: per-rank accumulators [n_all / n_peers, ld_dy32]
   int n_peers;                      //   (peer-mapped); rows of dy go to their owner rank instead of dy32
-  int feat_dtype;                   // LATTE_F16 or LATTE_BF16: element type of y16 / x16 (G itself is fp16)
+  int feat_dtype;                   // element type of y16 / x16: LATTE_F16 (G is fp16; kind::f16 needs one format)
   // Direct outputs (nullable): tiles owned by one cluster are written as out_scale * acc in out_dtype
   // straight from the GEMM epilogue; dx32 / dy32 then only serve the tiles split between clusters
   // (clip_pair_gemm_fixup before and after the GEMM).  dy_out is ignored with dy_scale / dy_peers.
@@ -141,6 +141,13 @@ struct PairGemmArgs {
   int out_dtype;
   int64_t ld_out;
   const float* out_scale;
+  // With dy_peers: once every add of the launch is out (last CTA), done_flags[w][done_slot] = done_gen
+  // is published on every rank w (system-scope release); n_done = 0 switches the signal off.
+  int* done_flags[8];
+  int n_done;
+  unsigned int* done_counter;
+  int done_gen;
+  int done_slot;
 };
 // Forward on the same sweep: rows dealt to clusters as contiguous tile ranges; a row block
 // split over several clusters gets one partial slot per cluster.
@@ -164,6 +171,11 @@ struct PairFwdArgs {
   float* col_part;            // [2 * row_blocks, ld_colpart] or NULL (rows only)
   float* col_ref;             // [2 * row_blocks, 4 * col_tiles]
   int* zero2;                 // nullable: two ints the sweep clears (fallback flag, loss counter)
+  // multi-rank: y is a gathered buffer filled shard by shard by the ranks' push kernels;
+  // landed[w] >= landed_gen says rank w's shard (rows [w * rows_per_rank, ...)) may be read
+  const int* landed = nullptr;
+  int landed_gen = 0;
+  int64_t rows_per_rank = 0;
 };
 PairFwdGeom clip_pair_fwd_geom(int64_t n_loc, int64_t n_all);
 int clip_pair_fwd_sweep(const PairFwdArgs& a, cudaStream_t stream);
@@ -189,6 +201,5 @@ int clip_bwd_rows_simt(const ClipBwdArgs& a, cudaStream_t stream);
 int clip_simt_ds_count(int64_t n_loc);
 
 int device_sm_count();
-bool want_fp16_copies();
 
 }  // namespace latte

@@ -183,12 +183,10 @@ extern "C" int latte_siglip_bwd(const void* img_loc, int64_t ld_img, const void*
     LATTE_CUDA_OK(cudaMemsetAsync(d_txt_partial, 0, (size_t)n_all * (size_t)dim * sizeof(float), st));
   sig_scale_kernel<<<1, 1, 0, st>>>(grad_loss, logit_scale, n_loc, out_scale);
   LATTE_LAUNCH_OK();
-  // operands of the gradient GEMMs: the features as they are (A = fp16 G, B = bf16 or fp16
-  // features), or fp16 copies with LATTE_B200_FP16_COPIES=1
+  // fp16 operands of the gradient GEMMs (G is fp16 and kind::f16 takes one 16-bit format)
   const void* x16 = img_loc; int64_t ldx16 = ld_img;
   const void* y16 = txt_all; int64_t ldy16 = ld_txt;
-  const bool copies16 = dtype == LATTE_BF16 && want_fp16_copies();
-  if (copies16) {
+  if (dtype == LATTE_BF16) {
     __half* xh = reinterpret_cast<__half*>(ws + w.off_x16);
     __half* yh = reinterpret_cast<__half*>(ws + w.off_y16);
     const int64_t per_row = dim / 8;
@@ -211,7 +209,7 @@ extern "C" int latte_siglip_bwd(const void* img_loc, int64_t ld_img, const void*
   PairGemmArgs ga = {};
   ga.g = ws + w.off_g; ga.n_loc = n_loc; ga.n_all = n_all; ga.dim = dim; ga.ld32 = (int64_t)w.ld32;
   ga.y16 = y16; ga.ldy16 = ldy16; ga.x16 = x16; ga.ldx16 = ldx16;
-  ga.feat_dtype = copies16 ? LATTE_F16 : dtype;
+  ga.feat_dtype = LATTE_F16;
   ga.out_dtype = grad_dtype; ga.ld_out = ld_grad; ga.out_scale = out_scale;
   ga.dx_out = d_img; ga.dy_out = own ? d_txt : nullptr;
   ga.dx32 = acc_i;

@@ -315,6 +315,13 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
                "f"(d)
                : "memory");
 }
+// the same reduction at system scope: the target may be another GPU's memory (peer mapping) that
+// several GPUs add into concurrently
+__device__ __forceinline__ void red_add_v4_sys(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.relaxed.sys.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b),
+               "f"(c), "f"(d)
+               : "memory");
+}
 __device__ __forceinline__ void ld_shared_v4(uint32_t addr, uint32_t& a, uint32_t& b, uint32_t& c,
                                              uint32_t& d) {
   asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
@@ -324,6 +331,38 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t
                                              uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d)
                : "memory");
+}
+
+// ---------------------------------------------------------------- cross-GPU flags (peer memory)
+// A flag is an int32 in THIS GPU's memory that a peer GPU (or this one) sets to a generation
+// number with a system-scope release store after its data stores; the consumer acquires it.
+__device__ __forceinline__ int ld_acquire_sys(const int* p) {
+  int v;
+  asm volatile("ld.acquire.sys.global.b32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(int* p, int v) {
+  asm volatile("st.release.sys.global.b32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// Bounded spin until *flag >= gen (generations only grow): a protocol bug or a dead peer must trap
+// (launch error) rather than hang the GPU.
+__device__ __forceinline__ void flag_wait_ge(const int* flag, int gen) {
+  if (ld_acquire_sys(flag) - gen >= 0) return;
+  uint64_t t0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  uint32_t spins = 0;
+  while (ld_acquire_sys(flag) - gen < 0) {
+    __nanosleep(64);
+    if ((++spins & 0xff) == 0) {
+      uint64_t t1;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      if (t1 - t0 > 8000000000ull) __trap();  // 8 s
+    }
+  }
+}
+// generic-proxy writes (possibly by a peer GPU) -> async-proxy (TMA) reads of the same memory
+__device__ __forceinline__ void fence_proxy_async_all() {
+  asm volatile("fence.proxy.async;" ::: "memory");
 }
 
 // ---------------------------------------------------------------- descriptors

@@ -124,12 +124,13 @@ _PEER_ACC = {}
 
 
 def _bwd_sweeps(world_size: int) -> int:
-    """Recompute sweeps per rank in the multi-rank backward: 1 = rows only, the text-side product
-    is reduce-scattered; 2 = rows and columns, nothing is exchanged.  LATTE_B200_BWD_SWEEPS overrides."""
+    """Recompute sweeps per rank in the multi-rank backward: 1 (default) = rows only, the text-side
+    product is reduce-scattered inside the GEMM; 2 = rows and columns, nothing is exchanged
+    (LATTE_B200_BWD_SWEEPS=2; executes 12 n N D for the 6 credited)."""
     env = os.environ.get("LATTE_B200_BWD_SWEEPS", "")
     if env in ("1", "2"):
         return int(env)
-    return 2 if world_size >= 8 else 1
+    return 1
 
 
 def _peer_accumulator(n: int, dim: int, device, group):
@@ -158,61 +159,149 @@ def _peer_accumulator(n: int, dim: int, device, group):
     return entry
 
 
-# Gathered feature buffers [2, N, D] in symmetric memory: every rank stores its shards straight
-# into all ranks' buffers (latte_push_shards), replacing the two NCCL all-gathers of the
-# forward.  A slot stays busy from a forward until its backward (the gathered features are
-# saved for the recompute), so several slots exist per shape; when none is free the call falls
-# back to NCCL -- every rank takes the same decision because the call sequence is the same.
-_GATHER_SLOTS = {}
-_MAX_GATHER_SLOTS = 4
+# ------------------------------------------------------------------------------------------
+# Peer-memory exchange state (torch symmetric memory: one allocation per rank, mapped by all)
+# ------------------------------------------------------------------------------------------
+# Per (shard shape, dtype, group) every rank owns `_COMM_SLOTS` slots, each holding the gathered
+# feature buffer [2, N, D], the forward payload blocks, the fp32 text-gradient accumulator and a
+# flag block (include/latte_b200.h: latte_comm_t).  The kernels store into / add into the peers'
+# slots and synchronise with generation-numbered flags; no host-side barrier or collective runs in
+# a step.  A slot is busy from a forward to the end of its backward (the gathered text features are
+# re-read by the recompute sweep); a forward that finds no free slot falls back to NCCL -- every
+# rank takes the same decision because the call sequence is the same.
+_COMM_STATES = {}
+_COMM_SLOTS = 4
 
 
-class _GatherSlot:
-    def __init__(self, buf, hdl):
-        self.buf, self.hdl = buf, hdl
-        self.ptrs = [int(p) for p in hdl.buffer_ptrs]
-        mc = 0
-        # NVSwitch multicast stores (multimem.st): measured no faster than per-peer stores at
-        # 4 ranks (1.129 vs 1.116 ms/step), so opt-in
-        if os.environ.get("LATTE_B200_MULTICAST") == "1":
-            try:
-                mc = int(hdl.multicast_ptr or 0)
-            except Exception:
-                mc = 0
-        self.multicast_ptr = mc
+def _round_up(x: int, a: int) -> int:
+    return (x + a - 1) // a * a
+
+
+class _CommSlot:
+    def __init__(self, state, index: int, offset: int):
+        self.state, self.index, self.offset = state, index, offset
+        self.gen = 0
+        self.busy = False
+        st = state
+        base = st.buf[offset:offset + st.slot_bytes]
+        self.gather = base[:st.gather_bytes].view(st.dtype).view(2, st.n_all, st.dim)
+        # per-rank pointers of the four regions
+        self._ptrs = [[p + offset + off for p in st.base_ptrs]
+                      for off in (0, st.off_payload, st.off_acc, st.off_flags)]
+        self.comm = _lib.make_comm(st.rank, st.world, 1, self._ptrs[0], self._ptrs[1], self._ptrs[2],
+                                   self._ptrs[3], st.payload_stride)
+
+    @property
+    def all_img(self):
+        return self.gather[0]
+
+    @property
+    def all_txt(self):
+        return self.gather[1]
+
+    def acquire(self):
+        self.gen += 1
+        self.comm.gen = self.gen
+        self.busy = True
+        return self
+
+    def release(self, signal: bool):
+        """Mark the slot free; ``signal`` launches the release kernel (a forward without backward:
+        the backward's last kernel normally publishes the release itself)."""
+        if not self.busy:
+            return
+        if signal:
+            _lib.comm_release(self.comm, self.state.device)
         self.busy = False
 
 
-def _acquire_gather_slot(n: int, dim: int, dtype, device, group, world: int):
+class _SlotLease:
+    """Ties a slot to the autograd node that saved its gathered features: if the node dies without a
+    backward (a logged validation loss, an exception), the slot is released when the node is
+    collected instead of staying busy forever."""
+
+    def __init__(self, slot):
+        self.slot = slot
+        self.gen = slot.gen
+
+    def done(self):
+        self.slot = None
+
+    def __del__(self):
+        slot = self.slot
+        if slot is not None and slot.busy and slot.gen == self.gen:
+            try:
+                slot.release(signal=True)
+            except Exception:      # interpreter shutdown
+                pass
+
+
+class _CommState:
+    def __init__(self, n, dim, dtype, device, group, world, rank, buf, hdl):
+        self.n, self.dim, self.dtype, self.device = n, dim, dtype, device
+        self.world, self.rank = world, rank
+        self.n_all = n * world
+        self.buf, self.hdl = buf, hdl
+        self.base_ptrs = [int(p) for p in hdl.buffer_ptrs]
+        (self.gather_bytes, self.off_payload, self.off_acc, self.off_flags, self.slot_bytes,
+         self.payload_stride) = _CommState.layout(n, dim, world)
+        self.slots = [_CommSlot(self, k, k * self.slot_bytes) for k in range(_COMM_SLOTS)]
+        self.next = 0
+
+    @staticmethod
+    def layout(n, dim, world):
+        n_all = n * world
+        gather_bytes = 2 * n_all * dim * 2
+        stride = _round_up(2 * n_all + 3 * n, 4)
+        payload_bytes = (world * stride + world * 2 * n_all) * 4
+        off_payload = _round_up(gather_bytes, 256)
+        off_acc = off_payload + _round_up(payload_bytes, 256)
+        off_flags = off_acc + _round_up(n * dim * 4, 256)
+        slot_bytes = off_flags + _round_up(_lib.COMM_FLAG_INTS * 4, 256)
+        return gather_bytes, off_payload, off_acc, off_flags, slot_bytes, stride
+
+    def acquire(self):
+        for k in range(len(self.slots)):
+            sl = self.slots[(self.next + k) % len(self.slots)]
+            if not sl.busy:
+                self.next = (sl.index + 1) % len(self.slots)
+                return sl.acquire()
+        return None
+
+
+def _comm_state(n: int, dim: int, dtype, device, group, world: int, rank: int):
+    """-> _CommState or None (no symmetric memory / LATTE_B200_NO_P2P=1 / unsupported shape); the
+    rendezvous happens once per shape and the decision is agreed on by all ranks."""
     if os.environ.get("LATTE_B200_NO_P2P") == "1" or device.type != "cuda":
         return None
-    if dtype not in (torch.bfloat16, torch.float16) or (n * dim * 2) % 16 != 0:
+    if dtype not in (torch.bfloat16, torch.float16) or (n * dim * 2) % 16 != 0 or dim % 4 != 0:
+        return None
+    if world > _lib.COMM_MAX_RANKS:
         return None
     key = (n, dim, dtype, device.index, id(group))
-    slots = _GATHER_SLOTS.setdefault(key, [])
-    for sl in slots:
-        if sl is not None and not sl.busy:
-            sl.busy = True
-            return sl
-    if len(slots) >= _MAX_GATHER_SLOTS or (slots and slots[-1] is None):
-        return None
-    slot = None
+    if key in _COMM_STATES:
+        return _COMM_STATES[key]
+    state = None
     try:
-        if dist.get_backend(group) == "nccl" and world <= 8:
+        if dist.get_backend(group) == "nccl":
             import torch.distributed._symmetric_memory as symm
-            buf = symm.empty(2, n * world, dim, dtype=dtype, device=device)
+            total = _CommState.layout(n, dim, world)[4] * _COMM_SLOTS
+            buf = symm.empty(total, dtype=torch.uint8, device=device)
+            buf.zero_()                                   # flags and accumulators start at zero
             hdl = symm.rendezvous(buf, group if group is not None else dist.group.WORLD)
-            slot = _GatherSlot(buf, hdl)
-    except Exception:
-        slot = None
-    ok = torch.tensor([1 if slot is not None else 0], device=device, dtype=torch.int32)
+            state = _CommState(n, dim, dtype, device, group, world, rank, buf, hdl)
+    except (ImportError, RuntimeError, AttributeError) as exc:
+        if os.environ.get("LATTE_B200_VERBOSE"):
+            print(f"latteclip_b200: peer-memory exchange unavailable ({exc}); using NCCL", flush=True)
+        state = None
+    # the decision must be the same on every rank (the collectives differ); this all-reduce also
+    # orders every rank's zero-fill before anybody's first signal
+    ok = torch.tensor([1 if state is not None else 0], device=device, dtype=torch.int32)
     dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
     if int(ok) == 0:
-        slot = None
-    slots.append(slot)
-    if slot is not None:
-        slot.busy = True
-    return slot
+        state = None
+    _COMM_STATES[key] = state
+    return state
 
 
 class _FusedClipLoss(torch.autograd.Function):
@@ -223,18 +312,26 @@ class _FusedClipLoss(torch.autograd.Function):
          local_loss & !gather_with_grad : own-block terms only (gathered copies carry no grad)
 
     Multi-rank, 16-bit features with dim <= 768 (every mode but the last): ONE logit sweep per
-    rank.  Forward: rows of this rank x all columns give the row LSEs and, from the same tiles,
-    per-column (max, sum) partials; one all-gather of [2N + 3n] floats per rank merges them into
-    every column's LSE.  Backward: one recompute sweep -> G[rows of this rank, :]; d_img is
-    local; the text gradient G^T.img_loc covers ALL columns and must be reduce-scattered -- the
-    reference's own collective (the backward of its all_gather).  With torch symmetric memory
-    the GEMM epilogue adds every row straight into its owner rank's peer-mapped fp32
-    accumulator (red.global.add over NVLink, two cross-rank barriers), so the reduce-scatter
-    overlaps the GEMM tile by tile; otherwise an fp32 [N, D] partial goes through NCCL.  d loss / d logit_scale then
-    covers this rank's rows x all columns: a different partition over ranks of the same global
-    sum as the reference's (identical after DDP's all-reduce of the parameter gradient).
-    Other cases: each rank sweeps its row block and its column block (two sweeps) and the
-    backward exchanges only the LSE vectors.
+    rank in each direction, exchanges by the kernels themselves over NVLink peer memory:
+      forward : a store kernel writes this rank's text shard into every rank's gathered buffer
+                (the all-gather of loss.py:49-50; the images of other ranks are never needed);
+                the sweep of own images x all texts starts on the shards as they land and yields
+                the row LSEs and per-column (max, sum) partials; each rank stores that payload
+                ([2N + 3n] floats) into every peer's block and merges the blocks into every
+                column's LSE as soon as they arrived.
+      backward: one recompute sweep -> G[rows of this rank, :]; d_img is local; the text gradient
+                G^T.img_loc covers ALL columns and must be reduce-scattered -- the reference's own
+                collective (the backward of its all_gather): the GEMM epilogue adds every row
+                straight into its owner rank's fp32 accumulator (system-scope red over NVLink), so
+                the exchange overlaps the GEMM tile by tile; a last kernel waits for every rank's
+                "adds done" flag and casts the accumulator.
+    d loss / d logit_scale then covers this rank's rows x all columns: a different partition over
+    ranks of the same global sum as the reference's (identical after DDP's all-reduce of the
+    parameter gradient -- logit_scale.grad must be all-reduced to match the reference).
+    Without symmetric memory (or LATTE_B200_NO_P2P=1) the same flow runs over NCCL: all-gathers of
+    the features and of the payload, fp32 [N, D] partial + reduce_scatter.
+    Other cases (fp32 features, local_loss without gather_with_grad): each rank sweeps its row block
+    and its column block and the backward exchanges only the LSE vectors.
     """
 
     @staticmethod
@@ -245,82 +342,101 @@ class _FusedClipLoss(torch.autograd.Function):
         cross_terms = not (world_size > 1 and local_loss and not gather_with_grad)
         rank_sweep = False
         slot = None
+        lease = None
+        two_sweeps = False
         if world_size > 1:
             label_offset = rank * img.shape[0]
             rank_sweep = cross_terms and _lib.rank_sweep_supported(img.dtype, img.shape[1])
+            two_sweeps = rank_sweep and _bwd_sweeps(world_size) == 2
             if rank_sweep and img.dtype == txt.dtype:
-                slot = _acquire_gather_slot(img.shape[0], img.shape[1], img.dtype, img.device, group,
-                                            world_size)
+                state = _comm_state(img.shape[0], img.shape[1], img.dtype, img.device, group,
+                                    world_size, rank)
+                slot = state.acquire() if state is not None else None
             if slot is not None:
-                # one NVLink store kernel instead of two NCCL all-gathers
-                slot.hdl.barrier(channel=0)       # readers of the slot's previous contents are done
-                _lib.push_shards(img, txt, slot.ptrs, rank, slot.buf[0].numel() * slot.buf.element_size(),
-                                 slot.multicast_ptr)
-                slot.hdl.barrier(channel=1)       # every rank's shards have landed
-                all_img, all_txt = slot.buf[0], slot.buf[1]
+                # one NVLink store kernel instead of NCCL all-gathers; the images of the other ranks
+                # are only needed when the backward recomputes rows AND columns
+                _lib.comm_push(slot.comm, txt, img if two_sweeps else None,
+                               tensor_stride_bytes=slot.all_img.numel() * slot.all_img.element_size())
+                all_img, all_txt = (slot.all_img if two_sweeps else None), slot.all_txt
             else:
-                all_img = _all_gather_cat(img, group)
+                all_img = _all_gather_cat(img, group) if (not rank_sweep or two_sweeps) else None
                 all_txt = _all_gather_cat(txt, group)
         else:
             all_img, all_txt, label_offset = img, txt, 0
-        if rank_sweep:
+        if rank_sweep and slot is not None:
+            row_lse_all, row_nll_all, col_lse_all, col_nll_all, loss, lse_stats, _ = _lib.clip_fwd_rank(
+                slot.comm, img, all_txt, label_offset, logit_scale)
+            stats = (row_lse_all, col_lse_all, row_nll_all, col_nll_all, lse_stats)
+        elif rank_sweep:
             payload = _lib.clip_fwd_rows(img, all_txt, label_offset, logit_scale)
             gathered = _all_gather_cat(payload.reshape(1, -1), group)            # [W, 2N + 3n]
-            row_lse_all, row_nll_all, col_lse_all, col_nll_all, loss = _lib.clip_fwd_cols(
-                gathered, all_img, all_txt, img.shape[0], label_offset, logit_scale)
-            stats = (row_lse_all, col_lse_all, row_nll_all, col_nll_all)
+            row_lse_all, row_nll_all, col_lse_all, col_nll_all, loss, lse_stats = _lib.clip_fwd_cols(
+                gathered, all_img if all_img is not None else _all_gather_cat(img, group), all_txt,
+                img.shape[0], label_offset, logit_scale)
+            stats = (row_lse_all, col_lse_all, row_nll_all, col_nll_all, lse_stats)
         else:
-            row_lse, col_lse, loss, row_nll, col_nll = _lib.clip_fwd(
-                img, txt, all_img, all_txt, label_offset, logit_scale, with_nll=True)
-            stats = (row_lse, col_lse, row_nll, col_nll)
+            row_lse, col_lse, loss, row_nll, col_nll, lse_stats = _lib.clip_fwd(
+                img, txt, all_img, all_txt, label_offset, logit_scale, with_nll=True, with_stats=True)
+            stats = (row_lse, col_lse, row_nll, col_nll, lse_stats)
         loss = loss.reshape(())
         if world_size > 1 and not local_loss:
             # L_global = mean over ranks of the per-rank block losses (equal shard sizes)
             loss = loss.clone()
             dist.all_reduce(loss, op=dist.ReduceOp.SUM, group=group)
             loss = loss / world_size
-        ctx.gather_slot = slot
-        if slot is not None and not any(ctx.needs_input_grad[:3]):
-            slot.busy = False                     # no backward will come for this call
-            ctx.gather_slot = None
+        if slot is not None:
+            if any(ctx.needs_input_grad[:3]):
+                lease = _SlotLease(slot)
+            else:
+                slot.release(signal=True)                 # no backward will come for this call
+                slot = None
+        ctx.lease = lease
+        if all_img is None:
+            all_img = img                                 # placeholder: never read in the one-sweep modes
         ctx.save_for_backward(img, txt, all_img, all_txt, logit_scale.detach(), *stats)
-        ctx.cfg = (local_loss, gather_with_grad, rank, world_size, group, label_offset, rank_sweep)
+        ctx.cfg = (local_loss, gather_with_grad, rank, world_size, group, label_offset, rank_sweep,
+                   two_sweeps)
         ctx.scale_meta = (logit_scale.dtype, logit_scale.shape)
         ctx.feat_dtypes = (image_features.dtype, text_features.dtype)
         return loss
 
     @staticmethod
     def backward(ctx, grad_out):
-        img, txt, all_img, all_txt, scale, row_lse, col_lse, row_nll, col_nll = ctx.saved_tensors
-        local_loss, gather_with_grad, rank, world_size, group, label_offset, rank_sweep = ctx.cfg
+        img, txt, all_img, all_txt, scale, row_lse, col_lse, row_nll, col_nll, lse_stats = ctx.saved_tensors
+        (local_loss, gather_with_grad, rank, world_size, group, label_offset, rank_sweep,
+         two_sweeps) = ctx.cfg
+        if world_size > 1 and not rank_sweep:
+            lse_stats = None    # per-rank statistics: the kernels recompute them from the gathered vectors
         cross_terms = not (world_size > 1 and local_loss and not gather_with_grad)
         grad_mult = 1.0
         if world_size > 1 and not local_loss and not gather_with_grad:
             grad_mult = 1.0 / world_size
-        # From 8 ranks on, a second recompute sweep (own texts x all images, no exchange) is cheaper
-        # than adding the text-side product into the owners' accumulators over NVLink.
-        local_dtxt = rank_sweep and _bwd_sweeps(world_size) == 2
-        peer = None
-        if rank_sweep and not local_dtxt:
-            peer = _peer_accumulator(img.shape[0], img.shape[1], img.device, group)
-        if local_dtxt:
+        lease = getattr(ctx, "lease", None)
+        slot = lease.slot if lease is not None else None
+        if lease is not None and (slot is None or not slot.busy or slot.gen != lease.gen):
+            raise RuntimeError(
+                "latteclip_b200.ClipLoss: backward called twice on a multi-rank forward (the gathered "
+                "features of that step were released after the first backward); call forward again")
+        if rank_sweep and two_sweeps:
+            # rows AND columns recomputed per rank, nothing exchanged (LATTE_B200_BWD_SWEEPS=2)
             d_img, d_txt, d_scale = _lib.clip_bwd(
                 img, txt, all_img, all_txt, label_offset, scale, row_lse, col_lse, grad_out,
-                grad_mult, True, row_nll_all=row_nll, col_nll_all=col_nll)
-        elif rank_sweep and peer is not None:
-            # fused reduce-scatter: every rank's GEMM adds into the owners' accumulators
-            acc, hdl, ptrs = peer
-            acc.zero_()
-            hdl.barrier(channel=0)            # all accumulators zeroed, last step's reads done
-            d_img, _, d_scale = _lib.clip_bwd(
-                img, txt, all_img, all_txt, label_offset, scale, row_lse, col_lse, grad_out,
-                grad_mult, True, row_nll_all=row_nll, col_nll_all=col_nll, peer_ptrs=ptrs)
-            hdl.barrier(channel=1)            # every rank's adds have landed
-            d_txt = acc.to(img.dtype)
+                grad_mult, True, row_nll_all=row_nll, col_nll_all=col_nll, lse_stats=lse_stats)
+            if slot is not None:
+                slot.release(signal=True)
+        elif rank_sweep and slot is not None:
+            # fused reduce-scatter: every rank's GEMM adds into the owners' accumulators; the call's
+            # last kernel publishes the slot's release
+            d_img, d_txt, d_scale = _lib.clip_bwd(
+                img, txt, None, all_txt, label_offset, scale, row_lse, col_lse, grad_out,
+                grad_mult, True, row_nll_all=row_nll, col_nll_all=col_nll, comm=slot.comm,
+                lse_stats=lse_stats)
+            slot.release(signal=False)
         elif rank_sweep:
             d_img, d_part, d_scale = _lib.clip_bwd(
-                img, txt, all_img, all_txt, label_offset, scale, row_lse, col_lse, grad_out,
-                grad_mult, True, row_nll_all=row_nll, col_nll_all=col_nll, partial=True)
+                img, txt, None, all_txt, label_offset, scale, row_lse, col_lse, grad_out,
+                grad_mult, True, row_nll_all=row_nll, col_nll_all=col_nll, partial=True,
+                lse_stats=lse_stats)
             d_txt = _reduce_scatter_sum(d_part, img.shape[0], rank, group).to(img.dtype)
         else:
             if world_size > 1:
@@ -330,10 +446,9 @@ class _FusedClipLoss(torch.autograd.Function):
                 row_all, col_all, rown_all, coln_all = row_lse, col_lse, row_nll, col_nll
             d_img, d_txt, d_scale = _lib.clip_bwd(
                 img, txt, all_img, all_txt, label_offset, scale, row_all, col_all, grad_out,
-                grad_mult, cross_terms, row_nll_all=rown_all, col_nll_all=coln_all)
-        if getattr(ctx, "gather_slot", None) is not None:
-            ctx.gather_slot.busy = False          # the next forward may overwrite the slot
-            ctx.gather_slot = None
+                grad_mult, cross_terms, row_nll_all=rown_all, col_nll_all=coln_all, lse_stats=lse_stats)
+        if lease is not None:
+            lease.done()
         if world_size > 1 and not local_loss:
             # every rank differentiates the same L_global: d/ds is the rank mean of the block sums
             d_scale = d_scale / grad_mult

@@ -41,13 +41,20 @@ def clip_fwd_cols(gathered, img_all, txt_all, n_loc, label_offset, logit_scale):
     own = slice(label_offset, label_offset + n_loc)
     loss = (row_nll_all[own].mean() + col_nll_all[own].mean()) / 2
     return (row_lse_all.float(), row_nll_all.float(), col_lse_all.float(), col_nll_all.float(),
-            loss.float().reshape(1))
+            loss.float().reshape(1), _stats(row_lse_all, col_lse_all, row_nll_all, col_nll_all))
+
+
+def _stats(row_lse, col_lse, row_nll, col_nll):
+    both = torch.cat([row_lse, col_lse])
+    return torch.stack([both.min(), both.max(), torch.cat([row_nll, col_nll]).max(),
+                        both.new_zeros(())]).float()
 
 
 LOG2E = 1.4426950408889634
 
 
-def clip_fwd(img_loc, txt_loc, img_all, txt_all, label_offset, logit_scale, with_nll=False):
+def clip_fwd(img_loc, txt_loc, img_all, txt_all, label_offset, logit_scale, with_nll=False,
+             with_stats=False):
     s = logit_scale.detach().double().reshape(())
     il, tl, ia, ta = (x.detach().double() for x in (img_loc, txt_loc, img_all, txt_all))
     n = il.shape[0]
@@ -59,16 +66,20 @@ def clip_fwd(img_loc, txt_loc, img_all, txt_all, label_offset, logit_scale, with
     diag_r = s_r[torch.arange(n), idx]
     diag_c = s_c[torch.arange(n), idx]
     loss = ((row_lse - diag_r).mean() + (col_lse - diag_c).mean()) / 2
+    out = (row_lse.float(), col_lse.float(), loss.float().reshape(1))
     if with_nll:
-        return (row_lse.float(), col_lse.float(), loss.float().reshape(1),
-                (row_lse - diag_r).float(), (col_lse - diag_c).float())
-    return row_lse.float(), col_lse.float(), loss.float().reshape(1)
+        out = out + ((row_lse - diag_r).float(), (col_lse - diag_c).float())
+    if with_stats:
+        out = out + (_stats(row_lse, col_lse, row_lse - diag_r, col_lse - diag_c),)
+    return out
 
 
 def clip_bwd(img_loc, txt_loc, img_all, txt_all, label_offset, logit_scale, row_lse_all,
              col_lse_all, grad_loss, grad_mult, cross_terms, grad_dtype=None, row_nll_all=None,
-             col_nll_all=None, partial=False, peer_ptrs=None):
+             col_nll_all=None, partial=False, comm=None, phases=3, lse_stats=None, out=None):
     s = logit_scale.detach().double().reshape(())
+    if img_all is None:
+        img_all = img_loc          # one-sweep modes read this rank's images only
     il, tl, ia, ta = (x.detach().double() for x in (img_loc, txt_loc, img_all, txt_all))
     n = il.shape[0]
     idx = torch.arange(n) + label_offset

@@ -51,7 +51,7 @@ def test_bad_arguments_are_rejected_without_a_gpu(lib):
     # null pointers never reach a kernel launch
     assert lib.latte_normalize_rows(None, 512, None, 512, 4, 512, None) == -1
     assert lib.latte_clip_fwd(None, 0, None, 0, None, 0, None, 0, 1, 1, 1, 1, 0,
-                              None, None, None, None, None, None, None, 0, None) == -1
+                              None, None, None, None, None, None, None, None, 0, None) == -1
     assert lib.latte_clip_fwd_rows(None, 0, None, 0, 1, 1, 1, 8, 0, None, None, None, None, None,
                                    None, 0, None) == -1
     assert lib.latte_clip_rank_sweep_supported(1, 512) == 1      # bf16, dim 512

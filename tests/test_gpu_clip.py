@@ -303,7 +303,7 @@ def test_one_sweep_per_rank_path_emulated_on_one_gpu(world, n, d, sigma):
     parts, d_imgs, d_scales = [], [], []
     for r in range(world):
         sl = slice(r * n, (r + 1) * n)
-        row_lse_all, row_nll_all, col_lse_all, col_nll_all, loss_r = _lib.clip_fwd_cols(
+        row_lse_all, row_nll_all, col_lse_all, col_nll_all, loss_r, _ = _lib.clip_fwd_cols(
             gathered, ib, tb, n, r * n, sc)
         assert abs(float(loss_r) - float(lo[r])) <= LOSS_RTOL * abs(float(lo[r])) + 2e-5
         d_img, d_part, d_s = _lib.clip_bwd(ib[sl], tb[sl], ib, tb, r * n, sc, row_lse_all, col_lse_all,
@@ -319,6 +319,97 @@ def test_one_sweep_per_rank_path_emulated_on_one_gpu(world, n, d, sigma):
         assert rel(d_txt[r * n:(r + 1) * n], dt[r]) < GRAD_RTOL_16
     ref_ds = sum(float(x) for x in ds)
     assert abs(sum(d_scales) - ref_ds) <= 2e-3 * abs(ref_ds) + 1e-6
+
+
+class _EmulatedRanks:
+    """W ranks' slots of the peer-memory exchange as plain tensors on ONE GPU: every 'peer pointer'
+    is just another tensor of this process, so the kernels' stores, system-scope adds and
+    generation flags run for real, phase by phase (the flags are always already set when a
+    waiting kernel starts -- nothing spins across launches)."""
+
+    def __init__(self, world, n, d, dtype, dev):
+        from latteclip_b200 import _lib
+        from latteclip_b200.loss import _CommState
+        self.world, self.n, self.d, self.N = world, n, d, n * world
+        (self.gather_bytes, off_payload, off_acc, off_flags, slot_bytes,
+         self.stride) = _CommState.layout(n, d, world)
+        self.bufs = [torch.zeros(slot_bytes, dtype=torch.uint8, device=dev) for _ in range(world)]
+        base = [b.data_ptr() for b in self.bufs]
+        self.gather = [b[:self.gather_bytes].view(dtype).view(2, self.N, d) for b in self.bufs]
+        self.acc = [b[off_acc:off_acc + n * d * 4].view(torch.float32).view(n, d) for b in self.bufs]
+        self.flags = [b[off_flags:off_flags + 256].view(torch.int32) for b in self.bufs]
+        self.comms = [_lib.make_comm(r, world, 1, base, [p + off_payload for p in base],
+                                     [p + off_acc for p in base], [p + off_flags for p in base],
+                                     self.stride) for r in range(world)]
+
+    def set_gen(self, gen):
+        for c in self.comms:
+            c.gen = gen
+
+
+@pytest.mark.parametrize("world,n,d,sigma,dtype", [(2, 512, 512, 4.0, torch.bfloat16),
+                                                   (4, 300, 256, 4.0, torch.float16),
+                                                   (3, 130, 64, 3.0, torch.bfloat16),
+                                                   (2, 600, 768, 5.0, torch.bfloat16),
+                                                   (8, 136, 128, 3.0, torch.bfloat16)])
+def test_peer_memory_rank_flow_emulated_on_one_gpu(world, n, d, sigma, dtype):
+    """latte_comm_push / latte_clip_fwd_rank / latte_clip_bwd(comm) -- the product's multi-rank
+    flow -- for every rank on one GPU, two generations of the same slot (credits, accumulator
+    re-zeroing).  Checked against the fp64 oracle of the reference's local_loss + gather_with_grad
+    mode (loss.py:102-113 and the all_gather backward)."""
+    from latteclip_b200 import _lib
+    from oracle.clip_loss import clip_loss_all_ranks
+    dev = torch.device("cuda:0")
+    em = _EmulatedRanks(world, n, d, dtype, dev)
+    sc = torch.tensor(100.0, device=dev)
+    one = torch.ones(1, device=dev)
+    for gen in (1, 2):
+        i_all, t_all = synth(n * world, d, sigma, 70 + n + gen)
+        ib, tb = i_all.to(dev).to(dtype), t_all.to(dev).to(dtype)
+        ir, tr = ib.float().cpu(), tb.float().cpu()
+        ish = [ir[r * n:(r + 1) * n] for r in range(world)]
+        tsh = [tr[r * n:(r + 1) * n] for r in range(world)]
+        lo, di, dt, ds = clip_loss_all_ranks(ish, tsh, 100.0, True, True)
+        em.set_gen(gen)
+        stride_bytes = em.N * d * 2
+        for r in range(world):
+            _lib.comm_push(em.comms[r], tb[r * n:(r + 1) * n], None, tensor_stride_bytes=stride_bytes)
+        torch.cuda.synchronize()
+        for r in range(world):
+            assert torch.equal(em.gather[r][1], tb), "text all-gather through peer stores"
+            assert em.flags[r][:world].tolist() == [gen] * world
+        outs = [None] * world
+        for ph in (1, 2, 4):
+            for r in range(world):
+                res = _lib.clip_fwd_rank(em.comms[r], ib[r * n:(r + 1) * n], em.gather[r][1], r * n, sc,
+                                         phases=ph, out=outs[r])
+                outs[r] = res[-1]
+                if ph == 4:
+                    outs[r] = res
+        bwd = [None] * world
+        for ph in (1, 2):
+            for r in range(world):
+                row_all, rown_all, col_all, coln_all, loss_r, stats, _ = outs[r]
+                sl = slice(r * n, (r + 1) * n)
+                res = _lib.clip_bwd(ib[sl], tb[sl], None, em.gather[r][1], r * n, sc, row_all, col_all, one,
+                                    1.0, True, grad_dtype=torch.float32, row_nll_all=rown_all,
+                                    col_nll_all=coln_all, comm=em.comms[r], phases=ph, lse_stats=stats,
+                                    out=None if bwd[r] is None else bwd[r][-1])
+                bwd[r] = res
+        torch.cuda.synchronize()
+        for r in range(world):
+            row_all, rown_all, col_all, coln_all, loss_r, stats, _ = outs[r]
+            assert abs(float(loss_r) - float(lo[r])) <= LOSS_RTOL * abs(float(lo[r])) + 2e-5
+            both = torch.cat([row_all, col_all])
+            assert float(stats[0]) == float(both.min()) and float(stats[1]) == float(both.max())
+            d_img, d_txt, d_s, _ = bwd[r]
+            assert rel(d_img, di[r]) < GRAD_RTOL_16, (gen, r)
+            assert rel(d_txt, dt[r]) < GRAD_RTOL_16, (gen, r)
+            assert float(em.acc[r].abs().max()) == 0.0, "accumulator cleared for the next generation"
+            assert em.flags[r][40:40 + world].tolist() == [gen] * world        # released by every rank
+        got_ds = sum(float(b[2]) for b in bwd)
+        ref_ds = sum(float(x) for x in ds)
+        assert abs(got_ds - ref_ds) <= 2e-3 * abs(ref_ds)
 
 
 def test_flushed_column_triggers_exact_fallback():
@@ -406,7 +497,7 @@ def test_full_size_rank_block_cfg4():
     one = torch.ones(1, device=dev)
     assert _lib.rank_sweep_supported(torch.bfloat16, d)
     gathered = torch.stack([_lib.clip_fwd_rows(ib[q * n:(q + 1) * n], tb, q * n, sc) for q in range(world)])
-    row_all, rown_all, col_all, coln_all, loss_r = _lib.clip_fwd_cols(gathered, ib, tb, n, r * n, sc)
+    row_all, rown_all, col_all, coln_all, loss_r, _ = _lib.clip_fwd_cols(gathered, ib, tb, n, r * n, sc)
     g = torch.Generator().manual_seed(8)
     rows = torch.randint(0, N, (48,), generator=g).to(dev)
     S_r = 100.0 * ib[rows].double() @ tb.double().T                 # [48, N]

@@ -56,7 +56,7 @@ gathered = torch.stack([_lib.clip_fwd_rows(ib[r * n:(r + 1) * n], tb, r * n, sc)
 parts, dIs, losses = [], [], []
 for r in range(world):
     sl = slice(r * n, (r + 1) * n)
-    row_lse_all, row_nll_all, col_lse_all, col_nll_all, loss_r = _lib.clip_fwd_cols(gathered, ib, tb, n, r * n, sc)
+    row_lse_all, row_nll_all, col_lse_all, col_nll_all, loss_r, _ = _lib.clip_fwd_cols(gathered, ib, tb, n, r * n, sc)
     losses.append(float(loss_r))
     di, dpart, ds = _lib.clip_bwd(ib[sl], tb[sl], ib, tb, r * n, sc, row_lse_all, col_lse_all, one, 1.0, True,
                                   grad_dtype=torch.float32, row_nll_all=row_nll_all, col_nll_all=col_nll_all,

@@ -30,7 +30,7 @@ for it in range(25):
     all_img, all_txt = slot.buf[0], slot.buf[1]
     payload = _lib.clip_fwd_rows(img, all_txt, off, sc); marks.append(ev())
     gathered = L._all_gather_cat(payload.reshape(1, -1), None); marks.append(ev())
-    row_all, rown_all, col_all, coln_all, loss = _lib.clip_fwd_cols(gathered, all_img, all_txt, n, off, sc); marks.append(ev())
+    row_all, rown_all, col_all, coln_all, loss, _ = _lib.clip_fwd_cols(gathered, all_img, all_txt, n, off, sc); marks.append(ev())
     acc.zero_(); hdl.barrier(channel=0); marks.append(ev())
     d_img, _, d_s = _lib.clip_bwd(img, txt, all_img, all_txt, off, sc, row_all, col_all, one, 1.0, True,
                                   row_nll_all=rown_all, col_nll_all=coln_all, peer_ptrs=ptrs); marks.append(ev())

@@ -5,7 +5,7 @@ mkdir -p gpurun_out
 O=gpurun_out
 timeout 1500 python -m pytest tests -m gpu -x -q > $O/r2c1_tests.log 2>&1
 echo "tests rc=$?" | tee -a $O/r2c1_tests.log
-if ! grep -q " passed" $O/r2c1_tests.log || grep -q "failed" $O/r2c1_tests.log; then
+if false; then
   LATTE_B200_FP16_COPIES=1 timeout 900 python -m pytest tests/test_gpu_clip.py -x -q > $O/r2c1_tests_copies.log 2>&1
   echo "copies rc=$?" | tee -a $O/r2c1_tests_copies.log
 fi
