@@ -24,6 +24,8 @@
 #include "latte_common.cuh"
 #include "tc_ptx.cuh"
 
+#include <stdlib.h>
+
 namespace latte {
 
 using namespace ptx;
@@ -250,7 +252,12 @@ pair_sweep_kernel(const __grid_constant__ CUtensorMap tmy, const __grid_constant
       uint32_t phase = 0;
       const uint32_t lead_xt = mapa_rank(bar_xt, 0);
       int ct = ct0, rb_i = rb0;
-      uint32_t landed_mask = p.landed ? 0u : 0xffffffffu;     // ranks whose shard is known to be here
+      // ranks whose shard is known to be here (bits of ranks that do not exist are set)
+      uint32_t landed_mask = 0xffffffffu;
+      if (p.landed) {
+        const int nranks = (int)((p.n_all + p.rows_per_rank - 1) / p.rows_per_rank);
+        landed_mask = nranks >= 32 ? 0u : ~((1u << nranks) - 1u);
+      }
       for (int it = 0; it < ntile; ++it) {
         if (landed_mask != 0xffffffffu) {
           // owners of this tile's rows of y (a tile can straddle two shards)
@@ -258,12 +265,14 @@ pair_sweep_kernel(const __grid_constant__ CUtensorMap tmy, const __grid_constant
           const int64_t r_last = min(r_first + kTN, p.n_all) - 1;
           if (r_first < p.n_all) {
             const int w0 = (int)(r_first / p.rows_per_rank), w1 = (int)(r_last / p.rows_per_rank);
+            bool waited = false;
             for (int w = w0; w <= w1; ++w)
               if (!((landed_mask >> w) & 1u)) {
                 flag_wait_ge(p.landed + w, p.landed_gen);
                 landed_mask |= 1u << w;
+                waited = true;
               }
-            fence_proxy_async_all();
+            if (waited) fence_proxy_async_all();
           }
         }
         if (TAIL && (it == 0 || ct == 0)) {
@@ -953,6 +962,13 @@ constexpr int kGemmABytes = 128 * kBK * 2;      // 16 KB: this CTA's 128 rows (o
 constexpr int kGemmBChunk = 64 * 64 * 2;        // 8 KB: 64 k-rows x 64 feature columns
 constexpr int kGemmStageBytes = kGemmABytes + 4 * kGemmBChunk;   // 48 KB
 constexpr int kGemmSmem = kGemmStages * kGemmStageBytes + kMiscBytes;
+// fused reduce-scatter through TMA: every epilogue warp stages 32 rows x 32 fp32 columns (4 KB,
+// 128B-swizzled) and one cp.reduce.async.bulk.tensor adds the box into the owner's accumulator
+constexpr int kPeerStageBytes = 32 * 128;
+constexpr int kGemmSmemPeer = kGemmSmem + kGemmEpiWarps * kPeerStageBytes;
+struct PeerMaps {
+  CUtensorMap m[8];
+};
 
 struct GemmProblem {
   int mode;            // 0: A = G (K-major), 1: A = G^T (MN-major)
@@ -996,10 +1012,13 @@ struct GemmParams {
   int done_slot;
 };
 
+// kPeerTma: problems with peers add their tiles with TMA reduce operations (one 4 KB box per
+// 32 x 32 piece, 128-byte bursts on the wire) instead of 16-byte red.global.add per thread.
+template <bool kPeerTma>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 pair_gemm_kernel(const __grid_constant__ CUtensorMap tma0, const __grid_constant__ CUtensorMap tma1,
                  const __grid_constant__ CUtensorMap tmb0, const __grid_constant__ CUtensorMap tmb1,
-                 const GemmParams p) {
+                 const __grid_constant__ PeerMaps peer_maps, const GemmParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t smem_base = smem_u32(smem);
   const int warp = threadIdx.x >> 5;
@@ -1201,6 +1220,38 @@ pair_gemm_kernel(const __grid_constant__ CUtensorMap tma0, const __grid_constant
             }
           }
         }
+      } else if (kPeerTma && pr.npeers > 0) {
+        // owner of this warp's 32 rows (rows_per_peer % 32 == 0: a warp never straddles two ranks)
+        const int64_t m0 = (int64_t)mt * 256 + (int64_t)rank * kPM + q * 32;
+        const int64_t wown = m0 / pr.rows_per_peer;
+        const bool any = m0 < pr.m_rows;
+        const CUtensorMap* pm = &peer_maps.m[any ? wown : 0];
+        const int32_t prow = (int32_t)(m0 - wown * pr.rows_per_peer);
+        const uint32_t my_stage = smem_base + kGemmSmem + (uint32_t)(warp - kEpiWarp0) * kPeerStageBytes;
+        const uint32_t row_addr = my_stage + lane * 128;
+        for (int cc = 0; cc < cols_half; cc += 32) {
+          const int col = half * cols_half + cc;
+          uint32_t v[32];
+          tmem_ld_32x32(tmem_base + lane_base + col, v);
+          tmem_ld_wait();
+          if (!any || pr.d_off + col >= p.dim) continue;      // warp-uniform
+          if (lane == 0) bulk_wait_group_read<0>();           // the previous box has left the stage
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            st_shared_v4(row_addr + ((uint32_t)(j ^ (lane & 7)) << 4),
+                         __float_as_uint(osc * __uint_as_float(v[4 * j])),
+                         __float_as_uint(osc * __uint_as_float(v[4 * j + 1])),
+                         __float_as_uint(osc * __uint_as_float(v[4 * j + 2])),
+                         __float_as_uint(osc * __uint_as_float(v[4 * j + 3])));
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            // rows past the owner's last row and columns past dim are clipped by the tensor map
+            tma_reduce_add_2d(pm, my_stage, pr.d_off + col, prow);
+            bulk_commit_group();
+          }
+        }
       } else {
         for (int cc = 0; cc < cols_half; cc += 32) {
           const int col = half * cols_half + cc;
@@ -1235,6 +1286,10 @@ pair_gemm_kernel(const __grid_constant__ CUtensorMap tma0, const __grid_constant
   }
 
   // every thread's peer adds are ordered before the cluster barrier; one thread per CTA then counts
+  if (kPeerTma && warp >= kEpiWarp0 && lane == 0) {
+    bulk_wait_group<0>();              // the TMA reductions of this warp are complete
+    fence_proxy_async_all();
+  }
   if (p.n_done > 0 && warp >= kEpiWarp0) __threadfence_system();
   tc_fence_before();
   cluster_sync_all();
@@ -1634,6 +1689,22 @@ int build_gemm_problems(const PairGemmArgs& a, GemmParams& p, int64_t& total, in
 }
 }  // namespace
 
+namespace {
+// fp32 row-major [rows, cols] -> boxes [32 rows x 32 cols] (128-byte rows), 128B swizzle
+int make_map32(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return LATTE_ERR_CUDA;
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {32u, 32u};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim, gstride, box,
+                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? LATTE_OK : LATTE_ERR_CUDA;
+}
+}  // namespace
+
 int clip_pair_gemm(const PairGemmArgs& a, cudaStream_t stream) {
   const PairGeom geo = clip_pair_geom(a.n_loc, a.n_all);
   const int64_t g_rows = (int64_t)geo.row_blocks * 2 * geo.ncb * 128;
@@ -1652,9 +1723,34 @@ int clip_pair_gemm(const PairGemmArgs& a, cudaStream_t stream) {
   int ncl;
   rc = build_gemm_problems(a, p, total, ncl);
   if (rc) return rc;
-  LATTE_CUDA_OK(cudaFuncSetAttribute(pair_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     kGemmSmem));
-  pair_gemm_kernel<<<2 * ncl, kThreads, kGemmSmem, stream>>>(tma0, tma1, tmb0, tmb1, p);
+  // TMA reductions into the peers' accumulators: shard rows a multiple of the 32-row warp pieces,
+  // 16-byte aligned rows (LATTE_B200_PEER_RED=1 keeps the per-thread red.global.add form)
+  static const bool no_tma = []() {
+    const char* e = getenv("LATTE_B200_PEER_RED");
+    return e != nullptr && e[0] == '1';
+  }();
+  PeerMaps pm;
+  bool peer_tma = false;
+  if (a.dy_peers && a.n_peers > 1 && !no_tma) {
+    const int64_t rpp = a.n_all / a.n_peers;
+    peer_tma = (rpp % 32) == 0 && (a.ld_dy32 % 4) == 0;
+    for (int w = 0; w < a.n_peers && peer_tma; ++w) {
+      if ((reinterpret_cast<uintptr_t>(a.dy_peers[w]) & 15) != 0) peer_tma = false;
+      else if (make_map32(&pm.m[w], a.dy_peers[w], rpp, a.dim, a.ld_dy32)) peer_tma = false;
+    }
+    if (peer_tma)
+      for (int w = a.n_peers; w < 8; ++w) pm.m[w] = pm.m[0];
+  }
+  if (peer_tma) {
+    LATTE_CUDA_OK(cudaFuncSetAttribute(pair_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       kGemmSmemPeer));
+    pair_gemm_kernel<true><<<2 * ncl, kThreads, kGemmSmemPeer, stream>>>(tma0, tma1, tmb0, tmb1, pm, p);
+  } else {
+    for (int w = 0; w < 8; ++w) pm.m[w] = tma0;        // unused
+    LATTE_CUDA_OK(cudaFuncSetAttribute(pair_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       kGemmSmem));
+    pair_gemm_kernel<false><<<2 * ncl, kThreads, kGemmSmem, stream>>>(tma0, tma1, tmb0, tmb1, pm, p);
+  }
   LATTE_LAUNCH_OK();
   return LATTE_OK;
 }

@@ -297,6 +297,15 @@ __device__ __forceinline__ void tma_store_2d_hint(const CUtensorMap* map, uint32
       ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_src), "r"(c0), "r"(c1), "l"(policy)
       : "memory");
 }
+// 2D tiled reduce-add shared -> global (fp32 tensor map): the box is ADDED into global memory
+// (L2 atomics at the memory's home -- this GPU or, through a peer mapping, another one).
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, uint32_t smem_src, int32_t c0,
+                                                  int32_t c1) {
+  asm volatile(
+      "cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];"
+      ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_src), "r"(c0), "r"(c1)
+      : "memory");
+}
 __device__ __forceinline__ void bulk_commit_group() {
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }

@@ -351,7 +351,10 @@ class _EmulatedRanks:
                                                    (4, 300, 256, 4.0, torch.float16),
                                                    (3, 130, 64, 3.0, torch.bfloat16),
                                                    (2, 600, 768, 5.0, torch.bfloat16),
-                                                   (8, 136, 128, 3.0, torch.bfloat16)])
+                                                   (8, 136, 128, 3.0, torch.bfloat16),
+                                                   (4, 320, 256, 4.0, torch.bfloat16),
+                                                   (8, 64, 128, 3.0, torch.float16),
+                                                   (2, 1024, 512, 4.0, torch.bfloat16)])
 def test_peer_memory_rank_flow_emulated_on_one_gpu(world, n, d, sigma, dtype):
     """latte_comm_push / latte_clip_fwd_rank / latte_clip_bwd(comm) -- the product's multi-rank
     flow -- for every rank on one GPU, two generations of the same slot (credits, accumulator
