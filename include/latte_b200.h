@@ -104,6 +104,24 @@ int latte_comm_push(const latte_comm_t* comm, const void* txt_shard, const void*
 /* Releases the slot's generation without a backward (forward-only call): free = gen on all ranks. */
 int latte_comm_release(const latte_comm_t* comm, void* stream);
 
+/* ---- operand preparation -------------------------------------------------------------- */
+/*
+ * Fused cast (+ opt-in L2 normalisation) of a feature matrix into the tensor-core operand format.
+ * The reference normalises in the towers (src/open_clip/model.py:415-418, 420-437 -- under amp the
+ * result is fp32) and casts inside its autocast matmuls (loss.py:109-116).  One pass: optional
+ * x / max(||x||, 1e-12) in fp32, rounding to `round_dtype` (LATTE_BF16 or LATTE_F16: the reference's
+ * autocast dtype) and storage as fp16 [rows, dim] -- the one 16-bit format all tensor-core kernels
+ * of this library take (a bf16 value is exact in fp16 down to 2^-17).  inv_norm (nullable, [rows]):
+ * 1 / max(||x||, 1e-12) for latte_normalize_bwd.  dim <= 768, dim % 8 == 0, 16-byte aligned rows.
+ */
+int latte_prep_features(const void* x, int64_t ld, int in_dtype, int64_t rows, int64_t dim,
+                        int normalize, int round_dtype, void* out_fp16, int64_t ld_out,
+                        float* inv_norm, void* stream);
+/* Backward of the normalisation: d_x = inv * (g - xh <xh, g>) with xh = x * inv; d_x in x_dtype. */
+int latte_normalize_bwd(const void* g, int64_t ld_g, int g_dtype, const void* x, int64_t ld_x,
+                        int x_dtype, const float* inv_norm, int64_t rows, int64_t dim,
+                        void* d_x, int64_t ld_dx, void* stream);
+
 /* ---- ClipLoss: open_clip/loss.py ------------------------------------------------------ */
 
 /* Bytes of scratch latte_clip_fwd / latte_clip_bwd need for these sizes. */
@@ -316,6 +334,24 @@ int latte_clip_stage_times(const void* img_loc, int64_t ld_img_loc,
                            void* fwd_workspace, size_t fwd_workspace_bytes,
                            void* bwd_workspace, size_t bwd_workspace_bytes,
                            void* stream, int reps, float* stage_ms);
+
+/* One real latte_clip_bwd call (same arguments; with `comm` every rank calls it for the same
+ * generation) with CUDA events around its stages: synchronises the stream and returns the
+ * milliseconds of THIS call's backward stages in stage_ms[LATTE_NUM_STAGES]. */
+int latte_clip_bwd_stage_times(const void* img_loc, int64_t ld_img_loc,
+                               const void* txt_loc, int64_t ld_txt_loc,
+                               const void* img_all, int64_t ld_img_all,
+                               const void* txt_all, int64_t ld_txt_all,
+                               int dtype, int64_t n_loc, int64_t n_all, int64_t dim,
+                               int64_t label_offset, const float* logit_scale,
+                               const float* row_lse_all, const float* col_lse_all,
+                               const float* row_nll_all, const float* col_nll_all,
+                               const float* lse_stats, const float* grad_loss,
+                               float grad_mult, int cross_terms,
+                               void* d_img, void* d_txt, int grad_dtype, int64_t ld_grad,
+                               float* d_txt_partial, const latte_comm_t* comm, int phases,
+                               float* d_scale, void* workspace, size_t workspace_bytes,
+                               void* stream, float* stage_ms);
 
 /* ---- prototype / pseudo-label path: src/training/train.py ---------------------------- */
 

@@ -74,9 +74,12 @@ def _declare(lib):
     lib.latte_clip_bwd.argtypes = [vp, i64, vp, i64, vp, i64, vp, i64, i32, i64, i64, i64, i64,
                                    vp, vp, vp, vp, vp, vp, vp, f32, i32, vp, vp, i32, i64, vp, vp, i32,
                                    vp, vp, sz, vp]    # ..., d_txt_partial, comm, phases, d_scale, ws, bytes, stream
+    lib.latte_clip_bwd_stage_times.argtypes = lib.latte_clip_bwd.argtypes + [c.POINTER(f32)]
     lib.latte_clip_stage_times.argtypes = [vp, i64, vp, i64, vp, i64, vp, i64, i32, i64, i64, i64, i64,
                                            vp, vp, vp, vp, vp, vp, vp, f32, i32, vp, vp, i32, i64,
                                            vp, vp, vp, sz, vp, sz, vp, i32, c.POINTER(f32)]
+    lib.latte_prep_features.argtypes = [vp, i64, i32, i64, i64, i32, i32, vp, i64, vp, vp]
+    lib.latte_normalize_bwd.argtypes = [vp, i64, i32, vp, i64, i32, vp, i64, i64, vp, i64, vp]
     lib.latte_comm_push.argtypes = [vp, vp, vp, i64, i64, vp]
     lib.latte_comm_release.argtypes = [vp, vp]
     lib.latte_clip_fwd_rank_workspace_bytes.argtypes = [i64, i64, i64, i32, c.POINTER(sz)]
@@ -107,9 +110,9 @@ def _declare(lib):
 
 EXPORTS = [
     "latte_version", "latte_status_string", "latte_device_info", "latte_clip_workspace_bytes",
-    "latte_clip_bwd_workspace_bytes", "latte_clip_stage_times", "latte_clip_rank_sweep_supported",
+    "latte_clip_bwd_workspace_bytes", "latte_clip_stage_times", "latte_clip_bwd_stage_times", "latte_clip_rank_sweep_supported",
     "latte_clip_fwd_rows", "latte_clip_fwd_cols_workspace_bytes", "latte_clip_fwd_cols",
-    "latte_comm_push", "latte_comm_release", "latte_clip_fwd_rank_workspace_bytes",
+    "latte_prep_features", "latte_normalize_bwd", "latte_comm_push", "latte_comm_release", "latte_clip_fwd_rank_workspace_bytes",
     "latte_clip_fwd_rank", "latte_siglip_supported", "latte_siglip_workspace_bytes",
     "latte_siglip_fwd", "latte_siglip_bwd",
     "latte_clip_fwd", "latte_clip_bwd", "latte_normalize_rows", "latte_nxc_workspace_bytes",
@@ -221,6 +224,39 @@ def clear_workspace_cache():
 
 def workspace_cache_bytes() -> int:
     return sum(int(t.numel()) for t in _WS_CACHE.values())
+
+
+# ------------------------------------------------------------------------------ operands
+def prep_features(x: torch.Tensor, compute_dtype: torch.dtype, normalize: bool = False):
+    """Fused (normalise +) cast of a feature matrix into the fp16 tensor-core operand:
+    ``fp16(round_to(compute_dtype, normalize(x)))`` -> (operand fp16 [n, dim], inv_norm fp32 [n] or
+    None).  fp16 inputs with fp16 compute and no normalisation are returned as they are (no kernel)."""
+    x = _rows(x.detach(), "features")
+    if x.dtype == torch.float16 and compute_dtype == torch.float16 and not normalize and \
+            x.stride(0) % 8 == 0 and x.data_ptr() % 16 == 0:
+        return x, None
+    if x.stride(0) % 8 != 0 or x.data_ptr() % 16 != 0:
+        x = x.contiguous()
+    n, dim = x.shape
+    out = torch.empty(n, dim, dtype=torch.float16, device=x.device)
+    inv = torch.empty(n, dtype=torch.float32, device=x.device) if normalize else None
+    with torch.cuda.device(x.device):
+        _check(load().latte_prep_features(_ptr(x), x.stride(0), _dt(x), n, dim, int(bool(normalize)),
+                                          _DTYPES[compute_dtype], _ptr(out), dim, _ptr(inv), _stream(x)),
+               "latte_prep_features")
+    return out, inv
+
+
+def normalize_bwd(g: torch.Tensor, x: torch.Tensor, inv_norm: torch.Tensor) -> torch.Tensor:
+    """d_x of ``F.normalize(x, dim=-1)`` given the gradient g of the normalised rows."""
+    g, x = _rows(g.detach(), "grad"), _rows(x.detach(), "features")
+    out = torch.empty(g.shape, dtype=x.dtype, device=g.device)
+    with torch.cuda.device(g.device):
+        _check(load().latte_normalize_bwd(_ptr(g), g.stride(0), _dt(g), _ptr(x), x.stride(0), _dt(x),
+                                          _ptr(inv_norm), g.shape[0], g.shape[1], _ptr(out), out.stride(0),
+                                          _stream(g)),
+               "latte_normalize_bwd")
+    return out
 
 
 # ------------------------------------------------------------------------------ ClipLoss
@@ -417,7 +453,8 @@ def clip_fwd_cols(gathered, img_all, txt_all, n_loc: int, label_offset: int, log
 def clip_bwd(img_loc, txt_loc, img_all, txt_all, label_offset: int, logit_scale,
              row_lse_all, col_lse_all, grad_loss, grad_mult: float, cross_terms: bool,
              grad_dtype=None, row_nll_all=None, col_nll_all=None, partial: bool = False,
-             comm: Optional[LatteComm] = None, phases: int = 3, lse_stats=None, out=None):
+             comm: Optional[LatteComm] = None, phases: int = 3, lse_stats=None, out=None,
+             stage_ms: Optional[dict] = None):
     """-> (d_img[n_loc, dim], d_txt[n_loc, dim], d_scale[1] fp32).  The feature gradients
     come back in ``grad_dtype`` (default: the feature dtype, what autograd needs).
     ``partial=True`` (one-sweep multi-rank mode): the second result is instead the fp32
@@ -462,18 +499,24 @@ def clip_bwd(img_loc, txt_loc, img_all, txt_all, label_offset: int, logit_scale,
     ws = _scratch("bwd" if phases == 3 else f"bwd{0 if comm is None else comm.rank}",
                   _clip_ws_bytes(n_loc, n_all, dim, dt, bwd=True), dev)
     wp, wn = _aligned_ptr(ws)
+    args = (_ptr(img_loc), img_loc.stride(0), _ptr(txt_loc), txt_loc.stride(0),
+            _ptr(img_all), 0 if img_all is None else img_all.stride(0),
+            _ptr(txt_all), txt_all.stride(0),
+            dt, n_loc, n_all, dim, label_offset, _ptr(s), _ptr(row_lse_all),
+            _ptr(col_lse_all), _ptr(row_nll_all), _ptr(col_nll_all),
+            _ptr(lse_stats), _ptr(g),
+            float(grad_mult), int(bool(cross_terms)),
+            _ptr(d_img), _ptr(d_txt), _DTYPES[gdt], dim, _ptr(d_part),
+            ctypes.byref(comm) if comm is not None else None, int(phases),
+            _ptr(d_scale), wp, wn, _stream(img_loc))
     with torch.cuda.device(dev):
-        _check(lib.latte_clip_bwd(_ptr(img_loc), img_loc.stride(0), _ptr(txt_loc), txt_loc.stride(0),
-                                  _ptr(img_all), 0 if img_all is None else img_all.stride(0),
-                                  _ptr(txt_all), txt_all.stride(0),
-                                  dt, n_loc, n_all, dim, label_offset, _ptr(s), _ptr(row_lse_all),
-                                  _ptr(col_lse_all), _ptr(row_nll_all), _ptr(col_nll_all),
-                                  _ptr(lse_stats), _ptr(g),
-                                  float(grad_mult), int(bool(cross_terms)),
-                                  _ptr(d_img), _ptr(d_txt), _DTYPES[gdt], dim, _ptr(d_part),
-                                  ctypes.byref(comm) if comm is not None else None, int(phases),
-                                  _ptr(d_scale), wp, wn, _stream(img_loc)),
-               "latte_clip_bwd")
+        if stage_ms is not None:
+            # the same call with CUDA events around its stages (synchronises the stream)
+            buf = (ctypes.c_float * len(STAGES))()
+            _check(lib.latte_clip_bwd_stage_times(*args, buf), "latte_clip_bwd_stage_times")
+            stage_ms.update({name: float(buf[k]) for k, name in enumerate(STAGES)})
+        else:
+            _check(lib.latte_clip_bwd(*args), "latte_clip_bwd")
     if out is not None or phases != 3:
         return d_img, (d_part if partial else d_txt), d_scale, (d_img, d_txt, d_part, d_scale)
     return d_img, (d_part if partial else d_txt), d_scale

@@ -569,6 +569,108 @@ ds_reduce_kernel(const float* partial, int count, const float* grad_loss, float 
   }
 }
 
+// Fused operand preparation (the reference normalises in the towers, model.py:415-418 / :420-437,
+// and casts inside its autocast matmul, loss.py:109-116): one warp per feature row -- optional L2
+// normalisation in fp32 (F.normalize: x / max(||x||, 1e-12)), rounding to the compute dtype
+// (bf16 or fp16, what the reference's matmul would see) and storage as fp16, the one 16-bit format
+// every tensor-core kernel of the path takes (a bf16 value is exact in fp16 down to 2^-17; below
+// that the absolute error is < 2^-25).  Replaces the ATen cast, the backward's prep pass and its
+// bf16 -> fp16 copies.  dim <= 768, dim % 8 == 0.
+__global__ void __launch_bounds__(256)
+prep_features_kernel(const void* x, int64_t ld, int in_dtype, int64_t rows, int64_t dim, int normalize,
+                     int round_dtype, __half* out, int64_t ld_out, float* inv_norm) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (row >= rows) return;
+  float v[24];
+  float ss = 0.f;
+#pragma unroll
+  for (int it = 0; it < 3; ++it) {
+    const int64_t c = (int64_t)it * 256 + lane * 8;
+    if (c < dim) {
+      if (in_dtype == LATTE_F32) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(static_cast<const float*>(x) + row * ld + c));
+        const float4 b = __ldg(reinterpret_cast<const float4*>(static_cast<const float*>(x) + row * ld + c) + 1);
+        v[it * 8 + 0] = a.x; v[it * 8 + 1] = a.y; v[it * 8 + 2] = a.z; v[it * 8 + 3] = a.w;
+        v[it * 8 + 4] = b.x; v[it * 8 + 5] = b.y; v[it * 8 + 6] = b.z; v[it * 8 + 7] = b.w;
+      } else {
+        const uint4 raw = __ldg(reinterpret_cast<const uint4*>(static_cast<const uint16_t*>(x) + row * ld + c));
+        if (in_dtype == LATTE_BF16) {
+          const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 f = __bfloat1622float2(h[e]);
+            v[it * 8 + 2 * e] = f.x; v[it * 8 + 2 * e + 1] = f.y;
+          }
+        } else {
+          const __half2* h = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 f = __half22float2(h[e]);
+            v[it * 8 + 2 * e] = f.x; v[it * 8 + 2 * e + 1] = f.y;
+          }
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) ss = fmaf(v[it * 8 + e], v[it * 8 + e], ss);
+    }
+  }
+  float inv = 1.0f;
+  if (normalize) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+    if (inv_norm && lane == 0) inv_norm[row] = inv;
+  }
+#pragma unroll
+  for (int it = 0; it < 3; ++it) {
+    const int64_t c = (int64_t)it * 256 + lane * 8;
+    if (c < dim) {
+      uint4 o;
+      __half2* h = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float a = v[it * 8 + 2 * e], b = v[it * 8 + 2 * e + 1];
+        if (normalize) { a *= inv; b *= inv; }
+        if (round_dtype == LATTE_BF16) {
+          a = __bfloat162float(__float2bfloat16_rn(a));
+          b = __bfloat162float(__float2bfloat16_rn(b));
+        }
+        h[e] = __floats2half2_rn(a, b);
+      }
+      *reinterpret_cast<uint4*>(out + row * ld_out + c) = o;
+    }
+  }
+}
+
+// Backward of the fused normalisation: d_x = inv * (g - xh <xh, g>), xh = x * inv (F.normalize).
+// One warp per row; x is the original input and d_x its gradient, both in `x_dtype`.
+__global__ void __launch_bounds__(256)
+normalize_bwd_kernel(const void* g, int64_t ld_g, int g_dtype, const void* x, int64_t ld_x, int x_dtype,
+                     const float* inv_norm, int64_t rows, int64_t dim, void* d_x, int64_t ld_dx) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (row >= rows) return;
+  auto ld1 = [](const void* base, int64_t idx, int dt) -> float {
+    if (dt == LATTE_F32) return static_cast<const float*>(base)[idx];
+    if (dt == LATTE_BF16) return __bfloat162float(static_cast<const __nv_bfloat16*>(base)[idx]);
+    return __half2float(static_cast<const __half*>(base)[idx]);
+  };
+  const float inv = inv_norm[row];
+  float dot = 0.f;
+  for (int64_t c = lane; c < dim; c += 32)
+    dot = fmaf(ld1(x, row * ld_x + c, x_dtype) * inv, ld1(g, row * ld_g + c, g_dtype), dot);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+  for (int64_t c = lane; c < dim; c += 32) {
+    const float xh = ld1(x, row * ld_x + c, x_dtype) * inv;
+    const float r = inv * (ld1(g, row * ld_g + c, g_dtype) - xh * dot);
+    if (x_dtype == LATTE_F32) static_cast<float*>(d_x)[row * ld_dx + c] = r;
+    else if (x_dtype == LATTE_BF16) static_cast<__nv_bfloat16*>(d_x)[row * ld_dx + c] = __float2bfloat16_rn(r);
+    else static_cast<__half*>(d_x)[row * ld_dx + c] = __float2half_rn(r);
+  }
+}
+
 // bf16 -> fp16 copy of a feature matrix (second GEMM of the tc backward, see clip_tc.cu)
 __global__ void bf16_to_fp16_kernel(const __nv_bfloat16* in0, __half* out0,
                                     const __nv_bfloat16* in1, __half* out1, int64_t ld_in,
@@ -1571,6 +1673,35 @@ extern "C" int latte_clip_bwd(const void* img_loc, int64_t ld_img_loc, const voi
                        workspace, workspace_bytes, stream, nullptr);
 }
 
+// One real backward (any mode, including the peer-memory reduce-scatter -- every rank then calls
+// this for the same generation) with CUDA events around its stages; synchronises the stream and
+// returns the milliseconds per stage of THIS call (forward stages stay 0).
+extern "C" int latte_clip_bwd_stage_times(const void* img_loc, int64_t ld_img_loc, const void* txt_loc,
+                                          int64_t ld_txt_loc, const void* img_all, int64_t ld_img_all,
+                                          const void* txt_all, int64_t ld_txt_all, int dtype, int64_t n_loc,
+                                          int64_t n_all, int64_t dim, int64_t label_offset,
+                                          const float* logit_scale, const float* row_lse_all,
+                                          const float* col_lse_all, const float* row_nll_all,
+                                          const float* col_nll_all, const float* lse_stats,
+                                          const float* grad_loss, float grad_mult,
+                                          int cross_terms, void* d_img, void* d_txt, int grad_dtype,
+                                          int64_t ld_grad, float* d_txt_partial, const latte_comm_t* comm,
+                                          int phases, float* d_scale, void* workspace,
+                                          size_t workspace_bytes, void* stream, float* stage_ms) {
+  LATTE_CHECK_ARG(stage_ms);
+  for (int k = 0; k < LATTE_NUM_STAGES; ++k) stage_ms[k] = 0.f;
+  StageTimer tm;
+  const int rc = clip_bwd_impl(img_loc, ld_img_loc, txt_loc, ld_txt_loc, img_all, ld_img_all, txt_all,
+                               ld_txt_all, dtype, n_loc, n_all, dim, label_offset, logit_scale,
+                               row_lse_all, col_lse_all, row_nll_all, col_nll_all, lse_stats, grad_loss,
+                               grad_mult, cross_terms, d_img, d_txt, grad_dtype, ld_grad, d_txt_partial,
+                               comm, phases, d_scale, workspace, workspace_bytes, stream, &tm);
+  const cudaError_t e = cudaStreamSynchronize(static_cast<cudaStream_t>(stream));
+  tm.collect(stage_ms);
+  if (rc) return rc;
+  return (e != cudaSuccess || tm.failed) ? LATTE_ERR_CUDA : LATTE_OK;
+}
+
 extern "C" int latte_clip_stage_times(const void* img_loc, int64_t ld_img_loc, const void* txt_loc,
                                       int64_t ld_txt_loc, const void* img_all, int64_t ld_img_all,
                                       const void* txt_all, int64_t ld_txt_all, int dtype,
@@ -1670,6 +1801,35 @@ extern "C" int latte_comm_release(const latte_comm_t* comm, void* stream) {
   LATTE_CHECK_ARG(comm_ok(comm));
   comm_release_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(comm_flags(comm), comm->world,
                                                                       comm->rank, comm->gen);
+  LATTE_LAUNCH_OK();
+  return LATTE_OK;
+}
+
+extern "C" int latte_prep_features(const void* x, int64_t ld, int in_dtype, int64_t rows, int64_t dim,
+                                   int normalize, int round_dtype, void* out_fp16, int64_t ld_out,
+                                   float* inv_norm, void* stream) {
+  LATTE_CHECK_ARG(x && out_fp16 && rows >= 0 && dim > 0 && ld >= dim && ld_out >= dim);
+  LATTE_CHECK_ARG(in_dtype >= LATTE_F32 && in_dtype <= LATTE_F16);
+  LATTE_CHECK_ARG(round_dtype == LATTE_BF16 || round_dtype == LATTE_F16);
+  if (dim > 768 || (dim % 8) != 0 || (ld % 8) != 0 || (ld_out % 8) != 0 ||
+      (reinterpret_cast<uintptr_t>(x) & 15) != 0 || (reinterpret_cast<uintptr_t>(out_fp16) & 15) != 0)
+    return LATTE_ERR_UNSUPPORTED;
+  if (rows == 0) return LATTE_OK;
+  prep_features_kernel<<<(unsigned)((rows * 32 + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, ld, in_dtype, rows, dim, normalize, round_dtype, static_cast<__half*>(out_fp16), ld_out, inv_norm);
+  LATTE_LAUNCH_OK();
+  return LATTE_OK;
+}
+
+extern "C" int latte_normalize_bwd(const void* g, int64_t ld_g, int g_dtype, const void* x, int64_t ld_x,
+                                   int x_dtype, const float* inv_norm, int64_t rows, int64_t dim,
+                                   void* d_x, int64_t ld_dx, void* stream) {
+  LATTE_CHECK_ARG(g && x && inv_norm && d_x && rows >= 0 && dim > 0);
+  LATTE_CHECK_ARG(g_dtype >= LATTE_F32 && g_dtype <= LATTE_F16 && x_dtype >= LATTE_F32 && x_dtype <= LATTE_F16);
+  LATTE_CHECK_ARG(ld_g >= dim && ld_x >= dim && ld_dx >= dim);
+  if (rows == 0) return LATTE_OK;
+  normalize_bwd_kernel<<<(unsigned)((rows * 32 + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      g, ld_g, g_dtype, x, ld_x, x_dtype, inv_norm, rows, dim, d_x, ld_dx);
   LATTE_LAUNCH_OK();
   return LATTE_OK;
 }

@@ -336,9 +336,23 @@ class _FusedClipLoss(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, image_features, text_features, logit_scale, local_loss, gather_with_grad,
-                rank, world_size, group):
-        img = image_features.detach()
-        txt = text_features.detach()
+                rank, world_size, group, compute_dtype, normalize):
+        # Operands: on the tensor-core path ONE fused kernel per matrix normalises (opt-in), rounds
+        # to the compute dtype and stores fp16 -- no ATen cast, no per-step copies in the backward;
+        # fp32 compute keeps the features as they are (SIMT parity kernels).
+        raw_i, raw_t = image_features.detach(), text_features.detach()
+        inv_i = inv_t = None
+        if compute_dtype in (torch.bfloat16, torch.float16) and \
+                _lib.rank_sweep_supported(compute_dtype, raw_i.shape[1]):
+            img, inv_i = _lib.prep_features(raw_i, compute_dtype, normalize)
+            txt, inv_t = _lib.prep_features(raw_t, compute_dtype, normalize)
+        else:
+            if normalize:
+                raise NotImplementedError(
+                    "latteclip_b200.ClipLoss(normalize_features=True) needs the tensor-core path "
+                    "(16-bit compute dtype, dim <= 768, dim % 8 == 0)")
+            img, txt = raw_i.to(compute_dtype), raw_t.to(compute_dtype)
+        ctx.norm = (raw_i, raw_t, inv_i, inv_t) if normalize else None
         cross_terms = not (world_size > 1 and local_loss and not gather_with_grad)
         rank_sweep = False
         slot = None
@@ -401,6 +415,13 @@ class _FusedClipLoss(torch.autograd.Function):
         return loss
 
     @staticmethod
+    def _grad_dtype(ctx):
+        if ctx.norm is not None:
+            return torch.float32          # the normalisation's backward rounds once, at its end
+        di, dt = ctx.feat_dtypes
+        return di if di == dt and di in (torch.float32, torch.bfloat16, torch.float16) else torch.float32
+
+    @staticmethod
     def backward(ctx, grad_out):
         img, txt, all_img, all_txt, scale, row_lse, col_lse, row_nll, col_nll, lse_stats = ctx.saved_tensors
         (local_loss, gather_with_grad, rank, world_size, group, label_offset, rank_sweep,
@@ -411,6 +432,7 @@ class _FusedClipLoss(torch.autograd.Function):
         grad_mult = 1.0
         if world_size > 1 and not local_loss and not gather_with_grad:
             grad_mult = 1.0 / world_size
+        gdt = _FusedClipLoss._grad_dtype(ctx)
         lease = getattr(ctx, "lease", None)
         slot = lease.slot if lease is not None else None
         if lease is not None and (slot is None or not slot.busy or slot.gen != lease.gen):
@@ -421,7 +443,7 @@ class _FusedClipLoss(torch.autograd.Function):
             # rows AND columns recomputed per rank, nothing exchanged (LATTE_B200_BWD_SWEEPS=2)
             d_img, d_txt, d_scale = _lib.clip_bwd(
                 img, txt, all_img, all_txt, label_offset, scale, row_lse, col_lse, grad_out,
-                grad_mult, True, row_nll_all=row_nll, col_nll_all=col_nll, lse_stats=lse_stats)
+                grad_mult, True, grad_dtype=gdt, row_nll_all=row_nll, col_nll_all=col_nll, lse_stats=lse_stats)
             if slot is not None:
                 slot.release(signal=True)
         elif rank_sweep and slot is not None:
@@ -429,15 +451,15 @@ class _FusedClipLoss(torch.autograd.Function):
             # last kernel publishes the slot's release
             d_img, d_txt, d_scale = _lib.clip_bwd(
                 img, txt, None, all_txt, label_offset, scale, row_lse, col_lse, grad_out,
-                grad_mult, True, row_nll_all=row_nll, col_nll_all=col_nll, comm=slot.comm,
-                lse_stats=lse_stats)
+                grad_mult, True, grad_dtype=gdt, row_nll_all=row_nll, col_nll_all=col_nll,
+                comm=slot.comm, lse_stats=lse_stats)
             slot.release(signal=False)
         elif rank_sweep:
             d_img, d_part, d_scale = _lib.clip_bwd(
                 img, txt, None, all_txt, label_offset, scale, row_lse, col_lse, grad_out,
-                grad_mult, True, row_nll_all=row_nll, col_nll_all=col_nll, partial=True,
+                grad_mult, True, grad_dtype=gdt, row_nll_all=row_nll, col_nll_all=col_nll, partial=True,
                 lse_stats=lse_stats)
-            d_txt = _reduce_scatter_sum(d_part, img.shape[0], rank, group).to(img.dtype)
+            d_txt = _reduce_scatter_sum(d_part, img.shape[0], rank, group).to(gdt)
         else:
             if world_size > 1:
                 four = _all_gather_cat(torch.stack([row_lse, col_lse, row_nll, col_nll], dim=1), group)
@@ -446,7 +468,8 @@ class _FusedClipLoss(torch.autograd.Function):
                 row_all, col_all, rown_all, coln_all = row_lse, col_lse, row_nll, col_nll
             d_img, d_txt, d_scale = _lib.clip_bwd(
                 img, txt, all_img, all_txt, label_offset, scale, row_all, col_all, grad_out,
-                grad_mult, cross_terms, row_nll_all=rown_all, col_nll_all=coln_all, lse_stats=lse_stats)
+                grad_mult, cross_terms, grad_dtype=gdt, row_nll_all=rown_all, col_nll_all=coln_all,
+                lse_stats=lse_stats)
         if lease is not None:
             lease.done()
         if world_size > 1 and not local_loss:
@@ -454,11 +477,20 @@ class _FusedClipLoss(torch.autograd.Function):
             d_scale = d_scale / grad_mult
             dist.all_reduce(d_scale, op=dist.ReduceOp.SUM, group=group)
             d_scale = d_scale / world_size
+        if ctx.norm is not None:
+            raw_i, raw_t, inv_i, inv_t = ctx.norm
+            d_img = _lib.normalize_bwd(d_img, raw_i, inv_i)
+            d_txt = _lib.normalize_bwd(d_txt, raw_t, inv_t)
+        di_t, dt_t = ctx.feat_dtypes
+        if d_img.dtype != di_t:
+            d_img = d_img.to(di_t)
+        if d_txt.dtype != dt_t:
+            d_txt = d_txt.to(dt_t)
         s_dtype, s_shape = ctx.scale_meta
         d_scale = d_scale.reshape(s_shape).to(s_dtype)
         need = ctx.needs_input_grad
         return (d_img if need[0] else None, d_txt if need[1] else None,
-                d_scale if need[2] else None, None, None, None, None, None)
+                d_scale if need[2] else None, None, None, None, None, None, None, None)
 
 
 class ClipLoss(nn.Module):
@@ -471,8 +503,14 @@ class ClipLoss(nn.Module):
             rank=0,
             world_size=1,
             use_horovod=False,
+            normalize_features=False,
     ):
         super().__init__()
+        # Extension (not in the reference signature; default off, SURVEY fact 4: ClipLoss does not
+        # normalise): L2-normalise both feature matrices inside the fused operand-preparation
+        # kernel, i.e. what encode_image / encode_text(normalize=True) do in the towers
+        # (model.py:415-418, 420-437), with the matching backward.
+        self.normalize_features = normalize_features
         self.local_loss = local_loss
         self.gather_with_grad = gather_with_grad
         self.cache_labels = cache_labels
@@ -534,8 +572,9 @@ class ClipLoss(nn.Module):
             cdt = torch.float32
         with torch.autocast(device_type="cuda", enabled=False):
             total_loss = _FusedClipLoss.apply(
-                image_features.to(cdt), text_features.to(cdt), logit_scale,
-                self.local_loss, self.gather_with_grad, self.rank, self.world_size, self.group)
+                image_features, text_features, logit_scale,
+                self.local_loss, self.gather_with_grad, self.rank, self.world_size, self.group,
+                cdt, self.normalize_features)
         return {"contrastive_loss": total_loss} if output_dict else total_loss
 
 

@@ -46,7 +46,7 @@ def _worker(rank, world, port, one_sweep, ret):
             mod = lb.ClipLoss(local_loss=local_loss, gather_with_grad=gwg, cache_labels=True,
                               rank=rank, world_size=world)
             # forward() insists on CUDA tensors only through _lib; the double accepts CPU ones
-            loss = lb.loss._FusedClipLoss.apply(il, tl, s, local_loss, gwg, rank, world, None)
+            loss = lb.loss._FusedClipLoss.apply(il, tl, s, local_loss, gwg, rank, world, None, il.dtype, False)
             loss.backward()
             key = f"ll{int(local_loss)}_gwg{int(gwg)}"
             out[key] = dict(loss=float(loss), dI=il.grad.numpy(), dT=tl.grad.numpy(), ds=float(s.grad))

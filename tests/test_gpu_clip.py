@@ -629,3 +629,95 @@ def test_large_batch_65536_w1():
     sds = 100.0 * float(ds)
     assert abs(eul_i - sds) <= 2e-3 * abs(sds) + 1e-6 and abs(eul_t - sds) <= 2e-3 * abs(sds) + 1e-6
     _lib.clear_workspace_cache()
+
+
+# ------------------------------------------------------------------ fused operand preparation (g1)
+@pytest.mark.parametrize("in_dtype", [torch.float32, torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("cdt", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("normalize", [False, True])
+def test_prep_features_matches_torch(in_dtype, cdt, normalize):
+    """latte_prep_features == fp16(round_to(cdt, F.normalize(x))) (model.py:415-418 + the autocast
+    cast of loss.py:109-116), bit for bit without normalisation, to one rounding with it."""
+    from latteclip_b200 import _lib
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(11)
+    x = (torch.randn(300, 520, generator=g) * 3.0).to(dev).to(in_dtype)
+    out, inv = _lib.prep_features(x, cdt, normalize)
+    ref = x.float()
+    if normalize:
+        ref = F.normalize(ref, dim=-1)
+        assert torch.allclose(inv, 1.0 / x.float().norm(dim=1), rtol=2e-6)
+    ref = ref.to(cdt).to(torch.float16)
+    assert out.dtype == torch.float16 and out.shape == x.shape
+    if normalize:
+        ulp = 2.0 ** -8 if cdt == torch.bfloat16 else 2.0 ** -11
+        assert float(((out.float() - ref.float()).abs() / ref.float().abs().clamp_min(1e-3)).max()) <= 2 * ulp
+        assert float((out != ref).float().mean()) < 0.01          # a rounding boundary now and then
+    else:
+        assert torch.equal(out, ref)
+
+
+@pytest.mark.parametrize("in_dtype,cdt", [(torch.float32, torch.bfloat16), (torch.float32, torch.float16),
+                                          (torch.bfloat16, torch.bfloat16)])
+def test_normalize_features_option_matches_reference_towers(in_dtype, cdt):
+    """ClipLoss(normalize_features=True) on raw tower outputs == the reference's
+    encode_*(normalize=True) (model.py:415-418, 420-437) followed by ClipLoss: loss and the
+    gradients w.r.t. the RAW features (through F.normalize), fp64 oracle on the rounded operands."""
+    import latteclip_b200 as lb
+    from oracle.clip_loss import clip_loss_reference
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(5)
+    n, d = 384, 256
+    base = torch.randn(n, d, generator=g)
+    ri = (base * (0.5 + torch.rand(n, 1, generator=g) * 4)).to(in_dtype)
+    rt = ((base + 0.35 * torch.randn(n, d, generator=g)) * (0.5 + torch.rand(n, 1, generator=g) * 4)).to(in_dtype)
+    il = ri.to(dev).requires_grad_(True)
+    tl = rt.to(dev).requires_grad_(True)
+    s = torch.tensor(100.0, device=dev, requires_grad=True)
+    with torch.autocast("cuda", dtype=cdt):
+        loss = lb.ClipLoss(normalize_features=True)(il, tl, s)
+    loss.backward()
+    # oracle: normalise in fp64, loss on the operands the kernels saw (rounded to cdt), gradients
+    # through the exact normalisation
+    ci = ri.double().requires_grad_(True)
+    ct = rt.double().requires_grad_(True)
+    cs = torch.tensor(100.0, dtype=torch.float64, requires_grad=True)
+    ni, nt = F.normalize(ci, dim=-1), F.normalize(ct, dim=-1)
+    qi = ni + (F.normalize(ri.float(), dim=-1).to(cdt).double() - ni).detach()      # straight-through rounding
+    qt = nt + (F.normalize(rt.float(), dim=-1).to(cdt).double() - nt).detach()
+    ref = clip_loss_reference(qi, qt, cs)
+    ref.backward()
+    assert abs(float(loss) - float(ref)) <= 3e-5 * abs(float(ref)) + 2e-5
+    tol = GRAD_RTOL_BF16_OUT if in_dtype == torch.bfloat16 else GRAD_RTOL_16
+    assert il.grad.dtype == in_dtype and tl.grad.dtype == in_dtype
+    assert rel(il.grad, ci.grad) < tol
+    assert rel(tl.grad, ct.grad) < tol
+    assert abs(float(s.grad) - float(cs.grad)) <= 2e-3 * abs(float(cs.grad))
+
+
+def test_autocast_fp32_inputs_launch_no_aten_cast():
+    """Under torch.autocast with fp32 tower outputs (F.normalize autocasts to fp32, model.py:418)
+    the cast is part of the fused operand kernel: no ATen copy / cast kernel in the step."""
+    import latteclip_b200 as lb
+    from torch.profiler import profile, ProfilerActivity
+    dev = torch.device("cuda:0")
+    i, t = synth(512, 256, 4.0, 77)
+    il = i.to(dev).requires_grad_(True)
+    tl = t.to(dev).requires_grad_(True)
+    s = torch.tensor(100.0, device=dev, requires_grad=True)
+    fn = lb.ClipLoss()
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        fn(il, tl, s).backward()                       # warm-up (module load, workspace)
+    il.grad = tl.grad = s.grad = None
+    torch.cuda.synchronize()
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            loss = fn(il, tl, s)
+        loss.backward()
+        torch.cuda.synchronize()
+    names = [e.key for e in prof.key_averages()]
+    assert any("prep_features_kernel" in k for k in names), names
+    bad = [k for k in names if ("copy" in k.lower() or "cast" in k.lower() or "convert" in k.lower())
+           and "latte" not in k]
+    assert not bad, bad
+    assert il.grad.dtype == torch.float32

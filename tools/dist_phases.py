@@ -26,6 +26,7 @@ def ev():
     e = torch.cuda.Event(enable_timing=True); e.record(); return e
 off = rank * n
 reps = 25
+all_marks = []
 for it in range(reps):
     slot = state.acquire()
     marks = [ev()]
@@ -41,13 +42,18 @@ for it in range(reps):
                           row_nll_all=rown_all, col_nll_all=coln_all, comm=slot.comm, phases=ph,
                           lse_stats=stats, out=None if b is None else b[-1]); marks.append(ev())
     slot.release(signal=False)
-    torch.cuda.synchronize()
-    if it >= 5:
-        for k, nm in enumerate(names):
-            tot[nm] += marks[k].elapsed_time(marks[k + 1])
-t = torch.tensor([tot[k] for k in names], device=dev)
-dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    all_marks.append(marks)
+torch.cuda.synchronize()
+for marks in all_marks[5:]:
+    for k, nm in enumerate(names):
+        tot[nm] += marks[k].elapsed_time(marks[k + 1])
+step_ms = all_marks[5][0].elapsed_time(all_marks[-1][-1]) / (reps - 5)
+t = torch.tensor([tot[k] / (reps - 5) * 1e3 for k in names] + [step_ms * 1e3], device=dev)
+allt = [torch.zeros_like(t) for _ in range(world)]
+dist.all_gather(allt, t)
 if rank == 0:
-    print(f"world {world} N {N}: " + ", ".join(f"{k} {float(v) / (reps - 5) * 1e3:.0f}us" for k, v in zip(names, t)),
-          f"| sum {float(t.sum()) / (reps - 5):.3f} ms", flush=True)
+    print(f"world {world} N {N} (us per phase, one line per rank; no host sync inside the loop)")
+    print("  rank " + " | ".join(n_[:18] for n_ in names) + " | step")
+    for r, v in enumerate(allt):
+        print(f"  {r}    " + " | ".join(f"{float(x):18.0f}" for x in v[:-1]) + f" | {float(v[-1]):.0f}", flush=True)
 dist.barrier(); dist.destroy_process_group()
