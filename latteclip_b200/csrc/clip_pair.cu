@@ -1010,6 +1010,12 @@ struct GemmParams {
   unsigned int* done_counter;
   int done_gen;
   int done_slot;
+  // Two-part schedule (fused reduce-scatter): the units [0, split_units) -- the problems that add
+  // into the peers -- are dealt evenly to ALL clusters and run first, the local problems after
+  // them.  Every cluster's remote reductions are then out in the first part of the kernel, the
+  // "done" flag is published when the last CTA finishes that part, and the transfer drains behind
+  // the local product instead of after the kernel.  0 = one part.
+  int64_t split_units;
 };
 
 // kPeerTma: problems with peers add their tiles with TMA reduce operations (one 4 KB box per
@@ -1043,8 +1049,14 @@ pair_gemm_kernel(const __grid_constant__ CUtensorMap tma0, const __grid_constant
   const int64_t total = ubase[4];
   const int64_t ncl = gridDim.x >> 1;
   const int64_t cl = blockIdx.x >> 1;
-  const int64_t u0 = cl * total / ncl;
-  const int64_t u1 = (cl + 1) * total / ncl;
+  const int nparts = p.split_units > 0 ? 2 : 1;
+  // this cluster's contiguous unit range inside part `part`
+  auto part_range = [&](int part, int64_t& a, int64_t& b) {
+    const int64_t lo = part == 0 ? 0 : p.split_units;
+    const int64_t hi = (nparts == 2 && part == 0) ? p.split_units : total;
+    a = lo + cl * (hi - lo) / ncl;
+    b = lo + (cl + 1) * (hi - lo) / ncl;
+  };
 
   if (warp == 0 && elect_one()) {
     prefetch_tensormap(&tma0);
@@ -1071,7 +1083,7 @@ pair_gemm_kernel(const __grid_constant__ CUtensorMap tma0, const __grid_constant
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   // A segment = (problem, output tile, contiguous chunk range); all roles walk the same list.
-  auto next_segment = [&](int64_t u, int& pi, int& mt, int& k0, int& k1) {
+  auto next_segment = [&](int64_t u, int64_t u1, int& pi, int& mt, int& k0, int& k1) {
     pi = 0;
     while (pi + 1 < p.nprob && u >= ubase[pi + 1]) ++pi;
     const int64_t local = u - ubase[pi];
@@ -1090,9 +1102,12 @@ pair_gemm_kernel(const __grid_constant__ CUtensorMap tma0, const __grid_constant
       const uint64_t stream_pol = policy_evict_first(); // G: read once per product
       int stage = 0;
       uint32_t phase = 0;
+      for (int part = 0; part < nparts; ++part) {
+      int64_t u0, u1;
+      part_range(part, u0, u1);
       for (int64_t u = u0; u < u1;) {
         int pi, mt, k0, k1;
-        next_segment(u, pi, mt, k0, k1);
+        next_segment(u, u1, pi, mt, k0, k1);
         const int mode = p.prob[pi].mode;
         const int nhalf = p.prob[pi].nhalf;
         const int dch0 = p.prob[pi].d_off / 64;
@@ -1123,6 +1138,7 @@ pair_gemm_kernel(const __grid_constant__ CUtensorMap tma0, const __grid_constant
         }
         u += k1 - k0;
       }
+      }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer (leader CTA)
@@ -1130,9 +1146,12 @@ pair_gemm_kernel(const __grid_constant__ CUtensorMap tma0, const __grid_constant
       int stage = 0;
       uint32_t phase = 0;
       int seg = 0;
+      for (int part = 0; part < nparts; ++part) {
+      int64_t u0, u1;
+      part_range(part, u0, u1);
       for (int64_t u = u0; u < u1; ++seg) {
         int pi, mt, k0, k1;
-        next_segment(u, pi, mt, k0, k1);
+        next_segment(u, u1, pi, mt, k0, k1);
         const int mode = p.prob[pi].mode;
         const int nmma = (p.prob[pi].nhalf + 1) / 2;
         mbar_wait(bar_tempty, (seg & 1) ^ 1);
@@ -1157,6 +1176,7 @@ pair_gemm_kernel(const __grid_constant__ CUtensorMap tma0, const __grid_constant
         tc_commit_pair(bar_tfull, 3);
         u += k1 - k0;
       }
+      }
     }
   } else if (warp >= kEpiWarp0) {
     // ------------------------------------------------------------ epilogue (both CTAs)
@@ -1165,9 +1185,12 @@ pair_gemm_kernel(const __grid_constant__ CUtensorMap tma0, const __grid_constant
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     const uint32_t lead_tempty = mapa_rank(bar_tempty, 0);
     int seg = 0;
+    for (int part = 0; part < nparts; ++part) {
+    int64_t u0, u1;
+    part_range(part, u0, u1);
     for (int64_t u = u0; u < u1; ++seg) {
       int pi, mt, k0, k1;
-      next_segment(u, pi, mt, k0, k1);
+      next_segment(u, u1, pi, mt, k0, k1);
       const GemmProblem& pr = p.prob[pi];
       const int cols_half = pr.nhalf * 64;        // accumulator columns per epilogue half
       const int64_t m = (int64_t)mt * 256 + (int64_t)rank * kPM + q * 32 + lane;
@@ -1283,18 +1306,38 @@ pair_gemm_kernel(const __grid_constant__ CUtensorMap tma0, const __grid_constant
       if (lane == 0) mbar_arrive_cluster(lead_tempty);
       u += k1 - k0;
     }
+    if (part == 0 && nparts == 2 && p.n_done > 0) {
+      // End of the peer part of this CTA: wait until its reductions are complete (the MMAs of the
+      // local part run meanwhile), then count the CTA; the last one publishes "done" on every rank.
+      if (kPeerTma && lane == 0) {
+        bulk_wait_group<0>();
+        fence_proxy_async_all();
+      }
+      __threadfence_system();
+      named_bar_sync(2, kGemmEpiWarps * 32);
+      if (warp == kEpiWarp0 && lane == 0) {
+        if (atomicInc(p.done_counter, gridDim.x - 1) == gridDim.x - 1) {
+          __threadfence_system();
+          for (int w = 0; w < p.n_done; ++w)
+            if (p.done_flags[w]) st_release_sys(p.done_flags[w] + p.done_slot, p.done_gen);
+        }
+      }
+    }
+    }
   }
 
-  // every thread's peer adds are ordered before the cluster barrier; one thread per CTA then counts
+  // one-part schedule with peers: the adds are ordered before the cluster barrier and the last CTA
+  // signals after it
+  const bool tail_signal = p.n_done > 0 && nparts == 1;
   if (kPeerTma && warp >= kEpiWarp0 && lane == 0) {
     bulk_wait_group<0>();              // the TMA reductions of this warp are complete
     fence_proxy_async_all();
   }
-  if (p.n_done > 0 && warp >= kEpiWarp0) __threadfence_system();
+  if (tail_signal && warp >= kEpiWarp0) __threadfence_system();
   tc_fence_before();
   cluster_sync_all();
   if (warp == 2) tmem_dealloc_pair(tmem_base, 512);
-  if (p.n_done > 0 && threadIdx.x == 0) {
+  if (tail_signal && threadIdx.x == 0) {
     if (atomicInc(p.done_counter, gridDim.x - 1) == gridDim.x - 1) {
       __threadfence_system();
       for (int w = 0; w < p.n_done; ++w)
@@ -1313,6 +1356,7 @@ struct FixupParams {
   int nprob;
   int64_t ubase[5];
   int64_t total, ncl;
+  int64_t split_units;               // two-part schedule of the GEMM (0 = one part)
   int m_tiles[4], k_chunks[4], d_off[4], ncols[4];
   int64_t m_rows[4];
   float* acc[4];
@@ -1331,9 +1375,14 @@ __global__ void __launch_bounds__(256) gemm_fixup_kernel(const FixupParams p) {
   int pi = 0, t = blockIdx.x;
   while (pi < p.nprob && t >= p.m_tiles[pi]) { t -= p.m_tiles[pi]; ++pi; }
   if (pi >= p.nprob || p.out[pi] == nullptr) return;
-  const int64_t u_first = p.ubase[pi] + (int64_t)t * p.k_chunks[pi];
+  int64_t u_first = p.ubase[pi] + (int64_t)t * p.k_chunks[pi];
+  // unit range of the schedule part this problem belongs to
+  const bool second = p.split_units > 0 && u_first >= p.split_units;
+  const int64_t part_lo = second ? p.split_units : 0;
+  const int64_t part_n = (p.split_units > 0 && !second ? p.split_units : p.total) - part_lo;
+  u_first -= part_lo;
   const int64_t u_last = u_first + p.k_chunks[pi] - 1;
-  if (cluster_of_tile(u_first, p.total, p.ncl) == cluster_of_tile(u_last, p.total, p.ncl)) return;
+  if (cluster_of_tile(u_first, part_n, p.ncl) == cluster_of_tile(u_last, part_n, p.ncl)) return;
   const int c0 = p.d_off[pi];
   const int c1 = min(p.dim, c0 + p.ncols[pi]);
   const int per_row = (c1 - c0) / 4;
@@ -1629,7 +1678,12 @@ int build_gemm_problems(const PairGemmArgs& a, GemmParams& p, int64_t& total, in
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   p.nprob = 0;
   total = 0;
-  for (int prod = 0; prod < nproducts; ++prod) {
+  p.split_units = 0;
+  // with peers the text-side product (the one that adds into the other ranks) goes first
+  const bool peers_first = nproducts == 2 && a.dy_peers && a.n_peers > 1;
+  for (int pidx = 0; pidx < nproducts; ++pidx) {
+    const int prod = peers_first ? 1 - pidx : pidx;
+    if (peers_first && pidx == 1) p.split_units = total;
     int done = 0;
     for (int sl = 0; sl < nslab; ++sl) {
       const int nh = (units128 - done + (nslab - sl) - 1) / (nslab - sl);   // even split
@@ -1766,6 +1820,7 @@ int clip_pair_gemm_fixup(const PairGemmArgs& a, int cast, cudaStream_t stream) {
   FixupParams f = {};
   f.nprob = g.nprob;
   f.total = total; f.ncl = ncl;
+  f.split_units = g.split_units;
   f.ld_acc = a.ld32; f.out_dtype = a.out_dtype; f.ld_out = a.ld_out; f.out_scale = a.out_scale;
   f.dim = (int)a.dim;
   int tiles = 0;
