@@ -3,6 +3,8 @@
 #include "latte_common.cuh"
 #include "tc_ptx.cuh"
 
+#include <stdlib.h>
+
 namespace latte {
 
 int device_sm_count() {
@@ -116,16 +118,16 @@ col_merge_kernel(const float* gathered, int64_t stride, int world, int64_t n_loc
   const int64_t j = (int64_t)blockIdx.x * 256 + threadIdx.x;
   if (j >= n_all) return;
   const float* own = gathered + (j / n_loc) * stride + 2 * n_all + (j % n_loc);
-  const float label_logit = __ldcv(own + 2 * n_loc);
-  row_lse_all[j] = __ldcv(own);
-  row_nll_all[j] = __ldcv(own + n_loc);
+  const float label_logit = __ldcg(own + 2 * n_loc);
+  row_lse_all[j] = __ldcg(own);
+  row_nll_all[j] = __ldcg(own + n_loc);
   label_logit_all[j] = label_logit;
   float mx[LATTE_COMM_MAX_RANKS], lx[LATTE_COMM_MAX_RANKS];
 #pragma unroll
   for (int w = 0; w < LATTE_COMM_MAX_RANKS; ++w) {
     // scalar loads: the rank stride 2 N + 3 n is odd for odd shard sizes
-    mx[w] = w < world ? __ldcv(gathered + (int64_t)w * stride + 2 * j) : -INFINITY;
-    lx[w] = w < world ? __ldcv(gathered + (int64_t)w * stride + 2 * j + 1) : 0.f;
+    mx[w] = w < world ? __ldcg(gathered + (int64_t)w * stride + 2 * j) : -INFINITY;
+    lx[w] = w < world ? __ldcg(gathered + (int64_t)w * stride + 2 * j + 1) : 0.f;
   }
   float M = -INFINITY, L = 0.f;
 #pragma unroll
@@ -161,8 +163,8 @@ col_merge_exact_kernel(const int* gate, const float* exact, int world, int64_t n
   if (j >= n_all) return;
   float M = -INFINITY, L = 0.f;
   for (int w = 0; w < world; ++w) {
-    const float m = __ldcv(exact + (int64_t)w * 2 * n_all + 2 * j);
-    const float l = __ldcv(exact + (int64_t)w * 2 * n_all + 2 * j + 1);
+    const float m = __ldcg(exact + (int64_t)w * 2 * n_all + 2 * j);
+    const float l = __ldcg(exact + (int64_t)w * 2 * n_all + 2 * j + 1);
     if (!(m > -INFINITY)) continue;
     if (m > M) {
       L = L * exp2f(M - m) + l;
@@ -712,9 +714,14 @@ struct PeerFlags {
 // of the grid to get here.  `counter` wraps back to 0.
 __device__ __forceinline__ bool grid_last_cta(unsigned int* counter) {
   __shared__ bool s_last;
-  __threadfence_system();            // this thread's stores before the counter bump, system-wide
+  // the CTA barrier orders every thread's stores before thread 0's system-scope fence, which is
+  // cumulative: one fence per CTA instead of one per thread (a MEMBAR.SYS per thread made these
+  // kernels several times slower)
   __syncthreads();
-  if (threadIdx.x == 0) s_last = atomicInc(counter, gridDim.x - 1) == gridDim.x - 1;
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    s_last = atomicInc(counter, gridDim.x - 1) == gridDim.x - 1;
+  }
   __syncthreads();
   return s_last;
 }
@@ -789,40 +796,38 @@ comm_payload_kernel(const int* gate, const float* pmax, const float* psum, int n
     signal_all(flags, world, kind, rank, gen);
 }
 
-// Last kernel of the fused reduce-scatter: wait until every rank's GEMM has published its adds,
-// turn this rank's accumulator into d_txt (the adders applied the scale), clear it for the slot's
-// next generation and release the slot.
+// Last step of the fused reduce-scatter: wait until every rank's GEMM has published its adds and
+// turn this rank's accumulator into d_txt (the adders applied the scale).  The accumulator is then
+// cleared for the slot's next generation by a memset node and the slot released by
+// comm_release_kernel (a zero store into the lines just read, fused in here, made this kernel
+// 3-5x slower than the three operations together).
 __global__ void __launch_bounds__(256)
-comm_acc_finish_kernel(float* acc, int64_t n_loc, int64_t dim, void* d_txt, int out_dtype,
-                       int64_t ld_out, PeerFlags flags, int* my_flags, int world, int rank, int gen) {
+comm_acc_finish_kernel(const float* acc, int64_t n_loc, int64_t dim, void* d_txt, int out_dtype,
+                       int64_t ld_out, const int* my_flags, int world, int gen) {
   if (my_flags) {
     if ((int)threadIdx.x < world) ptx::flag_wait_ge(my_flags + kFlagDone + threadIdx.x, gen);
     __syncthreads();
   }
+  // the acquire above orders these reads after the peers' adds (which happen in this GPU's L2, the
+  // point of coherence of its memory); .cg keeps them out of L1
   const int64_t per_row = dim / 4;
   const int64_t total = n_loc * per_row;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride) {
     const int64_t r = idx / per_row, c = (idx % per_row) * 4;
-    float4* a = reinterpret_cast<float4*>(acc + r * dim + c);
-    const float4 v = __ldcv(a);          // written by peer GPUs: bypass any stale line
-    *a = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 v = __ldcg(reinterpret_cast<const float4*>(acc + r * dim + c));
     if (out_dtype == LATTE_F32) {
-      float* po = static_cast<float*>(d_txt) + r * ld_out + c;
-      po[0] = v.x; po[1] = v.y; po[2] = v.z; po[3] = v.w;
+      *reinterpret_cast<float4*>(static_cast<float*>(d_txt) + r * ld_out + c) = v;
     } else if (out_dtype == LATTE_BF16) {
-      __nv_bfloat16* po = static_cast<__nv_bfloat16*>(d_txt) + r * ld_out + c;
-      po[0] = __float2bfloat16_rn(v.x); po[1] = __float2bfloat16_rn(v.y);
-      po[2] = __float2bfloat16_rn(v.z); po[3] = __float2bfloat16_rn(v.w);
+      __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+      *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(d_txt) + r * ld_out + c) =
+          make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
     } else {
-      __half* po = static_cast<__half*>(d_txt) + r * ld_out + c;
-      po[0] = __float2half_rn(v.x); po[1] = __float2half_rn(v.y);
-      po[2] = __float2half_rn(v.z); po[3] = __float2half_rn(v.w);
+      __half2 lo = __floats2half2_rn(v.x, v.y), hi = __floats2half2_rn(v.z, v.w);
+      *reinterpret_cast<uint2*>(static_cast<__half*>(d_txt) + r * ld_out + c) =
+          make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
     }
   }
-  if (!my_flags) return;
-  if (grid_last_cta(reinterpret_cast<unsigned int*>(my_flags + kFlagCounter + kCntFinish)))
-    signal_all(flags, world, kFlagFree, rank, gen);
 }
 
 struct WsLayout {
@@ -1349,6 +1354,21 @@ extern "C" int latte_clip_fwd_rank(const latte_comm_t* comm, const void* img_loc
   return LATTE_OK;
 }
 
+// cast accumulator -> d_txt, clear it, release the slot (three stream-ordered operations)
+static int comm_finish_reduce_scatter(const latte_comm_t* comm, int64_t n_loc, int64_t dim, void* d_txt,
+                                      int grad_dtype, int64_t ld_grad, cudaStream_t st) {
+  float* acc = comm->acc[comm->rank];
+  comm_acc_finish_kernel<<<(unsigned)(8 * device_sm_count()), 256, 0, st>>>(
+      acc, n_loc, dim, d_txt, grad_dtype, ld_grad, comm->flags[comm->rank], comm->world, comm->gen);
+  LATTE_LAUNCH_OK();
+  LATTE_CUDA_OK(cudaMemsetAsync(acc, 0, (size_t)n_loc * (size_t)dim * sizeof(float), st));
+  if (comm->flags[comm->rank]) {
+    comm_release_kernel<<<1, 32, 0, st>>>(comm_flags(comm), comm->world, comm->rank, comm->gen);
+    LATTE_LAUNCH_OK();
+  }
+  return LATTE_OK;
+}
+
 static int clip_bwd_impl(const void* img_loc, int64_t ld_img_loc, const void* txt_loc,
                          int64_t ld_txt_loc, const void* img_all, int64_t ld_img_all,
                          const void* txt_all, int64_t ld_txt_all, int dtype, int64_t n_loc,
@@ -1365,7 +1385,7 @@ static int clip_bwd_impl(const void* img_loc, int64_t ld_img_loc, const void* tx
                   d_scale && workspace);
   LATTE_CHECK_ARG(!(d_txt_partial && comm));
   LATTE_CHECK_ARG(!comm || (comm_ok(comm) && n_all == n_loc * comm->world && d_txt &&
-                            comm->acc[comm->rank] && (dim % 4) == 0));
+                            comm->acc[comm->rank] && (dim % 4) == 0 && (ld_grad % 4) == 0));
   LATTE_CHECK_ARG((row_nll_all == nullptr) == (col_nll_all == nullptr));
   LATTE_CHECK_ARG(n_loc > 0 && n_all >= n_loc && dim > 0);
   LATTE_CHECK_ARG(label_offset >= 0 && label_offset + n_loc <= n_all);
@@ -1381,11 +1401,7 @@ static int clip_bwd_impl(const void* img_loc, int64_t ld_img_loc, const void* tx
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (comm && !(phases & 1)) {
     // second phase only (single-process tests drive the ranks phase by phase)
-    comm_acc_finish_kernel<<<(unsigned)(2 * device_sm_count()), 256, 0, st>>>(
-        comm->acc[comm->rank], n_loc, dim, d_txt, grad_dtype, ld_grad, comm_flags(comm),
-        comm->flags[comm->rank], comm->world, comm->rank, comm->gen);
-    LATTE_LAUNCH_OK();
-    return LATTE_OK;
+    return comm_finish_reduce_scatter(comm, n_loc, dim, d_txt, grad_dtype, ld_grad, st);
   }
   const WsLayout w = ws_layout(n_loc, n_all, dim, dtype, true);
   if (workspace_bytes < w.total) return LATTE_ERR_WORKSPACE;
@@ -1618,10 +1634,8 @@ static int clip_bwd_impl(const void* img_loc, int64_t ld_img_loc, const void* tx
     ds_reduce_kernel<<<1, 256, 0, st>>>(dsp, 2 * dsn, grad_loss, grad_mult, n_loc, d_scale);
     LATTE_LAUNCH_OK();
     if (comm && (phases & 2)) {
-      comm_acc_finish_kernel<<<(unsigned)(2 * device_sm_count()), 256, 0, st>>>(
-          comm->acc[comm->rank], n_loc, dim, d_txt, grad_dtype, ld_grad, comm_flags(comm),
-          comm->flags[comm->rank], comm->world, comm->rank, comm->gen);
-      LATTE_LAUNCH_OK();
+      rc = comm_finish_reduce_scatter(comm, n_loc, dim, d_txt, grad_dtype, ld_grad, st);
+      if (rc) return rc;
     }
     LATTE_MARK(LATTE_STAGE_BWD_FINISH);
     return LATTE_OK;
