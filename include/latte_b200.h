@@ -382,6 +382,31 @@ int latte_nxc_argmax_margin(const void* x, int64_t ldx, int x_dtype,
                             void* workspace, size_t workspace_bytes, void* stream);
 
 /*
+ * The step's N x C products as ONE HBM-bound launch (C <= 64, e.g. DTD's 47 classes; SURVEY 2c
+ * K8/K9: the pseudo-label argmax of train.py:410-411 and the compute_text_weights margins of
+ * train.py:292-303 / :444-449 share a launch).  Prototypes are split once per matrix into three
+ * bf16 planes by latte_nxc_split_prototypes -- optionally fused with the row normalisation of
+ * train.py:384-389 (normalized_out, nullable, then receives F.normalize(protos) in fp32) -- and
+ * every job streams its feature rows exactly once: fp32 / fp16 rows are split into bf16 planes
+ * inside the kernel (no materialised copies), bf16 rows are used as they are.  Results are as
+ * accurate as an fp32 FMA loop (see latte_nxc_argmax_margin).  All jobs of one call must share
+ * the operand class (all bf16, or all fp32 / fp16).  planes: latte_nxc_planes_bytes() bytes,
+ * 128-byte aligned, caller-owned.
+ */
+typedef struct latte_nxc_job {
+  const void* x; int64_t ldx; int x_dtype;     /* [n, dim] feature rows                          */
+  int64_t n, dim;
+  const void* planes; int64_t num_classes;     /* from latte_nxc_split_prototypes, C <= 64        */
+  float scale;                                 /* top1_out = scale * max_c sim                    */
+  int64_t* argmax_out; float* margin_out; float* top1_out;   /* [n] each, nullable                */
+} latte_nxc_job_t;
+int latte_nxc_planes_bytes(int64_t num_classes, int64_t dim, size_t* bytes);
+int latte_nxc_split_prototypes(const float* protos, int64_t ld, int64_t num_classes, int64_t dim,
+                               int normalize, void* planes, float* normalized_out, int64_t ld_norm,
+                               void* stream);
+int latte_nxc_multi(const latte_nxc_job_t* jobs, int njobs, void* stream);
+
+/*
  * Fused N x C similarity + top-k class ids (k <= 16), for the zero-shot evaluator
  * (zero_shot.py:14-20,40: logits.topk(max(topk)); train.py:1352-1358).
  * topk_idx is [n, k] int64, topk_val [n, k] fp32 (scale * sim), sorted descending,

@@ -16,41 +16,13 @@ from typing import Optional, Tuple
 
 import torch
 
-_HERE = os.path.dirname(os.path.abspath(__file__))
-_SO_DIR = os.path.join(_HERE, "_C")
-SO_PATH = os.path.join(_SO_DIR, "liblatte_b200.so")
-CSRC = os.path.join(_HERE, "csrc")
-SOURCES = ["api.cu", "clip_tc.cu", "clip_pair.cu", "clip_simt.cu", "nxc.cu", "nxc_tc.cu", "proto.cu", "siglip.cu"]
+from ._build import SO_PATH, CSRC, SOURCES, build  # noqa: F401  (the nvcc recipe; setup.py uses it too)
 
 F32, BF16, F16 = 0, 1, 2
 LABEL_AXIS = {"row": 0, "quirk": 1}
 _DTYPES = {torch.float32: F32, torch.bfloat16: BF16, torch.float16: F16}
 
 _lib = None
-
-
-def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile the CUDA sources for sm_100a into latteclip_b200/_C/liblatte_b200.so
-    (in-tree, so the built library travels with the repository snapshot)."""
-    srcs = [os.path.join(CSRC, s) for s in SOURCES]
-    deps = srcs + [os.path.join(CSRC, h) for h in ("latte_common.cuh", "tc_ptx.cuh")] + \
-        [os.path.join(os.path.dirname(_HERE), "include", "latte_b200.h")]
-    if not force and os.path.exists(SO_PATH):
-        so_m = os.path.getmtime(SO_PATH)
-        if all(os.path.getmtime(d) <= so_m for d in deps):
-            return SO_PATH
-    os.makedirs(_SO_DIR, exist_ok=True)
-    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc, "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-           "-Xcompiler", "-fPIC", "-shared", "-cudart", "static", "-o", SO_PATH] + srcs
-    if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
-    if verbose:
-        sys.stderr.write(res.stderr)
-    return SO_PATH
 
 
 def _declare(lib):
@@ -96,6 +68,9 @@ def _declare(lib):
                                             vp, vp, vp, vp, sz, vp]
     lib.latte_nxc_topk.argtypes = [vp, i64, i32, i64, i64, vp, i64, i64, f32, i32, vp, vp, vp, sz, vp]
     lib.latte_seg_workspace_bytes.argtypes = [i64, i64, i64, c.POINTER(sz)]
+    lib.latte_nxc_planes_bytes.argtypes = [i64, i64, c.POINTER(sz)]
+    lib.latte_nxc_split_prototypes.argtypes = [vp, i64, i64, i64, i32, vp, vp, i64, vp]
+    lib.latte_nxc_multi.argtypes = [vp, i32, vp]
     lib.latte_mix_ema_fwd.argtypes = [vp, i64, vp, i64, vp, i64, vp, i64, vp, vp, vp, vp, vp, vp,
                                       f32, i32, i32, i64, i64, i64, vp, vp, i64, vp]
     lib.latte_mix_ema_bwd.argtypes = [vp, vp, i64, vp, vp, vp, vp, vp, vp, f32, i32, i32, i64,
@@ -116,7 +91,8 @@ EXPORTS = [
     "latte_clip_fwd_rank", "latte_siglip_supported", "latte_siglip_workspace_bytes",
     "latte_siglip_fwd", "latte_siglip_bwd",
     "latte_clip_fwd", "latte_clip_bwd", "latte_normalize_rows", "latte_nxc_workspace_bytes",
-    "latte_nxc_argmax_margin", "latte_nxc_topk", "latte_seg_workspace_bytes", "latte_mix_ema_fwd", "latte_mix_ema_bwd", "latte_bank_accumulate",
+    "latte_nxc_argmax_margin", "latte_nxc_topk", "latte_seg_workspace_bytes", "latte_nxc_planes_bytes",
+    "latte_nxc_split_prototypes", "latte_nxc_multi", "latte_mix_ema_fwd", "latte_mix_ema_bwd", "latte_bank_accumulate",
     "latte_bank_finalize",
 ]
 
@@ -673,6 +649,88 @@ def nxc_argmax_margin(x, protos, scale: float = 1.0, row_index=None, want_argmax
                                               _ptr(t1), wp, wn, _stream(x)),
                "latte_nxc_argmax_margin")
     return am, mg, t1
+
+
+NXC_MULTI_MAX_CLASSES = 64
+NXC_MULTI_MAX_JOBS = 4
+
+
+class LatteNxcJob(ctypes.Structure):
+    """latte_nxc_job_t of include/latte_b200.h."""
+    _fields_ = [("x", ctypes.c_void_p), ("ldx", ctypes.c_int64), ("x_dtype", ctypes.c_int),
+                ("n", ctypes.c_int64), ("dim", ctypes.c_int64),
+                ("planes", ctypes.c_void_p), ("num_classes", ctypes.c_int64),
+                ("scale", ctypes.c_float),
+                ("argmax_out", ctypes.c_void_p), ("margin_out", ctypes.c_void_p),
+                ("top1_out", ctypes.c_void_p)]
+
+
+class ProtoPlanes:
+    """bf16 operand planes of one prototype matrix (latte_nxc_split_prototypes)."""
+
+    def __init__(self, buf, num_classes, dim, normalized):
+        self.buf, self.num_classes, self.dim, self.normalized = buf, num_classes, dim, normalized
+
+
+def nxc_multi_supported(x: torch.Tensor, num_classes: int) -> bool:
+    """The one-launch path takes C <= 64 and rows whose pitch / base are 16-byte aligned."""
+    return (num_classes <= NXC_MULTI_MAX_CLASSES and x.dtype in _DTYPES and x.dim() == 2
+            and x.stride(1) == 1 and (x.stride(0) * x.element_size()) % 16 == 0
+            and x.data_ptr() % 16 == 0 and x.shape[0] > 0)
+
+
+def nxc_split_prototypes(protos: torch.Tensor, normalize: bool = False,
+                         want_normalized: bool = False) -> ProtoPlanes:
+    """fp32 [C, D] prototypes -> bf16 operand planes (once per matrix); ``normalize`` fuses
+    F.normalize(protos, dim=1) (train.py:384-389)."""
+    protos = _rows(protos.detach().to(torch.float32), "prototypes")
+    c, d = protos.shape
+    need = ctypes.c_size_t()
+    _check(load().latte_nxc_planes_bytes(c, d, ctypes.byref(need)), "latte_nxc_planes_bytes")
+    buf = torch.empty(need.value + 128, dtype=torch.uint8, device=protos.device)
+    off = (-buf.data_ptr()) % 128
+    normed = torch.empty(c, d, dtype=torch.float32, device=protos.device) if want_normalized else None
+    with torch.cuda.device(protos.device):
+        _check(load().latte_nxc_split_prototypes(_ptr(protos), protos.stride(0), c, d, int(bool(normalize)),
+                                                 ctypes.c_void_p(buf.data_ptr() + off), _ptr(normed), d,
+                                                 _stream(protos)),
+               "latte_nxc_split_prototypes")
+    pl = ProtoPlanes(buf, c, d, normed)
+    pl.ptr = buf.data_ptr() + off
+    return pl
+
+
+def nxc_multi(jobs):
+    """``jobs``: list of dicts {x, planes: ProtoPlanes, scale, argmax, margin, top1 (bools)} sharing
+    one operand class (all bf16, or all fp32 / fp16) -> list of (argmax | None, margin | None,
+    top1 | None) per job, from ONE launch."""
+    if not 1 <= len(jobs) <= NXC_MULTI_MAX_JOBS:
+        raise RuntimeError("nxc_multi takes 1..4 jobs")
+    arr = (LatteNxcJob * len(jobs))()
+    outs = []
+    keep = []
+    dev = jobs[0]["x"].device
+    for k, jb in enumerate(jobs):
+        x = jb["x"].detach()
+        pl = jb["planes"]
+        if x.shape[1] != pl.dim:
+            raise RuntimeError("nxc_multi: feature dims differ")
+        n = x.shape[0]
+        am = torch.empty(n, dtype=torch.int64, device=dev) if jb.get("argmax") else None
+        mg = torch.empty(n, dtype=torch.float32, device=dev) if jb.get("margin") else None
+        t1 = torch.empty(n, dtype=torch.float32, device=dev) if jb.get("top1") else None
+        a = arr[k]
+        a.x, a.ldx, a.x_dtype, a.n, a.dim = x.data_ptr(), x.stride(0), _dt(x), n, x.shape[1]
+        a.planes, a.num_classes, a.scale = pl.ptr, pl.num_classes, float(jb.get("scale", 1.0))
+        a.argmax_out = am.data_ptr() if am is not None else None
+        a.margin_out = mg.data_ptr() if mg is not None else None
+        a.top1_out = t1.data_ptr() if t1 is not None else None
+        outs.append((am, mg, t1))
+        keep.append(x)
+    with torch.cuda.device(dev):
+        _check(load().latte_nxc_multi(arr, len(jobs), ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)),
+               "latte_nxc_multi")
+    return outs
 
 
 def _nxc_workspace(dt: int, gathered: bool, n: int, dim: int, classes: int, dev):

@@ -44,6 +44,51 @@ def unstack_bank(bank: torch.Tensor, memory_bank, class_names: Iterable[str], to
 
 
 # ------------------------------------------------------------------------------ kernels
+# bf16 operand planes of the epoch-start prototype snapshot (train.py:347-350): split once per
+# snapshot tensor, not once per call.  The planes ride on the tensor object itself (with its
+# in-place version counter), so they die with it and a new tensor at a recycled address never
+# sees stale planes.
+def _snapshot_planes(proto_snapshot: torch.Tensor):
+    cached = getattr(proto_snapshot, "_latte_planes", None)
+    if cached is not None and cached[0] == proto_snapshot._version and \
+            cached[1] == proto_snapshot.data_ptr():
+        return cached[2]
+    pl = _lib.nxc_split_prototypes(proto_snapshot, normalize=False)
+    try:
+        proto_snapshot._latte_planes = (proto_snapshot._version, proto_snapshot.data_ptr(), pl)
+    except AttributeError:      # exotic tensor subclass without a __dict__: split per call
+        pass
+    return pl
+
+
+def step_similarities(image_features, bank, proto_snapshot, per_image, per_group, class_text):
+    """The step's five N x C products (train.py:410-411 and the distinct compute_text_weights calls
+    of :444-449) -> (preds int64 [B], margin(per_image) [B], margin(per_group) [B],
+    margin(class_text) [C]).  With C <= 64 they run as ONE launch per operand class
+    (latte_nxc_multi: stacked jobs, prototypes split once, rows streamed once); otherwise one
+    launch per product."""
+    xs = (image_features, per_image, per_group, class_text)
+    c = bank.shape[0]
+    if all(_lib.nxc_multi_supported(x.detach(), c) for x in xs) and proto_snapshot.shape == bank.shape:
+        cls_planes = _lib.nxc_split_prototypes(bank, normalize=True)          # :384-389 fused
+        snap_planes = _snapshot_planes(proto_snapshot)
+        jobs = [dict(x=image_features, planes=cls_planes, scale=100.0, argmax=True),
+                dict(x=per_image, planes=snap_planes, margin=True),
+                dict(x=per_group, planes=snap_planes, margin=True),
+                dict(x=class_text, planes=snap_planes, margin=True)]
+        res = [None] * 4
+        for direct in (True, False):
+            idx = [k for k, jb in enumerate(jobs) if (jb["x"].dtype == torch.bfloat16) == direct]
+            if idx:
+                for k, out in zip(idx, _lib.nxc_multi([jobs[k] for k in idx])):
+                    res[k] = out
+        return res[0][0], res[1][1], res[2][1], res[3][1]
+    classifier = build_classifier(bank)                                         # :384-389
+    preds = pseudo_label(image_features, classifier, 100.0)                     # :410-411
+    return (preds, text_margins(per_image, proto_snapshot), text_margins(per_group, proto_snapshot),
+            text_margins(class_text, proto_snapshot))
+
+
 def build_classifier(bank: torch.Tensor) -> torch.Tensor:
     """train.py:384-389 (and zero_shot.py:138-145): ``F.normalize(stack(bank), dim=1)``.
     Returns P_hat [C, D] fp32 (the reference then uses ``P_hat.T``)."""
@@ -170,12 +215,13 @@ def prototype_step(image_features: torch.Tensor,
     Returns the loss dict of the reference (keys ``contrastive_loss``, ``zeroshot``, ``loss``,
     train.py:491-504) plus ``preds``, ``t_ft``, ``t_zs`` and the weights.  Call
     ``out["loss"].backward()`` and then ``update_bank`` (train.py:506-530)."""
-    classifier = build_classifier(bank)                                         # :384-389
-    preds = pseudo_label(image_features, classifier, 100.0)                     # :410-411
-    # margins against the epoch-start snapshot (:347-350), weights detached (:444-449)
-    w_img = (text_margins(per_image, proto_snapshot) + 1e-6) * use_image_caption        # :444,:463
-    w_grp = (text_margins(per_group, proto_snapshot) + 1e-6) * use_batch_caption        # :445,:460
-    cls_margin = text_margins(class_text, proto_snapshot)        # one margin per class, gathered below
+    # pseudo-labels against the normalised bank (:384-389, :410-411) and the margins against the
+    # epoch-start snapshot (:347-350), weights detached (:444-449): one stacked launch
+    preds, m_img, m_grp, cls_margin = step_similarities(image_features, bank, proto_snapshot, per_image,
+                                                        per_group, class_text)
+    w_img = (m_img + 1e-6) * use_image_caption                                  # :444,:463
+    w_grp = (m_grp + 1e-6) * use_batch_caption                                  # :445,:460
+    # cls_margin: one margin per class, gathered below
     w_lbl = (cls_margin[preds] + 1e-6) * use_template_caption                   # :448,:468
     w_lbl_zs = (cls_margin[zs] + 1e-6) * use_template_caption                   # :449,:469
     t_ft, t_zs = mix_and_ema(class_text, per_image, per_group, bank, preds, zs,

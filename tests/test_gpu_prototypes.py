@@ -313,3 +313,138 @@ def test_extract_feature_records_with_mock_tower(tmp_path):
         assert back[k]["gt_classname"] == want[k]["gt_classname"] and back[k]["gt_class_id"] == want[k]["gt_class_id"]
         assert np.array_equal(back[k]["image"], want[k]["image"])
         assert np.allclose(back[k]["top_logit"], want[k]["top_logit"], rtol=0, atol=2e-5)
+
+
+def test_prototype_step_and_backward_capture_in_a_cuda_graph():
+    """The boundary takes caller workspaces only (no allocation, no host synchronisation inside the
+    library), so one whole head step -- pseudo-labels, margins, mixture + EMA, two ClipLoss calls,
+    backward, bank update (train.py:384-530) -- can be captured in a CUDA graph and replayed on
+    new data; the replay must reproduce the eager result (loss and bank bit for bit)."""
+    import latteclip_b200 as lb
+    from latteclip_b200 import prototypes as P
+    dev = torch.device("cuda:0")
+    b = d = 256
+    c = 23
+    g = torch.Generator().manual_seed(31)
+
+    def make():
+        bank = F.normalize(torch.randn(c, d, generator=g), dim=1)
+        cls = F.normalize(bank + 0.3 * torch.randn(c, d, generator=g), dim=1)
+        true = torch.randint(0, c, (b,), generator=g)
+        mk = lambda s: F.normalize(bank[true] + s * torch.randn(b, d, generator=g) * 3 / d ** 0.5, dim=1)
+        return dict(bank=bank, cls=cls, img=mk(1.2), pimg=mk(0.9), pgrp=mk(0.7),
+                    zs=torch.randint(0, c, (b,), generator=g))
+
+    loss_fn = lb.ClipLoss(local_loss=True, gather_with_grad=True, cache_labels=True)
+    static = {k: v.to(dev).clone() for k, v in make().items()}
+    leaves = {k: static[k].bfloat16().requires_grad_(True) for k in ("img", "cls", "pimg", "pgrp")}
+    log_s = torch.tensor(math.log(100.0), device=dev, requires_grad=True)
+    snap = static["bank"].clone()
+
+    def step():
+        out = P.prototype_step(leaves["img"], log_s.exp(), static["bank"], snap, static["zs"], leaves["cls"],
+                               leaves["pimg"], leaves["pgrp"], loss_fn, alpha=0.01, label_weight_axis="quirk")
+        out["loss"].backward()
+        P.update_bank(static["bank"], out["preds"], static["zs"], out["t_ft"], out["t_zs"])
+        return out["loss"].detach()
+
+    def load(data):
+        with torch.no_grad():
+            # the epoch-start snapshot (train.py:347-350) stays what it was at capture time: its
+            # operand planes are split once per epoch, outside the captured step
+            static["bank"].copy_(data["bank"].to(dev))
+            static["zs"].copy_(data["zs"].to(dev))
+            for k in leaves:
+                leaves[k].copy_(data[k].to(dev).bfloat16())
+
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(3):                       # warm-up: workspaces, gradient buffers
+            step()
+    torch.cuda.current_stream().wait_stream(side)
+    for x in list(leaves.values()) + [log_s]:
+        x.grad.zero_()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        loss_static = step()
+    static_grads = [(x, x.grad) for x in list(leaves.values()) + [log_s]]   # what the graph writes into
+    for trial in range(2):
+        data = make()
+        load(data)
+        for x, gbuf in static_grads:
+            x.grad = gbuf
+            gbuf.zero_()
+        graph.replay()
+        torch.cuda.synchronize()
+        got = dict(loss=loss_static.clone(), bank=static["bank"].clone(),
+                   **{k: leaves[k].grad.clone() for k in leaves}, s=log_s.grad.clone())
+        load(data)
+        for x in list(leaves.values()) + [log_s]:
+            x.grad = None
+        want_loss = step()
+        torch.cuda.synchronize()
+        assert torch.equal(got["loss"], want_loss)
+        assert torch.equal(got["bank"], static["bank"])
+        # gradients: tiles that the stream-K GEMM splits over more than two clusters are summed with
+        # red.global.add in arrival order, so the last fp32 bit (one bf16 ulp after rounding) may differ
+        for k in leaves:
+            assert torch.allclose(got[k].float(), leaves[k].grad.float(), rtol=2.0 ** -7, atol=1e-9), k
+        assert torch.allclose(got["s"], log_s.grad, rtol=1e-5)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("n,d,c", [(1000, 512, 47), (257, 64, 10), (4096, 768, 64), (130, 520, 33),
+                                   (20000, 512, 47)])
+def test_nxc_multi_one_launch_matches_fp64(dtype, n, d, c):
+    """latte_nxc_multi (stacked jobs, in-kernel plane split, persistent TMA pipeline): argmax
+    bit-exact wherever the fp64 top-1 / top-2 gap exceeds the fp32 rounding band, margins and top-1
+    to fp32 accuracy (train.py:410-411, 292-303); the fused normalisation equals F.normalize."""
+    from latteclip_b200 import _lib
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(n + d + c)
+    bank = (torch.randn(c, d, generator=g) * 1.7).to(dev)
+    snap = F.normalize(torch.randn(c, d, generator=g), dim=1).to(dev) * 0.98
+    xs = [F.normalize(torch.randn(m, d, generator=g), dim=1).to(dev).to(dtype) for m in (n, n, max(n // 3, 1), c)]
+    cls_planes = _lib.nxc_split_prototypes(bank, normalize=True, want_normalized=True)
+    snap_planes = _lib.nxc_split_prototypes(snap)
+    assert torch.allclose(cls_planes.normalized, F.normalize(bank, dim=1), rtol=0, atol=1e-7)
+    outs = _lib.nxc_multi([dict(x=xs[0], planes=cls_planes, scale=100.0, argmax=True, top1=True),
+                           dict(x=xs[1], planes=snap_planes, margin=True),
+                           dict(x=xs[2], planes=snap_planes, margin=True, argmax=True),
+                           dict(x=xs[3], planes=snap_planes, margin=True)])
+    torch.cuda.synchronize()
+    refs = [(xs[0].double() @ F.normalize(bank.double(), dim=1).T)] + \
+           [x.double() @ snap.double().T for x in xs[1:]]
+    # job 0: argmax + scaled top-1
+    top = refs[0].topk(2, dim=1)
+    gap = top.values[:, 0] - top.values[:, 1]
+    clear = gap > 4e-7
+    assert torch.equal(outs[0][0][clear], top.indices[:, 0][clear])
+    assert int((~clear).sum()) <= max(2, n // 500)
+    assert torch.allclose(outs[0][2].double(), 100.0 * top.values[:, 0], rtol=0, atol=3e-5)
+    # margins (differences of near-equal dots: absolute tolerance of a few fp32 ulps of a unit dot)
+    for k in (1, 2, 3):
+        tk = refs[k].topk(2, dim=1).values
+        assert torch.allclose(outs[k][1].double(), tk[:, 0] - tk[:, 1], rtol=0, atol=3e-7), k
+    tk2 = refs[2].topk(2, dim=1)
+    ok = (tk2.values[:, 0] - tk2.values[:, 1]) > 4e-7
+    assert torch.equal(outs[2][0][ok], tk2.indices[:, 0][ok])
+
+
+def test_step_similarities_one_launch_equals_per_product_kernels():
+    """prototypes.step_similarities through latte_nxc_multi == the per-product kernels it replaces."""
+    from latteclip_b200 import prototypes as P
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(17)
+    b, d, c = 3000, 512, 47
+    bank = F.normalize(torch.randn(c, d, generator=g), dim=1).to(dev)
+    snap = bank.clone()
+    for dtype in (torch.float32, torch.bfloat16):
+        img, pi, pg = (F.normalize(torch.randn(b, d, generator=g), dim=1).to(dev).to(dtype) for _ in range(3))
+        ct = F.normalize(torch.randn(c, d, generator=g), dim=1).to(dev).to(dtype)
+        preds, m_i, m_g, m_c = P.step_similarities(img, bank, snap, pi, pg, ct)
+        ref_preds = P.pseudo_label(img, P.build_classifier(bank), 100.0)
+        assert float((preds != ref_preds).float().mean()) < 2e-3
+        for got, x in ((m_i, pi), (m_g, pg), (m_c, ct)):
+            assert torch.allclose(got, P.text_margins(x, snap), rtol=0, atol=3e-7)
