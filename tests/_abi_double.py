@@ -161,3 +161,72 @@ def siglip_bwd(img_loc, txt_all, label_offset, logit_scale, logit_bias, grad_los
     d_txt = s * g.T @ il
     d_txt = d_txt.float() if partial else d_txt.to(gdt)
     return d_img, d_txt, (g * dots).sum().float().reshape(1), g.sum().float().reshape(1)
+
+
+# ------------------------------------------------------------------ prototype entry points
+# (host-logic tests of latteclip_b200.train_step: restated from include/latte_b200.h)
+def nxc_multi_supported(x, num_classes):
+    return False     # the per-product entry points below carry the host logic
+
+
+def normalize_rows(x):
+    return torch.nn.functional.normalize(x.detach().float(), dim=1)
+
+
+def nxc_argmax_margin(x, protos, scale=1.0, row_index=None, want_argmax=True, want_margin=True,
+                      want_top1=False):
+    xs = x.detach().double()
+    if row_index is not None:
+        xs = xs[row_index]
+    logits = scale * xs @ protos.detach().double().T
+    top2 = logits.topk(2, dim=1).values
+    am = logits.argmax(1) if want_argmax else None
+    mg = (top2[:, 0] - top2[:, 1]).float() if want_margin else None
+    return am, mg, (top2[:, 0].float() if want_top1 else None)
+
+
+def _mix_coeffs(w_lbl, w_lbl_zs, w_img, w_grp, alpha, axis, b, d):
+    tot, tot_z = (w_lbl + w_img + w_grp).double(), (w_lbl_zs + w_img + w_grp).double()
+    wl = w_lbl.double()[None, :].expand(b, d) if axis == "quirk" else w_lbl.double()[:, None].expand(b, d)
+    return tot, tot_z, wl
+
+
+def mix_ema_fwd(class_text, per_image, per_group, bank, preds, zs, w_lbl, w_lbl_zs, w_img, w_grp,
+                alpha, label_axis):
+    b, d = per_image.shape
+    tot, tot_z, wl = _mix_coeffs(w_lbl, w_lbl_zs, w_img, w_grp, alpha, label_axis, b, d)
+    ct, pi, pg, bk = (x.detach().double() for x in (class_text, per_image, per_group, bank))
+    common = pi * w_img.double()[:, None] + pg * w_grp.double()[:, None]
+    mix_ft = (wl * ct[preds] + common) / tot[:, None]
+    mix_zs = (wl * ct[zs] + common) / tot_z[:, None]
+    t_ft = bk[preds] + alpha * (mix_ft - bk[preds])
+    t_zs = bk[zs] + alpha * (mix_zs - bk[zs])
+    return t_ft.to(per_image.dtype), t_zs.to(per_image.dtype)
+
+
+def mix_ema_bwd(d_t_ft, d_t_zs, preds, zs, w_lbl, w_lbl_zs, w_img, w_grp, alpha, label_axis,
+                num_classes, want_bank=False):
+    b, d = d_t_ft.shape
+    tot, tot_z, wl = _mix_coeffs(w_lbl, w_lbl_zs, w_img, w_grp, alpha, label_axis, b, d)
+    gf, gz = d_t_ft.detach().double(), d_t_zs.detach().double()
+    af, az = alpha * gf / tot[:, None], alpha * gz / tot_z[:, None]
+    d_ct = torch.zeros(num_classes, d, dtype=torch.float64)
+    d_ct.index_add_(0, preds, wl * af)
+    d_ct.index_add_(0, zs, wl * az)
+    d_pi = (af + az) * w_img.double()[:, None]
+    d_pg = (af + az) * w_grp.double()[:, None]
+    d_bank = None
+    if want_bank:
+        d_bank = torch.zeros(num_classes, d, dtype=torch.float64)
+        d_bank.index_add_(0, preds, (1 - alpha) * gf)
+        d_bank.index_add_(0, zs, (1 - alpha) * gz)
+        d_bank = d_bank.float()
+    return d_ct.float(), d_pi.to(d_t_ft.dtype), d_pg.to(d_t_ft.dtype), d_bank
+
+
+def install(_lib):
+    """Point every entry point the host logic uses at this double."""
+    for name in ("clip_fwd", "clip_bwd", "clip_fwd_rows", "clip_fwd_cols", "bank_accumulate",
+                 "bank_finalize", "nxc_multi_supported", "normalize_rows", "nxc_argmax_margin",
+                 "mix_ema_fwd", "mix_ema_bwd"):
+        setattr(_lib, name, globals()[name])

@@ -25,6 +25,9 @@ What is executed is the reference's own code, imported from /root/reference/src
   * ``open_clip.loss.SigLipLoss`` forward + backward, world size 1 and with its ring exchange
     on real gloo process groups of 2, 3 and 4 ranks
       -> siglip.npz
+  * the ``--accum-freq`` feature-cache pattern of upstream open_clip (present in the reference at
+    train.py:972-1024 behind ``raise NotImplemented()``) driven with the reference's ``ClipLoss``
+      -> clip_accum.npz
 
 The fixtures hold both the inputs and the reference outputs, so tests never need the
 reference at run time (it does not exist on the GPU box).
@@ -370,6 +373,81 @@ def _siglip_worker(rank, world, port, i_all, t_all, scale, bias, ret):
     dist.destroy_process_group()
 
 
+# ----------------------------------------------------------------------------------
+# 7. --accum-freq feature cache (upstream code kept in the reference at train.py:972-1024)
+# ----------------------------------------------------------------------------------
+def gen_clip_accum(open_clip):
+    """The accumulation pattern of train.py:1002-1023 driven with the reference's own ClipLoss:
+    per micro-batch j the loss over cat(cached blocks, live block j), one backward each."""
+    out = {}
+    for name, k, m, d, sigma, scale in (("a3_m32", 3, 32, 64, 3.0, 100.0), ("a4_m40", 4, 40, 48, 5.0, 1.0 / 0.07)):
+        i_all, t_all = synth_pairs(k * m, d, sigma, 900 + k + m, torch.float64)
+        loss_fn = open_clip.ClipLoss(local_loss=True, gather_with_grad=True, cache_labels=True)
+        cached_i = [i_all[j * m:(j + 1) * m] for j in range(k)]
+        cached_t = [t_all[j * m:(j + 1) * m] for j in range(k)]
+        out[f"{name}_I"], out[f"{name}_T"] = i_all.numpy(), t_all.numpy()
+        out[f"{name}_meta"] = np.array([k, m, d, scale], dtype=np.float64)
+        for j in range(k):
+            live_i = cached_i[j].clone().requires_grad_(True)
+            live_t = cached_t[j].clone().requires_grad_(True)
+            s = torch.tensor(scale, dtype=torch.float64, requires_grad=True)
+            inputs = {"image_features": torch.cat(cached_i[:j] + [live_i] + cached_i[j + 1:]),
+                      "text_features": torch.cat(cached_t[:j] + [live_t] + cached_t[j + 1:])}
+            losses = loss_fn(**inputs, logit_scale=s, output_dict=True)
+            total = sum(losses.values())
+            total.backward()
+            out[f"{name}_loss{j}"] = total.detach().numpy()
+            out[f"{name}_dI{j}"] = live_i.grad.numpy()
+            out[f"{name}_dT{j}"] = live_t.grad.numpy()
+            out[f"{name}_ds{j}"] = s.grad.numpy()
+        print("clip_accum", name, float(total))
+    # the same pattern on a real 2-rank gloo group: every rank caches k micro-batches of m rows and
+    # the reference ClipLoss gathers the concatenated [k*m, D] features of both ranks
+    import torch.multiprocessing as mp
+    world, k, m, d, scale = 2, 2, 16, 32, 100.0
+    i_all, t_all = synth_pairs(world * k * m, d, 2.0, 977, torch.float64)
+    ret = mp.Manager().dict()
+    mp.spawn(_accum_dist_worker, args=(world, 29641, i_all, t_all, k, m, scale, ret), nprocs=world, join=True)
+    out["w2_I"], out["w2_T"] = i_all.numpy(), t_all.numpy()
+    out["w2_meta"] = np.array([k, m, d, scale, world], dtype=np.float64)
+    for r in range(world):
+        for key, arr in ret[r].items():
+            out[f"w2_r{r}_{key}"] = arr
+    print("clip_accum w2", float(ret[0]["loss0"]))
+    np.savez_compressed(os.path.join(HERE, "clip_accum.npz"), **out)
+
+
+def _accum_dist_worker(rank, world, port, i_all, t_all, k, m, scale, ret):
+    """Rank r holds rows [r*k*m, (r+1)*k*m) as k micro-batches; train.py:1002-1023 per micro-batch."""
+    import torch.distributed as dist
+    sys.modules.setdefault("ftfy", types.ModuleType("ftfy"))
+    sys.path.insert(0, REF_SRC)
+    import open_clip
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    loss_fn = open_clip.ClipLoss(local_loss=True, gather_with_grad=True, cache_labels=True,
+                                 rank=rank, world_size=world)
+    base = rank * k * m
+    cached_i = [i_all[base + j * m: base + (j + 1) * m] for j in range(k)]
+    cached_t = [t_all[base + j * m: base + (j + 1) * m] for j in range(k)]
+    res = {}
+    for j in range(k):
+        live_i = cached_i[j].clone().requires_grad_(True)
+        live_t = cached_t[j].clone().requires_grad_(True)
+        s = torch.tensor(scale, dtype=torch.float64, requires_grad=True)
+        losses = loss_fn(image_features=torch.cat(cached_i[:j] + [live_i] + cached_i[j + 1:]),
+                         text_features=torch.cat(cached_t[:j] + [live_t] + cached_t[j + 1:]),
+                         logit_scale=s, output_dict=True)
+        total = sum(losses.values())
+        total.backward()
+        res[f"loss{j}"] = total.detach().numpy()
+        res[f"dI{j}"], res[f"dT{j}"], res[f"ds{j}"] = live_i.grad.numpy(), live_t.grad.numpy(), s.grad.numpy()
+    ret[rank] = res
+    dist.barrier()
+    dist.destroy_process_group()
+
+
 def gen_siglip(open_clip):
     import torch.multiprocessing as mp
     out = {}
@@ -411,6 +489,7 @@ def main():
     gen_zero_shot(tt)
     gen_siglip(open_clip)
     gen_clip_dist()
+    gen_clip_accum(open_clip)
 
 
 if __name__ == "__main__":
