@@ -219,26 +219,59 @@ def prototype_kernel_rates(dev, peaks, batch=N_GLOBAL, dim=DIM, classes=47):
     zs = torch.randint(0, classes, (batch,), generator=g).to(dev)
     w = [torch.rand(batch, generator=g).to(dev) + 0.1 for _ in range(4)]
 
-    def timeit(fn, reps=10):
-        for k in range(3):
-            fn(k)
+    def timeit(fn, reps=12):
+        # `reps` calls captured in ONE CUDA graph and replayed between two events on the replay
+        # stream: the kernels are 20-160 us, the host side of a call (ctypes, tensor-map encoding,
+        # output allocation) ~20 us, so an eager loop would time the host for the short ones
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for k in range(3):
+                fn(k)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            for k in range(reps):
+                fn(k)
+        graph.replay()
         torch.cuda.synchronize()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        for k in range(reps):
-            fn(k)
+        graph.replay()
         b.record()
         torch.cuda.synchronize()
         return a.elapsed_time(b) / reps
 
     fb = 4
+    cp = (classes + 15) // 16 * 16
+    planes_bytes = 2 * 3 * cp * dim * 2
+    cls_planes = _lib.nxc_split_prototypes(bank, normalize=True)
+    snap_planes = _lib.nxc_split_prototypes(bank, normalize=False)
+    xh = [x.bfloat16() for x in xs]
+    clsh = cls.bfloat16()
+
+    def step_jobs(feats, ct, k):
+        # the four products of one LatteCLIP step (prototypes.step_similarities): pseudo-label argmax
+        # on the images, top-2 margins of the image-description, group-description and class-name texts
+        return [dict(x=feats[k % sets], planes=cls_planes, scale=100.0, argmax=True),
+                dict(x=feats[(k + 1) % sets], planes=snap_planes, margin=True),
+                dict(x=feats[(k + 2) % sets], planes=snap_planes, margin=True),
+                dict(x=ct, planes=snap_planes, margin=True)]
     rows = [
-        ("nxc_tc_kernel (pseudo-label argmax, train.py:410-411)",
+        ("nxc_stream_kernel<convert>, fp32 features: the step's 4 stacked N x C products in one launch "
+         "(train.py:410-411 argmax + 3 compute_text_weights margins :292-303)",
+         (3 * batch + classes) * dim * 4 + planes_bytes + batch * 16,
+         lambda k: _lib.nxc_multi(step_jobs(xs, cls, k))),
+        ("nxc_stream_kernel<direct>, bf16 features: the same 4 stacked products",
+         (3 * batch + classes) * dim * 2 + planes_bytes + batch * 16,
+         lambda k: _lib.nxc_multi(step_jobs(xh, clsh, k))),
+        ("nxc_stream_kernel<convert>, fp32 features: one product (pseudo-label argmax only)",
+         batch * dim * 4 + planes_bytes // 2 + batch * 8,
+         lambda k: _lib.nxc_multi(step_jobs(xs, cls, k)[:1])),
+        ("nxc_tc_kernel, fp32 features: per-product path kept for C > 64 (argmax)",
          batch * dim * fb + classes * dim * 4 + batch * 8,
          lambda k: _lib.nxc_argmax_margin(xs[k % sets], bank, scale=100.0, want_argmax=True, want_margin=False)),
-        ("nxc_tc_kernel (top-2 margin, train.py:292-303)",
-         batch * dim * fb + classes * dim * 4 + batch * 4,
-         lambda k: _lib.nxc_argmax_margin(xs[k % sets], bank, scale=1.0, want_argmax=False, want_margin=True)),
         # per_image + per_group read, t_ft + t_zs written; the label-text / bank rows are gathers
         # from [C, D] tables (96 KB each at C = 47) that stay in L2
         ("mix_ema_fwd_kernel (train.py:472-488)",
@@ -257,7 +290,9 @@ def prototype_kernel_rates(dev, peaks, batch=N_GLOBAL, dim=DIM, classes=47):
         gbs = nbytes / (ms * 1e-3) / 1e9
         out.append({"kernel": name, "ms": ms, "alg_bytes": nbytes, "achieved_gbs": gbs,
                     "frac_of_measured_hbm": gbs / peaks["hbm"]})
-    return {"batch": batch, "dim": dim, "classes": classes, "dtype": "f32", "rows": out}
+    return {"batch": batch, "dim": dim, "classes": classes, "dtype": "f32 unless the row says bf16",
+            "timing": "12 calls captured in one CUDA graph, replay timed with events; 6 rotating input "
+                      "sets (403 MiB fp32) larger than the L2", "rows": out}
 
 
 def siglip_times(dev, n=None, dim=None, reps=10):

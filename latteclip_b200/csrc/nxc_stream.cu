@@ -40,7 +40,8 @@ constexpr int kBufCols = 4 * kAccCols;         // per TMEM buffer: 4 accumulator
 constexpr int kCvtStages = 2;
 constexpr int kCvtStageBytes = kRawBytes + 3 * kPlaneBytes + kPBytes;        // 104 KB
 constexpr int kCvtSmem = kCvtStages * kCvtStageBytes + 1024;
-constexpr int kCvtThreads = 14 * 32;           // TMA, MMA, 4 epilogue warps, 8 converter warps
+constexpr int kCvtWarps = 16;                  // converter warps: 4 per scheduler hide the cvt -> sub chains
+constexpr int kCvtThreads = (6 + kCvtWarps) * 32;   // TMA, MMA, 4 epilogue warps, converters
 // direct variant (bf16 rows): stage = one plane 16 KB + prototypes 24 KB; five stages
 constexpr int kDirStages = 5;
 constexpr int kDirStageBytes = kPlaneBytes + kPBytes;                         // 40 KB
@@ -105,8 +106,8 @@ nxc_stream_kernel(const __grid_constant__ StreamMaps maps, const StreamParams p)
     }
     for (int s = 0; s < kStages; ++s) {
       mbar_init(bar_raw_full + 8 * s, 1);
-      mbar_init(bar_raw_empty + 8 * s, 8);
-      mbar_init(bar_op_full + 8 * s, kConvert ? 8 : 1);
+      mbar_init(bar_raw_empty + 8 * s, kCvtWarps);
+      mbar_init(bar_op_full + 8 * s, kConvert ? kCvtWarps : 1);
       mbar_init(bar_p_full + 8 * s, 1);
       mbar_init(bar_op_empty + 8 * s, 1);
     }
@@ -255,8 +256,8 @@ nxc_stream_kernel(const __grid_constant__ StreamMaps maps, const StreamParams p)
       }
     }
   } else if (kConvert) {
-    // ------------------------------------------------------------ converters (warps 6-13)
-    // thread -> (row r of the block, half h of the chunk): 32 consecutive features
+    // ------------------------------------------------------------ converters (warps 6-21)
+    // thread -> (row r of the block, quarter h of the chunk): 16 consecutive features
     const int t = threadIdx.x - 6 * 32;
     const int r = t & 127, h = t >> 7;
     const uint32_t sw = (uint32_t)(r & 7);
@@ -267,24 +268,25 @@ nxc_stream_kernel(const __grid_constant__ StreamMaps maps, const StreamParams p)
       for (int c = 0; c < jb.kch; ++c) {
         const uint32_t st = smem_base + stage * kStageBytes;
         mbar_wait(bar_raw_full + 8 * stage, phase);
-        float v[32];
+        float v[16];
         if (jb.raw_f32) {
-          // box h: row r = 128 bytes, 16-byte chunk j at position j ^ (r & 7)
-          const uint32_t row_addr = st + h * (kRawBytes / 2) + r * 128;
+          // box h / 2 holds 32 features: row r = 128 bytes, 16-byte chunk j at position j ^ (r & 7);
+          // this thread's 16 floats are chunks 4 (h & 1) .. 4 (h & 1) + 3
+          const uint32_t row_addr = st + (h >> 1) * (kRawBytes / 2) + r * 128;
 #pragma unroll
-          for (int jx = 0; jx < 8; ++jx) {
+          for (int jx = 0; jx < 4; ++jx) {
             uint32_t a, b, cw, d;
-            ld_shared_v4(row_addr + ((jx ^ sw) << 4), a, b, cw, d);
+            ld_shared_v4(row_addr + (((uint32_t)(4 * (h & 1) + jx) ^ sw) << 4), a, b, cw, d);
             v[4 * jx] = __uint_as_float(a); v[4 * jx + 1] = __uint_as_float(b);
             v[4 * jx + 2] = __uint_as_float(cw); v[4 * jx + 3] = __uint_as_float(d);
           }
         } else {
-          // fp16 rows: one box of 64 halves per row; this thread's 32 halves are chunks 4h .. 4h + 3
+          // fp16 rows: one box of 64 halves per row; this thread's 16 halves are chunks 2h, 2h + 1
           const uint32_t row_addr = st + r * 128;
 #pragma unroll
-          for (int jx = 0; jx < 4; ++jx) {
+          for (int jx = 0; jx < 2; ++jx) {
             uint32_t w4[4];
-            ld_shared_v4(row_addr + (((4 * h + jx) ^ sw) << 4), w4[0], w4[1], w4[2], w4[3]);
+            ld_shared_v4(row_addr + (((uint32_t)(2 * h + jx) ^ sw) << 4), w4[0], w4[1], w4[2], w4[3]);
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w4[e]));
@@ -301,16 +303,17 @@ nxc_stream_kernel(const __grid_constant__ StreamMaps maps, const StreamParams p)
         for (int pl = 0; pl < 3; ++pl) {
           if (pl < jb.x_planes) {
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
+            for (int g = 0; g < 2; ++g) {
               uint32_t w4[4];
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 const __nv_bfloat162 b2 = __floats2bfloat162_rn(v[8 * g + 2 * e], v[8 * g + 2 * e + 1]);
                 w4[e] = *reinterpret_cast<const uint32_t*>(&b2);
-                v[8 * g + 2 * e] -= __bfloat162float(b2.x);            // exact in fp32
-                v[8 * g + 2 * e + 1] -= __bfloat162float(b2.y);
+                // residual, exact in fp32: the two bf16 values widen by a mask and a shift
+                v[8 * g + 2 * e] -= __uint_as_float(w4[e] << 16);
+                v[8 * g + 2 * e + 1] -= __uint_as_float(w4[e] & 0xffff0000u);
               }
-              st_shared_v4(prow + pl * kPlaneBytes + (((4 * h + g) ^ sw) << 4), w4[0], w4[1], w4[2], w4[3]);
+              st_shared_v4(prow + pl * kPlaneBytes + (((uint32_t)(2 * h + g) ^ sw) << 4), w4[0], w4[1], w4[2], w4[3]);
             }
           }
         }

@@ -375,7 +375,217 @@ __global__ void __launch_bounds__(128) seg_final_kernel(SegArgs a) {
   }
 }
 
+// ------------------------------------------------------------------ per-class sums, streaming form
+// When the [C, D] fp32 accumulator fits in shared memory (C * D * 4 <= 200 KB: 47 x 512 = 94 KB) the
+// per-class sums need no sort: the batch is cut into a FIXED number of row chunks (a function of the
+// batch size only, so the result does not depend on the device), one CTA per chunk walks its rows
+// in order -- entry order of the reference loop, zs row then ft row of every sample,
+// train.py:511-527 -- adding each row into the accumulator row of its class (a thread owns its
+// feature columns: no conflicts, no atomics), and writes its [C, D] partial; a second kernel adds
+// the chunk partials in chunk order.  Every feature row is read exactly once, 16 rows in flight per
+// thread.  With `d_per_image` the same pass is the mixer's backward: it also writes the two
+// row-shaped gradients from the rows it holds, so d_t_ft / d_t_zs are read once for all four
+// outputs (the five-launch sort path re-read them for the class sums).
+constexpr int kClsChunks = 128;
+constexpr int kClsUnroll = 8;
+constexpr size_t kClsSmemMax = 200 * 1024;
+
+struct ClsArgs {
+  const void* src_ft; const void* src_zs; int64_t ld_src; int dtype;
+  const int64_t* preds; const int64_t* zs;
+  int64_t batch, dim;
+  int num_classes;
+  const float* w_lbl; const float* w_lbl_zs; const float* w_img; const float* w_grp;   // nullable set
+  float alpha; int label_axis;
+  void* d_per_image; void* d_per_group; int64_t ld_dp;      // nullable: row-shaped outputs
+  float* partial;           // [chunks, C, dim]
+  int* cnt_partial;         // [chunks, C]
+  int chunks; int64_t rows_per_chunk;
+  // final step
+  float* out; int64_t ld_out; int accumulate; float* counts; float post_scale;
+};
+
+struct ClsBatch {
+  float4 vf[kClsUnroll], vz[kClsUnroll];
+  int cp[kClsUnroll], cz[kClsUnroll];
+  float inv_f[kClsUnroll], inv_z[kClsUnroll], wl[kClsUnroll], wi[kClsUnroll], wg[kClsUnroll];
+};
+
+__device__ __forceinline__ void cls_load(const ClsArgs& a, int64_t i0, int64_t r1, int64_t d, bool col_ok,
+                                         bool quirk, ClsBatch& b) {
+#pragma unroll
+  for (int u = 0; u < kClsUnroll; ++u) {
+    const int64_t i = i0 + u;
+    b.cp[u] = b.cz[u] = -1;
+    b.vf[u] = b.vz[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+    b.inv_f[u] = b.inv_z[u] = b.wl[u] = 1.f;
+    b.wi[u] = b.wg[u] = 0.f;
+    if (i < r1) {
+      const int64_t p = __ldg(a.preds + i), z = __ldg(a.zs + i);
+      b.cp[u] = (p >= 0 && p < a.num_classes) ? (int)p : -1;      // out-of-range ids are dropped
+      b.cz[u] = (z >= 0 && z < a.num_classes) ? (int)z : -1;
+      if (col_ok) {
+        b.vf[u] = ld4(a.src_ft, i * a.ld_src + d, a.dtype);
+        b.vz[u] = ld4(a.src_zs, i * a.ld_src + d, a.dtype);
+      }
+      if (a.w_lbl) {
+        const float wl = __ldg(a.w_lbl + i);
+        b.wi[u] = __ldg(a.w_img + i);
+        b.wg[u] = __ldg(a.w_grp + i);
+        b.inv_f[u] = a.alpha / (wl + b.wi[u] + b.wg[u]);
+        b.inv_z[u] = a.alpha / (__ldg(a.w_lbl_zs + i) + b.wi[u] + b.wg[u]);
+        if (!quirk) b.wl[u] = wl;        // quirk axis: the label weight is a column factor (final step)
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ void cls_accum(const ClsArgs& a, int64_t i0, int64_t r1, int64_t d, bool col_ok,
+                                          bool quirk, int nvec, float4* acc, int* cnt, const ClsBatch& b) {
+#pragma unroll
+  for (int u = 0; u < kClsUnroll; ++u) {
+    const int64_t i = i0 + u;
+    if (i >= r1) break;
+    if (threadIdx.x == 0) {
+      if (b.cz[u] >= 0) cnt[b.cz[u]] += 1;
+      if (b.cp[u] >= 0) cnt[b.cp[u]] += 1;
+    }
+    if (!col_ok) continue;
+    const float4 gf = b.vf[u], gz = b.vz[u];
+    if (a.d_per_image) {
+      const float inv_ft = b.inv_f[u], inv_zs = b.inv_z[u];
+      float4 dm;
+      dm.x = gf.x * inv_ft + gz.x * inv_zs; dm.y = gf.y * inv_ft + gz.y * inv_zs;
+      dm.z = gf.z * inv_ft + gz.z * inv_zs; dm.w = gf.w * inv_ft + gz.w * inv_zs;
+      const float wi = b.wi[u], wg = b.wg[u];
+      st4(a.d_per_image, i * a.ld_dp + d, a.dtype, make_float4(wi * dm.x, wi * dm.y, wi * dm.z, wi * dm.w));
+      st4(a.d_per_group, i * a.ld_dp + d, a.dtype, make_float4(wg * dm.x, wg * dm.y, wg * dm.z, wg * dm.w));
+    }
+    if (b.cz[u] >= 0) {            // entry 2i: the zs-list row first (train.py:524)
+      float4* q = acc + (int64_t)b.cz[u] * nvec + threadIdx.x;
+      const float sc = b.inv_z[u] * b.wl[u];
+      float4 t = *q;
+      t.x = fmaf(gz.x, sc, t.x); t.y = fmaf(gz.y, sc, t.y);
+      t.z = fmaf(gz.z, sc, t.z); t.w = fmaf(gz.w, sc, t.w);
+      *q = t;
+    }
+    if (b.cp[u] >= 0) {            // entry 2i + 1: the ft-list row (train.py:525)
+      float4* q = acc + (int64_t)b.cp[u] * nvec + threadIdx.x;
+      const float sc = b.inv_f[u] * b.wl[u];
+      float4 t = *q;
+      t.x = fmaf(gf.x, sc, t.x); t.y = fmaf(gf.y, sc, t.y);
+      t.z = fmaf(gf.z, sc, t.z); t.w = fmaf(gf.w, sc, t.w);
+      *q = t;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) cls_stream_kernel(ClsArgs a) {
+  extern __shared__ __align__(16) uint8_t cls_smem[];
+  const int nvec = (int)(a.dim / 4);
+  float4* acc = reinterpret_cast<float4*>(cls_smem);                              // [C][nvec]
+  int* cnt = reinterpret_cast<int*>(cls_smem + (size_t)a.num_classes * nvec * 16);   // [C]
+  for (int k = threadIdx.x; k < a.num_classes * nvec; k += blockDim.x) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int k = threadIdx.x; k < a.num_classes; k += blockDim.x) cnt[k] = 0;
+  __syncthreads();
+  const int64_t r0 = (int64_t)blockIdx.x * a.rows_per_chunk;
+  const int64_t r1 = min(a.batch, r0 + a.rows_per_chunk);
+  const bool col_ok = (int)threadIdx.x < nvec;
+  const int64_t d = (int64_t)threadIdx.x * 4;
+  const bool quirk = a.w_lbl && a.label_axis == LATTE_LABEL_AXIS_QUIRK;
+  // two batches of rows in flight: the loads of batch k + 1 are issued before batch k is added
+  ClsBatch ba, bb;
+  cls_load(a, r0, r1, d, col_ok, quirk, ba);
+  for (int64_t i0 = r0; i0 < r1; i0 += 2 * kClsUnroll) {
+    cls_load(a, i0 + kClsUnroll, r1, d, col_ok, quirk, bb);
+    cls_accum(a, i0, r1, d, col_ok, quirk, nvec, acc, cnt, ba);
+    cls_load(a, i0 + 2 * kClsUnroll, r1, d, col_ok, quirk, ba);
+    cls_accum(a, i0 + kClsUnroll, r1, d, col_ok, quirk, nvec, acc, cnt, bb);
+  }
+  __syncthreads();
+  float4* dst = reinterpret_cast<float4*>(a.partial) + (int64_t)blockIdx.x * a.num_classes * nvec;
+  for (int k = threadIdx.x; k < a.num_classes * nvec; k += blockDim.x) dst[k] = acc[k];
+  for (int k = threadIdx.x; k < a.num_classes; k += blockDim.x)
+    a.cnt_partial[(int64_t)blockIdx.x * a.num_classes + k] = cnt[k];
+}
+
+// out[c] (+)= post_scale * colweight * sum over the chunks, in chunk order
+__global__ void __launch_bounds__(128) cls_final_kernel(ClsArgs a) {
+  const int nvec = (int)(a.dim / 4);
+  const int c = blockIdx.x;
+  const int v = blockIdx.y * 128 + threadIdx.x;
+  if (blockIdx.y == 0 && threadIdx.x == 0 && a.counts) {
+    int n = 0;
+    for (int k = 0; k < a.chunks; ++k) n += a.cnt_partial[(int64_t)k * a.num_classes + c];
+    a.counts[c] = (float)n;
+  }
+  if (v >= nvec) return;
+  const float4* src = reinterpret_cast<const float4*>(a.partial) + (int64_t)c * nvec + v;
+  const int64_t step = (int64_t)a.num_classes * nvec;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int k0 = 0; k0 < a.chunks; k0 += 8) {
+    float4 t[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+      t[u] = k0 + u < a.chunks ? __ldcg(src + (int64_t)(k0 + u) * step) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { s.x += t[u].x; s.y += t[u].y; s.z += t[u].z; s.w += t[u].w; }
+  }
+  if (a.w_lbl && a.label_axis == LATTE_LABEL_AXIS_QUIRK) {
+    const float4 w = __ldg(reinterpret_cast<const float4*>(a.w_lbl) + v);
+    s.x *= w.x; s.y *= w.y; s.z *= w.z; s.w *= w.w;
+  }
+  s.x *= a.post_scale; s.y *= a.post_scale; s.z *= a.post_scale; s.w *= a.post_scale;
+  float4* o = reinterpret_cast<float4*>(a.out + (int64_t)c * a.ld_out) + v;
+  if (a.accumulate) { const float4 p = *o; s.x += p.x; s.y += p.y; s.z += p.z; s.w += p.w; }
+  *o = s;
+}
+
 inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+struct ClsGeom { bool ok; int chunks; int64_t rows_per_chunk; size_t smem, part_bytes, cnt_bytes; };
+ClsGeom cls_geom(int64_t batch, int64_t dim, int64_t num_classes) {
+  ClsGeom g{};
+  g.smem = (size_t)num_classes * (size_t)dim * 4 + (size_t)num_classes * 4;
+  g.ok = batch > 0 && dim % 4 == 0 && dim / 4 <= 256 && g.smem <= kClsSmemMax;
+  if (!g.ok) return g;
+  g.rows_per_chunk = (batch + kClsChunks - 1) / kClsChunks;
+  if (g.rows_per_chunk < 16) g.rows_per_chunk = 16;
+  g.chunks = (int)((batch + g.rows_per_chunk - 1) / g.rows_per_chunk);
+  g.part_bytes = ((size_t)g.chunks * (size_t)num_classes * (size_t)dim * 4 + 255) / 256 * 256;
+  g.cnt_bytes = ((size_t)g.chunks * (size_t)num_classes * 4 + 255) / 256 * 256;
+  return g;
+}
+
+// -> LATTE_OK when the streaming form ran, 1 when it does not apply (caller takes the sort path)
+int class_sums_stream(ClsArgs a, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  const ClsGeom g = cls_geom(a.batch, a.dim, a.num_classes);
+  const int64_t esz = (int64_t)dtype_size(a.dtype);
+  const bool vec = g.ok && (a.ld_src % 4 == 0) && (a.ld_out % 4 == 0) && al16(a.out) &&
+                   (reinterpret_cast<uintptr_t>(a.src_ft) % (4 * esz) == 0) &&
+                   (reinterpret_cast<uintptr_t>(a.src_zs) % (4 * esz) == 0) &&
+                   (!a.d_per_image || ((a.ld_dp % 4 == 0) &&
+                                       (reinterpret_cast<uintptr_t>(a.d_per_image) % (4 * esz) == 0) &&
+                                       (reinterpret_cast<uintptr_t>(a.d_per_group) % (4 * esz) == 0))) &&
+                   (!a.w_lbl || al16(a.w_lbl));
+  if (!vec) return 1;
+  if (!workspace) return LATTE_ERR_BAD_ARG;
+  const uintptr_t base = (reinterpret_cast<uintptr_t>(workspace) + 255) / 256 * 256;
+  if (base - reinterpret_cast<uintptr_t>(workspace) + g.part_bytes + g.cnt_bytes > workspace_bytes)
+    return LATTE_ERR_WORKSPACE;
+  a.partial = reinterpret_cast<float*>(base);
+  a.cnt_partial = reinterpret_cast<int*>(base + g.part_bytes);
+  a.chunks = g.chunks;
+  a.rows_per_chunk = g.rows_per_chunk;
+  const int nvec = (int)(a.dim / 4);
+  const int threads = (nvec + 31) / 32 * 32;
+  if (g.smem > 48 * 1024)
+    LATTE_CUDA_OK(cudaFuncSetAttribute(cls_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
+  cls_stream_kernel<<<g.chunks, threads, g.smem, st>>>(a);
+  cls_final_kernel<<<dim3((unsigned)a.num_classes, (unsigned)((nvec + 127) / 128)), 128, 0, st>>>(a);
+  if (cudaGetLastError() != cudaSuccess) return LATTE_ERR_CUDA;
+  return LATTE_OK;
+}
 
 struct SegWs { size_t n_hist, int_bytes, part_bytes; int slices, max_pieces; };
 SegWs seg_ws(int64_t batch, int64_t dim, int64_t num_classes) {
@@ -451,6 +661,8 @@ extern "C" int latte_seg_workspace_bytes(int64_t batch, int64_t dim, int64_t num
   LATTE_CHECK_ARG(bytes && batch >= 0 && dim > 0 && num_classes > 0);
   const SegWs w = seg_ws(batch, dim, num_classes);
   *bytes = w.int_bytes + w.part_bytes + 256;
+  const ClsGeom g = cls_geom(batch, dim, num_classes);      // streaming form: chunk partials
+  if (g.ok && g.part_bytes + g.cnt_bytes + 256 > *bytes) *bytes = g.part_bytes + g.cnt_bytes + 256;
   return LATTE_OK;
 }
 
@@ -511,13 +723,28 @@ extern "C" int latte_mix_ema_bwd(const void* d_t_ft, const void* d_t_zs, int64_t
   if (num_classes > 12000) return LATTE_ERR_UNSUPPORTED;     // class histogram lives in smem
   if (batch == 0) return LATTE_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (d_per_image && d_per_group) {
+  bool rows_done = false, class_done = false;
+  if (d_class_text) {
+    // one pass over d_t_ft / d_t_zs for the row gradients and the class-text sums
+    ClsArgs c{};
+    c.src_ft = d_t_ft; c.src_zs = d_t_zs; c.ld_src = ld_dt; c.dtype = dtype;
+    c.preds = preds; c.zs = zs; c.batch = batch; c.dim = dim; c.num_classes = (int)num_classes;
+    c.w_lbl = w_lbl; c.w_lbl_zs = w_lbl_zs; c.w_img = w_img; c.w_grp = w_grp;
+    c.alpha = alpha; c.label_axis = label_axis;
+    const bool rows = d_per_image && d_per_group;
+    c.d_per_image = rows ? d_per_image : nullptr; c.d_per_group = rows ? d_per_group : nullptr; c.ld_dp = ld_dp;
+    c.out = d_class_text; c.ld_out = ld_dct; c.accumulate = 1; c.counts = nullptr; c.post_scale = 1.f;
+    const int rc = class_sums_stream(c, workspace, workspace_bytes, st);
+    if (rc < 0) return rc;
+    if (rc == LATTE_OK) { class_done = true; rows_done = rows; }
+  }
+  if (d_per_image && d_per_group && !rows_done) {
     MixBwdArgs a{d_t_ft, d_t_zs, ld_dt, w_lbl, w_lbl_zs, w_img, w_grp, alpha, dtype, batch, dim,
                  d_per_image, d_per_group, ld_dp};
     mix_ema_bwd_rows_kernel<<<(unsigned)batch, 128, 0, st>>>(a);
     LATTE_LAUNCH_OK();
   }
-  if (d_class_text) {
+  if (d_class_text && !class_done) {
     // d_class_text[c] += sum_{zs_i=c} wl * alpha/totz_i * dT_zs[i] + sum_{preds_i=c} wl * alpha/tot_i * dT_ft[i]
     SegArgs s{};
     s.src_ft = d_t_ft; s.src_zs = d_t_zs; s.ld_src = ld_dt; s.dtype = dtype;
@@ -551,6 +778,15 @@ extern "C" int latte_bank_accumulate(const void* t_ft, const void* t_zs, int64_t
   LATTE_CHECK_ARG(batch >= 0 && dim > 0 && num_classes > 0 && ld_t >= dim && ld_sums >= dim);
   LATTE_CHECK_ARG(dtype >= LATTE_F32 && dtype <= LATTE_F16);
   if (num_classes > 12000) return LATTE_ERR_UNSUPPORTED;       // class histogram lives in smem
+  if (batch > 0) {
+    ClsArgs c{};
+    c.src_ft = t_ft; c.src_zs = t_zs; c.ld_src = ld_t; c.dtype = dtype;
+    c.preds = preds; c.zs = zs; c.batch = batch; c.dim = dim; c.num_classes = (int)num_classes;
+    c.label_axis = LATTE_LABEL_AXIS_ROW;
+    c.out = sums; c.ld_out = ld_sums; c.accumulate = 0; c.counts = counts; c.post_scale = 1.f;
+    const int rc = class_sums_stream(c, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+    if (rc <= 0) return rc;
+  }
   SegArgs s{};
   s.src_ft = t_ft; s.src_zs = t_zs; s.ld_src = ld_t; s.dtype = dtype;
   s.preds = preds; s.zs = zs; s.batch = batch; s.dim = dim; s.num_classes = (int)num_classes;

@@ -179,6 +179,46 @@ def test_update_bank(b, d, c):
     assert torch.equal(bank_g.cpu()[~touched], bank[~touched])
 
 
+@pytest.mark.parametrize("b,d,c,dtype", [(32768, 512, 47, torch.float32), (32768, 512, 47, torch.bfloat16),
+                                         (20011, 768, 64, torch.float32), (3000, 512, 100, torch.float32)])
+def test_streaming_class_sums_at_headline_batch(b, d, c, dtype):
+    """The one-pass per-class sums (cls_stream_kernel: [C, D] accumulator in shared memory, fixed row
+    chunks) behind latte_bank_accumulate and latte_mix_ema_bwd at the headline batch: values against
+    fp64 index_add, exact counts, and bit-identical results from run to run (no atomics)."""
+    from latteclip_b200 import _lib
+    g = torch.Generator().manual_seed(b + c)
+    x = torch.randn(b, d, generator=g).to(DEV).to(dtype)
+    y = torch.randn(b, d, generator=g).to(DEV).to(dtype)
+    preds = torch.randint(0, c, (b,), generator=g).to(DEV)
+    zs = torch.randint(0, c - 1, (b,), generator=g).to(DEV)
+    sums, counts = _lib.bank_accumulate(x, y, preds, zs, c)
+    ref = torch.zeros(c, d, dtype=torch.float64, device=DEV)
+    ref.index_add_(0, zs, y.double())
+    ref.index_add_(0, preds, x.double())
+    assert rel(sums, ref) < 2e-6
+    cnt_ref = torch.bincount(preds, minlength=c) + torch.bincount(zs, minlength=c)
+    assert torch.equal(counts.long(), cnt_ref)
+    sums2, _ = _lib.bank_accumulate(x, y, preds, zs, c)
+    assert torch.equal(sums, sums2)
+    # mixer backward: row gradients and class-text sums from one pass
+    w = [torch.rand(b, generator=g).to(DEV) * 0.3 + 1e-3 for _ in range(4)]
+    alpha = 0.01
+    d_ct, d_pi, d_pg, _ = _lib.mix_ema_bwd(x, y, preds, zs, w[0], w[1], w[2], w[3], alpha, "row", c)
+    xd, yd = x.double(), y.double()
+    wl, wlz, wi, wg = (t.double() for t in w)
+    af = alpha * xd / (wl + wi + wg)[:, None]
+    az = alpha * yd / (wlz + wi + wg)[:, None]
+    ct_ref = torch.zeros(c, d, dtype=torch.float64, device=DEV)
+    ct_ref.index_add_(0, preds, wl[:, None] * af)
+    ct_ref.index_add_(0, zs, wl[:, None] * az)
+    tol = 2e-6 if dtype == torch.float32 else 4e-3      # 16-bit: the row outputs are rounded to dtype
+    assert rel(d_ct, ct_ref) < 2e-6
+    assert rel(d_pi, (af + az) * wi[:, None]) < tol
+    assert rel(d_pg, (af + az) * wg[:, None]) < tol
+    d_ct2, d_pi2, _, _ = _lib.mix_ema_bwd(x, y, preds, zs, w[0], w[1], w[2], w[3], alpha, "row", c)
+    assert torch.equal(d_ct, d_ct2) and torch.equal(d_pi, d_pi2)
+
+
 # ------------------------------------------------------------------ full step vs the real train loop
 @pytest.mark.parametrize("name", ["b32_c7", "b64_c10", "b64_c10_flags"])
 def test_prototype_step_matches_train_one_epoch_v2_golden(name):
