@@ -367,10 +367,32 @@ def latteclip_head_times(dev, batch=512, dim=512, classes=47, reps=20, axis="qui
         step()
     b.record()
     torch.cuda.synchronize()
+    eager_ms = a.elapsed_time(b) / reps
+    # the same step through prototypes.GraphedPrototypeStep: captured once in a CUDA graph, replayed per
+    # step; the inputs are copied into the graph's static buffers and the gradients handed back to
+    # autograd every step (that is inside the timed region)
+    graphed = P.GraphedPrototypeStep(loss_fn, alpha=0.01, label_weight_axis=axis)
+
+    def gstep():
+        for x in (dimg, dcls, dpi, dpg, log_s):
+            x.grad = None
+        out = graphed(dimg, log_s.exp(), bank_d, snap_d, zs_d, dcls, dpi, dpg)
+        out["loss"].backward()
+
+    for _ in range(3):
+        gstep()
+    torch.cuda.synchronize()
+    a.record()
+    for _ in range(reps):
+        gstep()
+    b.record()
+    torch.cuda.synchronize()
     ours_ms = a.elapsed_time(b) / reps
     res = {"workload": f"LatteCLIP head step, batch {batch}, dim {dim}, {classes} classes, bf16 features, "
                        f"label_weight_axis={axis}",
-           "ms_per_step": ours_ms, "samples_per_s": batch / (ours_ms * 1e-3)}
+           "ms_per_step": ours_ms, "samples_per_s": batch / (ours_ms * 1e-3),
+           "path": "prototypes.GraphedPrototypeStep (CUDA-graph replay of prototype_step + backward + update_bank)",
+           "eager_launch_ms_per_step": eager_ms}
     if not cpu:
         return res
     import oracle
@@ -440,6 +462,103 @@ def gpu_eager_reference(dev, reps=3):
     return out
 
 
+def gpu_eager_head_reference(dev, batch=512, dim=512, classes=47, reps=10):
+    """The loss-head part of one ``train_one_epoch_v2`` iteration restated op for op in eager PyTorch on
+    this GPU, at the reference's own fine-tuning shape (BASELINE cfg2), INCLUDING its per-sample Python
+    loops and their implicit device-to-host reads (train.py:412-431 label gathers, :508-530 bank update),
+    six ``compute_text_weights`` calls (:444-449, bmm + topk :292-303), the mixture (:472-488, literal
+    broadcast: B == D) and two calls of the reference's own ClipLoss module (baseline/_ref) sharing the
+    image features (:491-504), then backward (:506).  Towers are outside: features arrive as tensors;
+    the class-name text features are gathered from a per-class table instead of re-encoded.  None of our
+    kernels run here; it is the like-for-like bar of `latteclip_head` in our arm."""
+    import collections
+    ref_mod = load_reference_loss_module()
+    g = torch.Generator().manual_seed(77)
+    bank = F.normalize(torch.randn(classes, dim, generator=g), dim=1)
+    cls = F.normalize(bank + 0.3 * torch.randn(classes, dim, generator=g), dim=1)
+    true = torch.randint(0, classes, (batch,), generator=g)
+    mk = lambda sd: F.normalize(bank[true] + sd * torch.randn(batch, dim, generator=g) * 3 / dim ** 0.5, dim=1)  # noqa: E731
+    img, pimg, pgrp = mk(1.2), mk(0.9), mk(0.7)
+    zs_ids = torch.randint(0, classes, (batch,), generator=g).tolist()
+    names = [f"class{k}" for k in range(classes)]
+    name2id = {c: k for k, c in enumerate(names)}
+    zs_names = [(names[k],) for k in zs_ids]
+    memory_bank = {c: bank[k].to(dev).clone() for k, c in enumerate(names)}
+    dimg, dcls, dpi, dpg = (x.to(dev).requires_grad_(True) for x in (img, cls, pimg, pgrp))
+    log_s = torch.tensor(math.log(SCALE), device=dev, requires_grad=True)
+    prototypes = torch.stack([memory_bank[c] for c in names])                    # train.py:347-350
+    loss_mod = ref_mod.ClipLoss(local_loss=True, gather_with_grad=True, cache_labels=True) if ref_mod else None
+    labels = torch.arange(batch, device=dev)
+
+    def clip(i, t, s):
+        if loss_mod is not None:
+            return loss_mod(i, t, s)
+        return (F.cross_entropy(s * i @ t.T, labels) + F.cross_entropy(s * t @ i.T, labels)) / 2
+
+    def text_weights(x, protos, preds):                                          # train.py:292-303
+        w = torch.bmm(x.unsqueeze(1), protos.T.unsqueeze(0).expand(x.shape[0], -1, -1)).squeeze(1)
+        top2, idx = torch.topk(w, 2, dim=1)
+        _ = idx[:, 0] == preds
+        return top2[:, 0] - top2[:, 1]
+
+    def step():
+        for x in (dimg, dcls, dpi, dpg, log_s):
+            x.grad = None
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            classifier = F.normalize(torch.stack([memory_bank[c] for c in names]), dim=1).T      # :384-389
+            logit_scale = log_s.exp()
+            preds = (100.0 * dimg @ classifier).argmax(dim=1)                                     # :410-411
+            zs_preds = torch.zeros_like(preds)
+            mb, mbz, lab, labz = [], [], [], []
+            for i in range(batch):                                                                # :415-431
+                zname = zs_names[i][0]
+                zs_preds[i] = name2id[zname]
+                cname = names[preds[i]]                     # implicit device-to-host read per sample
+                lab.append(name2id[cname]); labz.append(name2id[zname])
+                mb.append(memory_bank[cname]); mbz.append(memory_bank[zname])
+            mb, mbz = torch.stack(mb), torch.stack(mbz)
+            l_ft, l_zs = dcls[torch.tensor(lab, device=dev)], dcls[torch.tensor(labz, device=dev)]
+            w_img = text_weights(dpi, prototypes, preds).detach() + 1e-6                          # :444-449
+            w_grp = text_weights(dpg, prototypes, preds).detach() + 1e-6
+            w_img_z = text_weights(dpi, prototypes, zs_preds).detach() + 1e-6
+            w_grp_z = text_weights(dpg, prototypes, zs_preds).detach() + 1e-6
+            w_lbl = text_weights(l_ft, prototypes, preds).detach() + 1e-6
+            w_lbl_z = text_weights(l_zs, prototypes, zs_preds).detach() + 1e-6
+            tot, tot_z = w_lbl + w_img + w_grp, w_lbl_z + w_img_z + w_grp_z                       # :472-473
+            t_ft = (w_lbl * l_ft + dpi * w_img.unsqueeze(1) + dpg * w_grp.unsqueeze(1)) / tot.unsqueeze(1)
+            t_zs = (w_lbl * l_zs + dpi * w_img_z.unsqueeze(1) + dpg * w_grp_z.unsqueeze(1)) / tot_z.unsqueeze(1)
+            t_ft = mb + 0.01 * (t_ft - mb)                                                        # :487-488
+            t_zs = mbz + 0.01 * (t_zs - mbz)
+            total = clip(dimg, t_ft, logit_scale) + clip(dimg, t_zs, logit_scale)                 # :491-504
+        total.backward()                                                                          # :506
+        with torch.no_grad():                                                                     # :508-530
+            temp, cnt = {}, collections.defaultdict(int)
+            for i in range(batch):
+                pname, zname = names[preds[i]], names[zs_preds[i]]
+                for nm in (zname, pname):
+                    if nm not in temp:
+                        temp[nm] = torch.zeros_like(t_ft[i])
+                temp[zname] += t_zs[i]
+                temp[pname] += t_ft[i]
+                cnt[zname] += 1
+                cnt[pname] += 1
+            for nm in temp:
+                memory_bank[nm] = F.normalize(temp[nm] / cnt[nm], dim=0)
+        return total
+
+    step()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        loss = step()
+    torch.cuda.synchronize()
+    ms = (time.perf_counter() - t0) / reps * 1e3
+    return {"workload": f"LatteCLIP head step, batch {batch}, dim {dim}, {classes} classes, eager PyTorch with the "
+                        "reference's per-sample loops, bf16 autocast",
+            "ms_per_step": ms, "samples_per_s": batch / (ms * 1e-3), "loss": float(loss.detach()),
+            "clip_loss": "baseline/_ref/open_clip/loss.py ClipLoss" if ref_mod else "restatement of loss.py:102-130"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -463,6 +582,11 @@ def run_reference(args):
         line["gpu_eager"] = dict(gpu_eager_reference(torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))),
                                  note="the same algorithm in eager PyTorch on this GPU (materialised logits); "
                                       "extra information, the arm's value is the CPU measurement")
+        try:
+            line["gpu_eager_head"] = gpu_eager_head_reference(
+                torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0"))))
+        except Exception as exc:
+            line["gpu_eager_head"] = {"error": str(exc).splitlines()[0][:200]}
     print(json.dumps(line), flush=True)
 
 

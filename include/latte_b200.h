@@ -481,6 +481,38 @@ int latte_bank_finalize(const float* sums, int64_t ld_sums, const float* counts,
                         float* bank, int64_t ld_bank,
                         int64_t dim, int64_t num_classes, void* stream);
 
+/*
+ * DistillClipLoss (src/open_clip/loss.py:324-362: soft-target cross-entropy of the student's logits
+ * against the teacher's softmax, both directions), world size 1, fp16 operands [n, dim] with
+ * dim <= 768 (latte_prep_features makes them).  With W(S) = softmax_rows(S) + softmax_cols(S):
+ *   loss     = 1/(2n) [ sum row_lse_S + sum col_lse_S - s <I, W(S') T> ]      (S' = teacher logits)
+ *   dL/dI    = s/(2n) ( W(S) - W(S') ) T,   dL/dT = s/(2n) ( W(S) - W(S') )^T I
+ *   dL/ds    = 1/(2n) ( <I, W(S) T> - <I, W(S') T> )
+ * latte_distill_products computes out_img = W(S) @ gemm_txt and out_txt = W(S)^T @ gemm_img (fp32) for
+ * S = s * sweep_img @ sweep_txt^T without storing S or W beyond the blocked fp16 scratch of
+ * latte_clip_bwd (workspace: latte_clip_bwd_workspace_bytes(n, n, dim, LATTE_F16)); row_lse / col_lse
+ * are the LSE vectors of S from latte_clip_fwd.  The forward calls it with the teacher's features as
+ * the sweep pair and the student's as the gemm pair, the backward with the student's for both.
+ * latte_distill_loss / latte_distill_bwd_combine are the two streaming reductions around it (`aux`:
+ * latte_distill_aux_bytes of scratch).
+ */
+int latte_distill_aux_bytes(size_t* bytes);
+int latte_distill_products(const void* sweep_img, int64_t ld_sweep_img, const void* sweep_txt,
+                           int64_t ld_sweep_txt, const void* gemm_img, int64_t ld_gemm_img,
+                           const void* gemm_txt, int64_t ld_gemm_txt, int64_t n, int64_t dim,
+                           const float* logit_scale, const float* row_lse, const float* col_lse,
+                           float* out_img, float* out_txt, int64_t ld_out, void* workspace,
+                           size_t workspace_bytes, void* stream);
+int latte_distill_loss(const float* row_lse, const float* col_lse, int64_t n, const void* img,
+                       int64_t ld_img, const float* teacher_prod, int64_t ld_prod, int64_t dim,
+                       const float* logit_scale, float* loss, float* dot_out, void* aux,
+                       size_t aux_bytes, void* stream);
+int latte_distill_bwd_combine(const float* a_s, const float* a_t, const float* b_s, const float* b_t,
+                              int64_t ld_prod, const void* img, int64_t ld_img, int64_t n, int64_t dim,
+                              const float* logit_scale, const float* grad_loss, const float* dot_t,
+                              void* d_img, void* d_txt, int grad_dtype, int64_t ld_grad, float* d_scale,
+                              void* aux, size_t aux_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

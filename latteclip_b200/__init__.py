@@ -10,9 +10,11 @@ pipeline and training driver remain the reference's PyTorch code.
 
 from .loss import ClipLoss, create_loss, gather_features  # noqa: F401
 from .siglip import SigLipLoss  # noqa: F401
+from .distill import DistillClipLoss  # noqa: F401
+from . import train_step  # noqa: F401
 from . import prototypes  # noqa: F401
 from . import zero_shot  # noqa: F401
 from ._lib import build, version, clear_workspace_cache  # noqa: F401
 
-__all__ = ["ClipLoss", "SigLipLoss", "create_loss", "gather_features", "prototypes", "zero_shot", "build", "version",
+__all__ = ["ClipLoss", "SigLipLoss", "DistillClipLoss", "train_step", "create_loss", "gather_features", "prototypes", "zero_shot", "build", "version",
            "clear_workspace_cache"]

@@ -78,6 +78,12 @@ def _declare(lib):
     lib.latte_bank_accumulate.argtypes = [vp, vp, i64, i32, vp, vp, i64, i64, i64, vp, i64, vp,
                                           vp, sz, vp]
     lib.latte_bank_finalize.argtypes = [vp, i64, vp, vp, i64, i64, i64, vp]
+    lib.latte_distill_aux_bytes.argtypes = [c.POINTER(sz)]
+    lib.latte_distill_products.argtypes = [vp, i64, vp, i64, vp, i64, vp, i64, i64, i64, vp, vp, vp,
+                                           vp, vp, i64, vp, sz, vp]
+    lib.latte_distill_loss.argtypes = [vp, vp, i64, vp, i64, vp, i64, i64, vp, vp, vp, vp, sz, vp]
+    lib.latte_distill_bwd_combine.argtypes = [vp, vp, vp, vp, i64, vp, i64, i64, i64, vp, vp, vp, vp, vp,
+                                              i32, i64, vp, vp, sz, vp]
     for name in EXPORTS:
         if name not in ("latte_version", "latte_status_string"):
             getattr(lib, name).restype = i32
@@ -93,7 +99,8 @@ EXPORTS = [
     "latte_clip_fwd", "latte_clip_bwd", "latte_normalize_rows", "latte_nxc_workspace_bytes",
     "latte_nxc_argmax_margin", "latte_nxc_topk", "latte_seg_workspace_bytes", "latte_nxc_planes_bytes",
     "latte_nxc_split_prototypes", "latte_nxc_multi", "latte_mix_ema_fwd", "latte_mix_ema_bwd", "latte_bank_accumulate",
-    "latte_bank_finalize",
+    "latte_bank_finalize", "latte_distill_aux_bytes", "latte_distill_products", "latte_distill_loss",
+    "latte_distill_bwd_combine",
 ]
 
 
@@ -496,6 +503,74 @@ def clip_bwd(img_loc, txt_loc, img_all, txt_all, label_offset: int, logit_scale,
     if out is not None or phases != 3:
         return d_img, (d_part if partial else d_txt), d_scale, (d_img, d_txt, d_part, d_scale)
     return d_img, (d_part if partial else d_txt), d_scale
+
+
+# ------------------------------------------------------------------------------ DistillClipLoss
+def _distill_aux(dev):
+    need = ctypes.c_size_t()
+    _check(load().latte_distill_aux_bytes(ctypes.byref(need)), "latte_distill_aux_bytes")
+    ws = _scratch("distill_aux", need.value, dev)
+    return _aligned_ptr(ws)
+
+
+def distill_products(sweep_img, sweep_txt, gemm_img, gemm_txt, logit_scale, row_lse, col_lse):
+    """W = softmax_rows(S) + softmax_cols(S) of S = s * sweep_img @ sweep_txt.T (never stored), multiplied
+    into the other operand pair: -> (W @ gemm_txt, W.T @ gemm_img), fp32 [n, dim].  All four matrices
+    fp16 [n, dim]; row_lse / col_lse are the forward's LSE vectors of S (latte_clip_fwd)."""
+    mats = [_rows(x.detach(), "features") for x in (sweep_img, sweep_txt, gemm_img, gemm_txt)]
+    if any(m.dtype != torch.float16 for m in mats):
+        raise RuntimeError("distill_products: operands must be fp16 (latte_prep_features)")
+    n, dim = mats[0].shape
+    dev = mats[0].device
+    out_i = torch.empty(n, dim, dtype=torch.float32, device=dev)
+    out_t = torch.empty(n, dim, dtype=torch.float32, device=dev)
+    s = _scalar_f32(logit_scale)
+    ws = _scratch("bwd", _clip_ws_bytes(n, n, dim, _DTYPES[torch.float16], bwd=True), dev)
+    wp, wn = _aligned_ptr(ws)
+    with torch.cuda.device(dev):
+        _check(load().latte_distill_products(
+            _ptr(mats[0]), mats[0].stride(0), _ptr(mats[1]), mats[1].stride(0), _ptr(mats[2]),
+            mats[2].stride(0), _ptr(mats[3]), mats[3].stride(0), n, dim, _ptr(s),
+            _ptr(_vec(row_lse, torch.float32, "row_lse")), _ptr(_vec(col_lse, torch.float32, "col_lse")),
+            _ptr(out_i), _ptr(out_t), dim, wp, wn, _stream(mats[0])), "latte_distill_products")
+    return out_i, out_t
+
+
+def distill_loss(row_lse, col_lse, img, teacher_prod, logit_scale):
+    """-> (loss[1], dot[1]): loss = (sum row_lse + sum col_lse - s * <img, teacher_prod>) / (2 n)."""
+    img = _rows(img.detach(), "image_features")
+    n, dim = img.shape
+    dev = img.device
+    loss = torch.empty(1, dtype=torch.float32, device=dev)
+    dot = torch.empty(1, dtype=torch.float32, device=dev)
+    s = _scalar_f32(logit_scale)
+    ap, an = _distill_aux(dev)
+    with torch.cuda.device(dev):
+        _check(load().latte_distill_loss(_ptr(_vec(row_lse, torch.float32, "row_lse")),
+                                         _ptr(_vec(col_lse, torch.float32, "col_lse")), n, _ptr(img),
+                                         img.stride(0), _ptr(teacher_prod), teacher_prod.stride(0), dim,
+                                         _ptr(s), _ptr(loss), _ptr(dot), ap, an, _stream(img)),
+               "latte_distill_loss")
+    return loss, dot
+
+
+def distill_bwd_combine(a_s, a_t, b_s, b_t, img, logit_scale, grad_loss, dot_t, grad_dtype):
+    """-> (d_img, d_txt [n, dim] in grad_dtype, d_scale[1]) from the student / teacher products."""
+    img = _rows(img.detach(), "image_features")
+    n, dim = img.shape
+    dev = img.device
+    d_img = torch.empty(n, dim, dtype=grad_dtype, device=dev)
+    d_txt = torch.empty(n, dim, dtype=grad_dtype, device=dev)
+    d_scale = torch.empty(1, dtype=torch.float32, device=dev)
+    s, g = _scalar_f32(logit_scale), _scalar_f32(grad_loss)
+    ap, an = _distill_aux(dev)
+    with torch.cuda.device(dev):
+        _check(load().latte_distill_bwd_combine(_ptr(a_s), _ptr(a_t), _ptr(b_s), _ptr(b_t), a_s.stride(0),
+                                                _ptr(img), img.stride(0), n, dim, _ptr(s), _ptr(g),
+                                                _ptr(dot_t), _ptr(d_img), _ptr(d_txt), _DTYPES[grad_dtype],
+                                                dim, _ptr(d_scale), ap, an, _stream(img)),
+               "latte_distill_bwd_combine")
+    return d_img, d_txt, d_scale
 
 
 def siglip_supported(dtype: torch.dtype, dim: int) -> bool:

@@ -507,6 +507,7 @@ struct BwdScalars { float rho; int fast; float gs; float out_scale; };
 __device__ __forceinline__ BwdScalars bwd_scalars(const float* stats, const float* grad_loss,
                                                   float grad_mult, const float* logit_scale,
                                                   int64_t n_loc) {
+  // grad_loss == NULL: plain products (latte_distill_products), out_scale only undoes the fp16 scale
   BwdScalars o;
   const float lo = __ldg(stats) * kLog2e, hi = __ldg(stats + 1) * kLog2e;
   const bool ok = (hi - lo) <= 64.0f && hi < 3.0e38f && lo > -3.0e38f;   // also rejects NaN / inf
@@ -517,7 +518,8 @@ __device__ __forceinline__ BwdScalars bwd_scalars(const float* stats, const floa
   if (!(u_raw >= 0.f)) u_raw = 1.0f;
   const float u = fminf(u_raw, 1.0f) + 1.0e-3f;
   o.gs = fminf(fmaxf(13.0f - ceilf(log2f(u)), 13.0f), 22.0f);
-  o.out_scale = __ldg(grad_loss) * grad_mult / (2.0f * (float)n_loc) * __ldg(logit_scale) * exp2f(-o.gs);
+  o.out_scale = grad_loss ? __ldg(grad_loss) * grad_mult / (2.0f * (float)n_loc) * __ldg(logit_scale) * exp2f(-o.gs)
+                          : exp2f(-o.gs);
   return o;
 }
 
@@ -1538,7 +1540,7 @@ static int clip_bwd_impl(const void* img_loc, int64_t ld_img_loc, const void* tx
     sa.dtype = dtype; sa.n_loc = n_loc; sa.n_all = n_all; sa.dim = dim;
     sa.label_offset = label_offset; sa.logit_scale = logit_scale; sa.cross_terms = cross_terms;
     sa.g = gbuf; sa.ds_both = (single || rank_sweep) ? 1 : 0;
-    sa.nll_a = row_nll_all; sa.nll_b = col_nll_all;
+    sa.nll_a = row_nll_all; sa.nll_b = col_nll_all; sa.no_label = 0;
     PairGemmArgs ga = {};
     ga.g = gbuf; ga.n_loc = n_loc; ga.n_all = n_all; ga.dim = dim; ga.ld32 = (int64_t)w.ld32;
     ga.feat_dtype = LATTE_F16;
@@ -1844,6 +1846,276 @@ extern "C" int latte_normalize_bwd(const void* g, int64_t ld_g, int g_dtype, con
   if (rows == 0) return LATTE_OK;
   normalize_bwd_kernel<<<(unsigned)((rows * 32 + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       g, ld_g, g_dtype, x, ld_x, x_dtype, inv_norm, rows, dim, d_x, ld_dx);
+  LATTE_LAUNCH_OK();
+  return LATTE_OK;
+}
+
+// =========================================================================== DistillClipLoss
+// /root/reference/src/open_clip/loss.py:324-362.  With S = s I T^T (student), S' the teacher's logits,
+// P / P' the row softmaxes and Q / Q' the column softmaxes:
+//   loss = 1/(2N) [ sum_i lse_j S_ij + sum_j lse_i S_ij - sum_ij (P'_ij + Q'_ij) S_ij ]
+//   dL/dS_ij = 1/(2N) [ (P_ij + Q_ij) - (P'_ij + Q'_ij) ]
+// and sum_ij W_ij S_ij = s <I, W T>, so both the loss and its gradient reduce to the products
+// W.T and W^T.I with W = P + Q of one model multiplied into the STUDENT features: the gradient sweep
+// (without its label term) and the stream-K gradient GEMM of ClipLoss, fed with two different
+// operand pairs.  The [N, N] logits of neither model are ever stored.
+namespace latte {
+namespace {
+
+constexpr int kDistillBlocks = 1024;
+
+// partial[b] = sum over this CTA's share of (a) the 2N LSE values, (b) img .* prod; the last CTA
+// adds the partials in index order (deterministic) and writes
+//   loss = (sum_lse - s * dot) / (2N)  and  dot_out = dot
+__global__ void __launch_bounds__(256)
+distill_loss_kernel(const float* row_lse, const float* col_lse, int64_t n, const __half* img, int64_t ld_img,
+                    const float* prod, int64_t ld_prod, int64_t dim, const float* logit_scale,
+                    double* partial, unsigned int* counter, float* loss, float* dot_out) {
+  __shared__ double red_a[8], red_b[8];
+  __shared__ bool last;
+  double lse = 0.0, dot = 0.0;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (int64_t i = t0; i < n; i += stride) lse += (double)row_lse[i] + (double)col_lse[i];
+  const int64_t per_row = dim / 4;
+  for (int64_t v = t0; v < n * per_row; v += stride) {
+    const int64_t r = v / per_row, c = (v % per_row) * 4;
+    const float4 a = *reinterpret_cast<const float4*>(prod + r * ld_prod + c);
+    const uint2 raw = *reinterpret_cast<const uint2*>(img + r * ld_img + c);
+    const float2 x0 = __half22float2(*reinterpret_cast<const __half2*>(&raw.x));
+    const float2 x1 = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
+    dot += (double)(a.x * x0.x + a.y * x0.y) + (double)(a.z * x1.x + a.w * x1.y);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    lse += __shfl_xor_sync(0xffffffffu, lse, o);
+    dot += __shfl_xor_sync(0xffffffffu, dot, o);
+  }
+  if ((threadIdx.x & 31) == 0) { red_a[threadIdx.x >> 5] = lse; red_b[threadIdx.x >> 5] = dot; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0.0, b = 0.0;
+    for (int w = 0; w < 8; ++w) { a += red_a[w]; b += red_b[w]; }
+    partial[2 * blockIdx.x] = a;
+    partial[2 * blockIdx.x + 1] = b;
+    __threadfence();
+    last = atomicInc(counter, gridDim.x - 1) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!last || threadIdx.x != 0) return;
+  __threadfence();
+  double a = 0.0, b = 0.0;
+  for (unsigned k = 0; k < gridDim.x; ++k) {
+    a += *reinterpret_cast<volatile double*>(partial + 2 * k);
+    b += *reinterpret_cast<volatile double*>(partial + 2 * k + 1);
+  }
+  if (loss) *loss = (float)((a - (double)__ldg(logit_scale) * b) / (2.0 * (double)n));
+  if (dot_out) *dot_out = (float)b;
+}
+
+// d_img = k (A_s - A_t), d_txt = k (B_s - B_t) with k = grad * s / (2N);
+// d_scale = grad / (2N) * (<img, A_s> - dot_t)
+__global__ void __launch_bounds__(256)
+distill_combine_kernel(const float* a_s, const float* a_t, const float* b_s, const float* b_t, int64_t ld_prod,
+                       const __half* img, int64_t ld_img, int64_t n, int64_t dim, const float* logit_scale,
+                       const float* grad_loss, const float* dot_t, void* d_img, void* d_txt, int grad_dtype,
+                       int64_t ld_grad, double* partial, unsigned int* counter, float* d_scale) {
+  __shared__ double red[8];
+  __shared__ bool last;
+  const float k = __ldg(grad_loss) * __ldg(logit_scale) / (2.0f * (float)n);
+  const int64_t per_row = dim / 4;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  double dot = 0.0;
+  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < n * per_row; v += stride) {
+    const int64_t r = v / per_row, c = (v % per_row) * 4;
+    const float4 as = *reinterpret_cast<const float4*>(a_s + r * ld_prod + c);
+    const float4 at = *reinterpret_cast<const float4*>(a_t + r * ld_prod + c);
+    const float4 bs = *reinterpret_cast<const float4*>(b_s + r * ld_prod + c);
+    const float4 bt = *reinterpret_cast<const float4*>(b_t + r * ld_prod + c);
+    const uint2 raw = *reinterpret_cast<const uint2*>(img + r * ld_img + c);
+    const float2 x0 = __half22float2(*reinterpret_cast<const __half2*>(&raw.x));
+    const float2 x1 = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
+    dot += (double)(as.x * x0.x + as.y * x0.y) + (double)(as.z * x1.x + as.w * x1.y);
+    const float gi[4] = {k * (as.x - at.x), k * (as.y - at.y), k * (as.z - at.z), k * (as.w - at.w)};
+    const float gt[4] = {k * (bs.x - bt.x), k * (bs.y - bt.y), k * (bs.z - bt.z), k * (bs.w - bt.w)};
+    if (grad_dtype == LATTE_F32) {
+      *reinterpret_cast<float4*>(static_cast<float*>(d_img) + r * ld_grad + c) = make_float4(gi[0], gi[1], gi[2], gi[3]);
+      *reinterpret_cast<float4*>(static_cast<float*>(d_txt) + r * ld_grad + c) = make_float4(gt[0], gt[1], gt[2], gt[3]);
+    } else if (grad_dtype == LATTE_BF16) {
+      __nv_bfloat162 i0 = __floats2bfloat162_rn(gi[0], gi[1]), i1 = __floats2bfloat162_rn(gi[2], gi[3]);
+      __nv_bfloat162 t0 = __floats2bfloat162_rn(gt[0], gt[1]), t1 = __floats2bfloat162_rn(gt[2], gt[3]);
+      *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(d_img) + r * ld_grad + c) =
+          make_uint2(*reinterpret_cast<uint32_t*>(&i0), *reinterpret_cast<uint32_t*>(&i1));
+      *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(d_txt) + r * ld_grad + c) =
+          make_uint2(*reinterpret_cast<uint32_t*>(&t0), *reinterpret_cast<uint32_t*>(&t1));
+    } else {
+      __half2 i0 = __floats2half2_rn(gi[0], gi[1]), i1 = __floats2half2_rn(gi[2], gi[3]);
+      __half2 t0 = __floats2half2_rn(gt[0], gt[1]), t1 = __floats2half2_rn(gt[2], gt[3]);
+      *reinterpret_cast<uint2*>(static_cast<__half*>(d_img) + r * ld_grad + c) =
+          make_uint2(*reinterpret_cast<uint32_t*>(&i0), *reinterpret_cast<uint32_t*>(&i1));
+      *reinterpret_cast<uint2*>(static_cast<__half*>(d_txt) + r * ld_grad + c) =
+          make_uint2(*reinterpret_cast<uint32_t*>(&t0), *reinterpret_cast<uint32_t*>(&t1));
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = dot;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double b = 0.0;
+    for (int w = 0; w < 8; ++w) b += red[w];
+    partial[blockIdx.x] = b;
+    __threadfence();
+    last = atomicInc(counter, gridDim.x - 1) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!last || threadIdx.x != 0) return;
+  __threadfence();
+  double b = 0.0;
+  for (unsigned q = 0; q < gridDim.x; ++q) b += *reinterpret_cast<volatile double*>(partial + q);
+  *d_scale = (float)((double)__ldg(grad_loss) / (2.0 * (double)n) * (b - (double)__ldg(dot_t)));
+}
+
+}  // namespace
+}  // namespace latte
+
+extern "C" int latte_distill_aux_bytes(size_t* bytes) {
+  LATTE_CHECK_ARG(bytes);
+  *bytes = (size_t)kDistillBlocks * 2 * sizeof(double) + 256;
+  return LATTE_OK;
+}
+
+extern "C" int latte_distill_products(const void* sweep_img, int64_t ld_sweep_img, const void* sweep_txt,
+                                      int64_t ld_sweep_txt, const void* gemm_img, int64_t ld_gemm_img,
+                                      const void* gemm_txt, int64_t ld_gemm_txt, int64_t n, int64_t dim,
+                                      const float* logit_scale, const float* row_lse, const float* col_lse,
+                                      float* out_img, float* out_txt, int64_t ld_out, void* workspace,
+                                      size_t workspace_bytes, void* stream) {
+  LATTE_CHECK_ARG(sweep_img && sweep_txt && gemm_img && gemm_txt && logit_scale && row_lse && col_lse &&
+                  out_img && out_txt && workspace);
+  LATTE_CHECK_ARG(n > 0 && dim > 0 && ld_sweep_img >= dim && ld_sweep_txt >= dim && ld_gemm_img >= dim &&
+                  ld_gemm_txt >= dim && ld_out >= dim);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int dtype = LATTE_F16;
+  const WsLayout w = ws_layout(n, n, dim, dtype, true);
+  if (workspace_bytes < w.total) return LATTE_ERR_WORKSPACE;
+  if ((reinterpret_cast<uintptr_t>(workspace) & 255) != 0) return LATTE_ERR_BAD_ARG;
+  if (!w.pair || !clip_pair_supported(dtype, dim, ld_sweep_img, ld_sweep_txt, sweep_img, sweep_txt) ||
+      !clip_pair_supported(dtype, dim, ld_gemm_img, ld_gemm_txt, gemm_img, gemm_txt) || (ld_out % 4) != 0 ||
+      (reinterpret_cast<uintptr_t>(out_img) & 15) != 0 || (reinterpret_cast<uintptr_t>(out_txt) & 15) != 0)
+    return LATTE_ERR_UNSUPPORTED;
+  float* ws = static_cast<float*>(workspace);
+  float* row2 = ws + w.off_row2;
+  float* col2 = ws + w.off_col2;
+  float* rho = ws + w.off_rho;
+  int* fast_flag = reinterpret_cast<int*>(ws + w.off_rho + 1);
+  float* gscale = ws + w.off_rho + 3;
+  float* out_scale = ws + w.off_rho + 4;
+  float* st_buf = ws + w.off_rho + 8;
+  // LSE range for the one-ex2 epilogue; without nll vectors the |W| bound is 2 (fp16 scale 2^13)
+  lse_stats_kernel<<<1, 1024, 0, st>>>(row_lse, col_lse, n, nullptr, nullptr, nullptr, st_buf);
+  LATTE_LAUNCH_OK();
+  lse_vectors_kernel<<<(unsigned)((w.n_pad + 255) / 256), 256, 0, st>>>(
+      row_lse, col_lse, n, (int64_t)w.n_pad, st_buf, nullptr, 1.0f, logit_scale, n, rho, row2, col2,
+      ws + w.off_erow, ws + w.off_einvrow, ws + w.off_ecol, ws + w.off_einvcol);
+  LATTE_LAUNCH_OK();
+  const int dsn = clip_pair_ds_count();
+  if ((size_t)(2 * dsn) > w.ds_cap) return LATTE_ERR_WORKSPACE;
+  float* dsp = ws + w.off_ds;
+  __half* gbuf = reinterpret_cast<__half*>(ws + w.off_g);
+  float* acc_i = ws + w.off_acc0;
+  float* acc_t = ws + w.off_acc1;
+  const size_t acc_bytes = (size_t)n * w.ld32 * sizeof(float);
+  LATTE_CUDA_OK(cudaMemsetAsync(dsp, 0, (size_t)2 * dsn * sizeof(float), st));
+  PairSweepArgs sa;
+  sa.dtype = dtype; sa.n_loc = n; sa.n_all = n; sa.dim = dim;
+  sa.label_offset = 0; sa.logit_scale = logit_scale; sa.cross_terms = 1; sa.no_label = 1;
+  sa.g = gbuf; sa.ds_both = 1; sa.nll_a = nullptr; sa.nll_b = nullptr;
+  sa.x = sweep_img; sa.ldx = ld_sweep_img; sa.y = sweep_txt; sa.ldy = ld_sweep_txt;
+  sa.lse_a2 = row2; sa.lse_b2 = col2; sa.ds_partial = dsp;
+  sa.e_a = ws + w.off_erow; sa.einv_b = ws + w.off_einvcol; sa.fast_flag = fast_flag;
+  sa.gscale_log2 = gscale;
+  PairGemmArgs ga = {};
+  ga.g = gbuf; ga.n_loc = n; ga.n_all = n; ga.dim = dim; ga.ld32 = (int64_t)w.ld32;
+  ga.feat_dtype = LATTE_F16;
+  ga.out_dtype = LATTE_F32; ga.ld_out = ld_out; ga.out_scale = out_scale;
+  ga.y16 = gemm_txt; ga.ldy16 = ld_gemm_txt;
+  ga.x16 = gemm_img; ga.ldx16 = ld_gemm_img;
+  ga.dx32 = acc_i; ga.dy32 = acc_t; ga.ld_dy32 = (int64_t)w.ld32; ga.dy_scale = nullptr;
+  ga.dy_peers = nullptr; ga.n_peers = 0;
+  ga.dx_out = out_img; ga.dy_out = out_txt;
+  const bool direct_i = clip_pair_gemm_direct(ga, 0);
+  const bool direct_t = clip_pair_gemm_direct(ga, 1);
+  if (!direct_i) LATTE_CUDA_OK(cudaMemsetAsync(acc_i, 0, acc_bytes, st));
+  if (!direct_t) LATTE_CUDA_OK(cudaMemsetAsync(acc_t, 0, acc_bytes, st));
+  int rc = clip_pair_gemm_fixup(ga, 0, st);
+  if (rc) return rc;
+  rc = clip_pair_sweep(sa, st);
+  if (rc) return rc;
+  rc = clip_pair_gemm(ga, st);
+  if (rc) return rc;
+  rc = clip_pair_gemm_fixup(ga, 1, st);
+  if (rc) return rc;
+  if (!direct_i) {
+    rc = clip_pair_scale_cast(acc_i, nullptr, (int64_t)w.ld32, out_img, nullptr, LATTE_F32, ld_out, n, dim,
+                              out_scale, st);
+    if (rc) return rc;
+  }
+  if (!direct_t) {
+    rc = clip_pair_scale_cast(acc_t, nullptr, (int64_t)w.ld32, out_txt, nullptr, LATTE_F32, ld_out, n, dim,
+                              out_scale, st);
+    if (rc) return rc;
+  }
+  return LATTE_OK;
+}
+
+extern "C" int latte_distill_loss(const float* row_lse, const float* col_lse, int64_t n, const void* img,
+                                  int64_t ld_img, const float* teacher_prod, int64_t ld_prod, int64_t dim,
+                                  const float* logit_scale, float* loss, float* dot_out, void* aux,
+                                  size_t aux_bytes, void* stream) {
+  LATTE_CHECK_ARG(row_lse && col_lse && img && teacher_prod && logit_scale && loss && dot_out && aux);
+  LATTE_CHECK_ARG(n > 0 && dim > 0 && (dim % 4) == 0 && (ld_img % 4) == 0 && (ld_prod % 4) == 0);
+  size_t need;
+  latte_distill_aux_bytes(&need);
+  if (aux_bytes < need) return LATTE_ERR_WORKSPACE;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const uintptr_t base = (reinterpret_cast<uintptr_t>(aux) + 15) / 16 * 16;
+  unsigned int* counter = reinterpret_cast<unsigned int*>(base);
+  double* partial = reinterpret_cast<double*>(base + 16);
+  LATTE_CUDA_OK(cudaMemsetAsync(counter, 0, 16, st));
+  int64_t blocks = (n * (dim / 4) + 255) / 256;
+  if (blocks > kDistillBlocks - 2) blocks = kDistillBlocks - 2;
+  distill_loss_kernel<<<(unsigned)blocks, 256, 0, st>>>(row_lse, col_lse, n, static_cast<const __half*>(img),
+                                                        ld_img, teacher_prod, ld_prod, dim, logit_scale,
+                                                        partial, counter, loss, dot_out);
+  LATTE_LAUNCH_OK();
+  return LATTE_OK;
+}
+
+extern "C" int latte_distill_bwd_combine(const float* a_s, const float* a_t, const float* b_s, const float* b_t,
+                                         int64_t ld_prod, const void* img, int64_t ld_img, int64_t n,
+                                         int64_t dim, const float* logit_scale, const float* grad_loss,
+                                         const float* dot_t, void* d_img, void* d_txt, int grad_dtype,
+                                         int64_t ld_grad, float* d_scale, void* aux, size_t aux_bytes,
+                                         void* stream) {
+  LATTE_CHECK_ARG(a_s && a_t && b_s && b_t && img && logit_scale && grad_loss && dot_t && d_img && d_txt &&
+                  d_scale && aux);
+  LATTE_CHECK_ARG(n > 0 && dim > 0 && (dim % 4) == 0 && (ld_img % 4) == 0 && (ld_prod % 4) == 0 &&
+                  (ld_grad % 4) == 0);
+  LATTE_CHECK_ARG(grad_dtype >= LATTE_F32 && grad_dtype <= LATTE_F16);
+  size_t need;
+  latte_distill_aux_bytes(&need);
+  if (aux_bytes < need) return LATTE_ERR_WORKSPACE;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const uintptr_t base = (reinterpret_cast<uintptr_t>(aux) + 15) / 16 * 16;
+  unsigned int* counter = reinterpret_cast<unsigned int*>(base);
+  double* partial = reinterpret_cast<double*>(base + 16);
+  LATTE_CUDA_OK(cudaMemsetAsync(counter, 0, 16, st));
+  int64_t blocks = (n * (dim / 4) + 255) / 256;
+  if (blocks > kDistillBlocks - 2) blocks = kDistillBlocks - 2;
+  distill_combine_kernel<<<(unsigned)blocks, 256, 0, st>>>(
+      a_s, a_t, b_s, b_t, ld_prod, static_cast<const __half*>(img), ld_img, n, dim, logit_scale, grad_loss,
+      dot_t, d_img, d_txt, grad_dtype, ld_grad, partial, counter, d_scale);
   LATTE_LAUNCH_OK();
   return LATTE_OK;
 }

@@ -1596,9 +1596,10 @@ int clip_pair_sweep(const PairSweepArgs& a, cudaStream_t stream) {
   p.nll_a = a.nll_a; p.nll_b = a.nll_b;
   p.cb = a.cross_terms ? 1.f : 0.f;
   p.cd = a.cross_terms ? 2.f : 1.f;
+  if (a.no_label) { p.cd = 0.f; p.nll_a = p.nll_b = nullptr; }
   // one sweep standing for both directions (world size 1) carries both softmax terms in ds
   p.ds_cb = a.ds_both ? p.cb : 0.f;
-  p.ds_cd = a.ds_both ? p.cd : 1.f;
+  p.ds_cd = a.no_label ? 0.f : (a.ds_both ? p.cd : 1.f);
   p.ds_partial = a.ds_partial;
   p.kch = (int)((a.dim + kBK - 1) / kBK);
   p.tail_chunks = p.kch > kTmemChunks ? p.kch - kTmemChunks : 0;

@@ -104,6 +104,7 @@ struct PairSweepArgs {
   const float* nll_b;         //           and the y side (accurate 1 - P_label near convergence)
   int cross_terms;
   int ds_both;                // 1: d loss / d s takes both softmax terms from this sweep
+  int no_label;               // 1: G = P_row + cb * P_col without the label term (soft-target losses)
   void* g;                    // blocked fp16 G scratch (PairGeom::g_elems)
   float* ds_partial;          // [clip_pair_ds_count()] zeroed by the caller
 };

@@ -6,6 +6,7 @@
 // warp-shuffle reductions, no floating-point atomics (deterministic; per-class accumulation
 // follows the reference's sample order).
 #include "latte_common.cuh"
+#include "tc_ptx.cuh"
 
 namespace latte {
 namespace {
@@ -56,6 +57,11 @@ __device__ __forceinline__ void st4(void* base, int64_t idx, int dtype, float4 v
   *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(base) + idx) = raw;
 }
 
+// dtype as a template parameter: with a run-time dtype every load sits behind a branch and the
+// 16-bit conversions consume each load where it is issued
+template <int DT> __device__ __forceinline__ float4 ld4t(const void* base, int64_t idx) { return ld4(base, idx, DT); }
+template <int DT> __device__ __forceinline__ void st4t(void* base, int64_t idx, float4 v) { st4(base, idx, DT, v); }
+
 __device__ __forceinline__ float block_sum(float v, float* red) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -104,6 +110,7 @@ __device__ __forceinline__ float mix_one(float wl, float l, float p, float wi, f
   return m + alpha * (mix - m);
 }
 
+template <int DT>
 __global__ void __launch_bounds__(128) mix_ema_fwd_kernel(MixArgs a) {
   const int64_t i = blockIdx.x;
   const int64_t cp = a.preds[i], cz = a.zs[i];
@@ -113,10 +120,10 @@ __global__ void __launch_bounds__(128) mix_ema_fwd_kernel(MixArgs a) {
   const bool quirk = a.label_axis == LATTE_LABEL_AXIS_QUIRK;
   if (a.vec) {
     for (int64_t d = (int64_t)threadIdx.x * 4; d < a.dim; d += (int64_t)blockDim.x * 4) {
-      const float4 lf = ld4(a.class_text, cp * a.ld_ct + d, a.dtype);
-      const float4 lz = ld4(a.class_text, cz * a.ld_ct + d, a.dtype);
-      const float4 p = ld4(a.per_image, i * a.ld_pi + d, a.dtype);
-      const float4 g = ld4(a.per_group, i * a.ld_pg + d, a.dtype);
+      const float4 lf = ld4t<DT>(a.class_text, cp * a.ld_ct + d);
+      const float4 lz = ld4t<DT>(a.class_text, cz * a.ld_ct + d);
+      const float4 p = ld4t<DT>(a.per_image, i * a.ld_pi + d);
+      const float4 g = ld4t<DT>(a.per_group, i * a.ld_pg + d);
       const float4 mf = __ldg(reinterpret_cast<const float4*>(a.bank + cp * a.ld_bank + d));
       const float4 mz = __ldg(reinterpret_cast<const float4*>(a.bank + cz * a.ld_bank + d));
       float4 wl = make_float4(wl_row, wl_row, wl_row, wl_row);
@@ -130,8 +137,8 @@ __global__ void __launch_bounds__(128) mix_ema_fwd_kernel(MixArgs a) {
       oz.y = mix_one(wl.y, lz.y, p.y, wi, g.y, wg, tot_zs, mz.y, a.alpha);
       oz.z = mix_one(wl.z, lz.z, p.z, wi, g.z, wg, tot_zs, mz.z, a.alpha);
       oz.w = mix_one(wl.w, lz.w, p.w, wi, g.w, wg, tot_zs, mz.w, a.alpha);
-      st4(a.t_ft, i * a.ld_out + d, a.dtype, of);
-      st4(a.t_zs, i * a.ld_out + d, a.dtype, oz);
+      st4t<DT>(a.t_ft, i * a.ld_out + d, of);
+      st4t<DT>(a.t_zs, i * a.ld_out + d, oz);
     }
   } else {
     for (int64_t d = threadIdx.x; d < a.dim; d += blockDim.x) {
@@ -382,12 +389,11 @@ __global__ void __launch_bounds__(128) seg_final_kernel(SegArgs a) {
 // in order -- entry order of the reference loop, zs row then ft row of every sample,
 // train.py:511-527 -- adding each row into the accumulator row of its class (a thread owns its
 // feature columns: no conflicts, no atomics), and writes its [C, D] partial; a second kernel adds
-// the chunk partials in chunk order.  Every feature row is read exactly once, 16 rows in flight per
-// thread.  With `d_per_image` the same pass is the mixer's backward: it also writes the two
+// the chunk partials in chunk order.  Every feature row is read exactly once, staged through a ring of
+// 1-D bulk copies (up to 64 row pairs in flight per SM).  With `d_per_image` the same pass is the mixer's backward: it also writes the two
 // row-shaped gradients from the rows it holds, so d_t_ft / d_t_zs are read once for all four
 // outputs (the five-launch sort path re-read them for the class sums).
 constexpr int kClsChunks = 128;
-constexpr int kClsUnroll = 8;
 constexpr size_t kClsSmemMax = 200 * 1024;
 
 struct ClsArgs {
@@ -405,131 +411,211 @@ struct ClsArgs {
   float* out; int64_t ld_out; int accumulate; float* counts; float post_scale;
 };
 
-struct ClsBatch {
-  float4 vf[kClsUnroll], vz[kClsUnroll];
-  int cp[kClsUnroll], cz[kClsUnroll];
-  float inv_f[kClsUnroll], inv_z[kClsUnroll], wl[kClsUnroll], wi[kClsUnroll], wg[kClsUnroll];
-};
-
-__device__ __forceinline__ void cls_load(const ClsArgs& a, int64_t i0, int64_t r1, int64_t d, bool col_ok,
-                                         bool quirk, ClsBatch& b) {
-#pragma unroll
-  for (int u = 0; u < kClsUnroll; ++u) {
-    const int64_t i = i0 + u;
-    b.cp[u] = b.cz[u] = -1;
-    b.vf[u] = b.vz[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-    b.inv_f[u] = b.inv_z[u] = b.wl[u] = 1.f;
-    b.wi[u] = b.wg[u] = 0.f;
-    if (i < r1) {
-      const int64_t p = __ldg(a.preds + i), z = __ldg(a.zs + i);
-      b.cp[u] = (p >= 0 && p < a.num_classes) ? (int)p : -1;      // out-of-range ids are dropped
-      b.cz[u] = (z >= 0 && z < a.num_classes) ? (int)z : -1;
-      if (col_ok) {
-        b.vf[u] = ld4(a.src_ft, i * a.ld_src + d, a.dtype);
-        b.vz[u] = ld4(a.src_zs, i * a.ld_src + d, a.dtype);
-      }
-      if (a.w_lbl) {
-        const float wl = __ldg(a.w_lbl + i);
-        b.wi[u] = __ldg(a.w_img + i);
-        b.wg[u] = __ldg(a.w_grp + i);
-        b.inv_f[u] = a.alpha / (wl + b.wi[u] + b.wg[u]);
-        b.inv_z[u] = a.alpha / (__ldg(a.w_lbl_zs + i) + b.wi[u] + b.wg[u]);
-        if (!quirk) b.wl[u] = wl;        // quirk axis: the label weight is a column factor (final step)
-      }
-    }
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+// 4 consecutive elements of a row staged in shared memory
+template <int DT> __device__ __forceinline__ float4 lds4(const uint8_t* row, int64_t col) {
+  if (DT == LATTE_F32) return *reinterpret_cast<const float4*>(row + col * 4);
+  const uint2 raw = *reinterpret_cast<const uint2*>(row + col * 2);
+  float4 o;
+  if (DT == LATTE_BF16) {
+    o.x = __uint_as_float(raw.x << 16); o.y = __uint_as_float(raw.x & 0xffff0000u);
+    o.z = __uint_as_float(raw.y << 16); o.w = __uint_as_float(raw.y & 0xffff0000u);
+  } else {
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&raw.x));
+    const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
+    o.x = a.x; o.y = a.y; o.z = b.x; o.w = b.y;
   }
+  return o;
 }
 
-__device__ __forceinline__ void cls_accum(const ClsArgs& a, int64_t i0, int64_t r1, int64_t d, bool col_ok,
-                                          bool quirk, int nvec, float4* acc, int* cnt, const ClsBatch& b) {
-#pragma unroll
-  for (int u = 0; u < kClsUnroll; ++u) {
-    const int64_t i = i0 + u;
-    if (i >= r1) break;
-    if (threadIdx.x == 0) {
-      if (b.cz[u] >= 0) cnt[b.cz[u]] += 1;
-      if (b.cp[u] >= 0) cnt[b.cp[u]] += 1;
-    }
-    if (!col_ok) continue;
-    const float4 gf = b.vf[u], gz = b.vz[u];
-    if (a.d_per_image) {
-      const float inv_ft = b.inv_f[u], inv_zs = b.inv_z[u];
-      float4 dm;
-      dm.x = gf.x * inv_ft + gz.x * inv_zs; dm.y = gf.y * inv_ft + gz.y * inv_zs;
-      dm.z = gf.z * inv_ft + gz.z * inv_zs; dm.w = gf.w * inv_ft + gz.w * inv_zs;
-      const float wi = b.wi[u], wg = b.wg[u];
-      st4(a.d_per_image, i * a.ld_dp + d, a.dtype, make_float4(wi * dm.x, wi * dm.y, wi * dm.z, wi * dm.w));
-      st4(a.d_per_group, i * a.ld_dp + d, a.dtype, make_float4(wg * dm.x, wg * dm.y, wg * dm.z, wg * dm.w));
-    }
-    if (b.cz[u] >= 0) {            // entry 2i: the zs-list row first (train.py:524)
-      float4* q = acc + (int64_t)b.cz[u] * nvec + threadIdx.x;
-      const float sc = b.inv_z[u] * b.wl[u];
-      float4 t = *q;
-      t.x = fmaf(gz.x, sc, t.x); t.y = fmaf(gz.y, sc, t.y);
-      t.z = fmaf(gz.z, sc, t.z); t.w = fmaf(gz.w, sc, t.w);
-      *q = t;
-    }
-    if (b.cp[u] >= 0) {            // entry 2i + 1: the ft-list row (train.py:525)
-      float4* q = acc + (int64_t)b.cp[u] * nvec + threadIdx.x;
-      const float sc = b.inv_f[u] * b.wl[u];
-      float4 t = *q;
-      t.x = fmaf(gf.x, sc, t.x); t.y = fmaf(gf.y, sc, t.y);
-      t.z = fmaf(gf.z, sc, t.z); t.w = fmaf(gf.w, sc, t.w);
-      *q = t;
-    }
-  }
-}
+// Shared memory of cls_stream_kernel: [C, D] fp32 accumulator | ring of `groups` x 4 row pairs (the zs
+// row and the ft row of one sample, filled by 1-D bulk copies: bytes in flight are bounded by the
+// ring, not by registers; one mbarrier per group of 4 samples keeps the per-row bookkeeping small) |
+// ids and weights of 256 samples | class counts | mbarriers.
+constexpr int kClsIdRows = 256;
+constexpr int kClsGrp = 4;
+struct __align__(16) ClsIds { int p, z; float wl, wlz, wi, wg, pad0, pad1; };
 
-__global__ void __launch_bounds__(256) cls_stream_kernel(ClsArgs a) {
-  extern __shared__ __align__(16) uint8_t cls_smem[];
+template <int DT>
+__global__ void __launch_bounds__(288) cls_stream_kernel(ClsArgs a, int groups, int row_bytes) {
+  extern __shared__ __align__(128) uint8_t cls_smem[];
+  using namespace ptx;
   const int nvec = (int)(a.dim / 4);
-  float4* acc = reinterpret_cast<float4*>(cls_smem);                              // [C][nvec]
-  int* cnt = reinterpret_cast<int*>(cls_smem + (size_t)a.num_classes * nvec * 16);   // [C]
-  for (int k = threadIdx.x; k < a.num_classes * nvec; k += blockDim.x) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int k = threadIdx.x; k < a.num_classes; k += blockDim.x) cnt[k] = 0;
-  __syncthreads();
+  const size_t acc_bytes = ((size_t)a.num_classes * nvec * 16 + 127) / 128 * 128;
+  float4* acc = reinterpret_cast<float4*>(cls_smem);                                        // [C][nvec]
+  uint8_t* ring = cls_smem + acc_bytes;                                    // [groups][4][2][row_bytes]
+  const int grp_bytes = kClsGrp * 2 * row_bytes;
+  ClsIds* ids = reinterpret_cast<ClsIds*>(ring + (size_t)groups * grp_bytes);               // [256]
+  int* cnt = reinterpret_cast<int*>(ids + kClsIdRows);                                      // [C]
+  const uint32_t bar_full = smem_u32(cnt + ((a.num_classes + 3) / 4 * 4));                  // [groups]
+  const uint32_t bar_empty = bar_full + 8 * groups;                                         // [groups]
+  const int ncons = (int)blockDim.x - 32;                  // consumer threads (the last warp produces)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool producer = warp == (ncons >> 5);
   const int64_t r0 = (int64_t)blockIdx.x * a.rows_per_chunk;
   const int64_t r1 = min(a.batch, r0 + a.rows_per_chunk);
-  const bool col_ok = (int)threadIdx.x < nvec;
-  const int64_t d = (int64_t)threadIdx.x * 4;
-  const bool quirk = a.w_lbl && a.label_axis == LATTE_LABEL_AXIS_QUIRK;
-  // two batches of rows in flight: the loads of batch k + 1 are issued before batch k is added
-  ClsBatch ba, bb;
-  cls_load(a, r0, r1, d, col_ok, quirk, ba);
-  for (int64_t i0 = r0; i0 < r1; i0 += 2 * kClsUnroll) {
-    cls_load(a, i0 + kClsUnroll, r1, d, col_ok, quirk, bb);
-    cls_accum(a, i0, r1, d, col_ok, quirk, nvec, acc, cnt, ba);
-    cls_load(a, i0 + 2 * kClsUnroll, r1, d, col_ok, quirk, ba);
-    cls_accum(a, i0 + kClsUnroll, r1, d, col_ok, quirk, nvec, acc, cnt, bb);
+  const int rows = (int)(r1 - r0);
+  const int ngrp = (rows + kClsGrp - 1) / kClsGrp;
+
+  for (int k = threadIdx.x; k < a.num_classes * nvec; k += blockDim.x) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int k = threadIdx.x; k < a.num_classes; k += blockDim.x) cnt[k] = 0;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < groups; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, ncons >> 5);
+    }
+    fence_mbar_init();
   }
   __syncthreads();
+
+  if (producer) {
+    if (lane == 0) {
+      const uint64_t pol = policy_evict_first();          // every row is read once
+      const uint8_t* sf = static_cast<const uint8_t*>(a.src_ft);
+      const uint8_t* sz = static_cast<const uint8_t*>(a.src_zs);
+      const int64_t pitch = a.ld_src * (int64_t)(row_bytes / a.dim);      // bytes per source row
+      int s = 0;
+      uint32_t phase = 0;
+      for (int gk = 0; gk < ngrp; ++gk) {
+        const int n = min(kClsGrp, rows - gk * kClsGrp);
+        mbar_wait(bar_empty + 8 * s, phase ^ 1);
+        const uint32_t dst = smem_u32(ring + (size_t)s * grp_bytes);
+        const uint32_t bar = bar_full + 8 * s;
+        mbar_arrive_expect_tx(bar, (uint32_t)(n * 2 * row_bytes));
+        for (int u = 0; u < n; ++u) {
+          const int64_t off = (r0 + gk * kClsGrp + u) * pitch;
+          bulk_load_1d(dst + (2 * u) * row_bytes, sz + off, (uint32_t)row_bytes, bar, pol);
+          bulk_load_1d(dst + (2 * u + 1) * row_bytes, sf + off, (uint32_t)row_bytes, bar, pol);
+        }
+        if (++s == groups) { s = 0; phase ^= 1; }
+      }
+    }
+    return;
+  }
+
+  // ------------------------------------------------------------ consumers: thread -> 4 columns
+  const bool col_ok = (int)threadIdx.x < nvec;
+  const int d = col_ok ? (int)threadIdx.x * 4 : 0;            // idle lanes re-read column 0
+  const bool quirk = a.w_lbl && a.label_axis == LATTE_LABEL_AXIS_QUIRK;
+  float4* my_acc = acc + threadIdx.x;
+  int s = 0;
+  uint32_t phase = 0;
+  for (int k0 = 0; k0 < rows; k0 += kClsIdRows) {
+    // ids and weights of the next 256 samples (coalesced), validated and counted once
+    named_bar_sync(1, ncons);
+    for (int t = threadIdx.x; t < kClsIdRows && k0 + t < rows; t += ncons) {
+      const int64_t i = r0 + k0 + t;
+      const int64_t p = a.preds[i], z = a.zs[i];
+      ClsIds q;
+      q.p = (p >= 0 && p < a.num_classes) ? (int)p : -1;      // out-of-range ids are dropped
+      q.z = (z >= 0 && z < a.num_classes) ? (int)z : -1;
+      q.wl = q.wlz = 1.f; q.wi = q.wg = 0.f; q.pad0 = q.pad1 = 0.f;
+      if (a.w_lbl) { q.wl = a.w_lbl[i]; q.wlz = a.w_lbl_zs[i]; q.wi = a.w_img[i]; q.wg = a.w_grp[i]; }
+      ids[t] = q;
+      if (q.z >= 0) atomicAdd(cnt + q.z, 1);                  // integer counts: order does not matter
+      if (q.p >= 0) atomicAdd(cnt + q.p, 1);
+    }
+    named_bar_sync(1, ncons);
+    const int kend = min(rows, k0 + kClsIdRows);
+    for (int k = k0; k < kend; k += kClsGrp) {
+      mbar_wait(bar_full + 8 * s, phase);
+      const uint8_t* grp = ring + (size_t)s * grp_bytes;
+      float4 gz[kClsGrp], gf[kClsGrp];
+#pragma unroll
+      for (int u = 0; u < kClsGrp; ++u) {                      // rows past the chunk: stale bytes, unused
+        gz[u] = lds4<DT>(grp + (2 * u) * row_bytes, d);
+        gf[u] = lds4<DT>(grp + (2 * u + 1) * row_bytes, d);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_empty + 8 * s);            // this warp has its copy of the group
+      if (++s == groups) { s = 0; phase ^= 1; }
+      if (!col_ok) continue;
+#pragma unroll
+      for (int u = 0; u < kClsGrp; ++u) {
+        if (k + u >= kend) break;
+        const ClsIds q = ids[k + u - k0];
+        float inv_ft = 1.f, inv_zs = 1.f, wl = 1.f;
+        if (a.w_lbl) {
+          inv_ft = a.alpha / (q.wl + q.wi + q.wg);
+          inv_zs = a.alpha / (q.wlz + q.wi + q.wg);
+          if (!quirk) wl = q.wl;       // quirk axis: the label weight is a column factor (final step)
+        }
+        if (a.d_per_image) {
+          const int64_t i = r0 + k + u;
+          float4 dm;
+          dm.x = gf[u].x * inv_ft + gz[u].x * inv_zs; dm.y = gf[u].y * inv_ft + gz[u].y * inv_zs;
+          dm.z = gf[u].z * inv_ft + gz[u].z * inv_zs; dm.w = gf[u].w * inv_ft + gz[u].w * inv_zs;
+          st4t<DT>(a.d_per_image, i * a.ld_dp + d, make_float4(q.wi * dm.x, q.wi * dm.y, q.wi * dm.z, q.wi * dm.w));
+          st4t<DT>(a.d_per_group, i * a.ld_dp + d, make_float4(q.wg * dm.x, q.wg * dm.y, q.wg * dm.z, q.wg * dm.w));
+        }
+        if (q.z >= 0) {            // entry 2i: the zs-list row first (train.py:524)
+          const float sc = inv_zs * wl;
+          float4* o = my_acc + q.z * nvec;
+          float4 t = *o;
+          t.x = fmaf(gz[u].x, sc, t.x); t.y = fmaf(gz[u].y, sc, t.y);
+          t.z = fmaf(gz[u].z, sc, t.z); t.w = fmaf(gz[u].w, sc, t.w);
+          *o = t;
+        }
+        if (q.p >= 0) {            // entry 2i + 1: the ft-list row (train.py:525)
+          const float sc = inv_ft * wl;
+          float4* o = my_acc + q.p * nvec;
+          float4 t = *o;
+          t.x = fmaf(gf[u].x, sc, t.x); t.y = fmaf(gf[u].y, sc, t.y);
+          t.z = fmaf(gf[u].z, sc, t.z); t.w = fmaf(gf[u].w, sc, t.w);
+          *o = t;
+        }
+      }
+    }
+  }
+  named_bar_sync(1, ncons);
   float4* dst = reinterpret_cast<float4*>(a.partial) + (int64_t)blockIdx.x * a.num_classes * nvec;
-  for (int k = threadIdx.x; k < a.num_classes * nvec; k += blockDim.x) dst[k] = acc[k];
-  for (int k = threadIdx.x; k < a.num_classes; k += blockDim.x)
+  for (int k = threadIdx.x; k < a.num_classes * nvec; k += ncons) dst[k] = acc[k];
+  for (int k = threadIdx.x; k < a.num_classes; k += ncons)
     a.cnt_partial[(int64_t)blockIdx.x * a.num_classes + k] = cnt[k];
 }
 
-// out[c] (+)= post_scale * colweight * sum over the chunks, in chunk order
+// out[c] (+)= post_scale * colweight * sum over the chunks.  One CTA per (class, 32 vector columns):
+// warp g adds the chunks of quarter g in chunk order, the four quarter sums are added in order.
 __global__ void __launch_bounds__(128) cls_final_kernel(ClsArgs a) {
+  __shared__ float4 quarter[4][32];
+  __shared__ int cnt_red[4];
   const int nvec = (int)(a.dim / 4);
   const int c = blockIdx.x;
-  const int v = blockIdx.y * 128 + threadIdx.x;
-  if (blockIdx.y == 0 && threadIdx.x == 0 && a.counts) {
+  const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
+  const int v = blockIdx.y * 32 + lane;
+  if (blockIdx.y == 0 && a.counts) {
     int n = 0;
-    for (int k = 0; k < a.chunks; ++k) n += a.cnt_partial[(int64_t)k * a.num_classes + c];
-    a.counts[c] = (float)n;
+    for (int k = threadIdx.x; k < a.chunks; k += 128) n += a.cnt_partial[(int64_t)k * a.num_classes + c];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
+    if (lane == 0) cnt_red[grp] = n;
   }
-  if (v >= nvec) return;
-  const float4* src = reinterpret_cast<const float4*>(a.partial) + (int64_t)c * nvec + v;
-  const int64_t step = (int64_t)a.num_classes * nvec;
+  const int per = (a.chunks + 3) / 4;
+  const int k_lo = grp * per, k_hi = min(a.chunks, k_lo + per);
   float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int k0 = 0; k0 < a.chunks; k0 += 8) {
-    float4 t[8];
+  if (v < nvec) {
+    const float4* src = reinterpret_cast<const float4*>(a.partial) + (int64_t)c * nvec + v;
+    const int64_t step = (int64_t)a.num_classes * nvec;
+    for (int k0 = k_lo; k0 < k_hi; k0 += 8) {
+      float4 t[8];
 #pragma unroll
-    for (int u = 0; u < 8; ++u)
-      t[u] = k0 + u < a.chunks ? __ldcg(src + (int64_t)(k0 + u) * step) : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int u = 0; u < 8; ++u) t[u] = __ldcg(src + (int64_t)min(k0 + u, k_hi - 1) * step);
 #pragma unroll
-    for (int u = 0; u < 8; ++u) { s.x += t[u].x; s.y += t[u].y; s.z += t[u].z; s.w += t[u].w; }
+      for (int u = 0; u < 8; ++u)
+        if (k0 + u < k_hi) { s.x += t[u].x; s.y += t[u].y; s.z += t[u].z; s.w += t[u].w; }
+    }
+  }
+  quarter[grp][lane] = s;
+  __syncthreads();
+  if (blockIdx.y == 0 && threadIdx.x == 0 && a.counts)
+    a.counts[c] = (float)(cnt_red[0] + cnt_red[1] + cnt_red[2] + cnt_red[3]);
+  if (grp != 0 || v >= nvec) return;
+#pragma unroll
+  for (int g = 1; g < 4; ++g) {
+    const float4 t = quarter[g][lane];
+    s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
   }
   if (a.w_lbl && a.label_axis == LATTE_LABEL_AXIS_QUIRK) {
     const float4 w = __ldg(reinterpret_cast<const float4*>(a.w_lbl) + v);
@@ -543,12 +629,19 @@ __global__ void __launch_bounds__(128) cls_final_kernel(ClsArgs a) {
 
 inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
-struct ClsGeom { bool ok; int chunks; int64_t rows_per_chunk; size_t smem, part_bytes, cnt_bytes; };
-ClsGeom cls_geom(int64_t batch, int64_t dim, int64_t num_classes) {
+struct ClsGeom { bool ok; int chunks; int64_t rows_per_chunk; size_t smem, part_bytes, cnt_bytes; int slots; };
+ClsGeom cls_geom(int64_t batch, int64_t dim, int64_t num_classes, int esz = 4) {
   ClsGeom g{};
-  g.smem = (size_t)num_classes * (size_t)dim * 4 + (size_t)num_classes * 4;
-  g.ok = batch > 0 && dim % 4 == 0 && dim / 4 <= 256 && g.smem <= kClsSmemMax;
+  const size_t acc = ((size_t)num_classes * (size_t)dim * 4 + 127) / 128 * 128;
+  const size_t fixed = acc + (size_t)kClsIdRows * sizeof(ClsIds) + ((size_t)num_classes + 3) / 4 * 16 + 64;
+  const size_t row_bytes = (size_t)dim * esz;
+  const size_t grp = (size_t)kClsGrp * 2 * row_bytes + 16;          // one group of 4 row pairs + 2 mbarriers
+  g.ok = batch > 0 && dim % 8 == 0 && dim / 4 <= 256 && fixed + 2 * grp <= kClsSmemMax;
   if (!g.ok) return g;
+  size_t groups = (kClsSmemMax - fixed) / grp;
+  if (groups > 16) groups = 16;
+  g.slots = (int)groups;
+  g.smem = fixed + groups * grp;
   g.rows_per_chunk = (batch + kClsChunks - 1) / kClsChunks;
   if (g.rows_per_chunk < 16) g.rows_per_chunk = 16;
   g.chunks = (int)((batch + g.rows_per_chunk - 1) / g.rows_per_chunk);
@@ -559,11 +652,11 @@ ClsGeom cls_geom(int64_t batch, int64_t dim, int64_t num_classes) {
 
 // -> LATTE_OK when the streaming form ran, 1 when it does not apply (caller takes the sort path)
 int class_sums_stream(ClsArgs a, void* workspace, size_t workspace_bytes, cudaStream_t st) {
-  const ClsGeom g = cls_geom(a.batch, a.dim, a.num_classes);
   const int64_t esz = (int64_t)dtype_size(a.dtype);
-  const bool vec = g.ok && (a.ld_src % 4 == 0) && (a.ld_out % 4 == 0) && al16(a.out) &&
-                   (reinterpret_cast<uintptr_t>(a.src_ft) % (4 * esz) == 0) &&
-                   (reinterpret_cast<uintptr_t>(a.src_zs) % (4 * esz) == 0) &&
+  const ClsGeom g = cls_geom(a.batch, a.dim, a.num_classes, (int)esz);
+  // bulk copies want 16-byte aligned rows; the row outputs and the final step use 4-element vectors
+  const bool vec = g.ok && ((a.ld_src * esz) % 16 == 0) && (a.ld_out % 4 == 0) && al16(a.out) &&
+                   al16(a.src_ft) && al16(a.src_zs) &&
                    (!a.d_per_image || ((a.ld_dp % 4 == 0) &&
                                        (reinterpret_cast<uintptr_t>(a.d_per_image) % (4 * esz) == 0) &&
                                        (reinterpret_cast<uintptr_t>(a.d_per_group) % (4 * esz) == 0))) &&
@@ -578,11 +671,20 @@ int class_sums_stream(ClsArgs a, void* workspace, size_t workspace_bytes, cudaSt
   a.chunks = g.chunks;
   a.rows_per_chunk = g.rows_per_chunk;
   const int nvec = (int)(a.dim / 4);
-  const int threads = (nvec + 31) / 32 * 32;
-  if (g.smem > 48 * 1024)
-    LATTE_CUDA_OK(cudaFuncSetAttribute(cls_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
-  cls_stream_kernel<<<g.chunks, threads, g.smem, st>>>(a);
-  cls_final_kernel<<<dim3((unsigned)a.num_classes, (unsigned)((nvec + 127) / 128)), 128, 0, st>>>(a);
+  const int threads = (nvec + 31) / 32 * 32 + 32;        // consumers + the producer warp
+  const int row_bytes = (int)(a.dim * esz);
+  auto launch = [&](auto kernel) -> int {
+    if (g.smem > 48 * 1024)
+      LATTE_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
+    kernel<<<g.chunks, threads, g.smem, st>>>(a, g.slots, row_bytes);
+    return LATTE_OK;
+  };
+  int lrc;
+  if (a.dtype == LATTE_F32) lrc = launch(cls_stream_kernel<LATTE_F32>);
+  else if (a.dtype == LATTE_BF16) lrc = launch(cls_stream_kernel<LATTE_BF16>);
+  else lrc = launch(cls_stream_kernel<LATTE_F16>);
+  if (lrc) return lrc;
+  cls_final_kernel<<<dim3((unsigned)a.num_classes, (unsigned)((nvec + 31) / 32)), 128, 0, st>>>(a);
   if (cudaGetLastError() != cudaSuccess) return LATTE_ERR_CUDA;
   return LATTE_OK;
 }
@@ -661,7 +763,7 @@ extern "C" int latte_seg_workspace_bytes(int64_t batch, int64_t dim, int64_t num
   LATTE_CHECK_ARG(bytes && batch >= 0 && dim > 0 && num_classes > 0);
   const SegWs w = seg_ws(batch, dim, num_classes);
   *bytes = w.int_bytes + w.part_bytes + 256;
-  const ClsGeom g = cls_geom(batch, dim, num_classes);      // streaming form: chunk partials
+  const ClsGeom g = cls_geom(batch, dim, num_classes, 2);   // streaming form: chunk partials
   if (g.ok && g.part_bytes + g.cnt_bytes + 256 > *bytes) *bytes = g.part_bytes + g.cnt_bytes + 256;
   return LATTE_OK;
 }
@@ -703,7 +805,10 @@ extern "C" int latte_mix_ema_fwd(const void* class_text, int64_t ld_ct, const vo
           (reinterpret_cast<uintptr_t>(per_image) % vb == 0) &&
           (reinterpret_cast<uintptr_t>(per_group) % vb == 0) &&
           (reinterpret_cast<uintptr_t>(t_ft) % vb == 0) && (reinterpret_cast<uintptr_t>(t_zs) % vb == 0);
-  mix_ema_fwd_kernel<<<(unsigned)batch, 128, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  cudaStream_t mst = static_cast<cudaStream_t>(stream);
+  if (dtype == LATTE_F32) mix_ema_fwd_kernel<LATTE_F32><<<(unsigned)batch, 128, 0, mst>>>(a);
+  else if (dtype == LATTE_BF16) mix_ema_fwd_kernel<LATTE_BF16><<<(unsigned)batch, 128, 0, mst>>>(a);
+  else mix_ema_fwd_kernel<LATTE_F16><<<(unsigned)batch, 128, 0, mst>>>(a);
   LATTE_LAUNCH_OK();
   return LATTE_OK;
 }

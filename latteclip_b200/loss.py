@@ -580,11 +580,13 @@ class ClipLoss(nn.Module):
 
 def create_loss(args):
     """The reference factory (factory.py:323-351): SigLipLoss on ``args.siglip`` (:337-342), else
-    ClipLoss (:344-351).  CoCa / distillation losses are outside the accelerated path."""
-    if "coca" in getattr(args, "model", "").lower() or getattr(args, "distill", False):
+    ClipLoss (:344-351).  CoCaLoss is outside the accelerated path."""
+    if "coca" in getattr(args, "model", "").lower():
         raise NotImplementedError(
             "latteclip_b200.create_loss provides ClipLoss and SigLipLoss; use the reference factory "
-            "for CoCa / distillation losses")
+            "for CoCaLoss (it wraps a ClipLoss, loss.py:309, which can be this one)")
+    # (the reference factory has no distillation branch: args.distill still gets a ClipLoss here;
+    #  latteclip_b200.DistillClipLoss is constructed directly, like open_clip.loss.DistillClipLoss)
     if getattr(args, "siglip", False):
         assert not args.horovod, "Horovod not currently supported for SigLip"
         from .siglip import SigLipLoss

@@ -33,9 +33,18 @@ def stack_bank(memory_bank, class_names: Iterable[str]) -> torch.Tensor:
     return torch.stack([memory_bank[c].detach() for c in class_names]).to(torch.float32).contiguous()
 
 
-def unstack_bank(bank: torch.Tensor, memory_bank, class_names: Iterable[str], touched=None):
+def unstack_bank(bank: torch.Tensor, memory_bank, class_names: Iterable[str], touched=None,
+                 inplace: bool = False):
     """Write rows of the stacked bank back into the ParameterDict (train.py:529-530 assigns a
-    new tensor per touched class).  ``touched``: optional bool/float [C] mask (counts > 0)."""
+    new tensor per touched class).  ``touched``: optional bool/float [C] mask (counts > 0); reading
+    it costs a device-to-host sync.  ``inplace=True`` copies EVERY row into the existing Parameters
+    with one foreach copy instead (no sync, no allocation): rows of untouched classes are
+    bit-identical in the stacked bank, so the stored values are the same as the reference's."""
+    if inplace:
+        names = list(class_names)
+        dst = [memory_bank[c].data for c in names]
+        torch._foreach_copy_(dst, [r.to(d.dtype) for r, d in zip(bank.unbind(0), dst)])
+        return memory_bank
     mask = None if touched is None else (touched > 0).tolist()
     for k, c in enumerate(class_names):
         if mask is None or mask[k]:
@@ -236,3 +245,110 @@ def prototype_step(image_features: torch.Tensor,
     losses.update(preds=preds, t_ft=t_ft, t_zs=t_zs, w_img=w_img, w_grp=w_grp,
                   w_lbl=w_lbl, w_lbl_zs=w_lbl_zs)
     return losses
+
+
+# ------------------------------------------------------------------------------ CUDA-graph step
+class _ReplayStep(torch.autograd.Function):
+    """Forward = one replay of the captured prototype_step + backward (+ bank update); backward hands
+    out the gradients that replay left in the static buffers, scaled by the incoming gradient."""
+
+    @staticmethod
+    def forward(ctx, runner, image_features, logit_scale, class_text, per_image, per_group):
+        runner._replay(image_features, logit_scale, class_text, per_image, per_group)
+        ctx.runner = runner
+        ctx.serial = runner.serial
+        st = runner.static_out
+        return st["loss"].detach().clone(), st["contrastive_loss"].detach().clone(), st["zeroshot"].detach().clone()
+
+    @staticmethod
+    def backward(ctx, g_loss, _g_c, _g_z):
+        r = ctx.runner
+        if ctx.serial != r.serial:
+            raise RuntimeError("GraphedPrototypeStep: backward after a later step replaced the static gradients")
+        return (None,) + tuple(g_loss * leaf.grad for leaf in r.leaves)
+
+
+class GraphedPrototypeStep:
+    """``prototype_step`` + ``loss.backward()`` (+ ``update_bank``) captured ONCE in a CUDA graph and
+    replayed per step: at the reference's fine-tuning shape (batch 512, 47 classes) the step is
+    ~40 short kernels and its cost is launch gaps, not arithmetic.
+
+        step = GraphedPrototypeStep(loss_fn, alpha=args.alpha, label_weight_axis="quirk")
+        out = step(image_features, logit_scale, bank, proto_snapshot, zs, class_text, per_image, per_group)
+        out["loss"].backward()          # hands the gradients computed by the replay to the towers
+
+    The replay already ran the loss head's backward (with upstream gradient 1); the returned
+    ``out["loss"]`` is connected to the five differentiable inputs through an autograd node that
+    scales those gradients by whatever arrives (a GradScaler factor, a loss weight).  ``bank`` and
+    ``proto_snapshot`` are baked into the graph by address (the bank is updated in place, as
+    ``update_bank`` does); new shapes, dtypes or tensors re-capture.  Single-process ClipLoss only
+    (collectives are not captured)."""
+
+    def __init__(self, loss_fn, alpha: float = 0.01, use_image_caption: float = 1.0,
+                 use_batch_caption: float = 1.0, use_template_caption: float = 1.0,
+                 use_zeroshot_pseudolabel: float = 1.0, use_finetune_pseudolabel: float = 1.0,
+                 label_weight_axis: str = "row", with_bank_update: bool = True):
+        if getattr(loss_fn, "world_size", 1) > 1:
+            raise NotImplementedError("GraphedPrototypeStep: world_size > 1 is not captured")
+        self.loss_fn = loss_fn
+        self.kw = dict(alpha=alpha, use_image_caption=use_image_caption, use_batch_caption=use_batch_caption,
+                       use_template_caption=use_template_caption,
+                       use_zeroshot_pseudolabel=use_zeroshot_pseudolabel,
+                       use_finetune_pseudolabel=use_finetune_pseudolabel, label_weight_axis=label_weight_axis)
+        self.with_bank_update = with_bank_update
+        self.key = None
+        self.graph = None
+        self.serial = 0
+
+    def _eager(self):
+        for x in self.leaves:
+            x.grad = None
+        out = prototype_step(self.leaves[0], self.leaves[1], self.bank, self.snapshot, self.s_zs,
+                             self.leaves[2], self.leaves[3], self.leaves[4], self.loss_fn, **self.kw)
+        out["loss"].backward()
+        if self.with_bank_update:
+            update_bank(self.bank, out["preds"], self.s_zs, out["t_ft"].detach(), out["t_zs"].detach())
+        return out
+
+    def _capture(self, image_features, logit_scale, bank, proto_snapshot, zs, class_text, per_image, per_group):
+        def leaf(x):
+            return x.detach().clone().requires_grad_(True)
+        self.leaves = [leaf(image_features), leaf(logit_scale), leaf(class_text), leaf(per_image), leaf(per_group)]
+        self.s_zs = zs.detach().clone()
+        self.bank, self.snapshot = bank, proto_snapshot
+        keep = bank.detach().clone()
+        side = torch.cuda.Stream(device=bank.device)
+        side.wait_stream(torch.cuda.current_stream(bank.device))
+        with torch.cuda.stream(side):
+            for _ in range(3):                       # warm-up: workspaces, lazy module state
+                self._eager()
+        torch.cuda.current_stream(bank.device).wait_stream(side)
+        bank.copy_(keep)                             # the warm-up steps must not move the bank
+        for x in self.leaves:
+            x.grad = None
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.static_out = self._eager()
+        bank.copy_(keep)                             # (capture does not execute, but keep it explicit)
+
+    def _replay(self, image_features, logit_scale, class_text, per_image, per_group):
+        with torch.no_grad():
+            for dst, src in zip(self.leaves, (image_features, logit_scale, class_text, per_image, per_group)):
+                dst.copy_(src)
+        self.graph.replay()
+        self.serial += 1
+
+    def __call__(self, image_features, logit_scale, bank, proto_snapshot, zs, class_text, per_image, per_group):
+        key = (tuple(image_features.shape), image_features.dtype, tuple(class_text.shape), class_text.dtype,
+               per_image.dtype, per_group.dtype, logit_scale.dtype, tuple(logit_scale.shape), bank.data_ptr(),
+               proto_snapshot.data_ptr(), proto_snapshot._version, tuple(zs.shape))
+        if key != self.key:
+            self._capture(image_features, logit_scale, bank, proto_snapshot, zs, class_text, per_image, per_group)
+            self.key = key
+        self.s_zs.copy_(zs)
+        loss, contrastive, zeroshot = _ReplayStep.apply(self, image_features, logit_scale, class_text,
+                                                        per_image, per_group)
+        st = self.static_out
+        return {"loss": loss, "contrastive_loss": contrastive, "zeroshot": zeroshot, "preds": st["preds"],
+                "t_ft": st["t_ft"].detach(), "t_zs": st["t_zs"].detach(), "w_img": st["w_img"],
+                "w_grp": st["w_grp"], "w_lbl": st["w_lbl"], "w_lbl_zs": st["w_lbl_zs"]}

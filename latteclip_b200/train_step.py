@@ -132,9 +132,9 @@ def latteclip_step(model, batch, loss: Callable, args, class_names: Sequence[str
     if do_backward:
         backward(out["loss"], scaler)                                          # :506
         sync_gradients(inner.parameters(), world, group)
-    _, counts = P.update_bank(bank, out["preds"], zs, out["t_ft"].detach(), out["t_zs"].detach(),
+    P.update_bank(bank, out["preds"], zs, out["t_ft"].detach(), out["t_zs"].detach(),
                               group=group, world_size=world)                   # :508-530
-    P.unstack_bank(bank, inner.memory_bank, class_names, touched=counts)
+    P.unstack_bank(bank, inner.memory_bank, class_names, inplace=True)     # no host sync
     out["zs"] = zs
     return out
 

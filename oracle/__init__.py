@@ -34,3 +34,5 @@ from .prototypes import (  # noqa: F401
 )
 from . import zero_shot  # noqa: F401,E402
 from . import siglip  # noqa: F401,E402
+from . import distill  # noqa: F401,E402
+from . import accum  # noqa: F401,E402

@@ -28,6 +28,8 @@ What is executed is the reference's own code, imported from /root/reference/src
   * the ``--accum-freq`` feature-cache pattern of upstream open_clip (present in the reference at
     train.py:972-1024 behind ``raise NotImplemented()``) driven with the reference's ``ClipLoss``
       -> clip_accum.npz
+  * ``open_clip.loss.DistillClipLoss`` forward + backward (loss.py:324-362), world size 1
+      -> distill.npz
 
 The fixtures hold both the inputs and the reference outputs, so tests never need the
 reference at run time (it does not exist on the GPU box).
@@ -448,6 +450,40 @@ def _accum_dist_worker(rank, world, port, i_all, t_all, k, m, scale, ret):
     dist.destroy_process_group()
 
 
+# ----------------------------------------------------------------------------------
+# 8. DistillClipLoss (loss.py:324-362)
+# ----------------------------------------------------------------------------------
+def gen_distill(open_clip):
+    from open_clip.loss import DistillClipLoss
+    out = {}
+    for name, n, d, sig_s, sig_t, s_s, s_t in (("n96_d64", 96, 64, 3.0, 1.5, 30.0, 100.0),
+                                                ("n200_d128", 200, 128, 5.0, 2.0, 1.0 / 0.07, 50.0),
+                                                ("n64_d32_close", 64, 32, 2.0, 2.0, 40.0, 40.0)):
+        i_s, t_s = synth_pairs(n, d, sig_s, 5000 + n, torch.float64)
+        if name.endswith("close"):        # a student close to its teacher: the gradient is a small difference
+            g = torch.Generator().manual_seed(77)
+            i_t = F.normalize(i_s + 0.02 * torch.randn(n, d, generator=g, dtype=torch.float64), dim=1)
+            t_t = F.normalize(t_s + 0.02 * torch.randn(n, d, generator=g, dtype=torch.float64), dim=1)
+        else:
+            i_t, t_t = synth_pairs(n, d, sig_t, 6000 + n, torch.float64)
+        out[f"{name}_I"], out[f"{name}_T"] = i_s.numpy(), t_s.numpy()
+        out[f"{name}_It"], out[f"{name}_Tt"] = i_t.numpy(), t_t.numpy()
+        out[f"{name}_scales"] = np.array([s_s, s_t], dtype=np.float64)
+        for tag, dt in (("f64", torch.float64), ("f32", torch.float32)):
+            il = i_s.to(dt).clone().requires_grad_(True)
+            tl = t_s.to(dt).clone().requires_grad_(True)
+            s = torch.tensor(s_s, dtype=dt, requires_grad=True)
+            mod = DistillClipLoss(local_loss=True, gather_with_grad=True, cache_labels=True)
+            res = mod(il, tl, s, i_t.to(dt), t_t.to(dt), torch.tensor(s_t, dtype=dt), output_dict=True)
+            assert res["contrastive_loss"] == 0
+            res["distill_loss"].backward()
+            out[f"{name}_loss_{tag}"] = res["distill_loss"].detach().numpy()
+            out[f"{name}_dI_{tag}"], out[f"{name}_dT_{tag}"] = il.grad.numpy(), tl.grad.numpy()
+            out[f"{name}_ds_{tag}"] = s.grad.numpy()
+        print("distill", name, float(out[f"{name}_loss_f64"]))
+    np.savez_compressed(os.path.join(HERE, "distill.npz"), **out)
+
+
 def gen_siglip(open_clip):
     import torch.multiprocessing as mp
     out = {}
@@ -490,6 +526,7 @@ def main():
     gen_siglip(open_clip)
     gen_clip_dist()
     gen_clip_accum(open_clip)
+    gen_distill(open_clip)
 
 
 if __name__ == "__main__":

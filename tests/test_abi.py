@@ -109,6 +109,11 @@ def test_factory_and_module_contracts_on_cpu():
     assert len(list(sig.parameters())) == 0
     with pytest.raises(NotImplementedError):
         lb.create_loss(SimpleNamespace(**dict(base, model="coca_ViT-B-32")))
+    # the reference factory has no distillation branch: args.distill still yields a ClipLoss
+    assert type(lb.create_loss(SimpleNamespace(**dict(base, distill=True)))) is lb.ClipLoss
+    assert issubclass(lb.DistillClipLoss, lb.ClipLoss)
+    with pytest.raises(NotImplementedError):
+        lb.DistillClipLoss(rank=0, world_size=2)(x16 := torch.zeros(8, 16), x16, 1.0, x16, x16, 1.0)
     with pytest.raises(AssertionError):
         lb.create_loss(SimpleNamespace(**dict(base, siglip=True, horovod=True)))
     with pytest.raises(AssertionError):

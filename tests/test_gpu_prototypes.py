@@ -488,3 +488,54 @@ def test_step_similarities_one_launch_equals_per_product_kernels():
         assert float((preds != ref_preds).float().mean()) < 2e-3
         for got, x in ((m_i, pi), (m_g, pg), (m_c, ct)):
             assert torch.allclose(got, P.text_margins(x, snap), rtol=0, atol=3e-7)
+
+
+def test_graphed_prototype_step_equals_eager_step():
+    """prototypes.GraphedPrototypeStep (one CUDA-graph replay per step, gradients handed to autograd)
+    against the eager prototype_step + backward + update_bank on the same data, over three steps with
+    a moving bank; upstream gradient 2.5 (as a GradScaler would send) on the last one."""
+    import latteclip_b200 as lb
+    from latteclip_b200 import prototypes as P
+    dev = torch.device("cuda:0")
+    b = d = 256
+    c = 23
+    g = torch.Generator().manual_seed(41)
+    bank0 = F.normalize(torch.randn(c, d, generator=g), dim=1)
+    cls = F.normalize(bank0 + 0.3 * torch.randn(c, d, generator=g), dim=1)
+
+    def batch():
+        true = torch.randint(0, c, (b,), generator=g)
+        mk = lambda s: F.normalize(bank0[true] + s * torch.randn(b, d, generator=g) * 3 / d ** 0.5, dim=1)  # noqa: E731
+        return dict(img=mk(1.2), pimg=mk(0.9), pgrp=mk(0.7), zs=torch.randint(0, c, (b,), generator=g))
+
+    loss_fn = lb.ClipLoss(local_loss=True, gather_with_grad=True, cache_labels=True)
+    graphed = P.GraphedPrototypeStep(loss_fn, alpha=0.01, label_weight_axis="quirk")
+    bank_g, bank_e = bank0.to(dev).clone(), bank0.to(dev).clone()
+    snap = bank0.to(dev).clone()
+    for it in range(3):
+        data = batch()
+        up = 2.5 if it == 2 else 1.0
+        res = {}
+        for tag, bank in (("graph", bank_g), ("eager", bank_e)):
+            leaves = {k: data[k].to(dev).bfloat16().requires_grad_(True) for k in ("img", "pimg", "pgrp")}
+            ct = cls.to(dev).bfloat16().requires_grad_(True)
+            log_s = torch.tensor(math.log(100.0), device=dev, requires_grad=True)
+            zs = data["zs"].to(dev)
+            if tag == "graph":
+                out = graphed(leaves["img"], log_s.exp(), bank, snap, zs, ct, leaves["pimg"], leaves["pgrp"])
+                (out["loss"] * up).backward()
+            else:
+                out = P.prototype_step(leaves["img"], log_s.exp(), bank, snap, zs, ct, leaves["pimg"],
+                                       leaves["pgrp"], loss_fn, alpha=0.01, label_weight_axis="quirk")
+                (out["loss"] * up).backward()
+                P.update_bank(bank, out["preds"], zs, out["t_ft"].detach(), out["t_zs"].detach())
+            torch.cuda.synchronize()
+            res[tag] = dict(loss=float(out["loss"]), preds=out["preds"].clone(), ct=ct.grad.clone(),
+                            s=float(log_s.grad), **{k: v.grad.clone() for k, v in leaves.items()})
+        assert abs(res["graph"]["loss"] - res["eager"]["loss"]) < 1e-6 * abs(res["eager"]["loss"])
+        assert torch.equal(res["graph"]["preds"], res["eager"]["preds"])
+        for k in ("img", "pimg", "pgrp", "ct"):
+            assert torch.allclose(res["graph"][k].float(), res["eager"][k].float(), rtol=2.0 ** -6, atol=1e-9), k
+        assert abs(res["graph"]["s"] - res["eager"]["s"]) < 1e-4 * abs(res["eager"]["s"]) + 1e-9
+        assert torch.allclose(bank_g, bank_e, rtol=0, atol=1e-6)
+    assert graphed.graph is not None and graphed.serial == 3

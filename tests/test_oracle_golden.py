@@ -188,3 +188,22 @@ def test_siglip_ring_emulation_matches_gloo_reference(world):
         assert rel(di[r], g[f"w{world}_r{r}_dI"]) < 1e-10 and rel(dt_[r], g[f"w{world}_r{r}_dT"]) < 1e-10
         assert abs(float(ds[r]) - float(g[f"w{world}_r{r}_ds"])) <= 1e-10 * abs(float(ds[r]))
         assert abs(float(db[r]) - float(g[f"w{world}_r{r}_db"])) <= 1e-10 * abs(float(db[r]))
+
+
+@pytest.mark.parametrize("name", ["n96_d64", "n200_d128", "n64_d32_close"])
+def test_distill_oracle_matches_reference_class(name):
+    """oracle/distill.py against open_clip.loss.DistillClipLoss (tests/golden/distill.npz)."""
+    from oracle.distill import distill_clip_loss
+    g = load_golden("distill.npz")
+    s_s, s_t = (float(v) for v in g[f"{name}_scales"])
+    for tag, dt, tol in (("f64", torch.float64, 1e-12), ("f32", torch.float32, 5e-6)):
+        il = torch.from_numpy(g[f"{name}_I"]).to(dt).requires_grad_(True)
+        tl = torch.from_numpy(g[f"{name}_T"]).to(dt).requires_grad_(True)
+        s = torch.tensor(s_s, dtype=dt, requires_grad=True)
+        loss = distill_clip_loss(il, tl, s, torch.from_numpy(g[f"{name}_It"]).to(dt),
+                                 torch.from_numpy(g[f"{name}_Tt"]).to(dt), torch.tensor(s_t, dtype=dt))
+        loss.backward()
+        assert abs(float(loss) - float(g[f"{name}_loss_{tag}"])) <= tol * abs(float(g[f"{name}_loss_{tag}"]))
+        assert rel(il.grad, g[f"{name}_dI_{tag}"]) < max(tol, 1e-6) * 10
+        assert rel(tl.grad, g[f"{name}_dT_{tag}"]) < max(tol, 1e-6) * 10
+        assert abs(float(s.grad) - float(g[f"{name}_ds_{tag}"])) <= max(tol * 100, 1e-9) * max(abs(float(g[f"{name}_ds_{tag}"])), 1e-3)
