@@ -98,7 +98,8 @@ struct MixArgs {
   float alpha; int label_axis; int dtype;
   int64_t batch, dim;
   void* t_ft; void* t_zs; int64_t ld_out;
-  int vec;   // 1 when every pointer / stride allows 4-element vector access
+  int vec;
+  int64_t num_classes;   // 1 when every pointer / stride allows 4-element vector access
 };
 
 __device__ __forceinline__ float mix_one(float wl, float l, float p, float wi, float g, float wg,
@@ -113,7 +114,10 @@ __device__ __forceinline__ float mix_one(float wl, float l, float p, float wi, f
 template <int DT>
 __global__ void __launch_bounds__(128) mix_ema_fwd_kernel(MixArgs a) {
   const int64_t i = blockIdx.x;
-  const int64_t cp = a.preds[i], cz = a.zs[i];
+  // ids index the [C, D] tables: clamp them so that a bad id (a stale pickled feature record) cannot
+  // read out of bounds; the class sums drop such ids, the reference would raise KeyError
+  const int64_t cp = min(max(a.preds[i], (int64_t)0), a.num_classes - 1);
+  const int64_t cz = min(max(a.zs[i], (int64_t)0), a.num_classes - 1);
   const float wl_row = a.w_lbl[i], wi = a.w_img[i], wg = a.w_grp[i];
   const float tot = wl_row + wi + wg;              // train.py:472
   const float tot_zs = a.w_lbl_zs[i] + wi + wg;    // train.py:473
@@ -414,20 +418,21 @@ struct ClsArgs {
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
-// 4 consecutive elements of a row staged in shared memory
-template <int DT> __device__ __forceinline__ float4 lds4(const uint8_t* row, int64_t col) {
-  if (DT == LATTE_F32) return *reinterpret_cast<const float4*>(row + col * 4);
-  const uint2 raw = *reinterpret_cast<const uint2*>(row + col * 2);
-  float4 o;
-  if (DT == LATTE_BF16) {
-    o.x = __uint_as_float(raw.x << 16); o.y = __uint_as_float(raw.x & 0xffff0000u);
-    o.z = __uint_as_float(raw.y << 16); o.w = __uint_as_float(raw.y & 0xffff0000u);
+// 2 consecutive elements of a row staged in shared memory / of a global row
+template <int DT> __device__ __forceinline__ float2 lds2(const uint8_t* row, int col) {
+  if (DT == LATTE_F32) return *reinterpret_cast<const float2*>(row + col * 4);
+  const uint32_t raw = *reinterpret_cast<const uint32_t*>(row + col * 2);
+  if (DT == LATTE_BF16) return make_float2(__uint_as_float(raw << 16), __uint_as_float(raw & 0xffff0000u));
+  return __half22float2(*reinterpret_cast<const __half2*>(&raw));
+}
+template <int DT> __device__ __forceinline__ void st2(void* base, int64_t idx, float2 v) {
+  if (DT == LATTE_F32) {
+    *reinterpret_cast<float2*>(static_cast<float*>(base) + idx) = v;
+  } else if (DT == LATTE_BF16) {
+    *reinterpret_cast<__nv_bfloat162*>(static_cast<__nv_bfloat16*>(base) + idx) = __floats2bfloat162_rn(v.x, v.y);
   } else {
-    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&raw.x));
-    const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
-    o.x = a.x; o.y = a.y; o.z = b.x; o.w = b.y;
+    *reinterpret_cast<__half2*>(static_cast<__half*>(base) + idx) = __floats2half2_rn(v.x, v.y);
   }
-  return o;
 }
 
 // Shared memory of cls_stream_kernel: [C, D] fp32 accumulator | ring of `groups` x 4 row pairs (the zs
@@ -439,12 +444,12 @@ constexpr int kClsGrp = 4;
 struct __align__(16) ClsIds { int p, z; float wl, wlz, wi, wg, pad0, pad1; };
 
 template <int DT>
-__global__ void __launch_bounds__(288) cls_stream_kernel(ClsArgs a, int groups, int row_bytes) {
+__global__ void __launch_bounds__(544) cls_stream_kernel(ClsArgs a, int groups, int row_bytes) {
   extern __shared__ __align__(128) uint8_t cls_smem[];
   using namespace ptx;
-  const int nvec = (int)(a.dim / 4);
-  const size_t acc_bytes = ((size_t)a.num_classes * nvec * 16 + 127) / 128 * 128;
-  float4* acc = reinterpret_cast<float4*>(cls_smem);                                        // [C][nvec]
+  const int nv2 = (int)(a.dim / 2);                        // a consumer thread owns 2 columns
+  const size_t acc_bytes = ((size_t)a.num_classes * a.dim * 4 + 127) / 128 * 128;
+  float2* acc = reinterpret_cast<float2*>(cls_smem);                                        // [C][dim / 2]
   uint8_t* ring = cls_smem + acc_bytes;                                    // [groups][4][2][row_bytes]
   const int grp_bytes = kClsGrp * 2 * row_bytes;
   ClsIds* ids = reinterpret_cast<ClsIds*>(ring + (size_t)groups * grp_bytes);               // [256]
@@ -459,7 +464,7 @@ __global__ void __launch_bounds__(288) cls_stream_kernel(ClsArgs a, int groups, 
   const int rows = (int)(r1 - r0);
   const int ngrp = (rows + kClsGrp - 1) / kClsGrp;
 
-  for (int k = threadIdx.x; k < a.num_classes * nvec; k += blockDim.x) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int k = threadIdx.x; k < a.num_classes * nv2; k += blockDim.x) acc[k] = make_float2(0.f, 0.f);
   for (int k = threadIdx.x; k < a.num_classes; k += blockDim.x) cnt[k] = 0;
   if (threadIdx.x == 0) {
     for (int s = 0; s < groups; ++s) {
@@ -484,10 +489,17 @@ __global__ void __launch_bounds__(288) cls_stream_kernel(ClsArgs a, int groups, 
         const uint32_t dst = smem_u32(ring + (size_t)s * grp_bytes);
         const uint32_t bar = bar_full + 8 * s;
         mbar_arrive_expect_tx(bar, (uint32_t)(n * 2 * row_bytes));
-        for (int u = 0; u < n; ++u) {
-          const int64_t off = (r0 + gk * kClsGrp + u) * pitch;
-          bulk_load_1d(dst + (2 * u) * row_bytes, sz + off, (uint32_t)row_bytes, bar, pol);
-          bulk_load_1d(dst + (2 * u + 1) * row_bytes, sf + off, (uint32_t)row_bytes, bar, pol);
+        const int64_t off = (r0 + gk * kClsGrp) * pitch;
+        if (pitch == row_bytes) {
+          // contiguous rows: one copy per list for the whole group (the issue rate of bulk copies,
+          // not their bytes, bounds a single producer thread)
+          bulk_load_1d(dst, sz + off, (uint32_t)(n * row_bytes), bar, pol);
+          bulk_load_1d(dst + kClsGrp * row_bytes, sf + off, (uint32_t)(n * row_bytes), bar, pol);
+        } else {
+          for (int u = 0; u < n; ++u) {
+            bulk_load_1d(dst + u * row_bytes, sz + off + u * pitch, (uint32_t)row_bytes, bar, pol);
+            bulk_load_1d(dst + (kClsGrp + u) * row_bytes, sf + off + u * pitch, (uint32_t)row_bytes, bar, pol);
+          }
         }
         if (++s == groups) { s = 0; phase ^= 1; }
       }
@@ -495,11 +507,13 @@ __global__ void __launch_bounds__(288) cls_stream_kernel(ClsArgs a, int groups, 
     return;
   }
 
-  // ------------------------------------------------------------ consumers: thread -> 4 columns
-  const bool col_ok = (int)threadIdx.x < nvec;
-  const int d = col_ok ? (int)threadIdx.x * 4 : 0;            // idle lanes re-read column 0
+  // ------------------------------------------------------------ consumers: thread -> 2 columns
+  // (the adds of one accumulator element form a dependent chain through shared memory; 8-16 warps
+  //  with 2 columns per thread hide it, 4 warps with 4 columns did not)
+  const bool col_ok = (int)threadIdx.x < nv2;
+  const int d = col_ok ? (int)threadIdx.x * 2 : 0;            // idle lanes re-read column 0
   const bool quirk = a.w_lbl && a.label_axis == LATTE_LABEL_AXIS_QUIRK;
-  float4* my_acc = acc + threadIdx.x;
+  float2* my_acc = acc + threadIdx.x;
   int s = 0;
   uint32_t phase = 0;
   for (int k0 = 0; k0 < rows; k0 += kClsIdRows) {
@@ -522,11 +536,11 @@ __global__ void __launch_bounds__(288) cls_stream_kernel(ClsArgs a, int groups, 
     for (int k = k0; k < kend; k += kClsGrp) {
       mbar_wait(bar_full + 8 * s, phase);
       const uint8_t* grp = ring + (size_t)s * grp_bytes;
-      float4 gz[kClsGrp], gf[kClsGrp];
+      float2 gz[kClsGrp], gf[kClsGrp];
 #pragma unroll
       for (int u = 0; u < kClsGrp; ++u) {                      // rows past the chunk: stale bytes, unused
-        gz[u] = lds4<DT>(grp + (2 * u) * row_bytes, d);
-        gf[u] = lds4<DT>(grp + (2 * u + 1) * row_bytes, d);
+        gz[u] = lds2<DT>(grp + u * row_bytes, d);                 // group layout: 4 zs rows, then 4 ft rows
+        gf[u] = lds2<DT>(grp + (kClsGrp + u) * row_bytes, d);
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_empty + 8 * s);            // this warp has its copy of the group
@@ -544,34 +558,30 @@ __global__ void __launch_bounds__(288) cls_stream_kernel(ClsArgs a, int groups, 
         }
         if (a.d_per_image) {
           const int64_t i = r0 + k + u;
-          float4 dm;
-          dm.x = gf[u].x * inv_ft + gz[u].x * inv_zs; dm.y = gf[u].y * inv_ft + gz[u].y * inv_zs;
-          dm.z = gf[u].z * inv_ft + gz[u].z * inv_zs; dm.w = gf[u].w * inv_ft + gz[u].w * inv_zs;
-          st4t<DT>(a.d_per_image, i * a.ld_dp + d, make_float4(q.wi * dm.x, q.wi * dm.y, q.wi * dm.z, q.wi * dm.w));
-          st4t<DT>(a.d_per_group, i * a.ld_dp + d, make_float4(q.wg * dm.x, q.wg * dm.y, q.wg * dm.z, q.wg * dm.w));
+          const float dx = gf[u].x * inv_ft + gz[u].x * inv_zs, dy = gf[u].y * inv_ft + gz[u].y * inv_zs;
+          st2<DT>(a.d_per_image, i * a.ld_dp + d, make_float2(q.wi * dx, q.wi * dy));
+          st2<DT>(a.d_per_group, i * a.ld_dp + d, make_float2(q.wg * dx, q.wg * dy));
         }
         if (q.z >= 0) {            // entry 2i: the zs-list row first (train.py:524)
           const float sc = inv_zs * wl;
-          float4* o = my_acc + q.z * nvec;
-          float4 t = *o;
+          float2* o = my_acc + q.z * nv2;
+          float2 t = *o;
           t.x = fmaf(gz[u].x, sc, t.x); t.y = fmaf(gz[u].y, sc, t.y);
-          t.z = fmaf(gz[u].z, sc, t.z); t.w = fmaf(gz[u].w, sc, t.w);
           *o = t;
         }
         if (q.p >= 0) {            // entry 2i + 1: the ft-list row (train.py:525)
           const float sc = inv_ft * wl;
-          float4* o = my_acc + q.p * nvec;
-          float4 t = *o;
+          float2* o = my_acc + q.p * nv2;
+          float2 t = *o;
           t.x = fmaf(gf[u].x, sc, t.x); t.y = fmaf(gf[u].y, sc, t.y);
-          t.z = fmaf(gf[u].z, sc, t.z); t.w = fmaf(gf[u].w, sc, t.w);
           *o = t;
         }
       }
     }
   }
   named_bar_sync(1, ncons);
-  float4* dst = reinterpret_cast<float4*>(a.partial) + (int64_t)blockIdx.x * a.num_classes * nvec;
-  for (int k = threadIdx.x; k < a.num_classes * nvec; k += ncons) dst[k] = acc[k];
+  float2* dst = reinterpret_cast<float2*>(a.partial) + (int64_t)blockIdx.x * a.num_classes * nv2;
+  for (int k = threadIdx.x; k < a.num_classes * nv2; k += ncons) dst[k] = acc[k];
   for (int k = threadIdx.x; k < a.num_classes; k += ncons)
     a.cnt_partial[(int64_t)blockIdx.x * a.num_classes + k] = cnt[k];
 }
@@ -636,7 +646,7 @@ ClsGeom cls_geom(int64_t batch, int64_t dim, int64_t num_classes, int esz = 4) {
   const size_t fixed = acc + (size_t)kClsIdRows * sizeof(ClsIds) + ((size_t)num_classes + 3) / 4 * 16 + 64;
   const size_t row_bytes = (size_t)dim * esz;
   const size_t grp = (size_t)kClsGrp * 2 * row_bytes + 16;          // one group of 4 row pairs + 2 mbarriers
-  g.ok = batch > 0 && dim % 8 == 0 && dim / 4 <= 256 && fixed + 2 * grp <= kClsSmemMax;
+  g.ok = batch > 0 && dim % 8 == 0 && dim / 2 <= 512 && fixed + 2 * grp <= kClsSmemMax;
   if (!g.ok) return g;
   size_t groups = (kClsSmemMax - fixed) / grp;
   if (groups > 16) groups = 16;
@@ -671,7 +681,7 @@ int class_sums_stream(ClsArgs a, void* workspace, size_t workspace_bytes, cudaSt
   a.chunks = g.chunks;
   a.rows_per_chunk = g.rows_per_chunk;
   const int nvec = (int)(a.dim / 4);
-  const int threads = (nvec + 31) / 32 * 32 + 32;        // consumers + the producer warp
+  const int threads = (int)((a.dim / 2 + 31) / 32 * 32) + 32;      // consumers (2 columns each) + the producer warp
   const int row_bytes = (int)(a.dim * esz);
   auto launch = [&](auto kernel) -> int {
     if (g.smem > 48 * 1024)
@@ -796,7 +806,7 @@ extern "C" int latte_mix_ema_fwd(const void* class_text, int64_t ld_ct, const vo
   if (batch == 0) return LATTE_OK;
   MixArgs a{class_text, ld_ct, per_image, ld_pi, per_group, ld_pg, bank, ld_bank, preds, zs,
             w_lbl, w_lbl_zs, w_img, w_grp, alpha, label_axis, dtype, batch, dim, t_ft, t_zs,
-            ld_out, 0};
+            ld_out, 0, num_classes};
   const int64_t esz = (int64_t)dtype_size(dtype);
   const int64_t vb = 4 * esz;   // bytes per 4-element vector
   a.vec = (dim % 4 == 0) && (ld_ct % 4 == 0) && (ld_pi % 4 == 0) && (ld_pg % 4 == 0) &&

@@ -494,6 +494,16 @@ class _FusedClipLoss(torch.autograd.Function):
 
 
 class ClipLoss(nn.Module):
+    """Same constructor, methods and call as the reference's ``ClipLoss`` (loss.py:66-130).
+
+    Notes beyond the reference: (1) scratch -- the backward keeps the fp16 gradient weights
+    ``G [n, N]`` (n * N * 2 bytes per rank: 2 GiB at N = 32768 on one GPU) in ONE growable buffer per
+    device and stream (``latteclip_b200.clear_workspace_cache()`` releases it); the logits themselves are
+    never stored.  (2) feature gradients are not bit-reproducible from run to run (fp32 ``red.add`` of
+    the stream-K partial tiles in arrival order: last-bit differences); the loss is.  (3) multi-rank
+    ``local_loss``: ``logit_scale.grad`` is this rank's partition (own rows x all columns) of the global
+    sum -- all-reduce it, as DDP does for the parameter, to match the reference.  (4)
+    ``normalize_features=True`` (extension, default off) fuses ``F.normalize`` of both inputs."""
 
     def __init__(
             self,

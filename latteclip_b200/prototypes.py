@@ -223,7 +223,13 @@ def prototype_step(image_features: torch.Tensor,
     (the reference re-encodes it per sample, train.py:433-438; the values are identical).
     Returns the loss dict of the reference (keys ``contrastive_loss``, ``zeroshot``, ``loss``,
     train.py:491-504) plus ``preds``, ``t_ft``, ``t_zs`` and the weights.  Call
-    ``out["loss"].backward()`` and then ``update_bank`` (train.py:506-530)."""
+    ``out["loss"].backward()`` and then ``update_bank`` (train.py:506-530).
+
+    Feature dtype: ``t_ft`` / ``t_zs`` come back in the dtype of ``per_image``.  In the reference's amp
+    flow the text features are fp32 (``F.normalize`` runs in fp32 under autocast, model.py:420-437), so
+    T and the bank update stay fp32 and only the ClipLoss operands are rounded to the autocast dtype
+    (inside ``latte_prep_features``).  Feeding 16-bit features (as the benchmarks do) rounds T -- and
+    the EMA step of ~alpha -- to that dtype: about 6e-4 relative on the updated bank rows."""
     # pseudo-labels against the normalised bank (:384-389, :410-411) and the margins against the
     # epoch-start snapshot (:347-350), weights detached (:444-449): one stacked launch
     preds, m_img, m_grp, cls_margin = step_similarities(image_features, bank, proto_snapshot, per_image,

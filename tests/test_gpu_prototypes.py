@@ -534,8 +534,10 @@ def test_graphed_prototype_step_equals_eager_step():
                             s=float(log_s.grad), **{k: v.grad.clone() for k, v in leaves.items()})
         assert abs(res["graph"]["loss"] - res["eager"]["loss"]) < 1e-6 * abs(res["eager"]["loss"])
         assert torch.equal(res["graph"]["preds"], res["eager"]["preds"])
+        # bf16 gradients: the two ClipLoss contributions are added and (last step) scaled in bf16, in a
+        # different order than autograd's accumulation -- one or two bf16 ulps per entry
         for k in ("img", "pimg", "pgrp", "ct"):
-            assert torch.allclose(res["graph"][k].float(), res["eager"][k].float(), rtol=2.0 ** -6, atol=1e-9), k
+            assert rel(res["graph"][k], res["eager"][k]) < 4e-3, k
         assert abs(res["graph"]["s"] - res["eager"]["s"]) < 1e-4 * abs(res["eager"]["s"]) + 1e-9
         assert torch.allclose(bank_g, bank_e, rtol=0, atol=1e-6)
     assert graphed.graph is not None and graphed.serial == 3
