@@ -427,9 +427,14 @@ def test_prototype_step_and_backward_capture_in_a_cuda_graph():
         assert torch.equal(got["loss"], want_loss)
         assert torch.equal(got["bank"], static["bank"])
         # gradients: tiles that the stream-K GEMM splits over more than two clusters are summed with
-        # red.global.add in arrival order, so the last fp32 bit (one bf16 ulp after rounding) may differ
+        # red.global.add in arrival order, so the last fp32 bit (one bf16 ulp after rounding) of each
+        # ClipLoss gradient may differ; a leaf that receives two such gradients (autograd adds them in
+        # bf16) can cancel, so the bound is one bf16 ulp of the tensor's largest entry per element and
+        # 2^-8 of the norm overall, not a per-element relative error
         for k in leaves:
-            assert torch.allclose(got[k].float(), leaves[k].grad.float(), rtol=2.0 ** -7, atol=1e-9), k
+            a, b = got[k].float(), leaves[k].grad.float()
+            assert float((a - b).abs().max()) <= 2.0 ** -7 * float(b.abs().max()), k
+            assert float((a - b).norm()) <= 2.0 ** -8 * float(b.norm()), k
         assert torch.allclose(got["s"], log_s.grad, rtol=1e-5)
 
 
