@@ -26,7 +26,8 @@ using namespace ptx;
 
 namespace {
 
-constexpr int kRows = 128;                     // rows per block (MMA M)
+constexpr int kRows = 128;                     // rows per tile (MMA M)
+constexpr int kGrpRows = 32;                   // rows per work unit = rows of one TMA box
 constexpr int kBK = 64;                        // features per chunk (128 bytes of bf16)
 constexpr int kMaxCls = 64;                    // classes per job (MMA N), padded to 16
 constexpr int kPlaneBytes = kRows * kBK * 2;   // 16 KB: one bf16 plane of one chunk
@@ -50,8 +51,8 @@ constexpr int kDirThreads = 6 * 32;
 
 struct StreamJob {
   int64_t n;                 // rows
-  int blocks;                // ceil(n / 128)
-  int block0;                // first global block index of this job
+  int groups;                // ceil(n / 32): the work unit is one 32-row group (one TMA box)
+  int group0;                // first global group index of this job
   int kch;                   // ceil(dim / 64)
   int cp;                    // classes padded to a multiple of 16 (<= 64)
   int num_classes;
@@ -63,17 +64,38 @@ struct StreamJob {
 struct StreamParams {
   StreamJob job[kMaxJobs];
   int njobs;
-  int total_blocks;
+  int total_groups;
 };
 struct StreamMaps {
-  CUtensorMap x[kMaxJobs];   // raw rows (fp32: box 32 x 128; 16-bit: box 64 x 128)
+  CUtensorMap x[kMaxJobs];   // raw rows, 32-row boxes (fp32: 32 features wide; 16-bit: 64 wide)
   CUtensorMap p[kMaxJobs];   // prototype planes [3 * cp rows, dim_pad] bf16, box 64 x cp
 };
 
-__device__ __forceinline__ int job_of_block(const StreamParams& p, int blk) {
-  int j = 0;
-  while (j + 1 < p.njobs && blk >= p.job[j + 1].block0) ++j;
-  return j;
+// Row tiles of one CTA.  The 32-row groups of all jobs form one flattened space that is dealt to the
+// CTAs in equal contiguous ranges (the persistent grid then finishes together: 128-row blocks dealt
+// round-robin left the last wave 73 % full at 32768 rows); a tile is up to four consecutive groups
+// of ONE job (MMA M = 128; rows past `ng` groups hold stale data and are masked by the epilogue).
+struct TileIter {
+  int g, g_end, j;           // next group, end of this CTA's range, job cursor
+  int job, ng;               // current tile: job, groups (1..4)
+  int32_t row0;              //               first row inside the job
+};
+__device__ __forceinline__ TileIter tile_iter(const StreamParams& p) {
+  TileIter t;
+  t.g = (int)((int64_t)blockIdx.x * p.total_groups / gridDim.x);
+  t.g_end = (int)((int64_t)(blockIdx.x + 1) * p.total_groups / gridDim.x);
+  t.j = 0; t.job = 0; t.ng = 0; t.row0 = 0;
+  return t;
+}
+__device__ __forceinline__ bool next_tile(const StreamParams& p, TileIter& t) {
+  if (t.g >= t.g_end) return false;
+  while (t.j + 1 < p.njobs && t.g >= p.job[t.j + 1].group0) ++t.j;
+  const int job_end = p.job[t.j].group0 + p.job[t.j].groups;
+  t.job = t.j;
+  t.row0 = (t.g - p.job[t.j].group0) * kGrpRows;
+  t.ng = min(kRows / kGrpRows, min(t.g_end, job_end) - t.g);
+  t.g += t.ng;
+  return true;
 }
 
 template <bool kConvert>
@@ -133,10 +155,10 @@ nxc_stream_kernel(const __grid_constant__ StreamMaps maps, const StreamParams p)
       const uint64_t keep_pol = policy_evict_last();      // prototype planes: re-read by every block
       int stage = 0;
       uint32_t phase = 0;
-      for (int blk = blockIdx.x; blk < p.total_blocks; blk += gridDim.x) {
-        const int j = job_of_block(p, blk);
+      constexpr uint32_t kGrpBytes = kGrpRows * 128;        // one box: 32 rows of 128 bytes
+      for (TileIter t = tile_iter(p); next_tile(p, t);) {
+        const int j = t.job;
         const StreamJob& jb = p.job[j];
-        const int32_t row0 = (blk - jb.block0) * kRows;
         const uint32_t p_tx = 3u * (uint32_t)jb.cp * (kBK * 2);
         for (int c = 0; c < jb.kch; ++c) {
           const uint32_t st = smem_base + stage * kStageBytes;
@@ -144,12 +166,16 @@ nxc_stream_kernel(const __grid_constant__ StreamMaps maps, const StreamParams p)
             mbar_wait(bar_raw_empty + 8 * stage, phase ^ 1);
             const uint32_t rf = bar_raw_full + 8 * stage;
             if (jb.raw_f32) {
-              mbar_arrive_expect_tx(rf, kRawBytes);
-              tma_load_2d_hint(st, &maps.x[j], rf, c * kBK, row0, stream_pol);
-              tma_load_2d_hint(st + kRawBytes / 2, &maps.x[j], rf, c * kBK + 32, row0, stream_pol);
+              mbar_arrive_expect_tx(rf, 2u * (uint32_t)t.ng * kGrpBytes);
+              for (int g = 0; g < t.ng; ++g) {
+                tma_load_2d_hint(st + g * kGrpBytes, &maps.x[j], rf, c * kBK, t.row0 + g * kGrpRows, stream_pol);
+                tma_load_2d_hint(st + kRawBytes / 2 + g * kGrpBytes, &maps.x[j], rf, c * kBK + 32,
+                                 t.row0 + g * kGrpRows, stream_pol);
+              }
             } else {
-              mbar_arrive_expect_tx(rf, kPlaneBytes);
-              tma_load_2d_hint(st, &maps.x[j], rf, c * kBK, row0, stream_pol);
+              mbar_arrive_expect_tx(rf, (uint32_t)t.ng * kGrpBytes);
+              for (int g = 0; g < t.ng; ++g)
+                tma_load_2d_hint(st + g * kGrpBytes, &maps.x[j], rf, c * kBK, t.row0 + g * kGrpRows, stream_pol);
             }
             mbar_wait(bar_op_empty + 8 * stage, phase ^ 1);
             const uint32_t pf = bar_p_full + 8 * stage;
@@ -160,8 +186,9 @@ nxc_stream_kernel(const __grid_constant__ StreamMaps maps, const StreamParams p)
           } else {
             mbar_wait(bar_op_empty + 8 * stage, phase ^ 1);
             const uint32_t of = bar_op_full + 8 * stage;
-            mbar_arrive_expect_tx(of, kPlaneBytes + p_tx);
-            tma_load_2d_hint(st, &maps.x[j], of, c * kBK, row0, stream_pol);
+            mbar_arrive_expect_tx(of, (uint32_t)t.ng * kGrpBytes + p_tx);
+            for (int g = 0; g < t.ng; ++g)
+              tma_load_2d_hint(st + g * kGrpBytes, &maps.x[j], of, c * kBK, t.row0 + g * kGrpRows, stream_pol);
             for (int b = 0; b < 3; ++b)
               tma_load_2d_hint(st + kOffP + b * (kMaxCls * kBK * 2), &maps.p[j], of, c * kBK, b * jb.cp,
                                keep_pol);
@@ -179,8 +206,8 @@ nxc_stream_kernel(const __grid_constant__ StreamMaps maps, const StreamParams p)
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int blk = blockIdx.x; blk < p.total_blocks; blk += gridDim.x, ++it) {
-        const StreamJob& jb = p.job[job_of_block(p, blk)];
+      for (TileIter t = tile_iter(p); next_tile(p, t); ++it) {
+        const StreamJob& jb = p.job[t.job];
         const int buf = it & 1;
         const uint32_t idesc = make_idesc_f16(kRows, jb.cp, 1u, 0, 0);
         mbar_wait(bar_tempty + 8 * buf, ((it >> 1) & 1) ^ 1);
@@ -215,10 +242,10 @@ nxc_stream_kernel(const __grid_constant__ StreamMaps maps, const StreamParams p)
     const int q = warp & 3;                               // TMEM lane quarter of this warp
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     int it = 0;
-    for (int blk = blockIdx.x; blk < p.total_blocks; blk += gridDim.x, ++it) {
-      const StreamJob& jb = p.job[job_of_block(p, blk)];
+    for (TileIter t = tile_iter(p); next_tile(p, t); ++it) {
+      const StreamJob& jb = p.job[t.job];
       const int buf = it & 1;
-      const int64_t gr = (int64_t)(blk - jb.block0) * kRows + q * 32 + lane;
+      const int64_t gr = (int64_t)t.row0 + q * 32 + lane;
       uint32_t used_mask = 8u;
       for (int c = 0; c < jb.kch; ++c) used_mask |= 1u << ((c * 3) / jb.kch);
       float v1 = -INFINITY, v2 = -INFINITY;
@@ -249,7 +276,7 @@ nxc_stream_kernel(const __grid_constant__ StreamMaps maps, const StreamParams p)
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
-      if (gr < jb.n) {
+      if (q < t.ng && gr < jb.n) {
         if (jb.argmax_out) jb.argmax_out[gr] = i1;
         if (jb.margin_out) jb.margin_out[gr] = v1 - v2;
         if (jb.top1_out) jb.top1_out[gr] = jb.scale * v1;
@@ -263,13 +290,17 @@ nxc_stream_kernel(const __grid_constant__ StreamMaps maps, const StreamParams p)
     const uint32_t sw = (uint32_t)(r & 7);
     int stage = 0;
     uint32_t phase = 0;
-    for (int blk = blockIdx.x; blk < p.total_blocks; blk += gridDim.x) {
-      const StreamJob& jb = p.job[job_of_block(p, blk)];
+    for (TileIter t = tile_iter(p); next_tile(p, t);) {
+      const StreamJob& jb = p.job[t.job];
       for (int c = 0; c < jb.kch; ++c) {
         const uint32_t st = smem_base + stage * kStageBytes;
         mbar_wait(bar_raw_full + 8 * stage, phase);
+        const bool live = (r >> 5) < t.ng;       // warp-uniform: this warp's 32-row group is part of the tile
         float v[16];
-        if (jb.raw_f32) {
+        if (!live) {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) v[e] = 0.f;
+        } else if (jb.raw_f32) {
           // box h / 2 holds 32 features: row r = 128 bytes, 16-byte chunk j at position j ^ (r & 7);
           // this thread's 16 floats are chunks 4 (h & 1) .. 4 (h & 1) + 3
           const uint32_t row_addr = st + (h >> 1) * (kRawBytes / 2) + r * 128;
@@ -301,7 +332,7 @@ nxc_stream_kernel(const __grid_constant__ StreamMaps maps, const StreamParams p)
         const uint32_t prow = st + kOffPlanes + r * 128;
 #pragma unroll
         for (int pl = 0; pl < 3; ++pl) {
-          if (pl < jb.x_planes) {
+          if (live && pl < jb.x_planes) {
 #pragma unroll
             for (int g = 0; g < 2; ++g) {
               uint32_t w4[4];
@@ -428,7 +459,7 @@ extern "C" int latte_nxc_multi(const latte_nxc_job_t* jobs, int njobs, void* str
   StreamParams p = {};
   StreamMaps maps;
   p.njobs = njobs;
-  int blocks = 0;
+  int groups = 0;
   bool convert = false, direct = false;
   for (int j = 0; j < njobs; ++j) {
     const latte_nxc_job_t& in = jobs[j];
@@ -441,9 +472,9 @@ extern "C" int latte_nxc_multi(const latte_nxc_job_t* jobs, int njobs, void* str
       return LATTE_ERR_UNSUPPORTED;
     StreamJob& jb = p.job[j];
     jb.n = in.n;
-    jb.blocks = (int)((in.n + kRows - 1) / kRows);
-    jb.block0 = blocks;
-    blocks += jb.blocks;
+    jb.groups = (int)((in.n + kGrpRows - 1) / kGrpRows);
+    jb.group0 = groups;
+    groups += jb.groups;
     jb.kch = (int)((in.dim + kBK - 1) / kBK);
     jb.cp = (int)((in.num_classes + 15) / 16 * 16);
     jb.num_classes = (int)in.num_classes;
@@ -455,11 +486,11 @@ extern "C" int latte_nxc_multi(const latte_nxc_job_t* jobs, int njobs, void* str
     const int64_t dim_pad = (int64_t)jb.kch * kBK;
     int rc;
     if (in.x_dtype == LATTE_F32)
-      rc = stream_make_map(&maps.x[j], in.x, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, in.n, in.dim, in.ldx, 32, kRows);
+      rc = stream_make_map(&maps.x[j], in.x, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, in.n, in.dim, in.ldx, 32, kGrpRows);
     else
       rc = stream_make_map(&maps.x[j], in.x, in.x_dtype == LATTE_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
                                                                       : CU_TENSOR_MAP_DATA_TYPE_FLOAT16,
-                           2, in.n, in.dim, in.ldx, kBK, kRows);
+                           2, in.n, in.dim, in.ldx, kBK, kGrpRows);
     if (rc) return rc;
     rc = stream_make_map(&maps.p[j], in.planes, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, 3 * (int64_t)jb.cp,
                          dim_pad, dim_pad, kBK, jb.cp);
@@ -468,9 +499,9 @@ extern "C" int latte_nxc_multi(const latte_nxc_job_t* jobs, int njobs, void* str
   // one launch handles one operand format: all jobs bf16 (direct) or all fp32 / fp16 (converting)
   if (convert && direct) return LATTE_ERR_UNSUPPORTED;
   for (int j = njobs; j < kMaxJobs; ++j) { maps.x[j] = maps.x[0]; maps.p[j] = maps.p[0]; }
-  p.total_blocks = blocks;
+  p.total_groups = groups;
   int grid = device_sm_count();
-  if (grid > blocks) grid = blocks;
+  if (grid > groups) grid = groups;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (convert) {
     LATTE_CUDA_OK(cudaFuncSetAttribute(nxc_stream_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -5,6 +5,8 @@
 // All kernels: 128-bit vectorised, coalesced access where the layout allows it,
 // warp-shuffle reductions, no floating-point atomics (deterministic; per-class accumulation
 // follows the reference's sample order).
+#include <type_traits>
+
 #include "latte_common.cuh"
 #include "tc_ptx.cuh"
 
@@ -397,7 +399,7 @@ __global__ void __launch_bounds__(128) seg_final_kernel(SegArgs a) {
 // 1-D bulk copies (up to 64 row pairs in flight per SM).  With `d_per_image` the same pass is the mixer's backward: it also writes the two
 // row-shaped gradients from the rows it holds, so d_t_ft / d_t_zs are read once for all four
 // outputs (the five-launch sort path re-read them for the class sums).
-constexpr int kClsChunks = 128;
+constexpr int kClsChunks = 148;          // fixed (one wave of a B200; the same on any device)
 constexpr size_t kClsSmemMax = 200 * 1024;
 
 struct ClsArgs {
@@ -418,42 +420,63 @@ struct ClsArgs {
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
-// 2 consecutive elements of a row staged in shared memory / of a global row
-template <int DT> __device__ __forceinline__ float2 lds2(const uint8_t* row, int col) {
-  if (DT == LATTE_F32) return *reinterpret_cast<const float2*>(row + col * 4);
-  const uint32_t raw = *reinterpret_cast<const uint32_t*>(row + col * 2);
-  if (DT == LATTE_BF16) return make_float2(__uint_as_float(raw << 16), __uint_as_float(raw & 0xffff0000u));
-  return __half22float2(*reinterpret_cast<const __half2*>(&raw));
+// Shared-window accesses by 32-bit address: the accumulator read-modify-writes below are a dependent
+// chain per class, and generic pointers to dynamic shared memory cost an S2UR + address rebuild per
+// access (measured: 40 % of the consumer loop's stall samples).
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+  return v;
 }
-template <int DT> __device__ __forceinline__ void st2(void* base, int64_t idx, float2 v) {
-  if (DT == LATTE_F32) {
-    *reinterpret_cast<float2*>(static_cast<float*>(base) + idx) = v;
-  } else if (DT == LATTE_BF16) {
-    *reinterpret_cast<__nv_bfloat162*>(static_cast<__nv_bfloat16*>(base) + idx) = __floats2bfloat162_rn(v.x, v.y);
-  } else {
-    *reinterpret_cast<__half2*>(static_cast<__half*>(base) + idx) = __floats2half2_rn(v.x, v.y);
-  }
+__device__ __forceinline__ void sts_f32(uint32_t addr, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ uint4 lds_u4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+// element `col` of a row staged in shared memory
+template <int DT> __device__ __forceinline__ float lds_elem(uint32_t row, int col) {
+  if (DT == LATTE_F32) return lds_f32(row + col * 4);
+  unsigned short raw;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(raw) : "r"(row + col * 2) : "memory");
+  if (DT == LATTE_BF16) return __uint_as_float((uint32_t)raw << 16);
+  return __half2float(__ushort_as_half(raw));
+}
+template <int DT> __device__ __forceinline__ void st_elem(void* base, int64_t idx, float v) {
+  if (DT == LATTE_F32) static_cast<float*>(base)[idx] = v;
+  else if (DT == LATTE_BF16) static_cast<__nv_bfloat16*>(base)[idx] = __float2bfloat16_rn(v);
+  else static_cast<__half*>(base)[idx] = __float2half_rn(v);
 }
 
 // Shared memory of cls_stream_kernel: [C, D] fp32 accumulator | ring of `groups` x 4 row pairs (the zs
 // row and the ft row of one sample, filled by 1-D bulk copies: bytes in flight are bounded by the
 // ring, not by registers; one mbarrier per group of 4 samples keeps the per-row bookkeeping small) |
-// ids and weights of 256 samples | class counts | mbarriers.
+// ids and per-sample factors of 256 samples | class counts | mbarriers.
 constexpr int kClsIdRows = 256;
 constexpr int kClsGrp = 4;
-struct __align__(16) ClsIds { int p, z; float wl, wlz, wi, wg, pad0, pad1; };
+struct __align__(16) ClsIdA { int p, z; float sc_z, sc_f; };          // class ids, accumulator scales
+struct __align__(16) ClsIdB { float inv_ft, inv_zs, wi, wg; };        // row-output factors (mixer backward)
 
-template <int DT>
-__global__ void __launch_bounds__(544) cls_stream_kernel(ClsArgs a, int groups, int row_bytes) {
+// DT: feature dtype; BWD: mixer backward (weighted rows, optional row-shaped outputs); VPT: columns per
+// consumer thread.
+// One column per thread (D <= 992) gives 16-24 consumer warps: each row costs a dependent
+// ld.shared -> fma -> st.shared on the accumulator row of its class, and only warp-level parallelism
+// hides that chain (8 warps with 2 columns each ran at 0.28 instructions / cycle / scheduler and made the
+// kernel compute-bound at 0.3 of the HBM rate for fp32 rows, 0.15 for bf16).
+template <int DT, bool BWD, int VPT>
+__global__ void __launch_bounds__(1024) cls_stream_kernel(ClsArgs a, int groups, int row_bytes) {
   extern __shared__ __align__(128) uint8_t cls_smem[];
   using namespace ptx;
-  const int nv2 = (int)(a.dim / 2);                        // a consumer thread owns 2 columns
+  const int dim = (int)a.dim;
   const size_t acc_bytes = ((size_t)a.num_classes * a.dim * 4 + 127) / 128 * 128;
-  float2* acc = reinterpret_cast<float2*>(cls_smem);                                        // [C][dim / 2]
+  float* acc = reinterpret_cast<float*>(cls_smem);                                          // [C][dim]
   uint8_t* ring = cls_smem + acc_bytes;                                    // [groups][4][2][row_bytes]
   const int grp_bytes = kClsGrp * 2 * row_bytes;
-  ClsIds* ids = reinterpret_cast<ClsIds*>(ring + (size_t)groups * grp_bytes);               // [256]
-  int* cnt = reinterpret_cast<int*>(ids + kClsIdRows);                                      // [C]
+  ClsIdA* ida = reinterpret_cast<ClsIdA*>(ring + (size_t)groups * grp_bytes);               // [256]
+  ClsIdB* idb = reinterpret_cast<ClsIdB*>(ida + kClsIdRows);                                // [256]
+  int* cnt = reinterpret_cast<int*>(idb + kClsIdRows);                                      // [C]
   const uint32_t bar_full = smem_u32(cnt + ((a.num_classes + 3) / 4 * 4));                  // [groups]
   const uint32_t bar_empty = bar_full + 8 * groups;                                         // [groups]
   const int ncons = (int)blockDim.x - 32;                  // consumer threads (the last warp produces)
@@ -464,7 +487,7 @@ __global__ void __launch_bounds__(544) cls_stream_kernel(ClsArgs a, int groups, 
   const int rows = (int)(r1 - r0);
   const int ngrp = (rows + kClsGrp - 1) / kClsGrp;
 
-  for (int k = threadIdx.x; k < a.num_classes * nv2; k += blockDim.x) acc[k] = make_float2(0.f, 0.f);
+  for (int k = threadIdx.x; k < a.num_classes * dim; k += blockDim.x) acc[k] = 0.f;
   for (int k = threadIdx.x; k < a.num_classes; k += blockDim.x) cnt[k] = 0;
   if (threadIdx.x == 0) {
     for (int s = 0; s < groups; ++s) {
@@ -507,27 +530,38 @@ __global__ void __launch_bounds__(544) cls_stream_kernel(ClsArgs a, int groups, 
     return;
   }
 
-  // ------------------------------------------------------------ consumers: thread -> 2 columns
-  // (the adds of one accumulator element form a dependent chain through shared memory; 8-16 warps
-  //  with 2 columns per thread hide it, 4 warps with 4 columns did not)
-  const bool col_ok = (int)threadIdx.x < nv2;
-  const int d = col_ok ? (int)threadIdx.x * 2 : 0;            // idle lanes re-read column 0
-  const bool quirk = a.w_lbl && a.label_axis == LATTE_LABEL_AXIS_QUIRK;
-  float2* my_acc = acc + threadIdx.x;
+  // ------------------------------------------------------------ consumers: thread -> VPT columns
+  const int d0 = (int)threadIdx.x * VPT;
+  const bool col_ok = d0 < dim;
+  const int d = col_ok ? d0 : 0;                              // idle lanes re-read column 0
+  const bool quirk = BWD && a.label_axis == LATTE_LABEL_AXIS_QUIRK;
+  const uint32_t acc_col = smem_u32(acc) + (uint32_t)d * 4;
+  const uint32_t ring_base = smem_u32(ring);
+  const uint32_t ida_base = smem_u32(ida), idb_base = smem_u32(idb);
   int s = 0;
   uint32_t phase = 0;
   for (int k0 = 0; k0 < rows; k0 += kClsIdRows) {
-    // ids and weights of the next 256 samples (coalesced), validated and counted once
+    // ids and factors of the next 256 samples (coalesced), validated and counted once
     named_bar_sync(1, ncons);
     for (int t = threadIdx.x; t < kClsIdRows && k0 + t < rows; t += ncons) {
       const int64_t i = r0 + k0 + t;
       const int64_t p = a.preds[i], z = a.zs[i];
-      ClsIds q;
+      ClsIdA q;
       q.p = (p >= 0 && p < a.num_classes) ? (int)p : -1;      // out-of-range ids are dropped
       q.z = (z >= 0 && z < a.num_classes) ? (int)z : -1;
-      q.wl = q.wlz = 1.f; q.wi = q.wg = 0.f; q.pad0 = q.pad1 = 0.f;
-      if (a.w_lbl) { q.wl = a.w_lbl[i]; q.wlz = a.w_lbl_zs[i]; q.wi = a.w_img[i]; q.wg = a.w_grp[i]; }
-      ids[t] = q;
+      q.sc_z = q.sc_f = 1.f;
+      if (BWD) {
+        const float wl = a.w_lbl[i], wlz = a.w_lbl_zs[i], wi = a.w_img[i], wg = a.w_grp[i];
+        ClsIdB f;
+        f.inv_ft = a.alpha / (wl + wi + wg);
+        f.inv_zs = a.alpha / (wlz + wi + wg);
+        f.wi = wi; f.wg = wg;
+        const float wle = quirk ? 1.f : wl;   // quirk axis: the label weight is a column factor (final step)
+        q.sc_z = f.inv_zs * wle;
+        q.sc_f = f.inv_ft * wle;
+        idb[t] = f;
+      }
+      ida[t] = q;
       if (q.z >= 0) atomicAdd(cnt + q.z, 1);                  // integer counts: order does not matter
       if (q.p >= 0) atomicAdd(cnt + q.p, 1);
     }
@@ -535,13 +569,15 @@ __global__ void __launch_bounds__(544) cls_stream_kernel(ClsArgs a, int groups, 
     const int kend = min(rows, k0 + kClsIdRows);
     for (int k = k0; k < kend; k += kClsGrp) {
       mbar_wait(bar_full + 8 * s, phase);
-      const uint8_t* grp = ring + (size_t)s * grp_bytes;
-      float2 gz[kClsGrp], gf[kClsGrp];
+      const uint32_t grp = ring_base + (uint32_t)s * grp_bytes;
+      float gz[kClsGrp][VPT], gf[kClsGrp][VPT];
 #pragma unroll
-      for (int u = 0; u < kClsGrp; ++u) {                      // rows past the chunk: stale bytes, unused
-        gz[u] = lds2<DT>(grp + u * row_bytes, d);                 // group layout: 4 zs rows, then 4 ft rows
-        gf[u] = lds2<DT>(grp + (kClsGrp + u) * row_bytes, d);
-      }
+      for (int u = 0; u < kClsGrp; ++u)                        // rows past the chunk: stale bytes, unused
+#pragma unroll
+        for (int v = 0; v < VPT; ++v) {                        // group layout: 4 zs rows, then 4 ft rows
+          gz[u][v] = lds_elem<DT>(grp + u * row_bytes, d + v);
+          gf[u][v] = lds_elem<DT>(grp + (kClsGrp + u) * row_bytes, d + v);
+        }
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_empty + 8 * s);            // this warp has its copy of the group
       if (++s == groups) { s = 0; phase ^= 1; }
@@ -549,39 +585,37 @@ __global__ void __launch_bounds__(544) cls_stream_kernel(ClsArgs a, int groups, 
 #pragma unroll
       for (int u = 0; u < kClsGrp; ++u) {
         if (k + u >= kend) break;
-        const ClsIds q = ids[k + u - k0];
-        float inv_ft = 1.f, inv_zs = 1.f, wl = 1.f;
-        if (a.w_lbl) {
-          inv_ft = a.alpha / (q.wl + q.wi + q.wg);
-          inv_zs = a.alpha / (q.wlz + q.wi + q.wg);
-          if (!quirk) wl = q.wl;       // quirk axis: the label weight is a column factor (final step)
-        }
-        if (a.d_per_image) {
+        const uint4 qa = lds_u4(ida_base + (uint32_t)(k + u - k0) * 16);
+        const int qp = (int)qa.x, qz = (int)qa.y;
+        const float sc_z = __uint_as_float(qa.z), sc_f = __uint_as_float(qa.w);
+        if (BWD && a.d_per_image) {
+          const uint4 qb = lds_u4(idb_base + (uint32_t)(k + u - k0) * 16);
+          const float inv_ft = __uint_as_float(qb.x), inv_zs = __uint_as_float(qb.y);
+          const float wi = __uint_as_float(qb.z), wg = __uint_as_float(qb.w);
           const int64_t i = r0 + k + u;
-          const float dx = gf[u].x * inv_ft + gz[u].x * inv_zs, dy = gf[u].y * inv_ft + gz[u].y * inv_zs;
-          st2<DT>(a.d_per_image, i * a.ld_dp + d, make_float2(q.wi * dx, q.wi * dy));
-          st2<DT>(a.d_per_group, i * a.ld_dp + d, make_float2(q.wg * dx, q.wg * dy));
+#pragma unroll
+          for (int v = 0; v < VPT; ++v) {
+            const float dx = gf[u][v] * inv_ft + gz[u][v] * inv_zs;
+            st_elem<DT>(a.d_per_image, i * a.ld_dp + d + v, wi * dx);
+            st_elem<DT>(a.d_per_group, i * a.ld_dp + d + v, wg * dx);
+          }
         }
-        if (q.z >= 0) {            // entry 2i: the zs-list row first (train.py:524)
-          const float sc = inv_zs * wl;
-          float2* o = my_acc + q.z * nv2;
-          float2 t = *o;
-          t.x = fmaf(gz[u].x, sc, t.x); t.y = fmaf(gz[u].y, sc, t.y);
-          *o = t;
+        if (qz >= 0) {             // entry 2i: the zs-list row first (train.py:524)
+          const uint32_t o = acc_col + (uint32_t)(qz * dim) * 4;
+#pragma unroll
+          for (int v = 0; v < VPT; ++v) sts_f32(o + 4 * v, fmaf(gz[u][v], sc_z, lds_f32(o + 4 * v)));
         }
-        if (q.p >= 0) {            // entry 2i + 1: the ft-list row (train.py:525)
-          const float sc = inv_ft * wl;
-          float2* o = my_acc + q.p * nv2;
-          float2 t = *o;
-          t.x = fmaf(gf[u].x, sc, t.x); t.y = fmaf(gf[u].y, sc, t.y);
-          *o = t;
+        if (qp >= 0) {             // entry 2i + 1: the ft-list row (train.py:525)
+          const uint32_t o = acc_col + (uint32_t)(qp * dim) * 4;
+#pragma unroll
+          for (int v = 0; v < VPT; ++v) sts_f32(o + 4 * v, fmaf(gf[u][v], sc_f, lds_f32(o + 4 * v)));
         }
       }
     }
   }
   named_bar_sync(1, ncons);
-  float2* dst = reinterpret_cast<float2*>(a.partial) + (int64_t)blockIdx.x * a.num_classes * nv2;
-  for (int k = threadIdx.x; k < a.num_classes * nv2; k += ncons) dst[k] = acc[k];
+  float* dst = a.partial + (int64_t)blockIdx.x * a.num_classes * dim;
+  for (int k = threadIdx.x; k < a.num_classes * dim; k += ncons) dst[k] = acc[k];
   for (int k = threadIdx.x; k < a.num_classes; k += ncons)
     a.cnt_partial[(int64_t)blockIdx.x * a.num_classes + k] = cnt[k];
 }
@@ -643,10 +677,11 @@ struct ClsGeom { bool ok; int chunks; int64_t rows_per_chunk; size_t smem, part_
 ClsGeom cls_geom(int64_t batch, int64_t dim, int64_t num_classes, int esz = 4) {
   ClsGeom g{};
   const size_t acc = ((size_t)num_classes * (size_t)dim * 4 + 127) / 128 * 128;
-  const size_t fixed = acc + (size_t)kClsIdRows * sizeof(ClsIds) + ((size_t)num_classes + 3) / 4 * 16 + 64;
+  const size_t fixed = acc + (size_t)kClsIdRows * (sizeof(ClsIdA) + sizeof(ClsIdB)) +
+                       ((size_t)num_classes + 3) / 4 * 16 + 64;
   const size_t row_bytes = (size_t)dim * esz;
   const size_t grp = (size_t)kClsGrp * 2 * row_bytes + 16;          // one group of 4 row pairs + 2 mbarriers
-  g.ok = batch > 0 && dim % 8 == 0 && dim / 2 <= 512 && fixed + 2 * grp <= kClsSmemMax;
+  g.ok = batch > 0 && dim % 8 == 0 && dim / 2 <= 992 && fixed + 2 * grp <= kClsSmemMax;
   if (!g.ok) return g;
   size_t groups = (kClsSmemMax - fixed) / grp;
   if (groups > 16) groups = 16;
@@ -681,18 +716,25 @@ int class_sums_stream(ClsArgs a, void* workspace, size_t workspace_bytes, cudaSt
   a.chunks = g.chunks;
   a.rows_per_chunk = g.rows_per_chunk;
   const int nvec = (int)(a.dim / 4);
-  const int threads = (int)((a.dim / 2 + 31) / 32 * 32) + 32;      // consumers (2 columns each) + the producer warp
+  const int vpt = a.dim <= 992 ? 1 : 2;                            // columns per consumer thread
+  const int threads = (int)((a.dim / vpt + 31) / 32 * 32) + 32;    // consumers + the producer warp
   const int row_bytes = (int)(a.dim * esz);
+  const bool bwd = a.w_lbl != nullptr;
   auto launch = [&](auto kernel) -> int {
     if (g.smem > 48 * 1024)
       LATTE_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
     kernel<<<g.chunks, threads, g.smem, st>>>(a, g.slots, row_bytes);
     return LATTE_OK;
   };
+  auto pick = [&](auto dt) -> int {
+    constexpr int DT = decltype(dt)::value;
+    if (bwd) return vpt == 1 ? launch(cls_stream_kernel<DT, true, 1>) : launch(cls_stream_kernel<DT, true, 2>);
+    return vpt == 1 ? launch(cls_stream_kernel<DT, false, 1>) : launch(cls_stream_kernel<DT, false, 2>);
+  };
   int lrc;
-  if (a.dtype == LATTE_F32) lrc = launch(cls_stream_kernel<LATTE_F32>);
-  else if (a.dtype == LATTE_BF16) lrc = launch(cls_stream_kernel<LATTE_BF16>);
-  else lrc = launch(cls_stream_kernel<LATTE_F16>);
+  if (a.dtype == LATTE_F32) lrc = pick(std::integral_constant<int, LATTE_F32>{});
+  else if (a.dtype == LATTE_BF16) lrc = pick(std::integral_constant<int, LATTE_BF16>{});
+  else lrc = pick(std::integral_constant<int, LATTE_F16>{});
   if (lrc) return lrc;
   cls_final_kernel<<<dim3((unsigned)a.num_classes, (unsigned)((nvec + 31) / 32)), 128, 0, st>>>(a);
   if (cudaGetLastError() != cudaSuccess) return LATTE_ERR_CUDA;

@@ -432,9 +432,9 @@ def test_prototype_step_and_backward_capture_in_a_cuda_graph():
         # bf16) can cancel, so the bound is one bf16 ulp of the tensor's largest entry per element and
         # 2^-8 of the norm overall, not a per-element relative error
         for k in leaves:
-            a, b = got[k].float(), leaves[k].grad.float()
-            assert float((a - b).abs().max()) <= 2.0 ** -7 * float(b.abs().max()), k
-            assert float((a - b).norm()) <= 2.0 ** -8 * float(b.norm()), k
+            g_rep, g_eag = got[k].float(), leaves[k].grad.float()
+            assert float((g_rep - g_eag).abs().max()) <= 2.0 ** -7 * float(g_eag.abs().max()), k
+            assert float((g_rep - g_eag).norm()) <= 2.0 ** -8 * float(g_eag.norm()), k
         assert torch.allclose(got["s"], log_s.grad, rtol=1e-5)
 
 
