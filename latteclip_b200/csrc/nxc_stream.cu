@@ -37,9 +37,11 @@ constexpr int kMaxJobs = 4;
 constexpr int kAccCols = 64;                   // TMEM columns per accumulator
 constexpr int kBufCols = 4 * kAccCols;         // per TMEM buffer: 4 accumulators
 
-// converting variant: stage = raw 32 KB + planes 48 KB + prototypes 24 KB; two stages
+// converting variant (fp32 rows): stage = raw 32 KB + two fp16 planes 32 KB + prototypes 24 KB; two stages
 constexpr int kCvtStages = 2;
-constexpr int kCvtStageBytes = kRawBytes + 3 * kPlaneBytes + kPBytes;        // 104 KB
+constexpr int kCvtXPlanes = 2;                 // fp32 = h0 + 2^-11 h1 with two fp16 planes (see below)
+constexpr int kCvtStageBytes = kRawBytes + kCvtXPlanes * kPlaneBytes + kPBytes;        // 88 KB
+constexpr float kLoScale = 2048.f;             // the low plane is stored times 2^11 (fp16 subnormals)
 constexpr int kCvtSmem = kCvtStages * kCvtStageBytes + 1024;
 constexpr int kCvtWarps = 16;                  // converter warps: 4 per scheduler hide the cvt -> sub chains
 constexpr int kCvtThreads = (6 + kCvtWarps) * 32;   // TMA, MMA, 4 epilogue warps, converters
@@ -56,8 +58,10 @@ struct StreamJob {
   int kch;                   // ceil(dim / 64)
   int cp;                    // classes padded to a multiple of 16 (<= 64)
   int num_classes;
-  int x_planes;              // 1 (bf16), 2 (fp16), 3 (fp32)
-  int raw_f32;               // raw tile is fp32 (two boxes per chunk) or fp16 (one box)
+  int x_planes;              // operand planes of a feature row: 1 (bf16, fp16: the row itself), 2 (fp32)
+  int p_planes;              // prototype planes: 3 bf16 planes (bf16 rows) or 2 fp16 planes (fp16 / fp32 rows)
+  int ab_fmt;                // MMA operand format: 1 bf16, 0 fp16
+  int raw_f32;               // raw tile is fp32 (two boxes per chunk, converted) or 16-bit (used as it is)
   float scale;
   int64_t* argmax_out; float* margin_out; float* top1_out;
 };
@@ -108,7 +112,7 @@ nxc_stream_kernel(const __grid_constant__ StreamMaps maps, const StreamParams p)
   constexpr int kStages = kConvert ? kCvtStages : kDirStages;
   constexpr int kStageBytes = kConvert ? kCvtStageBytes : kDirStageBytes;
   constexpr int kOffPlanes = kConvert ? kRawBytes : 0;                     // inside a stage
-  constexpr int kOffP = kOffPlanes + (kConvert ? 3 : 1) * kPlaneBytes;
+  constexpr int kOffP = kOffPlanes + (kConvert ? kCvtXPlanes : 1) * kPlaneBytes;
   const uint32_t misc = smem_base + kStages * kStageBytes;
   const uint32_t bar_raw_full = misc;                     // [kStages] raw tile landed (kConvert)
   const uint32_t bar_raw_empty = misc + 8 * kStages;      // [kStages] converters done with the raw tile
@@ -159,28 +163,22 @@ nxc_stream_kernel(const __grid_constant__ StreamMaps maps, const StreamParams p)
       for (TileIter t = tile_iter(p); next_tile(p, t);) {
         const int j = t.job;
         const StreamJob& jb = p.job[j];
-        const uint32_t p_tx = 3u * (uint32_t)jb.cp * (kBK * 2);
+        const uint32_t p_tx = (uint32_t)jb.p_planes * (uint32_t)jb.cp * (kBK * 2);
         for (int c = 0; c < jb.kch; ++c) {
           const uint32_t st = smem_base + stage * kStageBytes;
           if (kConvert) {
             mbar_wait(bar_raw_empty + 8 * stage, phase ^ 1);
             const uint32_t rf = bar_raw_full + 8 * stage;
-            if (jb.raw_f32) {
-              mbar_arrive_expect_tx(rf, 2u * (uint32_t)t.ng * kGrpBytes);
-              for (int g = 0; g < t.ng; ++g) {
-                tma_load_2d_hint(st + g * kGrpBytes, &maps.x[j], rf, c * kBK, t.row0 + g * kGrpRows, stream_pol);
-                tma_load_2d_hint(st + kRawBytes / 2 + g * kGrpBytes, &maps.x[j], rf, c * kBK + 32,
-                                 t.row0 + g * kGrpRows, stream_pol);
-              }
-            } else {
-              mbar_arrive_expect_tx(rf, (uint32_t)t.ng * kGrpBytes);
-              for (int g = 0; g < t.ng; ++g)
-                tma_load_2d_hint(st + g * kGrpBytes, &maps.x[j], rf, c * kBK, t.row0 + g * kGrpRows, stream_pol);
+            mbar_arrive_expect_tx(rf, 2u * (uint32_t)t.ng * kGrpBytes);
+            for (int g = 0; g < t.ng; ++g) {
+              tma_load_2d_hint(st + g * kGrpBytes, &maps.x[j], rf, c * kBK, t.row0 + g * kGrpRows, stream_pol);
+              tma_load_2d_hint(st + kRawBytes / 2 + g * kGrpBytes, &maps.x[j], rf, c * kBK + 32,
+                               t.row0 + g * kGrpRows, stream_pol);
             }
             mbar_wait(bar_op_empty + 8 * stage, phase ^ 1);
             const uint32_t pf = bar_p_full + 8 * stage;
             mbar_arrive_expect_tx(pf, p_tx);
-            for (int b = 0; b < 3; ++b)
+            for (int b = 0; b < jb.p_planes; ++b)
               tma_load_2d_hint(st + kOffP + b * (kMaxCls * kBK * 2), &maps.p[j], pf, c * kBK, b * jb.cp,
                                keep_pol);
           } else {
@@ -189,7 +187,7 @@ nxc_stream_kernel(const __grid_constant__ StreamMaps maps, const StreamParams p)
             mbar_arrive_expect_tx(of, (uint32_t)t.ng * kGrpBytes + p_tx);
             for (int g = 0; g < t.ng; ++g)
               tma_load_2d_hint(st + g * kGrpBytes, &maps.x[j], of, c * kBK, t.row0 + g * kGrpRows, stream_pol);
-            for (int b = 0; b < 3; ++b)
+            for (int b = 0; b < jb.p_planes; ++b)
               tma_load_2d_hint(st + kOffP + b * (kMaxCls * kBK * 2), &maps.p[j], of, c * kBK, b * jb.cp,
                                keep_pol);
           }
@@ -200,16 +198,21 @@ nxc_stream_kernel(const __grid_constant__ StreamMaps maps, const StreamParams p)
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
     if (elect_one()) {
-      // plane pairs (a, b) with a + b <= 2, small terms first
-      const int pa[6] = {2, 1, 0, 1, 0, 0};
-      const int pb[6] = {0, 1, 2, 0, 1, 0};
+      // plane pairs (a, b), small terms first.  bf16 rows (x = x0, p = p0 + p1 + p2 in bf16):
+      // (0,2) (0,1) (0,0).  fp16 planes (16-bit halves of an fp32 value: v = h0 + 2^-11 h1 with
+      // |v - h0 - 2^-11 h1| <= 2^-24 |v|; the low plane is stored times 2^11): fp16 rows (0,1) (0,0),
+      // fp32 rows (0,1) (1,0) (0,0) -- the (1,1) term is below 2^-22 |x||p| and dropped.  The large
+      // term (0,0) goes to accumulator `third`, all others to accumulator 3 (scaled by 2^-11 in the
+      // epilogue when the planes are fp16).
+      const int pa[4] = {0, 0, 1, 0};
+      const int pb[4] = {2, 1, 0, 0};
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
       for (TileIter t = tile_iter(p); next_tile(p, t); ++it) {
         const StreamJob& jb = p.job[t.job];
         const int buf = it & 1;
-        const uint32_t idesc = make_idesc_f16(kRows, jb.cp, 1u, 0, 0);
+        const uint32_t idesc = make_idesc_f16(kRows, jb.cp, (uint32_t)jb.ab_fmt, 0, 0);
         mbar_wait(bar_tempty + 8 * buf, ((it >> 1) & 1) ^ 1);
         tc_fence_after();
         uint32_t used = 0;                 // bit a: accumulator a already holds a partial sum
@@ -219,8 +222,8 @@ nxc_stream_kernel(const __grid_constant__ StreamMaps maps, const StreamParams p)
           tc_fence_after();
           const uint32_t st = smem_base + stage * kStageBytes;
           const int third = (c * 3) / jb.kch;            // accumulator of the x0.p0 term
-          for (int q = 0; q < 6; ++q) {
-            if (pa[q] >= jb.x_planes) continue;
+          for (int q = 0; q < 4; ++q) {
+            if (pa[q] >= jb.x_planes || pb[q] >= jb.p_planes) continue;
             const int acc_id = (pa[q] | pb[q]) == 0 ? third : 3;
             const uint32_t tmem_d = tmem_base + buf * kBufCols + acc_id * kAccCols;
             const uint64_t da0 = make_smem_desc_sw128(st + kOffPlanes + pa[q] * kPlaneBytes, 16, 1024);
@@ -250,6 +253,7 @@ nxc_stream_kernel(const __grid_constant__ StreamMaps maps, const StreamParams p)
       for (int c = 0; c < jb.kch; ++c) used_mask |= 1u << ((c * 3) / jb.kch);
       float v1 = -INFINITY, v2 = -INFINITY;
       int i1 = 0;
+      const float lo_scale = jb.ab_fmt == 0 ? 1.f / kLoScale : 1.f;   // fp16 planes: low plane stored times 2^11
       mbar_wait(bar_tfull + 8 * buf, (it >> 1) & 1);
       tc_fence_after();
       for (int cc = 0; cc < jb.cp; cc += 16) {
@@ -263,7 +267,7 @@ nxc_stream_kernel(const __grid_constant__ StreamMaps maps, const StreamParams p)
 #pragma unroll
         for (int jx = 0; jx < 16; ++jx) {
           float s = 0.f;                       // small terms first, round-to-nearest adds
-          if ((used_mask >> 3) & 1u) s = __uint_as_float(r[3][jx]);
+          if ((used_mask >> 3) & 1u) s = __uint_as_float(r[3][jx]) * lo_scale;
           if ((used_mask >> 2) & 1u) s += __uint_as_float(r[2][jx]);
           if ((used_mask >> 1) & 1u) s += __uint_as_float(r[1][jx]);
           if (used_mask & 1u) s += __uint_as_float(r[0][jx]);
@@ -300,7 +304,7 @@ nxc_stream_kernel(const __grid_constant__ StreamMaps maps, const StreamParams p)
         if (!live) {
 #pragma unroll
           for (int e = 0; e < 16; ++e) v[e] = 0.f;
-        } else if (jb.raw_f32) {
+        } else {
           // box h / 2 holds 32 features: row r = 128 bytes, 16-byte chunk j at position j ^ (r & 7);
           // this thread's 16 floats are chunks 4 (h & 1) .. 4 (h & 1) + 3
           const uint32_t row_addr = st + (h >> 1) * (kRawBytes / 2) + r * 128;
@@ -311,38 +315,29 @@ nxc_stream_kernel(const __grid_constant__ StreamMaps maps, const StreamParams p)
             v[4 * jx] = __uint_as_float(a); v[4 * jx + 1] = __uint_as_float(b);
             v[4 * jx + 2] = __uint_as_float(cw); v[4 * jx + 3] = __uint_as_float(d);
           }
-        } else {
-          // fp16 rows: one box of 64 halves per row; this thread's 16 halves are chunks 2h, 2h + 1
-          const uint32_t row_addr = st + r * 128;
-#pragma unroll
-          for (int jx = 0; jx < 2; ++jx) {
-            uint32_t w4[4];
-            ld_shared_v4(row_addr + (((uint32_t)(2 * h + jx) ^ sw) << 4), w4[0], w4[1], w4[2], w4[3]);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w4[e]));
-              v[8 * jx + 2 * e] = f.x; v[8 * jx + 2 * e + 1] = f.y;
-            }
-          }
         }
         // the raw tile is in registers: hand the buffer back before converting
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_raw_empty + 8 * stage);
         mbar_wait(bar_op_empty + 8 * stage, phase ^ 1);     // MMAs that read these planes are done
         const uint32_t prow = st + kOffPlanes + r * 128;
+        if (live) {
+          // h0 = fp16(v), h1 = fp16(2^11 (v - h0)): the residual is exact in fp32 and the scaling keeps
+          // the low plane out of fp16's subnormal range (|v| < 65504 is assumed: unit-norm features)
 #pragma unroll
-        for (int pl = 0; pl < 3; ++pl) {
-          if (live && pl < jb.x_planes) {
+          for (int pl = 0; pl < kCvtXPlanes; ++pl) {
 #pragma unroll
             for (int g = 0; g < 2; ++g) {
               uint32_t w4[4];
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
-                const __nv_bfloat162 b2 = __floats2bfloat162_rn(v[8 * g + 2 * e], v[8 * g + 2 * e + 1]);
-                w4[e] = *reinterpret_cast<const uint32_t*>(&b2);
-                // residual, exact in fp32: the two bf16 values widen by a mask and a shift
-                v[8 * g + 2 * e] -= __uint_as_float(w4[e] << 16);
-                v[8 * g + 2 * e + 1] -= __uint_as_float(w4[e] & 0xffff0000u);
+                const __half2 h2 = __floats2half2_rn(v[8 * g + 2 * e], v[8 * g + 2 * e + 1]);
+                w4[e] = *reinterpret_cast<const uint32_t*>(&h2);
+                if (pl == 0) {
+                  const float2 f = __half22float2(h2);
+                  v[8 * g + 2 * e] = (v[8 * g + 2 * e] - f.x) * kLoScale;
+                  v[8 * g + 2 * e + 1] = (v[8 * g + 2 * e + 1] - f.y) * kLoScale;
+                }
               }
               st_shared_v4(prow + pl * kPlaneBytes + (((uint32_t)(2 * h + g) ^ sw) << 4), w4[0], w4[1], w4[2], w4[3]);
             }
@@ -361,8 +356,10 @@ nxc_stream_kernel(const __grid_constant__ StreamMaps maps, const StreamParams p)
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
-// prototypes [C, D] fp32 -> bf16 planes [3][cp][dim_pad] (rows >= C and columns >= D are zero),
-// optionally L2-normalising each row first (train.py:384-389: F.normalize(stack(bank), dim=1)).
+// prototypes [C, D] fp32 -> bf16 planes [3][cp][dim_pad] followed by fp16 planes [2][cp][dim_pad]
+// (high half, and 2^11 times the residual; rows >= C and columns >= D are zero), optionally
+// L2-normalising each row first (train.py:384-389: F.normalize(stack(bank), dim=1)).  bf16 feature
+// rows multiply the bf16 planes, fp16 / fp32 rows the fp16 planes.
 __global__ void __launch_bounds__(256)
 nxc_split_protos_kernel(const float* protos, int64_t ld, int num_classes, int dim, int cp, int dim_pad,
                         int normalize, __nv_bfloat16* out, float* normalized_out, int64_t ld_norm) {
@@ -384,6 +381,12 @@ nxc_split_protos_kernel(const float* protos, int64_t ld, int num_classes, int di
     float v = (c < num_classes && d < dim) ? protos[(int64_t)c * ld + d] : 0.f;
     if (normalize) v *= inv;            // the same x * (1 / max(norm, eps)) as latte_normalize_rows
     if (normalized_out && c < num_classes && d < dim) normalized_out[(int64_t)c * ld_norm + d] = v;
+    {
+      __half* out16 = reinterpret_cast<__half*>(out + (int64_t)3 * cp * dim_pad);
+      const __half h0 = __float2half_rn(v);
+      out16[(int64_t)c * dim_pad + d] = h0;
+      out16[((int64_t)cp + c) * dim_pad + d] = __float2half_rn((v - __half2float(h0)) * kLoScale);
+    }
 #pragma unroll
     for (int pl = 0; pl < 3; ++pl) {
       const __nv_bfloat16 b = __float2bfloat16_rn(v);
@@ -434,7 +437,7 @@ extern "C" int latte_nxc_planes_bytes(int64_t num_classes, int64_t dim, size_t* 
   if (num_classes > kMaxCls) return LATTE_ERR_UNSUPPORTED;
   const int64_t cp = (num_classes + 15) / 16 * 16;
   const int64_t dim_pad = (dim + kBK - 1) / kBK * kBK;
-  *bytes = (size_t)3 * cp * dim_pad * sizeof(__nv_bfloat16);
+  *bytes = (size_t)(3 + 2) * cp * dim_pad * sizeof(__nv_bfloat16);      // 3 bf16 planes + 2 fp16 planes
   return LATTE_OK;
 }
 
@@ -478,11 +481,13 @@ extern "C" int latte_nxc_multi(const latte_nxc_job_t* jobs, int njobs, void* str
     jb.kch = (int)((in.dim + kBK - 1) / kBK);
     jb.cp = (int)((in.num_classes + 15) / 16 * 16);
     jb.num_classes = (int)in.num_classes;
-    jb.x_planes = in.x_dtype == LATTE_BF16 ? 1 : (in.x_dtype == LATTE_F16 ? 2 : 3);
+    jb.x_planes = in.x_dtype == LATTE_F32 ? kCvtXPlanes : 1;
+    jb.p_planes = in.x_dtype == LATTE_BF16 ? 3 : 2;
+    jb.ab_fmt = in.x_dtype == LATTE_BF16 ? 1 : 0;
     jb.raw_f32 = in.x_dtype == LATTE_F32;
     jb.scale = in.scale;
     jb.argmax_out = in.argmax_out; jb.margin_out = in.margin_out; jb.top1_out = in.top1_out;
-    (in.x_dtype == LATTE_BF16 ? direct : convert) = true;
+    (in.x_dtype == LATTE_F32 ? convert : direct) = true;
     const int64_t dim_pad = (int64_t)jb.kch * kBK;
     int rc;
     if (in.x_dtype == LATTE_F32)
@@ -492,11 +497,16 @@ extern "C" int latte_nxc_multi(const latte_nxc_job_t* jobs, int njobs, void* str
                                                                       : CU_TENSOR_MAP_DATA_TYPE_FLOAT16,
                            2, in.n, in.dim, in.ldx, kBK, kGrpRows);
     if (rc) return rc;
-    rc = stream_make_map(&maps.p[j], in.planes, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, 3 * (int64_t)jb.cp,
-                         dim_pad, dim_pad, kBK, jb.cp);
+    if (in.x_dtype == LATTE_BF16)
+      rc = stream_make_map(&maps.p[j], in.planes, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, 3 * (int64_t)jb.cp,
+                           dim_pad, dim_pad, kBK, jb.cp);
+    else
+      rc = stream_make_map(&maps.p[j], static_cast<const char*>(in.planes) + (size_t)3 * jb.cp * dim_pad * 2,
+                           CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, 2 * (int64_t)jb.cp, dim_pad, dim_pad, kBK, jb.cp);
     if (rc) return rc;
   }
-  // one launch handles one operand format: all jobs bf16 (direct) or all fp32 / fp16 (converting)
+  // one launch handles one operand class: all jobs 16-bit (rows are MMA operands as they are) or all
+  // fp32 (converting)
   if (convert && direct) return LATTE_ERR_UNSUPPORTED;
   for (int j = njobs; j < kMaxJobs; ++j) { maps.x[j] = maps.x[0]; maps.p[j] = maps.p[0]; }
   p.total_groups = groups;
