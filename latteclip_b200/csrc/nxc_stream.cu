@@ -71,8 +71,10 @@ struct StreamParams {
   int total_groups;
 };
 struct StreamMaps {
-  CUtensorMap x[kMaxJobs];   // raw rows, 32-row boxes (fp32: 32 features wide; 16-bit: 64 wide)
-  CUtensorMap p[kMaxJobs];   // prototype planes [3 * cp rows, dim_pad] bf16, box 64 x cp
+  CUtensorMap x[kMaxJobs];   // raw rows, 32-row boxes (fp32: 32 features wide; 16-bit: 64 wide): partial tiles
+  CUtensorMap xf[kMaxJobs];  // the same rows, 128-row boxes: full tiles (one TMA instead of four -- the
+                             // issue rate of the single producer thread bounds the 16-bit variant)
+  CUtensorMap p[kMaxJobs];   // prototype planes of one operand format, box 64 x (planes * cp): one TMA per chunk
 };
 
 // Row tiles of one CTA.  The 32-row groups of all jobs form one flattened space that is dealt to the
@@ -128,6 +130,7 @@ nxc_stream_kernel(const __grid_constant__ StreamMaps maps, const StreamParams p)
   if (warp == 0 && elect_one()) {
     for (int j = 0; j < p.njobs; ++j) {
       prefetch_tensormap(&maps.x[j]);
+      prefetch_tensormap(&maps.xf[j]);
       prefetch_tensormap(&maps.p[j]);
     }
     for (int s = 0; s < kStages; ++s) {
@@ -170,26 +173,31 @@ nxc_stream_kernel(const __grid_constant__ StreamMaps maps, const StreamParams p)
             mbar_wait(bar_raw_empty + 8 * stage, phase ^ 1);
             const uint32_t rf = bar_raw_full + 8 * stage;
             mbar_arrive_expect_tx(rf, 2u * (uint32_t)t.ng * kGrpBytes);
-            for (int g = 0; g < t.ng; ++g) {
-              tma_load_2d_hint(st + g * kGrpBytes, &maps.x[j], rf, c * kBK, t.row0 + g * kGrpRows, stream_pol);
-              tma_load_2d_hint(st + kRawBytes / 2 + g * kGrpBytes, &maps.x[j], rf, c * kBK + 32,
-                               t.row0 + g * kGrpRows, stream_pol);
+            if (t.ng == kRows / kGrpRows) {
+              tma_load_2d_hint(st, &maps.xf[j], rf, c * kBK, t.row0, stream_pol);
+              tma_load_2d_hint(st + kRawBytes / 2, &maps.xf[j], rf, c * kBK + 32, t.row0, stream_pol);
+            } else {
+              for (int g = 0; g < t.ng; ++g) {
+                tma_load_2d_hint(st + g * kGrpBytes, &maps.x[j], rf, c * kBK, t.row0 + g * kGrpRows, stream_pol);
+                tma_load_2d_hint(st + kRawBytes / 2 + g * kGrpBytes, &maps.x[j], rf, c * kBK + 32,
+                                 t.row0 + g * kGrpRows, stream_pol);
+              }
             }
             mbar_wait(bar_op_empty + 8 * stage, phase ^ 1);
             const uint32_t pf = bar_p_full + 8 * stage;
             mbar_arrive_expect_tx(pf, p_tx);
-            for (int b = 0; b < jb.p_planes; ++b)
-              tma_load_2d_hint(st + kOffP + b * (kMaxCls * kBK * 2), &maps.p[j], pf, c * kBK, b * jb.cp,
-                               keep_pol);
+            tma_load_2d_hint(st + kOffP, &maps.p[j], pf, c * kBK, 0, keep_pol);
           } else {
             mbar_wait(bar_op_empty + 8 * stage, phase ^ 1);
             const uint32_t of = bar_op_full + 8 * stage;
             mbar_arrive_expect_tx(of, (uint32_t)t.ng * kGrpBytes + p_tx);
-            for (int g = 0; g < t.ng; ++g)
-              tma_load_2d_hint(st + g * kGrpBytes, &maps.x[j], of, c * kBK, t.row0 + g * kGrpRows, stream_pol);
-            for (int b = 0; b < jb.p_planes; ++b)
-              tma_load_2d_hint(st + kOffP + b * (kMaxCls * kBK * 2), &maps.p[j], of, c * kBK, b * jb.cp,
-                               keep_pol);
+            if (t.ng == kRows / kGrpRows) {
+              tma_load_2d_hint(st, &maps.xf[j], of, c * kBK, t.row0, stream_pol);
+            } else {
+              for (int g = 0; g < t.ng; ++g)
+                tma_load_2d_hint(st + g * kGrpBytes, &maps.x[j], of, c * kBK, t.row0 + g * kGrpRows, stream_pol);
+            }
+            tma_load_2d_hint(st + kOffP, &maps.p[j], of, c * kBK, 0, keep_pol);
           }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
@@ -227,7 +235,7 @@ nxc_stream_kernel(const __grid_constant__ StreamMaps maps, const StreamParams p)
             const int acc_id = (pa[q] | pb[q]) == 0 ? third : 3;
             const uint32_t tmem_d = tmem_base + buf * kBufCols + acc_id * kAccCols;
             const uint64_t da0 = make_smem_desc_sw128(st + kOffPlanes + pa[q] * kPlaneBytes, 16, 1024);
-            const uint64_t db0 = make_smem_desc_sw128(st + kOffP + pb[q] * (kMaxCls * kBK * 2), 16, 1024);
+            const uint64_t db0 = make_smem_desc_sw128(st + kOffP + pb[q] * (jb.cp * kBK * 2), 16, 1024);
 #pragma unroll
             for (int k = 0; k < kBK / 16; ++k) {
               mma_ss(tmem_d, da0 + (uint64_t)(k * 2), db0 + (uint64_t)(k * 2), idesc, (used >> acc_id) & 1u);
@@ -489,26 +497,30 @@ extern "C" int latte_nxc_multi(const latte_nxc_job_t* jobs, int njobs, void* str
     jb.argmax_out = in.argmax_out; jb.margin_out = in.margin_out; jb.top1_out = in.top1_out;
     (in.x_dtype == LATTE_F32 ? convert : direct) = true;
     const int64_t dim_pad = (int64_t)jb.kch * kBK;
-    int rc;
-    if (in.x_dtype == LATTE_F32)
-      rc = stream_make_map(&maps.x[j], in.x, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, in.n, in.dim, in.ldx, 32, kGrpRows);
-    else
-      rc = stream_make_map(&maps.x[j], in.x, in.x_dtype == LATTE_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
-                                                                      : CU_TENSOR_MAP_DATA_TYPE_FLOAT16,
-                           2, in.n, in.dim, in.ldx, kBK, kGrpRows);
+    int rc = LATTE_OK;
+    for (int full = 0; full < 2 && !rc; ++full) {
+      CUtensorMap* m = full ? &maps.xf[j] : &maps.x[j];
+      const int box_rows = full ? kRows : kGrpRows;
+      if (in.x_dtype == LATTE_F32)
+        rc = stream_make_map(m, in.x, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, in.n, in.dim, in.ldx, 32, box_rows);
+      else
+        rc = stream_make_map(m, in.x, in.x_dtype == LATTE_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+                                                                : CU_TENSOR_MAP_DATA_TYPE_FLOAT16,
+                             2, in.n, in.dim, in.ldx, kBK, box_rows);
+    }
     if (rc) return rc;
     if (in.x_dtype == LATTE_BF16)
       rc = stream_make_map(&maps.p[j], in.planes, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, 3 * (int64_t)jb.cp,
-                           dim_pad, dim_pad, kBK, jb.cp);
+                           dim_pad, dim_pad, kBK, 3 * jb.cp);
     else
       rc = stream_make_map(&maps.p[j], static_cast<const char*>(in.planes) + (size_t)3 * jb.cp * dim_pad * 2,
-                           CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, 2 * (int64_t)jb.cp, dim_pad, dim_pad, kBK, jb.cp);
+                           CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, 2 * (int64_t)jb.cp, dim_pad, dim_pad, kBK, 2 * jb.cp);
     if (rc) return rc;
   }
   // one launch handles one operand class: all jobs 16-bit (rows are MMA operands as they are) or all
   // fp32 (converting)
   if (convert && direct) return LATTE_ERR_UNSUPPORTED;
-  for (int j = njobs; j < kMaxJobs; ++j) { maps.x[j] = maps.x[0]; maps.p[j] = maps.p[0]; }
+  for (int j = njobs; j < kMaxJobs; ++j) { maps.x[j] = maps.x[0]; maps.xf[j] = maps.xf[0]; maps.p[j] = maps.p[0]; }
   p.total_groups = groups;
   int grid = device_sm_count();
   if (grid > groups) grid = groups;
