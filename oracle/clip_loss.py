@@ -13,8 +13,8 @@ building, for every rank, exactly the tensors that rank would see after
 per-rank losses before a single ``backward`` -- the leaf gradients are then what the
 reference's all_gather backward (a reduce-scatter SUM) delivers to each rank.
 SURVEY.md appendix B probe 5 checked this emulation against a real 4-process gloo run
-of the reference; tests/test_oracle_vs_reference.py repeats that check when the
-reference is mounted.
+of the reference; tests/golden/make_golden.py records the reference's gloo runs (2 and 4
+processes) and tests/test_oracle_golden.py holds this emulation to them.
 """
 
 from __future__ import annotations
