@@ -671,12 +671,13 @@ def parity_check(loss_fn, il, tl, log_s, rank, world, dev, n_rows=64):
             "ok": bool(ok)}
 
 
-def weak_scaling_point(lb, rank, world, dev, steps):
-    """SURVEY 8d's weak-scaling datum: WEAK_ROWS_PER_GPU rows per GPU (global batch = rows * W),
-    per-GPU credited FLOP/s = 6 n N D / t, beside the same GPU running the one-rank problem
-    (n = N = WEAK_ROWS_PER_GPU) so the efficiency refers to the same box."""
+def weak_scaling_point(lb, rank, world, dev, steps, rows=WEAK_ROWS_PER_GPU):
+    """SURVEY 8d's weak-scaling datum: `rows` rows per GPU (global batch = rows * W), per-GPU credited
+    FLOP/s = 6 n N D / t, beside the same GPU running the one-rank problem (n = N = rows) so the
+    efficiency refers to the same box.  rows = 4096 is SURVEY 8d's operating point (launch-bound on one
+    GPU); rows = 32768 keeps the headline per-GPU batch fixed while the global batch grows to 32768 W."""
     import torch.distributed as dist
-    n = WEAK_ROWS_PER_GPU
+    n = rows
     n_glob = n * world
     sets = []
     for sidx in range(4):
@@ -960,6 +961,17 @@ def _run_ours(args):
     }
 
     weak = weak_scaling_point(lb, rank, world, dev, args.steps)
+    # the same at the headline per-GPU batch (32768 rows per GPU, global batch 32768 W): at W = 1 it
+    # is the main measurement itself
+    if world > 1:
+        from latteclip_b200 import _lib as _l
+        _l.clear_workspace_cache()
+        torch.cuda.empty_cache()
+        weak_big = weak_scaling_point(lb, rank, world, dev, min(args.steps, 5), rows=N_GLOBAL)
+        _l.clear_workspace_cache()
+        torch.cuda.empty_cache()
+    else:
+        weak_big = None
 
     # ---- prototype / pseudo-label kernels (HBM-bound rows of SURVEY 8a): achieved GB/s ------
     proto = None
@@ -1011,6 +1023,13 @@ def _run_ours(args):
             "gpu_launches": launches_per_step * args.steps,
             "clocks": clocks, "roofline": roofline, "parity": parity, "weak_scaling": weak,
         }
+        if weak_big is not None:
+            line["weak_scaling_32k_per_gpu"] = weak_big
+        else:
+            line["weak_scaling_32k_per_gpu"] = {
+                "rows_per_gpu": N_GLOBAL, "global_batch": N_GLOBAL, "ms_per_step": ms_step,
+                "efficiency_vs_single_gpu": 1.0,
+                "definition": "the headline step itself at W = 1 (see the same key at N > 1)"}
         if cpu_base is not None:
             line["cpu_baseline"] = cpu_base
         if proto is not None:
