@@ -180,7 +180,11 @@ def test_update_bank(b, d, c):
 
 
 @pytest.mark.parametrize("b,d,c,dtype", [(32768, 512, 47, torch.float32), (32768, 512, 47, torch.bfloat16),
-                                         (20011, 768, 64, torch.float32), (3000, 512, 100, torch.float32)])
+                                         (20011, 768, 64, torch.float32), (3000, 512, 100, torch.float32),
+                                         # > 992 columns: two columns per consumer thread
+                                         (1500, 1024, 20, torch.float32), (777, 1536, 12, torch.float16),
+                                         # fewer rows than chunks; one class only
+                                         (37, 512, 47, torch.float32), (4096, 256, 2, torch.bfloat16)])
 def test_streaming_class_sums_at_headline_batch(b, d, c, dtype):
     """The one-pass per-class sums (cls_stream_kernel: [C, D] accumulator in shared memory, fixed row
     chunks) behind latte_bank_accumulate and latte_mix_ema_bwd at the headline batch: values against
@@ -475,6 +479,36 @@ def test_nxc_multi_one_launch_matches_fp64(dtype, n, d, c):
     tk2 = refs[2].topk(2, dim=1)
     ok = (tk2.values[:, 0] - tk2.values[:, 1]) > 4e-7
     assert torch.equal(outs[2][0][ok], tk2.indices[:, 0][ok])
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
+def test_nxc_multi_fp16_planes_on_wide_dynamic_range(dtype):
+    """fp32 values enter the tensor core as two fp16 planes, v = h0 + 2^-11 h1 (the low plane stored times
+    2^11 so that it stays out of fp16's subnormal range).  Rows whose entries span seven decades and
+    prototypes of norm 0.01 .. 30 must still give fp32-accurate dots: the error bound is relative to
+    |x| . |p|, as for an fp32 FMA loop (train.py:410-411 runs on whatever the towers emit)."""
+    from latteclip_b200 import _lib
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(5)
+    n, d, c = 3000, 512, 47
+    mag = 10.0 ** (-7.0 * torch.rand(n, d, generator=g))              # entries from 1e-7 to 1
+    x = (torch.randn(n, d, generator=g) * mag)
+    if dtype == torch.float16:
+        x = x.clamp(-6e4, 6e4)
+    x = x.to(dev).to(dtype)
+    protos = torch.randn(c, d, generator=g) * (10.0 ** (torch.rand(c, 1, generator=g) * 3.5 - 2.0)) / d ** 0.5
+    protos = protos.to(dev)
+    planes = _lib.nxc_split_prototypes(protos)
+    (am, mg, t1), = _lib.nxc_multi([dict(x=x, planes=planes, scale=1.0, argmax=True, margin=True, top1=True)])
+    ref = x.double() @ protos.double().T
+    bound = x.double().norm(dim=1, keepdim=True) * protos.double().norm(dim=1)[None, :]      # |x| |p|
+    top = ref.topk(2, dim=1)
+    err = (t1.double() - top.values[:, 0]).abs() / bound.gather(1, top.indices[:, :1]).squeeze(1)
+    assert float(err.max()) < 2e-7, float(err.max())
+    gap = (top.values[:, 0] - top.values[:, 1]) / bound.max(dim=1).values
+    clear = gap > 1e-6
+    assert torch.equal(am[clear], top.indices[:, 0][clear])
+    assert int(clear.sum()) > n // 2
 
 
 def test_step_similarities_one_launch_equals_per_product_kernels():
