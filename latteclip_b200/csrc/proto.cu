@@ -113,50 +113,58 @@ __device__ __forceinline__ float mix_one(float wl, float l, float p, float wi, f
   return m + alpha * (mix - m);
 }
 
+// One WARP per row, persistent grid (4 CTAs of 8 warps per SM): a row needs two dependent global round
+// trips (ids and weights, then the table / feature rows), and one 128-thread CTA per row (32768 CTAs of
+// one iteration each) left that latency exposed at every CTA wave -- 16-bit rows took the same time as
+// fp32 rows.  A lane issues the loads of all its 4-element pieces of the row before the arithmetic.
 template <int DT>
-__global__ void __launch_bounds__(128) mix_ema_fwd_kernel(MixArgs a) {
-  const int64_t i = blockIdx.x;
-  // ids index the [C, D] tables: clamp them so that a bad id (a stale pickled feature record) cannot
-  // read out of bounds; the class sums drop such ids, the reference would raise KeyError
-  const int64_t cp = min(max(a.preds[i], (int64_t)0), a.num_classes - 1);
-  const int64_t cz = min(max(a.zs[i], (int64_t)0), a.num_classes - 1);
-  const float wl_row = a.w_lbl[i], wi = a.w_img[i], wg = a.w_grp[i];
-  const float tot = wl_row + wi + wg;              // train.py:472
-  const float tot_zs = a.w_lbl_zs[i] + wi + wg;    // train.py:473
+__global__ void __launch_bounds__(256, 4) mix_ema_fwd_kernel(MixArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
   const bool quirk = a.label_axis == LATTE_LABEL_AXIS_QUIRK;
-  if (a.vec) {
-    for (int64_t d = (int64_t)threadIdx.x * 4; d < a.dim; d += (int64_t)blockDim.x * 4) {
-      const float4 lf = ld4t<DT>(a.class_text, cp * a.ld_ct + d);
-      const float4 lz = ld4t<DT>(a.class_text, cz * a.ld_ct + d);
-      const float4 p = ld4t<DT>(a.per_image, i * a.ld_pi + d);
-      const float4 g = ld4t<DT>(a.per_group, i * a.ld_pg + d);
-      const float4 mf = __ldg(reinterpret_cast<const float4*>(a.bank + cp * a.ld_bank + d));
-      const float4 mz = __ldg(reinterpret_cast<const float4*>(a.bank + cz * a.ld_bank + d));
-      float4 wl = make_float4(wl_row, wl_row, wl_row, wl_row);
-      if (quirk) wl = __ldg(reinterpret_cast<const float4*>(a.w_lbl + d));
-      float4 of, oz;
-      of.x = mix_one(wl.x, lf.x, p.x, wi, g.x, wg, tot, mf.x, a.alpha);
-      of.y = mix_one(wl.y, lf.y, p.y, wi, g.y, wg, tot, mf.y, a.alpha);
-      of.z = mix_one(wl.z, lf.z, p.z, wi, g.z, wg, tot, mf.z, a.alpha);
-      of.w = mix_one(wl.w, lf.w, p.w, wi, g.w, wg, tot, mf.w, a.alpha);
-      oz.x = mix_one(wl.x, lz.x, p.x, wi, g.x, wg, tot_zs, mz.x, a.alpha);
-      oz.y = mix_one(wl.y, lz.y, p.y, wi, g.y, wg, tot_zs, mz.y, a.alpha);
-      oz.z = mix_one(wl.z, lz.z, p.z, wi, g.z, wg, tot_zs, mz.z, a.alpha);
-      oz.w = mix_one(wl.w, lz.w, p.w, wi, g.w, wg, tot_zs, mz.w, a.alpha);
-      st4t<DT>(a.t_ft, i * a.ld_out + d, of);
-      st4t<DT>(a.t_zs, i * a.ld_out + d, oz);
-    }
-  } else {
-    for (int64_t d = threadIdx.x; d < a.dim; d += blockDim.x) {
-      const float wl = quirk ? a.w_lbl[d] : wl_row;
-      const float p = ld1(a.per_image, i * a.ld_pi + d, a.dtype);
-      const float g = ld1(a.per_group, i * a.ld_pg + d, a.dtype);
-      const float of = mix_one(wl, ld1(a.class_text, cp * a.ld_ct + d, a.dtype), p, wi, g, wg, tot,
-                               a.bank[cp * a.ld_bank + d], a.alpha);
-      const float oz = mix_one(wl, ld1(a.class_text, cz * a.ld_ct + d, a.dtype), p, wi, g, wg, tot_zs,
-                               a.bank[cz * a.ld_bank + d], a.alpha);
-      st1(a.t_ft, i * a.ld_out + d, a.dtype, of);
-      st1(a.t_zs, i * a.ld_out + d, a.dtype, oz);
+  for (int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < a.batch; i += nwarps) {
+    // ids index the [C, D] tables: clamp them so that a bad id (a stale pickled feature record) cannot
+    // read out of bounds; the class sums drop such ids, the reference would raise KeyError
+    const int64_t cp = min(max(a.preds[i], (int64_t)0), a.num_classes - 1);
+    const int64_t cz = min(max(a.zs[i], (int64_t)0), a.num_classes - 1);
+    const float wl_row = a.w_lbl[i], wi = a.w_img[i], wg = a.w_grp[i];
+    const float tot = wl_row + wi + wg;              // train.py:472
+    const float tot_zs = a.w_lbl_zs[i] + wi + wg;    // train.py:473
+    if (a.vec) {
+#pragma unroll 1
+      for (int64_t d = (int64_t)lane * 4; d < a.dim; d += 128) {
+        const float4 lf = ld4t<DT>(a.class_text, cp * a.ld_ct + d);
+        const float4 lz = ld4t<DT>(a.class_text, cz * a.ld_ct + d);
+        const float4 p = ld4t<DT>(a.per_image, i * a.ld_pi + d);
+        const float4 g = ld4t<DT>(a.per_group, i * a.ld_pg + d);
+        const float4 mf = __ldg(reinterpret_cast<const float4*>(a.bank + cp * a.ld_bank + d));
+        const float4 mz = __ldg(reinterpret_cast<const float4*>(a.bank + cz * a.ld_bank + d));
+        float4 wl = make_float4(wl_row, wl_row, wl_row, wl_row);
+        if (quirk) wl = __ldg(reinterpret_cast<const float4*>(a.w_lbl + d));
+        float4 of, oz;
+        of.x = mix_one(wl.x, lf.x, p.x, wi, g.x, wg, tot, mf.x, a.alpha);
+        of.y = mix_one(wl.y, lf.y, p.y, wi, g.y, wg, tot, mf.y, a.alpha);
+        of.z = mix_one(wl.z, lf.z, p.z, wi, g.z, wg, tot, mf.z, a.alpha);
+        of.w = mix_one(wl.w, lf.w, p.w, wi, g.w, wg, tot, mf.w, a.alpha);
+        oz.x = mix_one(wl.x, lz.x, p.x, wi, g.x, wg, tot_zs, mz.x, a.alpha);
+        oz.y = mix_one(wl.y, lz.y, p.y, wi, g.y, wg, tot_zs, mz.y, a.alpha);
+        oz.z = mix_one(wl.z, lz.z, p.z, wi, g.z, wg, tot_zs, mz.z, a.alpha);
+        oz.w = mix_one(wl.w, lz.w, p.w, wi, g.w, wg, tot_zs, mz.w, a.alpha);
+        st4t<DT>(a.t_ft, i * a.ld_out + d, of);
+        st4t<DT>(a.t_zs, i * a.ld_out + d, oz);
+      }
+    } else {
+      for (int64_t d = lane; d < a.dim; d += 32) {
+        const float wl = quirk ? a.w_lbl[d] : wl_row;
+        const float p = ld1(a.per_image, i * a.ld_pi + d, a.dtype);
+        const float g = ld1(a.per_group, i * a.ld_pg + d, a.dtype);
+        const float of = mix_one(wl, ld1(a.class_text, cp * a.ld_ct + d, a.dtype), p, wi, g, wg, tot,
+                                 a.bank[cp * a.ld_bank + d], a.alpha);
+        const float oz = mix_one(wl, ld1(a.class_text, cz * a.ld_ct + d, a.dtype), p, wi, g, wg, tot_zs,
+                                 a.bank[cz * a.ld_bank + d], a.alpha);
+        st1(a.t_ft, i * a.ld_out + d, a.dtype, of);
+        st1(a.t_zs, i * a.ld_out + d, a.dtype, oz);
+      }
     }
   }
 }
@@ -858,9 +866,11 @@ extern "C" int latte_mix_ema_fwd(const void* class_text, int64_t ld_ct, const vo
           (reinterpret_cast<uintptr_t>(per_group) % vb == 0) &&
           (reinterpret_cast<uintptr_t>(t_ft) % vb == 0) && (reinterpret_cast<uintptr_t>(t_zs) % vb == 0);
   cudaStream_t mst = static_cast<cudaStream_t>(stream);
-  if (dtype == LATTE_F32) mix_ema_fwd_kernel<LATTE_F32><<<(unsigned)batch, 128, 0, mst>>>(a);
-  else if (dtype == LATTE_BF16) mix_ema_fwd_kernel<LATTE_BF16><<<(unsigned)batch, 128, 0, mst>>>(a);
-  else mix_ema_fwd_kernel<LATTE_F16><<<(unsigned)batch, 128, 0, mst>>>(a);
+  int64_t mgrid = (batch + 7) / 8;                                   // 8 warps (rows) per CTA
+  if (mgrid > 4 * (int64_t)device_sm_count()) mgrid = 4 * (int64_t)device_sm_count();
+  if (dtype == LATTE_F32) mix_ema_fwd_kernel<LATTE_F32><<<(unsigned)mgrid, 256, 0, mst>>>(a);
+  else if (dtype == LATTE_BF16) mix_ema_fwd_kernel<LATTE_BF16><<<(unsigned)mgrid, 256, 0, mst>>>(a);
+  else mix_ema_fwd_kernel<LATTE_F16><<<(unsigned)mgrid, 256, 0, mst>>>(a);
   LATTE_LAUNCH_OK();
   return LATTE_OK;
 }
