@@ -384,14 +384,15 @@ int latte_nxc_argmax_margin(const void* x, int64_t ldx, int x_dtype,
 /*
  * The step's N x C products as ONE HBM-bound launch (C <= 64, e.g. DTD's 47 classes; SURVEY 2c
  * K8/K9: the pseudo-label argmax of train.py:410-411 and the compute_text_weights margins of
- * train.py:292-303 / :444-449 share a launch).  Prototypes are split once per matrix into three
- * bf16 planes by latte_nxc_split_prototypes -- optionally fused with the row normalisation of
+ * train.py:292-303 / :444-449 share a launch).  Prototypes are split once per matrix into 16-bit
+ * operand planes by latte_nxc_split_prototypes (three bf16 planes for bf16 rows; two fp16 planes,
+ * v = h0 + 2^-11 h1, for fp16 / fp32 rows) -- optionally fused with the row normalisation of
  * train.py:384-389 (normalized_out, nullable, then receives F.normalize(protos) in fp32) -- and
- * every job streams its feature rows exactly once: fp32 / fp16 rows are split into bf16 planes
- * inside the kernel (no materialised copies), bf16 rows are used as they are.  Results are as
- * accurate as an fp32 FMA loop (see latte_nxc_argmax_margin).  All jobs of one call must share
- * the operand class (all bf16, or all fp32 / fp16).  planes: latte_nxc_planes_bytes() bytes,
- * 128-byte aligned, caller-owned.
+ * every job streams its feature rows exactly once: fp32 rows are split into two fp16 planes inside
+ * the kernel (no materialised copies), 16-bit rows are used as they are.  Results are as accurate
+ * as an fp32 FMA loop (see latte_nxc_argmax_margin) for |values| < 65504.  All jobs of one call
+ * must share the operand class (all 16-bit, or all fp32).  planes: latte_nxc_planes_bytes()
+ * bytes, 128-byte aligned, caller-owned.
  */
 typedef struct latte_nxc_job {
   const void* x; int64_t ldx; int x_dtype;     /* [n, dim] feature rows                          */

@@ -741,7 +741,8 @@ class LatteNxcJob(ctypes.Structure):
 
 
 class ProtoPlanes:
-    """bf16 operand planes of one prototype matrix (latte_nxc_split_prototypes)."""
+    """16-bit operand planes of one prototype matrix (latte_nxc_split_prototypes: three bf16 planes for
+    bf16 rows, two fp16 planes for fp16 / fp32 rows)."""
 
     def __init__(self, buf, num_classes, dim, normalized):
         self.buf, self.num_classes, self.dim, self.normalized = buf, num_classes, dim, normalized
@@ -756,7 +757,7 @@ def nxc_multi_supported(x: torch.Tensor, num_classes: int) -> bool:
 
 def nxc_split_prototypes(protos: torch.Tensor, normalize: bool = False,
                          want_normalized: bool = False) -> ProtoPlanes:
-    """fp32 [C, D] prototypes -> bf16 operand planes (once per matrix); ``normalize`` fuses
+    """fp32 [C, D] prototypes -> 16-bit operand planes (once per matrix); ``normalize`` fuses
     F.normalize(protos, dim=1) (train.py:384-389)."""
     protos = _rows(protos.detach().to(torch.float32), "prototypes")
     c, d = protos.shape
@@ -777,7 +778,7 @@ def nxc_split_prototypes(protos: torch.Tensor, normalize: bool = False,
 
 def nxc_multi(jobs):
     """``jobs``: list of dicts {x, planes: ProtoPlanes, scale, argmax, margin, top1 (bools)} sharing
-    one operand class (all bf16, or all fp32 / fp16) -> list of (argmax | None, margin | None,
+    one operand class (all 16-bit, or all fp32) -> list of (argmax | None, margin | None,
     top1 | None) per job, from ONE launch."""
     if not 1 <= len(jobs) <= NXC_MULTI_MAX_JOBS:
         raise RuntimeError("nxc_multi takes 1..4 jobs")

@@ -113,12 +113,12 @@ __device__ __forceinline__ float mix_one(float wl, float l, float p, float wi, f
   return m + alpha * (mix - m);
 }
 
-// One WARP per row, persistent grid (4 CTAs of 8 warps per SM): a row needs two dependent global round
+// One WARP per row, persistent grid (2-4 CTAs of 8 warps per SM): a row needs two dependent global round
 // trips (ids and weights, then the table / feature rows), and one 128-thread CTA per row (32768 CTAs of
 // one iteration each) left that latency exposed at every CTA wave -- 16-bit rows took the same time as
 // fp32 rows.  A lane issues the loads of all its 4-element pieces of the row before the arithmetic.
 template <int DT>
-__global__ void __launch_bounds__(256, 4) mix_ema_fwd_kernel(MixArgs a) {
+__global__ void __launch_bounds__(256, 2) mix_ema_fwd_kernel(MixArgs a) {
   const int lane = threadIdx.x & 31;
   const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
   const bool quirk = a.label_axis == LATTE_LABEL_AXIS_QUIRK;
@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(256, 4) mix_ema_fwd_kernel(MixArgs a) {
     const float tot = wl_row + wi + wg;              // train.py:472
     const float tot_zs = a.w_lbl_zs[i] + wi + wg;    // train.py:473
     if (a.vec) {
-#pragma unroll 1
+#pragma unroll 4
       for (int64_t d = (int64_t)lane * 4; d < a.dim; d += 128) {
         const float4 lf = ld4t<DT>(a.class_text, cp * a.ld_ct + d);
         const float4 lz = ld4t<DT>(a.class_text, cz * a.ld_ct + d);
@@ -867,7 +867,7 @@ extern "C" int latte_mix_ema_fwd(const void* class_text, int64_t ld_ct, const vo
           (reinterpret_cast<uintptr_t>(t_ft) % vb == 0) && (reinterpret_cast<uintptr_t>(t_zs) % vb == 0);
   cudaStream_t mst = static_cast<cudaStream_t>(stream);
   int64_t mgrid = (batch + 7) / 8;                                   // 8 warps (rows) per CTA
-  if (mgrid > 4 * (int64_t)device_sm_count()) mgrid = 4 * (int64_t)device_sm_count();
+  if (mgrid > 2 * (int64_t)device_sm_count()) mgrid = 2 * (int64_t)device_sm_count();   // 2 resident CTAs per SM
   if (dtype == LATTE_F32) mix_ema_fwd_kernel<LATTE_F32><<<(unsigned)mgrid, 256, 0, mst>>>(a);
   else if (dtype == LATTE_BF16) mix_ema_fwd_kernel<LATTE_BF16><<<(unsigned)mgrid, 256, 0, mst>>>(a);
   else mix_ema_fwd_kernel<LATTE_F16><<<(unsigned)mgrid, 256, 0, mst>>>(a);

@@ -86,8 +86,8 @@ def step_similarities(image_features, bank, proto_snapshot, per_image, per_group
                 dict(x=per_group, planes=snap_planes, margin=True),
                 dict(x=class_text, planes=snap_planes, margin=True)]
         res = [None] * 4
-        for direct in (True, False):
-            idx = [k for k, jb in enumerate(jobs) if (jb["x"].dtype == torch.bfloat16) == direct]
+        for direct in (True, False):      # 16-bit rows are MMA operands as they are; fp32 rows are converted
+            idx = [k for k, jb in enumerate(jobs) if (jb["x"].dtype != torch.float32) == direct]
             if idx:
                 for k, out in zip(idx, _lib.nxc_multi([jobs[k] for k in idx])):
                     res[k] = out

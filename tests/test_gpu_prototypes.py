@@ -527,6 +527,16 @@ def test_step_similarities_one_launch_equals_per_product_kernels():
         assert float((preds != ref_preds).float().mean()) < 2e-3
         for got, x in ((m_i, pi), (m_g, pg), (m_c, ct)):
             assert torch.allclose(got, P.text_margins(x, snap), rtol=0, atol=3e-7)
+    # mixed operand classes in one step: fp32 images and class texts (converted in the kernel), fp16 and
+    # bf16 description texts (MMA operands as they are) -> one launch per class
+    img = F.normalize(torch.randn(b, d, generator=g), dim=1).to(dev)
+    pi = F.normalize(torch.randn(b, d, generator=g), dim=1).to(dev).half()
+    pg = F.normalize(torch.randn(b, d, generator=g), dim=1).to(dev).bfloat16()
+    ct = F.normalize(torch.randn(c, d, generator=g), dim=1).to(dev)
+    preds, m_i, m_g, m_c = P.step_similarities(img, bank, snap, pi, pg, ct)
+    assert float((preds != P.pseudo_label(img, P.build_classifier(bank), 100.0)).float().mean()) < 2e-3
+    for got, x in ((m_i, pi), (m_g, pg), (m_c, ct)):
+        assert torch.allclose(got, P.text_margins(x, snap), rtol=0, atol=3e-7)
 
 
 def test_graphed_prototype_step_equals_eager_step():
