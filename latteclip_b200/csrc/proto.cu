@@ -113,16 +113,19 @@ __device__ __forceinline__ float mix_one(float wl, float l, float p, float wi, f
   return m + alpha * (mix - m);
 }
 
-// One WARP per row, persistent grid (2-4 CTAs of 8 warps per SM): a row needs two dependent global round
+// One WARP per row, persistent grid (4 CTAs of 8 warps per SM): a row needs two dependent global round
 // trips (ids and weights, then the table / feature rows), and one 128-thread CTA per row (32768 CTAs of
 // one iteration each) left that latency exposed at every CTA wave -- 16-bit rows took the same time as
 // fp32 rows.  A lane issues the loads of all its 4-element pieces of the row before the arithmetic.
-template <int DT>
-__global__ void __launch_bounds__(256, 2) mix_ema_fwd_kernel(MixArgs a) {
-  const int lane = threadIdx.x & 31;
-  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+// Small batches (the reference's 512) keep one 128-thread CTA per row: a single round of loads.
+template <int DT, bool kWarpRow>
+__global__ void __launch_bounds__(256, 4) mix_ema_fwd_kernel(MixArgs a) {
+  const int lane = kWarpRow ? (threadIdx.x & 31) : threadIdx.x;            // position inside the row team
+  const int team = kWarpRow ? 32 : blockDim.x;                               // threads per row
+  const int64_t nteams = kWarpRow ? (int64_t)gridDim.x * (blockDim.x >> 5) : gridDim.x;
+  const int64_t team0 = kWarpRow ? (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5) : blockIdx.x;
   const bool quirk = a.label_axis == LATTE_LABEL_AXIS_QUIRK;
-  for (int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < a.batch; i += nwarps) {
+  for (int64_t i = team0; i < a.batch; i += nteams) {
     // ids index the [C, D] tables: clamp them so that a bad id (a stale pickled feature record) cannot
     // read out of bounds; the class sums drop such ids, the reference would raise KeyError
     const int64_t cp = min(max(a.preds[i], (int64_t)0), a.num_classes - 1);
@@ -131,8 +134,8 @@ __global__ void __launch_bounds__(256, 2) mix_ema_fwd_kernel(MixArgs a) {
     const float tot = wl_row + wi + wg;              // train.py:472
     const float tot_zs = a.w_lbl_zs[i] + wi + wg;    // train.py:473
     if (a.vec) {
-#pragma unroll 4
-      for (int64_t d = (int64_t)lane * 4; d < a.dim; d += 128) {
+#pragma unroll 1
+      for (int64_t d = (int64_t)lane * 4; d < a.dim; d += (int64_t)team * 4) {
         const float4 lf = ld4t<DT>(a.class_text, cp * a.ld_ct + d);
         const float4 lz = ld4t<DT>(a.class_text, cz * a.ld_ct + d);
         const float4 p = ld4t<DT>(a.per_image, i * a.ld_pi + d);
@@ -154,7 +157,7 @@ __global__ void __launch_bounds__(256, 2) mix_ema_fwd_kernel(MixArgs a) {
         st4t<DT>(a.t_zs, i * a.ld_out + d, oz);
       }
     } else {
-      for (int64_t d = lane; d < a.dim; d += 32) {
+      for (int64_t d = lane; d < a.dim; d += team) {
         const float wl = quirk ? a.w_lbl[d] : wl_row;
         const float p = ld1(a.per_image, i * a.ld_pi + d, a.dtype);
         const float g = ld1(a.per_group, i * a.ld_pg + d, a.dtype);
@@ -464,7 +467,8 @@ template <int DT> __device__ __forceinline__ void st_elem(void* base, int64_t id
 // ids and per-sample factors of 256 samples | class counts | mbarriers.
 constexpr int kClsIdRows = 256;
 constexpr int kClsGrp = 4;
-struct __align__(16) ClsIdA { int p, z; float sc_z, sc_f; };          // class ids, accumulator scales
+struct __align__(16) ClsIdA { int p, z; float sc_z, sc_f; };          // byte offsets of the class rows in the
+                                                                      // accumulator (-1: dropped), scales
 struct __align__(16) ClsIdB { float inv_ft, inv_zs, wi, wg; };        // row-output factors (mixer backward)
 
 // DT: feature dtype; BWD: mixer backward (weighted rows, optional row-shaped outputs); VPT: columns per
@@ -555,8 +559,9 @@ __global__ void __launch_bounds__(1024) cls_stream_kernel(ClsArgs a, int groups,
       const int64_t i = r0 + k0 + t;
       const int64_t p = a.preds[i], z = a.zs[i];
       ClsIdA q;
-      q.p = (p >= 0 && p < a.num_classes) ? (int)p : -1;      // out-of-range ids are dropped
-      q.z = (z >= 0 && z < a.num_classes) ? (int)z : -1;
+      const bool p_ok = p >= 0 && p < a.num_classes, z_ok = z >= 0 && z < a.num_classes;
+      q.p = p_ok ? (int)p * dim * 4 : -1;                     // out-of-range ids are dropped
+      q.z = z_ok ? (int)z * dim * 4 : -1;
       q.sc_z = q.sc_f = 1.f;
       if (BWD) {
         const float wl = a.w_lbl[i], wlz = a.w_lbl_zs[i], wi = a.w_img[i], wg = a.w_grp[i];
@@ -570,8 +575,8 @@ __global__ void __launch_bounds__(1024) cls_stream_kernel(ClsArgs a, int groups,
         idb[t] = f;
       }
       ida[t] = q;
-      if (q.z >= 0) atomicAdd(cnt + q.z, 1);                  // integer counts: order does not matter
-      if (q.p >= 0) atomicAdd(cnt + q.p, 1);
+      if (z_ok) atomicAdd(cnt + (int)z, 1);                   // integer counts: order does not matter
+      if (p_ok) atomicAdd(cnt + (int)p, 1);
     }
     named_bar_sync(1, ncons);
     const int kend = min(rows, k0 + kClsIdRows);
@@ -590,9 +595,7 @@ __global__ void __launch_bounds__(1024) cls_stream_kernel(ClsArgs a, int groups,
       if (lane == 0) mbar_arrive(bar_empty + 8 * s);            // this warp has its copy of the group
       if (++s == groups) { s = 0; phase ^= 1; }
       if (!col_ok) continue;
-#pragma unroll
-      for (int u = 0; u < kClsGrp; ++u) {
-        if (k + u >= kend) break;
+      auto one_sample = [&](int u) {
         const uint4 qa = lds_u4(ida_base + (uint32_t)(k + u - k0) * 16);
         const int qp = (int)qa.x, qz = (int)qa.y;
         const float sc_z = __uint_as_float(qa.z), sc_f = __uint_as_float(qa.w);
@@ -609,14 +612,25 @@ __global__ void __launch_bounds__(1024) cls_stream_kernel(ClsArgs a, int groups,
           }
         }
         if (qz >= 0) {             // entry 2i: the zs-list row first (train.py:524)
-          const uint32_t o = acc_col + (uint32_t)(qz * dim) * 4;
+          const uint32_t o = acc_col + (uint32_t)qz;
 #pragma unroll
           for (int v = 0; v < VPT; ++v) sts_f32(o + 4 * v, fmaf(gz[u][v], sc_z, lds_f32(o + 4 * v)));
         }
         if (qp >= 0) {             // entry 2i + 1: the ft-list row (train.py:525)
-          const uint32_t o = acc_col + (uint32_t)(qp * dim) * 4;
+          const uint32_t o = acc_col + (uint32_t)qp;
 #pragma unroll
           for (int v = 0; v < VPT; ++v) sts_f32(o + 4 * v, fmaf(gf[u][v], sc_f, lds_f32(o + 4 * v)));
+        }
+      };
+      if (k + kClsGrp <= kend) {
+#pragma unroll
+        for (int u = 0; u < kClsGrp; ++u) one_sample(u);
+      } else {
+        for (int u = 0; u < kend - k; ++u) {
+          // a partial group at the end of the chunk: select the row by index (no dynamic register indexing)
+          if (u == 0) one_sample(0);
+          else if (u == 1) one_sample(1);
+          else one_sample(2);
         }
       }
     }
@@ -866,11 +880,17 @@ extern "C" int latte_mix_ema_fwd(const void* class_text, int64_t ld_ct, const vo
           (reinterpret_cast<uintptr_t>(per_group) % vb == 0) &&
           (reinterpret_cast<uintptr_t>(t_ft) % vb == 0) && (reinterpret_cast<uintptr_t>(t_zs) % vb == 0);
   cudaStream_t mst = static_cast<cudaStream_t>(stream);
-  int64_t mgrid = (batch + 7) / 8;                                   // 8 warps (rows) per CTA
-  if (mgrid > 2 * (int64_t)device_sm_count()) mgrid = 2 * (int64_t)device_sm_count();   // 2 resident CTAs per SM
-  if (dtype == LATTE_F32) mix_ema_fwd_kernel<LATTE_F32><<<(unsigned)mgrid, 256, 0, mst>>>(a);
-  else if (dtype == LATTE_BF16) mix_ema_fwd_kernel<LATTE_BF16><<<(unsigned)mgrid, 256, 0, mst>>>(a);
-  else mix_ema_fwd_kernel<LATTE_F16><<<(unsigned)mgrid, 256, 0, mst>>>(a);
+  if (batch >= 8192) {
+    int64_t mgrid = (batch + 7) / 8;                                   // 8 warps (rows) per CTA
+    if (mgrid > 4 * (int64_t)device_sm_count()) mgrid = 4 * (int64_t)device_sm_count();
+    if (dtype == LATTE_F32) mix_ema_fwd_kernel<LATTE_F32, true><<<(unsigned)mgrid, 256, 0, mst>>>(a);
+    else if (dtype == LATTE_BF16) mix_ema_fwd_kernel<LATTE_BF16, true><<<(unsigned)mgrid, 256, 0, mst>>>(a);
+    else mix_ema_fwd_kernel<LATTE_F16, true><<<(unsigned)mgrid, 256, 0, mst>>>(a);
+  } else {
+    if (dtype == LATTE_F32) mix_ema_fwd_kernel<LATTE_F32, false><<<(unsigned)batch, 128, 0, mst>>>(a);
+    else if (dtype == LATTE_BF16) mix_ema_fwd_kernel<LATTE_BF16, false><<<(unsigned)batch, 128, 0, mst>>>(a);
+    else mix_ema_fwd_kernel<LATTE_F16, false><<<(unsigned)batch, 128, 0, mst>>>(a);
+  }
   LATTE_LAUNCH_OK();
   return LATTE_OK;
 }
