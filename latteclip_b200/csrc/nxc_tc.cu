@@ -3,11 +3,16 @@
 // Replaces the fp32 SIMT tile kernel of nxc.cu for large problems (train.py:410-411,
 // compute_text_weights train.py:292-303, zero_shot.py:14-20,40).  Pseudo-labels must be exact
 // wherever the reference's fp32 GEMM has no tie and margins are differences of near-equal
-// dot products, so a plain bf16 MMA is not accurate enough.  Both operands are therefore
-// split into bf16 planes v = b0 + b1 + b2 (8 + 8 + 8 significand bits: exact for fp32) and
-// the product is accumulated in fp32 (TMEM) from every plane pair (a, b) with a + b <= 2:
-//     x.p = x0.p0 + x0.p1 + x1.p0 + x0.p2 + x2.p0 + x1.p1      (dropped terms < 2^-24 |x||p|)
-// bf16 features need one x plane (3 MMAs), fp16 features two (5 MMAs), fp32 three (6 MMAs).
+// dot products, so a plain 16-bit MMA is not accurate enough.  Operands are split into 16-bit
+// planes and the plane products are accumulated in fp32 (TMEM):
+//   bf16 rows: x is its own plane, p = b0 + b1 + b2 in bf16 (8 + 8 + 8 significand bits, exact):
+//              x.p = x.b0 + x.b1 + x.b2                                         (3 MMAs)
+//   fp16 / fp32 rows: fp16 planes v = h0 + 2^-11 h1 (11 + 11 bits + sign trick: the residual after
+//              two planes is <= 2^-24 |v|; the low plane is stored times 2^11 to stay clear of
+//              fp16's subnormals; |v| < 65504): x.p = x0.p0 + x0.p1 + x1.p0      (3 MMAs for fp32
+//              rows, 2 for fp16 rows which are their own plane; the x1.p1 term is < 2^-22 |x||p|).
+// Round 1 used three bf16 planes for every input (6 MMAs for fp32 rows, 5 for fp16): this kernel is
+// tensor-bound from C ~ 400, so half the MMAs is half the time.
 // The tensor core truncates its fp32 accumulator on every MMA (measured: a bias of ~-3e-7 on
 // unit-norm dots after 192 accumulations), so the large term x0.p0 is spread over three TMEM
 // accumulators (thirds of the feature axis), the small terms go to a fourth, and the epilogue
@@ -48,7 +53,7 @@ __device__ __forceinline__ float load_as_float(const void* base, int64_t idx, in
 // eight consecutive features per thread: 16-byte stores into every plane
 __global__ void __launch_bounds__(256)
 nxc_split_planes_kernel(const void* src, int64_t ld, int dtype, const int64_t* row_index,
-                        int64_t rows, int64_t dim, int64_t dim_pad, int planes,
+                        int64_t rows, int64_t dim, int64_t dim_pad, int planes, int fp16_planes,
                         __nv_bfloat16* out, int vec_ok) {
   const int64_t per_row = dim_pad / 8;
   const int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x;
@@ -63,6 +68,23 @@ nxc_split_planes_kernel(const void* src, int64_t ld, int dtype, const int64_t* r
   } else {
 #pragma unroll
     for (int e = 0; e < 8; ++e) v[e] = d0 + e < dim ? load_as_float(src, sr * ld + d0 + e, dtype) : 0.f;
+  }
+  if (fp16_planes) {
+    // h0 = fp16(v), h1 = fp16(2^11 (v - h0)): the residual is exact in fp32
+    for (int p = 0; p < planes; ++p) {
+      uint4 o;
+      __half2* h = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const __half2 b = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
+        h[e] = b;
+        const float2 f = __half22float2(b);
+        v[2 * e] = (v[2 * e] - f.x) * 2048.f;
+        v[2 * e + 1] = (v[2 * e + 1] - f.y) * 2048.f;
+      }
+      *reinterpret_cast<uint4*>(out + ((int64_t)p * rows + r) * dim_pad + d0) = o;
+    }
+    return;
   }
   for (int p = 0; p < planes; ++p) {
     uint4 o;
@@ -82,7 +104,9 @@ nxc_split_planes_kernel(const void* src, int64_t ld, int dtype, const int64_t* r
 struct NxcTcParams {
   int64_t n, num_classes;
   int kch;                 // ceil(dim / 64)
-  int x_planes;            // 1, 2 or 3
+  int x_planes;            // 1 (bf16 / fp16 rows) or 2 (fp32 rows)
+  int p_planes;            // 3 bf16 planes (bf16 rows) or 2 fp16 planes
+  int ab_fmt;              // MMA operand format: 1 bf16, 0 fp16
   int passes;              // ceil(C / 128)
   float scale;
   int64_t* argmax_out; float* margin_out; float* top1_out;
@@ -138,7 +162,7 @@ nxc_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ C
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
     if (elect_one()) {
-      const uint32_t tx = (uint32_t)(nplanes_x + 3) * kPlaneBytes;
+      const uint32_t tx = (uint32_t)(nplanes_x + p.p_planes) * kPlaneBytes;
       int stage = 0;
       uint32_t phase = 0;
       for (int pass = 0; pass < p.passes; ++pass) {
@@ -149,7 +173,7 @@ nxc_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ C
           mbar_arrive_expect_tx(full, tx);
           for (int a = 0; a < nplanes_x; ++a)
             tma_load_2d(sa + a * kPlaneBytes, &tmx, full, c * kBK, (int32_t)(a * p.n + row0));
-          for (int b = 0; b < 3; ++b)
+          for (int b = 0; b < p.p_planes; ++b)
             tma_load_2d(sa + (3 + b) * kPlaneBytes, &tmp, full, c * kBK,
                         (int32_t)(b * p.num_classes + pass * kCls));
           if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -159,15 +183,16 @@ nxc_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ C
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
     if (elect_one()) {
-      // plane pairs (a, b) with a + b <= 2, small terms first
-      const int pa[6] = {2, 1, 0, 1, 0, 0};
-      const int pb[6] = {0, 1, 2, 0, 1, 0};
+      // plane pairs (a, b), small terms first; (0, 0) goes to the accumulator of the chunk's third,
+      // every other pair to accumulator 3 (rescaled by 2^-11 in the epilogue for fp16 planes)
+      const int pa[4] = {0, 0, 1, 0};
+      const int pb[4] = {2, 1, 0, 0};
       int stage = 0;
       uint32_t phase = 0;
       for (int pass = 0; pass < p.passes; ++pass) {
         const int64_t left = p.num_classes - (int64_t)pass * kCls;
         const int ncols = (int)(left >= kCls ? kCls : (left + 15) / 16 * 16);
-        const uint32_t idesc = make_idesc_f16(kRows, ncols, 1u, 0, 0);
+        const uint32_t idesc = make_idesc_f16(kRows, ncols, (uint32_t)p.ab_fmt, 0, 0);
         mbar_wait(bar_tempty, (pass & 1) ^ 1);
         tc_fence_after();
         uint32_t used = 0;                 // bit a: accumulator a already holds a partial sum
@@ -176,8 +201,8 @@ nxc_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ C
           tc_fence_after();
           const uint32_t sa = smem_base + stage * kStageBytes;
           const int third = (c * 3) / p.kch;          // accumulator of the x0.p0 term
-          for (int q = 0; q < 6; ++q) {
-            if (pa[q] >= nplanes_x) continue;
+          for (int q = 0; q < 4; ++q) {
+            if (pa[q] >= nplanes_x || pb[q] >= p.p_planes) continue;
             const int acc_id = (pa[q] | pb[q]) == 0 ? third : 3;
             const uint32_t tmem_d = tmem_base + acc_id * kCls;
             const uint64_t da0 = make_smem_desc_sw128(sa + pa[q] * kPlaneBytes, 16, 1024);
@@ -202,6 +227,7 @@ nxc_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ C
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     float v1 = -INFINITY, v2 = -INFINITY;
     int i1 = 0;
+    const float lo_scale = p.ab_fmt == 0 ? 1.f / 2048.f : 1.f;   // fp16 planes: the low plane is stored times 2^11
     float tv[kTopK ? kMaxTopK : 1];
     int ti[kTopK ? kMaxTopK : 1];
     if (kTopK) {
@@ -225,7 +251,7 @@ nxc_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ C
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           float s = 0.f;                       // small terms first, round-to-nearest adds
-          if ((used >> 3) & 1u) s = __uint_as_float(r[3][j]);
+          if ((used >> 3) & 1u) s = __uint_as_float(r[3][j]) * lo_scale;
           if ((used >> 2) & 1u) s += __uint_as_float(r[2][j]);
           if ((used >> 1) & 1u) s += __uint_as_float(r[1][j]);
           if (used & 1u) s += __uint_as_float(r[0][j]);
@@ -294,14 +320,15 @@ EncodeTiledFn nxc_encode_fn() {
 }
 
 // bf16 [rows, cols] row-major (pitch ld) -> boxes [128 rows x 64 cols], 128B swizzle, OOB = 0
-int nxc_make_map(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld) {
+int nxc_make_map(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, bool fp16 = false) {
   EncodeTiledFn fn = nxc_encode_fn();
   if (!fn) return LATTE_ERR_CUDA;
   cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
   cuuint32_t box[2] = {64u, 128u};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride,
+  CUresult r = fn(map, fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                  const_cast<void*>(base), gdim, gstride,
                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? LATTE_OK : LATTE_ERR_CUDA;
@@ -310,17 +337,18 @@ int nxc_make_map(CUtensorMap* map, const void* base, int64_t rows, int64_t cols,
 }  // namespace
 
 namespace {
-struct NxcWsLayout { size_t x_elems, x_al, p_elems, total; int64_t dim_pad; int x_planes; bool direct_x; };
+struct NxcWsLayout { size_t x_elems, x_al, p_elems, total; int64_t dim_pad; int x_planes, p_planes; bool direct_x; };
 NxcWsLayout nxc_ws_layout(const void* x, int64_t ldx, int x_dtype, bool gathered, int64_t n, int64_t dim,
                           int64_t num_classes) {
   NxcWsLayout w;
   w.dim_pad = (dim + kBK - 1) / kBK * kBK;
   // x == NULL (size query): assume the planes of x have to be materialised unless bf16 rows are used as is
-  w.direct_x = x_dtype == LATTE_BF16 && !gathered && (ldx % 8) == 0 &&
-               (reinterpret_cast<uintptr_t>(x) & 15) == 0;
-  w.x_planes = x_dtype == LATTE_BF16 ? 1 : (x_dtype == LATTE_F16 ? 2 : 3);
+  w.direct_x = x_dtype != LATTE_F32 && !gathered && (ldx % 8) == 0 &&
+               (reinterpret_cast<uintptr_t>(x) & 15) == 0;          // 16-bit rows are MMA operands as they are
+  w.x_planes = x_dtype == LATTE_F32 ? 2 : 1;
+  w.p_planes = x_dtype == LATTE_BF16 ? 3 : 2;
   w.x_elems = w.direct_x ? 0 : (size_t)w.x_planes * (size_t)n * (size_t)w.dim_pad;
-  w.p_elems = (size_t)3 * (size_t)num_classes * (size_t)w.dim_pad;
+  w.p_elems = (size_t)w.p_planes * (size_t)num_classes * (size_t)w.dim_pad;
   w.x_al = (w.x_elems + 127) / 128 * 128;
   w.total = (w.x_al + w.p_elems) * sizeof(__nv_bfloat16);
   return w;
@@ -342,6 +370,7 @@ int nxc_tc_run(const void* x, int64_t ldx, int x_dtype, const int64_t* row_index
                float* topk_val, void* workspace, size_t workspace_bytes, cudaStream_t st) {
   // plane row offsets are 32-bit TMA coordinates
   if (3 * n >= (1ll << 31) || 3 * num_classes >= (1ll << 31)) return LATTE_ERR_UNSUPPORTED;
+  const int fp16_planes = x_dtype == LATTE_BF16 ? 0 : 1;
   const NxcWsLayout w = nxc_ws_layout(x, ldx, x_dtype, row_index != nullptr, n, dim, num_classes);
   const int64_t dim_pad = w.dim_pad;
   const bool direct_x = w.direct_x;
@@ -357,23 +386,25 @@ int nxc_tc_run(const void* x, int64_t ldx, int x_dtype, const int64_t* row_index
     const int64_t work = n * (dim_pad / 8);
     const int vec_ok = (ldx % 4) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
     nxc_split_planes_kernel<<<(unsigned)((work + 255) / 256), 256, 0, st>>>(
-        x, ldx, x_dtype, row_index, n, dim, dim_pad, x_planes, xp, vec_ok);
+        x, ldx, x_dtype, row_index, n, dim, dim_pad, x_planes, fp16_planes, xp, vec_ok);
   }
   {
     const int64_t work = num_classes * (dim_pad / 8);
     const int vec_ok = (ldp % 4) == 0 && (reinterpret_cast<uintptr_t>(protos) & 15) == 0;
     nxc_split_planes_kernel<<<(unsigned)((work + 255) / 256), 256, 0, st>>>(
-        protos, ldp, LATTE_F32, nullptr, num_classes, dim, dim_pad, 3, pp, vec_ok);
+        protos, ldp, LATTE_F32, nullptr, num_classes, dim, dim_pad, w.p_planes, fp16_planes, pp, vec_ok);
   }
   CUtensorMap tmx, tmpm;
-  if (direct_x) rc = nxc_make_map(&tmx, x, n, dim, ldx);
-  else rc = nxc_make_map(&tmx, xp, (int64_t)x_planes * n, dim_pad, dim_pad);
-  if (!rc) rc = nxc_make_map(&tmpm, pp, 3 * num_classes, dim_pad, dim_pad);
+  if (direct_x) rc = nxc_make_map(&tmx, x, n, dim, ldx, fp16_planes != 0);
+  else rc = nxc_make_map(&tmx, xp, (int64_t)x_planes * n, dim_pad, dim_pad, fp16_planes != 0);
+  if (!rc) rc = nxc_make_map(&tmpm, pp, (int64_t)w.p_planes * num_classes, dim_pad, dim_pad, fp16_planes != 0);
   if (!rc) {
     NxcTcParams p;
     p.n = n; p.num_classes = num_classes;
     p.kch = (int)(dim_pad / kBK);
     p.x_planes = x_planes;
+    p.p_planes = w.p_planes;
+    p.ab_fmt = fp16_planes ? 0 : 1;
     p.passes = (int)((num_classes + kCls - 1) / kCls);
     p.scale = scale;
     p.argmax_out = argmax_out; p.margin_out = margin_out; p.top1_out = top1_out;
