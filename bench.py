@@ -686,7 +686,7 @@ def weak_scaling_point(lb, rank, world, dev, steps, rows=WEAK_ROWS_PER_GPU):
     log_s = torch.tensor(math.log(SCALE), device=dev, requires_grad=True)
 
     def run(fn, k_steps):
-        for k in range(3):
+        for k in range(8):                 # every rotating set twice: workspaces, gradient buffers, clocks
             i, t = sets[k % 4]
             i.grad = None; t.grad = None; log_s.grad = None
             fn(i, t, log_s.exp()).backward()
@@ -967,7 +967,7 @@ def _run_ours(args):
         from latteclip_b200 import _lib as _l
         _l.clear_workspace_cache()
         torch.cuda.empty_cache()
-        weak_big = weak_scaling_point(lb, rank, world, dev, min(args.steps, 5), rows=N_GLOBAL)
+        weak_big = weak_scaling_point(lb, rank, world, dev, min(args.steps, 10), rows=N_GLOBAL)
         _l.clear_workspace_cache()
         torch.cuda.empty_cache()
     else:
