@@ -967,7 +967,11 @@ def _run_ours(args):
         from latteclip_b200 import _lib as _l
         _l.clear_workspace_cache()
         torch.cuda.empty_cache()
-        weak_big = weak_scaling_point(lb, rank, world, dev, min(args.steps, 10), rows=N_GLOBAL)
+        try:
+            weak_big = weak_scaling_point(lb, rank, world, dev, min(args.steps, 10), rows=N_GLOBAL)
+        except Exception as exc:           # an extra datum must not cost the line its headline numbers
+            weak_big = {"rows_per_gpu": N_GLOBAL, "global_batch": N_GLOBAL * world,
+                        "error": f"{type(exc).__name__}: {exc}"[:300]}
         _l.clear_workspace_cache()
         torch.cuda.empty_cache()
     else:
