@@ -6,12 +6,13 @@ so = os.path.join(ROOT, "latteclip_b200", "_C", "liblatte_b200.so")
 txt = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True).stdout
 funcs = re.split(r"\n\s*Function : ", txt)
 keys = ["UTCHMMA", "UTCBAR", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UTMAREDG", "UTMAPF", "SYNCS", "FFMA2", "FADD2",
-        "FMUL2", "MUFU.EX2", "REDG", "MEMBAR", "ELECT", "UCGABAR"]
-show = ("UTCHMMA", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UTMAREDG", "FFMA2", "UTCBAR")
+        "FMUL2", "MUFU.EX2", "REDG", "MEMBAR", "ELECT", "UCGABAR", "UBLKCP", "NANOSLEEP.SYNCS"]
+show = ("UTCHMMA", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UTMAREDG", "FFMA2", "UTCBAR", "UBLKCP", "NANOSLEEP.SYNCS")
 out = ["# SASS evidence, round 2", "",
        "`cuobjdump -sass latteclip_b200/_C/liblatte_b200.so` (sm_100a, the library the tests and bench load), per kernel:",
        "instruction count, counts of the tcgen05 (`UTCHMMA`, `UTCBAR`), TMEM (`LDTM`, `STTM`), TMA (`UTMALDG`, `UTMASTG`,",
-       "`UTMAREDG`) and packed-fp32 (`FFMA2`, `FADD2`, `FMUL2`) mnemonics, and the first occurrence of the main ones.",
+       "`UTMAREDG`, 1-D bulk copies `UBLKCP`) and packed-fp32 (`FFMA2`, `FADD2`, `FMUL2`) mnemonics, the suspended mbarrier",
+       "wait (`NANOSLEEP.SYNCS`, DESIGN 3.10), and the first occurrence of the main ones.",
        "Regenerate with `python tools/sass_summary.py`.", ""]
 for f in funcs[1:]:
     name = f.split("\n", 1)[0].strip()
