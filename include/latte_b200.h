@@ -369,7 +369,7 @@ int latte_normalize_rows(const float* in, int64_t ld_in, float* out, int64_t ld_
  * Any of the three outputs may be NULL.  x is [n, dim] in x_dtype; protos is fp32 [C, dim].
  * If row_index is not NULL, row i of x is x[row_index[i], :] (class-text gather,
  * train.py:420-438).  workspace: caller-owned scratch of latte_nxc_workspace_bytes()
- * bytes (bf16 operand planes of the tensor-core path; 0 bytes below 128 rows).
+ * bytes (16-bit operand planes of the tensor-core path; 0 bytes below 128 rows).
  */
 int latte_nxc_workspace_bytes(int x_dtype, int gathered, int64_t n, int64_t dim,
                               int64_t num_classes, size_t* bytes);

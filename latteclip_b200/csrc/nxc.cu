@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(kT) nxc_kernel(NxcArgs a) {
 }  // namespace latte
 
 namespace latte {
-// tcgen05 path with split-bf16 operands (nxc_tc.cu); LATTE_ERR_UNSUPPORTED -> use the SIMT tiles
+// tcgen05 path with operands split into 16-bit planes (nxc_tc.cu); LATTE_ERR_UNSUPPORTED -> use the SIMT tiles
 int nxc_tc_run(const void* x, int64_t ldx, int x_dtype, const int64_t* row_index, int64_t n,
                int64_t dim, const float* protos, int64_t ldp, int64_t num_classes, float scale,
                int64_t* argmax_out, float* margin_out, float* top1_out, int k, int64_t* topk_idx,

@@ -3,19 +3,25 @@
 // Per step the reference runs five distinct N x C products (train.py:410-411 pseudo-label argmax,
 // compute_text_weights train.py:292-303 on the image-description, group-description and class-name
 // text features -- SURVEY 2c K8/K9).  latte_nxc_multi runs them as one persistent launch:
-//   * prototypes are split ONCE per matrix into three bf16 planes p = p0 + p1 + p2
-//     (latte_nxc_split_prototypes, optionally fused with the row normalisation of train.py:384-389);
-//   * feature rows are streamed exactly once: TMA loads the raw tile ([128 rows x 64 features],
-//     fp32 or fp16) into shared memory, eight converter warps split it into bf16 planes in place
-//     (x = x0 + x1 + x2, exact for fp32) in the 128B-swizzled operand layout, and tcgen05.mma
-//     accumulates every plane pair (a, b) with a + b <= 2 in fp32 (TMEM); bf16 features skip the
-//     conversion and are the x0 plane as they are;
+//   * prototypes are split ONCE per matrix into 16-bit operand planes (latte_nxc_split_prototypes,
+//     optionally fused with the row normalisation of train.py:384-389): three bf16 planes
+//     p = p0 + p1 + p2 for bf16 rows, two fp16 planes p = h0 + 2^-11 h1 for fp16 / fp32 rows;
+//   * feature rows are streamed exactly once.  16-bit rows are MMA operands as they are; fp32 rows
+//     land raw in shared memory ([128 rows x 64 features]) and sixteen converter warps split them
+//     into two fp16 planes in place (x = h0 + 2^-11 h1: the residual after two planes is <= 2^-24 |x|,
+//     fp32's own rounding; the low plane is stored times 2^11 to stay clear of fp16's subnormals) in
+//     the 128B-swizzled operand layout; tcgen05.mma accumulates the plane pairs (0,0), (0,1), (1,0)
+//     in fp32 (TMEM): 3 MMAs per 16 features for fp32 and bf16 rows, 2 for fp16 rows.  The first version
+//     of this kernel used three bf16 planes for every input (6 / 5 / 3 MMAs) and was bound by the
+//     NUMBER of small MMAs (an M128 x N48 x K16 MMA costs ~4x its FLOP time): 0.53 of HBM for every
+//     input type; now 0.65 / 0.62 / 0.57 (fp32 / fp16 / bf16 rows);
 //   * four accumulators per tile (the large term x0.p0 spread over thirds of the feature axis + one
 //     for the small terms, summed in round-to-nearest fp32 by the epilogue) make the result as
 //     accurate as an fp32 FMA loop although the tensor core truncates its accumulator per MMA;
-//   * TMEM holds two sets of accumulators, so the argmax / top-2 epilogue of row block b overlaps
-//     the loads and MMAs of block b + 1; CTAs are persistent (grid = SM count) and walk the row
-//     blocks of all jobs round-robin.
+//   * TMEM holds two sets of accumulators, so the argmax / top-2 epilogue of tile t overlaps the loads
+//     and MMAs of tile t + 1; CTAs are persistent (grid = SM count) and the 32-row groups of all jobs
+//     are dealt to them in equal contiguous ranges (one 128-row TMA box per full tile, 32-row boxes
+//     for the partial tiles at range ends, one box for the packed prototype planes of a chunk).
 // Algorithmic bytes: N * D * sizeof(x) + outputs; the [N, C] logits never exist in memory.
 #include "latte_common.cuh"
 #include "tc_ptx.cuh"

@@ -18,7 +18,7 @@
 // accumulators (thirds of the feature axis), the small terms go to a fourth, and the epilogue
 // adds the four in round-to-nearest fp32: the result is as accurate as an fp32 FMA loop.
 //
-//   nxc_split_planes_kernel : (optionally gathered) rows -> bf16 planes [P][rows][dim_pad]
+//   nxc_split_planes_kernel : (optionally gathered) rows -> 16-bit planes [P][rows][dim_pad]
 //   nxc_tc_kernel           : 128 rows per CTA, class tiles of <= 128, K chunks of 64 through a
 //                             2-stage TMA ring, accumulators double-buffered in TMEM; four
 //                             epilogue warps keep the running argmax / top-2 / top-k per row.
@@ -42,7 +42,7 @@ constexpr int kNxcThreads = 192;           // warp 0 TMA, warp 1 MMA + TMEM allo
 constexpr int kNxcSmem = kStages * kStageBytes + 1024;
 constexpr int kMaxTopK = 16;
 
-// ---- split into bf16 planes ---------------------------------------------------------------
+// ---- split into 16-bit planes -------------------------------------------------------------
 __device__ __forceinline__ float load_as_float(const void* base, int64_t idx, int dtype) {
   if (dtype == LATTE_F32) return __ldg(reinterpret_cast<const float*>(base) + idx);
   if (dtype == LATTE_BF16)
@@ -355,7 +355,7 @@ NxcWsLayout nxc_ws_layout(const void* x, int64_t ldx, int x_dtype, bool gathered
 }
 }  // namespace
 
-// Scratch of one N x C call: bf16 planes of the prototypes and (unless bf16 rows are read in place)
+// Scratch of one N x C call: 16-bit planes of the prototypes and (unless 16-bit rows are read in place)
 // of x.  Upper bound over pointer alignments of x.
 size_t nxc_tc_workspace_bytes(int x_dtype, bool gathered, int64_t n, int64_t dim, int64_t num_classes) {
   // an unaligned bf16 x also needs its plane: query with direct_x = false

@@ -53,7 +53,7 @@ def unstack_bank(bank: torch.Tensor, memory_bank, class_names: Iterable[str], to
 
 
 # ------------------------------------------------------------------------------ kernels
-# bf16 operand planes of the epoch-start prototype snapshot (train.py:347-350): split once per
+# 16-bit operand planes of the epoch-start prototype snapshot (train.py:347-350): split once per
 # snapshot tensor, not once per call.  The planes ride on the tensor object itself (with its
 # in-place version counter), so they die with it and a new tensor at a recycled address never
 # sees stale planes.
