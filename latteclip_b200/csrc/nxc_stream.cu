@@ -67,7 +67,6 @@ struct StreamJob {
   int x_planes;              // operand planes of a feature row: 1 (bf16, fp16: the row itself), 2 (fp32)
   int p_planes;              // prototype planes: 3 bf16 planes (bf16 rows) or 2 fp16 planes (fp16 / fp32 rows)
   int ab_fmt;                // MMA operand format: 1 bf16, 0 fp16
-  int raw_f32;               // raw tile is fp32 (two boxes per chunk, converted) or 16-bit (used as it is)
   float scale;
   int64_t* argmax_out; float* margin_out; float* top1_out;
 };
@@ -498,7 +497,6 @@ extern "C" int latte_nxc_multi(const latte_nxc_job_t* jobs, int njobs, void* str
     jb.x_planes = in.x_dtype == LATTE_F32 ? kCvtXPlanes : 1;
     jb.p_planes = in.x_dtype == LATTE_BF16 ? 3 : 2;
     jb.ab_fmt = in.x_dtype == LATTE_BF16 ? 1 : 0;
-    jb.raw_f32 = in.x_dtype == LATTE_F32;
     jb.scale = in.scale;
     jb.argmax_out = in.argmax_out; jb.margin_out = in.margin_out; jb.top1_out = in.top1_out;
     (in.x_dtype == LATTE_F32 ? convert : direct) = true;
